@@ -1,0 +1,256 @@
+/*
+ * cc_b200.h -- C ABI of the B200-native continuous-clustering hot path.
+ *
+ * One handle == one sensor stream == one `continuous_clustering::ContinuousClustering` object of
+ * the reference (include/continuous_clustering/clustering/continuous_clustering.hpp:197-290).
+ * The reference has no FFI; the only caller of this ABI is the header-compatible C++ facade in
+ * facade/ (and, for tests/bench, Python ctypes).  Each entry point cites the reference interface it
+ * replaces ("hpp" = continuous_clustering.hpp, "cpp" = src/clustering/continuous_clustering.cpp).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++/torch types; every function returns a cc_status_t (0 = ok) unless
+ *    stated otherwise; cc_last_error() gives the message the facade re-throws as std::runtime_error.
+ *  - a handle may be used from one host thread at a time; handles are independent (one per GPU/stream).
+ *  - poses are 3x4 row-major doubles [R|t] (odom_from_sensor), 12 per firing.
+ *  - global column index ("gcol") = the reference's global_column_index (cpp:152-153);
+ *    ring cell = (gcol % (10*num_columns)) * num_rows + row   (cpp:17, 178-181).
+ *  - all compute runs in CUDA kernels on the handle's device; there is no CPU fallback.
+ */
+#ifndef CC_B200_H
+#define CC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CC_API
+#else
+#define CC_API __attribute__((visibility("default")))
+#endif
+
+typedef struct cc_handle cc_handle_t;
+
+typedef enum cc_status
+{
+    CC_OK = 0,
+    CC_ERR_INVALID_ARGUMENT = 1,
+    CC_ERR_CUDA = 2,
+    CC_ERR_ROW_COUNT_CHANGED = 3,   /* cpp:90-91   "The number of points in a firing has changed..."      */
+    CC_ERR_NO_ROBOT_TRANSFORM = 4,  /* cpp:298-299 "Transform robot frame from sensor frame was not set yet!" */
+    CC_ERR_COLUMN_NOT_CLEARED = 5,  /* cpp:337-344 ring buffer overrun                                     */
+    CC_ERR_RING_START_DECREASED = 6,/* cpp:1072-1075                                                      */
+    CC_ERR_NOT_RESET = 7,           /* push before cc_reset()                                              */
+    CC_ERR_BATCH_TOO_LARGE = 8,     /* more firings/columns in one push than the handle was sized for      */
+    CC_ERR_INTERNAL = 9
+} cc_status_t;
+
+/* Layout-identical to continuous_clustering::RawPoint (point_types.hpp:10-19), 48 bytes, so the facade
+ * can hand `firing->points.data()` straight to cc_push_firings. */
+typedef struct cc_raw_point
+{
+    float x, y, z;
+    uint32_t pad0_;
+    uint64_t firing_index;
+    uint8_t intensity;
+    uint8_t pad1_[7];
+    uint64_t stamp;
+    uint64_t globally_unique_point_index;
+} cc_raw_point_t;
+
+/* Plain-C mirror of continuous_clustering::Configuration (hpp:24-87); same names, same defaults
+ * (cc_config_default). Booleans are int32. */
+typedef struct cc_config
+{
+    /* GeneralConfiguration hpp:24-27. Accepted for API parity; the device pipeline always has the
+     * deterministic ordering of the reference's single-threaded mode. */
+    int32_t is_single_threaded;
+    /* ContinuousRangeImageConfiguration hpp:29-34 */
+    int32_t sensor_is_clockwise;
+    int32_t num_columns;
+    int32_t supplement_inclination_angle_for_nan_cells;
+    /* ContinuousGroundSegmentationConfiguration hpp:36-66 */
+    float max_slope;
+    float first_ring_as_ground_max_allowed_z_diff;
+    float first_ring_as_ground_min_allowed_z_diff;
+    float last_ground_point_slope_higher_than;
+    float last_ground_point_distance_smaller_than;
+    float ground_because_close_to_last_certain_ground_max_z_diff;
+    float ground_because_close_to_last_certain_ground_max_dist_diff;
+    float obstacle_because_next_certain_obstacle_max_dist_diff;
+    int32_t use_terrain;
+    float terrain_max_allowed_z_diff;
+    float height_ref_to_maximum_;
+    float height_ref_to_ground_;
+    float length_ref_to_front_end_;
+    float length_ref_to_rear_end_;
+    float width_ref_to_left_mirror_;
+    float width_ref_to_right_mirror_;
+    int32_t fog_filtering_enabled;
+    int32_t fog_filtering_intensity_below; /* uint8 in the reference */
+    float fog_filtering_distance_below;
+    float fog_filtering_inclination_above;
+    /* ContinuousClusteringConfiguration hpp:68-79 */
+    float max_distance;
+    int32_t max_steps_in_row;
+    int32_t max_steps_in_column;
+    int32_t stop_after_association_enabled;
+    int32_t stop_after_association_min_steps;
+    int32_t ignore_points_in_chessboard_pattern;
+    int32_t ignore_points_with_too_big_inclination_angle_diff;
+    int32_t use_last_point_for_cluster_stamp;
+    int32_t cluster_point_trees_every_nth_column;
+} cc_config_t;
+
+/* One finished-column callback of the reference: finished_column_callback_(from, to, ground_only)
+ * (cpp:618-620 with ground_only=1; cpp:1087-1089 with ground_only=0; `to < from` is an empty range and is
+ * reported exactly as the reference reports it). Events come in the order the reference's single-threaded
+ * mode invokes them. `n_clusters_before` = how many entries of the batch's cluster list precede this
+ * event in callback order (clusters finished by column c are delivered before c's ground_only=0 event). */
+typedef struct cc_column_event
+{
+    int64_t from_gcol;
+    int64_t to_gcol;
+    int32_t ground_points_only;
+    int32_t n_clusters_before;
+} cc_column_event_t;
+
+/* One finished cluster with more than 5 points (cpp:936-940). Points are cell references into the ring;
+ * `stamp` is what the reference passes to finished_cluster_callback_ (cpp:1025-1028); the reference only
+ * invokes that callback when num_points > 20 (cpp:1023). */
+typedef struct cc_cluster
+{
+    uint64_t id;            /* Point::id of every member, cpp:939, 1005 (ids are a permutation of the reference's) */
+    uint64_t stamp;         /* cpp:1025-1028 */
+    uint64_t min_stamp;
+    uint64_t max_stamp;
+    int64_t finished_at_gcol; /* column whose tree-combination pass finished the cluster (cpp:837) */
+    int64_t min_gcol;
+    int64_t max_gcol;
+    uint32_t num_points;
+    uint32_t point_offset;  /* first entry in the batch's cluster-point list */
+} cc_cluster_t;
+
+/* Member of a finished cluster: which ring cell. */
+typedef struct cc_cluster_point
+{
+    int64_t gcol;
+    int32_t row;
+    int32_t pad_;
+} cc_cluster_point_t;
+
+/* Summary of the last cc_push_firings call. */
+typedef struct cc_batch_info
+{
+    int64_t ground_from_gcol; /* columns [from, to) went through ground segmentation + association in this batch */
+    int64_t ground_to_gcol;
+    int64_t first_unpublished_gcol;  /* sc_first_unpublished_global_column_index after the batch (hpp:270) */
+    int64_t ring_start_gcol;         /* ring_buffer_start_global_column_index (hpp:250) */
+    int64_t ring_end_gcol;           /* ring_buffer_end_global_column_index (hpp:251) */
+    int64_t cleared_from_gcol;       /* columns [from, to) were recycled by clearColumns (cpp:1091) in this batch */
+    int64_t cleared_to_gcol;
+    int32_t n_events;
+    int32_t n_clusters;
+    int32_t n_cluster_points;
+    int32_t reset_required;          /* cpp:83-86 */
+    int32_t used_exact_path;         /* 1 if the batch needed the column-sequential exact kernels */
+    int32_t gpu_launches;            /* kernels launched for this batch */
+    float device_ms;                 /* CUDA-event time of the batch's kernels on the handle's stream */
+    int32_t pad_;
+} cc_batch_info_t;
+
+/* Field selector + destination pointers for cc_read_columns. Each non-NULL pointer receives
+ * n_cols*num_rows values in the reference's column-major cell order (column-by-column, row 0 = top
+ * laser). Cleared / never-written cells hold the reference's cleared values (cpp:1110-1142). */
+typedef struct cc_column_fields
+{
+    float* xyz;                        /* 3 floats per cell, Point::xyz                        */
+    float* distance;                   /* Point::distance                                      */
+    float* azimuth_angle;              /* Point::azimuth_angle                                 */
+    float* inclination_angle;          /* Point::inclination_angle (incl. NaN-cell supplement) */
+    double* continuous_azimuth_angle;  /* Point::continuous_azimuth_angle                      */
+    int64_t* global_column_index;      /* Point::global_column_index                           */
+    uint64_t* stamp;                   /* Point::stamp                                         */
+    uint64_t* globally_unique_point_index;
+    uint64_t* firing_index;
+    uint8_t* intensity;
+    uint8_t* ground_point_label;       /* Point::ground_point_label                            */
+    uint8_t* debug_ground_point_label; /* Point::debug_ground_point_label                      */
+    uint8_t* is_ignored;               /* Point::is_ignored                                    */
+    uint64_t* id;                      /* Point::id (0 = not part of a published cluster)      */
+    int64_t* tree_root_gcol;           /* global column of Point::tree_root_ (-1 = none)       */
+    int32_t* tree_root_row;            /* Point::tree_root_.row_index                          */
+} cc_column_fields_t;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+
+/* ContinuousClustering::ContinuousClustering() hpp:201. `max_firings_per_push` sizes the staging
+ * buffers (0 = default 4096). */
+CC_API cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t** out);
+CC_API void cc_destroy(cc_handle_t* h);
+CC_API const char* cc_last_error(const cc_handle_t* h);
+CC_API const char* cc_version(void);
+
+/* Defaults of hpp:24-87. */
+CC_API void cc_config_default(cc_config_t* cfg);
+/* ContinuousClustering::setConfiguration hpp:206, cpp:66-81 (sets reset_required when
+ * is_single_threaded / sensor_is_clockwise / num_columns change). */
+CC_API cc_status_t cc_set_config(cc_handle_t* h, const cc_config_t* cfg);
+/* ContinuousClustering::reset hpp:205, cpp:11-64. */
+CC_API cc_status_t cc_reset(cc_handle_t* h, int num_rows);
+/* ContinuousClustering::resetRequired hpp:207, cpp:83-86. Returns 0/1. */
+CC_API int cc_reset_required(const cc_handle_t* h);
+/* setTransformRobotFrameFromSensorFrame / hasTransformRobotFrameFromSensorFrame hpp:213-214, cpp:626-636. */
+CC_API cc_status_t cc_set_robot_from_sensor(cc_handle_t* h, const double robot_from_sensor[12]);
+CC_API int cc_has_robot_from_sensor(const cc_handle_t* h);
+
+/* ---- the hot path ------------------------------------------------------------------------------- */
+
+/* ContinuousClustering::addFiring hpp:210, cpp:88-93, for `n_firings` consecutive firings: runs
+ * insertFiringIntoRangeImage (cpp:105-292), performGroundPointSegmentationForColumn (cpp:294-624),
+ * associatePointsInColumn (cpp:773-835), findFinishedTreesAndAssignSameId (cpp:837-974), the id /
+ * bookkeeping half of collectPointsForCusterAndPublish (cpp:976-1092) and clearColumns (cpp:1094-1145)
+ * for every column the firings complete, on the device. `points` = n_firings*rows_per_firing host records,
+ * `poses` = n_firings*12 host doubles. Returns after the results are on the host.
+ * rows_per_firing != num_rows -> CC_ERR_ROW_COUNT_CHANGED (cpp:90-91). */
+CC_API cc_status_t cc_push_firings(cc_handle_t* h, int n_firings, int rows_per_firing,
+                                   const cc_raw_point_t* points, const double* poses);
+
+/* Same, with inputs already resident in device memory (device pointers on the handle's device). */
+CC_API cc_status_t cc_push_firings_device(cc_handle_t* h, int n_firings, int rows_per_firing,
+                                          const cc_raw_point_t* d_points, const double* d_poses);
+
+/* Results of the last push. */
+CC_API cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out);
+/* Copies min(cap, n) entries; returns the number copied through *n_out. */
+CC_API cc_status_t cc_get_column_events(const cc_handle_t* h, cc_column_event_t* out, int cap, int* n_out);
+CC_API cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int cap, int* n_out);
+CC_API cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out, int cap, int* n_out);
+
+/* Reads cells of columns [from_gcol, to_gcol] (inclusive, like the callback ranges) from the device
+ * ring -- what a caller reads from `range_image_` inside a column callback (ros_utils.cpp:56-63,
+ * kitti_demo.cpp:183-216). Only valid for columns still inside the ring. */
+CC_API cc_status_t cc_read_columns(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol,
+                                   const cc_column_fields_t* fields);
+
+/* Public data members of the reference object (hpp:244-251). */
+CC_API int cc_num_rows(const cc_handle_t* h);
+CC_API int cc_num_columns(const cc_handle_t* h);
+CC_API int cc_ring_buffer_max_columns(const cc_handle_t* h);
+
+/* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with CUDA events. */
+CC_API void* cc_stream(const cc_handle_t* h);
+/* Total kernels launched by this handle so far. */
+CC_API uint64_t cc_total_launches(const cc_handle_t* h);
+
+/* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
+/* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
+ * asinf(a[i]) (op 1). */
+CC_API cc_status_t cc_selftest_math(int device_ordinal, int op, int n, const float* a, const float* b, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CC_B200_H */
