@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's `continuous_clustering::ContinuousClustering` class
+(include/continuous_clustering/clustering/continuous_clustering.hpp:197-290) on top of the CUDA C ABI.
+
+Same method names, argument meaning and error behaviour as the reference class; every stage of the pipeline runs
+in CUDA kernels on one B200 (continuous_clustering_b200/csrc). Firings are handed to the device in batches
+(`addFirings`, or `addFiring` + `flush`); callbacks are delivered in the order of the reference's deterministic
+single-threaded mode (thread_pool.hpp:31-35).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+from . import _lib
+from .synth import RAW_POINT_DTYPE
+
+
+@dataclasses.dataclass
+class GeneralConfiguration:  # hpp:24-27
+    is_single_threaded: bool = False
+
+
+@dataclasses.dataclass
+class ContinuousRangeImageConfiguration:  # hpp:29-34
+    sensor_is_clockwise: bool = True
+    num_columns: int = 1700
+    supplement_inclination_angle_for_nan_cells: bool = True
+
+
+@dataclasses.dataclass
+class ContinuousGroundSegmentationConfiguration:  # hpp:36-66
+    max_slope: float = 0.2
+    first_ring_as_ground_max_allowed_z_diff: float = 0.4
+    first_ring_as_ground_min_allowed_z_diff: float = -0.4
+    last_ground_point_slope_higher_than: float = -0.1
+    last_ground_point_distance_smaller_than: float = 5.0
+    ground_because_close_to_last_certain_ground_max_z_diff: float = 0.4
+    ground_because_close_to_last_certain_ground_max_dist_diff: float = 2.0
+    obstacle_because_next_certain_obstacle_max_dist_diff: float = 0.3
+    use_terrain: bool = False
+    terrain_max_allowed_z_diff: float = 0.4
+    height_ref_to_maximum_: float = 0.0
+    height_ref_to_ground_: float = 0.0
+    length_ref_to_front_end_: float = 0.0
+    length_ref_to_rear_end_: float = 0.0
+    width_ref_to_left_mirror_: float = 0.0
+    width_ref_to_right_mirror_: float = 0.0
+    fog_filtering_enabled: bool = False
+    fog_filtering_intensity_below: int = 2
+    fog_filtering_distance_below: float = 18.0
+    fog_filtering_inclination_above: float = -0.06
+
+
+@dataclasses.dataclass
+class ContinuousClusteringConfiguration:  # hpp:68-79
+    max_distance: float = 0.7
+    max_steps_in_row: int = 20
+    max_steps_in_column: int = 20
+    stop_after_association_enabled: bool = True
+    stop_after_association_min_steps: int = 1
+    ignore_points_in_chessboard_pattern: bool = True
+    ignore_points_with_too_big_inclination_angle_diff: bool = True
+    use_last_point_for_cluster_stamp: bool = False
+    cluster_point_trees_every_nth_column: int = 1
+
+
+@dataclasses.dataclass
+class Configuration:  # hpp:81-87
+    general: GeneralConfiguration = dataclasses.field(default_factory=GeneralConfiguration)
+    range_image: ContinuousRangeImageConfiguration = dataclasses.field(default_factory=ContinuousRangeImageConfiguration)
+    ground_segmentation: ContinuousGroundSegmentationConfiguration = dataclasses.field(
+        default_factory=ContinuousGroundSegmentationConfiguration)
+    clustering: ContinuousClusteringConfiguration = dataclasses.field(default_factory=ContinuousClusteringConfiguration)
+
+    def to_c(self) -> _lib.CcConfig:
+        c = _lib.CcConfig()
+        for group in (self.general, self.range_image, self.ground_segmentation, self.clustering):
+            for f in dataclasses.fields(group):
+                v = getattr(group, f.name)
+                setattr(c, f.name, int(v) if isinstance(v, (bool, np.bool_)) else v)
+        return c
+
+    @staticmethod
+    def from_c(c) -> "Configuration":
+        cfg = Configuration()
+        for group in (cfg.general, cfg.range_image, cfg.ground_segmentation, cfg.clustering):
+            for f in dataclasses.fields(group):
+                v = getattr(c, f.name)
+                setattr(group, f.name, bool(v) if f.type in ("bool", bool) else v)
+        return cfg
+
+
+class ClusteringError(RuntimeError):
+    """Raised where the reference throws std::runtime_error (cpp:90-91, 298-299, 337-344, 1072-1075)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{_lib.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+@dataclasses.dataclass
+class BatchResult:
+    info: _lib.CcBatchInfo
+    events: np.ndarray  # EVENT_DTYPE, callback order
+    clusters: np.ndarray  # CLUSTER_DTYPE, finish order (> 5 points; the cluster callback needs > 20)
+    cluster_points: np.ndarray  # CLUSTER_POINT_DTYPE
+
+
+class ContinuousClustering:
+    """One sensor stream on one GPU. Mirrors hpp:197-251 (public methods and data members)."""
+
+    def __init__(self, device: int = 0, max_firings_per_push: int = 4096, batch_firings: int = 256, _library=None):
+        self._L = _library if _library is not None else _lib.load_library()
+        h = C.c_void_p()
+        rc = self._L.cc_create(device, max_firings_per_push, C.byref(h))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_create failed: a CUDA device (B200, sm_100a) is required")
+        self._h = h
+        self.device = device
+        self.max_firings_per_push = max_firings_per_push
+        self.batch_firings = min(batch_firings, max_firings_per_push)
+        self._pending_pts: list[np.ndarray] = []
+        self._pending_poses: list[np.ndarray] = []
+        self._column_cb = None
+        self._cluster_cb = None
+        self.last: BatchResult | None = None
+
+    # ---- lifecycle ----
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise ClusteringError(rc, self._L.cc_last_error(self._h).decode(errors="replace"))
+
+    def setConfiguration(self, config):  # hpp:206
+        c = config.to_c() if isinstance(config, Configuration) else config
+        self._keep_cfg = c
+        self._check(self._L.cc_set_config(self._h, C.addressof(c)))
+
+    def reset(self, num_rows: int):  # hpp:205
+        self._pending_pts.clear()
+        self._pending_poses.clear()
+        self._check(self._L.cc_reset(self._h, int(num_rows)))
+
+    def resetRequired(self) -> bool:  # hpp:207
+        return bool(self._L.cc_reset_required(self._h))
+
+    def setTransformRobotFrameFromSensorFrame(self, tf):  # hpp:213
+        m = np.ascontiguousarray(np.asarray(tf, dtype=np.float64).reshape(-1)[:12])
+        self._check(self._L.cc_set_robot_from_sensor(self._h, m.ctypes.data))
+
+    def hasTransformRobotFrameFromSensorFrame(self) -> bool:  # hpp:214
+        return bool(self._L.cc_has_robot_from_sensor(self._h))
+
+    def setFinishedColumnCallback(self, cb):  # hpp:217: cb(from_gcol, to_gcol, ground_points_only)
+        self._column_cb = cb
+
+    def setFinishedClusterCallback(self, cb):  # hpp:218: cb(points, stamp)
+        self._cluster_cb = cb
+
+    def recordJobQueueWorkload(self, num_jobs_sensor_input: int):  # hpp:221: there are no job queues on the device
+        return None
+
+    # public data members of the reference object (hpp:244-251)
+    @property
+    def num_rows_(self) -> int:
+        return self._L.cc_num_rows(self._h)
+
+    @property
+    def num_columns_(self) -> int:
+        return self._L.cc_num_columns(self._h)
+
+    @property
+    def ring_buffer_max_columns(self) -> int:
+        return self._L.cc_ring_buffer_max_columns(self._h)
+
+    @property
+    def ring_buffer_start_global_column_index(self) -> int:
+        return self.last.info.ring_start_gcol if self.last else -1
+
+    @property
+    def ring_buffer_end_global_column_index(self) -> int:
+        return self.last.info.ring_end_gcol if self.last else -1
+
+    # ---- the hot path ----
+    def addFiring(self, firing, odom_from_sensor):  # hpp:210
+        """One firing (array of num_rows RawPoints) + 3x4 pose. Buffered; pushed every `batch_firings` firings."""
+        pts = np.ascontiguousarray(firing, dtype=RAW_POINT_DTYPE).reshape(-1)
+        if pts.shape[0] != self.num_rows_:
+            raise ClusteringError(3, "The number of points in a firing has changed. This is probably a bug!")
+        self._pending_pts.append(pts)
+        self._pending_poses.append(np.asarray(odom_from_sensor, dtype=np.float64).reshape(-1)[:12])
+        if len(self._pending_pts) >= self.batch_firings:
+            self.flush()
+
+    def flush(self):
+        if not self._pending_pts:
+            return None
+        pts = np.stack(self._pending_pts)
+        poses = np.stack(self._pending_poses)
+        self._pending_pts.clear()
+        self._pending_poses.clear()
+        return self.addFirings(pts, poses)
+
+    def addFirings(self, points: np.ndarray, poses: np.ndarray) -> BatchResult:
+        """A batch of consecutive firings: points[n, num_rows] (RAW_POINT_DTYPE), poses[n, 12]."""
+        points = np.ascontiguousarray(points, dtype=RAW_POINT_DTYPE)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        n, rows = points.shape
+        out = None
+        for a in range(0, max(n, 1), self.max_firings_per_push):
+            b = min(n, a + self.max_firings_per_push)
+            self._check(self._L.cc_push_firings(self._h, b - a, rows, points[a:b].ctypes.data, poses[a:b].ctypes.data))
+            out = self._collect()
+            self._dispatch(out)
+        return out
+
+    def addFiringsDevice(self, d_points: int, d_poses: int, n: int, rows: int) -> BatchResult:
+        """Same with device pointers (cc_push_firings_device): inputs already resident in HBM."""
+        self._check(self._L.cc_push_firings_device(self._h, n, rows, d_points, d_poses))
+        out = self._collect()
+        self._dispatch(out)
+        return out
+
+    def _collect(self) -> BatchResult:
+        info = _lib.CcBatchInfo()
+        self._check(self._L.cc_get_batch_info(self._h, C.byref(info)))
+        ev = np.zeros(info.n_events, dtype=_lib.EVENT_DTYPE)
+        cl = np.zeros(info.n_clusters, dtype=_lib.CLUSTER_DTYPE)
+        cp = np.zeros(info.n_cluster_points, dtype=_lib.CLUSTER_POINT_DTYPE)
+        n = C.c_int(0)
+        if info.n_events:
+            self._check(self._L.cc_get_column_events(self._h, ev.ctypes.data, info.n_events, C.byref(n)))
+        if info.n_clusters:
+            self._check(self._L.cc_get_clusters(self._h, cl.ctypes.data, info.n_clusters, C.byref(n)))
+        if info.n_cluster_points:
+            self._check(self._L.cc_get_cluster_points(self._h, cp.ctypes.data, info.n_cluster_points, C.byref(n)))
+        self.last = BatchResult(info, ev, cl, cp)
+        return self.last
+
+    def _dispatch(self, res: BatchResult):
+        if self._column_cb is None and self._cluster_cb is None:
+            return
+        cells = None
+        if self._cluster_cb is not None and len(res.clusters):
+            big = res.clusters[res.clusters["num_points"] > 20]  # cpp:1023
+            if len(big):
+                lo, hi = int(big["min_gcol"].min()), int(big["max_gcol"].max())
+                cells = (lo, self.read_columns(lo, hi))
+        nxt = 0
+        for e in res.events:
+            while nxt < int(e["n_clusters_before"]):
+                c = res.clusters[nxt]
+                nxt += 1
+                if self._cluster_cb is not None and c["num_points"] > 20:
+                    p = res.cluster_points[int(c["point_offset"]) : int(c["point_offset"]) + int(c["num_points"])]
+                    pts = cells[1][p["gcol"] - cells[0], p["row"]]
+                    self._cluster_cb(pts, int(c["stamp"]))
+            if self._column_cb is not None:
+                self._column_cb(int(e["from_gcol"]), int(e["to_gcol"]), bool(e["ground_points_only"]))
+
+    def read_columns(self, from_gcol: int, to_gcol: int, fields=None) -> np.ndarray:
+        """Cells of columns [from, to] (inclusive) as a structured array [n_cols, num_rows]: what a caller of the
+        reference reads from `range_image_` inside a column callback (ros_utils.cpp:56-63)."""
+        names = list(fields) if fields is not None else list(_lib.COLUMN_FIELD_DTYPES)
+        ncols = max(0, to_gcol - from_gcol + 1)
+        rows = self.num_rows_
+        dt = np.dtype([(n, _lib.COLUMN_FIELD_DTYPES[n][0], (3,)) if _lib.COLUMN_FIELD_DTYPES[n][1] == 3
+                       else (n, _lib.COLUMN_FIELD_DTYPES[n][0]) for n in names])
+        out = np.zeros((ncols, rows), dtype=dt)
+        if ncols == 0:
+            return out
+        bufs = {n: np.zeros((ncols, rows) + ((3,) if _lib.COLUMN_FIELD_DTYPES[n][1] == 3 else ()),
+                            dtype=_lib.COLUMN_FIELD_DTYPES[n][0]) for n in names}
+        f = _lib.CcColumnFields()
+        for n in names:
+            setattr(f, n, bufs[n].ctypes.data)
+        self._check(self._L.cc_read_columns(self._h, from_gcol, to_gcol, C.byref(f)))
+        for n in names:
+            out[n] = bufs[n]
+        return out
+
+    @property
+    def total_launches(self) -> int:
+        return int(self._L.cc_total_launches(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.cc_stream(self._h) or 0)

@@ -1,0 +1,987 @@
+// cc_api.cu -- host side of the C ABI declared in include/cc_b200.h: owns the device memory of one sensor
+// stream, stages firings, launches the kernels of cc_kernels.cuh on the handle's stream and brings the results
+// of a push back to the host. There is no CPU implementation of the path in this library.
+#include "../../include/cc_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cc_kernels.cuh"
+
+namespace
+{
+
+struct Alloc
+{
+    void** slot;
+};
+
+} // namespace
+
+struct cc_handle
+{
+    int device{0};
+    cudaStream_t stream{nullptr};
+    cudaEvent_t ev0{nullptr}, ev1{nullptr};
+    std::string error;
+    cc_config_t config{};
+    bool config_set{false};
+    bool is_reset{false};
+    bool reset_required_cfg{false}; // set by cc_set_config (cpp:69-74)
+    bool has_tf{false};
+    double robot_from_sensor[12]{};
+    int R{-1}, N{0}, ringcols{0};
+    float width{0.f};
+    int max_firings{4096};
+    int maxcols{0};
+    int gap_rows{-1};
+    CcDevPtrs d{};
+    unsigned int* d_s_parent{nullptr};
+    unsigned char* d_raw{nullptr};
+    double* d_poses{nullptr};
+    std::vector<void*> allocs;       // freed on destroy / re-reset
+    std::vector<void*> allocs_fixed; // independent of the ring size
+    void* h_raw{nullptr};            // pinned staging
+    double* h_poses{nullptr};
+    CcDevState* h_state{nullptr}; // pinned mirror
+    CcDevState state{};
+    unsigned int seq{0};
+    uint64_t launches{0};
+    uint64_t launches_at_push_start{0};
+    int sm_count{148};
+    // results of the last push
+    cc_batch_info_t info{};
+    std::vector<cc_column_event_t> events;
+    std::vector<cc_cluster_t> clusters;
+    std::vector<cc_cluster_point_t> cluster_points;
+    std::vector<long long> h_first_unpub;
+    std::vector<unsigned char> h_flags;
+    std::vector<CcCluster> h_clusters;
+};
+
+#define CC_CHECK(h, expr)                                                                                              \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t cc_e_ = (expr);                                                                                    \
+        if (cc_e_ != cudaSuccess)                                                                                      \
+        {                                                                                                              \
+            (h)->error = std::string(#expr) + ": " + cudaGetErrorString(cc_e_);                                        \
+            return CC_ERR_CUDA;                                                                                        \
+        }                                                                                                              \
+    } while (0)
+
+#define CC_RUN(h, kernel, grid, block, smem, ...)                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        CC_LAUNCH(kernel, grid, block, smem, (h)->stream, __VA_ARGS__);                                                \
+        (h)->launches++;                                                                                               \
+    } while (0)
+
+static void free_list(std::vector<void*>& v)
+{
+    for (void* p : v)
+        cudaFree(p);
+    v.clear();
+}
+
+template<typename T>
+static cudaError_t dev_alloc(cc_handle* h, std::vector<void*>& list, T** out, size_t count)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess)
+        return e;
+    list.push_back(p);
+    *out = static_cast<T*>(p);
+    return cudaSuccess;
+}
+
+static void fill_devcfg(const cc_handle* h, CcDevCfg& c)
+{
+    const cc_config_t& s = h->config;
+    std::memset(&c, 0, sizeof(c));
+    c.R = h->R;
+    c.N = h->N;
+    c.ringcols = h->ringcols;
+    c.half = h->N / 2;
+    c.clockwise = s.sensor_is_clockwise != 0;
+    c.supplement = s.supplement_inclination_angle_for_nan_cells != 0;
+    c.width = h->width;
+    c.max_slope = s.max_slope;
+    c.first_max = s.first_ring_as_ground_max_allowed_z_diff;
+    c.first_min = s.first_ring_as_ground_min_allowed_z_diff;
+    c.lg_slope = s.last_ground_point_slope_higher_than;
+    c.lg_dist = s.last_ground_point_distance_smaller_than;
+    c.close_z = s.ground_because_close_to_last_certain_ground_max_z_diff;
+    c.close_d = s.ground_because_close_to_last_certain_ground_max_dist_diff;
+    c.next_obst_d = s.obstacle_because_next_certain_obstacle_max_dist_diff;
+    c.use_terrain = s.use_terrain != 0;
+    c.h_max = s.height_ref_to_maximum_;
+    c.h_ground = s.height_ref_to_ground_;
+    c.l_front = s.length_ref_to_front_end_;
+    c.l_rear = s.length_ref_to_rear_end_;
+    c.w_left = s.width_ref_to_left_mirror_;
+    c.w_right = s.width_ref_to_right_mirror_;
+    c.fog_enabled = s.fog_filtering_enabled != 0;
+    c.fog_intensity = static_cast<int>(static_cast<uint8_t>(s.fog_filtering_intensity_below));
+    c.fog_dist = s.fog_filtering_distance_below;
+    c.fog_incl = s.fog_filtering_inclination_above;
+    c.max_distance = s.max_distance;
+    c.max_distance_sq = s.max_distance * s.max_distance; // cpp:80
+    c.max_steps_row = s.max_steps_in_row;
+    c.max_steps_col = s.max_steps_in_column;
+    c.stop_enabled = s.stop_after_association_enabled != 0;
+    c.stop_min_steps = s.stop_after_association_min_steps;
+    c.chessboard = s.ignore_points_in_chessboard_pattern != 0;
+    c.incl_rule = s.ignore_points_with_too_big_inclination_angle_diff != 0;
+    c.use_last_stamp = s.use_last_point_for_cluster_stamp != 0;
+    c.nth = s.cluster_point_trees_every_nth_column > 0 ? s.cluster_point_trees_every_nth_column : 1;
+    std::memcpy(c.robot_from_sensor, h->robot_from_sensor, sizeof(c.robot_from_sensor));
+    c.height_sensor_to_ground = -static_cast<float>(h->robot_from_sensor[11]) + s.height_ref_to_ground_; // cpp:302-303
+}
+
+extern "C" {
+
+const char* cc_version(void)
+{
+#ifdef CC_EMU
+    return "continuous_clustering_b200 0.1 (CPU emulation build: tests only)";
+#else
+    return "continuous_clustering_b200 0.1 (sm_100a)";
+#endif
+}
+
+void cc_config_default(cc_config_t* c)
+{
+    std::memset(c, 0, sizeof(*c));
+    c->is_single_threaded = 0;
+    c->sensor_is_clockwise = 1;
+    c->num_columns = 1700;
+    c->supplement_inclination_angle_for_nan_cells = 1;
+    c->max_slope = 0.2f;
+    c->first_ring_as_ground_max_allowed_z_diff = 0.4f;
+    c->first_ring_as_ground_min_allowed_z_diff = -0.4f;
+    c->last_ground_point_slope_higher_than = -0.1f;
+    c->last_ground_point_distance_smaller_than = 5.f;
+    c->ground_because_close_to_last_certain_ground_max_z_diff = 0.4f;
+    c->ground_because_close_to_last_certain_ground_max_dist_diff = 2.0f;
+    c->obstacle_because_next_certain_obstacle_max_dist_diff = 0.3f;
+    c->use_terrain = 0;
+    c->terrain_max_allowed_z_diff = 0.4f;
+    c->fog_filtering_enabled = 0;
+    c->fog_filtering_intensity_below = 2;
+    c->fog_filtering_distance_below = 18.f;
+    c->fog_filtering_inclination_above = -0.06f;
+    c->max_distance = 0.7f;
+    c->max_steps_in_row = 20;
+    c->max_steps_in_column = 20;
+    c->stop_after_association_enabled = 1;
+    c->stop_after_association_min_steps = 1;
+    c->ignore_points_in_chessboard_pattern = 1;
+    c->ignore_points_with_too_big_inclination_angle_diff = 1;
+    c->use_last_point_for_cluster_stamp = 0;
+    c->cluster_point_trees_every_nth_column = 1;
+}
+
+cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t** out)
+{
+    if (!out)
+        return CC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ordinal < 0 || device_ordinal >= ndev)
+        return CC_ERR_CUDA; // no CUDA device: there is no other way to run this path
+    cc_handle* h = new cc_handle();
+    h->device = device_ordinal;
+    if (max_firings_per_push > 0)
+        h->max_firings = max_firings_per_push;
+    cc_config_default(&h->config);
+    if (cudaSetDevice(h->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(CcDevState)) != cudaSuccess)
+    {
+        delete h;
+        return CC_ERR_CUDA;
+    }
+#ifndef CC_EMU
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
+        h->sm_count = prop.multiProcessorCount;
+#endif
+    *out = h;
+    return CC_OK;
+}
+
+void cc_destroy(cc_handle_t* h)
+{
+    if (!h)
+        return;
+    cudaSetDevice(h->device);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
+    free_list(h->allocs);
+    free_list(h->allocs_fixed);
+    if (h->h_raw)
+        cudaFreeHost(h->h_raw);
+    if (h->h_poses)
+        cudaFreeHost(h->h_poses);
+    if (h->h_state)
+        cudaFreeHost(h->h_state);
+    if (h->ev0)
+        cudaEventDestroy(h->ev0);
+    if (h->ev1)
+        cudaEventDestroy(h->ev1);
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* cc_last_error(const cc_handle_t* h)
+{
+    return h ? h->error.c_str() : "null handle";
+}
+
+cc_status_t cc_set_config(cc_handle_t* h, const cc_config_t* cfg)
+{
+    if (!h || !cfg)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (cfg->num_columns <= 1 || cfg->cluster_point_trees_every_nth_column <= 0)
+    {
+        h->error = "invalid configuration";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    // cpp:66-81
+    if ((h->config.is_single_threaded != 0) != (cfg->is_single_threaded != 0))
+        h->reset_required_cfg = true;
+    if ((h->config.sensor_is_clockwise != 0) != (cfg->sensor_is_clockwise != 0))
+        h->reset_required_cfg = true;
+    if (h->config.num_columns != cfg->num_columns)
+        h->reset_required_cfg = true;
+    h->config = *cfg;
+    h->config_set = true;
+    return CC_OK;
+}
+
+int cc_reset_required(const cc_handle_t* h)
+{
+    return h && (h->reset_required_cfg || h->state.reset_required) ? 1 : 0;
+}
+
+cc_status_t cc_set_robot_from_sensor(cc_handle_t* h, const double m[12])
+{
+    if (!h || !m)
+        return CC_ERR_INVALID_ARGUMENT;
+    std::memcpy(h->robot_from_sensor, m, sizeof(h->robot_from_sensor));
+    h->has_tf = true;
+    return CC_OK;
+}
+
+int cc_has_robot_from_sensor(const cc_handle_t* h)
+{
+    return h && h->has_tf ? 1 : 0;
+}
+
+int cc_num_rows(const cc_handle_t* h)
+{
+    return h ? h->R : -1;
+}
+int cc_num_columns(const cc_handle_t* h)
+{
+    return h ? h->N : 0;
+}
+int cc_ring_buffer_max_columns(const cc_handle_t* h)
+{
+    return h ? h->ringcols : 0;
+}
+void* cc_stream(const cc_handle_t* h)
+{
+    return h ? static_cast<void*>(h->stream) : nullptr;
+}
+uint64_t cc_total_launches(const cc_handle_t* h)
+{
+    return h ? h->launches : 0;
+}
+
+static int grid_for(const cc_handle* h, long long work, int block)
+{
+    long long g = (work + block - 1) / block;
+    const long long cap = static_cast<long long>(h->sm_count) * 8;
+    if (g > cap)
+        g = cap;
+    if (g < 1)
+        g = 1;
+    return static_cast<int>(g);
+}
+
+// ContinuousClustering::reset cpp:11-64
+cc_status_t cc_reset(cc_handle_t* h, int num_rows)
+{
+    if (!h || num_rows <= 0 || num_rows > 1024)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    const int N = h->config.num_columns;
+    const bool realloc_ring = (num_rows != h->R) || (N != h->N) || h->allocs.empty();
+    if (realloc_ring)
+    {
+        free_list(h->allocs);
+        h->R = num_rows;
+        h->N = N;
+        h->ringcols = N * 10;
+        const size_t cells = static_cast<size_t>(h->ringcols) * h->R;
+        const size_t stage = static_cast<size_t>(h->max_firings) * h->R;
+        h->maxcols = h->max_firings + N;
+        CcDevPtrs& d = h->d;
+        const int keep_gap_rows = h->gap_rows;
+        float* keep_gap = d.gap_state;
+        std::memset(&d, 0, sizeof(d));
+        d.gap_state = keep_gap;
+        (void)keep_gap_rows;
+        std::vector<void*>& L = h->allocs;
+        CC_CHECK(h, dev_alloc(h, L, &d.st, 1));
+        CC_CHECK(h, dev_alloc(h, L, &d.pos, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.azimuth, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.incl, cells + 1));
+        CC_CHECK(h, dev_alloc(h, L, &d.cont_az, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.lab, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.stamp, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.guid, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.firing_index, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.assoc, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.mad, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tparent, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.cparent, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tfinish, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tmaxcol, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tnpoints, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tstate, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tid, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tslot, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.rootslot, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.cid, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.visited, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.slot_gcol, static_cast<size_t>(h->ringcols)));
+        CC_CHECK(h, dev_alloc(h, L, &d.rowmax, static_cast<size_t>(h->R)));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_pos, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_az, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_incl, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_incaz, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
+        CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
+        CC_CHECK(h, dev_alloc(h, L, &h->d_poses, static_cast<size_t>(h->max_firings) * 12));
+        const size_t mc = static_cast<size_t>(h->maxcols);
+        CC_CHECK(h, dev_alloc(h, L, &d.col_trigger, mc));
+        CC_CHECK(h, dev_alloc(h, L, &d.col_gap, mc * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.col_minaz, mc));
+        CC_CHECK(h, dev_alloc(h, L, &d.col_runmax, mc));
+        CC_CHECK(h, dev_alloc(h, L, &d.col_first_unpub, mc));
+        CC_CHECK(h, dev_alloc(h, L, &d.col_flag, mc));
+        CC_CHECK(h, dev_alloc(h, L, &h->d_s_parent, mc * h->R));
+        d.cap_ulist = 1 << 18;
+        d.cap_edges = 1 << 22;
+        d.cap_clusters = 1 << 16;
+        d.cap_cluster_points = static_cast<int>(std::min<size_t>(mc * h->R + (static_cast<size_t>(2) * N * h->R), 1u << 30));
+        d.cap_G = h->maxcols + 4 * N;
+        d.maxcols = h->maxcols;
+        d.max_firings = h->max_firings;
+        const size_t ul = static_cast<size_t>(d.cap_ulist);
+        CC_CHECK(h, dev_alloc(h, L, &d.ulist, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.ulist_new, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_rep, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_maxfinish, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_mincol, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_maxend, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_np, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_finishcol, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.u_cluster, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.sv_cparent, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.sv_tfinish, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.sv_tmaxcol, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.sv_tnpoints, ul));
+        CC_CHECK(h, dev_alloc(h, L, &d.edge_a, static_cast<size_t>(d.cap_edges)));
+        CC_CHECK(h, dev_alloc(h, L, &d.edge_b, static_cast<size_t>(d.cap_edges)));
+        CC_CHECK(h, dev_alloc(h, L, &d.G, static_cast<size_t>(d.cap_G)));
+        CC_CHECK(h, dev_alloc(h, L, &d.clusters, static_cast<size_t>(d.cap_clusters)));
+        CC_CHECK(h, dev_alloc(h, L, &d.cluster_points, static_cast<size_t>(d.cap_cluster_points)));
+        CC_CHECK(h, dev_alloc(h, L, &d.n_new_ulist, 1));
+        d.raw = h->d_raw;
+        d.poses = h->d_poses;
+        if (h->h_raw)
+            cudaFreeHost(h->h_raw);
+        if (h->h_poses)
+            cudaFreeHost(h->h_poses);
+        h->h_raw = nullptr;
+        h->h_poses = nullptr;
+        CC_CHECK(h, cudaMallocHost(&h->h_raw, stage * sizeof(cc_raw_point_t)));
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
+        CC_CHECK(h, cudaMemsetAsync(d.firing_index, 0, cells * sizeof(unsigned long long), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.cparent, 0, cells * sizeof(unsigned int), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.tfinish, 0, cells * sizeof(unsigned long long), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.tmaxcol, 0, cells * sizeof(long long), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.tnpoints, 0, cells * sizeof(unsigned int), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.tid, 0, cells * sizeof(unsigned int), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.tslot, 0xff, cells * sizeof(int), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.rootslot, 0, cells * sizeof(unsigned int), h->stream));
+        CC_CHECK(h, cudaMemsetAsync(d.incl, 0, (cells + 1) * sizeof(float), h->stream));
+    }
+    // sc_inclination_angles_between_lasers_.resize(num_rows, NaN) only fills new elements (cpp:46): the values
+    // survive a reset with an unchanged row count
+    if (h->gap_rows != num_rows)
+    {
+        free_list(h->allocs_fixed);
+        CC_CHECK(h, dev_alloc(h, h->allocs_fixed, &h->d.gap_state, static_cast<size_t>(num_rows)));
+        std::vector<float> nan(num_rows, std::nanf(""));
+        CC_CHECK(h, cudaMemcpy(h->d.gap_state, nan.data(), nan.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->gap_rows = num_rows;
+    }
+    h->width = static_cast<float>(2 * M_PI) / static_cast<float>(N); // cpp:16
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    // clearColumns(0, ring_buffer_max_columns - 1) cpp:29
+    CC_RUN(h, k_clear, grid_for(h, static_cast<long long>(h->ringcols) * h->R, 256), 256, 0, cfg, h->d, 0LL,
+           static_cast<long long>(h->ringcols), 0);
+    CcDevState s;
+    std::memset(&s, 0, sizeof(s));
+    s.P = 0;
+    s.foremost = -1;
+    s.F = -1;
+    s.ring_start = -1;
+    s.ring_end = -1;
+    s.first_unpub = -1;
+    s.cluster_counter = 1;
+    s.runmax_carry = -1.0;
+    s.colbase = -1;
+    s.clear_from = -1;
+    s.clear_to = -1;
+    s.danger_col = CC_COL_INF;
+    *h->h_state = s;
+    CC_CHECK(h, cudaMemcpyAsync(h->d.st, h->h_state, sizeof(s), cudaMemcpyHostToDevice, h->stream));
+    std::vector<long long> rm(h->R, -1);
+    CC_CHECK(h, cudaMemcpyAsync(h->d.rowmax, rm.data(), rm.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    CC_CHECK(h, cudaGetLastError());
+    h->state = s;
+    h->has_tf = false; // cpp:38
+    h->reset_required_cfg = false;
+    h->is_reset = true;
+    h->events.clear();
+    h->clusters.clear();
+    h->cluster_points.clear();
+    std::memset(&h->info, 0, sizeof(h->info));
+#ifndef CC_EMU
+    {
+        const int smem = CC_K1_WINDOW * h->R * static_cast<int>(sizeof(float)) + h->R * static_cast<int>(sizeof(long long));
+        if (smem > 48 * 1024)
+            CC_CHECK(h, cudaFuncSetAttribute(k_insert_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+#endif
+    return CC_OK;
+}
+
+static cc_status_t fetch_state(cc_handle* h)
+{
+    CC_CHECK(h, cudaMemcpyAsync(h->h_state, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    h->state = *h->h_state;
+    return CC_OK;
+}
+
+static cc_status_t device_error_to_status(cc_handle* h)
+{
+    const CcDevState& s = h->state;
+    switch (s.error)
+    {
+        case CC_DEV_OK:
+            return CC_OK;
+        case CC_DEV_COLUMN_NOT_CLEARED:
+            h->error = "This column is not cleared. Probably this means the ring buffer is full or there "
+                       "is some other issue with clearing (not cleared at all or written after clearing): " +
+                       std::to_string(s.err_a) + ", " + std::to_string(s.err_b) + ", " + std::to_string(h->ringcols);
+            return CC_ERR_COLUMN_NOT_CLEARED;
+        case CC_DEV_TOO_MANY_COLUMNS:
+            h->error = "more columns completed in one push than the handle was sized for";
+            return CC_ERR_BATCH_TOO_LARGE;
+        case CC_DEV_RING_START_DECREASED:
+            h->error = "This shouldn't happen, ring buffer is not allowed to increase at the front: " +
+                       std::to_string(s.err_a) + ", " + std::to_string(s.err_b);
+            return CC_ERR_RING_START_DECREASED;
+        default:
+            h->error = "device work list overflow (unfinished trees / links / clusters)";
+            return CC_ERR_INTERNAL;
+    }
+}
+
+// finish passes for columns [ci0, ci1] (ci1 < 0: all new columns)
+static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact)
+{
+    const unsigned int seq = ++h->seq;
+    const int g = h->sm_count * 2;
+    CC_RUN(h, k_fin_init, g, 256, 0, cfg, h->d, ci0, ci1, guard);
+    CC_RUN(h, k_fin_agg, g, 256, 0, cfg, h->d, guard);
+    CC_RUN(h, k_fin_decide, g, 256, 0, cfg, h->d, guard, exact);
+    CC_RUN(h, k_fin_mark, g, 256, 0, cfg, h->d, seq, guard);
+    CC_RUN(h, k_fin_copyback, g, 256, 0, h->d, guard);
+    CC_RUN(h, k_fin_columns, 1, 1024, 1024 * sizeof(long long), cfg, h->d, guard);
+    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
+}
+
+static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard)
+{
+    const int g = h->sm_count * 8;
+    CC_RUN(h, k_snapshot, h->sm_count * 2, 256, 0, h->d, guard);
+    CC_RUN(h, k_commit_copy, g, 256, 0, cfg, h->d, h->d_s_parent, ci0, ci1, guard);
+    CC_RUN(h, k_commit_roots, g, 256, 0, cfg, h->d, ci0, ci1, guard);
+    CC_RUN(h, k_commit_links, g, 256, 0, cfg, h->d, ci0, ci1, guard);
+}
+
+// Column-sequential exact path for pushes whose probe flagged a possibly refused association, that hit a cluster
+// about to span a rotation, or that run finish passes only every n-th column.
+static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
+{
+    const int ncols = h->state.ncols;
+    const long long colbase = h->state.colbase;
+    const long long danger = h->state.danger_col;
+    const bool all_careful = cfg.nth != 1;
+    h->h_flags.assign(ncols, 0);
+    CC_CHECK(h, cudaMemcpyAsync(h->h_flags.data(), h->d.col_flag, ncols, cudaMemcpyDeviceToHost, h->stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    std::vector<unsigned char> careful(ncols, 0);
+    for (int ci = 0; ci < ncols; ci++)
+        careful[ci] = all_careful || h->h_flags[ci] || (colbase + ci >= danger);
+    int ci = 0;
+    while (ci < ncols)
+    {
+        if (careful[ci])
+        {
+            CC_RUN(h, k_careful, 1, 1, 0, cfg, h->d, ci);
+            if ((colbase + ci) % cfg.nth == 0)
+                launch_finish(h, cfg, ci, ci, 0, 1);
+            ci++;
+            continue;
+        }
+        int cj = ci;
+        while (cj + 1 < ncols && !careful[cj + 1])
+            cj++;
+        launch_commit(h, cfg, ci, cj, 0);
+        launch_finish(h, cfg, ci, cj, 2, 0);
+        cc_status_t s = fetch_state(h);
+        if (s != CC_OK)
+            return s;
+        if (h->state.abort)
+        {
+            CC_RUN(h, k_restore, h->sm_count * 2, 256, 0, h->d);
+            CC_RUN(h, k_restore_finish, 1, 1, 0, h->d);
+            for (int c = ci; c <= cj; c++)
+                careful[c] = 1;
+            continue;
+        }
+        ci = cj + 1;
+    }
+    h->info.used_exact_path = 1;
+    return CC_OK;
+}
+
+static cc_status_t run_push(cc_handle* h, int n)
+{
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    h->launches_at_push_start = h->launches;
+    h->events.clear();
+    h->clusters.clear();
+    h->cluster_points.clear();
+    std::memset(&h->info, 0, sizeof(h->info));
+    const long long ring_start_before = h->state.ring_start;
+    (void)ring_start_before;
+
+    CC_CHECK(h, cudaEventRecord(h->ev0, h->stream));
+    const int R = h->R;
+    CC_RUN(h, k_clear, h->sm_count * 8, 256, 0, cfg, h->d, 0LL, 0LL, 1); // columns retired by the previous push
+    const long long pts = static_cast<long long>(n) * R;
+    CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
+    const int scan_smem = CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(long long));
+    CC_RUN(h, k_insert_scan, 1, CC_WARP, scan_smem, cfg, h->d, n);
+    CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
+
+    if (!h->has_tf)
+    {
+        // the reference throws from the segmentation stage of the first completed column (cpp:298-299)
+        cc_status_t s = fetch_state(h);
+        if (s != CC_OK)
+            return s;
+        if (h->state.ncols > 0)
+        {
+            h->error = "Transform robot frame from sensor frame was not set yet!";
+            return CC_ERR_NO_ROBOT_TRANSFORM;
+        }
+    }
+    else
+    {
+        CC_RUN(h, k_gap_scan, R, 256, 256 * sizeof(float), cfg, h->d);
+        const int gw = 4; // warps (columns) per block
+        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, gw * R * sizeof(CcGroundSmem), cfg, h->d);
+        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d);
+        CC_RUN(h, k_probe, h->sm_count * 8, 128, 0, cfg, h->d, h->d_s_parent);
+        const bool spec = cfg.nth == 1;
+        if (spec)
+        {
+            launch_commit(h, cfg, 0, -1, 1);
+            launch_finish(h, cfg, 0, -1, 1, 0);
+            CC_RUN(h, k_push_done, 1, 1, 0, h->d, 1);
+        }
+        cc_status_t s = fetch_state(h);
+        if (s != CC_OK)
+            return s;
+        if (h->state.error == 0 && h->state.ncols > 0 && (!spec || h->state.n_flagged > 0 || h->state.abort))
+        {
+            if (h->state.abort)
+            {
+                CC_RUN(h, k_restore, h->sm_count * 2, 256, 0, h->d);
+                CC_RUN(h, k_restore_finish, 1, 1, 0, h->d);
+            }
+            s = slow_path(h, cfg);
+            if (s != CC_OK)
+                return s;
+            CC_RUN(h, k_push_done, 1, 1, 0, h->d, 0);
+            s = fetch_state(h);
+            if (s != CC_OK)
+                return s;
+        }
+    }
+    CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
+    CC_CHECK(h, cudaGetLastError());
+    cc_status_t es = device_error_to_status(h);
+    if (es != CC_OK)
+        return es;
+
+    // ---- bring the results of the push to the host ----
+    const CcDevState& st = h->state;
+    const int ncols = h->has_tf ? st.ncols : 0;
+    const int ncl = st.n_clusters, ncp = st.n_cluster_points;
+    h->h_first_unpub.resize(ncols);
+    h->h_clusters.resize(ncl);
+    h->cluster_points.resize(ncp);
+    if (ncols)
+        CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data(), h->d.col_first_unpub, ncols * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (ncl)
+        CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data(), h->d.clusters, ncl * sizeof(CcCluster),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (ncp)
+    {
+        static_assert(sizeof(CcClusterPoint) == sizeof(cc_cluster_point_t), "cluster point layout");
+        CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data(), h->d.cluster_points, ncp * sizeof(CcClusterPoint),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+
+    // clusters in the order the reference would deliver them: by the column whose pass finished them
+    std::stable_sort(h->h_clusters.begin(), h->h_clusters.end(),
+                     [](const CcCluster& a, const CcCluster& b) { return a.finish_col < b.finish_col; });
+    h->clusters.reserve(ncl);
+    for (const CcCluster& c : h->h_clusters)
+    {
+        cc_cluster_t o;
+        o.id = c.id;
+        o.min_stamp = c.min_stamp;
+        o.max_stamp = c.max_stamp;
+        o.stamp = cfg.use_last_stamp ? c.max_stamp : c.min_stamp + (c.max_stamp - c.min_stamp) / 2; // cpp:1025-1028
+        o.finished_at_gcol = c.finish_col;
+        o.min_gcol = c.min_col;
+        o.max_gcol = c.max_col;
+        o.num_points = c.num_points;
+        o.point_offset = c.point_offset;
+        h->clusters.push_back(o);
+    }
+    // finished-column callbacks in the reference's single-threaded order (cpp:618-620, 1087-1089)
+    long long fu_old = st.push_first_unpub_old;
+    size_t next_cluster = 0;
+    h->events.reserve(static_cast<size_t>(ncols) * 2);
+    for (int ci = 0; ci < ncols; ci++)
+    {
+        const long long c = st.colbase + ci;
+        cc_column_event_t e;
+        e.from_gcol = c;
+        e.to_gcol = c;
+        e.ground_points_only = 1;
+        e.n_clusters_before = static_cast<int32_t>(next_cluster);
+        h->events.push_back(e);
+        if (c % cfg.nth != 0)
+            continue;
+        while (next_cluster < h->clusters.size() && h->clusters[next_cluster].finished_at_gcol <= c)
+            next_cluster++;
+        const long long fu = h->h_first_unpub[ci];
+        e.from_gcol = fu_old;
+        e.to_gcol = fu - 1;
+        e.ground_points_only = 0;
+        e.n_clusters_before = static_cast<int32_t>(next_cluster);
+        h->events.push_back(e);
+        fu_old = fu;
+    }
+    cc_batch_info_t& info = h->info;
+    info.ground_from_gcol = ncols ? st.colbase : 0;
+    info.ground_to_gcol = ncols ? st.colbase + ncols : 0;
+    info.first_unpublished_gcol = st.first_unpub;
+    info.ring_start_gcol = st.ring_start;
+    info.ring_end_gcol = st.ring_end;
+    info.cleared_from_gcol = st.clear_from;
+    info.cleared_to_gcol = st.clear_to;
+    info.n_events = static_cast<int32_t>(h->events.size());
+    info.n_clusters = ncl;
+    info.n_cluster_points = ncp;
+    info.reset_required = st.reset_required;
+    info.gpu_launches = static_cast<int32_t>(h->launches - h->launches_at_push_start);
+    info.device_ms = ms;
+    return CC_OK;
+}
+
+static cc_status_t check_push(cc_handle* h, int n, int rows)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (!h->is_reset)
+    {
+        h->error = "cc_reset() has not been called";
+        return CC_ERR_NOT_RESET;
+    }
+    if (rows != h->R)
+    {
+        h->error = "The number of points in a firing has changed. This is probably a bug!"; // cpp:90-91
+        return CC_ERR_ROW_COUNT_CHANGED;
+    }
+    if (n < 0 || n > h->max_firings)
+    {
+        h->error = "too many firings in one push";
+        return CC_ERR_BATCH_TOO_LARGE;
+    }
+    return CC_OK;
+}
+
+cc_status_t cc_push_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_t* points, const double* poses)
+{
+    cc_status_t s = check_push(h, n, rows);
+    if (s != CC_OK)
+        return s;
+    if (n == 0)
+    {
+        h->events.clear();
+        h->clusters.clear();
+        h->cluster_points.clear();
+        std::memset(&h->info, 0, sizeof(h->info));
+        return CC_OK;
+    }
+    if (!points || !poses)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
+    std::memcpy(h->h_raw, points, pb);
+    std::memcpy(h->h_poses, poses, qb);
+    CC_CHECK(h, cudaMemcpyAsync(h->d_raw, h->h_raw, pb, cudaMemcpyHostToDevice, h->stream));
+    CC_CHECK(h, cudaMemcpyAsync(h->d_poses, h->h_poses, qb, cudaMemcpyHostToDevice, h->stream));
+    h->d.raw = h->d_raw;
+    h->d.poses = h->d_poses;
+    return run_push(h, n);
+}
+
+cc_status_t cc_push_firings_device(cc_handle_t* h, int n, int rows, const cc_raw_point_t* d_points, const double* d_poses)
+{
+    cc_status_t s = check_push(h, n, rows);
+    if (s != CC_OK)
+        return s;
+    if (n == 0)
+        return cc_push_firings(h, 0, rows, nullptr, nullptr);
+    if (!d_points || !d_poses)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    h->d.raw = d_points;
+    h->d.poses = d_poses;
+    return run_push(h, n);
+}
+
+cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out)
+{
+    if (!h || !out)
+        return CC_ERR_INVALID_ARGUMENT;
+    *out = h->info;
+    return CC_OK;
+}
+
+} // extern "C"
+
+template<typename T>
+static cc_status_t copy_out(const std::vector<T>& v, T* out, int cap, int* n_out)
+{
+    if (cap < 0 || (cap > 0 && !out))
+        return CC_ERR_INVALID_ARGUMENT;
+    const int n = static_cast<int>(std::min<size_t>(v.size(), static_cast<size_t>(cap)));
+    if (n)
+        std::memcpy(out, v.data(), static_cast<size_t>(n) * sizeof(T));
+    if (n_out)
+        *n_out = n;
+    return CC_OK;
+}
+
+extern "C" {
+
+cc_status_t cc_get_column_events(const cc_handle_t* h, cc_column_event_t* out, int cap, int* n_out)
+{
+    return h ? copy_out(h->events, out, cap, n_out) : CC_ERR_INVALID_ARGUMENT;
+}
+cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int cap, int* n_out)
+{
+    return h ? copy_out(h->clusters, out, cap, n_out) : CC_ERR_INVALID_ARGUMENT;
+}
+cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out, int cap, int* n_out)
+{
+    return h ? copy_out(h->cluster_points, out, cap, n_out) : CC_ERR_INVALID_ARGUMENT;
+}
+
+// what a caller reads from range_image_ inside a column callback (ros_utils.cpp:56-63, kitti_demo.cpp:183-216)
+cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_column_fields_t* f)
+{
+    if (!h || !f || !h->is_reset)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (to < from)
+        return CC_OK;
+    if (from < 0 || to - from + 1 > h->ringcols)
+    {
+        h->error = "cc_read_columns: range outside the ring";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const int R = h->R;
+    const int64_t ncols = to - from + 1;
+    const size_t cells = static_cast<size_t>(ncols) * R;
+    // the range may wrap around the end of the ring: at most two contiguous spans
+    const int64_t l0 = from % h->ringcols;
+    const int64_t n0 = std::min<int64_t>(ncols, h->ringcols - l0);
+    const int64_t n1 = ncols - n0;
+    auto rd = [&](void* dst, const void* src, size_t elem) -> cudaError_t
+    {
+        cudaError_t e = cudaMemcpyAsync(dst, static_cast<const char*>(src) + static_cast<size_t>(l0) * R * elem,
+                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && n1 > 0)
+            e = cudaMemcpyAsync(static_cast<char*>(dst) + static_cast<size_t>(n0) * R * elem, src,
+                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->stream);
+        return e;
+    };
+    std::vector<float4> pos;
+    std::vector<uchar4> lab;
+    std::vector<unsigned int> u32;
+    std::vector<long long> slot(static_cast<size_t>(ncols));
+    if (f->xyz || f->distance || f->global_column_index)
+    {
+        pos.resize(cells);
+        CC_CHECK(h, rd(pos.data(), h->d.pos, sizeof(float4)));
+    }
+    if (f->intensity || f->ground_point_label || f->debug_ground_point_label || f->is_ignored)
+    {
+        lab.resize(cells);
+        CC_CHECK(h, rd(lab.data(), h->d.lab, sizeof(uchar4)));
+    }
+    {
+        // per-column tags
+        cudaError_t e = cudaMemcpyAsync(slot.data(), h->d.slot_gcol + l0, static_cast<size_t>(n0) * sizeof(long long),
+                                        cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && n1 > 0)
+            e = cudaMemcpyAsync(slot.data() + n0, h->d.slot_gcol, static_cast<size_t>(n1) * sizeof(long long),
+                                cudaMemcpyDeviceToHost, h->stream);
+        CC_CHECK(h, e);
+    }
+    if (f->azimuth_angle)
+        CC_CHECK(h, rd(f->azimuth_angle, h->d.azimuth, sizeof(float)));
+    if (f->inclination_angle)
+        CC_CHECK(h, rd(f->inclination_angle, h->d.incl, sizeof(float)));
+    if (f->continuous_azimuth_angle)
+        CC_CHECK(h, rd(f->continuous_azimuth_angle, h->d.cont_az, sizeof(double)));
+    if (f->stamp)
+        CC_CHECK(h, rd(f->stamp, h->d.stamp, sizeof(uint64_t)));
+    if (f->globally_unique_point_index)
+        CC_CHECK(h, rd(f->globally_unique_point_index, h->d.guid, sizeof(uint64_t)));
+    if (f->firing_index)
+        CC_CHECK(h, rd(f->firing_index, h->d.firing_index, sizeof(uint64_t)));
+    std::vector<unsigned int> tpar;
+    if (f->id || f->tree_root_gcol || f->tree_root_row)
+    {
+        u32.resize(cells);
+        CC_CHECK(h, rd(u32.data(), h->d.cid, sizeof(unsigned int)));
+        tpar.resize(cells);
+        CC_CHECK(h, rd(tpar.data(), h->d.tparent, sizeof(unsigned int)));
+    }
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    std::vector<long long> root_slot_gcol;
+    if (f->tree_root_gcol)
+    {
+        // global column of every tree root: one more small gather of the per-column tags
+        root_slot_gcol.resize(static_cast<size_t>(h->ringcols));
+        CC_CHECK(h, cudaMemcpy(root_slot_gcol.data(), h->d.slot_gcol, root_slot_gcol.size() * sizeof(long long),
+                               cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < cells; i++)
+    {
+        const size_t col = i / R;
+        if (f->xyz)
+        {
+            f->xyz[3 * i + 0] = pos[i].x;
+            f->xyz[3 * i + 1] = pos[i].y;
+            f->xyz[3 * i + 2] = pos[i].z;
+        }
+        if (f->distance)
+            f->distance[i] = pos[i].w;
+        if (f->global_column_index) // refilled by segmentation (cpp:347-350); -1 in cleared columns
+            f->global_column_index[i] = slot[col] == static_cast<long long>(from + static_cast<int64_t>(col)) ? slot[col] : -1;
+        if (f->intensity)
+            f->intensity[i] = lab[i].w;
+        if (f->ground_point_label)
+            f->ground_point_label[i] = lab[i].x;
+        if (f->debug_ground_point_label)
+            f->debug_ground_point_label[i] = lab[i].y;
+        if (f->is_ignored)
+            f->is_ignored[i] = lab[i].z;
+        if (f->id)
+            f->id[i] = u32[i];
+        if (f->tree_root_gcol)
+            f->tree_root_gcol[i] = tpar[i] == CC_NONE ? -1 : root_slot_gcol[tpar[i] / R];
+        if (f->tree_root_row)
+            f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
+    }
+    return CC_OK;
+}
+
+cc_status_t cc_selftest_math(int device_ordinal, int op, int n, const float* a, const float* b, float* out)
+{
+    if (n < 0 || !a || !out || (op == 0 && !b))
+        return CC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess)
+        return CC_ERR_CUDA;
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    const size_t bytes = static_cast<size_t>(std::max(n, 1)) * sizeof(float);
+    cc_status_t rc = CC_OK;
+    if (cudaMalloc(reinterpret_cast<void**>(&da), bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&db), bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&dout), bytes) != cudaSuccess)
+        rc = CC_ERR_CUDA;
+    if (rc == CC_OK)
+    {
+        cudaMemcpy(da, a, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice);
+        if (b)
+            cudaMemcpy(db, b, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice);
+        CC_LAUNCH(k_selftest_math, 1024, 256, 0, static_cast<cudaStream_t>(nullptr), op, n, da, db, dout);
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+            rc = CC_ERR_CUDA;
+        cudaMemcpy(out, dout, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return rc;
+}
+
+} // extern "C"

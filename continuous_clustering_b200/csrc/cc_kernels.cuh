@@ -1,0 +1,1498 @@
+// cc_kernels.cuh -- the sm_100a kernels of the per-column hot path. No tensor cores: the path has no dense
+// contraction; it is streaming scans + a neighbourhood walk + union-find, bound by HBM/L2 latency.
+//
+// Reference functions replaced ("cpp:" = src/clustering/continuous_clustering.cpp of the reference):
+//   k_prep + k_insert_scan + k_scatter   insertFiringIntoRangeImage              cpp:105-292
+//   k_gap_scan + k_ground + k_runmax     performGroundPointSegmentationForColumn cpp:294-624
+//   k_probe + k_commit_* / k_careful     associatePointsInColumn, traverseFieldOfView,
+//                                        associatePointToPointTree, associatePointTreeToPointTree cpp:638-835
+//   k_fin_*                              findFinishedTreesAndAssignSameId        cpp:837-974 and the id / ring
+//                                        bookkeeping half of collectPointsForCusterAndPublish cpp:976-1092
+//   k_clear                              clearColumns                            cpp:1094-1145
+//
+// Everything is compiled with -fmad=false: the reference is built without FMA contraction (CMakeLists.txt:5-12)
+// and ground labels / column indices must be bit-identical.
+#ifndef CC_KERNELS_CUH
+#define CC_KERNELS_CUH
+
+#include <math.h>
+
+#include "cc_math.cuh"
+#include "cc_types.h"
+
+#define CC_DEV __device__ __forceinline__
+
+struct CcRawPoint // layout of continuous_clustering::RawPoint (point_types.hpp:10-19) == cc_raw_point_t
+{
+    float x, y, z;
+    unsigned int pad0;
+    unsigned long long firing_index;
+    unsigned char intensity;
+    unsigned char pad1[7];
+    unsigned long long stamp;
+    unsigned long long guid;
+};
+
+CC_DEV float cc_nanf()
+{
+    return ccm::u2f(0x7fc00000u);
+}
+CC_DEV bool cc_isnan(float x)
+{
+    return x != x;
+}
+CC_DEV unsigned long long cc_d2ord(double d) // order-preserving for non-negative doubles
+{
+    return static_cast<unsigned long long>(__double_as_longlong(d));
+}
+CC_DEV double cc_ord2d(unsigned long long u)
+{
+    return __longlong_as_double(static_cast<long long>(u));
+}
+CC_DEV unsigned int cc_vload(const unsigned int* p)
+{
+    return *reinterpret_cast<const volatile unsigned int*>(p);
+}
+
+CC_DEV int cc_warp_min(int v)
+{
+    return __reduce_min_sync(CC_FULL_MASK, v);
+}
+CC_DEV int cc_warp_max(int v)
+{
+    return __reduce_max_sync(CC_FULL_MASK, v);
+}
+CC_DEV double cc_warp_min_f64(double v)
+{
+    for (int o = CC_WARP / 2; o > 0; o >>= 1)
+    {
+        double w = __shfl_xor_sync(CC_FULL_MASK, v, o);
+        v = (w < v) ? w : v;
+    }
+    return v;
+}
+
+// rigid transform helpers, double, evaluation order of the Eigen stand-in the oracle is built with
+CC_DEV void cc_iso_apply(const double* m, double x, double y, double z, double* out)
+{
+    for (int i = 0; i < 3; i++)
+        out[i] = ((m[i * 4 + 0] * x + m[i * 4 + 1] * y) + m[i * 4 + 2] * z) + m[i * 4 + 3];
+}
+CC_DEV void cc_iso_inverse(const double* m, double* r)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            r[i * 4 + j] = m[j * 4 + i];
+    for (int i = 0; i < 3; i++)
+        r[i * 4 + 3] = -(r[i * 4 + 0] * m[3] + (r[i * 4 + 1] * m[7] + r[i * 4 + 2] * m[11]));
+}
+CC_DEV void cc_iso_mul(const double* a, const double* b, double* r)
+{
+    for (int i = 0; i < 3; i++)
+    {
+        for (int j = 0; j < 3; j++)
+            r[i * 4 + j] = a[i * 4 + 0] * b[j] + (a[i * 4 + 1] * b[4 + j] + a[i * 4 + 2] * b[8 + j]);
+        r[i * 4 + 3] = (a[i * 4 + 0] * b[3] + (a[i * 4 + 1] * b[7] + a[i * 4 + 2] * b[11])) + a[i * 4 + 3];
+    }
+}
+
+CC_DEV int cc_local_col(long long g, int ringcols)
+{
+    return static_cast<int>(g % ringcols);
+}
+
+// =====================================================================================================
+// K0  per raw point: rigid transform, azimuth -> column within rotation, distance, inclination (cpp:125-151,
+//     189, 232). Fully parallel, one thread per (firing, row).
+// =====================================================================================================
+__global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+{
+    const int total = n_firings * cfg.R;
+    const float pi_f = static_cast<float>(M_PI);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const int k = idx / cfg.R;
+        const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
+        const float fx = raw->x, fy = raw->y, fz = raw->z;
+        p.o_g[idx] = -1;
+        if (cc_isnan(fx))
+        {
+            p.s_cwr[idx] = CC_INVALID_CWR;
+            continue;
+        }
+        const double* pose = p.poses + 12 * k;
+        double po[3];
+        cc_iso_apply(pose, static_cast<double>(fx), static_cast<double>(fy), static_cast<double>(fz), po);
+        const double rx = po[0] - pose[3], ry = po[1] - pose[7], rz = po[2] - pose[11];
+        const float az = ccm::atan2f_glibc(fy, fx); // sensor-frame azimuth, cpp:142
+        const float incaz = cfg.clockwise ? -az + pi_f : az + pi_f;
+        const int cwr = static_cast<int>(ccm::div_rn(incaz, cfg.width));
+        const float dist = static_cast<float>(sqrt(rx * rx + (ry * ry + rz * rz)));
+        p.s_pos[idx] = make_float4(static_cast<float>(po[0]), static_cast<float>(po[1]), static_cast<float>(po[2]), dist);
+        p.s_az[idx] = az;
+        p.s_incaz[idx] = incaz;
+        p.s_incl[idx] = ccm::asinf_glibc(ccm::div_rn(static_cast<float>(rz), dist));
+        p.s_cwr[idx] = cwr;
+    }
+}
+
+// =====================================================================================================
+// K1  insertion scan: the part of insertFiringIntoRangeImage that is sequential over firings -- rotation
+//     unwrapping against the previous rearmost column (cpp:119-175), the cell-collision rule (cpp:188-208),
+//     the "too far behind" cut (cpp:210-221), rearmost/foremost tracking, the straddle check (cpp:252-261)
+//     and which firing completes which column (cpp:289-291). ONE warp; lanes own rows; the per-row occupancy of
+//     the last CC_K1_WINDOW columns lives in shared memory so a firing costs a few shared-memory round trips and
+//     two warp reductions instead of dependent L2 reads. Distances are written through to the ring so that
+//     K1b can tell which writer of a cell won (the last writer is always the closest, cpp:207).
+// =====================================================================================================
+__global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+{
+    if (blockIdx.x != 0)
+        return;
+    CC_SMEM(smem);
+    const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
+    float* wdist = reinterpret_cast<float*>(smem);
+    long long* rmx = reinterpret_cast<long long*>(smem + static_cast<size_t>(W) * R * sizeof(float));
+    const int lane = threadIdx.x;
+    CcDevState* st = p.st;
+
+    for (int row = lane; row < R; row += CC_WARP)
+    {
+        const long long rm = p.rowmax[row];
+        rmx[row] = rm;
+        for (long long c = (rm - W + 1 > 0 ? rm - W + 1 : 0); c <= rm; c++)
+            wdist[(c & (W - 1)) * R + row] = p.pos[static_cast<size_t>(cc_local_col(c, ringcols)) * R + row].w;
+    }
+    __syncwarp();
+
+    long long P = st->P, Fm = st->foremost, F = st->F, ring_start = st->ring_start, ring_end = st->ring_end,
+              first_unpub = st->first_unpub;
+    int reset_required = st->reset_required;
+    int error = 0;
+    long long colbase = F;
+    long long prev_rot = P / N;
+    int pc = static_cast<int>(P % N);
+    int rot10 = static_cast<int>(prev_rot % 10);
+    const int half = cfg.half;
+    const float nanv = cc_nanf();
+
+    for (int k = 0; k < n_firings; k++)
+    {
+        int lmin = 0x7fffffff, lmax = -0x7fffffff - 1; // relative to P
+        for (int row = lane; row < R; row += CC_WARP)
+        {
+            const int idx = k * R + row;
+            const int cw = p.s_cwr[idx];
+            if (cw == CC_INVALID_CWR)
+                continue;
+            const float d = p.s_pos[idx].w;
+            long long g = prev_rot * N + cw;
+            const int diff = cw - pc;
+            int rotoff = 0;
+            if (diff < -half)
+            {
+                g += N;
+                rotoff = 1;
+            }
+            else if (P > 0 && diff > half)
+            {
+                g -= N;
+                rotoff = -1;
+            }
+            if (g < 0)
+                continue; // reference: out-of-bounds access (undefined); the point is dropped here
+            int r10 = rot10 + rotoff;
+            r10 = r10 < 0 ? 9 : (r10 > 9 ? 0 : r10);
+            int local = r10 * N + cw;
+            if (local >= ringcols)
+                local -= ringcols;
+
+            long long rm = rmx[row];
+            // occupancy of cell (g, row)
+            float cd;
+            if (g > rm)
+                cd = nanv;
+            else if (g > rm - W)
+                cd = wdist[(g & (W - 1)) * R + row];
+            else
+                cd = p.pos[static_cast<size_t>(local) * R + row].w;
+            if (!cc_isnan(cd) && !cc_isnan(d))
+            {
+                const long long g1 = g + 1;
+                int local1 = local + 1;
+                if (local1 >= ringcols)
+                    local1 -= ringcols;
+                float nd;
+                if (g1 > rm)
+                    nd = nanv;
+                else if (g1 > rm - W)
+                    nd = wdist[(g1 & (W - 1)) * R + row];
+                else
+                    nd = p.pos[static_cast<size_t>(local1) * R + row].w;
+                if (cc_isnan(nd))
+                {
+                    g = g1;
+                    local = local1;
+                    cd = nd;
+                }
+            }
+            if (!cc_isnan(cd) && (cc_isnan(d) || d >= cd))
+                continue;
+            const bool too_far_behind = F >= 0 && g < F;
+            if (!too_far_behind)
+            {
+                if (g > rm)
+                {
+                    long long lo = rm + 1;
+                    if (lo < g - W + 1)
+                        lo = g - W + 1;
+                    for (long long c = lo; c < g; c++)
+                        wdist[(c & (W - 1)) * R + row] = nanv;
+                    rmx[row] = g;
+                    rm = g;
+                }
+                if (g > rm - W)
+                    wdist[(g & (W - 1)) * R + row] = d;
+                p.pos[static_cast<size_t>(local) * R + row].w = d; // write-through
+                p.o_g[idx] = g;
+                p.o_rot[idx] = static_cast<int>(prev_rot + rotoff);
+            }
+            const long long rel = g - P;
+            const int reli = rel > 0x3fffffff ? 0x3fffffff : (rel < -0x3fffffff ? -0x3fffffff : static_cast<int>(rel));
+            lmin = reli < lmin ? reli : lmin;
+            lmax = reli > lmax ? reli : lmax;
+        }
+        const int wmin = cc_warp_min(lmin), wmax = cc_warp_max(lmax);
+        if (wmin != 0x7fffffff)
+        {
+            const long long rear = P + wmin, fore = P + wmax;
+            if (fore - rear > N / 2) // cpp:252-261
+            {
+                reset_required = 1;
+                continue;
+            }
+            if (rear > P)
+            {
+                pc += static_cast<int>(rear - P);
+                while (pc >= N)
+                {
+                    pc -= N;
+                    prev_rot++;
+                    rot10 = rot10 == 9 ? 0 : rot10 + 1;
+                }
+                P = rear;
+            }
+            if (fore > Fm)
+                Fm = fore;
+        }
+        if (Fm < 0)
+            continue;
+        if (ring_start == -1)
+        {
+            ring_start = P;
+            first_unpub = P;
+        }
+        if (Fm > ring_end)
+            ring_end = Fm;
+        if (F == -1)
+        {
+            F = P;
+            colbase = F;
+        }
+        // columns [F, P) are complete: this firing's pose drives their segmentation (cpp:289-291)
+        if (P > F)
+        {
+            if (P - colbase > p.maxcols)
+            {
+                error = CC_DEV_TOO_MANY_COLUMNS;
+                break;
+            }
+            for (long long c = F + lane; c < P; c += CC_WARP)
+                p.col_trigger[c - colbase] = k;
+            F = P;
+        }
+    }
+    __syncwarp();
+    for (int row = lane; row < R; row += CC_WARP)
+        p.rowmax[row] = rmx[row];
+    if (lane == 0)
+    {
+        st->P = P;
+        st->foremost = Fm;
+        st->F = F;
+        st->ring_start = ring_start;
+        st->ring_end = ring_end;
+        st->first_unpub = first_unpub;
+        st->reset_required = reset_required;
+        st->colbase = colbase;
+        st->ncols = colbase >= 0 ? static_cast<int>(F - colbase) : 0;
+        if (error)
+            st->error = error;
+        st->clear_from = ring_start;
+        st->clear_to = ring_start;
+        st->push_first_unpub_old = first_unpub;
+        st->n_edges = 0;
+        st->n_flagged = 0;
+        st->danger_col = CC_COL_INF;
+        st->abort = 0;
+        st->n_clusters = 0;
+        st->n_cluster_points = 0;
+    }
+}
+
+// =====================================================================================================
+// K1b scatter the staged fields of every stored point into the ring (cpp:223-237). Parallel; a point whose
+//     cell was re-written by a closer return of a later firing (cpp:207) sees a different distance and skips.
+// =====================================================================================================
+__global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+{
+    const int total = n_firings * cfg.R;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const long long g = p.o_g[idx];
+        if (g < 0)
+            continue;
+        const int row = idx % cfg.R;
+        const size_t cell = static_cast<size_t>(cc_local_col(g, cfg.ringcols)) * cfg.R + row;
+        const float4 sp = p.s_pos[idx];
+        if (ccm::f2u(p.pos[cell].w) != ccm::f2u(sp.w))
+            continue;
+        const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
+        p.pos[cell] = sp;
+        p.azimuth[cell] = p.s_az[idx];
+        p.incl[cell] = p.s_incl[idx];
+        p.cont_az[cell] = (2 * M_PI) * static_cast<double>(p.o_rot[idx]) + static_cast<double>(p.s_incaz[idx]);
+        uchar4 l = p.lab[cell];
+        l.w = raw->intensity;
+        p.lab[cell] = l;
+        p.stamp[cell] = raw->stamp;
+        p.guid[cell] = raw->guid;
+        p.firing_index[cell] = raw->firing_index;
+    }
+}
+
+// =====================================================================================================
+// K2a  sc_inclination_angles_between_lasers_ (cpp:353-357): per row, the last non-NaN inclination difference
+//      to the laser below seen in any column so far. One block per row: chunked "last valid" scan over the
+//      new columns, seeded with the value carried from earlier pushes.
+// =====================================================================================================
+__global__ void k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
+{
+    CC_SMEM(smem);
+    float* lastv = reinterpret_cast<float*>(smem);
+    const int R = cfg.R;
+    const int row = blockIdx.x;
+    if (row >= R)
+        return;
+    const int ncols = p.st->ncols;
+    const long long colbase = p.st->colbase;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int chunk = (ncols + T - 1) / T;
+    const int lo = t * chunk, hi = (lo + chunk < ncols) ? lo + chunk : ncols;
+    float last = cc_nanf();
+    for (int ci = lo; ci < hi; ci++)
+    {
+        const size_t cell = static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
+        const float a = p.incl[cell];
+        const float b = (row == R - 1) ? 0.f : p.incl[cell + 1];
+        const float d = a - b;
+        if (!cc_isnan(d))
+            last = d;
+    }
+    lastv[t] = last;
+    __syncthreads();
+    // exclusive "last valid" prefix over threads, seeded with the carried state
+    float pre = p.gap_state[row];
+    for (int j = 0; j < t; j++)
+    {
+        const float v = lastv[j];
+        if (!cc_isnan(v))
+            pre = v;
+    }
+    float cur = pre;
+    for (int ci = lo; ci < hi; ci++)
+    {
+        const size_t cell = static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
+        const float a = p.incl[cell];
+        const float b = (row == R - 1) ? 0.f : p.incl[cell + 1];
+        const float d = a - b;
+        if (!cc_isnan(d))
+            cur = d;
+        p.col_gap[static_cast<size_t>(ci) * R + row] = cur;
+    }
+    __syncthreads();
+    if (t == T - 1)
+    {
+        float fin = pre;
+        if (!cc_isnan(last))
+            fin = last;
+        if (ncols > 0)
+            p.gap_state[row] = fin;
+    }
+}
+
+// =====================================================================================================
+// K2b  ground-point segmentation of one column per warp (cpp:294-624). Lanes stage the column into shared
+//      memory (classification of every cell, projection into the azimuth plane, ego-box test in double), lane 0
+//      runs the bottom-to-top label state machine on the staged values, then all lanes derive is_ignored
+//      (cpp:567-616) and write the association view of the column.
+// =====================================================================================================
+struct CcGroundSmem
+{
+    // per row, per warp
+    float c2x, c2y, incl, gap;
+    unsigned char cls, label, dbg, pad;
+};
+
+__global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
+{
+    CC_SMEM(smem);
+    const int R = cfg.R;
+    const int warps_per_block = blockDim.x / CC_WARP;
+    const int wib = threadIdx.x / CC_WARP, lane = threadIdx.x % CC_WARP;
+    CcGroundSmem* s = reinterpret_cast<CcGroundSmem*>(smem) + static_cast<size_t>(wib) * R;
+    const int ncols = p.st->ncols;
+    const long long colbase = p.st->colbase;
+    const float nanv = cc_nanf();
+
+    for (int ci = blockIdx.x * warps_per_block + wib; ci < ncols; ci += gridDim.x * warps_per_block)
+    {
+        const long long gcol = colbase + ci;
+        const int local = cc_local_col(gcol, cfg.ringcols);
+        const size_t base = static_cast<size_t>(local) * R;
+        const int trig = p.col_trigger[ci];
+        const double* pose = p.poses + 12 * trig;
+        double inv[12], ego[12];
+        cc_iso_inverse(pose, inv);
+        cc_iso_mul(cfg.robot_from_sensor, inv, ego);
+        const float spx = static_cast<float>(pose[3]), spy = static_cast<float>(pose[7]),
+                    spz = static_cast<float>(pose[11]);
+        if (lane == 0 && p.slot_gcol[local] != -1)
+        {
+            p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
+            p.st->err_a = p.slot_gcol[local];
+            p.st->err_b = gcol;
+        }
+
+        // ---- stage ----
+        for (int row = lane; row < R; row += CC_WARP)
+        {
+            const float4 q = p.pos[base + row];
+            const float incl = p.incl[base + row];
+            const unsigned char intensity = p.lab[base + row].w;
+            unsigned char cls = 3;
+            float c2x = nanv, c2y = nanv;
+            if (cc_isnan(q.w))
+                cls = 0;
+            else if (cfg.fog_enabled && intensity < static_cast<unsigned char>(cfg.fog_intensity) &&
+                     q.w < cfg.fog_dist && incl > cfg.fog_incl)
+                cls = 1;
+            else
+            {
+                double e[3];
+                cc_iso_apply(ego, static_cast<double>(q.x), static_cast<double>(q.y), static_cast<double>(q.z), e);
+                if (e[0] < cfg.l_front && e[0] > cfg.l_rear && e[1] < cfg.w_left && e[1] > cfg.w_right &&
+                    e[2] < cfg.h_max && e[2] > cfg.h_ground)
+                    cls = 2;
+            }
+            // position w.r.t. the sensor in the azimuth plane (hpp:229-232); also needed for the relabel walk
+            const float x = q.x - spx, y = q.y - spy, z = q.z - spz;
+            c2x = ccm::sqrt_rn(x * x + y * y);
+            c2y = z;
+            s[row].c2x = c2x;
+            s[row].c2y = c2y;
+            s[row].incl = incl;
+            s[row].gap = p.col_gap[static_cast<size_t>(ci) * R + row];
+            s[row].cls = cls;
+            s[row].label = CC_GP_UNKNOWN;
+            s[row].dbg = CC_WHITE;
+        }
+        __syncwarp();
+
+        // ---- sequential label state machine (cpp:305-565) ----
+        if (lane == 0)
+        {
+            bool first_obstacle_detected = false, first_point_found = false;
+            float lg_x = 0.f, lg_y = cfg.height_sensor_to_ground; // to2d of last_ground_position_wrt_sensor
+            float pv_x = 0.f, pv_y = 0.f;
+            unsigned char prev_label = 0;
+            for (int row = R - 1; row >= 0; row--)
+            {
+                const unsigned char cls = s[row].cls;
+                if (cls == 0)
+                {
+                    if (cfg.supplement && row < R - 1)
+                        s[row].incl = s[row + 1].incl + s[row].gap; // cpp:364-369
+                    continue;
+                }
+                if (cls == 1)
+                {
+                    s[row].label = CC_GP_FOG;
+                    s[row].dbg = CC_LIGHTGRAY;
+                    continue;
+                }
+                if (cls == 2)
+                {
+                    s[row].label = CC_GP_EGO_VEHICLE;
+                    s[row].dbg = CC_VIOLET;
+                    continue;
+                }
+                const float c2x = s[row].c2x, c2y = s[row].c2y;
+                if (!first_point_found) // cpp:409-431
+                {
+                    first_point_found = true;
+                    const float h = c2y - cfg.height_sensor_to_ground;
+                    if (h > cfg.first_min && h < cfg.first_max)
+                    {
+                        s[row].label = CC_GP_GROUND;
+                        s[row].dbg = CC_GRAY;
+                        lg_x = c2x;
+                        lg_y = c2y;
+                        first_obstacle_detected = false;
+                    }
+                    else
+                    {
+                        s[row].label = CC_GP_OBSTACLE;
+                        s[row].dbg = CC_ORANGE;
+                        first_obstacle_detected = true;
+                    }
+                    pv_x = c2x;
+                    pv_y = c2y;
+                    prev_label = s[row].dbg;
+                    continue;
+                }
+                const float ptc_x = c2x - pv_x, ptc_y = c2y - pv_y;
+                const float slope_to_prev = ccm::div_rn(ptc_y, ptc_x);
+                bool flat_prev = fabsf(slope_to_prev) < cfg.max_slope && ptc_x > 0;
+                flat_prev = flat_prev && (!cfg.use_terrain || ptc_x < 5);
+                const float gtc_x = c2x - lg_x, gtc_y = c2y - lg_y;
+                const float slope_to_ground = ccm::div_rn(gtc_y, gtc_x);
+                const bool flat_ground = fabsf(slope_to_ground) < cfg.max_slope && gtc_x > 0;
+
+                unsigned char label = CC_GP_UNKNOWN, dbg = CC_WHITE;
+                if (!first_obstacle_detected && flat_prev)
+                {
+                    label = CC_GP_GROUND;
+                    dbg = CC_GREEN;
+                }
+                else if (!cfg.use_terrain)
+                {
+                    if (first_obstacle_detected && flat_prev && flat_ground)
+                    {
+                        label = CC_GP_GROUND;
+                        dbg = CC_YELLOWGREEN;
+                    }
+                    else if (fabsf(gtc_x) < cfg.close_d && fabsf(gtc_y) < cfg.close_z)
+                    {
+                        label = CC_GP_GROUND;
+                        dbg = CC_YELLOW;
+                    }
+                }
+                if (label != CC_GP_GROUND) // cpp:508-536
+                {
+                    label = CC_GP_OBSTACLE;
+                    dbg = CC_RED;
+                    int below = row + 1;
+                    while (below < R)
+                    {
+                        const unsigned char ql = s[below].label, qd = s[below].dbg;
+                        if (qd == CC_YELLOW || (ql == CC_GP_GROUND && fabsf(c2x - s[below].c2x) < cfg.next_obst_d))
+                        {
+                            if (ql == CC_GP_GROUND)
+                            {
+                                s[below].label = CC_GP_OBSTACLE;
+                                s[below].dbg = CC_DARKRED;
+                            }
+                            below++;
+                        }
+                        else
+                            break;
+                    }
+                }
+                s[row].label = label;
+                s[row].dbg = dbg;
+                first_obstacle_detected |= label == CC_GP_OBSTACLE;
+                if (dbg == CC_GREEN || dbg == CC_YELLOWGREEN) // cpp:541-561
+                {
+                    if (slope_to_prev > cfg.lg_slope && fabsf(ptc_x) < cfg.lg_dist && prev_label != CC_YELLOW)
+                    {
+                        lg_x = c2x;
+                        lg_y = c2y;
+                    }
+                }
+                pv_x = c2x;
+                pv_y = c2y;
+                prev_label = dbg;
+            }
+        }
+        __syncwarp();
+
+        // ---- is_ignored (cpp:567-616) + association view ----
+        double min_az = 1.7976931348623157e308;
+        for (int row = lane; row < R; row += CC_WARP)
+        {
+            const size_t cell = base + row;
+            const float4 q = p.pos[cell];
+            const unsigned char label = s[row].label;
+            bool ignored = false;
+            if (cc_isnan(q.w))
+                ignored = true;
+            else if (label != CC_GP_OBSTACLE)
+                ignored = true;
+            else if (q.w < cfg.max_distance)
+                ignored = true;
+            else if (cfg.incl_rule && row < R - 1 && ccm::atan2f_glibc(cfg.max_distance, q.w) < s[row].gap)
+                ignored = true;
+            else if (cfg.chessboard)
+            {
+                const bool column_even = (gcol % 2) == 0, row_even = (row % 2) == 0;
+                if (column_even != row_even)
+                    ignored = true;
+            }
+            double caz;
+            if (s[row].cls == 0)
+            {
+                caz = (static_cast<double>(gcol) + 0.5) * static_cast<double>(cfg.width); // cpp:371-372
+                p.cont_az[cell] = caz;
+                p.incl[cell] = s[row].incl;
+            }
+            else
+                caz = p.cont_az[cell];
+            if (caz < min_az)
+                min_az = caz;
+            uchar4 l = p.lab[cell];
+            l.x = label;
+            l.y = s[row].dbg;
+            l.z = ignored ? 1 : 0;
+            p.lab[cell] = l;
+            p.assoc[cell] = make_float4(ignored ? nanv : q.x, q.y, q.z, s[row].incl);
+            p.mad[cell] = ignored ? 0.f : ccm::asinf_glibc(ccm::div_rn(cfg.max_distance, q.w));
+        }
+        min_az = cc_warp_min_f64(min_az);
+        if (lane == 0)
+        {
+            p.col_minaz[ci] = min_az;
+            p.slot_gcol[local] = gcol;
+            p.col_flag[ci] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// K2c  running maximum of the columns' minimum azimuth (the value every finish pass compares against,
+//      cpp:884-885), continued across pushes. Single block, chunked scan.
+// =====================================================================================================
+__global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p)
+{
+    CC_SMEM(smem);
+    double* part = reinterpret_cast<double*>(smem);
+    if (blockIdx.x != 0)
+        return;
+    const int ncols = p.st->ncols;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int chunk = (ncols + T - 1) / T;
+    const int lo = t * chunk, hi = (lo + chunk < ncols) ? lo + chunk : ncols;
+    double m = -1.0;
+    for (int ci = lo; ci < hi; ci++)
+    {
+        const double v = p.col_minaz[ci];
+        m = v > m ? v : m;
+    }
+    part[t] = m;
+    __syncthreads();
+    double pre = p.st->runmax_carry;
+    for (int j = 0; j < t; j++)
+        pre = part[j] > pre ? part[j] : pre;
+    for (int ci = lo; ci < hi; ci++)
+    {
+        const double v = p.col_minaz[ci];
+        pre = v > pre ? v : pre;
+        p.col_runmax[ci] = pre;
+    }
+}
+
+// =====================================================================================================
+// K3a  association probe (cpp:698-835): every non-ignored cell of the new columns walks its field of view and
+//      records its first hit (the tree it joins) and every later hit (tree<->tree links). The walk is purely
+//      geometric as long as the reference never REFUSES an association (cpp:654-659, 688-690); every hit that
+//      could have been refused -- its target's finish azimuth is not beyond the largest column-minimum azimuth
+//      seen before this column, or its tree is already finished -- flags the column for the column-sequential
+//      exact path. No persistent state is modified here.
+// =====================================================================================================
+__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+{
+    const int R = cfg.R;
+    const int ncols = p.st->ncols;
+    const long long colbase = p.st->colbase;
+    const int total = ncols * R;
+    const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const int ci = idx / R, row = idx % R;
+        int local = base_local + ci;
+        if (local >= cfg.ringcols)
+            local -= cfg.ringcols;
+        const unsigned int q = static_cast<unsigned int>(local) * R + row;
+        s_parent[idx] = CC_NONE;
+        const float4 a = p.assoc[q];
+        if (cc_isnan(a.x))
+        {
+            p.visited[q] = 0;
+            continue; // is_ignored
+        }
+        const float mad = p.mad[q];
+        const double prev_runmax = ci > 0 ? p.col_runmax[ci - 1] : p.st->runmax_carry;
+        int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+        steps_back = steps_back < cfg.max_steps_row ? steps_back : cfg.max_steps_row;
+        unsigned int first = CC_NONE;
+        int visited = 0;
+        bool flagged = false;
+        int other_col = local;
+        for (int back = 0; back <= steps_back; back++)
+        {
+            for (int dir = -1; dir <= 1; dir += 2)
+            {
+                if (dir == 1 && back == 0)
+                    continue;
+                int steps_v = (dir == 1 || back == 0) ? 1 : 0;
+                int orow = (dir == 1 || back == 0) ? row + dir : row;
+                while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
+                {
+                    const unsigned int o = static_cast<unsigned int>(other_col) * R + orow;
+                    const float4 b = p.assoc[o];
+                    visited++;
+                    if (fabsf(b.w - a.w) > mad)
+                        break;
+                    if (!cc_isnan(b.x))
+                    {
+                        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                        if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
+                        {
+                            // could the reference have refused this hit?
+                            const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                            if (finish_o <= prev_runmax)
+                                flagged = true;
+                            if (back > ci)
+                            {
+                                const unsigned int ro = p.tparent[o];
+                                if (ro == CC_NONE || p.tstate[ro] != 0)
+                                    flagged = true;
+                            }
+                            if (first == CC_NONE)
+                                first = o;
+                            else if (o != first)
+                            {
+                                const int e = atomicAdd(&p.st->n_edges, 1);
+                                if (e < p.cap_edges)
+                                {
+                                    p.edge_a[e] = q;
+                                    p.edge_b[e] = o;
+                                }
+                                else
+                                    p.st->error = CC_DEV_LIST_OVERFLOW;
+                            }
+                        }
+                    }
+                    if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps)
+                        break;
+                    orow += dir;
+                    steps_v++;
+                }
+            }
+            if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+                break;
+            other_col--;
+            if (other_col < 0)
+                other_col += cfg.ringcols;
+        }
+        s_parent[idx] = first == CC_NONE ? q : first;
+        p.visited[q] = static_cast<unsigned short>(visited);
+        if (flagged)
+        {
+            p.col_flag[ci] = 1;
+            atomicAdd(&p.st->n_flagged, 1);
+        }
+    }
+}
+
+// ---- union-find over tree roots (lock-free, ECL-CC style: hook the larger index under the smaller) ----
+CC_DEV unsigned int cc_uf_find(unsigned int* parent, unsigned int x)
+{
+    unsigned int cur = cc_vload(parent + x);
+    if (cur != x)
+    {
+        unsigned int prev = x, next;
+        while (cur != (next = cc_vload(parent + cur)))
+        {
+            parent[prev] = next; // path halving; any ancestor is a valid parent
+            prev = cur;
+            cur = next;
+        }
+    }
+    return cur;
+}
+CC_DEV void cc_uf_union(unsigned int* parent, unsigned int a, unsigned int b)
+{
+    while (true)
+    {
+        a = cc_uf_find(parent, a);
+        b = cc_uf_find(parent, b);
+        if (a == b)
+            return;
+        if (a > b)
+        {
+            const unsigned int t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(parent + b, b, a) == b)
+            return;
+    }
+}
+
+// Speculative kernels run only while no column is flagged and the commit was not aborted.
+// guard 0: always run; 1: whole-push speculative commit (skip when any column is flagged, the commit was aborted
+// or an error was raised); 2: commit of a sub-range in the split path (skip only after an abort)
+CC_DEV bool cc_spec_ok(const CcDevState* st, int guard)
+{
+    if (st->ncols <= 0)
+        return false;
+    if (guard == 1)
+        return st->n_flagged == 0 && st->abort == 0 && st->error == 0;
+    if (guard == 2)
+        return st->abort == 0;
+    return true;
+}
+
+// =====================================================================================================
+// K3b  commit of probed columns [ci0, ci1]: (1) copy probe parents, initialise new roots and append them to the
+//      unfinished list; (2) resolve every point's tree root by pointer chasing with compression and add its
+//      contribution to the root (finished_at, width, tree_num_points: cpp:661-672); (3) apply tree<->tree
+//      links (cpp:675-696) to the union-find.
+// =====================================================================================================
+__global__ void k_snapshot(CcDevPtrs p, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int n = p.st->n_ulist;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int r = p.ulist[i];
+        p.sv_cparent[i] = p.cparent[r];
+        p.sv_tfinish[i] = p.tfinish[r];
+        p.sv_tmaxcol[i] = p.tmaxcol[r];
+        p.sv_tnpoints[i] = p.tnpoints[r];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        p.st->n_ulist_saved = n;
+        p.st->sv_n_clusters = p.st->n_clusters;
+        p.st->sv_n_cluster_points = p.st->n_cluster_points;
+    }
+}
+
+__global__ void k_restore(CcDevPtrs p)
+{
+    const int n = p.st->n_ulist_saved;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int r = p.ulist[i];
+        p.cparent[r] = p.sv_cparent[i];
+        p.tfinish[r] = p.sv_tfinish[i];
+        p.tmaxcol[r] = p.sv_tmaxcol[i];
+        p.tnpoints[r] = p.sv_tnpoints[i];
+    }
+}
+
+__global__ void k_restore_finish(CcDevPtrs p)
+{
+    p.st->n_ulist = p.st->n_ulist_saved;
+    p.st->abort = 0;
+    p.st->n_clusters = p.st->sv_n_clusters;
+    p.st->n_cluster_points = p.st->sv_n_cluster_points;
+}
+
+__global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int R = cfg.R;
+    if (ci1 < 0)
+        ci1 = p.st->ncols - 1;
+    const long long colbase = p.st->colbase;
+    const int total = (ci1 - ci0 + 1) * R;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        const int ci = ci0 + i / R, row = i % R;
+        const long long gcol = colbase + ci;
+        const unsigned int q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+        const unsigned int par = s_parent[static_cast<size_t>(ci) * R + row];
+        p.tparent[q] = par;
+        if (par == q) // new point tree (cpp:808-826)
+        {
+            p.cparent[q] = q;
+            p.tfinish[q] = cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q]));
+            p.tmaxcol[q] = gcol;
+            p.tnpoints[q] = 1;
+            p.tstate[q] = 0;
+            p.tid[q] = 0;
+            p.tslot[q] = -1;
+            const int pos = atomicAdd(&p.st->n_ulist, 1);
+            if (pos < p.cap_ulist)
+            {
+                p.ulist[pos] = q;
+                p.rootslot[q] = static_cast<unsigned int>(pos);
+            }
+            else
+                p.st->error = CC_DEV_LIST_OVERFLOW;
+        }
+    }
+}
+
+__global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int R = cfg.R;
+    if (ci1 < 0)
+        ci1 = p.st->ncols - 1;
+    const long long colbase = p.st->colbase;
+    const int total = (ci1 - ci0 + 1) * R;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        const int ci = ci0 + i / R, row = i % R;
+        const long long gcol = colbase + ci;
+        const unsigned int q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+        unsigned int r = cc_vload(p.tparent + q);
+        if (r == CC_NONE || r == q)
+            continue;
+        unsigned int n;
+        while ((n = cc_vload(p.tparent + r)) != r)
+            r = n;
+        p.tparent[q] = r;
+        atomicMax(p.tfinish + r, cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q])));
+        atomicMax(p.tmaxcol + r, gcol);
+        atomicAdd(p.tnpoints + r, 1u);
+    }
+}
+
+__global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int R = cfg.R;
+    if (ci1 < 0)
+        ci1 = p.st->ncols - 1;
+    int n = p.st->n_edges;
+    n = n < p.cap_edges ? n : p.cap_edges;
+    const int base_local = cc_local_col(p.st->colbase, cfg.ringcols);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    {
+        const unsigned int q = p.edge_a[e], o = p.edge_b[e];
+        int ci = static_cast<int>(q / R) - base_local;
+        if (ci < 0)
+            ci += cfg.ringcols;
+        if (ci < ci0 || ci > ci1)
+            continue;
+        const unsigned int ra = cc_vload(p.tparent + q), rb = cc_vload(p.tparent + o);
+        if (ra != rb)
+            cc_uf_union(p.cparent, ra, rb);
+    }
+}
+
+// =====================================================================================================
+// K3c  exact column-sequential association of ONE column (cpp:773-835 verbatim semantics, including refused
+//      associations and the stop at the first unpublished column). One thread; used only for columns the probe
+//      flagged and while a cluster is about to span a full rotation.
+// =====================================================================================================
+__global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0)
+        return;
+    const int R = cfg.R;
+    CcDevState* st = p.st;
+    const long long gcol = st->colbase + ci;
+    const int local = cc_local_col(gcol, cfg.ringcols);
+    const int first_local = cc_local_col(st->first_unpub, cfg.ringcols);
+    for (int row = 0; row < R; row++)
+    {
+        const unsigned int q = static_cast<unsigned int>(local) * R + row;
+        p.tparent[q] = CC_NONE;
+        p.visited[q] = 0;
+    }
+    for (int row = 0; row < R; row++)
+    {
+        const unsigned int q = static_cast<unsigned int>(local) * R + row;
+        const float4 a = p.assoc[q];
+        if (cc_isnan(a.x))
+            continue;
+        const float mad = p.mad[q];
+        const double my_finish = p.cont_az[q] + static_cast<double>(mad);
+        int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+        steps_back = steps_back < cfg.max_steps_row ? steps_back : cfg.max_steps_row;
+        unsigned int root = CC_NONE;
+        int visited = 0;
+        int other_col = local;
+        for (int back = 0; back <= steps_back; back++)
+        {
+            for (int dir = -1; dir <= 1; dir += 2)
+            {
+                if (dir == 1 && back == 0)
+                    continue;
+                int steps_v = (dir == 1 || back == 0) ? 1 : 0;
+                int orow = (dir == 1 || back == 0) ? row + dir : row;
+                while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
+                {
+                    const unsigned int o = static_cast<unsigned int>(other_col) * R + orow;
+                    const float4 b = p.assoc[o];
+                    visited++;
+                    if (fabsf(b.w - a.w) > mad)
+                        break;
+                    if (!cc_isnan(b.x))
+                    {
+                        const unsigned int ro = p.tparent[o];
+                        if (ro != CC_NONE && ro != root)
+                        {
+                            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                            if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq)
+                            {
+                                if (root == CC_NONE)
+                                {
+                                    // associatePointToPointTree cpp:643-673
+                                    const long long rootcol = p.slot_gcol[ro / R];
+                                    const unsigned int new_width = static_cast<unsigned int>(gcol - rootcol + 1);
+                                    if (new_width <= static_cast<unsigned int>(cfg.N) && p.tstate[ro] == 0)
+                                    {
+                                        root = ro;
+                                        p.tparent[q] = ro;
+                                        p.tmaxcol[ro] = gcol;
+                                        const unsigned long long f = cc_d2ord(my_finish);
+                                        if (f > p.tfinish[ro])
+                                            p.tfinish[ro] = f;
+                                        p.tnpoints[ro] += 1;
+                                    }
+                                }
+                                else if (p.tstate[root] == 0 && p.tstate[ro] == 0) // cpp:675-696
+                                    cc_uf_union(p.cparent, root, ro);
+                            }
+                        }
+                    }
+                    if (root != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps)
+                        break;
+                    orow += dir;
+                    steps_v++;
+                }
+            }
+            if (root != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+                break;
+            if (other_col == first_local)
+                break;
+            other_col--;
+            if (other_col < 0)
+                other_col += cfg.ringcols;
+        }
+        p.visited[q] = static_cast<unsigned short>(visited);
+        if (root == CC_NONE)
+        {
+            p.tparent[q] = q;
+            p.cparent[q] = q;
+            p.tfinish[q] = cc_d2ord(my_finish);
+            p.tmaxcol[q] = gcol;
+            p.tnpoints[q] = 1;
+            p.tstate[q] = 0;
+            p.tid[q] = 0;
+            p.tslot[q] = -1;
+            const int pos = st->n_ulist;
+            if (pos < p.cap_ulist)
+            {
+                p.ulist[pos] = q;
+                p.rootslot[q] = static_cast<unsigned int>(pos);
+                st->n_ulist = pos + 1;
+            }
+            else
+                st->error = CC_DEV_LIST_OVERFLOW;
+        }
+    }
+}
+
+// =====================================================================================================
+// K4  finish detection over the unfinished point trees for the passes of columns [c0, c1] (cpp:837-974) and
+//     the id / ring bookkeeping of the publish stage (cpp:1035-1083).
+//     spec = 1: c0..c1 is a whole range of columns processed at once; a component finishes at the first pass
+//               whose column minimum azimuth reaches the component's largest finished_at (binary search on the
+//               running maximum); anything that would need the reference's forced finish (cpp:909-919) aborts.
+//     spec = 0: c0 == c1, exact single pass including the forced finish.
+// =====================================================================================================
+__global__ void k_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    CcDevState* st = p.st;
+    if (ci1 < 0)
+        ci1 = st->ncols - 1;
+    const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
+    const long long gbase = st->first_unpub;
+    const long long c1 = st->colbase + ci1;
+    long long glen = c1 - gbase + 1;
+    if (glen > p.cap_G)
+        glen = p.cap_G;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < n; i += nt)
+    {
+        p.u_maxfinish[i] = 0ull;
+        p.u_mincol[i] = CC_COL_INF;
+        p.u_maxend[i] = -1;
+        p.u_np[i] = 0u;
+        p.u_finishcol[i] = CC_COL_INF;
+        p.u_cluster[i] = -1;
+    }
+    for (long long j = tid; j < glen; j += nt)
+        p.G[j] = -1;
+    if (tid == 0)
+    {
+        *p.n_new_ulist = 0;
+        st->seg_c0 = st->colbase + ci0;
+        st->seg_c1 = c1;
+        st->seg_first_unpub_old = st->first_unpub;
+        st->gbase = gbase;
+        if (c1 - gbase + 1 > p.cap_G)
+            st->error = CC_DEV_LIST_OVERFLOW;
+    }
+}
+
+__global__ void k_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int n = p.st->n_ulist < p.cap_ulist ? p.st->n_ulist : p.cap_ulist;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int root = p.ulist[i];
+        const unsigned int rep = cc_uf_find(p.cparent, root);
+        const int j = static_cast<int>(p.rootslot[rep]);
+        p.u_rep[i] = j;
+        atomicMax(p.u_maxfinish + j, p.tfinish[root]);
+        atomicMin(p.u_mincol + j, p.slot_gcol[root / cfg.R]);
+        atomicMax(p.u_maxend + j, p.tmaxcol[root] + 1);
+        atomicAdd(p.u_np + j, p.tnpoints[root]);
+    }
+}
+
+__global__ void k_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
+{
+    if (!cc_spec_ok(p.st, guard))
+        return;
+    const int spec = !exact;
+    CcDevState* st = p.st;
+    const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
+    const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        if (p.u_rep[i] != i)
+            continue;
+        const double F = cc_ord2d(p.u_maxfinish[i]);
+        const long long maxend = p.u_maxend[i], mincol = p.u_mincol[i];
+        long long finish_col = CC_COL_INF;
+        if (spec)
+        {
+            if (maxend - mincol >= cfg.N)
+            {
+                // a partial component could be force-finished from column mincol + N - 1 on (cpp:909-919)
+                atomicMin(&st->danger_col, mincol + cfg.N - 1);
+                st->abort = 1;
+                continue;
+            }
+            const long long lastcol = maxend - 1;
+            const long long s = lastcol > c0 ? lastcol : c0;
+            // first pass column c >= s with runmax(c) >= F
+            if (p.col_runmax[c1 - colbase] >= F)
+            {
+                long long lo = s, hi = c1;
+                while (lo < hi)
+                {
+                    const long long mid = (lo + hi) >> 1;
+                    if (p.col_runmax[mid - colbase] >= F)
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+                if (!(p.col_minaz[lo - colbase] >= F))
+                {
+                    // the running maximum was reached before the component was complete while this column's own
+                    // minimum is still behind it: needs the exact pass-by-pass rule
+                    st->abort = 1;
+                    atomicMin(&st->danger_col, lo);
+                    continue;
+                }
+                finish_col = lo;
+            }
+        }
+        else
+        {
+            const double min_az = p.col_minaz[c1 - colbase];
+            const bool unfinished = F > min_az;                 // cpp:884-885
+            const bool exceeds = (maxend - mincol) >= cfg.N;    // cpp:909-919
+            if (!unfinished || exceeds)
+                finish_col = c1;
+        }
+        if (finish_col != CC_COL_INF)
+        {
+            p.u_finishcol[i] = finish_col;
+            const unsigned int np = p.u_np[i];
+            if (np > 5) // cpp:936-940
+            {
+                const int slot = atomicAdd(&st->n_clusters, 1);
+                const int off = atomicAdd(&st->n_cluster_points, static_cast<int>(np));
+                if (slot < p.cap_clusters && off + static_cast<int>(np) <= p.cap_cluster_points)
+                {
+                    CcCluster c;
+                    c.id = st->cluster_counter + static_cast<unsigned long long>(slot);
+                    c.min_stamp = ~0ull;
+                    c.max_stamp = 0ull;
+                    c.finish_col = finish_col;
+                    c.min_col = mincol;
+                    c.max_col = maxend - 1;
+                    c.num_points = np;
+                    c.point_offset = static_cast<unsigned int>(off);
+                    c.cursor = 0;
+                    c.pad_ = 0;
+                    p.clusters[slot] = c;
+                    p.u_cluster[i] = slot;
+                }
+                else
+                    st->error = CC_DEV_LIST_OVERFLOW;
+            }
+        }
+    }
+}
+
+__global__ void k_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    CcDevState* st = p.st;
+    const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
+    const long long gbase = st->gbase;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int j = p.u_rep[i];
+        const long long fc = p.u_finishcol[j];
+        const unsigned int root = p.ulist[i];
+        const long long gi = p.slot_gcol[root / cfg.R] - gbase;
+        if (fc != CC_COL_INF)
+        {
+            const int slot = p.u_cluster[j];
+            p.tstate[root] = 1u + seq;
+            p.tslot[root] = slot;
+            p.tid[root] = slot >= 0 ? static_cast<unsigned int>(st->cluster_counter + static_cast<unsigned long long>(slot)) : 0u;
+            if (gi >= 0 && gi < p.cap_G)
+                atomicMax(p.G + gi, fc);
+        }
+        else
+        {
+            if (gi >= 0 && gi < p.cap_G)
+                atomicMax(p.G + gi, CC_COL_INF);
+            const int pos = atomicAdd(p.n_new_ulist, 1);
+            p.ulist_new[pos] = root;
+        }
+    }
+}
+
+__global__ void k_fin_copyback(CcDevPtrs p, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const int n = *p.n_new_ulist;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int root = p.ulist_new[i];
+        p.ulist[i] = root;
+        p.rootslot[root] = static_cast<unsigned int>(i);
+    }
+}
+
+// per column: sc_first_unpublished_global_column_index after its pass = the smallest root column among the trees
+// that were still unfinished when the pass started (cpp:943-959), or column + 1. G[r] = last column at which
+// some tree rooted in column gbase + r is unfinished; with PG = prefix max of G, the answer for column c is the
+// first r with PG[r] >= c. Single block.
+__global__ void k_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    if (blockIdx.x != 0)
+        return;
+    CC_SMEM(smem);
+    long long* part = reinterpret_cast<long long*>(smem);
+    CcDevState* st = p.st;
+    const long long gbase = st->gbase, c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase;
+    long long glen = c1 - gbase + 1;
+    if (glen > p.cap_G)
+        glen = p.cap_G;
+    const int T = blockDim.x, t = threadIdx.x;
+    const long long chunk = (glen + T - 1) / T;
+    const long long lo = t * chunk, hi = (lo + chunk < glen) ? lo + chunk : glen;
+    long long m = -1;
+    for (long long j = lo; j < hi; j++)
+        m = p.G[j] > m ? p.G[j] : m;
+    part[t] = m;
+    __syncthreads();
+    long long pre = -1;
+    for (int j = 0; j < t; j++)
+        pre = part[j] > pre ? part[j] : pre;
+    for (long long j = lo; j < hi; j++)
+    {
+        pre = p.G[j] > pre ? p.G[j] : pre;
+        p.G[j] = pre;
+    }
+    __syncthreads();
+    for (long long c = c0 + t; c <= c1; c += T)
+    {
+        // first r in [0, c - gbase] with PG[r] >= c, else c + 1 - gbase
+        long long a = 0, b = c - gbase + 1;
+        if (b > glen)
+            b = glen;
+        while (a < b)
+        {
+            const long long mid = (a + b) >> 1;
+            if (p.G[mid] >= c)
+                b = mid;
+            else
+                a = mid + 1;
+        }
+        long long fu = gbase + a;
+        if (fu > c + 1)
+            fu = c + 1;
+        p.col_first_unpub[c - colbase] = fu;
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+        const long long fu = p.col_first_unpub[c1 - colbase];
+        if (fu < st->first_unpub)
+        {
+            st->error = CC_DEV_RING_START_DECREASED; // cpp:1072-1075
+            st->err_a = fu;
+            st->err_b = st->first_unpub;
+        }
+        st->first_unpub = fu;
+        st->ring_start = fu - cfg.N > 0 ? fu - cfg.N : 0; // cpp:1079
+        st->runmax_carry = p.col_runmax[c1 - colbase];
+        st->n_ulist = *p.n_new_ulist;
+    }
+}
+
+// Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
+// host needs for the finished-cluster callback (cpp:1007-1028).
+__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+{
+    if (!cc_spec_ok(p.st, spec))
+        return;
+    const CcDevState* st = p.st;
+    const int R = cfg.R;
+    const long long gbase = st->gbase, c1 = st->seg_c1;
+    const long long total = (c1 - gbase + 1) * R;
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long gcol = gbase + i / R;
+        const int row = static_cast<int>(i % R);
+        const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+        if (p.slot_gcol[cell / R] != gcol)
+            continue;
+        const unsigned int root = p.tparent[cell];
+        if (root == CC_NONE)
+            continue;
+        if (p.tstate[root] != 1u + seq)
+            continue;
+        const int slot = p.tslot[root];
+        if (slot < 0)
+            continue;
+        p.cid[cell] = p.tid[root];
+        CcCluster* c = p.clusters + slot;
+        const unsigned int pos = atomicAdd(&c->cursor, 1u);
+        if (pos < c->num_points)
+        {
+            CcClusterPoint cp;
+            cp.gcol = gcol;
+            cp.row = row;
+            cp.pad_ = 0;
+            p.cluster_points[c->point_offset + pos] = cp;
+        }
+        const unsigned long long stamp = p.stamp[cell];
+        atomicMin(&c->min_stamp, stamp);
+        atomicMax(&c->max_stamp, stamp);
+    }
+}
+
+// =====================================================================================================
+// K5  clearColumns (cpp:1094-1145) for the columns that left the ring in this push.
+// =====================================================================================================
+// mode 0: explicit range [from, to) (reset); mode 1: the range the PREVIOUS push retired. Recycling is deferred by
+// one push so that every column a push reports through a finished-column event can still be read by the caller
+// after the push returns (the reference's callbacks read range_image_ before clearColumns runs, cpp:1087-1091).
+__global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
+{
+    CcDevState* st = p.st;
+    if (mode)
+    {
+        from = st->clear_from;
+        to = st->clear_to;
+    }
+    if (from < 0)
+        from = 0;
+    if (to <= from)
+        return;
+    const int R = cfg.R;
+    const long long total = (to - from) * R;
+    const float nanv = cc_nanf();
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long gcol = from + i / R;
+        const int row = static_cast<int>(i % R);
+        const int local = cc_local_col(gcol, cfg.ringcols);
+        const size_t cell = static_cast<size_t>(local) * R + row;
+        p.pos[cell] = make_float4(nanv, nanv, nanv, nanv);
+        p.azimuth[cell] = nanv;
+        p.incl[cell] = nanv;
+        p.cont_az[cell] = __longlong_as_double(0x7ff8000000000000LL);
+        p.lab[cell] = make_uchar4(CC_GP_UNKNOWN, CC_WHITE, 0, 0);
+        p.stamp[cell] = 0ull;
+        p.guid[cell] = ~0ull;
+        p.assoc[cell] = make_float4(nanv, nanv, nanv, nanv);
+        p.mad[cell] = 0.f;
+        p.tparent[cell] = CC_NONE;
+        p.cid[cell] = 0u;
+        p.visited[cell] = 0;
+        p.tstate[cell] = 0u;
+        if (row == 0)
+            p.slot_gcol[local] = -1;
+    }
+}
+
+// end of a push: remember the range of columns that left the ring (recycled at the start of the next push) and
+// advance sc_cluster_counter_ (cpp:939) by the ids handed out. guard as in cc_spec_ok.
+__global__ void k_push_done(CcDevPtrs p, int guard)
+{
+    CcDevState* st = p.st;
+    if (guard == 1 && (st->error != 0 || st->n_flagged != 0 || st->abort != 0))
+        return;
+    if (st->ring_start > st->clear_from)
+        st->clear_to = st->ring_start;
+    st->cluster_counter += static_cast<unsigned long long>(st->n_clusters);
+}
+
+// ---- device math self-test (bit equality with the host libm) ----
+__global__ void k_selftest_math(int op, int n, const float* a, const float* b, float* out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        if (op == 0)
+            out[i] = ccm::atan2f_glibc(a[i], b[i]);
+        else if (op == 1)
+            out[i] = ccm::asinf_glibc(a[i]);
+        else
+            out[i] = ccm::atanf_glibc(a[i]);
+    }
+}
+
+#endif

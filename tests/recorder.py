@@ -1,0 +1,80 @@
+"""Runs a firing stream through continuous_clustering_b200.ContinuousClustering and records the same things the
+oracle's recording driver (oracle/cc_driver.h) records, so tests/parity.py can compare them."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import drvlib
+
+_MAP = {  # drv_cell_t field -> cc_read_columns field
+    "continuous_azimuth_angle": "continuous_azimuth_angle", "global_column_index": "global_column_index",
+    "globally_unique_point_index": "globally_unique_point_index", "stamp": "stamp", "firing_index": "firing_index",
+    "id": "id", "tree_root_gcol": "tree_root_gcol", "distance": "distance", "azimuth_angle": "azimuth_angle",
+    "inclination_angle": "inclination_angle", "tree_root_row": "tree_root_row", "intensity": "intensity",
+    "ground_point_label": "ground_point_label", "debug_ground_point_label": "debug_ground_point_label",
+    "is_ignored": "is_ignored",
+}
+
+
+def _to_cells(cols):
+    out = np.zeros(cols.shape, dtype=drvlib.CELL_DTYPE)
+    for k, v in _MAP.items():
+        out[k] = cols[v]
+    out["x"], out["y"], out["z"] = cols["xyz"][..., 0], cols["xyz"][..., 1], cols["xyz"][..., 2]
+    return out
+
+
+def record(cc, pts, poses, chunk):
+    """Feeds the stream in pushes of `chunk` firings; returns the dict layout of tests/parity.record()."""
+    rows = pts.shape[1]
+    events, gcols, gcells, ccols, ccells, clusters, cpoints = [], [], [], [], [], [], []
+    n_events = 0
+    used_exact = 0
+    for a in range(0, pts.shape[0], chunk):
+        res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
+        used_exact += int(res.info.used_exact_path)
+        ev = res.events
+        if len(ev) == 0:
+            continue
+        g = ev[ev["ground_points_only"] == 1]
+        if len(g):
+            lo, hi = int(g["from_gcol"].min()), int(g["to_gcol"].max())
+            cells = _to_cells(cc.read_columns(lo, hi))
+            gcols.append(np.arange(lo, hi + 1))
+            gcells.append(cells)
+        c = ev[(ev["ground_points_only"] == 0) & (ev["to_gcol"] >= ev["from_gcol"])]
+        if len(c):
+            lo, hi = int(c["from_gcol"].min()), int(c["to_gcol"].max())
+            cells = _to_cells(cc.read_columns(lo, hi))
+            ccols.append(np.arange(lo, hi + 1))
+            ccells.append(cells)
+        # finished clusters the reference would hand to the callback (> 20 points, cpp:1023), with the number of
+        # column events delivered before each
+        nxt = 0
+        for i, e in enumerate(ev):
+            while nxt < int(e["n_clusters_before"]):
+                cl = res.clusters[nxt]
+                nxt += 1
+                if cl["num_points"] > 20:
+                    p = res.cluster_points[int(cl["point_offset"]) : int(cl["point_offset"]) + int(cl["num_points"])]
+                    off = sum(len(x) for x in cpoints)
+                    rec = np.zeros(1, dtype=drvlib.CLUSTER_DTYPE)
+                    rec["stamp"], rec["id"], rec["point_offset"], rec["num_points"] = cl["stamp"], cl["id"], off, len(p)
+                    rec["event_index"] = n_events + i
+                    clusters.append(rec)
+                    q = np.zeros(len(p), dtype=drvlib.CLUSTER_POINT_DTYPE)
+                    q["gcol"], q["row"] = p["gcol"], p["row"]
+                    cpoints.append(q)
+        n_events += len(ev)
+        events.append(ev)
+
+    def cat(xs, dt, shape=(0,)):
+        return np.concatenate(xs) if xs else np.zeros(shape, dtype=dt)
+
+    return dict(
+        events=cat(events, drvlib.EVENT_DTYPE),
+        ground_cols=cat(gcols, np.int64), ground_cells=cat(gcells, drvlib.CELL_DTYPE, (0, rows)),
+        cluster_cols=cat(ccols, np.int64), cluster_cells=cat(ccells, drvlib.CELL_DTYPE, (0, rows)),
+        clusters=cat(clusters, drvlib.CLUSTER_DTYPE), cluster_points=cat(cpoints, drvlib.CLUSTER_POINT_DTYPE),
+        reset_required=cc.resetRequired(), used_exact_path=used_exact,
+    )
