@@ -291,6 +291,18 @@ class ContinuousClustering:
             out[n] = bufs[n]
         return out
 
+    def set_kernel_timing(self, enable: bool):
+        self._check(self._L.cc_set_kernel_timing(self._h, int(enable)))
+
+    def kernel_timings(self):
+        """[(kernel name, milliseconds)] of the last push, launch order (needs set_kernel_timing(True))."""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = C.c_int(0)
+        self._check(self._L.cc_get_kernel_timings(self._h, names, 4096, ms, 64, C.byref(n)))
+        parts = names.value.decode().split(";")[: n.value]
+        return [(parts[i], float(ms[i])) for i in range(n.value)]
+
     @property
     def total_launches(self) -> int:
         return int(self._L.cc_total_launches(self._h))

@@ -60,7 +60,15 @@ struct cc_handle
     std::vector<long long> h_first_unpub;
     std::vector<unsigned char> h_flags;
     std::vector<CcCluster> h_clusters;
+    // per-kernel timing
+    bool timing{false};
+    int n_timed{0};
+    std::vector<cudaEvent_t> tev;
+    std::vector<const char*> tnames;
 };
+
+static int timing_begin(cc_handle* h, const char* name);
+static void timing_end(cc_handle* h, int i);
 
 #define CC_CHECK(h, expr)                                                                                              \
     do                                                                                                                 \
@@ -76,9 +84,27 @@ struct cc_handle
 #define CC_RUN(h, kernel, grid, block, smem, ...)                                                                      \
     do                                                                                                                 \
     {                                                                                                                  \
+        const int cc_t_ = timing_begin((h), #kernel);                                                                  \
         CC_LAUNCH(kernel, grid, block, smem, (h)->stream, __VA_ARGS__);                                                \
+        timing_end((h), cc_t_);                                                                                        \
         (h)->launches++;                                                                                               \
     } while (0)
+
+// optional per-kernel CUDA-event timing of one push (cc_set_kernel_timing); off by default
+static int timing_begin(cc_handle* h, const char* name)
+{
+    if (!h->timing || h->n_timed >= static_cast<int>(h->tev.size()) / 2)
+        return -1;
+    const int i = h->n_timed++;
+    h->tnames[i] = name;
+    cudaEventRecord(h->tev[2 * i], h->stream);
+    return i;
+}
+static void timing_end(cc_handle* h, int i)
+{
+    if (i >= 0)
+        cudaEventRecord(h->tev[2 * i + 1], h->stream);
+}
 
 static void free_list(std::vector<void*>& v)
 {
@@ -235,6 +261,8 @@ void cc_destroy(cc_handle_t* h)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
         cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->tev)
+        cudaEventDestroy(e);
     if (h->stream)
         cudaStreamDestroy(h->stream);
     delete h;
@@ -592,6 +620,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     CcDevCfg cfg;
     fill_devcfg(h, cfg);
     h->launches_at_push_start = h->launches;
+    h->n_timed = 0;
     h->events.clear();
     h->clusters.clear();
     h->cluster_points.clear();
@@ -952,6 +981,48 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         if (f->tree_root_row)
             f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
     }
+    return CC_OK;
+}
+
+cc_status_t cc_set_kernel_timing(cc_handle_t* h, int enable)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    if (enable && h->tev.empty())
+    {
+        h->tev.resize(2 * 64);
+        h->tnames.resize(64);
+        for (cudaEvent_t& e : h->tev)
+            CC_CHECK(h, cudaEventCreate(&e));
+    }
+    h->timing = enable != 0;
+    h->n_timed = 0;
+    return CC_OK;
+}
+
+cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_cap, float* ms, int cap, int* n_out)
+{
+    if (!h || !n_out)
+        return CC_ERR_INVALID_ARGUMENT;
+    std::string all;
+    int n = 0;
+    for (int i = 0; i < h->n_timed && i < cap; i++)
+    {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->tev[2 * i], h->tev[2 * i + 1]) != cudaSuccess)
+            t = -1.f;
+        ms[i] = t;
+        all += h->tnames[i];
+        all += ';';
+        n++;
+    }
+    if (names && names_cap > 0)
+    {
+        std::strncpy(names, all.c_str(), static_cast<size_t>(names_cap) - 1);
+        names[names_cap - 1] = 0;
+    }
+    *n_out = n;
     return CC_OK;
 }
 

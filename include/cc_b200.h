@@ -245,6 +245,12 @@ CC_API void* cc_stream(const cc_handle_t* h);
 /* Total kernels launched by this handle so far. */
 CC_API uint64_t cc_total_launches(const cc_handle_t* h);
 
+/* Optional per-kernel timing (bench.py's roofline leg): when enabled, every kernel launch of the next pushes is
+ * bracketed by CUDA events on the handle's stream; cc_get_kernel_timings returns, for the LAST push, the kernel
+ * names (';'-separated, launch order) and their durations in milliseconds. */
+CC_API cc_status_t cc_set_kernel_timing(cc_handle_t* h, int enable);
+CC_API cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_cap, float* ms, int cap, int* n_out);
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */
