@@ -3,7 +3,9 @@
 #   make oracle  oracle/libcc_oracle.so (+ oracle/_ref/libcc_ref.so where /root/reference exists)
 #   make emu     tests/emu/libcc_b200_emu_test.so              same sources, g++ -DCC_EMU, CPU tests only
 NVCC ?= /usr/local/cuda/bin/nvcc
-CXX ?= g++
+# the image's $CXX (/opt/gcc/bin/g++) links libstdc++ statically, which must not be mixed into a Python process that
+# already carries the system libstdc++ (crashes inside iostream locale code): always use the plain system g++
+CXX := $(if $(wildcard /usr/bin/g++),/usr/bin/g++,g++)
 CSRC := continuous_clustering_b200/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
            -Xcompiler -fPIC,-fvisibility=hidden -shared

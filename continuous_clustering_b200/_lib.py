@@ -115,6 +115,7 @@ EXPORTED_SYMBOLS = [
     "cc_push_firings_device", "cc_get_batch_info", "cc_get_column_events", "cc_get_clusters", "cc_get_cluster_points",
     "cc_read_columns", "cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns", "cc_stream",
     "cc_total_launches", "cc_selftest_math", "cc_set_kernel_timing", "cc_get_kernel_timings",
+    "cc_debug_flag_columns",
 ]
 
 
@@ -148,6 +149,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_total_launches.restype = C.c_uint64
     lib.cc_selftest_math.argtypes = [i32, i32, i32, vp, vp, vp]
     lib.cc_set_kernel_timing.argtypes = [vp, i32]
+    lib.cc_debug_flag_columns.argtypes = [vp, i32]
     lib.cc_get_kernel_timings.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32)]
     return lib
 

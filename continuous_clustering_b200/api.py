@@ -291,6 +291,10 @@ class ContinuousClustering:
             out[n] = bufs[n]
         return out
 
+    def debug_flag_columns(self, period: int):
+        """Test hook (cc_debug_flag_columns): force every n-th column through the exact column-sequential path."""
+        self._check(self._L.cc_debug_flag_columns(self._h, int(period)))
+
     def set_kernel_timing(self, enable: bool):
         self._check(self._L.cc_set_kernel_timing(self._h, int(enable)))
 

@@ -38,6 +38,7 @@ struct cc_handle
     int max_firings{4096};
     int maxcols{0};
     int gap_rows{-1};
+    int debug_flag_period{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
     unsigned char* d_raw{nullptr};
@@ -166,6 +167,7 @@ static void fill_devcfg(const cc_handle* h, CcDevCfg& c)
     c.use_last_stamp = s.use_last_point_for_cluster_stamp != 0;
     c.nth = s.cluster_point_trees_every_nth_column > 0 ? s.cluster_point_trees_every_nth_column : 1;
     std::memcpy(c.robot_from_sensor, h->robot_from_sensor, sizeof(c.robot_from_sensor));
+    c.debug_flag_period = h->debug_flag_period;
     c.height_sensor_to_ground = -static_cast<float>(h->robot_from_sensor[11]) + s.height_ref_to_ground_; // cpp:302-303
 }
 
@@ -334,6 +336,12 @@ uint64_t cc_total_launches(const cc_handle_t* h)
     return h ? h->launches : 0;
 }
 
+static int scan_smem_bytes(int R)
+{
+    return CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(long long)) +
+           2 * CC_K1_CHUNK * R * static_cast<int>(sizeof(int) + sizeof(float));
+}
+
 static int grid_for(const cc_handle* h, long long work, int block)
 {
     long long g = (work + block - 1) / block;
@@ -348,7 +356,7 @@ static int grid_for(const cc_handle* h, long long work, int block)
 // ContinuousClustering::reset cpp:11-64
 cc_status_t cc_reset(cc_handle_t* h, int num_rows)
 {
-    if (!h || num_rows <= 0 || num_rows > 1024)
+    if (!h || num_rows <= 0 || num_rows > 256)
         return CC_ERR_INVALID_ARGUMENT;
     CC_CHECK(h, cudaSetDevice(h->device));
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -395,10 +403,11 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.slot_gcol, static_cast<size_t>(h->ringcols)));
         CC_CHECK(h, dev_alloc(h, L, &d.rowmax, static_cast<size_t>(h->R)));
         CC_CHECK(h, dev_alloc(h, L, &d.s_pos, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_dist, stage + static_cast<size_t>(CC_K1_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.s_az, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incl, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incaz, stage));
-        CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
         CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
@@ -504,7 +513,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     std::memset(&h->info, 0, sizeof(h->info));
 #ifndef CC_EMU
     {
-        const int smem = CC_K1_WINDOW * h->R * static_cast<int>(sizeof(float)) + h->R * static_cast<int>(sizeof(long long));
+        const int smem = scan_smem_bytes(h->R);
         if (smem > 48 * 1024)
             CC_CHECK(h, cudaFuncSetAttribute(k_insert_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
@@ -633,7 +642,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     CC_RUN(h, k_clear, h->sm_count * 8, 256, 0, cfg, h->d, 0LL, 0LL, 1); // columns retired by the previous push
     const long long pts = static_cast<long long>(n) * R;
     CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
-    const int scan_smem = CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(long long));
+    const int scan_smem = scan_smem_bytes(R);
     CC_RUN(h, k_insert_scan, 1, CC_WARP, scan_smem, cfg, h->d, n);
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 
@@ -981,6 +990,14 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         if (f->tree_root_row)
             f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
     }
+    return CC_OK;
+}
+
+cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period)
+{
+    if (!h || period < 0)
+        return CC_ERR_INVALID_ARGUMENT;
+    h->debug_flag_period = period;
     return CC_OK;
 }
 

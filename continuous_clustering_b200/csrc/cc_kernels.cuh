@@ -17,6 +17,10 @@
 
 #include <math.h>
 
+#ifndef CC_EMU
+#include <cuda_pipeline.h>
+#endif
+
 #include "cc_math.cuh"
 #include "cc_types.h"
 
@@ -96,6 +100,39 @@ CC_DEV void cc_iso_mul(const double* a, const double* b, double* r)
     }
 }
 
+// exclusive block scan (Hillis-Steele in shared memory) with an ordered combine op(earlier, later)
+struct CcOpLastValid
+{
+    CC_DEV float operator()(float a, float b) const { return b != b ? a : b; }
+};
+struct CcOpMaxF64
+{
+    CC_DEV double operator()(double a, double b) const { return a > b ? a : b; }
+};
+struct CcOpMaxI64
+{
+    CC_DEV long long operator()(long long a, long long b) const { return a > b ? a : b; }
+};
+template<typename T, typename Op>
+CC_DEV T cc_block_exclusive_scan(T* sm, T v, T identity, Op op)
+{
+    const int t = threadIdx.x, n = blockDim.x;
+    sm[t] = v;
+    __syncthreads();
+    for (int off = 1; off < n; off <<= 1)
+    {
+        T x = sm[t];
+        if (t >= off)
+            x = op(sm[t - off], x);
+        __syncthreads();
+        sm[t] = x;
+        __syncthreads();
+    }
+    const T excl = t > 0 ? sm[t - 1] : identity;
+    __syncthreads();
+    return excl;
+}
+
 CC_DEV int cc_local_col(long long g, int ringcols)
 {
     return static_cast<int>(g % ringcols);
@@ -129,6 +166,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         const int cwr = static_cast<int>(ccm::div_rn(incaz, cfg.width));
         const float dist = static_cast<float>(sqrt(rx * rx + (ry * ry + rz * rz)));
         p.s_pos[idx] = make_float4(static_cast<float>(po[0]), static_cast<float>(po[1]), static_cast<float>(po[2]), dist);
+        p.s_dist[idx] = dist;
         p.s_az[idx] = az;
         p.s_incaz[idx] = incaz;
         p.s_incl[idx] = ccm::asinf_glibc(ccm::div_rn(static_cast<float>(rz), dist));
@@ -153,8 +191,29 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
     float* wdist = reinterpret_cast<float*>(smem);
     long long* rmx = reinterpret_cast<long long*>(smem + static_cast<size_t>(W) * R * sizeof(float));
+    // double-buffered staging of the per-point scan inputs (column-in-rotation, distance) for CC_K1_CHUNK firings:
+    // filled with cp.async one chunk ahead so the sequential loop never waits on HBM/L2
+    const int C = CC_K1_CHUNK;
+    int* st_cwr = reinterpret_cast<int*>(rmx + R);
+    float* st_dist = reinterpret_cast<float*>(st_cwr + 2 * C * R);
     const int lane = threadIdx.x;
     CcDevState* st = p.st;
+    const int n_chunks = (n_firings + C - 1) / C;
+    auto prefetch = [&](int chunk)
+    {
+        if (chunk < n_chunks)
+        {
+            const int buf = chunk & 1;
+            const size_t src = static_cast<size_t>(chunk) * C * R;
+            for (int i = lane * 4; i < C * R; i += CC_WARP * 4)
+            {
+                __pipeline_memcpy_async(st_cwr + buf * C * R + i, p.s_cwr + src + i, 16);
+                __pipeline_memcpy_async(st_dist + buf * C * R + i, p.s_dist + src + i, 16);
+            }
+        }
+        __pipeline_commit();
+    };
+    prefetch(0);
 
     for (int row = lane; row < R; row += CC_WARP)
     {
@@ -178,14 +237,21 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 
     for (int k = 0; k < n_firings; k++)
     {
+        if ((k % C) == 0)
+        {
+            prefetch(k / C + 1);
+            __pipeline_wait_prior(1);
+            __syncwarp();
+        }
+        const int sbase = ((k / C) & 1) * C * R + (k % C) * R;
         int lmin = 0x7fffffff, lmax = -0x7fffffff - 1; // relative to P
         for (int row = lane; row < R; row += CC_WARP)
         {
             const int idx = k * R + row;
-            const int cw = p.s_cwr[idx];
+            const int cw = st_cwr[sbase + row];
             if (cw == CC_INVALID_CWR)
                 continue;
-            const float d = p.s_pos[idx].w;
+            const float d = st_dist[sbase + row];
             long long g = prev_rot * N + cw;
             const int diff = cw - pc;
             int rotoff = 0;
@@ -399,16 +465,10 @@ __global__ void k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
         if (!cc_isnan(d))
             last = d;
     }
-    lastv[t] = last;
-    __syncthreads();
     // exclusive "last valid" prefix over threads, seeded with the carried state
-    float pre = p.gap_state[row];
-    for (int j = 0; j < t; j++)
-    {
-        const float v = lastv[j];
-        if (!cc_isnan(v))
-            pre = v;
-    }
+    float pre = cc_block_exclusive_scan(lastv, last, cc_nanf(), CcOpLastValid());
+    if (cc_isnan(pre))
+        pre = p.gap_state[row];
     float cur = pre;
     for (int ci = lo; ci < hi; ci++)
     {
@@ -699,11 +759,9 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p)
         const double v = p.col_minaz[ci];
         m = v > m ? v : m;
     }
-    part[t] = m;
-    __syncthreads();
-    double pre = p.st->runmax_carry;
-    for (int j = 0; j < t; j++)
-        pre = part[j] > pre ? part[j] : pre;
+    double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
+    const double carry = p.st->runmax_carry;
+    pre = carry > pre ? carry : pre;
     for (int ci = lo; ci < hi; ci++)
     {
         const double v = p.col_minaz[ci];
@@ -808,6 +866,8 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
         }
         s_parent[idx] = first == CC_NONE ? q : first;
         p.visited[q] = static_cast<unsigned short>(visited);
+        if (cfg.debug_flag_period > 0 && ((colbase + ci) % cfg.debug_flag_period) == 0)
+            flagged = true;
         if (flagged)
         {
             p.col_flag[ci] = 1;
@@ -1335,11 +1395,7 @@ __global__ void k_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
     long long m = -1;
     for (long long j = lo; j < hi; j++)
         m = p.G[j] > m ? p.G[j] : m;
-    part[t] = m;
-    __syncthreads();
-    long long pre = -1;
-    for (int j = 0; j < t; j++)
-        pre = part[j] > pre ? part[j] : pre;
+    long long pre = cc_block_exclusive_scan(part, m, -1LL, CcOpMaxI64());
     for (long long j = lo; j < hi; j++)
     {
         pre = p.G[j] > pre ? p.G[j] : pre;

@@ -35,6 +35,7 @@ enum : uint8_t
 #define CC_NONE 0xffffffffu
 #define CC_INVALID_CWR (-2147483647 - 1)
 #define CC_COL_INF 0x3fffffffffffffffLL
+#define CC_K1_CHUNK 32  /* firings staged per cp.async group by the insertion scan */
 #define CC_K1_WINDOW 64 /* columns of per-row occupancy history kept in shared memory by the insertion scan */
 
 // device-detected conditions (CcDevState::error)
@@ -60,7 +61,7 @@ struct CcDevCfg // plain copy of cc_config_t + derived values (cpp:13-17, 80, 30
     float max_distance, max_distance_sq;
     int max_steps_row, max_steps_col, stop_enabled, stop_min_steps, chessboard, incl_rule, use_last_stamp, nth;
     float height_sensor_to_ground;
-    int pad_;
+    int debug_flag_period; // test hook: treat every n-th column as flagged (0 = off)
     double robot_from_sensor[12];
 };
 
@@ -144,6 +145,7 @@ struct CcDevPtrs
     const void* raw;      // cc_raw_point_t[n * R]
     const double* poses;  // [n][12]
     float4* s_pos;        // odom x, y, z, distance
+    float* s_dist;        // distance again, contiguous (scan input)
     float* s_az;
     float* s_incl;
     float* s_incaz;

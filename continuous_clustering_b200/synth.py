@@ -84,18 +84,19 @@ def spec(name: str) -> StreamSpec:
     raise ValueError(f"unknown stream spec {name!r}")
 
 
-def make_scene(seed: int, n_boxes: int = 150, extent: float = 60.0):
+def make_scene(seed: int, n_boxes: int = 150, extent: float = 60.0, min_dist: float = 5.0,
+               height_range=(0.5, 3.0)):
     """150 axis-aligned boxes standing on the ground plane, none closer than 5 m to the origin."""
     rng = np.random.RandomState(seed)  # MT19937
     boxes = []
     while len(boxes) < n_boxes:
         cx, cy = rng.uniform(-extent, extent, 2)
-        if np.hypot(cx, cy) < 5.0:
+        if np.hypot(cx, cy) < min_dist:
             continue
         hx, hy = rng.uniform(0.3, 2.5, 2)
-        height = rng.uniform(0.5, 3.0)
+        height = rng.uniform(*height_range)
         boxes.append((cx - hx, cx + hx, cy - hy, cy + hy, 0.0, height))
-    return np.asarray(boxes, dtype=np.float64)  # z relative to the ground plane
+    return np.asarray(boxes, dtype=np.float64).reshape(-1, 6)  # z relative to the ground plane
 
 
 def _rot_x(a):
@@ -120,6 +121,11 @@ def make_stream(
     n_boxes: int = 150,
     dropout: float = 0.0,
     chunk: int = 128,
+    extent: float = 60.0,
+    min_box_dist: float = 5.0,
+    box_height_range=(0.5, 3.0),
+    wall_radius: float | None = None,
+    wall_height: float = 2.5,
 ):
     """Returns (points[n_firings, rows] of RAW_POINT_DTYPE, poses[n_firings, 12] float64, spec).
 
@@ -128,13 +134,16 @@ def make_stream(
     not straddle it (cpp:252-261). Stamps are t0 + k * T_rot / N nanoseconds; intensity 100;
     globally_unique_point_index = k * rows + row. `moving` drives the sensor at 10 m/s with 0.2 rad/s yaw
     so the double-precision rigid transform (cpp:129-138) is exercised; otherwise the pose is identity.
-    `dropout` randomly replaces that fraction of returns by NaN (missing returns).
+    `dropout` randomly replaces that fraction of returns by NaN (missing returns). `wall_radius` adds a closed
+    cylindrical wall around the sensor start position (a cluster that spans a full rotation: the reference's forced
+    finish, cpp:909-919); `min_box_dist` / `box_height_range` / `extent` shape the box scene (tall, close boxes
+    give steep inclinations: associations the reference refuses, cpp:654-659).
     """
     sp = spec(spec_name)
     rows, ncols = sp.rows, sp.num_columns
     if n_firings is None:
         n_firings = int(round(n_rotations * ncols))
-    boxes = make_scene(seed, n_boxes)
+    boxes = make_scene(seed, n_boxes, extent, min_box_dist, box_height_range)
     rng = np.random.RandomState(seed + 1)
     t_rot_ns = 1e9 / sp.rotation_hz
     t0 = 1_000_000_000
@@ -189,11 +198,25 @@ def make_stream(
             inv = 1.0 / d_w  # (f,r,3)
             ta = (lo[None, None] - o_w[:, :, None, :]) * inv[:, :, None, :]  # (f,r,b,3)
             tb = (hi[None, None] - o_w[:, :, None, :]) * inv[:, :, None, :]
-        tmin = np.nanmax(np.minimum(ta, tb), axis=-1)
-        tmax = np.nanmin(np.maximum(ta, tb), axis=-1)
-        ok = (tmax >= tmin) & (tmin > 0.5)
-        tbox = np.where(ok, tmin, np.inf).min(axis=-1)
-        best = np.minimum(best, tbox)
+        if boxes.shape[0]:
+            tmin = np.nanmax(np.minimum(ta, tb), axis=-1)
+            tmax = np.nanmin(np.maximum(ta, tb), axis=-1)
+            ok = (tmax >= tmin) & (tmin > 0.5)
+            tbox = np.where(ok, tmin, np.inf).min(axis=-1)
+            best = np.minimum(best, tbox)
+        if wall_radius is not None:
+            # vertical cylinder x^2 + y^2 = r^2 around the odom origin, from the ground up to wall_height
+            dx, dy = d_w[..., 0], d_w[..., 1]
+            ox, oy = o_w[..., 0], o_w[..., 1]
+            a = dx * dx + dy * dy
+            b = 2 * (ox * dx + oy * dy)
+            c = ox * ox + oy * oy - wall_radius**2
+            with np.errstate(divide="ignore", invalid="ignore"):
+                disc = b * b - 4 * a * c
+                tw = (-b + np.sqrt(disc)) / (2 * a)
+            zhit = o_w[..., 2] + tw * d_w[..., 2]
+            okw = (disc > 0) & (tw > 0.5) & (zhit > -h) & (zhit < -h + wall_height)
+            best = np.minimum(best, np.where(okw, tw, np.inf))
 
         valid = best < max_range
         rng_noise = rng.normal(0.0, range_noise, size=best.shape)

@@ -251,6 +251,10 @@ CC_API uint64_t cc_total_launches(const cc_handle_t* h);
 CC_API cc_status_t cc_set_kernel_timing(cc_handle_t* h, int enable);
 CC_API cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_cap, float* ms, int cap, int* n_out);
 
+/* Test hook: treat every `period`-th column as if the association probe had flagged it, which routes the push
+ * through the column-sequential exact kernels. Results must not change. 0 = off. */
+CC_API cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period);
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */

@@ -96,6 +96,12 @@ static inline int __reduce_or_sync(unsigned, int v)
 {
     return v;
 }
+static inline void __pipeline_memcpy_async(void* dst, const void* src, size_t n)
+{
+    memcpy(dst, src, n);
+}
+static inline void __pipeline_commit() {}
+static inline void __pipeline_wait_prior(int) {}
 template<typename T>
 static inline T __ldg(const T* p)
 {

@@ -19,7 +19,8 @@ from oracle import drvlib  # noqa: E402
 IDENTITY = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
 
 
-def run(spec, chunk, rotations, kwargs=None, emu=False, oracle_lib=None, cfg_overrides=None, verbose=True):
+def run(spec, chunk, rotations, kwargs=None, emu=False, oracle_lib=None, cfg_overrides=None, verbose=True,
+        flag_period=0):
     kwargs = dict(kwargs or {})
     pts, poses, sp = synth.make_stream(spec, n_rotations=rotations, **kwargs)
     cfg = drvlib.stream_config(spec, **(cfg_overrides or {}))
@@ -33,6 +34,7 @@ def run(spec, chunk, rotations, kwargs=None, emu=False, oracle_lib=None, cfg_ove
     cc.setConfiguration(cfg)
     cc.reset(sp.rows)
     cc.setTransformRobotFrameFromSensorFrame(IDENTITY)
+    cc.debug_flag_columns(flag_period)
     t0 = time.time()
     got = recorder.record(cc, pts, poses, chunk)
     t_got = time.time() - t0
@@ -56,4 +58,6 @@ if __name__ == "__main__":
     chunk = int(a[1]) if len(a) > 1 else 64
     rot = float(a[2]) if len(a) > 2 else 2.0
     kw = eval(a[3]) if len(a) > 3 else {}
-    run(spec, chunk, rot, kw, emu=emu)
+    co = eval(a[4]) if len(a) > 4 else {}
+    fp = int(a[5]) if len(a) > 5 else 0
+    run(spec, chunk, rot, kw, emu=emu, cfg_overrides=co, flag_period=fp)
