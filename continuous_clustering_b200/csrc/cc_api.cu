@@ -338,8 +338,9 @@ uint64_t cc_total_launches(const cc_handle_t* h)
 
 static int scan_smem_bytes(int R)
 {
-    return CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(long long)) +
-           2 * CC_K1_CHUNK * R * static_cast<int>(sizeof(int) + sizeof(float));
+    return CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(int)) +
+           2 * CC_K1_CHUNK * R * static_cast<int>(sizeof(int) + sizeof(float)) +
+           2 * 2 * CC_K1_MAXWARPS * static_cast<int>(sizeof(int));
 }
 
 static int grid_for(const cc_handle* h, long long work, int block)
@@ -370,7 +371,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         h->ringcols = N * 10;
         const size_t cells = static_cast<size_t>(h->ringcols) * h->R;
         const size_t stage = static_cast<size_t>(h->max_firings) * h->R;
-        h->maxcols = h->max_firings + N;
+        h->maxcols = std::min(h->max_firings + N, 8 * N); // relative column arithmetic must stay inside one ring length
         CcDevPtrs& d = h->d;
         const int keep_gap_rows = h->gap_rows;
         float* keep_gap = d.gap_state;
@@ -643,7 +644,8 @@ static cc_status_t run_push(cc_handle* h, int n)
     const long long pts = static_cast<long long>(n) * R;
     CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
     const int scan_smem = scan_smem_bytes(R);
-    CC_RUN(h, k_insert_scan, 1, CC_WARP, scan_smem, cfg, h->d, n);
+    const int scan_threads = ((R + CC_WARP - 1) / CC_WARP) * CC_WARP; // one thread per row
+    CC_RUN(h, k_insert_scan, 1, scan_threads, scan_smem, cfg, h->d, n);
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 
     if (!h->has_tf)

@@ -151,7 +151,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         const int k = idx / cfg.R;
         const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
         const float fx = raw->x, fy = raw->y, fz = raw->z;
-        p.o_g[idx] = -1;
+        p.o_g[idx] = -0x7fffffff - 1;
         if (cc_isnan(fx))
         {
             p.s_cwr[idx] = CC_INVALID_CWR;
@@ -188,16 +188,23 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     if (blockIdx.x != 0)
         return;
     CC_SMEM(smem);
-    const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
+    const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols, C = CC_K1_CHUNK;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid % CC_WARP, warp = tid / CC_WARP;
+    const int nwarps = (T + CC_WARP - 1) / CC_WARP;
     float* wdist = reinterpret_cast<float*>(smem);
-    long long* rmx = reinterpret_cast<long long*>(smem + static_cast<size_t>(W) * R * sizeof(float));
-    // double-buffered staging of the per-point scan inputs (column-in-rotation, distance) for CC_K1_CHUNK firings:
-    // filled with cp.async one chunk ahead so the sequential loop never waits on HBM/L2
-    const int C = CC_K1_CHUNK;
-    int* st_cwr = reinterpret_cast<int*>(rmx + R);
+    int* rmx = reinterpret_cast<int*>(wdist + static_cast<size_t>(W) * R);
+    int* st_cwr = rmx + R;
     float* st_dist = reinterpret_cast<float*>(st_cwr + 2 * C * R);
-    const int lane = threadIdx.x;
+    int* red = reinterpret_cast<int*>(st_dist + 2 * C * R); // [2][CC_K1_MAXWARPS][2] cross-warp min/max exchange
     CcDevState* st = p.st;
+
+    // all column arithmetic is 32-bit, relative to the rearmost column at the start of the push
+    const long long base = st->P;
+    const int base_slot = static_cast<int>(base & (W - 1));
+    const int base_local = static_cast<int>(base % ringcols);
+    const int neg_limit = base > 0x3fffffff ? -0x7fffffff : -static_cast<int>(base); // g_rel < neg_limit <=> g < 0
+    const int NOT_SET = -0x7fffffff - 1;
+
     const int n_chunks = (n_firings + C - 1) / C;
     auto prefetch = [&](int chunk)
     {
@@ -205,7 +212,7 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         {
             const int buf = chunk & 1;
             const size_t src = static_cast<size_t>(chunk) * C * R;
-            for (int i = lane * 4; i < C * R; i += CC_WARP * 4)
+            for (int i = tid * 4; i < C * R; i += T * 4)
             {
                 __pipeline_memcpy_async(st_cwr + buf * C * R + i, p.s_cwr + src + i, 16);
                 __pipeline_memcpy_async(st_dist + buf * C * R + i, p.s_dist + src + i, 16);
@@ -215,25 +222,33 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     };
     prefetch(0);
 
-    for (int row = lane; row < R; row += CC_WARP)
+    for (int row = tid; row < R; row += T)
     {
         const long long rm = p.rowmax[row];
-        rmx[row] = rm;
+        long long rel = rm - base;
+        if (rel < -0x3fffffff)
+            rel = -0x3fffffff;
+        rmx[row] = static_cast<int>(rel);
         for (long long c = (rm - W + 1 > 0 ? rm - W + 1 : 0); c <= rm; c++)
             wdist[(c & (W - 1)) * R + row] = p.pos[static_cast<size_t>(cc_local_col(c, ringcols)) * R + row].w;
     }
-    __syncwarp();
 
-    long long P = st->P, Fm = st->foremost, F = st->F, ring_start = st->ring_start, ring_end = st->ring_end,
-              first_unpub = st->first_unpub;
+    long long F64 = st->F, Fm64 = st->foremost;
+    long long ring_start = st->ring_start, ring_end = st->ring_end, first_unpub = st->first_unpub;
     int reset_required = st->reset_required;
     int error = 0;
-    long long colbase = F;
-    long long prev_rot = P / N;
-    int pc = static_cast<int>(P % N);
-    int rot10 = static_cast<int>(prev_rot % 10);
+    bool f_init = F64 >= 0;     // srig_first_unfinished_global_column_index != -1
+    bool fm_init = Fm64 >= 0;   // srig_previous_global_column_index_of_foremost_laser >= 0
+    int Prel = 0;
+    int Frel = f_init ? static_cast<int>(F64 - base) : 0;
+    int Fmrel = fm_init ? static_cast<int>(Fm64 - base) : 0;
+    int colbase_rel = Frel; // valid once f_init
+    int prev_rot = static_cast<int>(base / N);
+    int pc = static_cast<int>(base % N);
+    const bool p_positive_at_start = base > 0;
     const int half = cfg.half;
     const float nanv = cc_nanf();
+    __syncthreads();
 
     for (int k = 0; k < n_firings; k++)
     {
@@ -241,157 +256,186 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         {
             prefetch(k / C + 1);
             __pipeline_wait_prior(1);
-            __syncwarp();
+            __syncthreads();
         }
         const int sbase = ((k / C) & 1) * C * R + (k % C) * R;
-        int lmin = 0x7fffffff, lmax = -0x7fffffff - 1; // relative to P
-        for (int row = lane; row < R; row += CC_WARP)
+        const bool p_positive = p_positive_at_start || Prel > 0;
+        const int goff = Prel - pc;
+        int lmin = 0x7fffffff, lmax = NOT_SET;
+        for (int row = tid; row < R; row += T)
         {
-            const int idx = k * R + row;
             const int cw = st_cwr[sbase + row];
             if (cw == CC_INVALID_CWR)
                 continue;
             const float d = st_dist[sbase + row];
-            long long g = prev_rot * N + cw;
+            int g = goff + cw;
             const int diff = cw - pc;
-            int rotoff = 0;
+            int rot = prev_rot;
             if (diff < -half)
             {
                 g += N;
-                rotoff = 1;
+                rot++;
             }
-            else if (P > 0 && diff > half)
+            else if (p_positive && diff > half)
             {
                 g -= N;
-                rotoff = -1;
+                rot--;
             }
-            if (g < 0)
+            if (g < neg_limit)
                 continue; // reference: out-of-bounds access (undefined); the point is dropped here
-            int r10 = rot10 + rotoff;
-            r10 = r10 < 0 ? 9 : (r10 > 9 ? 0 : r10);
-            int local = r10 * N + cw;
-            if (local >= ringcols)
-                local -= ringcols;
-
-            long long rm = rmx[row];
-            // occupancy of cell (g, row)
-            float cd;
-            if (g > rm)
-                cd = nanv;
-            else if (g > rm - W)
-                cd = wdist[(g & (W - 1)) * R + row];
-            else
-                cd = p.pos[static_cast<size_t>(local) * R + row].w;
+            int rm = rmx[row];
+            const int slot = ((g + base_slot) & (W - 1)) * R + row;
+            float cd = nanv;
+            if (g <= rm)
+            {
+                if (g > rm - W)
+                    cd = wdist[slot];
+                else
+                {
+                    int local = base_local + g;
+                    local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                    cd = p.pos[static_cast<size_t>(local) * R + row].w;
+                }
+            }
+            int slot_w = slot;
             if (!cc_isnan(cd) && !cc_isnan(d))
             {
-                const long long g1 = g + 1;
-                int local1 = local + 1;
-                if (local1 >= ringcols)
-                    local1 -= ringcols;
-                float nd;
-                if (g1 > rm)
-                    nd = nanv;
-                else if (g1 > rm - W)
-                    nd = wdist[(g1 & (W - 1)) * R + row];
-                else
-                    nd = p.pos[static_cast<size_t>(local1) * R + row].w;
+                const int g1 = g + 1;
+                const int slot1 = ((g1 + base_slot) & (W - 1)) * R + row;
+                float nd = nanv;
+                if (g1 <= rm)
+                {
+                    if (g1 > rm - W)
+                        nd = wdist[slot1];
+                    else
+                    {
+                        int local = base_local + g1;
+                        local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                        nd = p.pos[static_cast<size_t>(local) * R + row].w;
+                    }
+                }
                 if (cc_isnan(nd))
                 {
                     g = g1;
-                    local = local1;
                     cd = nd;
+                    slot_w = slot1;
                 }
             }
             if (!cc_isnan(cd) && (cc_isnan(d) || d >= cd))
                 continue;
-            const bool too_far_behind = F >= 0 && g < F;
+            const bool too_far_behind = f_init && g < Frel;
             if (!too_far_behind)
             {
                 if (g > rm)
                 {
-                    long long lo = rm + 1;
+                    int lo = rm + 1;
                     if (lo < g - W + 1)
                         lo = g - W + 1;
-                    for (long long c = lo; c < g; c++)
-                        wdist[(c & (W - 1)) * R + row] = nanv;
+                    for (int c = lo; c < g; c++)
+                        wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
                     rmx[row] = g;
                     rm = g;
                 }
                 if (g > rm - W)
-                    wdist[(g & (W - 1)) * R + row] = d;
+                    wdist[slot_w] = d;
+                int local = base_local + g;
+                local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
                 p.pos[static_cast<size_t>(local) * R + row].w = d; // write-through
+                const int idx = k * R + row;
                 p.o_g[idx] = g;
-                p.o_rot[idx] = static_cast<int>(prev_rot + rotoff);
+                p.o_rot[idx] = rot;
             }
-            const long long rel = g - P;
-            const int reli = rel > 0x3fffffff ? 0x3fffffff : (rel < -0x3fffffff ? -0x3fffffff : static_cast<int>(rel));
-            lmin = reli < lmin ? reli : lmin;
-            lmax = reli > lmax ? reli : lmax;
+            lmin = g < lmin ? g : lmin;
+            lmax = g > lmax ? g : lmax;
         }
-        const int wmin = cc_warp_min(lmin), wmax = cc_warp_max(lmax);
+        int wmin = cc_warp_min(lmin), wmax = cc_warp_max(lmax);
+        if (nwarps > 1)
+        {
+            int* r = red + (k & 1) * (2 * CC_K1_MAXWARPS);
+            if (lane == 0)
+            {
+                r[2 * warp] = wmin;
+                r[2 * warp + 1] = wmax;
+            }
+            __syncthreads();
+            for (int w = 0; w < nwarps; w++)
+            {
+                const int a = r[2 * w], b = r[2 * w + 1];
+                wmin = a < wmin ? a : wmin;
+                wmax = b > wmax ? b : wmax;
+            }
+        }
         if (wmin != 0x7fffffff)
         {
-            const long long rear = P + wmin, fore = P + wmax;
+            const int rear = wmin, fore = wmax;
             if (fore - rear > N / 2) // cpp:252-261
             {
                 reset_required = 1;
                 continue;
             }
-            if (rear > P)
+            if (rear > Prel)
             {
-                pc += static_cast<int>(rear - P);
+                pc += rear - Prel;
                 while (pc >= N)
                 {
                     pc -= N;
                     prev_rot++;
-                    rot10 = rot10 == 9 ? 0 : rot10 + 1;
                 }
-                P = rear;
+                Prel = rear;
             }
-            if (fore > Fm)
-                Fm = fore;
+            if (!fm_init || fore > Fmrel)
+            {
+                Fmrel = fore;
+                fm_init = true;
+            }
         }
-        if (Fm < 0)
+        if (!fm_init)
             continue;
         if (ring_start == -1)
         {
-            ring_start = P;
-            first_unpub = P;
+            ring_start = base + Prel;
+            first_unpub = base + Prel;
         }
-        if (Fm > ring_end)
-            ring_end = Fm;
-        if (F == -1)
+        if (base + Fmrel > ring_end)
+            ring_end = base + Fmrel;
+        if (!f_init)
         {
-            F = P;
-            colbase = F;
+            f_init = true;
+            Frel = Prel;
+            colbase_rel = Frel;
         }
         // columns [F, P) are complete: this firing's pose drives their segmentation (cpp:289-291)
-        if (P > F)
+        if (Prel > Frel)
         {
-            if (P - colbase > p.maxcols)
+            if (Prel - colbase_rel > p.maxcols)
             {
                 error = CC_DEV_TOO_MANY_COLUMNS;
                 break;
             }
-            for (long long c = F + lane; c < P; c += CC_WARP)
-                p.col_trigger[c - colbase] = k;
-            F = P;
+            for (int c = Frel + tid; c < Prel; c += T)
+                p.col_trigger[c - colbase_rel] = k;
+            Frel = Prel;
         }
     }
-    __syncwarp();
-    for (int row = lane; row < R; row += CC_WARP)
-        p.rowmax[row] = rmx[row];
-    if (lane == 0)
+    __syncthreads();
+    for (int row = tid; row < R; row += T)
     {
-        st->P = P;
-        st->foremost = Fm;
-        st->F = F;
+        const int rm = rmx[row];
+        if (rm > -0x3fffffff)
+            p.rowmax[row] = base + rm;
+    }
+    if (tid == 0)
+    {
+        st->scan_base = base;
+        st->P = base + Prel;
+        st->foremost = fm_init ? base + Fmrel : -1;
+        st->F = f_init ? base + Frel : -1;
         st->ring_start = ring_start;
         st->ring_end = ring_end;
         st->first_unpub = first_unpub;
         st->reset_required = reset_required;
-        st->colbase = colbase;
-        st->ncols = colbase >= 0 ? static_cast<int>(F - colbase) : 0;
+        st->colbase = f_init ? base + colbase_rel : -1;
+        st->ncols = f_init ? Frel - colbase_rel : 0;
         if (error)
             st->error = error;
         st->clear_from = ring_start;
@@ -415,9 +459,10 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     const int total = n_firings * cfg.R;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
-        const long long g = p.o_g[idx];
-        if (g < 0)
+        const int grel = p.o_g[idx];
+        if (grel == -0x7fffffff - 1)
             continue;
+        const long long g = p.st->scan_base + grel;
         const int row = idx % cfg.R;
         const size_t cell = static_cast<size_t>(cc_local_col(g, cfg.ringcols)) * cfg.R + row;
         const float4 sp = p.s_pos[idx];

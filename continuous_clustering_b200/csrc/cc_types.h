@@ -35,6 +35,7 @@ enum : uint8_t
 #define CC_NONE 0xffffffffu
 #define CC_INVALID_CWR (-2147483647 - 1)
 #define CC_COL_INF 0x3fffffffffffffffLL
+#define CC_K1_MAXWARPS 8 /* the insertion scan runs one thread per row, up to 256 rows */
 #define CC_K1_CHUNK 32  /* firings staged per cp.async group by the insertion scan */
 #define CC_K1_WINDOW 64 /* columns of per-row occupancy history kept in shared memory by the insertion scan */
 
@@ -92,6 +93,7 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long seg_c0, seg_c1;       // column range of the running commit segment (inclusive)
     long long seg_first_unpub_old;
     long long gbase; // column of entry 0 of the per-root-column arrays
+    long long scan_base;            // column that o_g is relative to (rearmost column when the push started)
     long long push_first_unpub_old; // first_unpub before the first finish pass of this push
     int sv_n_clusters, sv_n_cluster_points;
 };
@@ -150,7 +152,7 @@ struct CcDevPtrs
     float* s_incl;
     float* s_incaz;
     int* s_cwr;
-    long long* o_g;       // resolved global column, -1 = not stored
+    int* o_g;             // resolved global column relative to CcDevState::scan_base, INT_MIN = not stored
     int* o_rot;           // rotation index used for the continuous azimuth
     // ---- per new column (maxcols) ----
     int* col_trigger;     // firing (index in this push) whose insertion completed the column (hpp:169-173)

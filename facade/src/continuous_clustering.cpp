@@ -1,0 +1,323 @@
+// B200 facade: the reference's ContinuousClustering class API (hpp:197-251) on top of the CUDA C ABI.
+// Replaces src/clustering/continuous_clustering.cpp of the reference at link time. No pipeline stage is computed here.
+#include <continuous_clustering/clustering/continuous_clustering.hpp>
+
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../include/cc_b200.h"
+
+namespace continuous_clustering
+{
+
+static_assert(sizeof(RawPoint) == sizeof(cc_raw_point_t), "RawPoint must stay layout-identical to cc_raw_point_t");
+
+static void toC(const Configuration& c, cc_config_t& o)
+{
+    cc_config_default(&o);
+    o.is_single_threaded = c.general.is_single_threaded;
+    o.sensor_is_clockwise = c.range_image.sensor_is_clockwise;
+    o.num_columns = c.range_image.num_columns;
+    o.supplement_inclination_angle_for_nan_cells = c.range_image.supplement_inclination_angle_for_nan_cells;
+    const auto& g = c.ground_segmentation;
+    o.max_slope = g.max_slope;
+    o.first_ring_as_ground_max_allowed_z_diff = g.first_ring_as_ground_max_allowed_z_diff;
+    o.first_ring_as_ground_min_allowed_z_diff = g.first_ring_as_ground_min_allowed_z_diff;
+    o.last_ground_point_slope_higher_than = g.last_ground_point_slope_higher_than;
+    o.last_ground_point_distance_smaller_than = g.last_ground_point_distance_smaller_than;
+    o.ground_because_close_to_last_certain_ground_max_z_diff = g.ground_because_close_to_last_certain_ground_max_z_diff;
+    o.ground_because_close_to_last_certain_ground_max_dist_diff = g.ground_because_close_to_last_certain_ground_max_dist_diff;
+    o.obstacle_because_next_certain_obstacle_max_dist_diff = g.obstacle_because_next_certain_obstacle_max_dist_diff;
+    o.use_terrain = g.use_terrain;
+    o.terrain_max_allowed_z_diff = g.terrain_max_allowed_z_diff;
+    o.height_ref_to_maximum_ = g.height_ref_to_maximum_;
+    o.height_ref_to_ground_ = g.height_ref_to_ground_;
+    o.length_ref_to_front_end_ = g.length_ref_to_front_end_;
+    o.length_ref_to_rear_end_ = g.length_ref_to_rear_end_;
+    o.width_ref_to_left_mirror_ = g.width_ref_to_left_mirror_;
+    o.width_ref_to_right_mirror_ = g.width_ref_to_right_mirror_;
+    o.fog_filtering_enabled = g.fog_filtering_enabled;
+    o.fog_filtering_intensity_below = g.fog_filtering_intensity_below;
+    o.fog_filtering_distance_below = g.fog_filtering_distance_below;
+    o.fog_filtering_inclination_above = g.fog_filtering_inclination_above;
+    const auto& k = c.clustering;
+    o.max_distance = k.max_distance;
+    o.max_steps_in_row = k.max_steps_in_row;
+    o.max_steps_in_column = k.max_steps_in_column;
+    o.stop_after_association_enabled = k.stop_after_association_enabled;
+    o.stop_after_association_min_steps = k.stop_after_association_min_steps;
+    o.ignore_points_in_chessboard_pattern = k.ignore_points_in_chessboard_pattern;
+    o.ignore_points_with_too_big_inclination_angle_diff = k.ignore_points_with_too_big_inclination_angle_diff;
+    o.use_last_point_for_cluster_stamp = k.use_last_point_for_cluster_stamp;
+    o.cluster_point_trees_every_nth_column = k.cluster_point_trees_every_nth_column;
+}
+
+static void pose12(const Eigen::Isometry3d& t, double* m)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++)
+            m[i * 4 + j] = t(i, j);
+}
+
+ContinuousClustering::ContinuousClustering()
+{
+    if (const char* b = std::getenv("CC_B200_BATCH"))
+        batch_size_ = std::max(1, std::atoi(b));
+    if (const char* d = std::getenv("CC_B200_DEVICE"))
+        device_ = std::atoi(d);
+}
+
+ContinuousClustering::~ContinuousClustering()
+{
+    if (handle_)
+        cc_destroy(handle_);
+}
+
+void ContinuousClustering::fail(int status)
+{
+    // the reference reports these conditions as std::runtime_error (cpp:90-91, 298-299, 337-344, 1072-1075)
+    std::string msg = handle_ ? cc_last_error(handle_) : "no CUDA device";
+    if (msg.empty())
+        msg = "continuous_clustering_b200 error " + std::to_string(status);
+    throw std::runtime_error(msg);
+}
+
+void ContinuousClustering::ensureHandle()
+{
+    if (handle_)
+        return;
+    int s = cc_create(device_, std::max(4096, batch_size_), &handle_);
+    if (s != CC_OK)
+    {
+        handle_ = nullptr;
+        throw std::runtime_error("continuous_clustering_b200: no usable CUDA device (the hot path has no CPU fallback)");
+    }
+}
+
+void ContinuousClustering::setDevice(int ordinal)
+{
+    device_ = ordinal;
+}
+
+void ContinuousClustering::setBatchSize(int firings)
+{
+    flush();
+    batch_size_ = std::max(1, std::min(firings, 4096));
+}
+
+void ContinuousClustering::setConfiguration(const Configuration& config)
+{
+    ensureHandle();
+    flush(); // firings already handed over were processed with the previous parameters
+    config_ = config;
+    cc_config_t c;
+    toC(config, c);
+    int s = cc_set_config(handle_, &c);
+    if (s != CC_OK)
+        fail(s);
+}
+
+bool ContinuousClustering::resetRequired() const
+{
+    return handle_ && cc_reset_required(handle_);
+}
+
+void ContinuousClustering::reset(int num_rows)
+{
+    ensureHandle();
+    pending_ = 0;
+    pending_points_.clear();
+    pending_poses_.clear();
+    int s = cc_reset(handle_, num_rows);
+    if (s != CC_OK)
+        fail(s);
+    num_rows_ = cc_num_rows(handle_);
+    num_columns_ = cc_num_columns(handle_);
+    ring_buffer_max_columns = cc_ring_buffer_max_columns(handle_);
+    range_image_.assign(static_cast<size_t>(ring_buffer_max_columns) * num_rows_, Point{});
+    ring_buffer_start_global_column_index = -1;
+    ring_buffer_end_global_column_index = -1;
+}
+
+void ContinuousClustering::setTransformRobotFrameFromSensorFrame(const Eigen::Isometry3d& tf)
+{
+    ensureHandle();
+    double m[12];
+    pose12(tf, m);
+    cc_set_robot_from_sensor(handle_, m);
+}
+
+bool ContinuousClustering::hasTransformRobotFrameFromSensorFrame()
+{
+    return handle_ && cc_has_robot_from_sensor(handle_);
+}
+
+void ContinuousClustering::setFinishedColumnCallback(std::function<void(int64_t, int64_t, bool)> cb)
+{
+    finished_column_callback_ = std::move(cb);
+}
+
+void ContinuousClustering::setFinishedClusterCallback(std::function<void(const std::vector<Point>&, uint64_t)> cb)
+{
+    finished_cluster_callback_ = std::move(cb);
+}
+
+void ContinuousClustering::recordJobQueueWorkload(size_t) {}
+
+void ContinuousClustering::addFiring(const RawPoints::ConstPtr& firing, const Eigen::Isometry3d& odom_from_sensor)
+{
+    if (num_rows_ != static_cast<int>(firing->points.size())) // cpp:90-91
+        throw std::runtime_error("The number of points in a firing has changed. This is probably a bug!");
+    const size_t bytes = firing->points.size() * sizeof(RawPoint);
+    const size_t off = pending_points_.size();
+    pending_points_.resize(off + bytes);
+    std::memcpy(pending_points_.data() + off, firing->points.data(), bytes);
+    pending_poses_.resize(pending_poses_.size() + 12);
+    pose12(odom_from_sensor, pending_poses_.data() + pending_poses_.size() - 12);
+    if (++pending_ >= batch_size_)
+        flush();
+}
+
+void ContinuousClustering::flush()
+{
+    if (!handle_ || pending_ == 0)
+        return;
+    const int n = pending_;
+    pending_ = 0;
+    int s = cc_push_firings(handle_, n, num_rows_, reinterpret_cast<const cc_raw_point_t*>(pending_points_.data()),
+                            pending_poses_.data());
+    pending_points_.clear();
+    pending_poses_.clear();
+    if (s != CC_OK)
+        fail(s);
+    deliver();
+}
+
+// host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63)
+void ContinuousClustering::materialise(int64_t from, int64_t to)
+{
+    if (to < from)
+        return;
+    const size_t ncols = static_cast<size_t>(to - from + 1), R = static_cast<size_t>(num_rows_), n = ncols * R;
+    std::vector<float> xyz(3 * n), dist(n), az(n), incl(n);
+    std::vector<double> caz(n);
+    std::vector<int64_t> gcol(n), root_gcol(n);
+    std::vector<uint64_t> stamp(n), guid(n), fidx(n), id(n);
+    std::vector<uint8_t> intensity(n), label(n), dbg(n), ign(n);
+    std::vector<int32_t> root_row(n);
+    cc_column_fields_t f{};
+    f.xyz = xyz.data();
+    f.distance = dist.data();
+    f.azimuth_angle = az.data();
+    f.inclination_angle = incl.data();
+    f.continuous_azimuth_angle = caz.data();
+    f.global_column_index = gcol.data();
+    f.stamp = stamp.data();
+    f.globally_unique_point_index = guid.data();
+    f.firing_index = fidx.data();
+    f.intensity = intensity.data();
+    f.ground_point_label = label.data();
+    f.debug_ground_point_label = dbg.data();
+    f.is_ignored = ign.data();
+    f.id = id.data();
+    f.tree_root_gcol = root_gcol.data();
+    f.tree_root_row = root_row.data();
+    int s = cc_read_columns(handle_, from, to, &f);
+    if (s != CC_OK)
+        fail(s);
+    for (size_t c = 0; c < ncols; c++)
+    {
+        const int local = static_cast<int>((from + static_cast<int64_t>(c)) % ring_buffer_max_columns);
+        for (size_t r = 0; r < R; r++)
+        {
+            const size_t i = c * R + r;
+            Point& p = range_image_[static_cast<size_t>(local) * R + r];
+            p.xyz = Point3D(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+            p.firing_index = fidx[i];
+            p.intensity = intensity[i];
+            p.distance = dist[i];
+            p.azimuth_angle = az[i];
+            p.inclination_angle = incl[i];
+            p.continuous_azimuth_angle = caz[i];
+            p.global_column_index = gcol[i];
+            p.local_column_index = gcol[i] >= 0 ? local : -1;
+            p.row_index = std::isnan(dist[i]) ? -1 : static_cast<int>(r); // set by insertion only (cpp:235)
+            p.stamp = stamp[i];
+            p.globally_unique_point_index = guid[i];
+            p.ground_point_label = label[i];
+            p.debug_ground_point_label = dbg[i];
+            p.is_ignored = ign[i] != 0;
+            p.id = id[i];
+            if (root_gcol[i] >= 0)
+            {
+                p.tree_root_ = RangeImageIndex(static_cast<uint16_t>(root_row[i]),
+                                               static_cast<int64_t>(root_gcol[i] % ring_buffer_max_columns));
+                p.tree_id = static_cast<uint64_t>(root_gcol[i]) * R + static_cast<uint64_t>(root_row[i]);
+            }
+            else
+            {
+                p.tree_root_ = RangeImageIndex(0, -1);
+                p.tree_id = 0;
+            }
+        }
+    }
+}
+
+// callbacks of the last push, in the order of the reference's single-threaded mode
+void ContinuousClustering::deliver()
+{
+    cc_batch_info_t info;
+    cc_get_batch_info(handle_, &info);
+    ring_buffer_start_global_column_index = info.ring_start_gcol;
+    ring_buffer_end_global_column_index = info.ring_end_gcol;
+    if (!finished_column_callback_ && !finished_cluster_callback_)
+        return;
+    std::vector<cc_column_event_t> events(info.n_events);
+    std::vector<cc_cluster_t> clusters(info.n_clusters);
+    std::vector<cc_cluster_point_t> points(info.n_cluster_points);
+    int n = 0;
+    cc_get_column_events(handle_, events.data(), info.n_events, &n);
+    cc_get_clusters(handle_, clusters.data(), info.n_clusters, &n);
+    cc_get_cluster_points(handle_, points.data(), info.n_cluster_points, &n);
+    // one read of every column any callback of this push can look at
+    int64_t lo = INT64_MAX, hi = -1;
+    for (const auto& e : events)
+        if (e.to_gcol >= e.from_gcol)
+        {
+            lo = std::min(lo, e.from_gcol);
+            hi = std::max(hi, e.to_gcol);
+        }
+    if (finished_cluster_callback_)
+        for (const auto& c : clusters)
+            if (c.num_points > 20)
+            {
+                lo = std::min(lo, c.min_gcol);
+                hi = std::max(hi, c.max_gcol);
+            }
+    if (hi >= lo && hi >= 0)
+        materialise(lo, hi);
+    size_t next = 0;
+    for (const auto& e : events)
+    {
+        while (next < static_cast<size_t>(e.n_clusters_before) && next < clusters.size())
+        {
+            const cc_cluster_t& c = clusters[next++];
+            if (c.num_points > 20 && finished_cluster_callback_) // cpp:1023
+            {
+                cluster_buffer_.clear();
+                for (uint32_t i = 0; i < c.num_points; i++)
+                {
+                    const cc_cluster_point_t& cp = points[c.point_offset + i];
+                    const int local = static_cast<int>(cp.gcol % ring_buffer_max_columns);
+                    cluster_buffer_.push_back(range_image_[static_cast<size_t>(local) * num_rows_ + cp.row]);
+                }
+                finished_cluster_callback_(cluster_buffer_, c.stamp);
+            }
+        }
+        if (finished_column_callback_)
+            finished_column_callback_(e.from_gcol, e.to_gcol, e.ground_points_only != 0);
+    }
+}
+
+} // namespace continuous_clustering

@@ -249,6 +249,9 @@ int drv_add_firings(drv_t* d, int n, int rows, const cc_raw_point_t* pts, const 
     {
         for (int k = 0; k < n; k++)
             d->cc.addFiring(makeFiring(rows, pts + static_cast<size_t>(k) * rows), poseFrom12(poses + 12 * k));
+#ifdef CC_B200_FACADE
+        d->cc.flush(); // the facade batches firings; the reference delivers everything inside addFiring
+#endif
     }
     catch (const std::exception& e)
     {
@@ -309,6 +312,9 @@ double drv_run_prepared(drv_t* d, int from, int to, int64_t max_lag_columns)
                     std::this_thread::yield();
             }
         }
+#ifdef CC_B200_FACADE
+        d->cc.flush();
+#endif
         if (!d->config.general.is_single_threaded)
         {
             // drain: wait until no callback has arrived for a while
