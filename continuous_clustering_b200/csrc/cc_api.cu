@@ -340,7 +340,8 @@ static int scan_smem_bytes(int R)
 {
     return CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(int)) +
            2 * CC_K1_CHUNK * R * static_cast<int>(sizeof(int) + sizeof(float)) +
-           2 * 2 * CC_K1_MAXWARPS * static_cast<int>(sizeof(int));
+           2 * 2 * CC_K1_MAXWARPS * static_cast<int>(sizeof(int)) +
+           (CC_K1_CHUNK * (R + 1) + 3 * CC_K1_CHUNK + 1 + 8) * static_cast<int>(sizeof(int));
 }
 
 static int grid_for(const cc_handle* h, long long work, int block)
@@ -644,7 +645,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     const long long pts = static_cast<long long>(n) * R;
     CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
     const int scan_smem = scan_smem_bytes(R);
-    const int scan_threads = ((R + CC_WARP - 1) / CC_WARP) * CC_WARP; // one thread per row
+    const int scan_threads = 256; // >= one thread per row (R <= 256); the chunk fast path uses all of them
     CC_RUN(h, k_insert_scan, 1, scan_threads, scan_smem, cfg, h->d, n);
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 

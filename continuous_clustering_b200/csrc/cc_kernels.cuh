@@ -196,6 +196,13 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     int* st_cwr = rmx + R;
     float* st_dist = reinterpret_cast<float*>(st_cwr + 2 * C * R);
     int* red = reinterpret_cast<int*>(st_dist + 2 * C * R); // [2][CC_K1_MAXWARPS][2] cross-warp min/max exchange
+    // scratch of the chunk fast path
+    const int GS = R + 1;                                 // padded row stride of G
+    int* G = red + 2 * 2 * CC_K1_MAXWARPS;                // [C][GS] unwrapped column of every point of the chunk
+    int* f_rear = G + C * GS;                             // [C] rearmost / foremost column of each firing
+    int* f_fore = f_rear + C;
+    int* f_P = f_fore + C;                                // [C + 1] rearmost-so-far before each firing
+    int* f_misc = f_P + C + 1;                            // [0] irregular flag, [1] gmin, [2] gmax, [3] foremost
     CcDevState* st = p.st;
 
     // all column arithmetic is 32-bit, relative to the rearmost column at the start of the push
@@ -250,15 +257,199 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     const float nanv = cc_nanf();
     __syncthreads();
 
-    for (int k = 0; k < n_firings; k++)
+    bool stop = false;
+    for (int chunk = 0; chunk < n_chunks && !stop; chunk++)
     {
-        if ((k % C) == 0)
+        prefetch(chunk + 1);
+        __pipeline_wait_prior(1);
+        __syncthreads();
+        const int k0 = chunk * C;
+        const int kc = (n_firings - k0) < C ? (n_firings - k0) : C;
+        const int cbuf = (chunk & 1) * C * R;
+
+        // ------------------------------------------------------------------------------------------------
+        // Fast path: a chunk is REGULAR when (a) every point unwraps to the same column for any rearmost column
+        // the chunk can reach, (b) per row the columns are strictly increasing and beyond the row's front -- so
+        // every cell is empty when it is hit and the collision rule (cpp:188-208) never fires -- and (c) no firing
+        // straddles the -x axis. Then the firings are independent given the running rearmost column, which is a
+        // prefix maximum: the whole chunk is resolved data-parallel. Anything else takes the per-firing loop below.
+        // ------------------------------------------------------------------------------------------------
+        bool fast = f_init && fm_init && (p_positive_at_start || Prel > 0) && ring_start != -1;
+        if (fast)
         {
-            prefetch(k / C + 1);
-            __pipeline_wait_prior(1);
+            if (tid == 0)
+            {
+                f_misc[0] = 0;
+                f_misc[1] = 0x7fffffff;
+                f_misc[2] = NOT_SET;
+            }
+            __syncthreads();
+            // phase A: unwrap every point against the chunk-start state
+            {
+                const int goff = Prel - pc;
+                int tmin = 0x7fffffff, tmax = NOT_SET, bad = 0;
+                const int total = kc * R;
+                for (int i = tid; i < total; i += T)
+                {
+                    const int k = i / R, row = i - k * R;
+                    const int cw = st_cwr[cbuf + i];
+                    int g = NOT_SET;
+                    if (cw != CC_INVALID_CWR)
+                    {
+                        const int diff = cw - pc;
+                        g = goff + cw;
+                        if (diff < -half)
+                            g += N;
+                        else if (diff > half)
+                            g -= N;
+                        if (g < neg_limit)
+                            bad = 1;
+                        tmin = g < tmin ? g : tmin;
+                        tmax = g > tmax ? g : tmax;
+                    }
+                    G[k * GS + row] = g;
+                }
+                tmin = cc_warp_min(tmin);
+                tmax = cc_warp_max(tmax);
+                bad = __reduce_or_sync(CC_FULL_MASK, bad);
+                if (lane == 0)
+                {
+                    atomicMin(&f_misc[1], tmin);
+                    atomicMax(&f_misc[2], tmax);
+                    if (bad)
+                        f_misc[0] = 1;
+                }
+            }
+            __syncthreads();
+            // phase B: rearmost / foremost column of every firing (one warp per firing, lanes over rows)
+            for (int k = warp; k < kc; k += nwarps)
+            {
+                int lmin = 0x7fffffff, lmax = NOT_SET;
+                for (int row = lane; row < R; row += CC_WARP)
+                {
+                    const int g = G[k * GS + row];
+                    if (g != NOT_SET)
+                    {
+                        lmin = g < lmin ? g : lmin;
+                        lmax = g > lmax ? g : lmax;
+                    }
+                }
+                lmin = cc_warp_min(lmin);
+                lmax = cc_warp_max(lmax);
+                if (lane == 0)
+                {
+                    f_rear[k] = lmin;
+                    f_fore[k] = lmax;
+                }
+            }
+            __syncthreads();
+            // rearmost-so-far before every firing = prefix maximum (cpp:263-266); straddle check (cpp:252-261)
+            if (tid == 0)
+            {
+                int Pcur = Prel, Fcur = Fmrel, irregular = 0;
+                for (int k = 0; k < kc; k++)
+                {
+                    f_P[k] = Pcur;
+                    const int rear = f_rear[k], fore = f_fore[k];
+                    if (rear != 0x7fffffff)
+                    {
+                        if (fore - rear > N / 2)
+                            irregular = 1;
+                        Pcur = rear > Pcur ? rear : Pcur;
+                        Fcur = fore > Fcur ? fore : Fcur;
+                    }
+                }
+                f_P[kc] = Pcur;
+                f_misc[3] = Fcur;
+                const int gmin = f_misc[1], gmax = f_misc[2];
+                if (gmax != NOT_SET && (gmax - Prel >= half || gmin - Prel <= -half || gmax - gmin >= half))
+                    irregular = 1; // the unwrap decision could depend on how far the rearmost column has moved
+                if (Pcur - colbase_rel > p.maxcols)
+                    irregular = 1;
+                if (irregular)
+                    f_misc[0] = 1;
+            }
+            // phase C1: per row, columns strictly increasing and beyond the row's front
+            for (int row = tid; row < R; row += T)
+            {
+                int run = rmx[row], bad = 0;
+                for (int k = 0; k < kc; k++)
+                {
+                    const int g = G[k * GS + row];
+                    if (g != NOT_SET)
+                    {
+                        if (g <= run)
+                            bad = 1;
+                        run = g;
+                    }
+                }
+                if (bad)
+                    f_misc[0] = 1;
+            }
+            __syncthreads();
+            fast = f_misc[0] == 0;
+            if (fast)
+            {
+                // phase C2: per row, advance the occupancy window with the stored points
+                for (int row = tid; row < R; row += T)
+                {
+                    int rm = rmx[row];
+                    for (int k = 0; k < kc; k++)
+                    {
+                        const int g = G[k * GS + row];
+                        if (g == NOT_SET || g < f_P[k]) // invalid, or too far behind (cpp:210-221)
+                            continue;
+                        int lo = rm + 1;
+                        if (lo < g - W + 1)
+                            lo = g - W + 1;
+                        for (int c = lo; c < g; c++)
+                            wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
+                        wdist[((g + base_slot) & (W - 1)) * R + row] = st_dist[cbuf + k * R + row];
+                        rm = g;
+                    }
+                    rmx[row] = rm;
+                }
+                // phase D: outputs of every stored point
+                const int total = kc * R;
+                for (int i = tid; i < total; i += T)
+                {
+                    const int k = i / R, row = i - k * R;
+                    const int g = G[k * GS + row];
+                    if (g == NOT_SET || g < f_P[k])
+                        continue;
+                    int local = base_local + g;
+                    local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                    p.pos[static_cast<size_t>(local) * R + row].w = st_dist[cbuf + i];
+                    const int cw = st_cwr[cbuf + i];
+                    const int diff = cw - pc;
+                    p.o_g[k0 * R + i] = g;
+                    p.o_rot[k0 * R + i] = prev_rot + (diff < -half ? 1 : (diff > half ? -1 : 0));
+                }
+                // columns completed by each firing (cpp:289-291)
+                for (int k = tid; k < kc; k += T)
+                    for (int c = f_P[k]; c < f_P[k + 1]; c++)
+                        p.col_trigger[c - colbase_rel] = k0 + k;
+                const int Pnew = f_P[kc];
+                pc += Pnew - Prel;
+                while (pc >= N)
+                {
+                    pc -= N;
+                    prev_rot++;
+                }
+                Prel = Pnew;
+                Frel = Pnew;
+                Fmrel = f_misc[3];
+                if (base + Fmrel > ring_end)
+                    ring_end = base + Fmrel;
+            }
             __syncthreads();
         }
-        const int sbase = ((k / C) & 1) * C * R + (k % C) * R;
+        if (fast)
+            continue;
+
+      for (int k = k0; k < k0 + kc; k++)
+      {
+        const int sbase = cbuf + (k - k0) * R;
         const bool p_positive = p_positive_at_start || Prel > 0;
         const int goff = Prel - pc;
         int lmin = 0x7fffffff, lmax = NOT_SET;
@@ -410,12 +601,15 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
             if (Prel - colbase_rel > p.maxcols)
             {
                 error = CC_DEV_TOO_MANY_COLUMNS;
+                stop = true;
                 break;
             }
             for (int c = Frel + tid; c < Prel; c += T)
                 p.col_trigger[c - colbase_rel] = k;
             Frel = Prel;
         }
+      }
+      __syncthreads();
     }
     __syncthreads();
     for (int row = tid; row < R; row += T)

@@ -126,6 +126,8 @@ def make_stream(
     box_height_range=(0.5, 3.0),
     wall_radius: float | None = None,
     wall_height: float = 2.5,
+    az_jitter: float = 0.0,
+    az_step_scale: float = 1.0,
 ):
     """Returns (points[n_firings, rows] of RAW_POINT_DTYPE, poses[n_firings, 12] float64, spec).
 
@@ -137,7 +139,9 @@ def make_stream(
     `dropout` randomly replaces that fraction of returns by NaN (missing returns). `wall_radius` adds a closed
     cylindrical wall around the sensor start position (a cluster that spans a full rotation: the reference's forced
     finish, cpp:909-919); `min_box_dist` / `box_height_range` / `extent` shape the box scene (tall, close boxes
-    give steep inclinations: associations the reference refuses, cpp:654-659).
+    give steep inclinations: associations the reference refuses, cpp:654-659). `az_jitter` (in column widths) adds
+    per-firing azimuth noise and `az_step_scale` stretches / shrinks the azimuth step per firing, so that firings land
+    in the same column twice or skip columns: the cell-collision rule (cpp:188-208) and the "too far behind" cut.
     """
     sp = spec(spec_name)
     rows, ncols = sp.rows, sp.num_columns
@@ -177,7 +181,10 @@ def make_stream(
         poses[c0:c1, 8:11] = rmat[:, 2, :]
         poses[c0:c1, 11] = tvec[:, 2]
 
-        az = np.pi - ((k % ncols) + 0.5) * (2 * np.pi / ncols)  # (f,)
+        az = np.pi - (((k * az_step_scale) % ncols) + 0.5) * (2 * np.pi / ncols)  # (f,)
+        if az_jitter > 0:
+            az = az + rng.normal(0.0, az_jitter * 2 * np.pi / ncols, size=az.shape)
+            az = (az + np.pi) % (2 * np.pi) - np.pi
         az = az[:, None] + sp.azimuth_offsets_rad[None, :]  # (f, rows)
         inc = sp.inclinations_rad[None, :]
         d_s = np.stack([np.cos(az) * np.cos(inc), np.sin(az) * np.cos(inc), np.broadcast_to(np.sin(inc), az.shape)], -1)

@@ -46,6 +46,13 @@ CASES = [
     ("velodyne64", dict(n_rotations=1.2, moving=True, dropout=0.03), {}, 700, 0),
     ("os32_left", dict(n_firings=900, moving=True), {}, 256, 0),
     ("vls128", dict(n_firings=600, moving=True), {}, 256, 0),  # begins with firings that straddle the -x axis
+    # azimuth jitter: firings land twice in a column / skip columns / run backwards (collision rule cpp:188-208,
+    # "too far behind" cpp:210-221): regular and irregular chunks of the insertion scan are mixed
+    ("tiny16", dict(n_rotations=3.0, az_jitter=0.7), {}, 64, 0),
+    ("tiny16", dict(n_rotations=3.0, az_jitter=0.3, az_step_scale=0.93, moving=True, dropout=0.05), {}, 200, 0),
+    ("tiny16", dict(n_rotations=2.0, az_jitter=3.0), {}, 33, 0),
+    ("velodyne64", dict(n_rotations=1.3, az_jitter=0.5, az_step_scale=1.04), {}, 1024, 0),
+    ("vls128", dict(n_rotations=1.1, az_jitter=1.5, start_firing=40, moving=True), {}, 512, 0),
 ]
 
 

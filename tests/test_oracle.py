@@ -41,6 +41,10 @@ STREAMS = [
     ("vls128", dict(n_rotations=1.1, moving=True, start_firing=40), {}),
     ("os32_right", dict(n_rotations=2.0, moving=True), {}),
     ("tiny16", dict(n_rotations=3.0, n_boxes=0, wall_radius=6.0), {}),
+    ("tiny16", dict(n_rotations=3.0, az_jitter=0.7), {}),
+    ("tiny16", dict(n_rotations=2.0, az_jitter=3.0, dropout=0.05), {}),
+    ("velodyne64", dict(n_rotations=1.3, az_jitter=0.5, az_step_scale=1.04), {}),
+    ("vls128", dict(n_rotations=1.1, az_jitter=1.5, start_firing=40, moving=True), {}),
     ("tiny16", dict(n_rotations=2.0, dropout=0.3), dict(stop_after_association_enabled=0)),
     ("tiny16", dict(n_rotations=2.0), dict(sensor_is_clockwise=0)),
     ("tiny16", dict(n_rotations=2.0), dict(fog_filtering_enabled=1, fog_filtering_intensity_below=120,
