@@ -70,7 +70,7 @@ class CcBatchInfo(C.Structure):
         ("used_exact_path", C.c_int32),
         ("gpu_launches", C.c_int32),
         ("device_ms", C.c_float),
-        ("pad_", C.c_int32),
+        ("slow_insert_firings", C.c_int32),
     ]
 
 

@@ -11,6 +11,8 @@
 
 #include "cc_kernels.cuh"
 
+static const int CC_PREFETCH_CLUSTERS = 1024, CC_PREFETCH_POINTS = 32768;
+
 namespace
 {
 
@@ -39,6 +41,7 @@ struct cc_handle
     int maxcols{0};
     int gap_rows{-1};
     int debug_flag_period{0};
+    size_t probe_smem_set{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
     unsigned char* d_raw{nullptr};
@@ -48,6 +51,11 @@ struct cc_handle
     void* h_raw{nullptr};            // pinned staging
     double* h_poses{nullptr};
     CcDevState* h_state{nullptr}; // pinned mirror
+    // pinned landing buffers: the state and a prefix of the results come back with ONE stream synchronisation
+    long long* hp_first_unpub{nullptr};
+    CcCluster* hp_clusters{nullptr};
+    CcClusterPoint* hp_points{nullptr};
+    int pre_cols{0}, pre_clusters{0}, pre_points{0}; // how much of each the last fetch brought
     CcDevState state{};
     unsigned int seq{0};
     uint64_t launches{0};
@@ -259,6 +267,12 @@ void cc_destroy(cc_handle_t* h)
         cudaFreeHost(h->h_poses);
     if (h->h_state)
         cudaFreeHost(h->h_state);
+    if (h->hp_first_unpub)
+        cudaFreeHost(h->hp_first_unpub);
+    if (h->hp_clusters)
+        cudaFreeHost(h->hp_clusters);
+    if (h->hp_points)
+        cudaFreeHost(h->hp_points);
     if (h->ev0)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
@@ -336,12 +350,31 @@ uint64_t cc_total_launches(const cc_handle_t* h)
     return h ? h->launches : 0;
 }
 
+static int scan_chunk(int R)
+{
+    int c = CC_K1_MAX_CHUNK;
+    while (c > 1 && c * R > CC_K1_POINTS_PER_CHUNK)
+        c >>= 1;
+    return c;
+}
+
+static int scan_threads()
+{
+#ifdef CC_EMU
+    return 1;
+#else
+    return 1024;
+#endif
+}
+
 static int scan_smem_bytes(int R)
 {
-    return CC_K1_WINDOW * R * static_cast<int>(sizeof(float)) + R * static_cast<int>(sizeof(int)) +
-           2 * CC_K1_CHUNK * R * static_cast<int>(sizeof(int) + sizeof(float)) +
-           2 * 2 * CC_K1_MAXWARPS * static_cast<int>(sizeof(int)) +
-           (CC_K1_CHUNK * (R + 1) + 3 * CC_K1_CHUNK + 1 + 8) * static_cast<int>(sizeof(int));
+    const int C = scan_chunk(R);
+    const int T = scan_threads();
+    const int nparts = T / R > 0 ? (T / R < C ? T / R : C) : 1;
+    size_t words = static_cast<size_t>(CC_K1_WINDOW) * R + 2 * R + 4 * static_cast<size_t>(C) * R + 2 * 2 * 32 +
+                   static_cast<size_t>(C) * (R + 1) + 2 * C + 2 * (C + 1) + 3 * static_cast<size_t>(R) * nparts + 8;
+    return static_cast<int>(words * 4);
 }
 
 static int grid_for(const cc_handle* h, long long work, int block)
@@ -405,11 +438,11 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.slot_gcol, static_cast<size_t>(h->ringcols)));
         CC_CHECK(h, dev_alloc(h, L, &d.rowmax, static_cast<size_t>(h->R)));
         CC_CHECK(h, dev_alloc(h, L, &d.s_pos, stage));
-        CC_CHECK(h, dev_alloc(h, L, &d.s_dist, stage + static_cast<size_t>(CC_K1_CHUNK) * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_dist, stage + static_cast<size_t>(CC_K1_MAX_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.s_az, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incl, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incaz, stage));
-        CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_CHUNK) * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_MAX_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
         CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
@@ -459,6 +492,18 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         h->h_poses = nullptr;
         CC_CHECK(h, cudaMallocHost(&h->h_raw, stage * sizeof(cc_raw_point_t)));
         CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
+        if (h->hp_first_unpub)
+            cudaFreeHost(h->hp_first_unpub);
+        if (h->hp_clusters)
+            cudaFreeHost(h->hp_clusters);
+        if (h->hp_points)
+            cudaFreeHost(h->hp_points);
+        h->hp_first_unpub = nullptr;
+        h->hp_clusters = nullptr;
+        h->hp_points = nullptr;
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_first_unpub), mc * sizeof(long long)));
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
         CC_CHECK(h, cudaMemsetAsync(d.firing_index, 0, cells * sizeof(unsigned long long), h->stream));
         CC_CHECK(h, cudaMemsetAsync(d.cparent, 0, cells * sizeof(unsigned int), h->stream));
         CC_CHECK(h, cudaMemsetAsync(d.tfinish, 0, cells * sizeof(unsigned long long), h->stream));
@@ -523,9 +568,23 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     return CC_OK;
 }
 
-static cc_status_t fetch_state(cc_handle* h)
+static cc_status_t fetch_state(cc_handle* h, int n_firings_hint = -1)
 {
     CC_CHECK(h, cudaMemcpyAsync(h->h_state, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->stream));
+    h->pre_cols = h->pre_clusters = h->pre_points = 0;
+    if (n_firings_hint >= 0)
+    {
+        // optimistic prefix of the results in the same round trip (what a push normally produces fits)
+        h->pre_cols = std::min(h->maxcols, n_firings_hint + 64);
+        h->pre_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
+        h->pre_points = std::min(h->d.cap_cluster_points, CC_PREFETCH_POINTS);
+        CC_CHECK(h, cudaMemcpyAsync(h->hp_first_unpub, h->d.col_first_unpub, h->pre_cols * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CC_CHECK(h, cudaMemcpyAsync(h->hp_clusters, h->d.clusters, h->pre_clusters * sizeof(CcCluster),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CC_CHECK(h, cudaMemcpyAsync(h->hp_points, h->d.cluster_points, h->pre_points * sizeof(CcClusterPoint),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
     h->state = *h->h_state;
     return CC_OK;
@@ -556,24 +615,24 @@ static cc_status_t device_error_to_status(cc_handle* h)
     }
 }
 
-// finish passes for columns [ci0, ci1] (ci1 < 0: all new columns)
-static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact)
+// finish passes for columns [ci0, ci1] (ci1 < 0: all new columns); `last` also closes the push (k_push_done)
+static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact, int last)
 {
     const unsigned int seq = ++h->seq;
-    const int g = h->sm_count * 2;
-    CC_RUN(h, k_fin_init, g, 256, 0, cfg, h->d, ci0, ci1, guard);
-    CC_RUN(h, k_fin_agg, g, 256, 0, cfg, h->d, guard);
-    CC_RUN(h, k_fin_decide, g, 256, 0, cfg, h->d, guard, exact);
-    CC_RUN(h, k_fin_mark, g, 256, 0, cfg, h->d, seq, guard);
-    CC_RUN(h, k_fin_copyback, g, 256, 0, h->d, guard);
-    CC_RUN(h, k_fin_columns, 1, 1024, 1024 * sizeof(long long), cfg, h->d, guard);
+#ifdef CC_EMU
+    const int fin_threads = 1;
+#else
+    const int fin_threads = 1024;
+#endif
+    CC_RUN(h, k_fin_all, 1, fin_threads, fin_threads * sizeof(long long), cfg, h->d, ci0, ci1, seq, guard, exact, last);
     CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
 }
 
-static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard)
+static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)
 {
     const int g = h->sm_count * 8;
-    CC_RUN(h, k_snapshot, h->sm_count * 2, 256, 0, h->d, guard);
+    if (snapshot)
+        CC_RUN(h, k_snapshot, h->sm_count * 2, 256, 0, h->d, guard);
     CC_RUN(h, k_commit_copy, g, 256, 0, cfg, h->d, h->d_s_parent, ci0, ci1, guard);
     CC_RUN(h, k_commit_roots, g, 256, 0, cfg, h->d, ci0, ci1, guard);
     CC_RUN(h, k_commit_links, g, 256, 0, cfg, h->d, ci0, ci1, guard);
@@ -600,15 +659,15 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
         {
             CC_RUN(h, k_careful, 1, 1, 0, cfg, h->d, ci);
             if ((colbase + ci) % cfg.nth == 0)
-                launch_finish(h, cfg, ci, ci, 0, 1);
+                launch_finish(h, cfg, ci, ci, 0, 1, 0);
             ci++;
             continue;
         }
         int cj = ci;
         while (cj + 1 < ncols && !careful[cj + 1])
             cj++;
-        launch_commit(h, cfg, ci, cj, 0);
-        launch_finish(h, cfg, ci, cj, 2, 0);
+        launch_commit(h, cfg, ci, cj, 0, true);
+        launch_finish(h, cfg, ci, cj, 2, 0, 0);
         cc_status_t s = fetch_state(h);
         if (s != CC_OK)
             return s;
@@ -645,8 +704,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     const long long pts = static_cast<long long>(n) * R;
     CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
     const int scan_smem = scan_smem_bytes(R);
-    const int scan_threads = 256; // >= one thread per row (R <= 256); the chunk fast path uses all of them
-    CC_RUN(h, k_insert_scan, 1, scan_threads, scan_smem, cfg, h->d, n);
+    CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R));
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 
     if (!h->has_tf)
@@ -666,16 +724,29 @@ static cc_status_t run_push(cc_handle* h, int n)
         CC_RUN(h, k_gap_scan, R, 256, 256 * sizeof(float), cfg, h->d);
         const int gw = 4; // warps (columns) per block
         CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, gw * R * sizeof(CcGroundSmem), cfg, h->d);
-        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d);
-        CC_RUN(h, k_probe, h->sm_count * 8, 128, 0, cfg, h->d, h->d_s_parent);
         const bool spec = cfg.nth == 1;
+        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d, spec ? 1 : 0);
+        {
+            // one CTA per tile of 8 new columns; the tile's sliding window of prior columns is staged in shared memory
+            const int tile_cols = 8;
+            const size_t win_bytes = static_cast<size_t>(tile_cols + cfg.max_steps_row) * R * sizeof(float4);
+            const int use_smem = (cfg.max_steps_row >= 0 && win_bytes <= 160 * 1024) ? 1 : 0;
+#ifndef CC_EMU
+            if (use_smem && win_bytes > 48 * 1024 && win_bytes != h->probe_smem_set)
+            {
+                CC_CHECK(h, cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(win_bytes)));
+                h->probe_smem_set = win_bytes;
+            }
+#endif
+            CC_RUN(h, k_probe, h->sm_count * 4, 256, use_smem ? win_bytes : 0, cfg, h->d, h->d_s_parent, tile_cols, use_smem);
+        }
         if (spec)
         {
-            launch_commit(h, cfg, 0, -1, 1);
-            launch_finish(h, cfg, 0, -1, 1, 0);
-            CC_RUN(h, k_push_done, 1, 1, 0, h->d, 1);
+            launch_commit(h, cfg, 0, -1, 1, false);
+            launch_finish(h, cfg, 0, -1, 1, 0, 1);
         }
-        cc_status_t s = fetch_state(h);
+        CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
+        cc_status_t s = fetch_state(h, n);
         if (s != CC_OK)
             return s;
         if (h->state.error == 0 && h->state.ncols > 0 && (!spec || h->state.n_flagged > 0 || h->state.abort))
@@ -689,12 +760,12 @@ static cc_status_t run_push(cc_handle* h, int n)
             if (s != CC_OK)
                 return s;
             CC_RUN(h, k_push_done, 1, 1, 0, h->d, 0);
-            s = fetch_state(h);
+            CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
+            s = fetch_state(h, n);
             if (s != CC_OK)
                 return s;
         }
     }
-    CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
     CC_CHECK(h, cudaGetLastError());
     cc_status_t es = device_error_to_status(h);
     if (es != CC_OK)
@@ -707,19 +778,38 @@ static cc_status_t run_push(cc_handle* h, int n)
     h->h_first_unpub.resize(ncols);
     h->h_clusters.resize(ncl);
     h->cluster_points.resize(ncp);
-    if (ncols)
-        CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data(), h->d.col_first_unpub, ncols * sizeof(long long),
-                                    cudaMemcpyDeviceToHost, h->stream));
-    if (ncl)
-        CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data(), h->d.clusters, ncl * sizeof(CcCluster),
-                                    cudaMemcpyDeviceToHost, h->stream));
-    if (ncp)
+    static_assert(sizeof(CcClusterPoint) == sizeof(cc_cluster_point_t), "cluster point layout");
     {
-        static_assert(sizeof(CcClusterPoint) == sizeof(cc_cluster_point_t), "cluster point layout");
-        CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data(), h->d.cluster_points, ncp * sizeof(CcClusterPoint),
-                                    cudaMemcpyDeviceToHost, h->stream));
+        // what the prefetch already brought, then (rarely) the remainder with a second round trip
+        const int c0 = std::min(ncols, h->pre_cols), l0 = std::min(ncl, h->pre_clusters), p0 = std::min(ncp, h->pre_points);
+        if (c0)
+            std::memcpy(h->h_first_unpub.data(), h->hp_first_unpub, c0 * sizeof(long long));
+        if (l0)
+            std::memcpy(h->h_clusters.data(), h->hp_clusters, l0 * sizeof(CcCluster));
+        if (p0)
+            std::memcpy(h->cluster_points.data(), h->hp_points, p0 * sizeof(CcClusterPoint));
+        bool more = false;
+        if (ncols > c0)
+        {
+            CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data() + c0, h->d.col_first_unpub + c0,
+                                        (ncols - c0) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            more = true;
+        }
+        if (ncl > l0)
+        {
+            CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data() + l0, h->d.clusters + l0, (ncl - l0) * sizeof(CcCluster),
+                                        cudaMemcpyDeviceToHost, h->stream));
+            more = true;
+        }
+        if (ncp > p0)
+        {
+            CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data() + p0, h->d.cluster_points + p0,
+                                        (ncp - p0) * sizeof(CcClusterPoint), cudaMemcpyDeviceToHost, h->stream));
+            more = true;
+        }
+        if (more)
+            CC_CHECK(h, cudaStreamSynchronize(h->stream));
     }
-    CC_CHECK(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
 
@@ -780,6 +870,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     info.reset_required = st.reset_required;
     info.gpu_launches = static_cast<int32_t>(h->launches - h->launches_at_push_start);
     info.device_ms = ms;
+    info.slow_insert_firings = st.scan_slow_firings; // firings that needed the per-firing insertion path
     return CC_OK;
 }
 

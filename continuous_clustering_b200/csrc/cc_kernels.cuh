@@ -178,39 +178,65 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 // K1  insertion scan: the part of insertFiringIntoRangeImage that is sequential over firings -- rotation
 //     unwrapping against the previous rearmost column (cpp:119-175), the cell-collision rule (cpp:188-208),
 //     the "too far behind" cut (cpp:210-221), rearmost/foremost tracking, the straddle check (cpp:252-261)
-//     and which firing completes which column (cpp:289-291). ONE warp; lanes own rows; the per-row occupancy of
-//     the last CC_K1_WINDOW columns lives in shared memory so a firing costs a few shared-memory round trips and
-//     two warp reductions instead of dependent L2 reads. Distances are written through to the ring so that
-//     K1b can tell which writer of a cell won (the last writer is always the closest, cpp:207).
+//     and which firing completes which column (cpp:289-291). One CTA of 1024 threads.
+//
+//     Firings are staged CC chunk by chunk into shared memory with cp.async, one chunk ahead. A run of firings is
+//     REGULAR when (a) every point unwraps to the same column for any rearmost column the run can reach, (b) per
+//     row the columns are strictly increasing and beyond the row's front -- so every cell is empty when it is
+//     hit and the collision rule never fires -- and (c) no firing straddles the -x axis. Then the firings are
+//     independent given the running rearmost column, which is a prefix maximum: the whole run is resolved
+//     data-parallel (phases A..D). The first firing that breaks regularity is found exactly; a few firings from
+//     there go through the per-firing path (exact for everything), then the fast path resumes.
+//     The per-row occupancy of the last CC_K1_WINDOW columns lives in shared memory; distances are written
+//     through to the ring so that K1b can tell which writer of a cell won (the last writer is the closest, cpp:207).
 // =====================================================================================================
-__global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+struct CcScanState // uniform across the CTA, kept in registers by every thread
+{
+    int Prel, Frel, Fmrel, colbase_rel, prev_rot, pc;
+    bool f_init, fm_init;
+    long long ring_start, ring_end, first_unpub;
+    int reset_required, error;
+};
+
+__global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C)
 {
     if (blockIdx.x != 0)
         return;
     CC_SMEM(smem);
-    const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols, C = CC_K1_CHUNK;
+    const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
     const int T = blockDim.x, tid = threadIdx.x, lane = tid % CC_WARP, warp = tid / CC_WARP;
     const int nwarps = (T + CC_WARP - 1) / CC_WARP;
-    float* wdist = reinterpret_cast<float*>(smem);
-    int* rmx = reinterpret_cast<int*>(wdist + static_cast<size_t>(W) * R);
-    int* st_cwr = rmx + R;
+    const int row_warps = (R + CC_WARP - 1) / CC_WARP < nwarps ? (R + CC_WARP - 1) / CC_WARP : nwarps;
+    const int GS = R + 1;
+    // threads per row in the row phases; every (row, part) owns `seg` consecutive firings of a run
+    const int nparts = T / R > 0 ? (T / R < C ? T / R : C) : 1;
+    const int seg = (C + nparts - 1) / nparts;
+
+    float* wdist = reinterpret_cast<float*>(smem);           // [W][R] occupancy window
+    int* rmx = reinterpret_cast<int*>(wdist + static_cast<size_t>(W) * R); // [R] row front
+    int* rm_new = rmx + R;                                    // [R]
+    int* st_cwr = rm_new + R;                                 // [2][C][R] staged column-in-rotation
     float* st_dist = reinterpret_cast<float*>(st_cwr + 2 * C * R);
-    int* red = reinterpret_cast<int*>(st_dist + 2 * C * R); // [2][CC_K1_MAXWARPS][2] cross-warp min/max exchange
-    // scratch of the chunk fast path
-    const int GS = R + 1;                                 // padded row stride of G
-    int* G = red + 2 * 2 * CC_K1_MAXWARPS;                // [C][GS] unwrapped column of every point of the chunk
-    int* f_rear = G + C * GS;                             // [C] rearmost / foremost column of each firing
-    int* f_fore = f_rear + C;
-    int* f_P = f_fore + C;                                // [C + 1] rearmost-so-far before each firing
-    int* f_misc = f_P + C + 1;                            // [0] irregular flag, [1] gmin, [2] gmax, [3] foremost
+    int* red = reinterpret_cast<int*>(st_dist + 2 * C * R);  // [2][32][2]
+    int* G = red + 2 * 2 * 32;                                // [C][GS]
+    int* f_rear = G + C * GS;                                 // [C]
+    int* f_fore = f_rear + C;                                 // [C]
+    int* f_P = f_fore + C;                                    // [C + 1] rearmost-so-far before firing k
+    int* f_F = f_P + C + 1;                                   // [C + 1] foremost-so-far before firing k
+    int* seg_first = f_F + C + 1;                             // [R][nparts] first valid column of a segment
+    int* seg_firstk = seg_first + R * nparts;                 // its firing
+    int* seg_last = seg_firstk + R * nparts;                  // last valid column of a segment
+    int* f_misc = seg_last + R * nparts;                      // [0] k_bad, [1] gmin, [2] gmax
     CcDevState* st = p.st;
 
-    // all column arithmetic is 32-bit, relative to the rearmost column at the start of the push
     const long long base = st->P;
     const int base_slot = static_cast<int>(base & (W - 1));
     const int base_local = static_cast<int>(base % ringcols);
     const int neg_limit = base > 0x3fffffff ? -0x7fffffff : -static_cast<int>(base); // g_rel < neg_limit <=> g < 0
     const int NOT_SET = -0x7fffffff - 1;
+    const int half = cfg.half;
+    const float nanv = cc_nanf();
+    const bool p_positive_at_start = base > 0;
 
     const int n_chunks = (n_firings + C - 1) / C;
     auto prefetch = [&](int chunk)
@@ -240,24 +266,27 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
             wdist[(c & (W - 1)) * R + row] = p.pos[static_cast<size_t>(cc_local_col(c, ringcols)) * R + row].w;
     }
 
-    long long F64 = st->F, Fm64 = st->foremost;
-    long long ring_start = st->ring_start, ring_end = st->ring_end, first_unpub = st->first_unpub;
-    int reset_required = st->reset_required;
-    int error = 0;
-    bool f_init = F64 >= 0;     // srig_first_unfinished_global_column_index != -1
-    bool fm_init = Fm64 >= 0;   // srig_previous_global_column_index_of_foremost_laser >= 0
-    int Prel = 0;
-    int Frel = f_init ? static_cast<int>(F64 - base) : 0;
-    int Fmrel = fm_init ? static_cast<int>(Fm64 - base) : 0;
-    int colbase_rel = Frel; // valid once f_init
-    int prev_rot = static_cast<int>(base / N);
-    int pc = static_cast<int>(base % N);
-    const bool p_positive_at_start = base > 0;
-    const int half = cfg.half;
-    const float nanv = cc_nanf();
+    CcScanState s;
+    {
+        const long long F64 = st->F, Fm64 = st->foremost;
+        s.f_init = F64 >= 0;
+        s.fm_init = Fm64 >= 0;
+        s.Prel = 0;
+        s.Frel = s.f_init ? static_cast<int>(F64 - base) : 0;
+        s.Fmrel = s.fm_init ? static_cast<int>(Fm64 - base) : 0;
+        s.colbase_rel = s.Frel;
+        s.prev_rot = static_cast<int>(base / N);
+        s.pc = static_cast<int>(base % N);
+        s.ring_start = st->ring_start;
+        s.ring_end = st->ring_end;
+        s.first_unpub = st->first_unpub;
+        s.reset_required = st->reset_required;
+        s.error = 0;
+    }
     __syncthreads();
 
     bool stop = false;
+    int n_fast = 0, n_slow = 0, n_attempts = 0;
     for (int chunk = 0; chunk < n_chunks && !stop; chunk++)
     {
         prefetch(chunk + 1);
@@ -266,350 +295,479 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         const int k0 = chunk * C;
         const int kc = (n_firings - k0) < C ? (n_firings - k0) : C;
         const int cbuf = (chunk & 1) * C * R;
-
-        // ------------------------------------------------------------------------------------------------
-        // Fast path: a chunk is REGULAR when (a) every point unwraps to the same column for any rearmost column
-        // the chunk can reach, (b) per row the columns are strictly increasing and beyond the row's front -- so
-        // every cell is empty when it is hit and the collision rule (cpp:188-208) never fires -- and (c) no firing
-        // straddles the -x axis. Then the firings are independent given the running rearmost column, which is a
-        // prefix maximum: the whole chunk is resolved data-parallel. Anything else takes the per-firing loop below.
-        // ------------------------------------------------------------------------------------------------
-        bool fast = f_init && fm_init && (p_positive_at_start || Prel > 0) && ring_start != -1;
-        if (fast)
+        int ka = 0; // next firing of the chunk to process
+        while (ka < kc && !stop)
         {
-            if (tid == 0)
+            int kgood = ka; // firings [ka, kgood) are resolved by the fast path
+            const bool try_fast = s.f_init && s.fm_init && (p_positive_at_start || s.Prel > 0) && s.ring_start != -1;
+            if (try_fast)
             {
-                f_misc[0] = 0;
-                f_misc[1] = 0x7fffffff;
-                f_misc[2] = NOT_SET;
-            }
-            __syncthreads();
-            // phase A: unwrap every point against the chunk-start state
-            {
-                const int goff = Prel - pc;
-                int tmin = 0x7fffffff, tmax = NOT_SET, bad = 0;
-                const int total = kc * R;
-                for (int i = tid; i < total; i += T)
+                const int kb = kc;
+                if (tid == 0)
                 {
-                    const int k = i / R, row = i - k * R;
-                    const int cw = st_cwr[cbuf + i];
-                    int g = NOT_SET;
-                    if (cw != CC_INVALID_CWR)
-                    {
-                        const int diff = cw - pc;
-                        g = goff + cw;
-                        if (diff < -half)
-                            g += N;
-                        else if (diff > half)
-                            g -= N;
-                        if (g < neg_limit)
-                            bad = 1;
-                        tmin = g < tmin ? g : tmin;
-                        tmax = g > tmax ? g : tmax;
-                    }
-                    G[k * GS + row] = g;
+                    f_misc[0] = kb;
+                    f_misc[1] = 0x7fffffff;
+                    f_misc[2] = NOT_SET;
                 }
-                tmin = cc_warp_min(tmin);
-                tmax = cc_warp_max(tmax);
-                bad = __reduce_or_sync(CC_FULL_MASK, bad);
-                if (lane == 0)
-                {
-                    atomicMin(&f_misc[1], tmin);
-                    atomicMax(&f_misc[2], tmax);
-                    if (bad)
-                        f_misc[0] = 1;
-                }
-            }
-            __syncthreads();
-            // phase B: rearmost / foremost column of every firing (one warp per firing, lanes over rows)
-            for (int k = warp; k < kc; k += nwarps)
-            {
-                int lmin = 0x7fffffff, lmax = NOT_SET;
-                for (int row = lane; row < R; row += CC_WARP)
-                {
-                    const int g = G[k * GS + row];
-                    if (g != NOT_SET)
-                    {
-                        lmin = g < lmin ? g : lmin;
-                        lmax = g > lmax ? g : lmax;
-                    }
-                }
-                lmin = cc_warp_min(lmin);
-                lmax = cc_warp_max(lmax);
-                if (lane == 0)
-                {
-                    f_rear[k] = lmin;
-                    f_fore[k] = lmax;
-                }
-            }
-            __syncthreads();
-            // rearmost-so-far before every firing = prefix maximum (cpp:263-266); straddle check (cpp:252-261)
-            if (tid == 0)
-            {
-                int Pcur = Prel, Fcur = Fmrel, irregular = 0;
-                for (int k = 0; k < kc; k++)
-                {
-                    f_P[k] = Pcur;
-                    const int rear = f_rear[k], fore = f_fore[k];
-                    if (rear != 0x7fffffff)
-                    {
-                        if (fore - rear > N / 2)
-                            irregular = 1;
-                        Pcur = rear > Pcur ? rear : Pcur;
-                        Fcur = fore > Fcur ? fore : Fcur;
-                    }
-                }
-                f_P[kc] = Pcur;
-                f_misc[3] = Fcur;
-                const int gmin = f_misc[1], gmax = f_misc[2];
-                if (gmax != NOT_SET && (gmax - Prel >= half || gmin - Prel <= -half || gmax - gmin >= half))
-                    irregular = 1; // the unwrap decision could depend on how far the rearmost column has moved
-                if (Pcur - colbase_rel > p.maxcols)
-                    irregular = 1;
-                if (irregular)
-                    f_misc[0] = 1;
-            }
-            // phase C1: per row, columns strictly increasing and beyond the row's front
-            for (int row = tid; row < R; row += T)
-            {
-                int run = rmx[row], bad = 0;
-                for (int k = 0; k < kc; k++)
-                {
-                    const int g = G[k * GS + row];
-                    if (g != NOT_SET)
-                    {
-                        if (g <= run)
-                            bad = 1;
-                        run = g;
-                    }
-                }
-                if (bad)
-                    f_misc[0] = 1;
-            }
-            __syncthreads();
-            fast = f_misc[0] == 0;
-            if (fast)
-            {
-                // phase C2: per row, advance the occupancy window with the stored points
                 for (int row = tid; row < R; row += T)
+                    rm_new[row] = rmx[row];
+                __syncthreads();
+                // ---- phase A: unwrap every point against the state at the start of the run ----
                 {
-                    int rm = rmx[row];
-                    for (int k = 0; k < kc; k++)
+                    const int goff = s.Prel - s.pc;
+                    int tmin = 0x7fffffff, tmax = NOT_SET, kbad = kb;
+                    const int total = (kb - ka) * R;
+                    int k, row;
+                    const bool tiled = (T % R) == 0;
+                    const int kstep = tiled ? T / R : 0;
+                    if (tiled)
+                    {
+                        k = ka + tid / R;
+                        row = tid % R;
+                    }
+                    for (int i = tid; i < total; i += T)
+                    {
+                        if (!tiled)
+                        {
+                            k = ka + i / R;
+                            row = i % R;
+                        }
+                        const int cw = st_cwr[cbuf + k * R + row];
+                        int g = NOT_SET;
+                        if (cw != CC_INVALID_CWR)
+                        {
+                            const int diff = cw - s.pc;
+                            g = goff + cw;
+                            if (diff < -half)
+                                g += N;
+                            else if (diff > half)
+                                g -= N;
+                            if (g < neg_limit)
+                                kbad = k < kbad ? k : kbad;
+                            tmin = g < tmin ? g : tmin;
+                            tmax = g > tmax ? g : tmax;
+                        }
+                        G[k * GS + row] = g;
+                        k += kstep;
+                    }
+                    tmin = cc_warp_min(tmin);
+                    tmax = cc_warp_max(tmax);
+                    kbad = cc_warp_min(kbad);
+                    if (lane == 0)
+                    {
+                        atomicMin(&f_misc[1], tmin);
+                        atomicMax(&f_misc[2], tmax);
+                        if (kbad < kb)
+                            atomicMin(&f_misc[0], kbad);
+                    }
+                }
+                __syncthreads();
+                // ---- phase B: rearmost / foremost column of every firing (one warp per firing, lanes over rows) ----
+                for (int k = ka + warp; k < kb; k += nwarps)
+                {
+                    int lmin = 0x7fffffff, lmax = NOT_SET;
+                    for (int row = lane; row < R; row += CC_WARP)
                     {
                         const int g = G[k * GS + row];
-                        if (g == NOT_SET || g < f_P[k]) // invalid, or too far behind (cpp:210-221)
-                            continue;
-                        int lo = rm + 1;
-                        if (lo < g - W + 1)
-                            lo = g - W + 1;
-                        for (int c = lo; c < g; c++)
-                            wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
-                        wdist[((g + base_slot) & (W - 1)) * R + row] = st_dist[cbuf + k * R + row];
-                        rm = g;
+                        if (g != NOT_SET)
+                        {
+                            lmin = g < lmin ? g : lmin;
+                            lmax = g > lmax ? g : lmax;
+                        }
                     }
-                    rmx[row] = rm;
-                }
-                // phase D: outputs of every stored point
-                const int total = kc * R;
-                for (int i = tid; i < total; i += T)
-                {
-                    const int k = i / R, row = i - k * R;
-                    const int g = G[k * GS + row];
-                    if (g == NOT_SET || g < f_P[k])
-                        continue;
-                    int local = base_local + g;
-                    local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-                    p.pos[static_cast<size_t>(local) * R + row].w = st_dist[cbuf + i];
-                    const int cw = st_cwr[cbuf + i];
-                    const int diff = cw - pc;
-                    p.o_g[k0 * R + i] = g;
-                    p.o_rot[k0 * R + i] = prev_rot + (diff < -half ? 1 : (diff > half ? -1 : 0));
-                }
-                // columns completed by each firing (cpp:289-291)
-                for (int k = tid; k < kc; k += T)
-                    for (int c = f_P[k]; c < f_P[k + 1]; c++)
-                        p.col_trigger[c - colbase_rel] = k0 + k;
-                const int Pnew = f_P[kc];
-                pc += Pnew - Prel;
-                while (pc >= N)
-                {
-                    pc -= N;
-                    prev_rot++;
-                }
-                Prel = Pnew;
-                Frel = Pnew;
-                Fmrel = f_misc[3];
-                if (base + Fmrel > ring_end)
-                    ring_end = base + Fmrel;
-            }
-            __syncthreads();
-        }
-        if (fast)
-            continue;
-
-      for (int k = k0; k < k0 + kc; k++)
-      {
-        const int sbase = cbuf + (k - k0) * R;
-        const bool p_positive = p_positive_at_start || Prel > 0;
-        const int goff = Prel - pc;
-        int lmin = 0x7fffffff, lmax = NOT_SET;
-        for (int row = tid; row < R; row += T)
-        {
-            const int cw = st_cwr[sbase + row];
-            if (cw == CC_INVALID_CWR)
-                continue;
-            const float d = st_dist[sbase + row];
-            int g = goff + cw;
-            const int diff = cw - pc;
-            int rot = prev_rot;
-            if (diff < -half)
-            {
-                g += N;
-                rot++;
-            }
-            else if (p_positive && diff > half)
-            {
-                g -= N;
-                rot--;
-            }
-            if (g < neg_limit)
-                continue; // reference: out-of-bounds access (undefined); the point is dropped here
-            int rm = rmx[row];
-            const int slot = ((g + base_slot) & (W - 1)) * R + row;
-            float cd = nanv;
-            if (g <= rm)
-            {
-                if (g > rm - W)
-                    cd = wdist[slot];
-                else
-                {
-                    int local = base_local + g;
-                    local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-                    cd = p.pos[static_cast<size_t>(local) * R + row].w;
-                }
-            }
-            int slot_w = slot;
-            if (!cc_isnan(cd) && !cc_isnan(d))
-            {
-                const int g1 = g + 1;
-                const int slot1 = ((g1 + base_slot) & (W - 1)) * R + row;
-                float nd = nanv;
-                if (g1 <= rm)
-                {
-                    if (g1 > rm - W)
-                        nd = wdist[slot1];
-                    else
+                    lmin = cc_warp_min(lmin);
+                    lmax = cc_warp_max(lmax);
+                    if (lane == 0)
                     {
-                        int local = base_local + g1;
-                        local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-                        nd = p.pos[static_cast<size_t>(local) * R + row].w;
+                        f_rear[k] = lmin;
+                        f_fore[k] = lmax;
                     }
                 }
-                if (cc_isnan(nd))
+                __syncthreads();
+                // ---- phase S: rearmost / foremost so far before every firing = prefix maxima (cpp:263-266) ----
+                if (warp == 0)
                 {
-                    g = g1;
-                    cd = nd;
-                    slot_w = slot1;
+                    const int n = kb - ka;
+                    const int per = (n + CC_WARP - 1) / CC_WARP;
+                    const int a = ka + lane * per, b = (a + per < kb) ? a + per : kb;
+                    int mP = NOT_SET, mF = NOT_SET, kbad = kb;
+                    for (int k = a; k < b; k++)
+                    {
+                        const int rear = f_rear[k], fore = f_fore[k];
+                        if (rear != 0x7fffffff)
+                        {
+                            if (fore - rear > N / 2) // cpp:252-261
+                                kbad = k < kbad ? k : kbad;
+                            mP = rear > mP ? rear : mP;
+                            mF = fore > mF ? fore : mF;
+                        }
+                    }
+                    // exclusive scan of the per-lane maxima
+                    int eP = mP, eF = mF;
+                    for (int o = 1; o < CC_WARP; o <<= 1)
+                    {
+                        const int vP = __shfl_up_sync(CC_FULL_MASK, eP, o), vF = __shfl_up_sync(CC_FULL_MASK, eF, o);
+                        if (lane >= o)
+                        {
+                            eP = vP > eP ? vP : eP;
+                            eF = vF > eF ? vF : eF;
+                        }
+                    }
+                    int pP = __shfl_up_sync(CC_FULL_MASK, eP, 1), pF = __shfl_up_sync(CC_FULL_MASK, eF, 1);
+                    if (lane == 0)
+                    {
+                        pP = NOT_SET;
+                        pF = NOT_SET;
+                    }
+                    int Pcur = pP > s.Prel ? pP : s.Prel, Fcur = pF > s.Fmrel ? pF : s.Fmrel;
+                    for (int k = a; k < b; k++)
+                    {
+                        f_P[k] = Pcur;
+                        f_F[k] = Fcur;
+                        const int rear = f_rear[k], fore = f_fore[k];
+                        if (rear != 0x7fffffff)
+                        {
+                            Pcur = rear > Pcur ? rear : Pcur;
+                            Fcur = fore > Fcur ? fore : Fcur;
+                        }
+                        if (Pcur - s.colbase_rel > p.maxcols)
+                            kbad = k < kbad ? k : kbad; // the per-firing path raises the error
+                    }
+                    if (a < kb && b == kb) // the lane whose range ends the run publishes the totals
+                    {
+                        f_P[kb] = Pcur;
+                        f_F[kb] = Fcur;
+                    }
+                    kbad = cc_warp_min(kbad);
+                    if (lane == 0)
+                    {
+                        const int gmin = f_misc[1], gmax = f_misc[2];
+                        if (gmax != NOT_SET && (gmax - s.Prel >= half || gmin - s.Prel <= -half || gmax - gmin >= half))
+                            kbad = ka; // the unwrap decision could depend on how far the rearmost column moves
+                        if (kbad < kb)
+                            atomicMin(&f_misc[0], kbad);
+                    }
                 }
-            }
-            if (!cc_isnan(cd) && (cc_isnan(d) || d >= cd))
-                continue;
-            const bool too_far_behind = f_init && g < Frel;
-            if (!too_far_behind)
-            {
-                if (g > rm)
+                // ---- phase C1: per (row, segment): columns strictly increasing inside the segment ----
+                for (int item = tid; item < R * nparts; item += T)
                 {
-                    int lo = rm + 1;
-                    if (lo < g - W + 1)
-                        lo = g - W + 1;
-                    for (int c = lo; c < g; c++)
-                        wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
-                    rmx[row] = g;
-                    rm = g;
+                    const int row = item % R, part = item / R;
+                    const int a = ka + part * seg, b = (a + seg < kb) ? a + seg : kb;
+                    int first = NOT_SET, firstk = kb, last = NOT_SET, kbad = kb;
+                    for (int k = a; k < b; k++)
+                    {
+                        const int g = G[k * GS + row];
+                        if (g != NOT_SET)
+                        {
+                            if (first == NOT_SET)
+                            {
+                                first = g;
+                                firstk = k;
+                            }
+                            else if (g <= last)
+                                kbad = k < kbad ? k : kbad;
+                            last = g;
+                        }
+                    }
+                    seg_first[item] = first;
+                    seg_firstk[item] = firstk;
+                    seg_last[item] = last;
+                    if (kbad < kb)
+                        atomicMin(&f_misc[0], kbad);
                 }
-                if (g > rm - W)
-                    wdist[slot_w] = d;
-                int local = base_local + g;
-                local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-                p.pos[static_cast<size_t>(local) * R + row].w = d; // write-through
-                const int idx = k * R + row;
-                p.o_g[idx] = g;
-                p.o_rot[idx] = rot;
+                __syncthreads();
+                // ---- phase C1b: first column of a segment beyond everything before it (and the row's front) ----
+                for (int item = tid; item < R * nparts; item += T)
+                {
+                    const int row = item % R, part = item / R;
+                    const int first = seg_first[item];
+                    if (first == NOT_SET)
+                        continue;
+                    int prev = rmx[row];
+                    for (int q = part - 1; q >= 0; q--)
+                    {
+                        const int l = seg_last[q * R + row];
+                        if (l != NOT_SET)
+                        {
+                            prev = l;
+                            break;
+                        }
+                    }
+                    if (first <= prev)
+                        atomicMin(&f_misc[0], seg_firstk[item]);
+                }
+                __syncthreads();
+                kgood = f_misc[0];
+                n_attempts++;
+                n_fast += kgood - ka;
+                if (kgood > ka)
+                {
+                    // ---- phase C2a: new front of every row = its last stored column in [ka, kgood) ----
+                    for (int item = tid; item < R * nparts; item += T)
+                    {
+                        const int row = item % R, part = item / R;
+                        const int a = ka + part * seg;
+                        int b = (a + seg < kb) ? a + seg : kb;
+                        b = b < kgood ? b : kgood;
+                        int last = NOT_SET;
+                        for (int k = a; k < b; k++)
+                        {
+                            const int g = G[k * GS + row];
+                            if (g != NOT_SET && g >= f_P[k]) // not "too far behind" (cpp:210-221)
+                                last = g;
+                        }
+                        if (last != NOT_SET)
+                            atomicMax(&rm_new[row], last);
+                    }
+                    __syncthreads();
+                    // ---- phase C2b: the window cells between the old and the new front start out empty ----
+                    for (int item = tid; item < R * nparts; item += T)
+                    {
+                        const int row = item % R, part = item / R;
+                        const int rn = rm_new[row];
+                        int lo = rmx[row] + 1;
+                        if (lo < rn - W + 1)
+                            lo = rn - W + 1;
+                        for (int c = lo + part; c <= rn; c += nparts)
+                            wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
+                    }
+                    __syncthreads();
+                    // ---- phase D: every stored point: window, ring write-through, resolved column ----
+                    {
+                        const int total = (kgood - ka) * R;
+                        int k, row;
+                        const bool tiled = (T % R) == 0;
+                        const int kstep = tiled ? T / R : 0;
+                        if (tiled)
+                        {
+                            k = ka + tid / R;
+                            row = tid % R;
+                        }
+                        for (int i = tid; i < total; i += T)
+                        {
+                            if (!tiled)
+                            {
+                                k = ka + i / R;
+                                row = i % R;
+                            }
+                            const int g = G[k * GS + row];
+                            if (g != NOT_SET && g >= f_P[k])
+                            {
+                                const float d = st_dist[cbuf + k * R + row];
+                                if (g > rm_new[row] - W)
+                                    wdist[((g + base_slot) & (W - 1)) * R + row] = d;
+                                int local = base_local + g;
+                                local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                                p.pos[static_cast<size_t>(local) * R + row].w = d;
+                                const int diff = st_cwr[cbuf + k * R + row] - s.pc;
+                                const int idx = (k0 + k) * R + row;
+                                p.o_g[idx] = g;
+                                p.o_rot[idx] = s.prev_rot + (diff < -half ? 1 : (diff > half ? -1 : 0));
+                            }
+                            k += kstep;
+                        }
+                    }
+                    // columns completed by each firing (cpp:289-291)
+                    for (int k = ka + tid; k < kgood; k += T)
+                        for (int c = f_P[k]; c < f_P[k + 1]; c++)
+                            p.col_trigger[c - s.colbase_rel] = k0 + k;
+                    const int Pnew = f_P[kgood], Fnew = f_F[kgood];
+                    __syncthreads();
+                    for (int row = tid; row < R; row += T)
+                        rmx[row] = rm_new[row];
+                    s.pc += Pnew - s.Prel;
+                    while (s.pc >= N)
+                    {
+                        s.pc -= N;
+                        s.prev_rot++;
+                    }
+                    s.Prel = Pnew;
+                    s.Frel = Pnew;
+                    s.Fmrel = Fnew;
+                    if (base + s.Fmrel > s.ring_end)
+                        s.ring_end = base + s.Fmrel;
+                }
+                __syncthreads();
             }
-            lmin = g < lmin ? g : lmin;
-            lmax = g > lmax ? g : lmax;
-        }
-        int wmin = cc_warp_min(lmin), wmax = cc_warp_max(lmax);
-        if (nwarps > 1)
-        {
-            int* r = red + (k & 1) * (2 * CC_K1_MAXWARPS);
-            if (lane == 0)
+            ka = kgood;
+            if (ka >= kc)
+                break;
+
+            // ---- per-firing path: exact for everything; a few firings, then the fast path is tried again ----
+            const int kslow_end = (ka + CC_K1_SLOW_RUN < kc) ? ka + CC_K1_SLOW_RUN : kc;
+            for (int k = ka; k < kslow_end; k++)
             {
-                r[2 * warp] = wmin;
-                r[2 * warp + 1] = wmax;
+                const int sbase = cbuf + k * R;
+                const bool p_positive = p_positive_at_start || s.Prel > 0;
+                const int goff = s.Prel - s.pc;
+                int lmin = 0x7fffffff, lmax = NOT_SET;
+                for (int row = tid; row < R; row += T)
+                {
+                    const int cw = st_cwr[sbase + row];
+                    if (cw == CC_INVALID_CWR)
+                        continue;
+                    const float d = st_dist[sbase + row];
+                    int g = goff + cw;
+                    const int diff = cw - s.pc;
+                    int rot = s.prev_rot;
+                    if (diff < -half)
+                    {
+                        g += N;
+                        rot++;
+                    }
+                    else if (p_positive && diff > half)
+                    {
+                        g -= N;
+                        rot--;
+                    }
+                    if (g < neg_limit)
+                        continue; // reference: out-of-bounds access (undefined); the point is dropped here
+                    int rm = rmx[row];
+                    const int slot = ((g + base_slot) & (W - 1)) * R + row;
+                    float cd = nanv;
+                    if (g <= rm)
+                    {
+                        if (g > rm - W)
+                            cd = wdist[slot];
+                        else
+                        {
+                            int local = base_local + g;
+                            local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                            cd = p.pos[static_cast<size_t>(local) * R + row].w;
+                        }
+                    }
+                    int slot_w = slot;
+                    if (!cc_isnan(cd) && !cc_isnan(d))
+                    {
+                        const int g1 = g + 1;
+                        const int slot1 = ((g1 + base_slot) & (W - 1)) * R + row;
+                        float nd = nanv;
+                        if (g1 <= rm)
+                        {
+                            if (g1 > rm - W)
+                                nd = wdist[slot1];
+                            else
+                            {
+                                int local = base_local + g1;
+                                local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                                nd = p.pos[static_cast<size_t>(local) * R + row].w;
+                            }
+                        }
+                        if (cc_isnan(nd))
+                        {
+                            g = g1;
+                            cd = nd;
+                            slot_w = slot1;
+                        }
+                    }
+                    if (!cc_isnan(cd) && (cc_isnan(d) || d >= cd))
+                        continue;
+                    const bool too_far_behind = s.f_init && g < s.Frel;
+                    if (!too_far_behind)
+                    {
+                        if (g > rm)
+                        {
+                            int lo = rm + 1;
+                            if (lo < g - W + 1)
+                                lo = g - W + 1;
+                            for (int c = lo; c < g; c++)
+                                wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
+                            rmx[row] = g;
+                            rm = g;
+                        }
+                        if (g > rm - W)
+                            wdist[slot_w] = d;
+                        int local = base_local + g;
+                        local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                        p.pos[static_cast<size_t>(local) * R + row].w = d; // write-through
+                        const int idx = (k0 + k) * R + row;
+                        p.o_g[idx] = g;
+                        p.o_rot[idx] = rot;
+                    }
+                    lmin = g < lmin ? g : lmin;
+                    lmax = g > lmax ? g : lmax;
+                }
+                int wmin = 0x7fffffff, wmax = NOT_SET;
+                if (warp < row_warps)
+                {
+                    wmin = cc_warp_min(lmin);
+                    wmax = cc_warp_max(lmax);
+                }
+                if (nwarps > 1)
+                {
+                    int* r = red + (k & 1) * (2 * 32);
+                    if (lane == 0 && warp < row_warps)
+                    {
+                        r[2 * warp] = wmin;
+                        r[2 * warp + 1] = wmax;
+                    }
+                    __syncthreads();
+                    wmin = 0x7fffffff;
+                    wmax = NOT_SET;
+                    for (int w = 0; w < row_warps; w++)
+                    {
+                        const int a = r[2 * w], b = r[2 * w + 1];
+                        wmin = a < wmin ? a : wmin;
+                        wmax = b > wmax ? b : wmax;
+                    }
+                }
+                if (wmin != 0x7fffffff)
+                {
+                    const int rear = wmin, fore = wmax;
+                    if (fore - rear > N / 2) // cpp:252-261
+                    {
+                        s.reset_required = 1;
+                        continue;
+                    }
+                    if (rear > s.Prel)
+                    {
+                        s.pc += rear - s.Prel;
+                        while (s.pc >= N)
+                        {
+                            s.pc -= N;
+                            s.prev_rot++;
+                        }
+                        s.Prel = rear;
+                    }
+                    if (!s.fm_init || fore > s.Fmrel)
+                    {
+                        s.Fmrel = fore;
+                        s.fm_init = true;
+                    }
+                }
+                if (!s.fm_init)
+                    continue;
+                if (s.ring_start == -1)
+                {
+                    s.ring_start = base + s.Prel;
+                    s.first_unpub = base + s.Prel;
+                }
+                if (base + s.Fmrel > s.ring_end)
+                    s.ring_end = base + s.Fmrel;
+                if (!s.f_init)
+                {
+                    s.f_init = true;
+                    s.Frel = s.Prel;
+                    s.colbase_rel = s.Frel;
+                }
+                // columns [F, P) are complete: this firing's pose drives their segmentation (cpp:289-291)
+                if (s.Prel > s.Frel)
+                {
+                    if (s.Prel - s.colbase_rel > p.maxcols)
+                    {
+                        s.error = CC_DEV_TOO_MANY_COLUMNS;
+                        stop = true;
+                        break;
+                    }
+                    for (int c = s.Frel + tid; c < s.Prel; c += T)
+                        p.col_trigger[c - s.colbase_rel] = k0 + k;
+                    s.Frel = s.Prel;
+                }
             }
             __syncthreads();
-            for (int w = 0; w < nwarps; w++)
-            {
-                const int a = r[2 * w], b = r[2 * w + 1];
-                wmin = a < wmin ? a : wmin;
-                wmax = b > wmax ? b : wmax;
-            }
+            n_slow += kslow_end - ka;
+            ka = kslow_end;
         }
-        if (wmin != 0x7fffffff)
-        {
-            const int rear = wmin, fore = wmax;
-            if (fore - rear > N / 2) // cpp:252-261
-            {
-                reset_required = 1;
-                continue;
-            }
-            if (rear > Prel)
-            {
-                pc += rear - Prel;
-                while (pc >= N)
-                {
-                    pc -= N;
-                    prev_rot++;
-                }
-                Prel = rear;
-            }
-            if (!fm_init || fore > Fmrel)
-            {
-                Fmrel = fore;
-                fm_init = true;
-            }
-        }
-        if (!fm_init)
-            continue;
-        if (ring_start == -1)
-        {
-            ring_start = base + Prel;
-            first_unpub = base + Prel;
-        }
-        if (base + Fmrel > ring_end)
-            ring_end = base + Fmrel;
-        if (!f_init)
-        {
-            f_init = true;
-            Frel = Prel;
-            colbase_rel = Frel;
-        }
-        // columns [F, P) are complete: this firing's pose drives their segmentation (cpp:289-291)
-        if (Prel > Frel)
-        {
-            if (Prel - colbase_rel > p.maxcols)
-            {
-                error = CC_DEV_TOO_MANY_COLUMNS;
-                stop = true;
-                break;
-            }
-            for (int c = Frel + tid; c < Prel; c += T)
-                p.col_trigger[c - colbase_rel] = k;
-            Frel = Prel;
-        }
-      }
-      __syncthreads();
     }
     __syncthreads();
     for (int row = tid; row < R; row += T)
@@ -621,20 +779,23 @@ __global__ void k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     if (tid == 0)
     {
         st->scan_base = base;
-        st->P = base + Prel;
-        st->foremost = fm_init ? base + Fmrel : -1;
-        st->F = f_init ? base + Frel : -1;
-        st->ring_start = ring_start;
-        st->ring_end = ring_end;
-        st->first_unpub = first_unpub;
-        st->reset_required = reset_required;
-        st->colbase = f_init ? base + colbase_rel : -1;
-        st->ncols = f_init ? Frel - colbase_rel : 0;
-        if (error)
-            st->error = error;
-        st->clear_from = ring_start;
-        st->clear_to = ring_start;
-        st->push_first_unpub_old = first_unpub;
+        st->scan_fast_firings = n_fast;
+        st->scan_slow_firings = n_slow;
+        st->scan_fast_attempts = n_attempts;
+        st->P = base + s.Prel;
+        st->foremost = s.fm_init ? base + s.Fmrel : -1;
+        st->F = s.f_init ? base + s.Frel : -1;
+        st->ring_start = s.ring_start;
+        st->ring_end = s.ring_end;
+        st->first_unpub = s.first_unpub;
+        st->reset_required = s.reset_required;
+        st->colbase = s.f_init ? base + s.colbase_rel : -1;
+        st->ncols = s.f_init ? s.Frel - s.colbase_rel : 0;
+        if (s.error)
+            st->error = s.error;
+        st->clear_from = s.ring_start;
+        st->clear_to = s.ring_start;
+        st->push_first_unpub_old = s.first_unpub;
         st->n_edges = 0;
         st->n_flagged = 0;
         st->danger_col = CC_COL_INF;
@@ -982,12 +1143,16 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
 // K2c  running maximum of the columns' minimum azimuth (the value every finish pass compares against,
 //      cpp:884-885), continued across pushes. Single block, chunked scan.
 // =====================================================================================================
-__global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p)
+__device__ void d_snapshot(CcDevPtrs p, int spec);
+
+__global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 {
     CC_SMEM(smem);
     double* part = reinterpret_cast<double*>(smem);
     if (blockIdx.x != 0)
         return;
+    if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts)
+        d_snapshot(p, 1);
     const int ncols = p.st->ncols;
     const int T = blockDim.x, t = threadIdx.x;
     const int chunk = (ncols + T - 1) / T;
@@ -1009,6 +1174,8 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p)
     }
 }
 
+
+
 // =====================================================================================================
 // K3a  association probe (cpp:698-835): every non-ignored cell of the new columns walks its field of view and
 //      records its first hit (the tree it joins) and every later hit (tree<->tree links). The walk is purely
@@ -1017,101 +1184,133 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p)
 //      seen before this column, or its tree is already finished -- flags the column for the column-sequential
 //      exact path. No persistent state is modified here.
 // =====================================================================================================
-__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int tile_cols, int use_smem)
 {
+    CC_SMEM(smem);
+    float4* win = reinterpret_cast<float4*>(smem); // association view of the tile's columns + the window before them
     const int R = cfg.R;
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
-    const int total = ncols * R;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    const int msr = cfg.max_steps_row;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int ntiles = (ncols + tile_cols - 1) / tile_cols;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     {
-        const int ci = idx / R, row = idx % R;
-        int local = base_local + ci;
-        if (local >= cfg.ringcols)
-            local -= cfg.ringcols;
-        const unsigned int q = static_cast<unsigned int>(local) * R + row;
-        s_parent[idx] = CC_NONE;
-        const float4 a = p.assoc[q];
-        if (cc_isnan(a.x))
+        const int ci0 = tile * tile_cols;
+        const int nc = (ncols - ci0) < tile_cols ? (ncols - ci0) : tile_cols;
+        // ring column of window column 0 (msr columns before the tile)
+        int wl0 = (base_local + ci0 - msr) % cfg.ringcols;
+        if (wl0 < 0)
+            wl0 += cfg.ringcols;
+        if (use_smem)
         {
-            p.visited[q] = 0;
-            continue; // is_ignored
-        }
-        const float mad = p.mad[q];
-        const double prev_runmax = ci > 0 ? p.col_runmax[ci - 1] : p.st->runmax_carry;
-        int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
-        steps_back = steps_back < cfg.max_steps_row ? steps_back : cfg.max_steps_row;
-        unsigned int first = CC_NONE;
-        int visited = 0;
-        bool flagged = false;
-        int other_col = local;
-        for (int back = 0; back <= steps_back; back++)
-        {
-            for (int dir = -1; dir <= 1; dir += 2)
+            // stage the sliding window: each window column is one contiguous R*16-byte span of the ring
+            const int wcells = (msr + nc) * R;
+            for (int i = tid; i < wcells; i += T)
             {
-                if (dir == 1 && back == 0)
-                    continue;
-                int steps_v = (dir == 1 || back == 0) ? 1 : 0;
-                int orow = (dir == 1 || back == 0) ? row + dir : row;
-                while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
+                const int w = i / R, row = i - w * R;
+                int local = wl0 + w;
+                if (local >= cfg.ringcols)
+                    local -= cfg.ringcols;
+                win[i] = p.assoc[static_cast<size_t>(local) * R + row];
+            }
+            __syncthreads();
+        }
+        for (int cell = tid; cell < nc * R; cell += T)
+        {
+            const int cl = cell / R, row = cell - cl * R;
+            const int ci = ci0 + cl;
+            const int wq = msr + cl; // window column of this cell
+            int local = wl0 + wq;
+            if (local >= cfg.ringcols)
+                local -= cfg.ringcols;
+            const unsigned int q = static_cast<unsigned int>(local) * R + row;
+            const int idx = ci * R + row;
+            s_parent[idx] = CC_NONE;
+            const float4 a = use_smem ? win[wq * R + row] : p.assoc[q];
+            if (cc_isnan(a.x))
+            {
+                p.visited[q] = 0;
+                continue; // is_ignored
+            }
+            const float mad = p.mad[q];
+            const double prev_runmax = ci > 0 ? p.col_runmax[ci - 1] : p.st->runmax_carry;
+            int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+            steps_back = steps_back < msr ? steps_back : msr;
+            unsigned int first = CC_NONE;
+            int visited = 0;
+            bool flagged = false;
+            for (int back = 0; back <= steps_back; back++)
+            {
+                const int wo = wq - back;
+                int olocal = wl0 + wo;
+                if (olocal >= cfg.ringcols)
+                    olocal -= cfg.ringcols;
+                for (int dir = -1; dir <= 1; dir += 2)
                 {
-                    const unsigned int o = static_cast<unsigned int>(other_col) * R + orow;
-                    const float4 b = p.assoc[o];
-                    visited++;
-                    if (fabsf(b.w - a.w) > mad)
-                        break;
-                    if (!cc_isnan(b.x))
+                    if (dir == 1 && back == 0)
+                        continue;
+                    int steps_v = (dir == 1 || back == 0) ? 1 : 0;
+                    int orow = (dir == 1 || back == 0) ? row + dir : row;
+                    while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
                     {
-                        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-                        if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
+                        const unsigned int o = static_cast<unsigned int>(olocal) * R + orow;
+                        const float4 b = use_smem ? win[wo * R + orow] : p.assoc[o];
+                        visited++;
+                        if (fabsf(b.w - a.w) > mad)
+                            break;
+                        if (!cc_isnan(b.x))
                         {
-                            // could the reference have refused this hit?
-                            const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
-                            if (finish_o <= prev_runmax)
-                                flagged = true;
-                            if (back > ci)
+                            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                            if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
                             {
-                                const unsigned int ro = p.tparent[o];
-                                if (ro == CC_NONE || p.tstate[ro] != 0)
+                                // could the reference have refused this hit?
+                                const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                                if (finish_o <= prev_runmax)
                                     flagged = true;
-                            }
-                            if (first == CC_NONE)
-                                first = o;
-                            else if (o != first)
-                            {
-                                const int e = atomicAdd(&p.st->n_edges, 1);
-                                if (e < p.cap_edges)
+                                if (back > ci)
                                 {
-                                    p.edge_a[e] = q;
-                                    p.edge_b[e] = o;
+                                    const unsigned int ro = p.tparent[o];
+                                    if (ro == CC_NONE || p.tstate[ro] != 0)
+                                        flagged = true;
                                 }
-                                else
-                                    p.st->error = CC_DEV_LIST_OVERFLOW;
+                                if (first == CC_NONE)
+                                    first = o;
+                                else if (o != first)
+                                {
+                                    const int e = atomicAdd(&p.st->n_edges, 1);
+                                    if (e < p.cap_edges)
+                                    {
+                                        p.edge_a[e] = q;
+                                        p.edge_b[e] = o;
+                                    }
+                                    else
+                                        p.st->error = CC_DEV_LIST_OVERFLOW;
+                                }
                             }
                         }
+                        if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps)
+                            break;
+                        orow += dir;
+                        steps_v++;
                     }
-                    if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps)
-                        break;
-                    orow += dir;
-                    steps_v++;
                 }
+                if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+                    break;
             }
-            if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
-                break;
-            other_col--;
-            if (other_col < 0)
-                other_col += cfg.ringcols;
+            s_parent[idx] = first == CC_NONE ? q : first;
+            p.visited[q] = static_cast<unsigned short>(visited);
+            if (cfg.debug_flag_period > 0 && ((colbase + ci) % cfg.debug_flag_period) == 0)
+                flagged = true;
+            if (flagged)
+            {
+                p.col_flag[ci] = 1;
+                atomicAdd(&p.st->n_flagged, 1);
+            }
         }
-        s_parent[idx] = first == CC_NONE ? q : first;
-        p.visited[q] = static_cast<unsigned short>(visited);
-        if (cfg.debug_flag_period > 0 && ((colbase + ci) % cfg.debug_flag_period) == 0)
-            flagged = true;
-        if (flagged)
-        {
-            p.col_flag[ci] = 1;
-            atomicAdd(&p.st->n_flagged, 1);
-        }
+        if (use_smem)
+            __syncthreads();
     }
 }
 
@@ -1170,7 +1369,7 @@ CC_DEV bool cc_spec_ok(const CcDevState* st, int guard)
 //      contribution to the root (finished_at, width, tree_num_points: cpp:661-672); (3) apply tree<->tree
 //      links (cpp:675-696) to the union-find.
 // =====================================================================================================
-__global__ void k_snapshot(CcDevPtrs p, int spec)
+__device__ void d_snapshot(CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1189,6 +1388,11 @@ __global__ void k_snapshot(CcDevPtrs p, int spec)
         p.st->sv_n_clusters = p.st->n_clusters;
         p.st->sv_n_cluster_points = p.st->n_cluster_points;
     }
+}
+
+__global__ void k_snapshot(CcDevPtrs p, int guard)
+{
+    d_snapshot(p, guard);
 }
 
 __global__ void k_restore(CcDevPtrs p)
@@ -1423,7 +1627,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
 //               running maximum); anything that would need the reference's forced finish (cpp:909-919) aborts.
 //     spec = 0: c0 == c1, exact single pass including the forced finish.
 // =====================================================================================================
-__global__ void k_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+__device__ void d_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1460,7 +1664,7 @@ __global__ void k_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec
     }
 }
 
-__global__ void k_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
+__device__ void d_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1478,7 +1682,7 @@ __global__ void k_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
     }
 }
 
-__global__ void k_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
+__device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
 {
     if (!cc_spec_ok(p.st, guard))
         return;
@@ -1566,7 +1770,7 @@ __global__ void k_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
     }
 }
 
-__global__ void k_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+__device__ void d_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1598,7 +1802,7 @@ __global__ void k_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec
     }
 }
 
-__global__ void k_fin_copyback(CcDevPtrs p, int spec)
+__device__ void d_fin_copyback(CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1615,7 +1819,7 @@ __global__ void k_fin_copyback(CcDevPtrs p, int spec)
 // that were still unfinished when the pass started (cpp:943-959), or column + 1. G[r] = last column at which
 // some tree rooted in column gbase + r is unfinished; with PG = prefix max of G, the answer for column c is the
 // first r with PG[r] >= c. Single block.
-__global__ void k_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
+__device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -1675,6 +1879,31 @@ __global__ void k_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
         st->runmax_carry = p.col_runmax[c1 - colbase];
         st->n_ulist = *p.n_new_ulist;
     }
+}
+
+__device__ void d_push_done(CcDevPtrs p, int guard);
+
+// All list-sized phases of a finish pass in ONE CTA (the unfinished-tree list holds 10^2..10^4 entries: a single
+// CTA with block-wide barriers between the phases is faster than six dependent launches).
+__global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
+                                                  int exact, int last)
+{
+    if (blockIdx.x != 0)
+        return;
+    d_fin_init(cfg, p, ci0, ci1, guard);
+    __syncthreads();
+    d_fin_agg(cfg, p, guard);
+    __syncthreads();
+    d_fin_decide(cfg, p, guard, exact);
+    __syncthreads();
+    d_fin_mark(cfg, p, seq, guard);
+    __syncthreads();
+    d_fin_copyback(p, guard);
+    __syncthreads();
+    d_fin_columns(cfg, p, guard);
+    __syncthreads();
+    if (last && threadIdx.x == 0)
+        d_push_done(p, guard);
 }
 
 // Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
@@ -1766,7 +1995,12 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
 
 // end of a push: remember the range of columns that left the ring (recycled at the start of the next push) and
 // advance sc_cluster_counter_ (cpp:939) by the ids handed out. guard as in cc_spec_ok.
+__device__ void d_push_done(CcDevPtrs p, int guard);
 __global__ void k_push_done(CcDevPtrs p, int guard)
+{
+    d_push_done(p, guard);
+}
+__device__ void d_push_done(CcDevPtrs p, int guard)
 {
     CcDevState* st = p.st;
     if (guard == 1 && (st->error != 0 || st->n_flagged != 0 || st->abort != 0))

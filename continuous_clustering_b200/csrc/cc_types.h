@@ -35,8 +35,9 @@ enum : uint8_t
 #define CC_NONE 0xffffffffu
 #define CC_INVALID_CWR (-2147483647 - 1)
 #define CC_COL_INF 0x3fffffffffffffffLL
-#define CC_K1_MAXWARPS 8 /* the insertion scan runs one thread per row, up to 256 rows */
-#define CC_K1_CHUNK 32  /* firings staged per cp.async group by the insertion scan */
+#define CC_K1_POINTS_PER_CHUNK 8192 /* the insertion scan stages min(128, 8192 / rows) firings per cp.async group */
+#define CC_K1_MAX_CHUNK 128
+#define CC_K1_SLOW_RUN 4 /* firings that go through the per-firing path after an irregular one */
 #define CC_K1_WINDOW 64 /* columns of per-row occupancy history kept in shared memory by the insertion scan */
 
 // device-detected conditions (CcDevState::error)
@@ -96,6 +97,8 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long scan_base;            // column that o_g is relative to (rearmost column when the push started)
     long long push_first_unpub_old; // first_unpub before the first finish pass of this push
     int sv_n_clusters, sv_n_cluster_points;
+    int scan_fast_firings, scan_slow_firings, scan_fast_attempts; // insertion scan statistics of this push
+    int pad_;
 };
 
 struct CcCluster // device -> host record of one finished cluster with more than 5 points (cpp:936-940)

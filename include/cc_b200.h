@@ -158,7 +158,7 @@ typedef struct cc_batch_info
     int32_t used_exact_path;         /* 1 if the batch needed the column-sequential exact kernels */
     int32_t gpu_launches;            /* kernels launched for this batch */
     float device_ms;                 /* CUDA-event time of the batch's kernels on the handle's stream */
-    int32_t pad_;
+    int32_t slow_insert_firings;     /* firings that went through the per-firing insertion path (collisions) */
 } cc_batch_info_t;
 
 /* Field selector + destination pointers for cc_read_columns. Each non-NULL pointer receives

@@ -76,6 +76,11 @@ static inline T __shfl_down_sync(unsigned, T v, int)
     return v;
 }
 template<typename T>
+static inline T __shfl_up_sync(unsigned, T v, int)
+{
+    return v;
+}
+template<typename T>
 static inline T __shfl_xor_sync(unsigned, T v, int)
 {
     return v;

@@ -30,9 +30,11 @@ def record(cc, pts, poses, chunk):
     events, gcols, gcells, ccols, ccells, clusters, cpoints = [], [], [], [], [], [], []
     n_events = 0
     used_exact = 0
+    slow_firings = 0
     for a in range(0, pts.shape[0], chunk):
         res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
         used_exact += int(res.info.used_exact_path)
+        slow_firings += int(res.info.slow_insert_firings)
         ev = res.events
         if len(ev) == 0:
             continue
@@ -76,5 +78,5 @@ def record(cc, pts, poses, chunk):
         ground_cols=cat(gcols, np.int64), ground_cells=cat(gcells, drvlib.CELL_DTYPE, (0, rows)),
         cluster_cols=cat(ccols, np.int64), cluster_cells=cat(ccells, drvlib.CELL_DTYPE, (0, rows)),
         clusters=cat(clusters, drvlib.CLUSTER_DTYPE), cluster_points=cat(cpoints, drvlib.CLUSTER_POINT_DTYPE),
-        reset_required=cc.resetRequired(), used_exact_path=used_exact,
+        reset_required=cc.resetRequired(), used_exact_path=used_exact, slow_insert_firings=slow_firings,
     )

@@ -42,7 +42,7 @@ def run(spec, chunk, rotations, kwargs=None, emu=False, oracle_lib=None, cfg_ove
     tree_bad = int((ref["cluster_cells"]["tree_root_gcol"] != got["cluster_cells"]["tree_root_gcol"]).sum())
     if verbose:
         print(f"{spec} chunk={chunk} rot={rotations} {kwargs}: OK events={len(got['events'])} "
-              f"clusters={len(got['clusters'])} exact_pushes={got['used_exact_path']} tree_root_mismatch={tree_bad} "
+              f"clusters={len(got['clusters'])} exact_pushes={got['used_exact_path']} slow_insert_firings={got['slow_insert_firings']}/{pts.shape[0]} tree_root_mismatch={tree_bad} "
               f"oracle={t_ref:.2f}s impl={t_got:.2f}s launches={cc.total_launches}")
     cc.close()
     return ref, got
