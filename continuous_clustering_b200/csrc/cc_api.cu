@@ -44,6 +44,7 @@ struct cc_handle
     size_t probe_smem_set{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
+    unsigned int* d_s_links{nullptr};
     unsigned char* d_raw{nullptr};
     double* d_poses{nullptr};
     std::vector<void*> allocs;       // freed on destroy / re-reset
@@ -373,7 +374,7 @@ static int scan_smem_bytes(int R)
     const int T = scan_threads();
     const int nparts = T / R > 0 ? (T / R < C ? T / R : C) : 1;
     size_t words = static_cast<size_t>(CC_K1_WINDOW) * R + 2 * R + 4 * static_cast<size_t>(C) * R + 2 * 2 * 32 +
-                   static_cast<size_t>(C) * (R + 1) + 2 * C + 2 * (C + 1) + 3 * static_cast<size_t>(R) * nparts + 8;
+                   static_cast<size_t>(C) * (R + 1) + 2 * C + 2 * (C + 1) + 4 * static_cast<size_t>(R) * nparts + 8;
     return static_cast<int>(words * 4);
 }
 
@@ -445,6 +446,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_MAX_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.firing_rec, static_cast<size_t>(h->max_firings)));
         CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
         CC_CHECK(h, dev_alloc(h, L, &h->d_poses, static_cast<size_t>(h->max_firings) * 12));
         const size_t mc = static_cast<size_t>(h->maxcols);
@@ -455,6 +457,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.col_first_unpub, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_flag, mc));
         CC_CHECK(h, dev_alloc(h, L, &h->d_s_parent, mc * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &h->d_s_links, mc * h->R * CC_LINK_SLOTS));
         d.cap_ulist = 1 << 18;
         d.cap_edges = 1 << 22;
         d.cap_clusters = 1 << 16;
@@ -635,7 +638,7 @@ static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
         CC_RUN(h, k_snapshot, h->sm_count * 2, 256, 0, h->d, guard);
     CC_RUN(h, k_commit_copy, g, 256, 0, cfg, h->d, h->d_s_parent, ci0, ci1, guard);
     CC_RUN(h, k_commit_roots, g, 256, 0, cfg, h->d, ci0, ci1, guard);
-    CC_RUN(h, k_commit_links, g, 256, 0, cfg, h->d, ci0, ci1, guard);
+    CC_RUN(h, k_commit_links, g, 256, 0, cfg, h->d, h->d_s_parent, h->d_s_links, ci0, ci1, guard);
 }
 
 // Column-sequential exact path for pushes whose probe flagged a possibly refused association, that hit a cluster
@@ -738,7 +741,7 @@ static cc_status_t run_push(cc_handle* h, int n)
                 h->probe_smem_set = win_bytes;
             }
 #endif
-            CC_RUN(h, k_probe, h->sm_count * 4, 256, use_smem ? win_bytes : 0, cfg, h->d, h->d_s_parent, tile_cols, use_smem);
+            CC_RUN(h, k_probe, h->sm_count * 4, 256, use_smem ? win_bytes : 0, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem);
         }
         if (spec)
         {

@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
     int* seg_first = f_F + C + 1;                             // [R][nparts] first valid column of a segment
     int* seg_firstk = seg_first + R * nparts;                 // its firing
     int* seg_last = seg_firstk + R * nparts;                  // last valid column of a segment
-    int* f_misc = seg_last + R * nparts;                      // [0] k_bad, [1] gmin, [2] gmax
+    int* seg_stored = seg_last + R * nparts;                  // last stored column of a segment
+    int* f_misc = seg_stored + R * nparts;                    // [0] k_bad
     CcDevState* st = p.st;
+    float* ring_w = &p.pos[0].w; // distance of ring cell i is ring_w[4 * i]
 
     const long long base = st->P;
     const int base_slot = static_cast<int>(base & (W - 1));
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
 
     bool stop = false;
     int n_fast = 0, n_slow = 0, n_attempts = 0;
+    int slow_run = CC_K1_SLOW_RUN; // grows while fast attempts keep failing early (dense collisions)
     for (int chunk = 0; chunk < n_chunks && !stop; chunk++)
     {
         prefetch(chunk + 1);
@@ -306,82 +309,50 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                 if (tid == 0)
                 {
                     f_misc[0] = kb;
-                    f_misc[1] = 0x7fffffff;
-                    f_misc[2] = NOT_SET;
                 }
                 for (int row = tid; row < R; row += T)
                     rm_new[row] = rmx[row];
                 __syncthreads();
-                // ---- phase A: unwrap every point against the state at the start of the run ----
+                // ---- phase A+B: one warp per firing, lanes over rows: unwrap every point against the state at the
+                //      start of the run; rearmost / foremost column of the firing by warp reduction ----
                 {
                     const int goff = s.Prel - s.pc;
-                    int tmin = 0x7fffffff, tmax = NOT_SET, kbad = kb;
-                    const int total = (kb - ka) * R;
-                    int k, row;
-                    const bool tiled = (T % R) == 0;
-                    const int kstep = tiled ? T / R : 0;
-                    if (tiled)
+                    int kbad = kb;
+                    for (int k = ka + warp; k < kb; k += nwarps)
                     {
-                        k = ka + tid / R;
-                        row = tid % R;
-                    }
-                    for (int i = tid; i < total; i += T)
-                    {
-                        if (!tiled)
+                        int lmin = 0x7fffffff, lmax = NOT_SET;
+                        const int* cwp = st_cwr + cbuf + k * R;
+                        int* gp = G + k * GS;
+                        for (int row = lane; row < R; row += CC_WARP)
                         {
-                            k = ka + i / R;
-                            row = i % R;
+                            const int cw = cwp[row];
+                            int g = NOT_SET;
+                            if (cw != CC_INVALID_CWR)
+                            {
+                                const int diff = cw - s.pc;
+                                g = goff + cw;
+                                if (diff < -half)
+                                    g += N;
+                                else if (diff > half)
+                                    g -= N;
+                                if (g < neg_limit)
+                                    kbad = k < kbad ? k : kbad;
+                                lmin = g < lmin ? g : lmin;
+                                lmax = g > lmax ? g : lmax;
+                            }
+                            gp[row] = g;
                         }
-                        const int cw = st_cwr[cbuf + k * R + row];
-                        int g = NOT_SET;
-                        if (cw != CC_INVALID_CWR)
+                        lmin = cc_warp_min(lmin);
+                        lmax = cc_warp_max(lmax);
+                        if (lane == 0)
                         {
-                            const int diff = cw - s.pc;
-                            g = goff + cw;
-                            if (diff < -half)
-                                g += N;
-                            else if (diff > half)
-                                g -= N;
-                            if (g < neg_limit)
-                                kbad = k < kbad ? k : kbad;
-                            tmin = g < tmin ? g : tmin;
-                            tmax = g > tmax ? g : tmax;
+                            f_rear[k] = lmin;
+                            f_fore[k] = lmax;
                         }
-                        G[k * GS + row] = g;
-                        k += kstep;
                     }
-                    tmin = cc_warp_min(tmin);
-                    tmax = cc_warp_max(tmax);
                     kbad = cc_warp_min(kbad);
-                    if (lane == 0)
-                    {
-                        atomicMin(&f_misc[1], tmin);
-                        atomicMax(&f_misc[2], tmax);
-                        if (kbad < kb)
-                            atomicMin(&f_misc[0], kbad);
-                    }
-                }
-                __syncthreads();
-                // ---- phase B: rearmost / foremost column of every firing (one warp per firing, lanes over rows) ----
-                for (int k = ka + warp; k < kb; k += nwarps)
-                {
-                    int lmin = 0x7fffffff, lmax = NOT_SET;
-                    for (int row = lane; row < R; row += CC_WARP)
-                    {
-                        const int g = G[k * GS + row];
-                        if (g != NOT_SET)
-                        {
-                            lmin = g < lmin ? g : lmin;
-                            lmax = g > lmax ? g : lmax;
-                        }
-                    }
-                    lmin = cc_warp_min(lmin);
-                    lmax = cc_warp_max(lmax);
-                    if (lane == 0)
-                    {
-                        f_rear[k] = lmin;
-                        f_fore[k] = lmax;
-                    }
+                    if (lane == 0 && kbad < kb)
+                        atomicMin(&f_misc[0], kbad);
                 }
                 __syncthreads();
                 // ---- phase S: rearmost / foremost so far before every firing = prefix maxima (cpp:263-266) ----
@@ -390,7 +361,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                     const int n = kb - ka;
                     const int per = (n + CC_WARP - 1) / CC_WARP;
                     const int a = ka + lane * per, b = (a + per < kb) ? a + per : kb;
-                    int mP = NOT_SET, mF = NOT_SET, kbad = kb;
+                    int mP = NOT_SET, mF = NOT_SET, kbad = kb, gmin = 0x7fffffff;
                     for (int k = a; k < b; k++)
                     {
                         const int rear = f_rear[k], fore = f_fore[k];
@@ -400,6 +371,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                                 kbad = k < kbad ? k : kbad;
                             mP = rear > mP ? rear : mP;
                             mF = fore > mF ? fore : mF;
+                            gmin = rear < gmin ? rear : gmin;
                         }
                     }
                     // exclusive scan of the per-lane maxima
@@ -439,21 +411,24 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                         f_F[kb] = Fcur;
                     }
                     kbad = cc_warp_min(kbad);
+                    gmin = cc_warp_min(gmin);
+                    const int gmax = cc_warp_max(mF);
                     if (lane == 0)
                     {
-                        const int gmin = f_misc[1], gmax = f_misc[2];
                         if (gmax != NOT_SET && (gmax - s.Prel >= half || gmin - s.Prel <= -half || gmax - gmin >= half))
                             kbad = ka; // the unwrap decision could depend on how far the rearmost column moves
                         if (kbad < kb)
                             atomicMin(&f_misc[0], kbad);
                     }
                 }
-                // ---- phase C1: per (row, segment): columns strictly increasing inside the segment ----
+                __syncthreads();
+                // ---- phase C: per (row, segment): columns strictly increasing inside the segment; its last stored
+                //      column (stored = not "too far behind", cpp:210-221) ----
                 for (int item = tid; item < R * nparts; item += T)
                 {
                     const int row = item % R, part = item / R;
                     const int a = ka + part * seg, b = (a + seg < kb) ? a + seg : kb;
-                    int first = NOT_SET, firstk = kb, last = NOT_SET, kbad = kb;
+                    int first = NOT_SET, firstk = kb, last = NOT_SET, kbad = kb, last_stored = NOT_SET;
                     for (int k = a; k < b; k++)
                     {
                         const int g = G[k * GS + row];
@@ -467,11 +442,14 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                             else if (g <= last)
                                 kbad = k < kbad ? k : kbad;
                             last = g;
+                            if (g >= f_P[k])
+                                last_stored = g;
                         }
                     }
                     seg_first[item] = first;
                     seg_firstk[item] = firstk;
                     seg_last[item] = last;
+                    seg_stored[item] = last_stored;
                     if (kbad < kb)
                         atomicMin(&f_misc[0], kbad);
                 }
@@ -495,31 +473,42 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                     }
                     if (first <= prev)
                         atomicMin(&f_misc[0], seg_firstk[item]);
+                    const int ls = seg_stored[item];
+                    if (ls != NOT_SET)
+                        atomicMax(&rm_new[row], ls); // new front of the row (valid when the whole run is regular)
                 }
                 __syncthreads();
                 kgood = f_misc[0];
                 n_attempts++;
                 n_fast += kgood - ka;
+                slow_run = (kgood - ka) < 8 ? (slow_run * 2 < 64 ? slow_run * 2 : 64) : CC_K1_SLOW_RUN;
                 if (kgood > ka)
                 {
-                    // ---- phase C2a: new front of every row = its last stored column in [ka, kgood) ----
-                    for (int item = tid; item < R * nparts; item += T)
+                    if (kgood < kb)
                     {
-                        const int row = item % R, part = item / R;
-                        const int a = ka + part * seg;
-                        int b = (a + seg < kb) ? a + seg : kb;
-                        b = b < kgood ? b : kgood;
-                        int last = NOT_SET;
-                        for (int k = a; k < b; k++)
+                        // the run ends early: recompute the new fronts for [ka, kgood) only
+                        __syncthreads();
+                        for (int row = tid; row < R; row += T)
+                            rm_new[row] = rmx[row];
+                        __syncthreads();
+                        for (int item = tid; item < R * nparts; item += T)
                         {
-                            const int g = G[k * GS + row];
-                            if (g != NOT_SET && g >= f_P[k]) // not "too far behind" (cpp:210-221)
-                                last = g;
+                            const int row = item % R, part = item / R;
+                            const int a = ka + part * seg;
+                            int b = (a + seg < kb) ? a + seg : kb;
+                            b = b < kgood ? b : kgood;
+                            int last = NOT_SET;
+                            for (int k = a; k < b; k++)
+                            {
+                                const int g = G[k * GS + row];
+                                if (g != NOT_SET && g >= f_P[k])
+                                    last = g;
+                            }
+                            if (last != NOT_SET)
+                                atomicMax(&rm_new[row], last);
                         }
-                        if (last != NOT_SET)
-                            atomicMax(&rm_new[row], last);
+                        __syncthreads();
                     }
-                    __syncthreads();
                     // ---- phase C2b: the window cells between the old and the new front start out empty ----
                     for (int item = tid; item < R * nparts; item += T)
                     {
@@ -532,39 +521,36 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                             wdist[((c + base_slot) & (W - 1)) * R + row] = nanv;
                     }
                     __syncthreads();
-                    // ---- phase D: every stored point: window, ring write-through, resolved column ----
+                    // ---- phase D: every stored point: occupancy window + distance write-through to the ring. The
+                    //      resolved columns themselves are recomputed by K1b from the per-firing record. ----
+                    for (int k = ka + warp; k < kgood; k += nwarps)
                     {
-                        const int total = (kgood - ka) * R;
-                        int k, row;
-                        const bool tiled = (T % R) == 0;
-                        const int kstep = tiled ? T / R : 0;
-                        if (tiled)
+                        const int Pk = f_P[k];
+                        const int* gp = G + k * GS;
+                        const float* dp = st_dist + cbuf + k * R;
+                        for (int row = lane; row < R; row += CC_WARP)
                         {
-                            k = ka + tid / R;
-                            row = tid % R;
-                        }
-                        for (int i = tid; i < total; i += T)
-                        {
-                            if (!tiled)
+                            const int g = gp[row];
+                            if (g != NOT_SET && g >= Pk)
                             {
-                                k = ka + i / R;
-                                row = i % R;
-                            }
-                            const int g = G[k * GS + row];
-                            if (g != NOT_SET && g >= f_P[k])
-                            {
-                                const float d = st_dist[cbuf + k * R + row];
+                                const float d = dp[row];
                                 if (g > rm_new[row] - W)
                                     wdist[((g + base_slot) & (W - 1)) * R + row] = d;
                                 int local = base_local + g;
                                 local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-                                p.pos[static_cast<size_t>(local) * R + row].w = d;
-                                const int diff = st_cwr[cbuf + k * R + row] - s.pc;
-                                const int idx = (k0 + k) * R + row;
-                                p.o_g[idx] = g;
-                                p.o_rot[idx] = s.prev_rot + (diff < -half ? 1 : (diff > half ? -1 : 0));
+                                ring_w[static_cast<size_t>(static_cast<unsigned int>(local * R + row)) * 4] = d;
                             }
-                            k += kstep;
+                        }
+                        if (lane == 0)
+                        {
+                            CcFiringRecord rec;
+                            rec.mode = 1;
+                            rec.goff = s.Prel - s.pc;
+                            rec.pc = s.pc;
+                            rec.rot = s.prev_rot;
+                            rec.P = Pk;
+                            rec.pad_[0] = rec.pad_[1] = rec.pad_[2] = 0;
+                            p.firing_rec[k0 + k] = rec;
                         }
                     }
                     // columns completed by each firing (cpp:289-291)
@@ -594,9 +580,11 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
                 break;
 
             // ---- per-firing path: exact for everything; a few firings, then the fast path is tried again ----
-            const int kslow_end = (ka + CC_K1_SLOW_RUN < kc) ? ka + CC_K1_SLOW_RUN : kc;
+            const int kslow_end = (ka + slow_run < kc) ? ka + slow_run : kc;
             for (int k = ka; k < kslow_end; k++)
             {
+                if (tid == 0)
+                    p.firing_rec[k0 + k].mode = 0; // resolved columns of this firing are in o_g / o_rot
                 const int sbase = cbuf + k * R;
                 const bool p_positive = p_positive_at_start || s.Prel > 0;
                 const int goff = s.Prel - s.pc;
@@ -814,11 +802,39 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     const int total = n_firings * cfg.R;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
-        const int grel = p.o_g[idx];
-        if (grel == -0x7fffffff - 1)
-            continue;
+        const int k = idx / cfg.R, row = idx - k * cfg.R;
+        const CcFiringRecord rec = p.firing_rec[k];
+        int grel, rot;
+        if (rec.mode)
+        {
+            // regular firing: recompute the unwrap of the scan (same integers) instead of reading per-point outputs
+            const int cw = p.s_cwr[idx];
+            if (cw == CC_INVALID_CWR)
+                continue;
+            const int diff = cw - rec.pc;
+            grel = rec.goff + cw;
+            rot = rec.rot;
+            if (diff < -cfg.half)
+            {
+                grel += cfg.N;
+                rot++;
+            }
+            else if (diff > cfg.half)
+            {
+                grel -= cfg.N;
+                rot--;
+            }
+            if (grel < rec.P)
+                continue; // too far behind (cpp:210-221)
+        }
+        else
+        {
+            grel = p.o_g[idx];
+            if (grel == -0x7fffffff - 1)
+                continue;
+            rot = p.o_rot[idx];
+        }
         const long long g = p.st->scan_base + grel;
-        const int row = idx % cfg.R;
         const size_t cell = static_cast<size_t>(cc_local_col(g, cfg.ringcols)) * cfg.R + row;
         const float4 sp = p.s_pos[idx];
         if (ccm::f2u(p.pos[cell].w) != ccm::f2u(sp.w))
@@ -827,7 +843,7 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         p.pos[cell] = sp;
         p.azimuth[cell] = p.s_az[idx];
         p.incl[cell] = p.s_incl[idx];
-        p.cont_az[cell] = (2 * M_PI) * static_cast<double>(p.o_rot[idx]) + static_cast<double>(p.s_incaz[idx]);
+        p.cont_az[cell] = (2 * M_PI) * static_cast<double>(rot) + static_cast<double>(p.s_incaz[idx]);
         uchar4 l = p.lab[cell];
         l.w = raw->intensity;
         p.lab[cell] = l;
@@ -1184,7 +1200,7 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 //      seen before this column, or its tree is already finished -- flags the column for the column-sequential
 //      exact path. No persistent state is modified here.
 // =====================================================================================================
-__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int tile_cols, int use_smem)
+__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem)
 {
     CC_SMEM(smem);
     float4* win = reinterpret_cast<float4*>(smem); // association view of the tile's columns + the window before them
@@ -1239,7 +1255,7 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int t
             int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
             steps_back = steps_back < msr ? steps_back : msr;
             unsigned int first = CC_NONE;
-            int visited = 0;
+            int visited = 0, nlinks = 0;
             bool flagged = false;
             for (int back = 0; back <= steps_back; back++)
             {
@@ -1279,14 +1295,21 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int t
                                     first = o;
                                 else if (o != first)
                                 {
-                                    const int e = atomicAdd(&p.st->n_edges, 1);
-                                    if (e < p.cap_edges)
-                                    {
-                                        p.edge_a[e] = q;
-                                        p.edge_b[e] = o;
-                                    }
+                                    // tree<->tree link candidate: a few per point fit the point's own slots (no
+                                    // contended counter); only walks with stop_after_association off overflow
+                                    if (nlinks < CC_LINK_SLOTS)
+                                        s_links[static_cast<size_t>(idx) * CC_LINK_SLOTS + nlinks++] = o;
                                     else
-                                        p.st->error = CC_DEV_LIST_OVERFLOW;
+                                    {
+                                        const int e = atomicAdd(&p.st->n_edges, 1);
+                                        if (e < p.cap_edges)
+                                        {
+                                            p.edge_a[e] = q;
+                                            p.edge_b[e] = o;
+                                        }
+                                        else
+                                            p.st->error = CC_DEV_LIST_OVERFLOW;
+                                    }
                                 }
                             }
                         }
@@ -1299,6 +1322,8 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int t
                 if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
                     break;
             }
+            for (int j = nlinks; j < CC_LINK_SLOTS; j++)
+                s_links[static_cast<size_t>(idx) * CC_LINK_SLOTS + j] = CC_NONE;
             s_parent[idx] = first == CC_NONE ? q : first;
             p.visited[q] = static_cast<unsigned short>(visited);
             if (cfg.debug_flag_period > 0 && ((colbase + ci) % cfg.debug_flag_period) == 0)
@@ -1480,13 +1505,33 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
     }
 }
 
-__global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+__global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
+                               int ci0, int ci1, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
     const int R = cfg.R;
     if (ci1 < 0)
         ci1 = p.st->ncols - 1;
+    {
+        const long long colbase = p.st->colbase;
+        const int total = (ci1 - ci0 + 1) * R * CC_LINK_SLOTS;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        {
+            const int cell = i / CC_LINK_SLOTS;
+            const size_t idx = static_cast<size_t>(ci0) * R + cell;
+            if (s_parent[idx] == CC_NONE)
+                continue; // is_ignored: its slots were not written
+            const unsigned int o = s_links[idx * CC_LINK_SLOTS + (i % CC_LINK_SLOTS)];
+            if (o == CC_NONE)
+                continue;
+            const int ci = ci0 + cell / R, row = cell % R;
+            const unsigned int q = static_cast<unsigned int>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
+            const unsigned int ra = cc_vload(p.tparent + q), rb = cc_vload(p.tparent + o);
+            if (ra != rb)
+                cc_uf_union(p.cparent, ra, rb);
+        }
+    }
     int n = p.st->n_edges;
     n = n < p.cap_edges ? n : p.cap_edges;
     const int base_local = cc_local_col(p.st->colbase, cfg.ringcols);

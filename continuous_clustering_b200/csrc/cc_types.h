@@ -37,6 +37,7 @@ enum : uint8_t
 #define CC_COL_INF 0x3fffffffffffffffLL
 #define CC_K1_POINTS_PER_CHUNK 8192 /* the insertion scan stages min(128, 8192 / rows) firings per cp.async group */
 #define CC_K1_MAX_CHUNK 128
+#define CC_LINK_SLOTS 4 /* tree<->tree link candidates kept per probed point before the overflow list is used */
 #define CC_K1_SLOW_RUN 4 /* firings that go through the per-firing path after an irregular one */
 #define CC_K1_WINDOW 64 /* columns of per-row occupancy history kept in shared memory by the insertion scan */
 
@@ -101,6 +102,13 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     int pad_;
 };
 
+struct CcFiringRecord // insertion scan -> K1b: how the points of one firing were resolved
+{
+    int mode; // 1: regular firing, column = unwrap(cwr) with the integers below; 0: per point in o_g / o_rot
+    int goff, pc, rot, P;
+    int pad_[3];
+};
+
 struct CcCluster // device -> host record of one finished cluster with more than 5 points (cpp:936-940)
 {
     unsigned long long id;
@@ -157,6 +165,7 @@ struct CcDevPtrs
     int* s_cwr;
     int* o_g;             // resolved global column relative to CcDevState::scan_base, INT_MIN = not stored
     int* o_rot;           // rotation index used for the continuous azimuth
+    CcFiringRecord* firing_rec; // [max_firings]
     // ---- per new column (maxcols) ----
     int* col_trigger;     // firing (index in this push) whose insertion completed the column (hpp:169-173)
     float* col_gap;       // [maxcols * R] value of sc_inclination_angles_between_lasers_ when the column is segmented
