@@ -1233,9 +1233,18 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsig
             }
             __syncthreads();
         }
-        for (int cell = tid; cell < nc * R; cell += T)
+        // Warp-cooperative walk: a warp takes 32 consecutive cells of the tile, ballots the non-ignored ones and walks
+        // the field of view of one point at a time with ALL lanes: every vertical run of the walk (cpp:716-750) is
+        // evaluated 32 cells at once (inclination break, 3-D distance predicate) and the sequential early-exit rules
+        // are applied to the ballot masks. The walk order, the visit count and which hit is first are those of the
+        // reference; the cost of an isolated point drops from ~860 dependent visits to ~41 warp steps.
+        const int lane = tid % CC_WARP, warp = tid / CC_WARP, nwarps = (T + CC_WARP - 1) / CC_WARP;
+        const unsigned int lt_mask = (1u << lane) - 1u;
+        for (int g0 = warp * CC_WARP; g0 < nc * R; g0 += nwarps * CC_WARP)
         {
-            const int cl = cell / R, row = cell - cl * R;
+            const int cell = g0 + lane;
+            const bool in_tile = cell < nc * R;
+            const int cl = in_tile ? cell / R : 0, row = in_tile ? cell - cl * R : 0;
             const int ci = ci0 + cl;
             const int wq = msr + cl; // window column of this cell
             int local = wl0 + wq;
@@ -1243,95 +1252,156 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsig
                 local -= cfg.ringcols;
             const unsigned int q = static_cast<unsigned int>(local) * R + row;
             const int idx = ci * R + row;
-            s_parent[idx] = CC_NONE;
-            const float4 a = use_smem ? win[wq * R + row] : p.assoc[q];
-            if (cc_isnan(a.x))
+            float4 a = make_float4(cc_nanf(), 0.f, 0.f, 0.f);
+            if (in_tile)
             {
-                p.visited[q] = 0;
-                continue; // is_ignored
-            }
-            const float mad = p.mad[q];
-            const double prev_runmax = ci > 0 ? p.col_runmax[ci - 1] : p.st->runmax_carry;
-            int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
-            steps_back = steps_back < msr ? steps_back : msr;
-            unsigned int first = CC_NONE;
-            int visited = 0, nlinks = 0;
-            bool flagged = false;
-            for (int back = 0; back <= steps_back; back++)
-            {
-                const int wo = wq - back;
-                int olocal = wl0 + wo;
-                if (olocal >= cfg.ringcols)
-                    olocal -= cfg.ringcols;
-                for (int dir = -1; dir <= 1; dir += 2)
+                a = use_smem ? win[wq * R + row] : p.assoc[q];
+                if (cc_isnan(a.x))
                 {
-                    if (dir == 1 && back == 0)
-                        continue;
-                    int steps_v = (dir == 1 || back == 0) ? 1 : 0;
-                    int orow = (dir == 1 || back == 0) ? row + dir : row;
-                    while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
+                    s_parent[idx] = CC_NONE;
+                    p.visited[q] = 0;
+                }
+            }
+            const float my_mad = (in_tile && !cc_isnan(a.x)) ? p.mad[q] : 0.f;
+            unsigned int todo = __ballot_sync(CC_FULL_MASK, in_tile && !cc_isnan(a.x));
+            while (todo)
+            {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                // the point being walked (broadcast from its lane)
+                const float ax = __shfl_sync(CC_FULL_MASK, a.x, src), ay = __shfl_sync(CC_FULL_MASK, a.y, src),
+                            az = __shfl_sync(CC_FULL_MASK, a.z, src), aw = __shfl_sync(CC_FULL_MASK, a.w, src);
+                const float mad = __shfl_sync(CC_FULL_MASK, my_mad, src);
+                const int prow = __shfl_sync(CC_FULL_MASK, row, src), pwq = __shfl_sync(CC_FULL_MASK, wq, src);
+                const int pci = __shfl_sync(CC_FULL_MASK, ci, src), pidx = __shfl_sync(CC_FULL_MASK, idx, src);
+                const unsigned int pq = __shfl_sync(CC_FULL_MASK, q, src);
+                const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
+                int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+                steps_back = steps_back < msr ? steps_back : msr;
+                unsigned int first = CC_NONE;
+                int visited = 0, nlinks = 0;
+                bool flagged = false;
+                for (int back = 0; back <= steps_back; back++)
+                {
+                    const int wo = pwq - back;
+                    int olocal = wl0 + wo;
+                    if (olocal >= cfg.ringcols)
+                        olocal -= cfg.ringcols;
+                    for (int dir = -1; dir <= 1; dir += 2)
                     {
-                        const unsigned int o = static_cast<unsigned int>(olocal) * R + orow;
-                        const float4 b = use_smem ? win[wo * R + orow] : p.assoc[o];
-                        visited++;
-                        if (fabsf(b.w - a.w) > mad)
-                            break;
-                        if (!cc_isnan(b.x))
+                        if (dir == 1 && back == 0)
+                            continue;
+                        const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+                        const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+                        int n = cfg.max_steps_col - start_step + 1; // cells of this vertical run
+                        const int room = dir < 0 ? start_row + 1 : R - start_row;
+                        n = n < room ? n : room;
+                        bool run_done = false;
+                        for (int jb = 0; jb < n && !run_done; jb += CC_WARP)
                         {
-                            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-                            if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
+                            const int cnt = (n - jb) < CC_WARP ? (n - jb) : CC_WARP;
+                            const int j = jb + lane;
+                            const bool in = lane < cnt;
+                            const int orow = start_row + dir * j;
+                            const unsigned int o = static_cast<unsigned int>(olocal) * R + (in ? orow : 0);
+                            float4 b = make_float4(cc_nanf(), 0.f, 0.f, cc_nanf());
+                            if (in)
+                                b = use_smem ? win[wo * R + orow] : p.assoc[o];
+                            const bool brk = in && fabsf(b.w - aw) > mad; // cpp:728-729 (NaN never breaks)
+                            bool hit = false;
+                            if (in && !brk && !cc_isnan(b.x))
                             {
-                                // could the reference have refused this hit?
-                                const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
-                                if (finish_o <= prev_runmax)
-                                    flagged = true;
-                                if (back > ci)
+                                const float dx = ax - b.x, dy = ay - b.y, dz = az - b.z;
+                                hit = dx * dx + dy * dy + dz * dz < cfg.max_distance_sq; // cpp:638-641
+                            }
+                            const unsigned int brk_mask = __ballot_sync(CC_FULL_MASK, brk);
+                            const unsigned int hit_mask = __ballot_sync(CC_FULL_MASK, hit);
+                            const int limit = brk_mask ? __ffs(brk_mask) - 1 : cnt; // cells before the break are processed
+                            const unsigned int below_limit = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
+                            // early stop once associated (cpp:747-749): after the first cell with steps >= min steps
+                            int jstop = 0x7fffffff;
+                            if (cfg.stop_enabled)
+                            {
+                                const int need = cfg.stop_min_steps - start_step - jb; // lane index where steps >= min
+                                if (first != CC_NONE)
+                                    jstop = need > 0 ? need : 0;
+                                else if (hit_mask & below_limit)
                                 {
-                                    const unsigned int ro = p.tparent[o];
-                                    if (ro == CC_NONE || p.tstate[ro] != 0)
+                                    const int jh = __ffs(hit_mask & below_limit) - 1;
+                                    jstop = jh > need ? jh : need;
+                                }
+                            }
+                            int processed = limit; // number of cells whose association step runs
+                            bool stopped = false;
+                            if (jstop < limit)
+                            {
+                                processed = jstop + 1;
+                                stopped = true;
+                            }
+                            visited += stopped ? processed : (limit < cnt ? limit + 1 : cnt);
+                            const unsigned int proc_mask = processed >= 32 ? 0xffffffffu : ((1u << processed) - 1u);
+                            unsigned int hp = hit_mask & proc_mask;
+                            if (hp)
+                            {
+                                if ((hp >> lane) & 1u) // every hit lane checks its own target
+                                {
+                                    // could the reference have refused this hit?
+                                    const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                                    if (finish_o <= prev_runmax)
                                         flagged = true;
+                                    if (back > pci)
+                                    {
+                                        const unsigned int ro = p.tparent[o];
+                                        if (ro == CC_NONE || p.tstate[ro] != 0)
+                                            flagged = true;
+                                    }
                                 }
                                 if (first == CC_NONE)
-                                    first = o;
-                                else if (o != first)
                                 {
-                                    // tree<->tree link candidate: a few per point fit the point's own slots (no
-                                    // contended counter); only walks with stop_after_association off overflow
-                                    if (nlinks < CC_LINK_SLOTS)
-                                        s_links[static_cast<size_t>(idx) * CC_LINK_SLOTS + nlinks++] = o;
+                                    const int jf = __ffs(hp) - 1;
+                                    first = __shfl_sync(CC_FULL_MASK, o, jf);
+                                    hp &= hp - 1;
+                                }
+                                // the remaining hits are tree<->tree link candidates (cpp:740-741)
+                                if ((hp >> lane) & 1u)
+                                {
+                                    const int slot = nlinks + __popc(hp & lt_mask);
+                                    if (slot < CC_LINK_SLOTS)
+                                        s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + slot] = o;
                                     else
                                     {
                                         const int e = atomicAdd(&p.st->n_edges, 1);
                                         if (e < p.cap_edges)
                                         {
-                                            p.edge_a[e] = q;
+                                            p.edge_a[e] = pq;
                                             p.edge_b[e] = o;
                                         }
                                         else
                                             p.st->error = CC_DEV_LIST_OVERFLOW;
                                     }
                                 }
+                                nlinks += __popc(hp);
                             }
+                            run_done = stopped || limit < cnt;
                         }
-                        if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps)
-                            break;
-                        orow += dir;
-                        steps_v++;
+                    }
+                    if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+                        break;
+                }
+                const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
+                                      (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
+                for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
+                    s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
+                if (lane == 0)
+                {
+                    s_parent[pidx] = first == CC_NONE ? pq : first;
+                    p.visited[pq] = static_cast<unsigned short>(visited);
+                    if (any_flag)
+                    {
+                        p.col_flag[pci] = 1;
+                        atomicAdd(&p.st->n_flagged, 1);
                     }
                 }
-                if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
-                    break;
-            }
-            for (int j = nlinks; j < CC_LINK_SLOTS; j++)
-                s_links[static_cast<size_t>(idx) * CC_LINK_SLOTS + j] = CC_NONE;
-            s_parent[idx] = first == CC_NONE ? q : first;
-            p.visited[q] = static_cast<unsigned short>(visited);
-            if (cfg.debug_flag_period > 0 && ((colbase + ci) % cfg.debug_flag_period) == 0)
-                flagged = true;
-            if (flagged)
-            {
-                p.col_flag[ci] = 1;
-                atomicAdd(&p.st->n_flagged, 1);
             }
         }
         if (use_smem)

@@ -101,6 +101,14 @@ static inline int __reduce_or_sync(unsigned, int v)
 {
     return v;
 }
+static inline int __ffs(unsigned v)
+{
+    return __builtin_ffs(static_cast<int>(v));
+}
+static inline int __popc(unsigned v)
+{
+    return __builtin_popcount(v);
+}
 static inline void __pipeline_memcpy_async(void* dst, const void* src, size_t n)
 {
     memcpy(dst, src, n);
