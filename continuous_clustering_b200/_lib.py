@@ -115,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "cc_push_firings_device", "cc_get_batch_info", "cc_get_column_events", "cc_get_clusters", "cc_get_cluster_points",
     "cc_read_columns", "cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns", "cc_stream",
     "cc_total_launches", "cc_selftest_math", "cc_set_kernel_timing", "cc_get_kernel_timings",
-    "cc_debug_flag_columns",
+    "cc_debug_flag_columns", "cc_get_result_views",
 ]
 
 
@@ -140,6 +140,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_get_batch_info.argtypes = [vp, C.POINTER(CcBatchInfo)]
     for name in ("cc_get_column_events", "cc_get_clusters", "cc_get_cluster_points"):
         getattr(lib, name).argtypes = [vp, vp, i32, C.POINTER(i32)]
+    lib.cc_get_result_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.cc_read_columns.argtypes = [vp, i64, i64, C.POINTER(CcColumnFields)]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]

@@ -102,6 +102,9 @@ class ClusteringError(RuntimeError):
 
 @dataclasses.dataclass
 class BatchResult:
+    """Results of one push. The arrays are zero-copy views of the handle's buffers: valid until the next push on the
+    same object (copy them to keep them)."""
+
     info: _lib.CcBatchInfo
     events: np.ndarray  # EVENT_DTYPE, callback order
     clusters: np.ndarray  # CLUSTER_DTYPE, finish order (> 5 points; the cluster callback needs > 20)
@@ -234,19 +237,20 @@ class ContinuousClustering:
         return out
 
     def _collect(self) -> BatchResult:
+        """Results of the last push as numpy views of the handle's own arrays (valid until the next push)."""
         info = _lib.CcBatchInfo()
         self._check(self._L.cc_get_batch_info(self._h, C.byref(info)))
-        ev = np.zeros(info.n_events, dtype=_lib.EVENT_DTYPE)
-        cl = np.zeros(info.n_clusters, dtype=_lib.CLUSTER_DTYPE)
-        cp = np.zeros(info.n_cluster_points, dtype=_lib.CLUSTER_POINT_DTYPE)
-        n = C.c_int(0)
-        if info.n_events:
-            self._check(self._L.cc_get_column_events(self._h, ev.ctypes.data, info.n_events, C.byref(n)))
-        if info.n_clusters:
-            self._check(self._L.cc_get_clusters(self._h, cl.ctypes.data, info.n_clusters, C.byref(n)))
-        if info.n_cluster_points:
-            self._check(self._L.cc_get_cluster_points(self._h, cp.ctypes.data, info.n_cluster_points, C.byref(n)))
-        self.last = BatchResult(info, ev, cl, cp)
+        pe, pc, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._L.cc_get_result_views(self._h, C.byref(pe), C.byref(pc), C.byref(pp))
+
+        def view(ptr, n, dtype):
+            if n == 0 or not ptr.value:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype=dtype, count=n)
+
+        self.last = BatchResult(info, view(pe, info.n_events, _lib.EVENT_DTYPE), view(pc, info.n_clusters, _lib.CLUSTER_DTYPE),
+                                view(pp, info.n_cluster_points, _lib.CLUSTER_POINT_DTYPE))
         return self.last
 
     def _dispatch(self, res: BatchResult):

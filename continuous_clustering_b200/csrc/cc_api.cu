@@ -11,7 +11,7 @@
 
 #include "cc_kernels.cuh"
 
-static const int CC_PREFETCH_CLUSTERS = 1024, CC_PREFETCH_POINTS = 32768;
+static const int CC_PREFETCH_CLUSTERS = 512, CC_PREFETCH_POINTS = 8192;
 
 namespace
 {
@@ -730,18 +730,21 @@ static cc_status_t run_push(cc_handle* h, int n)
         const bool spec = cfg.nth == 1;
         CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d, spec ? 1 : 0);
         {
-            // one CTA per tile of 8 new columns; the tile's sliding window of prior columns is staged in shared memory
-            const int tile_cols = 8;
-            const size_t win_bytes = static_cast<size_t>(tile_cols + cfg.max_steps_row) * R * sizeof(float4);
-            const int use_smem = (cfg.max_steps_row >= 0 && win_bytes <= 160 * 1024) ? 1 : 0;
+            // one CTA per tile of 2 new columns; the tile's sliding window of prior columns is staged in shared
+            // memory; warps take the tile's non-ignored points from a shared list
+            const int tile_cols = 2;
+            const size_t list_bytes = ((static_cast<size_t>(tile_cols) * R + 4) * sizeof(int) + 15) / 16 * 16;
+            const size_t win_only = static_cast<size_t>(tile_cols + cfg.max_steps_row) * R * sizeof(float4);
+            const int use_smem = (cfg.max_steps_row >= 0 && win_only <= 160 * 1024) ? 1 : 0;
+            const size_t win_bytes = list_bytes + (use_smem ? win_only : 0);
 #ifndef CC_EMU
-            if (use_smem && win_bytes > 48 * 1024 && win_bytes != h->probe_smem_set)
+            if (win_bytes > 48 * 1024 && win_bytes != h->probe_smem_set)
             {
                 CC_CHECK(h, cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(win_bytes)));
                 h->probe_smem_set = win_bytes;
             }
 #endif
-            CC_RUN(h, k_probe, h->sm_count * 4, 256, use_smem ? win_bytes : 0, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem);
+            CC_RUN(h, k_probe, h->sm_count * 8, 256, win_bytes, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem);
         }
         if (spec)
         {
@@ -916,10 +919,30 @@ cc_status_t cc_push_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_
         return CC_ERR_INVALID_ARGUMENT;
     CC_CHECK(h, cudaSetDevice(h->device));
     const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
-    std::memcpy(h->h_raw, points, pb);
-    std::memcpy(h->h_poses, poses, qb);
-    CC_CHECK(h, cudaMemcpyAsync(h->d_raw, h->h_raw, pb, cudaMemcpyHostToDevice, h->stream));
-    CC_CHECK(h, cudaMemcpyAsync(h->d_poses, h->h_poses, qb, cudaMemcpyHostToDevice, h->stream));
+    // page-locked caller buffers are copied straight to the device; anything else goes through the handle's own
+    // pinned staging buffer first (an asynchronous copy from pageable memory would serialise on the host anyway)
+    const void* src_pts = points;
+    const void* src_poses = poses;
+#ifndef CC_EMU
+    cudaPointerAttributes attr;
+    const bool pts_pinned = cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    const bool poses_pinned = cudaPointerGetAttributes(&attr, poses) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+#else
+    const bool pts_pinned = false, poses_pinned = false;
+#endif
+    if (!pts_pinned)
+    {
+        std::memcpy(h->h_raw, points, pb);
+        src_pts = h->h_raw;
+    }
+    if (!poses_pinned)
+    {
+        std::memcpy(h->h_poses, poses, qb);
+        src_poses = h->h_poses;
+    }
+    CC_CHECK(h, cudaMemcpyAsync(h->d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->stream));
+    CC_CHECK(h, cudaMemcpyAsync(h->d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->stream));
     h->d.raw = h->d_raw;
     h->d.poses = h->d_poses;
     return run_push(h, n);
@@ -964,6 +987,20 @@ static cc_status_t copy_out(const std::vector<T>& v, T* out, int cap, int* n_out
 }
 
 extern "C" {
+
+cc_status_t cc_get_result_views(const cc_handle_t* h, const cc_column_event_t** events, const cc_cluster_t** clusters,
+                                const cc_cluster_point_t** points)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (events)
+        *events = h->events.data();
+    if (clusters)
+        *clusters = h->clusters.data();
+    if (points)
+        *points = h->cluster_points.data();
+    return CC_OK;
+}
 
 cc_status_t cc_get_column_events(const cc_handle_t* h, cc_column_event_t* out, int cap, int* n_out)
 {

@@ -1203,8 +1203,11 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem)
 {
     CC_SMEM(smem);
-    float4* win = reinterpret_cast<float4*>(smem); // association view of the tile's columns + the window before them
     const int R = cfg.R;
+    int* plist_n = reinterpret_cast<int*>(smem);          // [0] points in the list, [1] next point to take
+    int* plist = plist_n + 4;                             // [tile_cols * R] non-ignored cells of the tile
+    // association view of the tile's columns + the window before them
+    float4* win = reinterpret_cast<float4*>(smem + ((static_cast<size_t>(tile_cols) * R + 4) * sizeof(int) + 15) / 16 * 16);
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
@@ -1238,43 +1241,54 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsig
         // evaluated 32 cells at once (inclination break, 3-D distance predicate) and the sequential early-exit rules
         // are applied to the ballot masks. The walk order, the visit count and which hit is first are those of the
         // reference; the cost of an isolated point drops from ~860 dependent visits to ~41 warp steps.
-        const int lane = tid % CC_WARP, warp = tid / CC_WARP, nwarps = (T + CC_WARP - 1) / CC_WARP;
+        const int lane = tid % CC_WARP;
         const unsigned int lt_mask = (1u << lane) - 1u;
-        for (int g0 = warp * CC_WARP; g0 < nc * R; g0 += nwarps * CC_WARP)
+        // compact the tile's non-ignored cells into a shared list; warps then take points from it one at a time, so
+        // a dense object does not serialise on the warp that happens to own its rows
+        if (tid == 0)
         {
-            const int cell = g0 + lane;
-            const bool in_tile = cell < nc * R;
-            const int cl = in_tile ? cell / R : 0, row = in_tile ? cell - cl * R : 0;
-            const int ci = ci0 + cl;
-            const int wq = msr + cl; // window column of this cell
+            plist_n[0] = 0;
+            plist_n[1] = 0;
+        }
+        __syncthreads();
+        for (int cell = tid; cell < nc * R; cell += T)
+        {
+            const int cl = cell / R, row = cell - cl * R;
+            const int wq = msr + cl;
             int local = wl0 + wq;
             if (local >= cfg.ringcols)
                 local -= cfg.ringcols;
             const unsigned int q = static_cast<unsigned int>(local) * R + row;
-            const int idx = ci * R + row;
-            float4 a = make_float4(cc_nanf(), 0.f, 0.f, 0.f);
-            if (in_tile)
+            const float ax = use_smem ? win[wq * R + row].x : p.assoc[q].x;
+            if (cc_isnan(ax))
             {
-                a = use_smem ? win[wq * R + row] : p.assoc[q];
-                if (cc_isnan(a.x))
-                {
-                    s_parent[idx] = CC_NONE;
-                    p.visited[q] = 0;
-                }
+                s_parent[(ci0 + cl) * R + row] = CC_NONE;
+                p.visited[q] = 0;
             }
-            const float my_mad = (in_tile && !cc_isnan(a.x)) ? p.mad[q] : 0.f;
-            unsigned int todo = __ballot_sync(CC_FULL_MASK, in_tile && !cc_isnan(a.x));
-            while (todo)
+            else
+                plist[atomicAdd(&plist_n[0], 1)] = cell;
+        }
+        __syncthreads();
+        const int npoints = plist_n[0];
+        while (true)
+        {
+            int pi = 0;
+            if (lane == 0)
+                pi = atomicAdd(&plist_n[1], 1);
+            pi = __shfl_sync(CC_FULL_MASK, pi, 0);
+            if (pi >= npoints)
+                break;
             {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                // the point being walked (broadcast from its lane)
-                const float ax = __shfl_sync(CC_FULL_MASK, a.x, src), ay = __shfl_sync(CC_FULL_MASK, a.y, src),
-                            az = __shfl_sync(CC_FULL_MASK, a.z, src), aw = __shfl_sync(CC_FULL_MASK, a.w, src);
-                const float mad = __shfl_sync(CC_FULL_MASK, my_mad, src);
-                const int prow = __shfl_sync(CC_FULL_MASK, row, src), pwq = __shfl_sync(CC_FULL_MASK, wq, src);
-                const int pci = __shfl_sync(CC_FULL_MASK, ci, src), pidx = __shfl_sync(CC_FULL_MASK, idx, src);
-                const unsigned int pq = __shfl_sync(CC_FULL_MASK, q, src);
+                const int cell = plist[pi];
+                const int pcl = cell / R, prow = cell - pcl * R;
+                const int pci = ci0 + pcl, pwq = msr + pcl, pidx = pci * R + prow;
+                int plocal = wl0 + pwq;
+                if (plocal >= cfg.ringcols)
+                    plocal -= cfg.ringcols;
+                const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
+                const float4 pa = use_smem ? win[pwq * R + prow] : p.assoc[pq];
+                const float ax = pa.x, ay = pa.y, az = pa.z, aw = pa.w;
+                const float mad = p.mad[pq];
                 const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
                 int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
                 steps_back = steps_back < msr ? steps_back : msr;
@@ -1404,8 +1418,7 @@ __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsig
                 }
             }
         }
-        if (use_smem)
-            __syncthreads();
+        __syncthreads();
     }
 }
 

@@ -213,7 +213,8 @@ CC_API int cc_has_robot_from_sensor(const cc_handle_t* h);
  * associatePointsInColumn (cpp:773-835), findFinishedTreesAndAssignSameId (cpp:837-974), the id /
  * bookkeeping half of collectPointsForCusterAndPublish (cpp:976-1092) and clearColumns (cpp:1094-1145)
  * for every column the firings complete, on the device. `points` = n_firings*rows_per_firing host records,
- * `poses` = n_firings*12 host doubles. Returns after the results are on the host.
+ * `poses` = n_firings*12 host doubles (page-locked buffers are copied to the device without staging). Returns after
+ * the results are on the host.
  * rows_per_firing != num_rows -> CC_ERR_ROW_COUNT_CHANGED (cpp:90-91). */
 CC_API cc_status_t cc_push_firings(cc_handle_t* h, int n_firings, int rows_per_firing,
                                    const cc_raw_point_t* points, const double* poses);
@@ -228,6 +229,11 @@ CC_API cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out)
 CC_API cc_status_t cc_get_column_events(const cc_handle_t* h, cc_column_event_t* out, int cap, int* n_out);
 CC_API cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int cap, int* n_out);
 CC_API cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out, int cap, int* n_out);
+
+/* Zero-copy variant: pointers to the handle's own result arrays (n_events / n_clusters / n_cluster_points entries,
+ * see cc_get_batch_info), valid until the next push or reset on this handle. */
+CC_API cc_status_t cc_get_result_views(const cc_handle_t* h, const cc_column_event_t** events,
+                                       const cc_cluster_t** clusters, const cc_cluster_point_t** points);
 
 /* Reads cells of columns [from_gcol, to_gcol] (inclusive, like the callback ranges) from the device
  * ring -- what a caller reads from `range_image_` inside a column callback (ros_utils.cpp:56-63,

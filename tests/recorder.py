@@ -35,7 +35,7 @@ def record(cc, pts, poses, chunk):
         res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
         used_exact += int(res.info.used_exact_path)
         slow_firings += int(res.info.slow_insert_firings)
-        ev = res.events
+        ev = res.events.copy()  # results are views of the handle's buffers, valid until the next push
         if len(ev) == 0:
             continue
         g = ev[ev["ground_points_only"] == 1]
