@@ -447,6 +447,10 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.firing_rec, static_cast<size_t>(h->max_firings)));
+        CC_CHECK(h, dev_alloc(h, L, &d.lite_sum, static_cast<size_t>(h->max_firings)));
+        CC_CHECK(h, dev_alloc(h, L, &d.lite_U, static_cast<size_t>(h->max_firings)));
+        CC_CHECK(h, dev_alloc(h, L, &d.lite_P, static_cast<size_t>(h->max_firings) + 1));
+        CC_CHECK(h, dev_alloc(h, L, &d.lite_F, static_cast<size_t>(h->max_firings) + 1));
         CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
         CC_CHECK(h, dev_alloc(h, L, &h->d_poses, static_cast<size_t>(h->max_firings) * 12));
         const size_t mc = static_cast<size_t>(h->maxcols);
@@ -705,9 +709,14 @@ static cc_status_t run_push(cc_handle* h, int n)
     const int R = h->R;
     CC_RUN(h, k_clear, h->sm_count * 8, 256, 0, cfg, h->d, 0LL, 0LL, 1); // columns retired by the previous push
     const long long pts = static_cast<long long>(n) * R;
-    CC_RUN(h, k_prep, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
+    CC_RUN(h, k_prep, grid_for(h, static_cast<long long>(n) * CC_WARP, 256), 256, 0, cfg, h->d, n);
+    // lite insertion path (regular prefix of the push, grid-wide) ...
+    CC_RUN(h, k_scan_lite, 1, CC_WARP, 0, cfg, h->d, n);
+    CC_RUN(h, k_scan_check, R, 256, 256 * sizeof(int), cfg, h->d, n);
+    CC_RUN(h, k_scan_apply, R, 256, 256 * sizeof(int), cfg, h->d, n);
+    // ... then the single-CTA scan commits that prefix and resolves whatever is left
     const int scan_smem = scan_smem_bytes(R);
-    CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R));
+    CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R), 1);
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 
     if (!h->has_tf)
@@ -876,7 +885,7 @@ static cc_status_t run_push(cc_handle* h, int n)
     info.reset_required = st.reset_required;
     info.gpu_launches = static_cast<int32_t>(h->launches - h->launches_at_push_start);
     info.device_ms = ms;
-    info.slow_insert_firings = st.scan_slow_firings; // firings that needed the per-firing insertion path
+    info.slow_insert_firings = st.scan_slow_firings + st.scan_fast_firings; // everything the lite path did not take // firings that needed the per-firing insertion path
     return CC_OK;
 }
 

@@ -142,35 +142,341 @@ CC_DEV int cc_local_col(long long g, int ringcols)
 // K0  per raw point: rigid transform, azimuth -> column within rotation, distance, inclination (cpp:125-151,
 //     189, 232). Fully parallel, one thread per (firing, row).
 // =====================================================================================================
+CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/2]
+{
+    if (2 * d > N)
+        d -= N;
+    else if (2 * d <= -N)
+        d += N;
+    return d;
+}
+
 __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
-    const int total = n_firings * cfg.R;
+    // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
+    // (anchor = column-in-rotation of its first valid row; rearmost / foremost column relative to the anchor)
+    const int R = cfg.R;
     const float pi_f = static_cast<float>(M_PI);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x % CC_WARP;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) / CC_WARP;
+    const int nw = (gridDim.x * blockDim.x + CC_WARP - 1) / CC_WARP;
+    for (int k = gwarp; k < n_firings; k += nw)
     {
-        const int k = idx / cfg.R;
-        const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
-        const float fx = raw->x, fy = raw->y, fz = raw->z;
-        p.o_g[idx] = -0x7fffffff - 1;
-        if (cc_isnan(fx))
-        {
-            p.s_cwr[idx] = CC_INVALID_CWR;
-            continue;
-        }
         const double* pose = p.poses + 12 * k;
-        double po[3];
-        cc_iso_apply(pose, static_cast<double>(fx), static_cast<double>(fy), static_cast<double>(fz), po);
-        const double rx = po[0] - pose[3], ry = po[1] - pose[7], rz = po[2] - pose[11];
-        const float az = ccm::atan2f_glibc(fy, fx); // sensor-frame azimuth, cpp:142
-        const float incaz = cfg.clockwise ? -az + pi_f : az + pi_f;
-        const int cwr = static_cast<int>(ccm::div_rn(incaz, cfg.width));
-        const float dist = static_cast<float>(sqrt(rx * rx + (ry * ry + rz * rz)));
-        p.s_pos[idx] = make_float4(static_cast<float>(po[0]), static_cast<float>(po[1]), static_cast<float>(po[2]), dist);
-        p.s_dist[idx] = dist;
-        p.s_az[idx] = az;
-        p.s_incaz[idx] = incaz;
-        p.s_incl[idx] = ccm::asinf_glibc(ccm::div_rn(static_cast<float>(rz), dist));
-        p.s_cwr[idx] = cwr;
+        unsigned int kmin = 0xffffffffu;
+        int nvalid = 0, weird = 0;
+        for (int row = lane; row < R; row += CC_WARP)
+        {
+            const int idx = k * R + row;
+            const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
+            const float fx = raw->x, fy = raw->y, fz = raw->z;
+            p.o_g[idx] = -0x7fffffff - 1;
+            if (cc_isnan(fx))
+            {
+                p.s_cwr[idx] = CC_INVALID_CWR;
+                continue;
+            }
+            double po[3];
+            cc_iso_apply(pose, static_cast<double>(fx), static_cast<double>(fy), static_cast<double>(fz), po);
+            const double rx = po[0] - pose[3], ry = po[1] - pose[7], rz = po[2] - pose[11];
+            const float az = ccm::atan2f_glibc(fy, fx); // sensor-frame azimuth, cpp:142
+            const float incaz = cfg.clockwise ? -az + pi_f : az + pi_f;
+            const int cwr = static_cast<int>(ccm::div_rn(incaz, cfg.width));
+            const float dist = static_cast<float>(sqrt(rx * rx + (ry * ry + rz * rz)));
+            p.s_pos[idx] = make_float4(static_cast<float>(po[0]), static_cast<float>(po[1]), static_cast<float>(po[2]), dist);
+            p.s_dist[idx] = dist;
+            p.s_az[idx] = az;
+            p.s_incaz[idx] = incaz;
+            p.s_incl[idx] = ccm::asinf_glibc(ccm::div_rn(static_cast<float>(rz), dist));
+            p.s_cwr[idx] = cwr;
+            if (cwr != CC_INVALID_CWR)
+            {
+                nvalid++;
+                if (cwr < 0 || cwr > cfg.N || cwr >= (1 << 20))
+                    weird = 1;
+                const unsigned int key = (static_cast<unsigned int>(row) << 20) | (static_cast<unsigned int>(cwr) & 0xfffffu);
+                kmin = key < kmin ? key : kmin;
+            }
+        }
+        kmin = __reduce_min_sync(CC_FULL_MASK, kmin);
+        nvalid = __reduce_add_sync(CC_FULL_MASK, nvalid);
+        weird = __reduce_or_sync(CC_FULL_MASK, weird);
+        int rear = 0, fore = 0;
+        const int anchor = static_cast<int>(kmin & 0xfffffu);
+        if (nvalid > 0 && !weird)
+        {
+            int lmin = 0x7fffffff, lmax = -0x7fffffff - 1;
+            for (int row = lane; row < R; row += CC_WARP)
+            {
+                const int cw = p.s_cwr[k * R + row]; // written by this very lane above
+                if (cw != CC_INVALID_CWR)
+                {
+                    const int d = cc_wrapdiff(cw - anchor, cfg.N);
+                    lmin = d < lmin ? d : lmin;
+                    lmax = d > lmax ? d : lmax;
+                }
+            }
+            rear = cc_warp_min(lmin);
+            fore = cc_warp_max(lmax);
+        }
+        if (lane == 0)
+        {
+            CcFiringSummary fs;
+            fs.anchor = anchor;
+            fs.rear_rel = rear;
+            fs.fore_rel = fore;
+            fs.nvalid = weird ? -1 : nvalid; // -1: the firing must go through the per-firing path
+            p.lite_sum[k] = fs;
+        }
+    }
+}
+
+// =====================================================================================================
+// K1-lite  the insertion scan when every firing of (a prefix of) the push is REGULAR (see k_insert_scan), done
+//     grid-wide instead of on one SM:
+//     k_scan_lite  (1 warp)      unwrapped column of every firing's anchor = prefix sum of wrapped anchor deltas;
+//                                rearmost column before every firing = prefix maximum; straddle / margin checks
+//     k_scan_check (block / row) per row the columns are strictly increasing and beyond the row's front
+//     k_scan_apply (block / row) distance write-through of the stored points, new row fronts
+//     The first irregular firing (scan_kbad) is exact; k_insert_scan then commits the prefix and processes the rest.
+// =====================================================================================================
+__global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    if (blockIdx.x != 0 || threadIdx.x >= CC_WARP)
+        return;
+    __shared__ int l_has[32], l_first[32], l_last[32], l_off[32], l_base[32];
+    CcDevState* st = p.st;
+    const int lane = threadIdx.x;
+    const int N = cfg.N, half = cfg.half;
+    const int NOT_SET = -0x7fffffff - 1;
+    const long long base = st->P;
+    const bool ok = st->F >= 0 && st->foremost >= 0 && base > 0 && st->ring_start != -1;
+    const int pc0 = static_cast<int>(base % N);
+    const int Fm0 = static_cast<int>(st->foremost - base);
+    const int colbase_rel = static_cast<int>(st->F - base);
+    if (!ok)
+    {
+        if (lane == 0)
+        {
+            st->scan_kbad = 0;
+            st->scan_lite_base = base;
+        }
+        return;
+    }
+    const int per = (n + CC_WARP - 1) / CC_WARP;
+    const int a = lane * per < n ? lane * per : n, b = (a + per < n) ? a + per : n;
+    int kbad = n;
+    // pass 1: anchor columns relative to the lane's first valid firing
+    int has = 0, first_cw = 0, prev_cw = 0, off = 0;
+    for (int k = a; k < b; k++)
+    {
+        const CcFiringSummary fs = p.lite_sum[k];
+        if (fs.nvalid < 0)
+            kbad = k < kbad ? k : kbad;
+        if (fs.nvalid > 0)
+        {
+            if (!has)
+            {
+                has = 1;
+                first_cw = fs.anchor;
+            }
+            else
+                off += cc_wrapdiff(fs.anchor - prev_cw, N);
+            prev_cw = fs.anchor;
+        }
+        p.lite_U[k] = off;
+    }
+    l_has[lane] = has;
+    l_first[lane] = first_cw;
+    l_last[lane] = prev_cw;
+    l_off[lane] = off;
+    __syncwarp();
+    if (lane == 0)
+    {
+        bool cur = false;
+        int lastU = 0, last_cw = 0;
+        for (int i = 0; i < CC_WARP; i++)
+        {
+            l_base[i] = 0;
+            if (!l_has[i])
+                continue;
+            int bU;
+            if (!cur)
+            {
+                // the reference's unwrap of the first valid firing against the rearmost column (cpp:152-175)
+                const int cw = l_first[i], diff = cw - pc0;
+                bU = -pc0 + cw;
+                if (diff < -half)
+                    bU += N;
+                else if (diff > half)
+                    bU -= N;
+                cur = true;
+            }
+            else
+                bU = lastU + cc_wrapdiff(l_first[i] - last_cw, N);
+            l_base[i] = bU;
+            lastU = bU + l_off[i];
+            last_cw = l_last[i];
+        }
+    }
+    __syncwarp();
+    // pass 2: absolute anchors, per-firing rearmost / foremost, lane-local exclusive prefix maxima
+    const int mybase = l_base[lane];
+    int runP = NOT_SET, runF = NOT_SET;
+    for (int k = a; k < b; k++)
+    {
+        const CcFiringSummary fs = p.lite_sum[k];
+        p.lite_P[k] = runP;
+        p.lite_F[k] = runF;
+        if (fs.nvalid > 0)
+        {
+            const int U = mybase + p.lite_U[k];
+            p.lite_U[k] = U;
+            const int rear = U + fs.rear_rel, fore = U + fs.fore_rel;
+            if (fore - rear > N / 2) // cpp:252-261
+                kbad = k < kbad ? k : kbad;
+            runP = rear > runP ? rear : runP;
+            runF = fore > runF ? fore : runF;
+        }
+    }
+    int eP = runP, eF = runF;
+    for (int o = 1; o < CC_WARP; o <<= 1)
+    {
+        const int vP = __shfl_up_sync(CC_FULL_MASK, eP, o), vF = __shfl_up_sync(CC_FULL_MASK, eF, o);
+        if (lane >= o)
+        {
+            eP = vP > eP ? vP : eP;
+            eF = vF > eF ? vF : eF;
+        }
+    }
+    int pP = __shfl_up_sync(CC_FULL_MASK, eP, 1), pF = __shfl_up_sync(CC_FULL_MASK, eF, 1);
+    if (lane == 0)
+    {
+        pP = NOT_SET;
+        pF = NOT_SET;
+    }
+    pP = pP > 0 ? pP : 0;      // rearmost column at the start of the push (relative: 0)
+    pF = pF > Fm0 ? pF : Fm0;  // foremost column at the start of the push
+    // pass 3: rearmost / foremost so far before every firing; unwrap margins
+    for (int k = a; k < b; k++)
+    {
+        const CcFiringSummary fs = p.lite_sum[k];
+        const int lp = p.lite_P[k], lf = p.lite_F[k];
+        const int Pk = lp > pP ? lp : pP, Fk = lf > pF ? lf : pF;
+        p.lite_P[k] = Pk;
+        p.lite_F[k] = Fk;
+        if (fs.nvalid > 0)
+        {
+            const int U = p.lite_U[k];
+            const int rear = U + fs.rear_rel, fore = U + fs.fore_rel;
+            if (!(rear - Pk > -half && fore - Pk < half))
+                kbad = k < kbad ? k : kbad; // the unwrap of some point could differ from the reference's
+            const int Pnext = rear > Pk ? rear : Pk;
+            if (Pnext - colbase_rel > p.maxcols)
+                kbad = k < kbad ? k : kbad; // the per-firing path raises the error
+        }
+    }
+    if (a < n && b == n)
+    {
+        const int Pn = runP > pP ? runP : pP, Fn = runF > pF ? runF : pF;
+        p.lite_P[n] = Pn;
+        p.lite_F[n] = Fn;
+    }
+    kbad = cc_warp_min(kbad);
+    if (lane == 0)
+    {
+        st->scan_kbad = kbad;
+        st->scan_lite_base = base;
+    }
+}
+
+struct CcOpLastSetI32
+{
+    CC_DEV int operator()(int a, int b) const { return b == (-0x7fffffff - 1) ? a : b; }
+};
+
+__global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    CC_SMEM(smem);
+    int* sm = reinterpret_cast<int*>(smem);
+    const int R = cfg.R, N = cfg.N;
+    const int row = blockIdx.x;
+    if (row >= R)
+        return;
+    const CcDevState* st = p.st;
+    const int kmax = st->scan_kbad < n ? st->scan_kbad : n;
+    const int NOT_SET = -0x7fffffff - 1;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int seg = (kmax + T - 1) / T;
+    const int a = t * seg < kmax ? t * seg : kmax, b = (a + seg < kmax) ? a + seg : kmax;
+    int first = NOT_SET, firstk = kmax, last = NOT_SET, kbad = n;
+    for (int k = a; k < b; k++)
+    {
+        const int cw = p.s_cwr[k * R + row];
+        if (cw == CC_INVALID_CWR)
+            continue;
+        const int g = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, N);
+        if (first == NOT_SET)
+        {
+            first = g;
+            firstk = k;
+        }
+        else if (g <= last)
+            kbad = k < kbad ? k : kbad;
+        last = g;
+    }
+    int prev = cc_block_exclusive_scan(sm, last, NOT_SET, CcOpLastSetI32());
+    if (prev == NOT_SET)
+    {
+        long long rel = p.rowmax[row] - st->scan_lite_base; // the row's front
+        prev = rel < -0x3fffffff ? -0x3fffffff : static_cast<int>(rel);
+    }
+    if (first != NOT_SET && first <= prev)
+        kbad = firstk < kbad ? firstk : kbad;
+    if (kbad < n)
+        atomicMin(&p.st->scan_kbad, kbad);
+}
+
+__global__ void k_scan_apply(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    CC_SMEM(smem);
+    int* sm = reinterpret_cast<int*>(smem);
+    const int R = cfg.R, N = cfg.N, ringcols = cfg.ringcols;
+    const int row = blockIdx.x;
+    if (row >= R)
+        return;
+    const CcDevState* st = p.st;
+    const int kbad = st->scan_kbad < n ? st->scan_kbad : n;
+    const long long base = st->scan_lite_base;
+    const int base_local = static_cast<int>(base % ringcols);
+    const int NOT_SET = -0x7fffffff - 1;
+    if (threadIdx.x == 0)
+        sm[0] = NOT_SET;
+    __syncthreads();
+    int gmax = NOT_SET;
+    for (int k = threadIdx.x; k < kbad; k += blockDim.x)
+    {
+        const int idx = k * R + row;
+        const int cw = p.s_cwr[idx];
+        if (cw == CC_INVALID_CWR)
+            continue;
+        const int g = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, N);
+        if (g < p.lite_P[k])
+            continue; // too far behind (cpp:210-221)
+        int local = base_local + g;
+        local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+        p.pos[static_cast<size_t>(local) * R + row].w = p.s_dist[idx]; // write-through, as k_insert_scan does
+        gmax = g > gmax ? g : gmax;
+    }
+    gmax = cc_warp_max(gmax);
+    if ((threadIdx.x % CC_WARP) == 0 && gmax != NOT_SET)
+        atomicMax(&sm[0], gmax);
+    __syncthreads();
+    if (threadIdx.x == 0 && sm[0] != NOT_SET)
+    {
+        const long long front = base + sm[0];
+        if (front > p.rowmax[row])
+            p.rowmax[row] = front;
     }
 }
 
@@ -198,7 +504,7 @@ struct CcScanState // uniform across the CTA, kept in registers by every thread
     int reset_required, error;
 };
 
-__global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C)
+__global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
 {
     if (blockIdx.x != 0)
         return;
@@ -241,6 +547,14 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
     const bool p_positive_at_start = base > 0;
 
     const int n_chunks = (n_firings + C - 1) / C;
+    // firings [0, k_start) were resolved by the lite path (k_scan_lite / _check / _apply)
+    int k_start = 0;
+    if (after_lite)
+    {
+        k_start = st->scan_kbad;
+        k_start = k_start < 0 ? 0 : (k_start > n_firings ? n_firings : k_start);
+    }
+    const int chunk_start = k_start / C;
     auto prefetch = [&](int chunk)
     {
         if (chunk < n_chunks)
@@ -255,7 +569,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         }
         __pipeline_commit();
     };
-    prefetch(0);
+    prefetch(chunk_start);
 
     for (int row = tid; row < R; row += T)
     {
@@ -285,12 +599,31 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         s.reset_required = st->reset_required;
         s.error = 0;
     }
+    if (k_start > 0)
+    {
+        // commit the lite prefix: columns completed by each firing (cpp:289-291), rearmost / foremost so far
+        for (int k = tid; k < k_start; k += T)
+            for (int c = p.lite_P[k]; c < p.lite_P[k + 1]; c++)
+                p.col_trigger[c - s.colbase_rel] = k;
+        const int Pnew = p.lite_P[k_start], Fnew = p.lite_F[k_start];
+        s.pc += Pnew - s.Prel;
+        while (s.pc >= N)
+        {
+            s.pc -= N;
+            s.prev_rot++;
+        }
+        s.Prel = Pnew;
+        s.Frel = Pnew;
+        s.Fmrel = Fnew;
+        if (base + s.Fmrel > s.ring_end)
+            s.ring_end = base + s.Fmrel;
+    }
     __syncthreads();
 
     bool stop = false;
     int n_fast = 0, n_slow = 0, n_attempts = 0;
     int slow_run = CC_K1_SLOW_RUN; // grows while fast attempts keep failing early (dense collisions)
-    for (int chunk = 0; chunk < n_chunks && !stop; chunk++)
+    for (int chunk = chunk_start; chunk < n_chunks && !stop && k_start < n_firings; chunk++)
     {
         prefetch(chunk + 1);
         __pipeline_wait_prior(1);
@@ -298,7 +631,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         const int k0 = chunk * C;
         const int kc = (n_firings - k0) < C ? (n_firings - k0) : C;
         const int cbuf = (chunk & 1) * C * R;
-        int ka = 0; // next firing of the chunk to process
+        int ka = chunk == chunk_start ? k_start - k0 : 0; // next firing of the chunk to process
         while (ka < kc && !stop)
         {
             int kgood = ka; // firings [ka, kgood) are resolved by the fast path
@@ -767,6 +1100,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
     if (tid == 0)
     {
         st->scan_base = base;
+        st->scan_lite_firings = k_start;
         st->scan_fast_firings = n_fast;
         st->scan_slow_firings = n_slow;
         st->scan_fast_attempts = n_attempts;
@@ -803,11 +1137,22 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
         const int k = idx / cfg.R, row = idx - k * cfg.R;
-        const CcFiringRecord rec = p.firing_rec[k];
         int grel, rot;
-        if (rec.mode)
+        if (k < p.st->scan_kbad)
+        {
+            // firing resolved by the lite path: same integers as k_scan_check / k_scan_apply
+            const int cw = p.s_cwr[idx];
+            if (cw == CC_INVALID_CWR)
+                continue;
+            grel = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, cfg.N);
+            if (grel < p.lite_P[k])
+                continue; // too far behind (cpp:210-221)
+            rot = static_cast<int>((p.st->scan_base + grel - cw) / cfg.N); // exact: column == rot * N + cw
+        }
+        else if (p.firing_rec[k].mode)
         {
             // regular firing: recompute the unwrap of the scan (same integers) instead of reading per-point outputs
+            const CcFiringRecord rec = p.firing_rec[k];
             const int cw = p.s_cwr[idx];
             if (cw == CC_INVALID_CWR)
                 continue;

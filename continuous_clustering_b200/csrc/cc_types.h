@@ -99,7 +99,9 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long push_first_unpub_old; // first_unpub before the first finish pass of this push
     int sv_n_clusters, sv_n_cluster_points;
     int scan_fast_firings, scan_slow_firings, scan_fast_attempts; // insertion scan statistics of this push
-    int pad_;
+    int scan_kbad;            // firings [0, scan_kbad) were resolved by the lite insertion path
+    long long scan_lite_base; // column the lite arrays are relative to
+    int scan_lite_firings, pad_;
 };
 
 struct CcFiringRecord // insertion scan -> K1b: how the points of one firing were resolved
@@ -107,6 +109,14 @@ struct CcFiringRecord // insertion scan -> K1b: how the points of one firing wer
     int mode; // 1: regular firing, column = unwrap(cwr) with the integers below; 0: per point in o_g / o_rot
     int goff, pc, rot, P;
     int pad_[3];
+};
+
+struct CcFiringSummary // k_prep -> lite insertion path
+{
+    int anchor;   // column-in-rotation of the firing's first valid row
+    int rear_rel; // rearmost / foremost column of the firing relative to the anchor (wrapped into (-N/2, N/2])
+    int fore_rel;
+    int nvalid;   // valid points; -1 = a column-in-rotation outside [0, N]: per-firing path only
 };
 
 struct CcCluster // device -> host record of one finished cluster with more than 5 points (cpp:936-940)
@@ -166,6 +176,10 @@ struct CcDevPtrs
     int* o_g;             // resolved global column relative to CcDevState::scan_base, INT_MIN = not stored
     int* o_rot;           // rotation index used for the continuous azimuth
     CcFiringRecord* firing_rec; // [max_firings]
+    CcFiringSummary* lite_sum;  // [max_firings]
+    int* lite_U;                // [max_firings] unwrapped anchor column, relative to scan_lite_base
+    int* lite_P;                // [max_firings + 1] rearmost column so far before firing k
+    int* lite_F;                // [max_firings + 1] foremost column so far before firing k
     // ---- per new column (maxcols) ----
     int* col_trigger;     // firing (index in this push) whose insertion completed the column (hpp:169-173)
     float* col_gap;       // [maxcols * R] value of sc_inclination_angles_between_lasers_ when the column is segmented

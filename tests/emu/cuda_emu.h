@@ -21,6 +21,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __shared__ static
 
 struct emu_dim3
 {
@@ -89,7 +90,13 @@ static inline unsigned __ballot_sync(unsigned, int p)
 {
     return p ? 1u : 0u;
 }
-static inline int __reduce_min_sync(unsigned, int v)
+template<typename T>
+static inline T __reduce_min_sync(unsigned, T v)
+{
+    return v;
+}
+template<typename T>
+static inline T __reduce_add_sync(unsigned, T v)
 {
     return v;
 }
