@@ -346,6 +346,11 @@ def main():
     # ------------------------------------------------------------------ end-to-end leg through the public API
     cc = new_handle()
     h_pts, h_poses = tile_stream(base_pts, base_poses, sp, 0, total)
+    # page-locked host buffers (the contract's "pinned host memory"): cc_push_firings copies them straight to the device
+    pin_pts = torch.from_numpy(h_pts.view(np.uint8).reshape(total, R * 48)).pin_memory()
+    pin_poses = torch.from_numpy(h_poses).pin_memory()
+    h_pts = pin_pts.numpy().view(h_pts.dtype).reshape(total, R)
+    h_poses = pin_poses.numpy()
     d2h = 0
     for s in range(W):
         cc.addFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])

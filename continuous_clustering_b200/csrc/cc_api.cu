@@ -42,6 +42,7 @@ struct cc_handle
     int gap_rows{-1};
     int debug_flag_period{0};
     size_t probe_smem_set{0};
+    size_t lite_smem_set{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
     unsigned int* d_s_links{nullptr};
@@ -234,7 +235,7 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     cc_handle* h = new cc_handle();
     h->device = device_ordinal;
     if (max_firings_per_push > 0)
-        h->max_firings = max_firings_per_push;
+        h->max_firings = std::min(max_firings_per_push, 8192); // per-firing scan arrays must fit one CTA's shared memory
     cc_config_default(&h->config);
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -711,7 +712,20 @@ static cc_status_t run_push(cc_handle* h, int n)
     const long long pts = static_cast<long long>(n) * R;
     CC_RUN(h, k_prep, grid_for(h, static_cast<long long>(n) * CC_WARP, 256), 256, 0, cfg, h->d, n);
     // lite insertion path (regular prefix of the push, grid-wide) ...
-    CC_RUN(h, k_scan_lite, 1, CC_WARP, 0, cfg, h->d, n);
+    {
+        const size_t lite_smem = static_cast<size_t>(n) * (sizeof(CcFiringSummary) + sizeof(int)) + 2 * (static_cast<size_t>(n) + 1) * sizeof(int);
+#ifndef CC_EMU
+        if (lite_smem > 48 * 1024 && lite_smem > h->lite_smem_set)
+        {
+            CC_CHECK(h, cudaFuncSetAttribute(k_scan_lite, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lite_smem)));
+            h->lite_smem_set = lite_smem;
+        }
+        const int lite_threads = 256;
+#else
+        const int lite_threads = 1;
+#endif
+        CC_RUN(h, k_scan_lite, 1, lite_threads, lite_smem, cfg, h->d, n);
+    }
     CC_RUN(h, k_scan_check, R, 256, 256 * sizeof(int), cfg, h->d, n);
     CC_RUN(h, k_scan_apply, R, 256, 256 * sizeof(int), cfg, h->d, n);
     // ... then the single-CTA scan commits that prefix and resolves whatever is left

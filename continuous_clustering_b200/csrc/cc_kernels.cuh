@@ -240,13 +240,43 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 //     k_scan_apply (block / row) distance write-through of the stored points, new row fronts
 //     The first irregular firing (scan_kbad) is exact; k_insert_scan then commits the prefix and processes the rest.
 // =====================================================================================================
-__global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
+__global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
 {
-    if (blockIdx.x != 0 || threadIdx.x >= CC_WARP)
+    if (blockIdx.x != 0)
         return;
+    CC_SMEM(smem);
     __shared__ int l_has[32], l_first[32], l_last[32], l_off[32], l_base[32];
-    CcDevState* st = p.st;
+    // the per-firing arrays live in shared memory while the single warp below works on them (L2 round trips per
+    // firing would dominate otherwise); all threads of the CTA copy them in and out
+    // (structure of arrays + an odd per-lane range length: lane i works on firings [i*per, (i+1)*per), so
+    // consecutive lanes hit consecutive banks)
+    struct Local
+    {
+        int *s_anchor, *s_rear, *s_fore, *s_nvalid;
+        int *lite_U, *lite_P, *lite_F;
+        int maxcols;
+    } p;
+    p.s_anchor = reinterpret_cast<int*>(smem);
+    p.s_rear = p.s_anchor + n;
+    p.s_fore = p.s_rear + n;
+    p.s_nvalid = p.s_fore + n;
+    p.lite_U = p.s_nvalid + n;
+    p.lite_P = p.lite_U + n;
+    p.lite_F = p.lite_P + n + 1;
+    p.maxcols = pg.maxcols;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const CcFiringSummary fs = pg.lite_sum[i];
+        p.s_anchor[i] = fs.anchor;
+        p.s_rear[i] = fs.rear_rel;
+        p.s_fore[i] = fs.fore_rel;
+        p.s_nvalid[i] = fs.nvalid;
+    }
+    __syncthreads();
+    CcDevState* st = pg.st;
     const int lane = threadIdx.x;
+    if (threadIdx.x < CC_WARP)
+    {
     const int N = cfg.N, half = cfg.half;
     const int NOT_SET = -0x7fffffff - 1;
     const long long base = st->P;
@@ -261,16 +291,21 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
             st->scan_kbad = 0;
             st->scan_lite_base = base;
         }
-        return;
     }
-    const int per = (n + CC_WARP - 1) / CC_WARP;
+    else
+    {
+    const int per = ((n + CC_WARP - 1) / CC_WARP) | 1;
     const int a = lane * per < n ? lane * per : n, b = (a + per < n) ? a + per : n;
     int kbad = n;
     // pass 1: anchor columns relative to the lane's first valid firing
     int has = 0, first_cw = 0, prev_cw = 0, off = 0;
     for (int k = a; k < b; k++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
+        CcFiringSummary fs;
+        fs.anchor = p.s_anchor[k];
+        fs.rear_rel = p.s_rear[k];
+        fs.fore_rel = p.s_fore[k];
+        fs.nvalid = p.s_nvalid[k];
         if (fs.nvalid < 0)
             kbad = k < kbad ? k : kbad;
         if (fs.nvalid > 0)
@@ -325,7 +360,11 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
     int runP = NOT_SET, runF = NOT_SET;
     for (int k = a; k < b; k++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
+        CcFiringSummary fs;
+        fs.anchor = p.s_anchor[k];
+        fs.rear_rel = p.s_rear[k];
+        fs.fore_rel = p.s_fore[k];
+        fs.nvalid = p.s_nvalid[k];
         p.lite_P[k] = runP;
         p.lite_F[k] = runF;
         if (fs.nvalid > 0)
@@ -360,7 +399,11 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
     // pass 3: rearmost / foremost so far before every firing; unwrap margins
     for (int k = a; k < b; k++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
+        CcFiringSummary fs;
+        fs.anchor = p.s_anchor[k];
+        fs.rear_rel = p.s_rear[k];
+        fs.fore_rel = p.s_fore[k];
+        fs.nvalid = p.s_nvalid[k];
         const int lp = p.lite_P[k], lf = p.lite_F[k];
         const int Pk = lp > pP ? lp : pP, Fk = lf > pF ? lf : pF;
         p.lite_P[k] = Pk;
@@ -387,6 +430,16 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
     {
         st->scan_kbad = kbad;
         st->scan_lite_base = base;
+    }
+    }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= n; i += blockDim.x)
+    {
+        if (i < n)
+            pg.lite_U[i] = p.lite_U[i];
+        pg.lite_P[i] = p.lite_P[i];
+        pg.lite_F[i] = p.lite_F[i];
     }
 }
 
@@ -578,9 +631,15 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         if (rel < -0x3fffffff)
             rel = -0x3fffffff;
         rmx[row] = static_cast<int>(rel);
-        for (long long c = (rm - W + 1 > 0 ? rm - W + 1 : 0); c <= rm; c++)
-            wdist[(c & (W - 1)) * R + row] = p.pos[static_cast<size_t>(cc_local_col(c, ringcols)) * R + row].w;
     }
+    if (k_start < n_firings) // occupancy window of the last W columns of every row, from the ring
+        for (int i = tid; i < R * W; i += T)
+        {
+            const int row = i % R;
+            const long long c = p.rowmax[row] - i / R;
+            if (c >= 0)
+                wdist[(c & (W - 1)) * R + row] = p.pos[static_cast<size_t>(cc_local_col(c, ringcols)) * R + row].w;
+        }
 
     CcScanState s;
     {
