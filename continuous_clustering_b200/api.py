@@ -236,6 +236,33 @@ class ContinuousClustering:
         self._dispatch(out)
         return out
 
+    # ---- asynchronous pushes: keep the GPU busy with submit(k + 1); wait(k) ----
+    def submitFirings(self, points: np.ndarray, poses: np.ndarray):
+        points = np.ascontiguousarray(points, dtype=RAW_POINT_DTYPE)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        n, rows = points.shape
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((points, poses))  # inputs must stay alive until waited for
+        self._check(self._L.cc_submit_firings(self._h, n, rows, points.ctypes.data, poses.ctypes.data))
+
+    def submitFiringsDevice(self, d_points: int, d_poses: int, n: int, rows: int):
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append(None)
+        self._check(self._L.cc_submit_firings_device(self._h, n, rows, d_points, d_poses))
+
+    def wait(self) -> BatchResult:
+        """Finishes the oldest submitted push and returns its results (callbacks are dispatched here)."""
+        self._check(self._L.cc_wait(self._h))
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
+        out = self._collect()
+        self._dispatch(out)
+        return out
+
+    @property
+    def pending(self) -> int:
+        return int(self._L.cc_pending(self._h))
+
     def _collect(self) -> BatchResult:
         """Results of the last push as numpy views of the handle's own arrays (valid until the next push)."""
         info = _lib.CcBatchInfo()

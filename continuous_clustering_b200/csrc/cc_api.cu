@@ -41,23 +41,45 @@ struct cc_handle
     int maxcols{0};
     int gap_rows{-1};
     int debug_flag_period{0};
+    int used_exact_flag{0};
     size_t probe_smem_set{0};
     size_t lite_smem_set{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
     unsigned int* d_s_links{nullptr};
-    unsigned char* d_raw{nullptr};
-    double* d_poses{nullptr};
+    // per-push buffers, double-buffered so that a push can be in flight while the previous one is collected
+    struct Slot
+    {
+        // device
+        CcDevState* d_state_snap{nullptr};
+        long long* d_first_unpub{nullptr};
+        CcCluster* d_clusters{nullptr};
+        CcClusterPoint* d_points{nullptr};
+        unsigned char* d_raw{nullptr};
+        double* d_poses{nullptr};
+        // page-locked host
+        CcDevState* h_state{nullptr};
+        long long* h_first_unpub{nullptr};
+        CcCluster* h_clusters{nullptr};
+        CcClusterPoint* h_points{nullptr};
+        void* h_raw{nullptr};
+        double* h_poses{nullptr};
+        cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr}, h2d{nullptr};
+        // the push occupying the slot
+        int n{0};
+        const void* in_points{nullptr}; // device pointers of the inputs
+        const double* in_poses{nullptr};
+        bool has_tf{false}, spec{false};
+        uint64_t launches0{0}, launches1{0};
+        int pre_cols{0}, pre_clusters{0}, pre_points{0};
+    } slots[2];
+    int next_slot{0};
+    int pending[2]{-1, -1}; // slots of the pushes in flight, oldest first
+    int n_pending{0};
+    cudaStream_t copy_stream{nullptr};
     std::vector<void*> allocs;       // freed on destroy / re-reset
     std::vector<void*> allocs_fixed; // independent of the ring size
-    void* h_raw{nullptr};            // pinned staging
-    double* h_poses{nullptr};
-    CcDevState* h_state{nullptr}; // pinned mirror
-    // pinned landing buffers: the state and a prefix of the results come back with ONE stream synchronisation
-    long long* hp_first_unpub{nullptr};
-    CcCluster* hp_clusters{nullptr};
-    CcClusterPoint* hp_points{nullptr};
-    int pre_cols{0}, pre_clusters{0}, pre_points{0}; // how much of each the last fetch brought
+    CcDevState* h_state{nullptr}; // pinned mirror (reset, column-sequential path)
     CcDevState state{};
     unsigned int seq{0};
     uint64_t launches{0};
@@ -80,6 +102,7 @@ struct cc_handle
 
 static int timing_begin(cc_handle* h, const char* name);
 static void timing_end(cc_handle* h, int i);
+static void free_host_slots(cc_handle* h);
 
 #define CC_CHECK(h, expr)                                                                                              \
     do                                                                                                                 \
@@ -115,6 +138,23 @@ static void timing_end(cc_handle* h, int i)
 {
     if (i >= 0)
         cudaEventRecord(h->tev[2 * i + 1], h->stream);
+}
+
+static void free_host_slots(cc_handle* h)
+{
+    for (cc_handle::Slot& sl : h->slots)
+    {
+        for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters),
+                        static_cast<void*>(sl.h_points), sl.h_raw, static_cast<void*>(sl.h_poses)})
+            if (q)
+                cudaFreeHost(q);
+        sl.h_state = nullptr;
+        sl.h_first_unpub = nullptr;
+        sl.h_clusters = nullptr;
+        sl.h_points = nullptr;
+        sl.h_raw = nullptr;
+        sl.h_poses = nullptr;
+    }
 }
 
 static void free_list(std::vector<void*>& v)
@@ -239,12 +279,21 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     cc_config_default(&h->config);
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(CcDevState)) != cudaSuccess)
     {
         delete h;
         return CC_ERR_CUDA;
     }
+    for (cc_handle::Slot& sl : h->slots)
+        if (cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess ||
+            cudaEventCreate(&sl.ready) != cudaSuccess || cudaEventCreate(&sl.done) != cudaSuccess ||
+            cudaEventCreate(&sl.h2d) != cudaSuccess)
+        {
+            delete h;
+            return CC_ERR_CUDA;
+        }
 #ifndef CC_EMU
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
@@ -263,18 +312,17 @@ void cc_destroy(cc_handle_t* h)
         cudaStreamSynchronize(h->stream);
     free_list(h->allocs);
     free_list(h->allocs_fixed);
-    if (h->h_raw)
-        cudaFreeHost(h->h_raw);
-    if (h->h_poses)
-        cudaFreeHost(h->h_poses);
+    if (h->copy_stream)
+        cudaStreamSynchronize(h->copy_stream);
+    free_host_slots(h);
+    for (cc_handle::Slot& sl : h->slots)
+        for (cudaEvent_t e : {sl.ev0, sl.ev1, sl.ready, sl.done, sl.h2d})
+            if (e)
+                cudaEventDestroy(e);
+    if (h->copy_stream)
+        cudaStreamDestroy(h->copy_stream);
     if (h->h_state)
         cudaFreeHost(h->h_state);
-    if (h->hp_first_unpub)
-        cudaFreeHost(h->hp_first_unpub);
-    if (h->hp_clusters)
-        cudaFreeHost(h->hp_clusters);
-    if (h->hp_points)
-        cudaFreeHost(h->hp_points);
     if (h->ev0)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
@@ -397,6 +445,9 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         return CC_ERR_INVALID_ARGUMENT;
     CC_CHECK(h, cudaSetDevice(h->device));
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+    h->n_pending = 0;
+    h->next_slot = 0;
     const int N = h->config.num_columns;
     const bool realloc_ring = (num_rows != h->R) || (N != h->N) || h->allocs.empty();
     if (realloc_ring)
@@ -452,14 +503,11 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.lite_U, static_cast<size_t>(h->max_firings)));
         CC_CHECK(h, dev_alloc(h, L, &d.lite_P, static_cast<size_t>(h->max_firings) + 1));
         CC_CHECK(h, dev_alloc(h, L, &d.lite_F, static_cast<size_t>(h->max_firings) + 1));
-        CC_CHECK(h, dev_alloc(h, L, &h->d_raw, stage * sizeof(cc_raw_point_t)));
-        CC_CHECK(h, dev_alloc(h, L, &h->d_poses, static_cast<size_t>(h->max_firings) * 12));
         const size_t mc = static_cast<size_t>(h->maxcols);
         CC_CHECK(h, dev_alloc(h, L, &d.col_trigger, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_gap, mc * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.col_minaz, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_runmax, mc));
-        CC_CHECK(h, dev_alloc(h, L, &d.col_first_unpub, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_flag, mc));
         CC_CHECK(h, dev_alloc(h, L, &h->d_s_parent, mc * h->R));
         CC_CHECK(h, dev_alloc(h, L, &h->d_s_links, mc * h->R * CC_LINK_SLOTS));
@@ -487,31 +535,28 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.edge_a, static_cast<size_t>(d.cap_edges)));
         CC_CHECK(h, dev_alloc(h, L, &d.edge_b, static_cast<size_t>(d.cap_edges)));
         CC_CHECK(h, dev_alloc(h, L, &d.G, static_cast<size_t>(d.cap_G)));
-        CC_CHECK(h, dev_alloc(h, L, &d.clusters, static_cast<size_t>(d.cap_clusters)));
-        CC_CHECK(h, dev_alloc(h, L, &d.cluster_points, static_cast<size_t>(d.cap_cluster_points)));
         CC_CHECK(h, dev_alloc(h, L, &d.n_new_ulist, 1));
-        d.raw = h->d_raw;
-        d.poses = h->d_poses;
-        if (h->h_raw)
-            cudaFreeHost(h->h_raw);
-        if (h->h_poses)
-            cudaFreeHost(h->h_poses);
-        h->h_raw = nullptr;
-        h->h_poses = nullptr;
-        CC_CHECK(h, cudaMallocHost(&h->h_raw, stage * sizeof(cc_raw_point_t)));
-        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
-        if (h->hp_first_unpub)
-            cudaFreeHost(h->hp_first_unpub);
-        if (h->hp_clusters)
-            cudaFreeHost(h->hp_clusters);
-        if (h->hp_points)
-            cudaFreeHost(h->hp_points);
-        h->hp_first_unpub = nullptr;
-        h->hp_clusters = nullptr;
-        h->hp_points = nullptr;
-        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_first_unpub), mc * sizeof(long long)));
-        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
-        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->hp_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
+        free_host_slots(h);
+        for (cc_handle::Slot& sl : h->slots)
+        {
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_state_snap, 1));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_first_unpub, mc));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_clusters, static_cast<size_t>(d.cap_clusters)));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_points, static_cast<size_t>(d.cap_cluster_points)));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_raw, stage * sizeof(cc_raw_point_t)));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_poses, static_cast<size_t>(h->max_firings) * 12));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_state), sizeof(CcDevState)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_first_unpub), mc * sizeof(long long)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
+            CC_CHECK(h, cudaMallocHost(&sl.h_raw, stage * sizeof(cc_raw_point_t)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
+        }
+        d.raw = h->slots[0].d_raw;
+        d.poses = h->slots[0].d_poses;
+        d.col_first_unpub = h->slots[0].d_first_unpub;
+        d.clusters = h->slots[0].d_clusters;
+        d.cluster_points = h->slots[0].d_points;
         CC_CHECK(h, cudaMemsetAsync(d.firing_index, 0, cells * sizeof(unsigned long long), h->stream));
         CC_CHECK(h, cudaMemsetAsync(d.cparent, 0, cells * sizeof(unsigned int), h->stream));
         CC_CHECK(h, cudaMemsetAsync(d.tfinish, 0, cells * sizeof(unsigned long long), h->stream));
@@ -576,23 +621,9 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     return CC_OK;
 }
 
-static cc_status_t fetch_state(cc_handle* h, int n_firings_hint = -1)
+static cc_status_t fetch_state(cc_handle* h)
 {
     CC_CHECK(h, cudaMemcpyAsync(h->h_state, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->stream));
-    h->pre_cols = h->pre_clusters = h->pre_points = 0;
-    if (n_firings_hint >= 0)
-    {
-        // optimistic prefix of the results in the same round trip (what a push normally produces fits)
-        h->pre_cols = std::min(h->maxcols, n_firings_hint + 64);
-        h->pre_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
-        h->pre_points = std::min(h->d.cap_cluster_points, CC_PREFETCH_POINTS);
-        CC_CHECK(h, cudaMemcpyAsync(h->hp_first_unpub, h->d.col_first_unpub, h->pre_cols * sizeof(long long),
-                                    cudaMemcpyDeviceToHost, h->stream));
-        CC_CHECK(h, cudaMemcpyAsync(h->hp_clusters, h->d.clusters, h->pre_clusters * sizeof(CcCluster),
-                                    cudaMemcpyDeviceToHost, h->stream));
-        CC_CHECK(h, cudaMemcpyAsync(h->hp_points, h->d.cluster_points, h->pre_points * sizeof(CcClusterPoint),
-                                    cudaMemcpyDeviceToHost, h->stream));
-    }
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
     h->state = *h->h_state;
     return CC_OK;
@@ -689,24 +720,53 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
         }
         ci = cj + 1;
     }
-    h->info.used_exact_path = 1;
+    h->used_exact_flag = 1;
     return CC_OK;
 }
 
-static cc_status_t run_push(cc_handle* h, int n)
+// state snapshot + optimistic prefix of the results of the push in `sl`, brought to the host on the copy stream so
+// that the next push's kernels do not wait for the transfer (the device-side result arrays are per slot)
+static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl)
+{
+    CC_CHECK(h, cudaMemcpyAsync(sl.d_state_snap, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToDevice, h->stream));
+    CC_CHECK(h, cudaEventRecord(sl.ready, h->stream));
+    CC_CHECK(h, cudaStreamWaitEvent(h->copy_stream, sl.ready, 0));
+    sl.pre_cols = std::min(h->maxcols, sl.n + 64);
+    sl.pre_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
+    sl.pre_points = std::min(h->d.cap_cluster_points, CC_PREFETCH_POINTS);
+    CC_CHECK(h, cudaMemcpyAsync(sl.h_state, sl.d_state_snap, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->copy_stream));
+    CC_CHECK(h, cudaMemcpyAsync(sl.h_first_unpub, sl.d_first_unpub, sl.pre_cols * sizeof(long long),
+                                cudaMemcpyDeviceToHost, h->copy_stream));
+    CC_CHECK(h, cudaMemcpyAsync(sl.h_clusters, sl.d_clusters, sl.pre_clusters * sizeof(CcCluster),
+                                cudaMemcpyDeviceToHost, h->copy_stream));
+    CC_CHECK(h, cudaMemcpyAsync(sl.h_points, sl.d_points, sl.pre_points * sizeof(CcClusterPoint),
+                                cudaMemcpyDeviceToHost, h->copy_stream));
+    CC_CHECK(h, cudaEventRecord(sl.done, h->copy_stream));
+    return CC_OK;
+}
+
+static void bind_slot(cc_handle* h, const cc_handle::Slot& sl)
+{
+    h->d.raw = sl.in_points;
+    h->d.poses = sl.in_poses;
+    h->d.col_first_unpub = sl.d_first_unpub;
+    h->d.clusters = sl.d_clusters;
+    h->d.cluster_points = sl.d_points;
+}
+
+// Enqueues every kernel of one push on the handle's stream (nothing here waits for the device).
+static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
 {
     CcDevCfg cfg;
     fill_devcfg(h, cfg);
-    h->launches_at_push_start = h->launches;
+    bind_slot(h, sl);
+    const int n = sl.n;
+    sl.launches0 = h->launches;
     h->n_timed = 0;
-    h->events.clear();
-    h->clusters.clear();
-    h->cluster_points.clear();
-    std::memset(&h->info, 0, sizeof(h->info));
-    const long long ring_start_before = h->state.ring_start;
-    (void)ring_start_before;
+    sl.has_tf = h->has_tf;
+    sl.spec = cfg.nth == 1;
 
-    CC_CHECK(h, cudaEventRecord(h->ev0, h->stream));
+    CC_CHECK(h, cudaEventRecord(sl.ev0, h->stream));
     const int R = h->R;
     CC_RUN(h, k_clear, h->sm_count * 8, 256, 0, cfg, h->d, 0LL, 0LL, 1); // columns retired by the previous push
     const long long pts = static_cast<long long>(n) * R;
@@ -733,25 +793,18 @@ static cc_status_t run_push(cc_handle* h, int n)
     CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R), 1);
     CC_RUN(h, k_scatter, grid_for(h, pts, 256), 256, 0, cfg, h->d, n);
 
-    if (!h->has_tf)
+    if (!sl.has_tf)
     {
-        // the reference throws from the segmentation stage of the first completed column (cpp:298-299)
-        cc_status_t s = fetch_state(h);
-        if (s != CC_OK)
-            return s;
-        if (h->state.ncols > 0)
-        {
-            h->error = "Transform robot frame from sensor frame was not set yet!";
-            return CC_ERR_NO_ROBOT_TRANSFORM;
-        }
+        // the reference throws from the segmentation stage of the first completed column (cpp:298-299): nothing
+        // after insertion runs; pushes queued behind this one must not run either
+        CC_RUN(h, k_halt, 1, 1, 0, h->d, 1);
     }
     else
     {
         CC_RUN(h, k_gap_scan, R, 256, 256 * sizeof(float), cfg, h->d);
         const int gw = 4; // warps (columns) per block
         CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, gw * R * sizeof(CcGroundSmem), cfg, h->d);
-        const bool spec = cfg.nth == 1;
-        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d, spec ? 1 : 0);
+        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d, sl.spec ? 1 : 0);
         {
             // one CTA per tile of 2 new columns; the tile's sliding window of prior columns is staged in shared
             // memory; warps take the tile's non-ignored points from a shared list
@@ -769,78 +822,138 @@ static cc_status_t run_push(cc_handle* h, int n)
 #endif
             CC_RUN(h, k_probe, h->sm_count * 8, 256, win_bytes, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem);
         }
-        if (spec)
+        if (sl.spec)
         {
             launch_commit(h, cfg, 0, -1, 1, false);
             launch_finish(h, cfg, 0, -1, 1, 0, 1);
         }
-        CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
-        cc_status_t s = fetch_state(h, n);
+        else
+            CC_RUN(h, k_halt, 1, 1, 0, h->d, 0); // finish passes every n-th column: column-sequential path, on the host's cue
+    }
+    CC_CHECK(h, cudaEventRecord(sl.ev1, h->stream));
+    sl.launches1 = h->launches;
+    return enqueue_results(h, sl);
+}
+
+// Waits for the oldest push in flight, finishes it (column-sequential path if the speculative commit could not be
+// used) and builds its results.
+static cc_status_t finish_push(cc_handle* h)
+{
+    if (h->n_pending == 0)
+    {
+        h->error = "no push in flight";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    cc_handle::Slot& sl = h->slots[h->pending[0]];
+    h->events.clear();
+    h->clusters.clear();
+    h->cluster_points.clear();
+    std::memset(&h->info, 0, sizeof(h->info));
+    auto pop = [&]()
+    {
+        h->pending[0] = h->pending[1];
+        h->n_pending--;
+    };
+    CC_CHECK(h, cudaEventSynchronize(sl.done));
+    h->state = *sl.h_state;
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    cc_status_t es = device_error_to_status(h);
+    if (es == CC_OK && !sl.has_tf && h->state.ncols > 0)
+    {
+        h->error = "Transform robot frame from sensor frame was not set yet!";
+        es = CC_ERR_NO_ROBOT_TRANSFORM;
+    }
+    if (es != CC_OK)
+    {
+        // later pushes saw the halt flag and did nothing; they are dropped. The stream needs a reset, like the
+        // reference after an exception escaped addFiring.
+        h->n_pending = 0;
+        return es;
+    }
+    if (sl.has_tf && h->state.ncols > 0 && (!sl.spec || h->state.n_flagged > 0 || h->state.abort))
+    {
+        // the speculative commit was not usable: pushes queued behind this one skipped themselves (halt flag).
+        // Finish this push column-sequentially, then run them again.
+        for (int i = 1; i < h->n_pending; i++)
+            CC_CHECK(h, cudaEventSynchronize(h->slots[h->pending[i]].done));
+        bind_slot(h, sl);
+        CC_RUN(h, k_halt, 1, 1, 0, h->d, -1); // clear
+        if (h->state.abort)
+        {
+            CC_RUN(h, k_restore, h->sm_count * 2, 256, 0, h->d);
+            CC_RUN(h, k_restore_finish, 1, 1, 0, h->d);
+        }
+        cc_status_t s = slow_path(h, cfg);
+        if (s != CC_OK)
+        {
+            h->n_pending = 0;
+            return s;
+        }
+        CC_RUN(h, k_push_done, 1, 1, 0, h->d, 0);
+        CC_CHECK(h, cudaEventRecord(sl.ev1, h->stream));
+        sl.launches1 = h->launches;
+        s = enqueue_results(h, sl);
         if (s != CC_OK)
             return s;
-        if (h->state.error == 0 && h->state.ncols > 0 && (!spec || h->state.n_flagged > 0 || h->state.abort))
+        for (int i = 1; i < h->n_pending; i++)
         {
-            if (h->state.abort)
-            {
-                CC_RUN(h, k_restore, h->sm_count * 2, 256, 0, h->d);
-                CC_RUN(h, k_restore_finish, 1, 1, 0, h->d);
-            }
-            s = slow_path(h, cfg);
-            if (s != CC_OK)
-                return s;
-            CC_RUN(h, k_push_done, 1, 1, 0, h->d, 0);
-            CC_CHECK(h, cudaEventRecord(h->ev1, h->stream));
-            s = fetch_state(h, n);
+            s = launch_push(h, h->slots[h->pending[i]]);
             if (s != CC_OK)
                 return s;
         }
+        CC_CHECK(h, cudaEventSynchronize(sl.done));
+        h->state = *sl.h_state;
+        es = device_error_to_status(h);
+        if (es != CC_OK)
+        {
+            h->n_pending = 0;
+            return es;
+        }
     }
     CC_CHECK(h, cudaGetLastError());
-    cc_status_t es = device_error_to_status(h);
-    if (es != CC_OK)
-        return es;
 
-    // ---- bring the results of the push to the host ----
+    // ---- results of the push ----
     const CcDevState& st = h->state;
-    const int ncols = h->has_tf ? st.ncols : 0;
+    const int ncols = sl.has_tf ? st.ncols : 0;
     const int ncl = st.n_clusters, ncp = st.n_cluster_points;
     h->h_first_unpub.resize(ncols);
     h->h_clusters.resize(ncl);
     h->cluster_points.resize(ncp);
     static_assert(sizeof(CcClusterPoint) == sizeof(cc_cluster_point_t), "cluster point layout");
     {
-        // what the prefetch already brought, then (rarely) the remainder with a second round trip
-        const int c0 = std::min(ncols, h->pre_cols), l0 = std::min(ncl, h->pre_clusters), p0 = std::min(ncp, h->pre_points);
+        // what the prefetch already brought, then (rarely) the remainder from the slot's device arrays
+        const int c0 = std::min(ncols, sl.pre_cols), l0 = std::min(ncl, sl.pre_clusters), p0 = std::min(ncp, sl.pre_points);
         if (c0)
-            std::memcpy(h->h_first_unpub.data(), h->hp_first_unpub, c0 * sizeof(long long));
+            std::memcpy(h->h_first_unpub.data(), sl.h_first_unpub, c0 * sizeof(long long));
         if (l0)
-            std::memcpy(h->h_clusters.data(), h->hp_clusters, l0 * sizeof(CcCluster));
+            std::memcpy(h->h_clusters.data(), sl.h_clusters, l0 * sizeof(CcCluster));
         if (p0)
-            std::memcpy(h->cluster_points.data(), h->hp_points, p0 * sizeof(CcClusterPoint));
+            std::memcpy(h->cluster_points.data(), sl.h_points, p0 * sizeof(CcClusterPoint));
         bool more = false;
         if (ncols > c0)
         {
-            CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data() + c0, h->d.col_first_unpub + c0,
-                                        (ncols - c0) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data() + c0, sl.d_first_unpub + c0,
+                                        (ncols - c0) * sizeof(long long), cudaMemcpyDeviceToHost, h->copy_stream));
             more = true;
         }
         if (ncl > l0)
         {
-            CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data() + l0, h->d.clusters + l0, (ncl - l0) * sizeof(CcCluster),
-                                        cudaMemcpyDeviceToHost, h->stream));
+            CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data() + l0, sl.d_clusters + l0, (ncl - l0) * sizeof(CcCluster),
+                                        cudaMemcpyDeviceToHost, h->copy_stream));
             more = true;
         }
         if (ncp > p0)
         {
-            CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data() + p0, h->d.cluster_points + p0,
-                                        (ncp - p0) * sizeof(CcClusterPoint), cudaMemcpyDeviceToHost, h->stream));
+            CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data() + p0, sl.d_points + p0,
+                                        (ncp - p0) * sizeof(CcClusterPoint), cudaMemcpyDeviceToHost, h->copy_stream));
             more = true;
         }
         if (more)
-            CC_CHECK(h, cudaStreamSynchronize(h->stream));
+            CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
     }
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
 
     // clusters in the order the reference would deliver them: by the column whose pass finished them
     std::stable_sort(h->h_clusters.begin(), h->h_clusters.end(),
@@ -897,9 +1010,12 @@ static cc_status_t run_push(cc_handle* h, int n)
     info.n_clusters = ncl;
     info.n_cluster_points = ncp;
     info.reset_required = st.reset_required;
-    info.gpu_launches = static_cast<int32_t>(h->launches - h->launches_at_push_start);
+    info.used_exact_path = h->used_exact_flag;
+    h->used_exact_flag = 0;
+    info.gpu_launches = static_cast<int32_t>(sl.launches1 - sl.launches0);
     info.device_ms = ms;
-    info.slow_insert_firings = st.scan_slow_firings + st.scan_fast_firings; // everything the lite path did not take // firings that needed the per-firing insertion path
+    info.slow_insert_firings = st.scan_slow_firings + st.scan_fast_firings; // everything the lite path did not take
+    pop();
     return CC_OK;
 }
 
@@ -917,20 +1033,106 @@ static cc_status_t check_push(cc_handle* h, int n, int rows)
         h->error = "The number of points in a firing has changed. This is probably a bug!"; // cpp:90-91
         return CC_ERR_ROW_COUNT_CHANGED;
     }
-    if (n < 0 || n > h->max_firings)
+    if (n <= 0 || n > h->max_firings)
     {
-        h->error = "too many firings in one push";
-        return CC_ERR_BATCH_TOO_LARGE;
+        h->error = n <= 0 ? "empty push" : "too many firings in one push";
+        return n <= 0 ? CC_ERR_INVALID_ARGUMENT : CC_ERR_BATCH_TOO_LARGE;
+    }
+    if (h->n_pending >= 2)
+    {
+        h->error = "two pushes are already in flight: call cc_wait() first";
+        return CC_ERR_INVALID_ARGUMENT;
     }
     return CC_OK;
 }
 
-cc_status_t cc_push_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_t* points, const double* poses)
+static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, const double* poses, bool device_inputs)
 {
     cc_status_t s = check_push(h, n, rows);
     if (s != CC_OK)
         return s;
-    if (n == 0)
+    if (!points || !poses)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    cc_handle::Slot& sl = h->slots[h->next_slot];
+    sl.n = n;
+    if (device_inputs)
+    {
+        sl.in_points = points;
+        sl.in_poses = poses;
+    }
+    else
+    {
+        const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
+        // page-locked caller buffers are copied straight to the device; anything else goes through the slot's own
+        // pinned staging buffer first. The copy runs on the copy stream, so it overlaps the kernels of the push
+        // before this one.
+        const void* src_pts = points;
+        const void* src_poses = poses;
+#ifndef CC_EMU
+        cudaPointerAttributes attr;
+        const bool pts_pinned = cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        const bool poses_pinned = cudaPointerGetAttributes(&attr, poses) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+#else
+        const bool pts_pinned = false, poses_pinned = false;
+#endif
+        if (!pts_pinned)
+        {
+            std::memcpy(sl.h_raw, points, pb);
+            src_pts = sl.h_raw;
+        }
+        if (!poses_pinned)
+        {
+            std::memcpy(sl.h_poses, poses, qb);
+            src_poses = sl.h_poses;
+        }
+        CC_CHECK(h, cudaMemcpyAsync(sl.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->copy_stream));
+        CC_CHECK(h, cudaMemcpyAsync(sl.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->copy_stream));
+        CC_CHECK(h, cudaEventRecord(sl.h2d, h->copy_stream));
+        CC_CHECK(h, cudaStreamWaitEvent(h->stream, sl.h2d, 0));
+        sl.in_points = sl.d_raw;
+        sl.in_poses = sl.d_poses;
+    }
+    s = launch_push(h, sl);
+    if (s != CC_OK)
+        return s;
+    h->pending[h->n_pending++] = h->next_slot;
+    h->next_slot ^= 1;
+    return CC_OK;
+}
+
+cc_status_t cc_submit_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_t* points, const double* poses)
+{
+    return submit(h, n, rows, points, poses, false);
+}
+
+cc_status_t cc_submit_firings_device(cc_handle_t* h, int n, int rows, const cc_raw_point_t* d_points, const double* d_poses)
+{
+    return submit(h, n, rows, d_points, d_poses, true);
+}
+
+cc_status_t cc_wait(cc_handle_t* h)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    return finish_push(h);
+}
+
+int cc_pending(const cc_handle_t* h)
+{
+    return h ? h->n_pending : 0;
+}
+
+static cc_status_t push_sync(cc_handle* h, int n, int rows, const void* points, const double* poses, bool device_inputs)
+{
+    if (h && h->n_pending > 0)
+    {
+        h->error = "asynchronous pushes are in flight: call cc_wait() first";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    if (h && h->is_reset && rows == h->R && n == 0)
     {
         h->events.clear();
         h->clusters.clear();
@@ -938,52 +1140,20 @@ cc_status_t cc_push_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_
         std::memset(&h->info, 0, sizeof(h->info));
         return CC_OK;
     }
-    if (!points || !poses)
-        return CC_ERR_INVALID_ARGUMENT;
-    CC_CHECK(h, cudaSetDevice(h->device));
-    const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
-    // page-locked caller buffers are copied straight to the device; anything else goes through the handle's own
-    // pinned staging buffer first (an asynchronous copy from pageable memory would serialise on the host anyway)
-    const void* src_pts = points;
-    const void* src_poses = poses;
-#ifndef CC_EMU
-    cudaPointerAttributes attr;
-    const bool pts_pinned = cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    const bool poses_pinned = cudaPointerGetAttributes(&attr, poses) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-#else
-    const bool pts_pinned = false, poses_pinned = false;
-#endif
-    if (!pts_pinned)
-    {
-        std::memcpy(h->h_raw, points, pb);
-        src_pts = h->h_raw;
-    }
-    if (!poses_pinned)
-    {
-        std::memcpy(h->h_poses, poses, qb);
-        src_poses = h->h_poses;
-    }
-    CC_CHECK(h, cudaMemcpyAsync(h->d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->stream));
-    CC_CHECK(h, cudaMemcpyAsync(h->d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->stream));
-    h->d.raw = h->d_raw;
-    h->d.poses = h->d_poses;
-    return run_push(h, n);
+    cc_status_t s = submit(h, n, rows, points, poses, device_inputs);
+    if (s != CC_OK)
+        return s;
+    return finish_push(h);
+}
+
+cc_status_t cc_push_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_t* points, const double* poses)
+{
+    return push_sync(h, n, rows, points, poses, false);
 }
 
 cc_status_t cc_push_firings_device(cc_handle_t* h, int n, int rows, const cc_raw_point_t* d_points, const double* d_poses)
 {
-    cc_status_t s = check_push(h, n, rows);
-    if (s != CC_OK)
-        return s;
-    if (n == 0)
-        return cc_push_firings(h, 0, rows, nullptr, nullptr);
-    if (!d_points || !d_poses)
-        return CC_ERR_INVALID_ARGUMENT;
-    CC_CHECK(h, cudaSetDevice(h->device));
-    h->d.raw = d_points;
-    h->d.poses = d_poses;
-    return run_push(h, n);
+    return push_sync(h, n, rows, d_points, d_poses, true);
 }
 
 cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out)
@@ -1051,6 +1221,8 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         return CC_ERR_INVALID_ARGUMENT;
     }
     CC_CHECK(h, cudaSetDevice(h->device));
+    // reads run on the copy stream: ordered after every finished push (their `done` events live there) and not behind
+    // the kernels of a push that is still in flight (which never touches columns already reported)
     const int R = h->R;
     const int64_t ncols = to - from + 1;
     const size_t cells = static_cast<size_t>(ncols) * R;
@@ -1061,10 +1233,10 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
     auto rd = [&](void* dst, const void* src, size_t elem) -> cudaError_t
     {
         cudaError_t e = cudaMemcpyAsync(dst, static_cast<const char*>(src) + static_cast<size_t>(l0) * R * elem,
-                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->stream);
+                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->copy_stream);
         if (e == cudaSuccess && n1 > 0)
             e = cudaMemcpyAsync(static_cast<char*>(dst) + static_cast<size_t>(n0) * R * elem, src,
-                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->stream);
+                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->copy_stream);
         return e;
     };
     std::vector<float4> pos;
@@ -1084,10 +1256,10 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
     {
         // per-column tags
         cudaError_t e = cudaMemcpyAsync(slot.data(), h->d.slot_gcol + l0, static_cast<size_t>(n0) * sizeof(long long),
-                                        cudaMemcpyDeviceToHost, h->stream);
+                                        cudaMemcpyDeviceToHost, h->copy_stream);
         if (e == cudaSuccess && n1 > 0)
             e = cudaMemcpyAsync(slot.data() + n0, h->d.slot_gcol, static_cast<size_t>(n1) * sizeof(long long),
-                                cudaMemcpyDeviceToHost, h->stream);
+                                cudaMemcpyDeviceToHost, h->copy_stream);
         CC_CHECK(h, e);
     }
     if (f->azimuth_angle)
@@ -1110,14 +1282,15 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         tpar.resize(cells);
         CC_CHECK(h, rd(tpar.data(), h->d.tparent, sizeof(unsigned int)));
     }
-    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
     std::vector<long long> root_slot_gcol;
     if (f->tree_root_gcol)
     {
         // global column of every tree root: one more small gather of the per-column tags
         root_slot_gcol.resize(static_cast<size_t>(h->ringcols));
-        CC_CHECK(h, cudaMemcpy(root_slot_gcol.data(), h->d.slot_gcol, root_slot_gcol.size() * sizeof(long long),
-                               cudaMemcpyDeviceToHost));
+        CC_CHECK(h, cudaMemcpyAsync(root_slot_gcol.data(), h->d.slot_gcol, root_slot_gcol.size() * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->copy_stream));
+        CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
     }
     for (size_t i = 0; i < cells; i++)
     {

@@ -153,6 +153,8 @@ CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/
 
 __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
     // (anchor = column-in-rotation of its first valid row; rearmost / foremost column relative to the anchor)
     const int R = cfg.R;
@@ -242,7 +244,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 // =====================================================================================================
 __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
 {
-    if (blockIdx.x != 0)
+    if (blockIdx.x != 0 || pg.st->halted)
         return;
     CC_SMEM(smem);
     __shared__ int l_has[32], l_first[32], l_last[32], l_off[32], l_base[32];
@@ -450,6 +452,8 @@ struct CcOpLastSetI32
 
 __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     int* sm = reinterpret_cast<int*>(smem);
     const int R = cfg.R, N = cfg.N;
@@ -492,6 +496,8 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 
 __global__ void k_scan_apply(CcDevCfg cfg, CcDevPtrs p, int n)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     int* sm = reinterpret_cast<int*>(smem);
     const int R = cfg.R, N = cfg.N, ringcols = cfg.ringcols;
@@ -559,7 +565,7 @@ struct CcScanState // uniform across the CTA, kept in registers by every thread
 
 __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
 {
-    if (blockIdx.x != 0)
+    if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
     const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
@@ -1192,6 +1198,8 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
 // =====================================================================================================
 __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
@@ -1264,6 +1272,8 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 // =====================================================================================================
 __global__ void k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     float* lastv = reinterpret_cast<float*>(smem);
     const int R = cfg.R;
@@ -1326,6 +1336,8 @@ struct CcGroundSmem
 
 __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     const int R = cfg.R;
     const int warps_per_block = blockDim.x / CC_WARP;
@@ -1567,6 +1579,8 @@ __device__ void d_snapshot(CcDevPtrs p, int spec);
 
 __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     double* part = reinterpret_cast<double*>(smem);
     if (blockIdx.x != 0)
@@ -1606,6 +1620,8 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 // =====================================================================================================
 __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     const int R = cfg.R;
     int* plist_n = reinterpret_cast<int*>(smem);          // [0] points in the list, [1] next point to take
@@ -1904,6 +1920,8 @@ __device__ void d_snapshot(CcDevPtrs p, int spec)
 
 __global__ void k_snapshot(CcDevPtrs p, int guard)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     d_snapshot(p, guard);
 }
 
@@ -1930,6 +1948,8 @@ __global__ void k_restore_finish(CcDevPtrs p)
 
 __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
         return;
     const int R = cfg.R;
@@ -1967,6 +1987,8 @@ __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_p
 
 __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
         return;
     const int R = cfg.R;
@@ -1995,6 +2017,8 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
 __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
                                int ci0, int ci1, int spec)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
         return;
     const int R = cfg.R;
@@ -2420,6 +2444,8 @@ __device__ void d_push_done(CcDevPtrs p, int guard);
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
                                                   int exact, int last)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (blockIdx.x != 0)
         return;
     d_fin_init(cfg, p, ci0, ci1, guard);
@@ -2442,6 +2468,8 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 // host needs for the finished-cluster callback (cpp:1007-1028).
 __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
         return;
     const CcDevState* st = p.st;
@@ -2491,6 +2519,8 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
     CcDevState* st = p.st;
     if (mode)
     {
+        if (st->halted)
+            return;
         from = st->clear_from;
         to = st->clear_to;
     }
@@ -2536,10 +2566,25 @@ __device__ void d_push_done(CcDevPtrs p, int guard)
 {
     CcDevState* st = p.st;
     if (guard == 1 && (st->error != 0 || st->n_flagged != 0 || st->abort != 0))
+    {
+        if (st->ncols > 0 || st->error != 0)
+            st->halted = 1; // pushes already queued behind this one must not run before the host has finished it
         return;
+    }
     if (st->ring_start > st->clear_from)
         st->clear_to = st->ring_start;
     st->cluster_counter += static_cast<unsigned long long>(st->n_clusters);
+}
+
+// mode 1: halt if this push completed columns (no robot transform: the reference throws); 0: halt if it has new
+// columns (finish passes only every n-th column: always column-sequential); -1: clear the flag
+__global__ void k_halt(CcDevPtrs p, int mode)
+{
+    CcDevState* st = p.st;
+    if (mode < 0)
+        st->halted = 0;
+    else if (!st->halted && (st->ncols > 0 || st->error != 0))
+        st->halted = 1;
 }
 
 // ---- device math self-test (bit equality with the host libm) ----

@@ -101,7 +101,8 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     int scan_fast_firings, scan_slow_firings, scan_fast_attempts; // insertion scan statistics of this push
     int scan_kbad;            // firings [0, scan_kbad) were resolved by the lite insertion path
     long long scan_lite_base; // column the lite arrays are relative to
-    int scan_lite_firings, pad_;
+    int scan_lite_firings;
+    int halted; // set when a push could not be committed speculatively: later pushes in flight skip themselves
 };
 
 struct CcFiringRecord // insertion scan -> K1b: how the points of one firing were resolved

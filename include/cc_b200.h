@@ -223,6 +223,19 @@ CC_API cc_status_t cc_push_firings(cc_handle_t* h, int n_firings, int rows_per_f
 CC_API cc_status_t cc_push_firings_device(cc_handle_t* h, int n_firings, int rows_per_firing,
                                           const cc_raw_point_t* d_points, const double* d_poses);
 
+/* Asynchronous variant: cc_submit_* enqueues the host->device copy (on a separate copy stream) and every kernel of
+ * the push and returns at once; cc_wait() blocks until the OLDEST submitted push is finished and makes its results
+ * current (cc_get_batch_info & co). At most two pushes may be in flight, so a caller keeps the GPU busy with
+ * `submit(k+1); wait(k)`. Inputs must stay valid until the push has been waited for. cc_push_firings* ==
+ * submit + wait. If a push in flight cannot be committed speculatively the pushes behind it
+ * skip themselves on the device and cc_wait() transparently re-runs them after finishing it. */
+CC_API cc_status_t cc_submit_firings(cc_handle_t* h, int n_firings, int rows_per_firing,
+                                     const cc_raw_point_t* points, const double* poses);
+CC_API cc_status_t cc_submit_firings_device(cc_handle_t* h, int n_firings, int rows_per_firing,
+                                            const cc_raw_point_t* d_points, const double* d_poses);
+CC_API cc_status_t cc_wait(cc_handle_t* h);
+CC_API int cc_pending(const cc_handle_t* h); /* pushes in flight (0..2) */
+
 /* Results of the last push. */
 CC_API cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out);
 /* Copies min(cap, n) entries; returns the number copied through *n_out. */

@@ -292,6 +292,10 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
     e->t = std::chrono::steady_clock::now();
     return cudaSuccess;
 }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned)
+{
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t)
 {
     return cudaSuccess;

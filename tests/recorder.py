@@ -24,15 +24,25 @@ def _to_cells(cols):
     return out
 
 
-def record(cc, pts, poses, chunk):
-    """Feeds the stream in pushes of `chunk` firings; returns the dict layout of tests/parity.record()."""
+def record(cc, pts, poses, chunk, pipelined=False):
+    """Feeds the stream in pushes of `chunk` firings; returns the dict layout of tests/parity.record().
+    pipelined=True uses the asynchronous API with two pushes in flight (submit(k + 1); wait(k))."""
     rows = pts.shape[1]
     events, gcols, gcells, ccols, ccells, clusters, cpoints = [], [], [], [], [], [], []
     n_events = 0
     used_exact = 0
     slow_firings = 0
-    for a in range(0, pts.shape[0], chunk):
-        res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
+    starts = list(range(0, pts.shape[0], chunk))
+    if pipelined and starts:
+        cc.submitFirings(pts[0:chunk], poses[0:chunk])
+    for i, a in enumerate(starts):
+        if pipelined:
+            if i + 1 < len(starts):
+                b = starts[i + 1]
+                cc.submitFirings(pts[b : b + chunk], poses[b : b + chunk])
+            res = cc.wait()
+        else:
+            res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
         used_exact += int(res.info.used_exact_path)
         slow_firings += int(res.info.slow_insert_firings)
         ev = res.events.copy()  # results are views of the handle's buffers, valid until the next push

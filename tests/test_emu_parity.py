@@ -81,6 +81,30 @@ def test_emulated_kernels_match_golden(emu_library, name):
     parity.compare(want, got, name_a="reference(golden)", name_b="emulated kernels")
 
 
+ASYNC_CASES = [
+    ("tiny16", dict(n_rotations=3.0, moving=True, dropout=0.05), {}, 64, 0),
+    ("tiny16", dict(n_rotations=3.0), {}, 50, 11),                                # flagged columns: halt + replay
+    ("tiny16", dict(n_rotations=3.0, n_boxes=0, wall_radius=8.0), {}, 100, 0),   # forced finish: abort + rollback + replay
+    ("tiny16", dict(n_rotations=2.0), dict(cluster_point_trees_every_nth_column=3), 64, 0),
+    ("tiny16", dict(n_rotations=3.0, az_jitter=0.7), {}, 40, 0),
+    ("velodyne64", dict(n_rotations=1.3, moving=True), {}, 512, 0),
+]
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", ASYNC_CASES)
+def test_pipelined_pushes_match_oracle(emu_library, oracle_lib, spec, kw, cfg_over, chunk, flag_period):
+    """Two pushes in flight (cc_submit_firings / cc_wait): same results, including when a push in flight has to
+    fall back to the column-sequential path and the one queued behind it is re-run."""
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(emu_library, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk, pipelined=True)
+    parity.compare(want, got, name_a="oracle", name_b="emulated kernels, pipelined")
+    assert cc.pending == 0
+
+
 def test_results_do_not_depend_on_push_size(emu_library):
     pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0, moving=True, dropout=0.05)
     cfg = drvlib.stream_config("tiny16")

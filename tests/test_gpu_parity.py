@@ -11,7 +11,7 @@ import recorder
 from continuous_clustering_b200 import ContinuousClustering, synth
 from golden import make_golden
 from oracle import drvlib
-from test_emu_parity import CASES, IDENTITY, make_cc, oracle_record
+from test_emu_parity import ASYNC_CASES, CASES, IDENTITY, make_cc, oracle_record
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,20 @@ def test_cuda_matches_oracle_small(cuda_library, oracle_lib, spec, kw, cfg_over,
     got = recorder.record(cc, pts, poses, chunk)
     parity.compare(want, got, name_a="oracle", name_b="cuda")
     assert np.array_equal(want["cluster_cells"]["tree_root_gcol"], got["cluster_cells"]["tree_root_gcol"])
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", ASYNC_CASES + [
+    ("velodyne64", dict(n_rotations=4.2, moving=True, dropout=0.02), {}, 2048, 0),
+    ("velodyne64", dict(n_rotations=2.2), {}, 1024, 97),
+])
+def test_cuda_pipelined_pushes_match_oracle(cuda_library, oracle_lib, spec, kw, cfg_over, chunk, flag_period):
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(None, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk, pipelined=True)
+    parity.compare(want, got, name_a="oracle", name_b="cuda, pipelined")
 
 
 @pytest.mark.parametrize("name", sorted(make_golden.FIXTURES))
