@@ -222,8 +222,9 @@ class ContinuousClustering:
         poses = np.ascontiguousarray(poses, dtype=np.float64)
         n, rows = points.shape
         out = None
-        for a in range(0, max(n, 1), self.max_firings_per_push):
-            b = min(n, a + self.max_firings_per_push)
+        step = max(1, int(self._L.cc_max_firings_per_push(self._h)))
+        for a in range(0, max(n, 1), step):  # larger batches are pushed piecewise; the LAST piece's result is returned
+            b = min(n, a + step)
             self._check(self._L.cc_push_firings(self._h, b - a, rows, points[a:b].ctypes.data, poses[a:b].ctypes.data))
             out = self._collect()
             self._dispatch(out)

@@ -596,6 +596,8 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     s.colbase = -1;
     s.clear_from = -1;
     s.clear_to = -1;
+    s.clear2_from = -1;
+    s.clear2_to = -1;
     s.danger_col = CC_COL_INF;
     *h->h_state = s;
     CC_CHECK(h, cudaMemcpyAsync(h->d.st, h->h_state, sizeof(s), cudaMemcpyHostToDevice, h->stream));
@@ -1019,6 +1021,13 @@ static cc_status_t finish_push(cc_handle* h)
     return CC_OK;
 }
 
+int cc_max_firings_per_push(const cc_handle_t* h)
+{
+    if (!h)
+        return 0;
+    return h->N > 0 ? std::min(h->max_firings, 3 * h->N) : h->max_firings;
+}
+
 static cc_status_t check_push(cc_handle* h, int n, int rows)
 {
     if (!h)
@@ -1033,9 +1042,10 @@ static cc_status_t check_push(cc_handle* h, int n, int rows)
         h->error = "The number of points in a firing has changed. This is probably a bug!"; // cpp:90-91
         return CC_ERR_ROW_COUNT_CHANGED;
     }
-    if (n <= 0 || n > h->max_firings)
+    if (n <= 0 || n > cc_max_firings_per_push(h))
     {
-        h->error = n <= 0 ? "empty push" : "too many firings in one push";
+        // the ring keeps 10 rotations and recycles columns two pushes late: a push may span at most 3 rotations
+        h->error = n <= 0 ? "empty push" : "too many firings in one push (limit: min(max_firings_per_push, 3 * num_columns))";
         return n <= 0 ? CC_ERR_INVALID_ARGUMENT : CC_ERR_BATCH_TOO_LARGE;
     }
     if (h->n_pending >= 2)

@@ -1180,6 +1180,8 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         st->ncols = s.f_init ? s.Frel - s.colbase_rel : 0;
         if (s.error)
             st->error = s.error;
+        st->clear2_from = st->clear_from; // retired by the previous push: recycled at the start of the next one
+        st->clear2_to = st->clear_to;
         st->clear_from = s.ring_start;
         st->clear_to = s.ring_start;
         st->push_first_unpub_old = s.first_unpub;
@@ -2511,9 +2513,10 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 // =====================================================================================================
 // K5  clearColumns (cpp:1094-1145) for the columns that left the ring in this push.
 // =====================================================================================================
-// mode 0: explicit range [from, to) (reset); mode 1: the range the PREVIOUS push retired. Recycling is deferred by
-// one push so that every column a push reports through a finished-column event can still be read by the caller
-// after the push returns (the reference's callbacks read range_image_ before clearColumns runs, cpp:1087-1091).
+// mode 0: explicit range [from, to) (reset); mode 1: the range retired TWO pushes ago. Recycling is deferred so that
+// every column a push reports through a finished-column event can still be read by the caller after the push has
+// been waited for, even while the next push is already in flight (the reference's callbacks read range_image_
+// before clearColumns runs, cpp:1087-1091).
 __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
 {
     CcDevState* st = p.st;
@@ -2521,8 +2524,8 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
     {
         if (st->halted)
             return;
-        from = st->clear_from;
-        to = st->clear_to;
+        from = st->clear2_from;
+        to = st->clear2_to;
     }
     if (from < 0)
         from = 0;

@@ -91,7 +91,8 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long danger_col; // first column at which a cluster could be force-finished (cpp:909-919), CC_COL_INF if none
     int abort;            // speculative commit must be rolled back
     int n_clusters, n_cluster_points;
-    long long clear_from, clear_to; // columns recycled in this push [from, to)
+    long long clear_from, clear_to;   // columns retired by this push [from, to)
+    long long clear2_from, clear2_to; // columns retired by the push before (recycled at the start of the next push)
     long long seg_c0, seg_c1;       // column range of the running commit segment (inclusive)
     long long seg_first_unpub_old;
     long long gbase; // column of entry 0 of the per-root-column arrays

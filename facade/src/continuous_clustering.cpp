@@ -185,13 +185,24 @@ void ContinuousClustering::flush()
         return;
     const int n = pending_;
     pending_ = 0;
-    int s = cc_push_firings(handle_, n, num_rows_, reinterpret_cast<const cc_raw_point_t*>(pending_points_.data()),
-                            pending_poses_.data());
+    const int step = std::max(1, cc_max_firings_per_push(handle_));
+    const size_t rec = static_cast<size_t>(num_rows_) * sizeof(cc_raw_point_t);
+    for (int a = 0; a < n; a += step)
+    {
+        const int m = std::min(step, n - a);
+        int s = cc_push_firings(handle_, m, num_rows_,
+                                reinterpret_cast<const cc_raw_point_t*>(pending_points_.data() + static_cast<size_t>(a) * rec),
+                                pending_poses_.data() + static_cast<size_t>(a) * 12);
+        if (s != CC_OK)
+        {
+            pending_points_.clear();
+            pending_poses_.clear();
+            fail(s);
+        }
+        deliver();
+    }
     pending_points_.clear();
     pending_poses_.clear();
-    if (s != CC_OK)
-        fail(s);
-    deliver();
 }
 
 // host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63)

@@ -235,6 +235,8 @@ CC_API cc_status_t cc_submit_firings_device(cc_handle_t* h, int n_firings, int r
                                             const cc_raw_point_t* d_points, const double* d_poses);
 CC_API cc_status_t cc_wait(cc_handle_t* h);
 CC_API int cc_pending(const cc_handle_t* h); /* pushes in flight (0..2) */
+/* Largest n_firings one push accepts: min(max_firings_per_push, 3 * num_columns). */
+CC_API int cc_max_firings_per_push(const cc_handle_t* h);
 
 /* Results of the last push. */
 CC_API cc_status_t cc_get_batch_info(const cc_handle_t* h, cc_batch_info_t* out);

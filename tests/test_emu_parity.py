@@ -32,7 +32,7 @@ def make_cc(library, cfg, rows, max_push=4096, tf=True):
 CASES = [
     ("tiny16", dict(n_rotations=2.0), {}, 64, 0),
     ("tiny16", dict(n_rotations=1.5, moving=True, dropout=0.1), {}, 1, 0),  # one firing per push, like addFiring
-    ("tiny16", dict(n_rotations=3.0), {}, 1000, 0),                          # more than a rotation per push
+    ("tiny16", dict(n_rotations=3.0), {}, 700, 0),                           # more than two rotations per push
     ("tiny16", dict(n_rotations=2.0), {}, 37, 5),                            # every 5th column through the exact path
     ("tiny16", dict(n_rotations=2.0, moving=True), {}, 300, 1),              # every column through the exact path
     ("tiny16", dict(n_rotations=3.0, n_boxes=0, wall_radius=8.0), {}, 128, 0),  # forced finish (cpp:909-919)
