@@ -11,7 +11,7 @@
 
 #include "cc_kernels.cuh"
 
-static const int CC_PREFETCH_CLUSTERS = 512, CC_PREFETCH_POINTS = 8192;
+static const int CC_PREFETCH_CLUSTERS = 512, CC_PREFETCH_POINTS = 16384;
 
 namespace
 {
@@ -77,6 +77,9 @@ struct cc_handle
     int pending[2]{-1, -1}; // slots of the pushes in flight, oldest first
     int n_pending{0};
     cudaStream_t copy_stream{nullptr};
+    // host-initiated reads of finished results (remainders beyond the prefetch, cc_read_columns): never queued behind
+    // the copy stream's wait for a push that is still in flight
+    cudaStream_t aux_stream{nullptr};
     std::vector<void*> allocs;       // freed on destroy / re-reset
     std::vector<void*> allocs_fixed; // independent of the ring size
     CcDevState* h_state{nullptr}; // pinned mirror (reset, column-sequential path)
@@ -280,6 +283,7 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(CcDevState)) != cudaSuccess)
     {
@@ -321,6 +325,8 @@ void cc_destroy(cc_handle_t* h)
                 cudaEventDestroy(e);
     if (h->copy_stream)
         cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream)
+        cudaStreamDestroy(h->aux_stream);
     if (h->h_state)
         cudaFreeHost(h->h_state);
     if (h->ev0)
@@ -623,6 +629,22 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     return CC_OK;
 }
 
+// cudaEventSynchronize wakes up late (hundreds of microseconds) while other work keeps the device busy; a push is
+// only a few hundred microseconds long, so poll instead
+static cudaError_t spin_wait(cudaEvent_t e)
+{
+#ifdef CC_EMU
+    (void)e;
+    return cudaSuccess;
+#else
+    cudaError_t r;
+    while ((r = cudaEventQuery(e)) == cudaErrorNotReady)
+    {
+    }
+    return r;
+#endif
+}
+
 static cc_status_t fetch_state(cc_handle* h)
 {
     CC_CHECK(h, cudaMemcpyAsync(h->h_state, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->stream));
@@ -730,7 +752,7 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
 // that the next push's kernels do not wait for the transfer (the device-side result arrays are per slot)
 static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl)
 {
-    CC_CHECK(h, cudaMemcpyAsync(sl.d_state_snap, h->d.st, sizeof(CcDevState), cudaMemcpyDeviceToDevice, h->stream));
+    CC_LAUNCH(k_state_snapshot, 1, CC_WARP, 0, h->stream, h->d, sl.d_state_snap);
     CC_CHECK(h, cudaEventRecord(sl.ready, h->stream));
     CC_CHECK(h, cudaStreamWaitEvent(h->copy_stream, sl.ready, 0));
     sl.pre_cols = std::min(h->maxcols, sl.n + 64);
@@ -856,7 +878,7 @@ static cc_status_t finish_push(cc_handle* h)
         h->pending[0] = h->pending[1];
         h->n_pending--;
     };
-    CC_CHECK(h, cudaEventSynchronize(sl.done));
+    CC_CHECK(h, spin_wait(sl.done));
     h->state = *sl.h_state;
     CcDevCfg cfg;
     fill_devcfg(h, cfg);
@@ -904,7 +926,7 @@ static cc_status_t finish_push(cc_handle* h)
             if (s != CC_OK)
                 return s;
         }
-        CC_CHECK(h, cudaEventSynchronize(sl.done));
+        CC_CHECK(h, spin_wait(sl.done));
         h->state = *sl.h_state;
         es = device_error_to_status(h);
         if (es != CC_OK)
@@ -936,23 +958,23 @@ static cc_status_t finish_push(cc_handle* h)
         if (ncols > c0)
         {
             CC_CHECK(h, cudaMemcpyAsync(h->h_first_unpub.data() + c0, sl.d_first_unpub + c0,
-                                        (ncols - c0) * sizeof(long long), cudaMemcpyDeviceToHost, h->copy_stream));
+                                        (ncols - c0) * sizeof(long long), cudaMemcpyDeviceToHost, h->aux_stream));
             more = true;
         }
         if (ncl > l0)
         {
             CC_CHECK(h, cudaMemcpyAsync(h->h_clusters.data() + l0, sl.d_clusters + l0, (ncl - l0) * sizeof(CcCluster),
-                                        cudaMemcpyDeviceToHost, h->copy_stream));
+                                        cudaMemcpyDeviceToHost, h->aux_stream));
             more = true;
         }
         if (ncp > p0)
         {
             CC_CHECK(h, cudaMemcpyAsync(h->cluster_points.data() + p0, sl.d_points + p0,
-                                        (ncp - p0) * sizeof(CcClusterPoint), cudaMemcpyDeviceToHost, h->copy_stream));
+                                        (ncp - p0) * sizeof(CcClusterPoint), cudaMemcpyDeviceToHost, h->aux_stream));
             more = true;
         }
         if (more)
-            CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+            CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
@@ -1231,7 +1253,7 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         return CC_ERR_INVALID_ARGUMENT;
     }
     CC_CHECK(h, cudaSetDevice(h->device));
-    // reads run on the copy stream: ordered after every finished push (their `done` events live there) and not behind
+    // reads run on their own stream: the host has already seen every finished push complete, and they must not queue behind
     // the kernels of a push that is still in flight (which never touches columns already reported)
     const int R = h->R;
     const int64_t ncols = to - from + 1;
@@ -1243,10 +1265,10 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
     auto rd = [&](void* dst, const void* src, size_t elem) -> cudaError_t
     {
         cudaError_t e = cudaMemcpyAsync(dst, static_cast<const char*>(src) + static_cast<size_t>(l0) * R * elem,
-                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->copy_stream);
+                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->aux_stream);
         if (e == cudaSuccess && n1 > 0)
             e = cudaMemcpyAsync(static_cast<char*>(dst) + static_cast<size_t>(n0) * R * elem, src,
-                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->copy_stream);
+                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->aux_stream);
         return e;
     };
     std::vector<float4> pos;
@@ -1266,10 +1288,10 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
     {
         // per-column tags
         cudaError_t e = cudaMemcpyAsync(slot.data(), h->d.slot_gcol + l0, static_cast<size_t>(n0) * sizeof(long long),
-                                        cudaMemcpyDeviceToHost, h->copy_stream);
+                                        cudaMemcpyDeviceToHost, h->aux_stream);
         if (e == cudaSuccess && n1 > 0)
             e = cudaMemcpyAsync(slot.data() + n0, h->d.slot_gcol, static_cast<size_t>(n1) * sizeof(long long),
-                                cudaMemcpyDeviceToHost, h->copy_stream);
+                                cudaMemcpyDeviceToHost, h->aux_stream);
         CC_CHECK(h, e);
     }
     if (f->azimuth_angle)
@@ -1292,15 +1314,15 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         tpar.resize(cells);
         CC_CHECK(h, rd(tpar.data(), h->d.tparent, sizeof(unsigned int)));
     }
-    CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
     std::vector<long long> root_slot_gcol;
     if (f->tree_root_gcol)
     {
         // global column of every tree root: one more small gather of the per-column tags
         root_slot_gcol.resize(static_cast<size_t>(h->ringcols));
         CC_CHECK(h, cudaMemcpyAsync(root_slot_gcol.data(), h->d.slot_gcol, root_slot_gcol.size() * sizeof(long long),
-                                    cudaMemcpyDeviceToHost, h->copy_stream));
-        CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+                                    cudaMemcpyDeviceToHost, h->aux_stream));
+        CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
     }
     for (size_t i = 0; i < cells; i++)
     {
@@ -1331,6 +1353,15 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
             f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
     }
     return CC_OK;
+}
+
+int cc_debug_event_query(cc_handle_t* h, int slot, int which)
+{
+    if (!h || slot < 0 || slot > 1)
+        return -1;
+    cc_handle::Slot& sl = h->slots[slot];
+    cudaEvent_t e = which == 0 ? sl.ev0 : which == 1 ? sl.ev1 : which == 2 ? sl.ready : sl.done;
+    return cudaEventQuery(e) == cudaSuccess ? 1 : 0;
 }
 
 cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period)

@@ -2590,6 +2590,16 @@ __global__ void k_halt(CcDevPtrs p, int mode)
         st->halted = 1;
 }
 
+// copy of the stream state at the end of a push (what the host reads while the next push already runs)
+__global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
+{
+    const int n = static_cast<int>(sizeof(CcDevState) / sizeof(int));
+    const int* src = reinterpret_cast<const int*>(p.st);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        d[i] = src[i];
+}
+
 // ---- device math self-test (bit equality with the host libm) ----
 __global__ void k_selftest_math(int op, int n, const float* a, const float* b, float* out)
 {

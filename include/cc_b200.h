@@ -276,6 +276,10 @@ CC_API cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_
  * through the column-sequential exact kernels. Results must not change. 0 = off. */
 CC_API cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period);
 
+/* Debug hook: 1 if the event `which` (0 start, 1 end of kernels, 2 state snapshot ready, 3 results on the host) of
+ * in-flight slot 0/1 has completed. */
+CC_API int cc_debug_event_query(cc_handle_t* h, int slot, int which);
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */

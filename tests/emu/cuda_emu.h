@@ -296,6 +296,10 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
 {
     return cudaSuccess;
 }
+static inline cudaError_t cudaEventQuery(cudaEvent_t)
+{
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t)
 {
     return cudaSuccess;
