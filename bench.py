@@ -374,6 +374,7 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end leg through the public API
     cc = new_handle()
+    cc.set_label_prefetch(True)  # the ground labels of the new columns come back with every push's results
     h_pts, h_poses = tile_stream(base_pts, base_poses, sp, 0, total)
     # page-locked host buffers (the contract's "pinned host memory"): cc_push_firings copies them straight to the device
     pin_pts = torch.from_numpy(h_pts.view(np.uint8).reshape(total, R * 48)).pin_memory()
@@ -391,10 +392,9 @@ def main():
         if s + 1 < W + K:
             cc.submitFirings(h_pts[(s + 1) * B:(s + 2) * B], h_poses[(s + 1) * B:(s + 2) * B])
         res = cc.wait()
-        lo, hi = int(res.info.ground_from_gcol), int(res.info.ground_to_gcol) - 1
-        labels = cc.read_columns(lo, hi, fields=["ground_point_label"])
-        d2h += (res.events.nbytes // 2 + res.clusters.nbytes + res.cluster_points.nbytes + labels.size * 4
-                + (hi - lo + 1) * 8 + 256)
+        labels = cc.column_labels()  # [n_cols, rows, 4] u8: ground label, debug label, is_ignored, intensity
+        assert labels.shape[0] == int(res.info.ground_to_gcol - res.info.ground_from_gcol)
+        d2h += res.clusters.nbytes + res.cluster_points.nbytes + labels.nbytes + labels.shape[0] * 8 + 512
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:

@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "cc_read_columns", "cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns", "cc_stream",
     "cc_total_launches", "cc_selftest_math", "cc_set_kernel_timing", "cc_get_kernel_timings",
     "cc_debug_flag_columns", "cc_get_result_views", "cc_submit_firings", "cc_submit_firings_device", "cc_wait", "cc_pending",
-    "cc_max_firings_per_push", "cc_debug_event_query",
+    "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
 ]
 
 
@@ -144,6 +144,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_pending.argtypes = [vp]
     lib.cc_max_firings_per_push.argtypes = [vp]
     lib.cc_debug_event_query.argtypes = [vp, i32, i32]
+    lib.cc_set_label_prefetch.argtypes = [vp, i32]
+    lib.cc_get_column_labels.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
     lib.cc_get_batch_info.argtypes = [vp, C.POINTER(CcBatchInfo)]
     for name in ("cc_get_column_events", "cc_get_clusters", "cc_get_cluster_points"):
         getattr(lib, name).argtypes = [vp, vp, i32, C.POINTER(i32)]

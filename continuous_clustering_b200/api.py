@@ -323,6 +323,21 @@ class ContinuousClustering:
             out[n] = bufs[n]
         return out
 
+    def set_label_prefetch(self, enable: bool):
+        """Bring the labels of every push's new columns back with its results (cc_set_label_prefetch)."""
+        self._check(self._L.cc_set_label_prefetch(self._h, int(enable)))
+
+    def column_labels(self) -> np.ndarray:
+        """uint8 [n_cols, num_rows, 4] view: ground_point_label, debug label, is_ignored, intensity of the columns
+        [ground_from_gcol, ground_to_gcol) of the last finished push (needs set_label_prefetch(True))."""
+        ptr, n = C.c_void_p(), C.c_int(0)
+        self._check(self._L.cc_get_column_labels(self._h, C.byref(ptr), C.byref(n)))
+        rows = self.num_rows_
+        if n.value == 0 or not ptr.value:
+            return np.zeros((0, rows, 4), dtype=np.uint8)
+        buf = (C.c_ubyte * (n.value * rows * 4)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(n.value, rows, 4)
+
     def debug_flag_columns(self, period: int):
         """Test hook (cc_debug_flag_columns): force every n-th column through the exact column-sequential path."""
         self._check(self._L.cc_debug_flag_columns(self._h, int(period)))

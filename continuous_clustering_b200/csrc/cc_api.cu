@@ -41,6 +41,9 @@ struct cc_handle
     int maxcols{0};
     int gap_rows{-1};
     int debug_flag_period{0};
+    bool label_prefetch{false};
+    const uchar4* cur_labels{nullptr}; // labels of the last finished push (pinned slot buffer)
+    int cur_label_cols{0};
     int used_exact_flag{0};
     size_t probe_smem_set{0};
     size_t lite_smem_set{0};
@@ -55,6 +58,7 @@ struct cc_handle
         long long* d_first_unpub{nullptr};
         CcCluster* d_clusters{nullptr};
         CcClusterPoint* d_points{nullptr};
+        uchar4* d_labels{nullptr};
         unsigned char* d_raw{nullptr};
         double* d_poses{nullptr};
         // page-locked host
@@ -62,6 +66,7 @@ struct cc_handle
         long long* h_first_unpub{nullptr};
         CcCluster* h_clusters{nullptr};
         CcClusterPoint* h_points{nullptr};
+        uchar4* h_labels{nullptr};
         void* h_raw{nullptr};
         double* h_poses{nullptr};
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr}, h2d{nullptr};
@@ -148,13 +153,14 @@ static void free_host_slots(cc_handle* h)
     for (cc_handle::Slot& sl : h->slots)
     {
         for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters),
-                        static_cast<void*>(sl.h_points), sl.h_raw, static_cast<void*>(sl.h_poses)})
+                        static_cast<void*>(sl.h_points), static_cast<void*>(sl.h_labels), sl.h_raw, static_cast<void*>(sl.h_poses)})
             if (q)
                 cudaFreeHost(q);
         sl.h_state = nullptr;
         sl.h_first_unpub = nullptr;
         sl.h_clusters = nullptr;
         sl.h_points = nullptr;
+        sl.h_labels = nullptr;
         sl.h_raw = nullptr;
         sl.h_poses = nullptr;
     }
@@ -549,12 +555,14 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, dev_alloc(h, L, &sl.d_first_unpub, mc));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_clusters, static_cast<size_t>(d.cap_clusters)));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_points, static_cast<size_t>(d.cap_cluster_points)));
+            CC_CHECK(h, dev_alloc(h, L, &sl.d_labels, mc * h->R));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_raw, stage * sizeof(cc_raw_point_t)));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_poses, static_cast<size_t>(h->max_firings) * 12));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_state), sizeof(CcDevState)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_first_unpub), mc * sizeof(long long)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_labels), mc * h->R * sizeof(uchar4)));
             CC_CHECK(h, cudaMallocHost(&sl.h_raw, stage * sizeof(cc_raw_point_t)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
         }
@@ -753,6 +761,12 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
 static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl)
 {
     CC_LAUNCH(k_state_snapshot, 1, CC_WARP, 0, h->stream, h->d, sl.d_state_snap);
+    if (h->label_prefetch && sl.has_tf)
+    {
+        CcDevCfg cfg;
+        fill_devcfg(h, cfg);
+        CC_RUN(h, k_pack_labels, h->sm_count * 4, 256, 0, cfg, h->d, sl.d_labels, h->maxcols);
+    }
     CC_CHECK(h, cudaEventRecord(sl.ready, h->stream));
     CC_CHECK(h, cudaStreamWaitEvent(h->copy_stream, sl.ready, 0));
     sl.pre_cols = std::min(h->maxcols, sl.n + 64);
@@ -765,6 +779,9 @@ static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl)
                                 cudaMemcpyDeviceToHost, h->copy_stream));
     CC_CHECK(h, cudaMemcpyAsync(sl.h_points, sl.d_points, sl.pre_points * sizeof(CcClusterPoint),
                                 cudaMemcpyDeviceToHost, h->copy_stream));
+    if (h->label_prefetch && sl.has_tf)
+        CC_CHECK(h, cudaMemcpyAsync(sl.h_labels, sl.d_labels, static_cast<size_t>(sl.pre_cols) * h->R * sizeof(uchar4),
+                                    cudaMemcpyDeviceToHost, h->copy_stream));
     CC_CHECK(h, cudaEventRecord(sl.done, h->copy_stream));
     return CC_OK;
 }
@@ -975,6 +992,19 @@ static cc_status_t finish_push(cc_handle* h)
         }
         if (more)
             CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
+    }
+    h->cur_labels = nullptr;
+    h->cur_label_cols = 0;
+    if (h->label_prefetch && sl.has_tf)
+    {
+        if (ncols > sl.pre_cols) // more columns than the prefetch covered: fetch the packed labels again, all of them
+        {
+            CC_CHECK(h, cudaMemcpyAsync(sl.h_labels, sl.d_labels, static_cast<size_t>(std::min(ncols, h->maxcols)) * h->R * sizeof(uchar4),
+                                        cudaMemcpyDeviceToHost, h->aux_stream));
+            CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
+        }
+        h->cur_labels = sl.h_labels;
+        h->cur_label_cols = std::min(ncols, h->maxcols);
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
@@ -1352,6 +1382,23 @@ cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_c
         if (f->tree_root_row)
             f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
     }
+    return CC_OK;
+}
+
+cc_status_t cc_set_label_prefetch(cc_handle_t* h, int enable)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    h->label_prefetch = enable != 0;
+    return CC_OK;
+}
+
+cc_status_t cc_get_column_labels(const cc_handle_t* h, const uint8_t** labels, int* n_cols)
+{
+    if (!h || !labels || !n_cols)
+        return CC_ERR_INVALID_ARGUMENT;
+    *labels = reinterpret_cast<const uint8_t*>(h->cur_labels);
+    *n_cols = h->cur_labels ? h->cur_label_cols : 0;
     return CC_OK;
 }
 

@@ -2590,6 +2590,26 @@ __global__ void k_halt(CcDevPtrs p, int mode)
         st->halted = 1;
 }
 
+// labels (ground label, debug label, is_ignored, intensity) of the push's new columns, packed contiguously for one
+// device->host copy next to the other results of the push (cc_set_label_prefetch)
+__global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
+{
+    const CcDevState* st = p.st;
+    if (st->halted)
+        return;
+    int ncols = st->ncols;
+    ncols = ncols < cap_cols ? ncols : cap_cols;
+    const long long colbase = st->colbase;
+    const int R = cfg.R;
+    const long long total = static_cast<long long>(ncols) * R;
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long ci = i / R;
+        const int row = static_cast<int>(i - ci * R);
+        out[i] = p.lab[static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row];
+    }
+}
+
 // copy of the stream state at the end of a push (what the host reads while the next push already runs)
 __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
 {

@@ -250,6 +250,13 @@ CC_API cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_
 CC_API cc_status_t cc_get_result_views(const cc_handle_t* h, const cc_column_event_t** events,
                                        const cc_cluster_t** clusters, const cc_cluster_point_t** points);
 
+/* Optional: bring the per-cell labels of every push's new columns (columns [ground_from_gcol, ground_to_gcol) of
+ * cc_batch_info_t) back together with the other results -- 4 bytes per cell in cell order: ground_point_label,
+ * debug_ground_point_label, is_ignored, intensity. cc_get_column_labels returns a pointer into the handle's
+ * page-locked buffer, valid until the next cc_wait / push. Saves a cc_read_columns round trip per push. */
+CC_API cc_status_t cc_set_label_prefetch(cc_handle_t* h, int enable);
+CC_API cc_status_t cc_get_column_labels(const cc_handle_t* h, const uint8_t** labels, int* n_cols);
+
 /* Reads cells of columns [from_gcol, to_gcol] (inclusive, like the callback ranges) from the device
  * ring -- what a caller reads from `range_image_` inside a column callback (ros_utils.cpp:56-63,
  * kitti_demo.cpp:183-216). Only valid for columns still inside the ring. */

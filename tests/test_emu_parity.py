@@ -105,6 +105,24 @@ def test_pipelined_pushes_match_oracle(emu_library, oracle_lib, spec, kw, cfg_ov
     assert cc.pending == 0
 
 
+def check_label_prefetch(library):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0, moving=True)
+    cc = make_cc(library, drvlib.stream_config("tiny16"), sp.rows)
+    cc.set_label_prefetch(True)
+    for a in range(0, pts.shape[0], 128):
+        r = cc.addFirings(pts[a:a + 128], poses[a:a + 128])
+        lab = cc.column_labels()
+        lo, hi = int(r.info.ground_from_gcol), int(r.info.ground_to_gcol) - 1
+        ref = cc.read_columns(lo, hi, fields=["ground_point_label", "debug_ground_point_label", "is_ignored", "intensity"])
+        assert lab.shape == (hi - lo + 1, sp.rows, 4)
+        for j, f in enumerate(("ground_point_label", "debug_ground_point_label", "is_ignored", "intensity")):
+            assert np.array_equal(lab[..., j], ref[f])
+
+
+def test_label_prefetch_equals_read_columns(emu_library):
+    check_label_prefetch(emu_library)
+
+
 def test_results_do_not_depend_on_push_size(emu_library):
     pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0, moving=True, dropout=0.05)
     cfg = drvlib.stream_config("tiny16")

@@ -11,7 +11,7 @@ import recorder
 from continuous_clustering_b200 import ContinuousClustering, synth
 from golden import make_golden
 from oracle import drvlib
-from test_emu_parity import ASYNC_CASES, CASES, IDENTITY, make_cc, oracle_record
+from test_emu_parity import ASYNC_CASES, CASES, IDENTITY, check_label_prefetch, make_cc, oracle_record
 
 pytestmark = pytest.mark.gpu
 
@@ -102,6 +102,10 @@ def test_size_independent_properties(cuda_library):
     assert counts.min() > 5
     assert (cells["is_ignored"][cells["id"] != 0] == 0).all()
     assert (cells["ground_point_label"][cells["id"] != 0] == 119).all()
+
+
+def test_cuda_label_prefetch(cuda_library):
+    check_label_prefetch(None)
 
 
 def test_device_resident_push_equals_host_push(cuda_library):
