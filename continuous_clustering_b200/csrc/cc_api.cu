@@ -47,6 +47,7 @@ struct cc_handle
     int used_exact_flag{0};
     size_t probe_smem_set{0};
     size_t lite_smem_set{0};
+    size_t fin_smem_set{0};
     CcDevPtrs d{};
     unsigned int* d_s_parent{nullptr};
     unsigned int* d_s_links{nullptr};
@@ -695,7 +696,19 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
 #else
     const int fin_threads = 1024;
 #endif
-    CC_RUN(h, k_fin_all, 1, fin_threads, fin_threads * sizeof(long long), cfg, h->d, ci0, ci1, seq, guard, exact, last);
+    // scan scratch + room for the segment's running maxima / the prefix maxima of G (whichever phase is running)
+    size_t fin_smem = fin_threads * sizeof(long long) +
+                      std::max(static_cast<size_t>(h->maxcols) * sizeof(double), static_cast<size_t>(h->d.cap_G) * sizeof(int));
+    if (fin_smem > 200 * 1024)
+        fin_smem = 200 * 1024;
+#ifndef CC_EMU
+    if (fin_smem > 48 * 1024 && fin_smem != h->fin_smem_set)
+    {
+        cudaFuncSetAttribute(k_fin_all, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem));
+        h->fin_smem_set = fin_smem;
+    }
+#endif
+    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem));
     CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
 }
 
@@ -814,18 +827,12 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     CC_RUN(h, k_prep, grid_for(h, static_cast<long long>(n) * CC_WARP, 256), 256, 0, cfg, h->d, n);
     // lite insertion path (regular prefix of the push, grid-wide) ...
     {
-        const size_t lite_smem = static_cast<size_t>(n) * (sizeof(CcFiringSummary) + sizeof(int)) + 2 * (static_cast<size_t>(n) + 1) * sizeof(int);
 #ifndef CC_EMU
-        if (lite_smem > 48 * 1024 && lite_smem > h->lite_smem_set)
-        {
-            CC_CHECK(h, cudaFuncSetAttribute(k_scan_lite, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lite_smem)));
-            h->lite_smem_set = lite_smem;
-        }
-        const int lite_threads = 256;
+        const int lite_threads = 1024;
 #else
         const int lite_threads = 1;
 #endif
-        CC_RUN(h, k_scan_lite, 1, lite_threads, lite_smem, cfg, h->d, n);
+        CC_RUN(h, k_scan_lite, 1, lite_threads, lite_threads * sizeof(CcAnchorSeg), cfg, h->d, n);
     }
     CC_RUN(h, k_scan_check, R, 256, 256 * sizeof(int), cfg, h->d, n);
     CC_RUN(h, k_scan_apply, R, 256, 256 * sizeof(int), cfg, h->d, n);

@@ -242,43 +242,53 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 //     k_scan_apply (block / row) distance write-through of the stored points, new row fronts
 //     The first irregular firing (scan_kbad) is exact; k_insert_scan then commits the prefix and processes the rest.
 // =====================================================================================================
-__global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
+struct CcAnchorSeg // a run of firings: first / last valid anchor and the unwrapped distance between them
 {
-    if (blockIdx.x != 0 || pg.st->halted)
+    int has, first_cw, last_cw, off;
+};
+struct CcOpAnchorSeg
+{
+    int N;
+    CC_DEV CcAnchorSeg operator()(const CcAnchorSeg& a, const CcAnchorSeg& b) const
+    {
+        if (!a.has)
+            return b;
+        if (!b.has)
+            return a;
+        CcAnchorSeg r;
+        r.has = 1;
+        r.first_cw = a.first_cw;
+        r.last_cw = b.last_cw;
+        r.off = a.off + cc_wrapdiff(b.first_cw - a.last_cw, N) + b.off;
+        return r;
+    }
+};
+struct CcMaxPair
+{
+    int p, f;
+};
+struct CcOpMaxPair
+{
+    CC_DEV CcMaxPair operator()(const CcMaxPair& a, const CcMaxPair& b) const
+    {
+        CcMaxPair r;
+        r.p = a.p > b.p ? a.p : b.p;
+        r.f = a.f > b.f ? a.f : b.f;
+        return r;
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
-    __shared__ int l_has[32], l_first[32], l_last[32], l_off[32], l_base[32];
-    // the per-firing arrays live in shared memory while the single warp below works on them (L2 round trips per
-    // firing would dominate otherwise); all threads of the CTA copy them in and out
-    // (structure of arrays + an odd per-lane range length: lane i works on firings [i*per, (i+1)*per), so
-    // consecutive lanes hit consecutive banks)
-    struct Local
-    {
-        int *s_anchor, *s_rear, *s_fore, *s_nvalid;
-        int *lite_U, *lite_P, *lite_F;
-        int maxcols;
-    } p;
-    p.s_anchor = reinterpret_cast<int*>(smem);
-    p.s_rear = p.s_anchor + n;
-    p.s_fore = p.s_rear + n;
-    p.s_nvalid = p.s_fore + n;
-    p.lite_U = p.s_nvalid + n;
-    p.lite_P = p.lite_U + n;
-    p.lite_F = p.lite_P + n + 1;
-    p.maxcols = pg.maxcols;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-    {
-        const CcFiringSummary fs = pg.lite_sum[i];
-        p.s_anchor[i] = fs.anchor;
-        p.s_rear[i] = fs.rear_rel;
-        p.s_fore[i] = fs.fore_rel;
-        p.s_nvalid[i] = fs.nvalid;
-    }
-    __syncthreads();
-    CcDevState* st = pg.st;
-    const int lane = threadIdx.x;
-    if (threadIdx.x < CC_WARP)
-    {
+    // every thread owns a few consecutive firings; the cross-thread parts are block scans
+    CcAnchorSeg* sm_seg = reinterpret_cast<CcAnchorSeg*>(smem);
+    CcMaxPair* sm_max = reinterpret_cast<CcMaxPair*>(smem);
+    __shared__ int sh_kbad, sh_first_cw, sh_has;
+    CcDevState* st = p.st;
+    const int T = blockDim.x, t = threadIdx.x;
     const int N = cfg.N, half = cfg.half;
     const int NOT_SET = -0x7fffffff - 1;
     const long long base = st->P;
@@ -286,89 +296,79 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
     const int pc0 = static_cast<int>(base % N);
     const int Fm0 = static_cast<int>(st->foremost - base);
     const int colbase_rel = static_cast<int>(st->F - base);
+    if (t == 0)
+        sh_kbad = ok ? n : 0;
+    __syncthreads();
     if (!ok)
     {
-        if (lane == 0)
+        if (t == 0)
         {
             st->scan_kbad = 0;
             st->scan_lite_base = base;
         }
+        return;
     }
-    else
-    {
-    const int per = ((n + CC_WARP - 1) / CC_WARP) | 1;
-    const int a = lane * per < n ? lane * per : n, b = (a + per < n) ? a + per : n;
+    const int per = (n + T - 1) / T;
+    const int a = t * per < n ? t * per : n, b = (a + per < n) ? a + per : n;
     int kbad = n;
-    // pass 1: anchor columns relative to the lane's first valid firing
-    int has = 0, first_cw = 0, prev_cw = 0, off = 0;
+    // pass 1: anchor columns relative to the thread's first valid firing
+    CcAnchorSeg mine;
+    mine.has = 0;
+    mine.first_cw = 0;
+    mine.last_cw = 0;
+    mine.off = 0;
     for (int k = a; k < b; k++)
     {
-        CcFiringSummary fs;
-        fs.anchor = p.s_anchor[k];
-        fs.rear_rel = p.s_rear[k];
-        fs.fore_rel = p.s_fore[k];
-        fs.nvalid = p.s_nvalid[k];
+        const CcFiringSummary fs = p.lite_sum[k];
         if (fs.nvalid < 0)
             kbad = k < kbad ? k : kbad;
         if (fs.nvalid > 0)
         {
-            if (!has)
+            if (!mine.has)
             {
-                has = 1;
-                first_cw = fs.anchor;
+                mine.has = 1;
+                mine.first_cw = fs.anchor;
             }
             else
-                off += cc_wrapdiff(fs.anchor - prev_cw, N);
-            prev_cw = fs.anchor;
+                mine.off += cc_wrapdiff(fs.anchor - mine.last_cw, N);
+            mine.last_cw = fs.anchor;
         }
-        p.lite_U[k] = off;
+        p.lite_U[k] = mine.off;
     }
-    l_has[lane] = has;
-    l_first[lane] = first_cw;
-    l_last[lane] = prev_cw;
-    l_off[lane] = off;
-    __syncwarp();
-    if (lane == 0)
+    CcAnchorSeg ident;
+    ident.has = 0;
+    ident.first_cw = ident.last_cw = ident.off = 0;
+    CcOpAnchorSeg op;
+    op.N = N;
+    const CcAnchorSeg before = cc_block_exclusive_scan(sm_seg, mine, ident, op);
+    if (t == T - 1)
     {
-        bool cur = false;
-        int lastU = 0, last_cw = 0;
-        for (int i = 0; i < CC_WARP; i++)
-        {
-            l_base[i] = 0;
-            if (!l_has[i])
-                continue;
-            int bU;
-            if (!cur)
-            {
-                // the reference's unwrap of the first valid firing against the rearmost column (cpp:152-175)
-                const int cw = l_first[i], diff = cw - pc0;
-                bU = -pc0 + cw;
-                if (diff < -half)
-                    bU += N;
-                else if (diff > half)
-                    bU -= N;
-                cur = true;
-            }
-            else
-                bU = lastU + cc_wrapdiff(l_first[i] - last_cw, N);
-            l_base[i] = bU;
-            lastU = bU + l_off[i];
-            last_cw = l_last[i];
-        }
+        const CcAnchorSeg all = op(before, mine);
+        sh_has = all.has;
+        sh_first_cw = all.first_cw;
     }
-    __syncwarp();
-    // pass 2: absolute anchors, per-firing rearmost / foremost, lane-local exclusive prefix maxima
-    const int mybase = l_base[lane];
-    int runP = NOT_SET, runF = NOT_SET;
+    __syncthreads();
+    // the reference's unwrap of the push's first valid firing against the rearmost column (cpp:152-175)
+    int U0 = 0;
+    if (sh_has)
+    {
+        const int cw = sh_first_cw, diff = cw - pc0;
+        U0 = -pc0 + cw;
+        if (diff < -half)
+            U0 += N;
+        else if (diff > half)
+            U0 -= N;
+    }
+    const int mybase = U0 + (before.has && mine.has ? before.off + cc_wrapdiff(mine.first_cw - before.last_cw, N) : 0);
+    // pass 2: absolute anchors, per-firing rearmost / foremost, thread-local exclusive prefix maxima
+    CcMaxPair run;
+    run.p = NOT_SET;
+    run.f = NOT_SET;
     for (int k = a; k < b; k++)
     {
-        CcFiringSummary fs;
-        fs.anchor = p.s_anchor[k];
-        fs.rear_rel = p.s_rear[k];
-        fs.fore_rel = p.s_fore[k];
-        fs.nvalid = p.s_nvalid[k];
-        p.lite_P[k] = runP;
-        p.lite_F[k] = runF;
+        const CcFiringSummary fs = p.lite_sum[k];
+        p.lite_P[k] = run.p;
+        p.lite_F[k] = run.f;
         if (fs.nvalid > 0)
         {
             const int U = mybase + p.lite_U[k];
@@ -376,38 +376,21 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
             const int rear = U + fs.rear_rel, fore = U + fs.fore_rel;
             if (fore - rear > N / 2) // cpp:252-261
                 kbad = k < kbad ? k : kbad;
-            runP = rear > runP ? rear : runP;
-            runF = fore > runF ? fore : runF;
+            run.p = rear > run.p ? rear : run.p;
+            run.f = fore > run.f ? fore : run.f;
         }
     }
-    int eP = runP, eF = runF;
-    for (int o = 1; o < CC_WARP; o <<= 1)
-    {
-        const int vP = __shfl_up_sync(CC_FULL_MASK, eP, o), vF = __shfl_up_sync(CC_FULL_MASK, eF, o);
-        if (lane >= o)
-        {
-            eP = vP > eP ? vP : eP;
-            eF = vF > eF ? vF : eF;
-        }
-    }
-    int pP = __shfl_up_sync(CC_FULL_MASK, eP, 1), pF = __shfl_up_sync(CC_FULL_MASK, eF, 1);
-    if (lane == 0)
-    {
-        pP = NOT_SET;
-        pF = NOT_SET;
-    }
-    pP = pP > 0 ? pP : 0;      // rearmost column at the start of the push (relative: 0)
-    pF = pF > Fm0 ? pF : Fm0;  // foremost column at the start of the push
+    CcMaxPair seed;
+    seed.p = 0;   // rearmost column at the start of the push (relative: 0)
+    seed.f = Fm0; // foremost column at the start of the push
+    CcMaxPair pre = cc_block_exclusive_scan(sm_max, run, seed, CcOpMaxPair());
+    pre = CcOpMaxPair()(pre, seed);
     // pass 3: rearmost / foremost so far before every firing; unwrap margins
     for (int k = a; k < b; k++)
     {
-        CcFiringSummary fs;
-        fs.anchor = p.s_anchor[k];
-        fs.rear_rel = p.s_rear[k];
-        fs.fore_rel = p.s_fore[k];
-        fs.nvalid = p.s_nvalid[k];
+        const CcFiringSummary fs = p.lite_sum[k];
         const int lp = p.lite_P[k], lf = p.lite_F[k];
-        const int Pk = lp > pP ? lp : pP, Fk = lf > pF ? lf : pF;
+        const int Pk = lp > pre.p ? lp : pre.p, Fk = lf > pre.f ? lf : pre.f;
         p.lite_P[k] = Pk;
         p.lite_F[k] = Fk;
         if (fs.nvalid > 0)
@@ -423,25 +406,16 @@ __global__ void k_scan_lite(CcDevCfg cfg, CcDevPtrs pg, int n)
     }
     if (a < n && b == n)
     {
-        const int Pn = runP > pP ? runP : pP, Fn = runF > pF ? runF : pF;
-        p.lite_P[n] = Pn;
-        p.lite_F[n] = Fn;
+        p.lite_P[n] = run.p > pre.p ? run.p : pre.p;
+        p.lite_F[n] = run.f > pre.f ? run.f : pre.f;
     }
-    kbad = cc_warp_min(kbad);
-    if (lane == 0)
-    {
-        st->scan_kbad = kbad;
-        st->scan_lite_base = base;
-    }
-    }
-    }
+    if (kbad < n)
+        atomicMin(&sh_kbad, kbad);
     __syncthreads();
-    for (int i = threadIdx.x; i <= n; i += blockDim.x)
+    if (t == 0)
     {
-        if (i < n)
-            pg.lite_U[i] = p.lite_U[i];
-        pg.lite_P[i] = p.lite_P[i];
-        pg.lite_F[i] = p.lite_F[i];
+        st->scan_kbad = sh_kbad;
+        st->scan_lite_base = base;
     }
 }
 
@@ -2240,11 +2214,13 @@ __device__ void d_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
     }
 }
 
-__device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
+__device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, const double* runmax_s)
 {
     if (!cc_spec_ok(p.st, guard))
         return;
     const int spec = !exact;
+    // running maximum of the segment's columns: shared-memory copy when the caller staged one (index 0 = column c0)
+    const double* rmx = runmax_s ? runmax_s - (p.st->seg_c0 - p.st->colbase) : p.col_runmax;
     CcDevState* st = p.st;
     const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
     const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase;
@@ -2267,13 +2243,13 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact)
             const long long lastcol = maxend - 1;
             const long long s = lastcol > c0 ? lastcol : c0;
             // first pass column c >= s with runmax(c) >= F
-            if (p.col_runmax[c1 - colbase] >= F)
+            if (rmx[c1 - colbase] >= F)
             {
                 long long lo = s, hi = c1;
                 while (lo < hi)
                 {
                     const long long mid = (lo + hi) >> 1;
-                    if (p.col_runmax[mid - colbase] >= F)
+                    if (rmx[mid - colbase] >= F)
                         hi = mid;
                     else
                         lo = mid + 1;
@@ -2377,7 +2353,7 @@ __device__ void d_fin_copyback(CcDevPtrs p, int spec)
 // that were still unfinished when the pass started (cpp:943-959), or column + 1. G[r] = last column at which
 // some tree rooted in column gbase + r is unfinished; with PG = prefix max of G, the answer for column c is the
 // first r with PG[r] >= c. Single block.
-__device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
+__device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec, int smem_ints)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -2391,6 +2367,10 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
     if (glen > p.cap_G)
         glen = p.cap_G;
     const int T = blockDim.x, t = threadIdx.x;
+    // the prefix maxima live in shared memory when they fit (binary searches below: 11 dependent reads per column),
+    // as columns relative to gbase (CC_COL_INF -> INT_MAX)
+    int* pg = reinterpret_cast<int*>(part + T);
+    const bool in_smem = glen <= smem_ints;
     const long long chunk = (glen + T - 1) / T;
     const long long lo = t * chunk, hi = (lo + chunk < glen) ? lo + chunk : glen;
     long long m = -1;
@@ -2400,7 +2380,13 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
     for (long long j = lo; j < hi; j++)
     {
         pre = p.G[j] > pre ? p.G[j] : pre;
-        p.G[j] = pre;
+        if (in_smem)
+        {
+            const long long rel = pre - gbase;
+            pg[j] = pre < 0 ? -1 : (rel > 0x7ffffffe ? 0x7fffffff : static_cast<int>(rel));
+        }
+        else
+            p.G[j] = pre;
     }
     __syncthreads();
     for (long long c = c0 + t; c <= c1; c += T)
@@ -2409,14 +2395,27 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec)
         long long a = 0, b = c - gbase + 1;
         if (b > glen)
             b = glen;
-        while (a < b)
+        if (in_smem)
         {
-            const long long mid = (a + b) >> 1;
-            if (p.G[mid] >= c)
-                b = mid;
-            else
-                a = mid + 1;
+            const int crel = static_cast<int>(c - gbase);
+            while (a < b)
+            {
+                const long long mid = (a + b) >> 1;
+                if (pg[mid] >= crel)
+                    b = mid;
+                else
+                    a = mid + 1;
+            }
         }
+        else
+            while (a < b)
+            {
+                const long long mid = (a + b) >> 1;
+                if (p.G[mid] >= c)
+                    b = mid;
+                else
+                    a = mid + 1;
+            }
         long long fu = gbase + a;
         if (fu > c + 1)
             fu = c + 1;
@@ -2444,23 +2443,40 @@ __device__ void d_push_done(CcDevPtrs p, int guard);
 // All list-sized phases of a finish pass in ONE CTA (the unfinished-tree list holds 10^2..10^4 entries: a single
 // CTA with block-wide barriers between the phases is faster than six dependent launches).
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
-                                                  int exact, int last)
+                                                  int exact, int last, int smem_bytes)
 {
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (blockIdx.x != 0)
         return;
+    CC_SMEM(smem);
     d_fin_init(cfg, p, ci0, ci1, guard);
+    __syncthreads();
+    // shared memory: [block-scan scratch: T x 8 B][running maximum of the segment's columns | prefix maxima of G]
+    const int T = blockDim.x;
+    const int spare = (smem_bytes - T * 8) / 8; // doubles (or pairs of ints) that fit behind the scan scratch
+    double* runmax_s = nullptr;
+    if (cc_spec_ok(p.st, guard))
+    {
+        const int nseg = static_cast<int>(p.st->seg_c1 - p.st->seg_c0 + 1);
+        if (nseg <= spare)
+        {
+            runmax_s = reinterpret_cast<double*>(smem) + T;
+            const long long off = p.st->seg_c0 - p.st->colbase;
+            for (int i = threadIdx.x; i < nseg; i += T)
+                runmax_s[i] = p.col_runmax[off + i];
+        }
+    }
     __syncthreads();
     d_fin_agg(cfg, p, guard);
     __syncthreads();
-    d_fin_decide(cfg, p, guard, exact);
+    d_fin_decide(cfg, p, guard, exact, runmax_s);
     __syncthreads();
     d_fin_mark(cfg, p, seq, guard);
     __syncthreads();
     d_fin_copyback(p, guard);
     __syncthreads();
-    d_fin_columns(cfg, p, guard);
+    d_fin_columns(cfg, p, guard, spare * 2);
     __syncthreads();
     if (last && threadIdx.x == 0)
         d_push_done(p, guard);
