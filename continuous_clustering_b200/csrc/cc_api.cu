@@ -83,6 +83,9 @@ struct cc_handle
     int pending[2]{-1, -1}; // slots of the pushes in flight, oldest first
     int n_pending{0};
     cudaStream_t copy_stream{nullptr};
+    // host -> device copies of the raw firings run on their own stream: the copy stream carries the result read-back of
+    // the push before, which waits for that push's kernels; inputs queued behind it could not overlap them
+    cudaStream_t in_stream{nullptr};
     // host-initiated reads of finished results (remainders beyond the prefetch, cc_read_columns): never queued behind
     // the copy stream's wait for a push that is still in flight
     cudaStream_t aux_stream{nullptr};
@@ -290,6 +293,7 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(CcDevState)) != cudaSuccess)
@@ -332,6 +336,11 @@ void cc_destroy(cc_handle_t* h)
                 cudaEventDestroy(e);
     if (h->copy_stream)
         cudaStreamDestroy(h->copy_stream);
+    if (h->in_stream)
+    {
+        cudaStreamSynchronize(h->in_stream);
+        cudaStreamDestroy(h->in_stream);
+    }
     if (h->aux_stream)
         cudaStreamDestroy(h->aux_stream);
     if (h->h_state)
@@ -459,6 +468,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     CC_CHECK(h, cudaSetDevice(h->device));
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
     CC_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->in_stream));
     h->n_pending = 0;
     h->next_slot = 0;
     const int N = h->config.num_columns;
@@ -1156,9 +1166,9 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
             std::memcpy(sl.h_poses, poses, qb);
             src_poses = sl.h_poses;
         }
-        CC_CHECK(h, cudaMemcpyAsync(sl.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->copy_stream));
-        CC_CHECK(h, cudaMemcpyAsync(sl.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->copy_stream));
-        CC_CHECK(h, cudaEventRecord(sl.h2d, h->copy_stream));
+        CC_CHECK(h, cudaMemcpyAsync(sl.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
+        CC_CHECK(h, cudaMemcpyAsync(sl.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
+        CC_CHECK(h, cudaEventRecord(sl.h2d, h->in_stream));
         CC_CHECK(h, cudaStreamWaitEvent(h->stream, sl.h2d, 0));
         sl.in_points = sl.d_raw;
         sl.in_poses = sl.d_poses;
