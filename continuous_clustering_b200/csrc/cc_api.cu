@@ -46,6 +46,7 @@ struct cc_handle
     int cur_label_cols{0};
     int used_exact_flag{0};
     size_t probe_smem_set{0};
+    size_t ground_smem_set{0};
     size_t lite_smem_set{0};
     size_t fin_smem_set{0};
     CcDevPtrs d{};
@@ -526,9 +527,12 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.lite_U, static_cast<size_t>(h->max_firings)));
         CC_CHECK(h, dev_alloc(h, L, &d.lite_P, static_cast<size_t>(h->max_firings) + 1));
         CC_CHECK(h, dev_alloc(h, L, &d.lite_F, static_cast<size_t>(h->max_firings) + 1));
+        CC_CHECK(h, dev_alloc(h, L, &d.lite_rowfront, static_cast<size_t>(h->R)));
         const size_t mc = static_cast<size_t>(h->maxcols);
         CC_CHECK(h, dev_alloc(h, L, &d.col_trigger, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_gap, mc * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.gap_chunk_last, (mc / CC_GAP_CHUNK + 1) * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.gap_chunk_carry, (mc / CC_GAP_CHUNK + 1) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.col_minaz, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_runmax, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_flag, mc));
@@ -698,7 +702,8 @@ static cc_status_t device_error_to_status(cc_handle* h)
 }
 
 // finish passes for columns [ci0, ci1] (ci1 < 0: all new columns); `last` also closes the push (k_push_done)
-static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact, int last)
+static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact, int last,
+                          CcDevState* snap = nullptr)
 {
     const unsigned int seq = ++h->seq;
 #ifdef CC_EMU
@@ -718,7 +723,7 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
         h->fin_smem_set = fin_smem;
     }
 #endif
-    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem));
+    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
     CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
 }
 
@@ -781,9 +786,13 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
 
 // state snapshot + optimistic prefix of the results of the push in `sl`, brought to the host on the copy stream so
 // that the next push's kernels do not wait for the transfer (the device-side result arrays are per slot)
-static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl)
+static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl, bool state_snapshot_done = false)
 {
-    CC_LAUNCH(k_state_snapshot, 1, CC_WARP, 0, h->stream, h->d, sl.d_state_snap);
+    if (!state_snapshot_done) // the push's last finish pass already wrote it on the normal path
+    {
+        CC_LAUNCH(k_state_snapshot, 1, 128, 0, h->stream, h->d, sl.d_state_snap);
+        h->launches++;
+    }
     if (h->label_prefetch && sl.has_tf)
     {
         CcDevCfg cfg;
@@ -845,7 +854,6 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
         CC_RUN(h, k_scan_lite, 1, lite_threads, lite_threads * sizeof(CcAnchorSeg), cfg, h->d, n);
     }
     CC_RUN(h, k_scan_check, R, 256, 256 * sizeof(int), cfg, h->d, n);
-    CC_RUN(h, k_scan_apply, R, 256, 256 * sizeof(int), cfg, h->d, n);
     // ... then the single-CTA scan commits that prefix and resolves whatever is left
     const int scan_smem = scan_smem_bytes(R);
     CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R), 1);
@@ -859,10 +867,17 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     }
     else
     {
-        CC_RUN(h, k_gap_scan, R, 256, 256 * sizeof(float), cfg, h->d);
+        CC_RUN(h, k_gap_scan, h->sm_count, 256, 0, cfg, h->d); // its last block chains the column chunks
         const int gw = 4; // warps (columns) per block
-        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, gw * R * sizeof(CcGroundSmem), cfg, h->d);
-        CC_RUN(h, k_runmax, 1, 1024, 1024 * sizeof(double), cfg, h->d, sl.spec ? 1 : 0);
+        const size_t ground_smem = std::max(gw * cc_ground_warp_bytes(R), gw * CC_WARP * sizeof(double));
+#ifndef CC_EMU
+        if (ground_smem > 48 * 1024 && ground_smem != h->ground_smem_set)
+        {
+            CC_CHECK(h, cudaFuncSetAttribute(k_ground, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ground_smem)));
+            h->ground_smem_set = ground_smem;
+        }
+#endif
+        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, ground_smem, cfg, h->d); // its last block also does the running maxima
         {
             // one CTA per tile of 2 new columns; the tile's sliding window of prior columns is staged in shared
             // memory; warps take the tile's non-ignored points from a shared list
@@ -878,19 +893,19 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
                 h->probe_smem_set = win_bytes;
             }
 #endif
-            CC_RUN(h, k_probe, h->sm_count * 8, 256, win_bytes, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem);
+            CC_RUN(h, k_probe, h->sm_count * 8, 256, win_bytes, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem, sl.spec ? 1 : 0);
         }
         if (sl.spec)
         {
             launch_commit(h, cfg, 0, -1, 1, false);
-            launch_finish(h, cfg, 0, -1, 1, 0, 1);
+            launch_finish(h, cfg, 0, -1, 1, 0, 1, sl.d_state_snap);
         }
         else
             CC_RUN(h, k_halt, 1, 1, 0, h->d, 0); // finish passes every n-th column: column-sequential path, on the host's cue
     }
     CC_CHECK(h, cudaEventRecord(sl.ev1, h->stream));
     sl.launches1 = h->launches;
-    return enqueue_results(h, sl);
+    return enqueue_results(h, sl, sl.has_tf && sl.spec);
 }
 
 // Waits for the oldest push in flight, finishes it (column-sequential path if the speculative commit could not be

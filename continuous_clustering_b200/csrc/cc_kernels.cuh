@@ -3,7 +3,7 @@
 //
 // Reference functions replaced ("cpp:" = src/clustering/continuous_clustering.cpp of the reference):
 //   k_prep + k_insert_scan + k_scatter   insertFiringIntoRangeImage              cpp:105-292
-//   k_gap_scan + k_ground + k_runmax     performGroundPointSegmentationForColumn cpp:294-624
+//   k_gap_scan + k_ground                performGroundPointSegmentationForColumn cpp:294-624
 //   k_probe + k_commit_* / k_careful     associatePointsInColumn, traverseFieldOfView,
 //                                        associatePointToPointTree, associatePointTreeToPointTree cpp:638-835
 //   k_fin_*                              findFinishedTreesAndAssignSameId        cpp:837-974 and the id / ring
@@ -239,7 +239,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 //     k_scan_lite  (1 warp)      unwrapped column of every firing's anchor = prefix sum of wrapped anchor deltas;
 //                                rearmost column before every firing = prefix maximum; straddle / margin checks
 //     k_scan_check (block / row) per row the columns are strictly increasing and beyond the row's front
-//     k_scan_apply (block / row) distance write-through of the stored points, new row fronts
+//     (k_insert_scan then applies the new row fronts and, if firings remain, the distance write-through)
 //     The first irregular firing (scan_kbad) is exact; k_insert_scan then commits the prefix and processes the rest.
 // =====================================================================================================
 struct CcAnchorSeg // a run of firings: first / last valid anchor and the unwrapped distance between them
@@ -440,7 +440,10 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
     const int T = blockDim.x, t = threadIdx.x;
     const int seg = (kmax + T - 1) / T;
     const int a = t * seg < kmax ? t * seg : kmax, b = (a + seg < kmax) ? a + seg : kmax;
-    int first = NOT_SET, firstk = kmax, last = NOT_SET, kbad = n;
+    int first = NOT_SET, firstk = kmax, last = NOT_SET, kbad = n, gmax = NOT_SET;
+    __shared__ int sh_front;
+    if (t == 0)
+        sh_front = NOT_SET;
     for (int k = a; k < b; k++)
     {
         const int cw = p.s_cwr[k * R + row];
@@ -455,6 +458,8 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
         else if (g <= last)
             kbad = k < kbad ? k : kbad;
         last = g;
+        if (g >= p.lite_P[k]) // stored (not too far behind, cpp:210-221): candidate for the row's new front
+            gmax = g > gmax ? g : gmax;
     }
     int prev = cc_block_exclusive_scan(sm, last, NOT_SET, CcOpLastSetI32());
     if (prev == NOT_SET)
@@ -466,51 +471,13 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
         kbad = firstk < kbad ? firstk : kbad;
     if (kbad < n)
         atomicMin(&p.st->scan_kbad, kbad);
-}
-
-__global__ void k_scan_apply(CcDevCfg cfg, CcDevPtrs p, int n)
-{
-    if (p.st->halted)
-        return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    CC_SMEM(smem);
-    int* sm = reinterpret_cast<int*>(smem);
-    const int R = cfg.R, N = cfg.N, ringcols = cfg.ringcols;
-    const int row = blockIdx.x;
-    if (row >= R)
-        return;
-    const CcDevState* st = p.st;
-    const int kbad = st->scan_kbad < n ? st->scan_kbad : n;
-    const long long base = st->scan_lite_base;
-    const int base_local = static_cast<int>(base % ringcols);
-    const int NOT_SET = -0x7fffffff - 1;
-    if (threadIdx.x == 0)
-        sm[0] = NOT_SET;
-    __syncthreads();
-    int gmax = NOT_SET;
-    for (int k = threadIdx.x; k < kbad; k += blockDim.x)
-    {
-        const int idx = k * R + row;
-        const int cw = p.s_cwr[idx];
-        if (cw == CC_INVALID_CWR)
-            continue;
-        const int g = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, N);
-        if (g < p.lite_P[k])
-            continue; // too far behind (cpp:210-221)
-        int local = base_local + g;
-        local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
-        p.pos[static_cast<size_t>(local) * R + row].w = p.s_dist[idx]; // write-through, as k_insert_scan does
-        gmax = g > gmax ? g : gmax;
-    }
+    // the row's front after the lite prefix, valid when the whole prefix [0, kmax) survives every row's check
     gmax = cc_warp_max(gmax);
-    if ((threadIdx.x % CC_WARP) == 0 && gmax != NOT_SET)
-        atomicMax(&sm[0], gmax);
+    if ((t % CC_WARP) == 0 && gmax != NOT_SET)
+        atomicMax(&sh_front, gmax);
     __syncthreads();
-    if (threadIdx.x == 0 && sm[0] != NOT_SET)
-    {
-        const long long front = base + sm[0];
-        if (front > p.rowmax[row])
-            p.rowmax[row] = front;
-    }
+    if (t == 0)
+        p.lite_rowfront[row] = sh_front;
 }
 
 // =====================================================================================================
@@ -603,6 +570,48 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         __pipeline_commit();
     };
     prefetch(chunk_start);
+
+    if (after_lite && k_start > 0)
+    {
+        // apply the lite prefix: new row fronts and -- only when firings remain for the paths below, which test cell
+        // occupancy -- the distance write-through of its stored points. A push that is regular as a whole hits every
+        // cell once and finds it empty, so k_scatter needs no winner test and nothing is written here.
+        if (k_start >= n_firings)
+        {
+            for (int row = tid; row < R; row += T)
+            {
+                const int f = p.lite_rowfront[row];
+                if (f != NOT_SET && base + f > p.rowmax[row])
+                    p.rowmax[row] = base + f;
+            }
+        }
+        else
+        {
+            for (int row = tid; row < R; row += T)
+                rm_new[row] = NOT_SET;
+            __syncthreads();
+            const int total = k_start * R;
+            for (int idx = tid; idx < total; idx += T)
+            {
+                const int k = idx / R, row = idx - k * R;
+                const int cw = p.s_cwr[idx];
+                if (cw == CC_INVALID_CWR)
+                    continue;
+                const int g = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, N);
+                if (g < p.lite_P[k])
+                    continue; // too far behind (cpp:210-221)
+                int local = base_local + g;
+                local = local < 0 ? local + ringcols : (local >= ringcols ? local - ringcols : local);
+                p.pos[static_cast<size_t>(local) * R + row].w = p.s_dist[idx];
+                atomicMax(&rm_new[row], g);
+            }
+            __syncthreads();
+            for (int row = tid; row < R; row += T)
+                if (rm_new[row] != NOT_SET && base + rm_new[row] > p.rowmax[row])
+                    p.rowmax[row] = base + rm_new[row];
+        }
+        __syncthreads();
+    }
 
     for (int row = tid; row < R; row += T)
     {
@@ -1181,8 +1190,10 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     {
         const int k = idx / cfg.R, row = idx - k * cfg.R;
         int grel, rot;
+        bool winner_test = true;
         if (k < p.st->scan_kbad)
         {
+            winner_test = p.st->scan_kbad < n_firings; // a push that is regular as a whole has one writer per cell
             // firing resolved by the lite path: same integers as k_scan_check / k_scan_apply
             const int cw = p.s_cwr[idx];
             if (cw == CC_INVALID_CWR)
@@ -1225,7 +1236,7 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         const long long g = p.st->scan_base + grel;
         const size_t cell = static_cast<size_t>(cc_local_col(g, cfg.ringcols)) * cfg.R + row;
         const float4 sp = p.s_pos[idx];
-        if (ccm::f2u(p.pos[cell].w) != ccm::f2u(sp.w))
+        if (winner_test && ccm::f2u(p.pos[cell].w) != ccm::f2u(sp.w))
             continue;
         const CcRawPoint* raw = reinterpret_cast<const CcRawPoint*>(p.raw) + idx;
         p.pos[cell] = sp;
@@ -1243,57 +1254,147 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 
 // =====================================================================================================
 // K2a  sc_inclination_angles_between_lasers_ (cpp:353-357): per row, the last non-NaN inclination difference
-//      to the laser below seen in any column so far. One block per row: chunked "last valid" scan over the
-//      new columns, seeded with the value carried from earlier pushes.
+//      to the laser below seen in any column so far. Columns are cut into chunks of CC_GAP_CHUNK: every (chunk, row)
+//      resolves its columns locally with coalesced reads (NaN where the chunk has not seen a valid value yet) and
+//      leaves its last valid value; the block that finishes last chains the chunks per row (warp scan), seeded with
+//      the value carried from earlier pushes. k_ground takes the chunk's carry-in where the local value is NaN.
 // =====================================================================================================
-__global__ void k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
+#define CC_GAP_CHUNK 32
+#define CC_GAP_BATCH 16 /* columns whose loads are issued together */
+
+CC_DEV float cc_ldcg_f32(const float* q)
+{
+#ifdef CC_EMU
+    return *q;
+#else
+    return __ldcg(q);
+#endif
+}
+
+__global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    CC_SMEM(smem);
-    float* lastv = reinterpret_cast<float*>(smem);
     const int R = cfg.R;
-    const int row = blockIdx.x;
-    if (row >= R)
-        return;
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
     const int T = blockDim.x, t = threadIdx.x;
-    const int chunk = (ncols + T - 1) / T;
-    const int lo = t * chunk, hi = (lo + chunk < ncols) ? lo + chunk : ncols;
-    float last = cc_nanf();
-    for (int ci = lo; ci < hi; ci++)
+    const int nchunks = (ncols + CC_GAP_CHUNK - 1) / CC_GAP_CHUNK;
+    const float nanv = cc_nanf();
+    const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
+    const int items = nchunks * R; // (chunk, row), rows fastest: a warp reads consecutive rows of one column
+    for (int it = blockIdx.x * T + t; it < items; it += gridDim.x * T)
     {
-        const size_t cell = static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
-        const float a = p.incl[cell];
-        const float b = (row == R - 1) ? 0.f : p.incl[cell + 1];
-        const float d = a - b;
-        if (!cc_isnan(d))
-            last = d;
+        const int chunk = it / R, row = it - chunk * R;
+        const int c0 = chunk * CC_GAP_CHUNK;
+        float last = nanv;
+        for (int jb = 0; jb < CC_GAP_CHUNK && c0 + jb < ncols; jb += CC_GAP_BATCH)
+        {
+            float a[CC_GAP_BATCH], b[CC_GAP_BATCH];
+            int local = base_local + c0 + jb;
+            if (local >= cfg.ringcols)
+                local -= cfg.ringcols;
+#pragma unroll
+            for (int j = 0; j < CC_GAP_BATCH; j++)
+            {
+                const bool in = c0 + jb + j < ncols;
+                const size_t cell = static_cast<size_t>(local) * R + row;
+                a[j] = in ? p.incl[cell] : nanv;
+                b[j] = (row == R - 1) ? 0.f : (in ? p.incl[cell + 1] : nanv);
+                local = local + 1 == cfg.ringcols ? 0 : local + 1;
+            }
+#pragma unroll
+            for (int j = 0; j < CC_GAP_BATCH; j++)
+            {
+                const float d = a[j] - b[j];
+                if (!cc_isnan(d))
+                    last = d;
+                if (c0 + jb + j < ncols)
+                    p.col_gap[static_cast<size_t>(c0 + jb + j) * R + row] = last;
+            }
+        }
+        p.gap_chunk_last[it] = last;
     }
-    // exclusive "last valid" prefix over threads, seeded with the carried state
-    float pre = cc_block_exclusive_scan(lastv, last, cc_nanf(), CcOpLastValid());
-    if (cc_isnan(pre))
-        pre = p.gap_state[row];
-    float cur = pre;
-    for (int ci = lo; ci < hi; ci++)
+
+    __shared__ int sh_last;
+    __syncthreads();
+    if (t == 0)
     {
-        const size_t cell = static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
-        const float a = p.incl[cell];
-        const float b = (row == R - 1) ? 0.f : p.incl[cell + 1];
-        const float d = a - b;
-        if (!cc_isnan(d))
-            cur = d;
-        p.col_gap[static_cast<size_t>(ci) * R + row] = cur;
+        __threadfence();
+        const int ticket = atomicAdd(&p.st->ticket_gap, 1);
+        sh_last = ticket == static_cast<int>(gridDim.x) - 1;
     }
     __syncthreads();
-    if (t == T - 1)
+    if (!sh_last)
+        return;
+    __threadfence();
+    if (t == 0)
+        p.st->ticket_gap = 0;
+    // chain the chunks: tiles of chunks are staged in shared memory with independent coalesced loads (one memory
+    // round trip per tile); every row is then walked by `parts` threads, each over a contiguous range of chunks
+    __shared__ float sh_tile[8192];
+    __shared__ float sh_part[256];
+    const int tile_chunks = 8192 / R;
+    const int parts = T / R > 0 ? T / R : 1;
+    for (int cb = 0; cb < nchunks; cb += tile_chunks)
     {
-        float fin = pre;
-        if (!cc_isnan(last))
-            fin = last;
-        if (ncols > 0)
-            p.gap_state[row] = fin;
+        const int nc = (nchunks - cb) < tile_chunks ? (nchunks - cb) : tile_chunks;
+        const int n = nc * R;
+        const float* src = p.gap_chunk_last + static_cast<size_t>(cb) * R;
+        for (int i0 = 0; i0 < n; i0 += 8 * T)
+        {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                v[u] = i0 + u * T + t < n ? cc_ldcg_f32(src + i0 + u * T + t) : nanv;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u * T + t < n)
+                    sh_tile[i0 + u * T + t] = v[u];
+        }
+        __syncthreads();
+        const int per = (nc + parts - 1) / parts;
+        for (int it = t; it < parts * R; it += T)
+        {
+            const int part = it / R, row = it - part * R;
+            const int ca = part * per < nc ? part * per : nc, cz = (ca + per < nc) ? ca + per : nc;
+            float last = nanv;
+            for (int c = ca; c < cz; c++)
+            {
+                const float v = sh_tile[c * R + row];
+                if (!cc_isnan(v))
+                    last = v;
+            }
+            sh_part[it] = last;
+        }
+        __syncthreads();
+        for (int it = t; it < parts * R; it += T)
+        {
+            const int part = it / R, row = it - part * R;
+            const int ca = part * per < nc ? part * per : nc, cz = (ca + per < nc) ? ca + per : nc;
+            float carry = p.gap_state[row];
+            for (int q = 0; q < part; q++)
+            {
+                const float v = sh_part[q * R + row];
+                if (!cc_isnan(v))
+                    carry = v;
+            }
+            for (int c = ca; c < cz; c++)
+            {
+                const float v = sh_tile[c * R + row];
+                sh_tile[c * R + row] = carry;
+                if (!cc_isnan(v))
+                    carry = v;
+            }
+            if (part == parts - 1)
+                sh_part[it] = carry; // the row's value after the tile (its own entry is no longer needed)
+        }
+        __syncthreads();
+        for (int row = t; row < R; row += T)
+            p.gap_state[row] = sh_part[(parts - 1) * R + row];
+        for (int i = t; i < n; i += T)
+            p.gap_chunk_carry[static_cast<size_t>(cb) * R + i] = sh_tile[i];
+        __syncthreads();
     }
 }
 
@@ -1303,14 +1404,47 @@ __global__ void k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 //      runs the bottom-to-top label state machine on the staged values, then all lanes derive is_ignored
 //      (cpp:567-616) and write the association view of the column.
 // =====================================================================================================
-struct CcGroundSmem
+// per-warp shared memory of k_ground (R rows): by-row staging, the compacted sequence of regular points the label
+// state machine walks, inclinations, labels, cell classes and the bitmap of regular rows
+struct CcGroundRow
 {
-    // per row, per warp
-    float c2x, c2y, incl, gap;
-    unsigned char cls, label, dbg, pad;
+    float c2x, c2y; // position w.r.t. the sensor in the azimuth plane (hpp:229-232)
+    unsigned int flags;
+    float gap;
 };
+#define CC_GF_FIRST 1u /* first regular point of the column (cpp:409-431) */
+#define CC_GF_FLAT 2u  /* first point: inside the first-ring bounds; else: flat w.r.t. the previous point (cpp:434-441) */
+#define CC_GF_LG 4u    /* slope / distance part of the last-certain-ground update rule (cpp:542-551) */
+static inline __host__ __device__ size_t cc_ground_warp_bytes(int R)
+{
+    return (static_cast<size_t>(R) * (2 * sizeof(CcGroundRow) + sizeof(float) + sizeof(unsigned short) + 1) + 28 * sizeof(unsigned int) + 15) / 16 * 16;
+}
 
-__global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
+CC_DEV double cc_ldcg_f64(const double* q)
+{
+#ifdef CC_EMU
+    return *q;
+#else
+    return __ldcg(q);
+#endif
+}
+
+// |RN(y / x)| < m, decided without the division unless the quotient is within 1e-6 (relative) of m
+CC_DEV bool cc_slope_below(float y, float x, float m)
+{
+    const float t = m * fabsf(x);
+    if (t > 1e-30f && t < 1e30f)
+    {
+        const float ay = fabsf(y);
+        if (ay < t * 0.999999f)
+            return true;
+        if (ay > t * 1.000001f)
+            return false;
+    }
+    return fabsf(ccm::div_rn(y, x)) < m;
+}
+
+__global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
 {
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -1318,10 +1452,21 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
     const int R = cfg.R;
     const int warps_per_block = blockDim.x / CC_WARP;
     const int wib = threadIdx.x / CC_WARP, lane = threadIdx.x % CC_WARP;
-    CcGroundSmem* s = reinterpret_cast<CcGroundSmem*>(smem) + static_cast<size_t>(wib) * R;
+    unsigned char* wbase = smem + static_cast<size_t>(wib) * cc_ground_warp_bytes(R);
+    CcGroundRow* s = reinterpret_cast<CcGroundRow*>(wbase);  // by row
+    CcGroundRow* cseq = s + R;                               // regular points, bottom row first; flags carry the row
+    float* s_incl = reinterpret_cast<float*>(cseq + R);
+    unsigned int* vm = reinterpret_cast<unsigned int*>(s_incl + R); // bitmap of regular rows (8 words)
+    unsigned int* fm = vm + 8;  // by position in cseq: flat w.r.t. the previous point
+    unsigned int* lm = fm + 8;  // by position in cseq: passes the slope / distance part of the last-ground update rule
+    unsigned int* cst = lm + 8; // state handed from C1 to C3
+    unsigned short* s_lab = reinterpret_cast<unsigned short*>(cst + 4); // label | debug label << 8
+    unsigned char* s_cls = reinterpret_cast<unsigned char*>(s_lab + R);
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
     const float nanv = cc_nanf();
+    const int nwords = (R + 31) / 32;
+    const float hsg = cfg.height_sensor_to_ground;
 
     for (int ci = blockIdx.x * warps_per_block + wib; ci < ncols; ci += gridDim.x * warps_per_block)
     {
@@ -1335,173 +1480,300 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
         cc_iso_mul(cfg.robot_from_sensor, inv, ego);
         const float spx = static_cast<float>(pose[3]), spy = static_cast<float>(pose[7]),
                     spz = static_cast<float>(pose[11]);
-        if (lane == 0 && p.slot_gcol[local] != -1)
+        if (lane == 0)
         {
-            p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
-            p.st->err_a = p.slot_gcol[local];
-            p.st->err_b = gcol;
+            if (p.slot_gcol[local] != -1)
+            {
+                p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
+                p.st->err_a = p.slot_gcol[local];
+                p.st->err_b = gcol;
+            }
+            for (int w = 0; w < 24; w++)
+                vm[w] = 0u; // vm, fm, lm
         }
 
-        // ---- stage ----
-        for (int row = lane; row < R; row += CC_WARP)
+        // ---- A: stage every cell (class, azimuth-plane projection), bitmap of the regular rows ----
+        for (int row0 = 0; row0 < R; row0 += CC_WARP)
         {
-            const float4 q = p.pos[base + row];
-            const float incl = p.incl[base + row];
-            const unsigned char intensity = p.lab[base + row].w;
-            unsigned char cls = 3;
-            float c2x = nanv, c2y = nanv;
-            if (cc_isnan(q.w))
-                cls = 0;
-            else if (cfg.fog_enabled && intensity < static_cast<unsigned char>(cfg.fog_intensity) &&
-                     q.w < cfg.fog_dist && incl > cfg.fog_incl)
-                cls = 1;
-            else
+            const int row = row0 + lane;
+            const bool in = row < R;
+            unsigned char cls = 0;
+            if (in)
             {
-                double e[3];
-                cc_iso_apply(ego, static_cast<double>(q.x), static_cast<double>(q.y), static_cast<double>(q.z), e);
-                if (e[0] < cfg.l_front && e[0] > cfg.l_rear && e[1] < cfg.w_left && e[1] > cfg.w_right &&
-                    e[2] < cfg.h_max && e[2] > cfg.h_ground)
-                    cls = 2;
+                const float4 q = p.pos[base + row];
+                const float incl = p.incl[base + row];
+                const unsigned char intensity = p.lab[base + row].w;
+                cls = 3;
+                unsigned short lab = CC_GP_UNKNOWN | (CC_WHITE << 8);
+                if (cc_isnan(q.w))
+                    cls = 0;
+                else if (cfg.fog_enabled && intensity < static_cast<unsigned char>(cfg.fog_intensity) &&
+                         q.w < cfg.fog_dist && incl > cfg.fog_incl)
+                {
+                    cls = 1;
+                    lab = CC_GP_FOG | (CC_LIGHTGRAY << 8); // cpp:376-382
+                }
+                else
+                {
+                    double e[3];
+                    cc_iso_apply(ego, static_cast<double>(q.x), static_cast<double>(q.y), static_cast<double>(q.z), e);
+                    if (e[0] < cfg.l_front && e[0] > cfg.l_rear && e[1] < cfg.w_left && e[1] > cfg.w_right &&
+                        e[2] < cfg.h_max && e[2] > cfg.h_ground)
+                    {
+                        cls = 2;
+                        lab = CC_GP_EGO_VEHICLE | (CC_VIOLET << 8); // cpp:396-402
+                    }
+                }
+                const float x = q.x - spx, y = q.y - spy, z = q.z - spz;
+                CcGroundRow r;
+                r.c2x = ccm::sqrt_rn(x * x + y * y);
+                r.c2y = z;
+                r.flags = 0u;
+                r.gap = p.col_gap[static_cast<size_t>(ci) * R + row];
+                if (cc_isnan(r.gap)) // nothing valid in the column's chunk so far: what the chunks before it left
+                    r.gap = p.gap_chunk_carry[static_cast<size_t>(ci / CC_GAP_CHUNK) * R + row];
+                s[row] = r;
+                s_incl[row] = incl;
+                s_lab[row] = lab;
+                s_cls[row] = cls;
             }
-            // position w.r.t. the sensor in the azimuth plane (hpp:229-232); also needed for the relabel walk
-            const float x = q.x - spx, y = q.y - spy, z = q.z - spz;
-            c2x = ccm::sqrt_rn(x * x + y * y);
-            c2y = z;
-            s[row].c2x = c2x;
-            s[row].c2y = c2y;
-            s[row].incl = incl;
-            s[row].gap = p.col_gap[static_cast<size_t>(ci) * R + row];
-            s[row].cls = cls;
-            s[row].label = CC_GP_UNKNOWN;
-            s[row].dbg = CC_WHITE;
+            const unsigned int m = __ballot_sync(CC_FULL_MASK, in && cls == 3);
+            if (lane == 0)
+                vm[row0 >> 5] |= m << (row0 & 31);
         }
         __syncwarp();
 
-        // ---- sequential label state machine (cpp:305-565) ----
-        if (lane == 0)
+        // ---- B: everything of the label rules that does not depend on carried state, for all rows at once: the
+        //      previous regular point (fog / ego / empty cells never become "previous", cpp:360-404), the slope to it,
+        //      the compacted bottom-to-top sequence; and the inclination supplement of runs of empty cells ----
+        int nregular = 0;
+        for (int w = 0; w < nwords; w++)
+            nregular += __popc(vm[w]);
+        for (int row = lane; row < R; row += CC_WARP)
         {
-            bool first_obstacle_detected = false, first_point_found = false;
-            float lg_x = 0.f, lg_y = cfg.height_sensor_to_ground; // to2d of last_ground_position_wrt_sensor
-            float pv_x = 0.f, pv_y = 0.f;
-            unsigned char prev_label = 0;
-            for (int row = R - 1; row >= 0; row--)
+            const unsigned char cls = s_cls[row];
+            if (cls == 3)
             {
-                const unsigned char cls = s[row].cls;
-                if (cls == 0)
+                int w = row >> 5;
+                unsigned int m = vm[w] & ~((2u << (row & 31)) - 1u); // regular rows below this one (higher index)
+                int rank = __popc(m);
+                while (!m && ++w < nwords)
+                    m = vm[w];
+                for (int w2 = (row >> 5) + 1; w2 < nwords; w2++)
+                    rank += __popc(vm[w2]);
+                const CcGroundRow me = s[row];
+                unsigned int f = 0u;
+                if (!m)
                 {
-                    if (cfg.supplement && row < R - 1)
-                        s[row].incl = s[row + 1].incl + s[row].gap; // cpp:364-369
-                    continue;
+                    const float h = me.c2y - hsg; // cpp:412-414
+                    f = CC_GF_FIRST | ((h > cfg.first_min && h < cfg.first_max) ? CC_GF_FLAT : 0u);
                 }
-                if (cls == 1)
+                else
                 {
-                    s[row].label = CC_GP_FOG;
-                    s[row].dbg = CC_LIGHTGRAY;
-                    continue;
+                    const int pv = w * 32 + __ffs(m) - 1;
+                    const float ptc_x = me.c2x - s[pv].c2x, ptc_y = me.c2y - s[pv].c2y;
+                    const float slope_to_prev = ccm::div_rn(ptc_y, ptc_x);
+                    bool flat_prev = fabsf(slope_to_prev) < cfg.max_slope && ptc_x > 0;
+                    flat_prev = flat_prev && (!cfg.use_terrain || ptc_x < 5);
+                    if (flat_prev)
+                        f |= CC_GF_FLAT;
+                    if (slope_to_prev > cfg.lg_slope && fabsf(ptc_x) < cfg.lg_dist)
+                        f |= CC_GF_LG;
                 }
-                if (cls == 2)
+                CcGroundRow c = me;
+                c.flags = f | (static_cast<unsigned int>(row) << 16);
+                cseq[rank] = c;
+                if (f & CC_GF_FLAT)
+                    atomicOr(&fm[rank >> 5], 1u << (rank & 31));
+                if (f & CC_GF_LG)
+                    atomicOr(&lm[rank >> 5], 1u << (rank & 31));
+            }
+            else if (cls == 0 && cfg.supplement && (row == R - 1 || s_cls[row + 1] != 0))
+            {
+                // bottom cell of a run of empty cells: the supplement chains upwards through the run (cpp:364-369)
+                float v = s_incl[row];
+                if (row < R - 1)
                 {
-                    s[row].label = CC_GP_EGO_VEHICLE;
-                    s[row].dbg = CC_VIOLET;
-                    continue;
+                    v = s_incl[row + 1] + s[row].gap;
+                    s_incl[row] = v;
                 }
-                const float c2x = s[row].c2x, c2y = s[row].c2y;
-                if (!first_point_found) // cpp:409-431
+                for (int r2 = row - 1; r2 >= 0 && s_cls[r2] == 0; r2--)
                 {
-                    first_point_found = true;
-                    const float h = c2y - cfg.height_sensor_to_ground;
-                    if (h > cfg.first_min && h < cfg.first_max)
-                    {
-                        s[row].label = CC_GP_GROUND;
-                        s[row].dbg = CC_GRAY;
-                        lg_x = c2x;
-                        lg_y = c2y;
-                        first_obstacle_detected = false;
-                    }
-                    else
-                    {
-                        s[row].label = CC_GP_OBSTACLE;
-                        s[row].dbg = CC_ORANGE;
-                        first_obstacle_detected = true;
-                    }
-                    pv_x = c2x;
-                    pv_y = c2y;
-                    prev_label = s[row].dbg;
-                    continue;
+                    v = v + s[r2].gap;
+                    s_incl[r2] = v;
                 }
-                const float ptc_x = c2x - pv_x, ptc_y = c2y - pv_y;
-                const float slope_to_prev = ccm::div_rn(ptc_y, ptc_x);
-                bool flat_prev = fabsf(slope_to_prev) < cfg.max_slope && ptc_x > 0;
-                flat_prev = flat_prev && (!cfg.use_terrain || ptc_x < 5);
-                const float gtc_x = c2x - lg_x, gtc_y = c2y - lg_y;
-                const float slope_to_ground = ccm::div_rn(gtc_y, gtc_x);
-                const bool flat_ground = fabsf(slope_to_ground) < cfg.max_slope && gtc_x > 0;
+            }
+        }
+        __syncwarp();
 
-                unsigned char label = CC_GP_UNKNOWN, dbg = CC_WHITE;
-                if (!first_obstacle_detected && flat_prev)
+        // ---- C: the sequential label state machine (cpp:305-565) over the regular points only ----
+        // C1 (lane 0): up to the first obstacle a flat point is GREEN whatever came before, so the walk jumps from one
+        //     non-flat point to the next with bit operations on the flat / last-ground-candidate masks
+        // C2 (all lanes): GREEN labels of that prefix
+        // C3 (lane 0): the rest, point by point
+        if (lane == 0 && nregular > 0)
+        {
+            bool fod = false, prev_yellow = false;
+            float lg_x = 0.f, lg_y = hsg; // to2d of last_ground_position_wrt_sensor
+            {
+                const CcGroundRow cur = cseq[0]; // always the FIRST point (cpp:409-431)
+                const int row = static_cast<int>(cur.flags >> 16);
+                if (cur.flags & CC_GF_FLAT)
                 {
-                    label = CC_GP_GROUND;
-                    dbg = CC_GREEN;
+                    s_lab[row] = CC_GP_GROUND | (CC_GRAY << 8);
+                    lg_x = cur.c2x;
+                    lg_y = cur.c2y;
                 }
+                else
+                {
+                    s_lab[row] = CC_GP_OBSTACLE | (CC_ORANGE << 8);
+                    fod = true;
+                }
+            }
+            int i = 1;
+            while (!fod && i < nregular)
+            {
+                // next point at index >= i that is not flat w.r.t. its predecessor
+                int j = nregular;
+                for (int w = i >> 5; w < nwords; w++)
+                {
+                    unsigned int m = ~fm[w];
+                    if (w == (i >> 5))
+                        m &= ~((1u << (i & 31)) - 1u);
+                    if (m)
+                    {
+                        const int cand = w * 32 + __ffs(m) - 1;
+                        j = cand < nregular ? cand : nregular;
+                        break;
+                    }
+                }
+                if (j > i)
+                {
+                    // points [i, j) are GREEN; the last of them that passes the update rule (cpp:542-551) becomes the
+                    // last certain ground point (only point i can have a YELLOW predecessor)
+                    int k = -1;
+                    for (int w = (j - 1) >> 5; w >= (i >> 5) && k < 0; w--)
+                    {
+                        unsigned int m = lm[w];
+                        if (w == ((j - 1) >> 5) && ((j - 1) & 31) != 31)
+                            m &= (2u << ((j - 1) & 31)) - 1u;
+                        if (w == (i >> 5))
+                        {
+                            m &= ~((1u << (i & 31)) - 1u);
+                            if (prev_yellow)
+                                m &= ~(1u << (i & 31));
+                        }
+                        if (m)
+                            k = w * 32 + 31 - __clz(static_cast<int>(m));
+                    }
+                    if (k >= 0)
+                    {
+                        lg_x = cseq[k].c2x;
+                        lg_y = cseq[k].c2y;
+                    }
+                    prev_yellow = false;
+                    i = j;
+                    if (i >= nregular)
+                        break;
+                }
+                // point i is not flat: YELLOW if close to the last certain ground, else the first obstacle
+                const CcGroundRow cur = cseq[i];
+                const float gtc_x = cur.c2x - lg_x, gtc_y = cur.c2y - lg_y;
+                if (!cfg.use_terrain && fabsf(gtc_x) < cfg.close_d && fabsf(gtc_y) < cfg.close_z)
+                {
+                    s_lab[cur.flags >> 16] = CC_GP_GROUND | (CC_YELLOW << 8);
+                    prev_yellow = true;
+                    i++;
+                }
+                else
+                    break; // handled by C3
+            }
+            cst[0] = i;
+            cst[1] = (fod ? 1u : 0u) | (prev_yellow ? 2u : 0u);
+            cst[2] = ccm::f2u(lg_x);
+            cst[3] = ccm::f2u(lg_y);
+        }
+        __syncwarp();
+        if (nregular > 0)
+        {
+            const int npre = static_cast<int>(cst[0]);
+            for (int k = 1 + lane; k < npre; k += CC_WARP)
+            {
+                const unsigned int f = cseq[k].flags;
+                if (f & CC_GF_FLAT)
+                    s_lab[f >> 16] = CC_GP_GROUND | (CC_GREEN << 8);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && nregular > 0 && static_cast<int>(cst[0]) < nregular)
+        {
+            int i = static_cast<int>(cst[0]);
+            bool fod = (cst[1] & 1u) != 0, prev_yellow = (cst[1] & 2u) != 0;
+            float lg_x = ccm::u2f(cst[2]), lg_y = ccm::u2f(cst[3]);
+            CcGroundRow nx = cseq[i];
+            int prev_row = -1;
+            unsigned int prev_lab = 0u;
+            for (; i < nregular; i++)
+            {
+                const CcGroundRow cur = nx;
+                if (i + 1 < nregular)
+                    nx = cseq[i + 1];
+                const int row = static_cast<int>(cur.flags >> 16);
+                const float c2x = cur.c2x, c2y = cur.c2y;
+                const bool flat_prev = (cur.flags & CC_GF_FLAT) != 0;
+                unsigned int lab = 0u;
+                if (!fod && flat_prev)
+                    lab = CC_GP_GROUND | (CC_GREEN << 8);
                 else if (!cfg.use_terrain)
                 {
-                    if (first_obstacle_detected && flat_prev && flat_ground)
-                    {
-                        label = CC_GP_GROUND;
-                        dbg = CC_YELLOWGREEN;
-                    }
+                    const float gtc_x = c2x - lg_x, gtc_y = c2y - lg_y;
+                    if (fod && flat_prev && gtc_x > 0 && cc_slope_below(gtc_y, gtc_x, cfg.max_slope))
+                        lab = CC_GP_GROUND | (CC_YELLOWGREEN << 8);
                     else if (fabsf(gtc_x) < cfg.close_d && fabsf(gtc_y) < cfg.close_z)
-                    {
-                        label = CC_GP_GROUND;
-                        dbg = CC_YELLOW;
-                    }
+                        lab = CC_GP_GROUND | (CC_YELLOW << 8);
                 }
-                if (label != CC_GP_GROUND) // cpp:508-536
+                if (lab == 0u) // cpp:508-536
                 {
-                    label = CC_GP_OBSTACLE;
-                    dbg = CC_RED;
+                    lab = CC_GP_OBSTACLE | (CC_RED << 8);
                     int below = row + 1;
                     while (below < R)
                     {
-                        const unsigned char ql = s[below].label, qd = s[below].dbg;
-                        if (qd == CC_YELLOW || (ql == CC_GP_GROUND && fabsf(c2x - s[below].c2x) < cfg.next_obst_d))
+                        const unsigned int ql = below == prev_row ? prev_lab : static_cast<unsigned int>(s_lab[below]);
+                        const bool is_ground = (ql & 0xffu) == CC_GP_GROUND;
+                        if ((ql >> 8) == CC_YELLOW || (is_ground && fabsf(c2x - s[below].c2x) < cfg.next_obst_d))
                         {
-                            if (ql == CC_GP_GROUND)
-                            {
-                                s[below].label = CC_GP_OBSTACLE;
-                                s[below].dbg = CC_DARKRED;
-                            }
+                            if (is_ground)
+                                s_lab[below] = CC_GP_OBSTACLE | (CC_DARKRED << 8);
                             below++;
                         }
                         else
                             break;
                     }
+                    fod = true;
                 }
-                s[row].label = label;
-                s[row].dbg = dbg;
-                first_obstacle_detected |= label == CC_GP_OBSTACLE;
-                if (dbg == CC_GREEN || dbg == CC_YELLOWGREEN) // cpp:541-561
+                s_lab[row] = static_cast<unsigned short>(lab);
+                const unsigned int dbg = lab >> 8;
+                if ((dbg == CC_GREEN || dbg == CC_YELLOWGREEN) && (cur.flags & CC_GF_LG) && !prev_yellow) // cpp:541-561
                 {
-                    if (slope_to_prev > cfg.lg_slope && fabsf(ptc_x) < cfg.lg_dist && prev_label != CC_YELLOW)
-                    {
-                        lg_x = c2x;
-                        lg_y = c2y;
-                    }
+                    lg_x = c2x;
+                    lg_y = c2y;
                 }
-                pv_x = c2x;
-                pv_y = c2y;
-                prev_label = dbg;
+                prev_yellow = dbg == CC_YELLOW;
+                prev_row = row;
+                prev_lab = lab;
             }
         }
         __syncwarp();
 
-        // ---- is_ignored (cpp:567-616) + association view ----
+        // ---- D: is_ignored (cpp:567-616) + association view ----
         double min_az = 1.7976931348623157e308;
         for (int row = lane; row < R; row += CC_WARP)
         {
             const size_t cell = base + row;
             const float4 q = p.pos[cell];
-            const unsigned char label = s[row].label;
+            const unsigned short lab = s_lab[row];
+            const unsigned char label = static_cast<unsigned char>(lab & 0xff);
+            const float gap = s[row].gap;
             bool ignored = false;
             if (cc_isnan(q.w))
                 ignored = true;
@@ -1509,7 +1781,7 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
                 ignored = true;
             else if (q.w < cfg.max_distance)
                 ignored = true;
-            else if (cfg.incl_rule && row < R - 1 && ccm::atan2f_glibc(cfg.max_distance, q.w) < s[row].gap)
+            else if (cfg.incl_rule && row < R - 1 && ccm::atan2f_glibc(cfg.max_distance, q.w) < gap)
                 ignored = true;
             else if (cfg.chessboard)
             {
@@ -1517,12 +1789,13 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
                 if (column_even != row_even)
                     ignored = true;
             }
+            const float incl = s_incl[row];
             double caz;
-            if (s[row].cls == 0)
+            if (s_cls[row] == 0)
             {
                 caz = (static_cast<double>(gcol) + 0.5) * static_cast<double>(cfg.width); // cpp:371-372
                 p.cont_az[cell] = caz;
-                p.incl[cell] = s[row].incl;
+                p.incl[cell] = incl;
             }
             else
                 caz = p.cont_az[cell];
@@ -1530,10 +1803,10 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
                 min_az = caz;
             uchar4 l = p.lab[cell];
             l.x = label;
-            l.y = s[row].dbg;
+            l.y = static_cast<unsigned char>(lab >> 8);
             l.z = ignored ? 1 : 0;
             p.lab[cell] = l;
-            p.assoc[cell] = make_float4(ignored ? nanv : q.x, q.y, q.z, s[row].incl);
+            p.assoc[cell] = make_float4(ignored ? nanv : q.x, q.y, q.z, incl);
             p.mad[cell] = ignored ? 0.f : ccm::asinf_glibc(ccm::div_rn(cfg.max_distance, q.w));
         }
         min_az = cc_warp_min_f64(min_az);
@@ -1545,32 +1818,31 @@ __global__ void k_ground(CcDevCfg cfg, CcDevPtrs p)
         }
         __syncwarp();
     }
-}
 
-// =====================================================================================================
-// K2c  running maximum of the columns' minimum azimuth (the value every finish pass compares against,
-//      cpp:884-885), continued across pushes. Single block, chunked scan.
-// =====================================================================================================
-__device__ void d_snapshot(CcDevPtrs p, int spec);
-
-__global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
-{
-    if (p.st->halted)
-        return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    CC_SMEM(smem);
-    double* part = reinterpret_cast<double*>(smem);
-    if (blockIdx.x != 0)
+    // ---- running maximum of the columns' minimum azimuth (the value every finish pass compares against,
+    //      cpp:884-885), continued across pushes: done by whichever block finishes last ----
+    __shared__ int sh_last;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        const int ticket = atomicAdd(&p.st->ticket_ground, 1);
+        sh_last = ticket == static_cast<int>(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (!sh_last)
         return;
-    if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts)
-        d_snapshot(p, 1);
-    const int ncols = p.st->ncols;
+    __threadfence();
+    if (threadIdx.x == 0)
+        p.st->ticket_ground = 0;
+    double* part = reinterpret_cast<double*>(smem);
     const int T = blockDim.x, t = threadIdx.x;
     const int chunk = (ncols + T - 1) / T;
     const int lo = t * chunk, hi = (lo + chunk < ncols) ? lo + chunk : ncols;
     double m = -1.0;
     for (int ci = lo; ci < hi; ci++)
     {
-        const double v = p.col_minaz[ci];
+        const double v = cc_ldcg_f64(p.col_minaz + ci);
         m = v > m ? v : m;
     }
     double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
@@ -1578,13 +1850,13 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
     pre = carry > pre ? carry : pre;
     for (int ci = lo; ci < hi; ci++)
     {
-        const double v = p.col_minaz[ci];
+        const double v = cc_ldcg_f64(p.col_minaz + ci);
         pre = v > pre ? v : pre;
         p.col_runmax[ci] = pre;
     }
 }
 
-
+__device__ void d_snapshot(CcDevPtrs p, int spec);
 
 // =====================================================================================================
 // K3a  association probe (cpp:698-835): every non-ignored cell of the new columns walks its field of view and
@@ -1594,10 +1866,13 @@ __global__ void k_runmax(CcDevCfg cfg, CcDevPtrs p, int do_snapshot)
 //      seen before this column, or its tree is already finished -- flags the column for the column-sequential
 //      exact path. No persistent state is modified here.
 // =====================================================================================================
-__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem)
+__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem,
+                        int do_snapshot)
 {
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts); the probe itself
+        d_snapshot(p, 0); // modifies no persistent state
     CC_SMEM(smem);
     const int R = cfg.R;
     int* plist_n = reinterpret_cast<int*>(smem);          // [0] points in the list, [1] next point to take
@@ -1933,32 +2208,62 @@ __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_p
         ci1 = p.st->ncols - 1;
     const long long colbase = p.st->colbase;
     const int total = (ci1 - ci0 + 1) * R;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x % CC_WARP;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    // warps stay converged: the new roots of a warp's cells take their places in the unfinished list with one atomic
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x)
     {
-        const int ci = ci0 + i / R, row = i % R;
-        const long long gcol = colbase + ci;
-        const unsigned int q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
-        const unsigned int par = s_parent[static_cast<size_t>(ci) * R + row];
-        p.tparent[q] = par;
-        if (par == q) // new point tree (cpp:808-826)
+        const int i = i0 + lane;
+        bool is_root = false;
+        unsigned int q = 0u;
+        if (i < total)
         {
-            p.cparent[q] = q;
-            p.tfinish[q] = cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q]));
-            p.tmaxcol[q] = gcol;
-            p.tnpoints[q] = 1;
-            p.tstate[q] = 0;
-            p.tid[q] = 0;
-            p.tslot[q] = -1;
-            const int pos = atomicAdd(&p.st->n_ulist, 1);
-            if (pos < p.cap_ulist)
+            const int ci = ci0 + i / R, row = i % R;
+            const long long gcol = colbase + ci;
+            q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+            const unsigned int par = s_parent[static_cast<size_t>(ci) * R + row];
+            p.tparent[q] = par;
+            if (par == q) // new point tree (cpp:808-826)
             {
-                p.ulist[pos] = q;
-                p.rootslot[q] = static_cast<unsigned int>(pos);
+                is_root = true;
+                p.cparent[q] = q;
+                p.tfinish[q] = cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q]));
+                p.tmaxcol[q] = gcol;
+                p.tnpoints[q] = 1;
+                p.tstate[q] = 0;
+                p.tid[q] = 0;
+                p.tslot[q] = -1;
             }
-            else
-                p.st->error = CC_DEV_LIST_OVERFLOW;
+        }
+        const unsigned int roots = __ballot_sync(CC_FULL_MASK, is_root);
+        if (roots)
+        {
+            int pos0 = 0;
+            if (lane == __ffs(roots) - 1)
+                pos0 = atomicAdd(&p.st->n_ulist, __popc(roots));
+            pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(roots) - 1);
+            if (is_root)
+            {
+                const int pos = pos0 + __popc(roots & lt_mask);
+                if (pos < p.cap_ulist)
+                {
+                    p.ulist[pos] = q;
+                    p.rootslot[q] = static_cast<unsigned int>(pos);
+                }
+                else
+                    p.st->error = CC_DEV_LIST_OVERFLOW;
+            }
         }
     }
+}
+
+// 64-bit maximum over the lanes of `grp` (all lanes of the warp call this; lanes outside the group pass anything)
+CC_DEV unsigned long long cc_group_max_u64(bool mine, unsigned long long v)
+{
+    const unsigned int hi = __reduce_max_sync(CC_FULL_MASK, mine ? static_cast<unsigned int>(v >> 32) : 0u);
+    const bool top = mine && static_cast<unsigned int>(v >> 32) == hi;
+    const unsigned int lo = __reduce_max_sync(CC_FULL_MASK, top ? static_cast<unsigned int>(v) : 0u);
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
 __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
@@ -1972,21 +2277,49 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
         ci1 = p.st->ncols - 1;
     const long long colbase = p.st->colbase;
     const int total = (ci1 - ci0 + 1) * R;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x % CC_WARP;
+    // warps stay converged: the contributions of a warp's cells to one root (cells of one object in neighbouring rows
+    // mostly share it) are combined before they touch the root's words in memory
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x)
     {
-        const int ci = ci0 + i / R, row = i % R;
-        const long long gcol = colbase + ci;
-        const unsigned int q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
-        unsigned int r = cc_vload(p.tparent + q);
-        if (r == CC_NONE || r == q)
-            continue;
-        unsigned int n;
-        while ((n = cc_vload(p.tparent + r)) != r)
-            r = n;
-        p.tparent[q] = r;
-        atomicMax(p.tfinish + r, cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q])));
-        atomicMax(p.tmaxcol + r, gcol);
-        atomicAdd(p.tnpoints + r, 1u);
+        const int i = i0 + lane;
+        unsigned int r = CC_NONE;
+        unsigned long long fin = 0ull;
+        int ci = 0;
+        if (i < total)
+        {
+            ci = ci0 + i / R;
+            const int row = i % R;
+            const unsigned int q = static_cast<unsigned int>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
+            r = cc_vload(p.tparent + q);
+            if (r == q)
+                r = CC_NONE; // a root contributes nothing to itself
+            if (r != CC_NONE)
+            {
+                unsigned int n;
+                while ((n = cc_vload(p.tparent + r)) != r)
+                    r = n;
+                p.tparent[q] = r;
+                fin = cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q]));
+            }
+        }
+        unsigned int remaining = __ballot_sync(CC_FULL_MASK, r != CC_NONE);
+        while (remaining)
+        {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned int key = __shfl_sync(CC_FULL_MASK, r, leader);
+            const bool mine = r == key;
+            const unsigned int grp = __ballot_sync(CC_FULL_MASK, mine);
+            const unsigned long long gfin = cc_group_max_u64(mine, fin);
+            const int gci = cc_warp_max(mine ? ci : -0x7fffffff - 1);
+            if (lane == leader)
+            {
+                atomicMax(p.tfinish + key, gfin);
+                atomicMax(p.tmaxcol + key, colbase + gci);
+                atomicAdd(p.tnpoints + key, static_cast<unsigned int>(__popc(grp)));
+            }
+            remaining &= ~grp;
+        }
     }
 }
 
@@ -2439,16 +2772,28 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec, int smem_ints
 }
 
 __device__ void d_push_done(CcDevPtrs p, int guard);
+CC_DEV void d_state_snapshot(CcDevPtrs p, CcDevState* dst)
+{
+    const int n = static_cast<int>(sizeof(CcDevState) / sizeof(int));
+    const int* src = reinterpret_cast<const int*>(p.st);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        d[i] = src[i];
+}
 
 // All list-sized phases of a finish pass in ONE CTA (the unfinished-tree list holds 10^2..10^4 entries: a single
 // CTA with block-wide barriers between the phases is faster than six dependent launches).
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
-                                                  int exact, int last, int smem_bytes)
+                                                  int exact, int last, int smem_bytes, CcDevState* snap)
 {
-    if (p.st->halted)
-        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (blockIdx.x != 0)
         return;
+    if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
+    {
+        if (snap)
+            d_state_snapshot(p, snap);
+        return;
+    }
     CC_SMEM(smem);
     d_fin_init(cfg, p, ci0, ci1, guard);
     __syncthreads();
@@ -2480,6 +2825,11 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
     __syncthreads();
     if (last && threadIdx.x == 0)
         d_push_done(p, guard);
+    if (snap) // copy of the stream state at the end of the push (what the host reads while the next push already runs)
+    {
+        __syncthreads();
+        d_state_snapshot(p, snap);
+    }
 }
 
 // Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
@@ -2494,35 +2844,68 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
     const int R = cfg.R;
     const long long gbase = st->gbase, c1 = st->seg_c1;
     const long long total = (c1 - gbase + 1) * R;
-    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    const int lane = threadIdx.x % CC_WARP;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    // warps stay converged: the members of one cluster among a warp's cells reserve their slots in the cluster's point
+    // list and update its stamp range with one atomic each
+    for (long long i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += static_cast<long long>(gridDim.x) * blockDim.x)
     {
-        const long long gcol = gbase + i / R;
-        const int row = static_cast<int>(i % R);
-        const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
-        if (p.slot_gcol[cell / R] != gcol)
-            continue;
-        const unsigned int root = p.tparent[cell];
-        if (root == CC_NONE)
-            continue;
-        if (p.tstate[root] != 1u + seq)
-            continue;
-        const int slot = p.tslot[root];
-        if (slot < 0)
-            continue;
-        p.cid[cell] = p.tid[root];
-        CcCluster* c = p.clusters + slot;
-        const unsigned int pos = atomicAdd(&c->cursor, 1u);
-        if (pos < c->num_points)
+        const long long i = i0 + lane;
+        int slot = -1;
+        long long gcol = 0;
+        int row = 0;
+        unsigned long long stamp = 0ull;
+        if (i < total)
         {
-            CcClusterPoint cp;
-            cp.gcol = gcol;
-            cp.row = row;
-            cp.pad_ = 0;
-            p.cluster_points[c->point_offset + pos] = cp;
+            gcol = gbase + i / R;
+            row = static_cast<int>(i % R);
+            const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+            if (p.slot_gcol[cell / R] == gcol)
+            {
+                const unsigned int root = p.tparent[cell];
+                if (root != CC_NONE && p.tstate[root] == 1u + seq)
+                {
+                    slot = p.tslot[root];
+                    if (slot >= 0)
+                    {
+                        p.cid[cell] = p.tid[root];
+                        stamp = p.stamp[cell];
+                    }
+                }
+            }
         }
-        const unsigned long long stamp = p.stamp[cell];
-        atomicMin(&c->min_stamp, stamp);
-        atomicMax(&c->max_stamp, stamp);
+        unsigned int remaining = __ballot_sync(CC_FULL_MASK, slot >= 0);
+        while (remaining)
+        {
+            const int leader = __ffs(remaining) - 1;
+            const int key = __shfl_sync(CC_FULL_MASK, slot, leader);
+            const bool mine = slot == key;
+            const unsigned int grp = __ballot_sync(CC_FULL_MASK, mine);
+            const unsigned long long smax = cc_group_max_u64(mine, stamp);
+            const unsigned long long smin = ~cc_group_max_u64(mine, ~stamp);
+            CcCluster* c = p.clusters + key;
+            unsigned int pos0 = 0u;
+            if (lane == leader)
+            {
+                pos0 = atomicAdd(&c->cursor, static_cast<unsigned int>(__popc(grp)));
+                atomicMin(&c->min_stamp, smin);
+                atomicMax(&c->max_stamp, smax);
+            }
+            pos0 = __shfl_sync(CC_FULL_MASK, pos0, leader);
+            if (mine)
+            {
+                const unsigned int pos = pos0 + static_cast<unsigned int>(__popc(grp & lt_mask));
+                if (pos < c->num_points)
+                {
+                    CcClusterPoint cp;
+                    cp.gcol = gcol;
+                    cp.row = row;
+                    cp.pad_ = 0;
+                    p.cluster_points[c->point_offset + pos] = cp;
+                }
+            }
+            remaining &= ~grp;
+        }
     }
 }
 
@@ -2629,11 +3012,7 @@ __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_co
 // copy of the stream state at the end of a push (what the host reads while the next push already runs)
 __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
 {
-    const int n = static_cast<int>(sizeof(CcDevState) / sizeof(int));
-    const int* src = reinterpret_cast<const int*>(p.st);
-    int* d = reinterpret_cast<int*>(dst);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        d[i] = src[i];
+    d_state_snapshot(p, dst);
 }
 
 // ---- device math self-test (bit equality with the host libm) ----

@@ -103,6 +103,8 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     int scan_kbad;            // firings [0, scan_kbad) were resolved by the lite insertion path
     long long scan_lite_base; // column the lite arrays are relative to
     int scan_lite_firings;
+    int ticket_gap;    // same for k_gap_scan (the last block chains the column chunks)
+    int ticket_ground; // blocks of k_ground that are done (the last one computes the running maxima); 0 between launches
     int halted; // set when a push could not be committed speculatively: later pushes in flight skip themselves
 };
 
@@ -182,9 +184,12 @@ struct CcDevPtrs
     int* lite_U;                // [max_firings] unwrapped anchor column, relative to scan_lite_base
     int* lite_P;                // [max_firings + 1] rearmost column so far before firing k
     int* lite_F;                // [max_firings + 1] foremost column so far before firing k
+    int* lite_rowfront;         // [R] last stored column of the row within the lite prefix (INT_MIN none)
     // ---- per new column (maxcols) ----
     int* col_trigger;     // firing (index in this push) whose insertion completed the column (hpp:169-173)
     float* col_gap;       // [maxcols * R] value of sc_inclination_angles_between_lasers_ when the column is segmented
+    float* gap_chunk_last;  // [maxcols / CC_GAP_CHUNK + 1][R] last valid value inside a chunk of columns
+    float* gap_chunk_carry; // same shape: value carried into the chunk
     double* col_minaz;    // current_minimum_continuous_azimuth_angle (cpp:777, 791-793)
     double* col_runmax;   // running max of col_minaz including earlier pushes
     long long* col_first_unpub; // sc_first_unpublished_global_column_index after the column's pass

@@ -104,6 +104,14 @@ static inline int __reduce_max_sync(unsigned, int v)
 {
     return v;
 }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+    return v;
+}
+static inline int __clz(int v)
+{
+    return v ? __builtin_clz(static_cast<unsigned>(v)) : 32;
+}
 static inline int __reduce_or_sync(unsigned, int v)
 {
     return v;
