@@ -16,6 +16,7 @@
 #define CC_KERNELS_CUH
 
 #include <math.h>
+#include <string.h>
 
 #ifndef CC_EMU
 #include <cuda_pipeline.h>
@@ -113,22 +114,56 @@ struct CcOpMaxI64
 {
     CC_DEV long long operator()(long long a, long long b) const { return a > b ? a : b; }
 };
+template<typename T>
+CC_DEV T cc_shfl_up_any(T v, int off) // shuffle of a plain struct, word by word
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized types only");
+    unsigned int w[sizeof(T) / 4];
+    memcpy(w, &v, sizeof(T));
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(T) / 4); i++)
+        w[i] = __shfl_up_sync(CC_FULL_MASK, w[i], off);
+    memcpy(&v, w, sizeof(T));
+    return v;
+}
+// Two-level: shuffle scan inside every warp, the warp totals scanned by warp 0 (two block barriers in all; the block
+// has at most 32 warps). `sm` needs room for one T per warp. op(identity, x) == x and op(x, identity) == x.
 template<typename T, typename Op>
 CC_DEV T cc_block_exclusive_scan(T* sm, T v, T identity, Op op)
 {
-    const int t = threadIdx.x, n = blockDim.x;
-    sm[t] = v;
-    __syncthreads();
-    for (int off = 1; off < n; off <<= 1)
+    const int t = threadIdx.x, lane = t % CC_WARP, warp = t / CC_WARP;
+    const int nw = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    T x = v;
+    for (int off = 1; off < CC_WARP; off <<= 1)
     {
-        T x = sm[t];
-        if (t >= off)
-            x = op(sm[t - off], x);
-        __syncthreads();
-        sm[t] = x;
-        __syncthreads();
+        const T y = cc_shfl_up_any(x, off);
+        if (lane >= off)
+            x = op(y, x);
     }
-    const T excl = t > 0 ? sm[t - 1] : identity;
+    if (lane == CC_WARP - 1)
+        sm[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+        T xi = lane < nw ? sm[lane] : identity;
+        for (int off = 1; off < CC_WARP; off <<= 1)
+        {
+            const T y = cc_shfl_up_any(xi, off);
+            if (lane >= off)
+                xi = op(y, xi);
+        }
+        T ex = cc_shfl_up_any(xi, 1);
+        if (lane == 0)
+            ex = identity;
+        if (lane < nw)
+            sm[lane] = ex;
+    }
+    __syncthreads();
+    const T warp_prefix = sm[warp];
+    T e = cc_shfl_up_any(x, 1);
+    if (lane == 0)
+        e = identity;
+    const T excl = op(warp_prefix, e);
     __syncthreads();
     return excl;
 }
@@ -153,6 +188,7 @@ CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/
 
 __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
@@ -278,8 +314,15 @@ struct CcOpMaxPair
     }
 };
 
+#ifdef CC_EMU
+#define CC_LITE_PER 8192 /* the emulation runs the block as one thread */
+#else
+#define CC_LITE_PER 8 /* firings per thread of k_scan_lite: 8192 firings per push with 1024 threads */
+#endif
+
 __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
 {
+    CC_PDL_ENTER();
     if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
@@ -292,10 +335,11 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     const int N = cfg.N, half = cfg.half;
     const int NOT_SET = -0x7fffffff - 1;
     const long long base = st->P;
-    const bool ok = st->F >= 0 && st->foremost >= 0 && base > 0 && st->ring_start != -1;
+    const bool ok_state = st->F >= 0 && st->foremost >= 0 && base > 0 && st->ring_start != -1;
     const int pc0 = static_cast<int>(base % N);
     const int Fm0 = static_cast<int>(st->foremost - base);
     const int colbase_rel = static_cast<int>(st->F - base);
+    const bool ok = ok_state && (n + T - 1) / T <= CC_LITE_PER;
     if (t == 0)
         sh_kbad = ok ? n : 0;
     __syncthreads();
@@ -311,29 +355,43 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     const int per = (n + T - 1) / T;
     const int a = t * per < n ? t * per : n, b = (a + per < n) ? a + per : n;
     int kbad = n;
+    // every thread keeps its (at most CC_LITE_PER) firings in registers across the three passes: one batch of loads, one
+    // batch of stores
+    CcFiringSummary fs[CC_LITE_PER];
+    int U[CC_LITE_PER], lP[CC_LITE_PER], lF[CC_LITE_PER];
+#pragma unroll
+    for (int u = 0; u < CC_LITE_PER; u++)
+    {
+        fs[u].anchor = fs[u].rear_rel = fs[u].fore_rel = fs[u].nvalid = 0;
+        if (a + u < b)
+            fs[u] = p.lite_sum[a + u];
+    }
     // pass 1: anchor columns relative to the thread's first valid firing
     CcAnchorSeg mine;
     mine.has = 0;
     mine.first_cw = 0;
     mine.last_cw = 0;
     mine.off = 0;
-    for (int k = a; k < b; k++)
+#pragma unroll
+    for (int u = 0; u < CC_LITE_PER; u++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
-        if (fs.nvalid < 0)
-            kbad = k < kbad ? k : kbad;
-        if (fs.nvalid > 0)
+        if (a + u < b)
         {
-            if (!mine.has)
+            if (fs[u].nvalid < 0)
+                kbad = a + u < kbad ? a + u : kbad;
+            if (fs[u].nvalid > 0)
             {
-                mine.has = 1;
-                mine.first_cw = fs.anchor;
+                if (!mine.has)
+                {
+                    mine.has = 1;
+                    mine.first_cw = fs[u].anchor;
+                }
+                else
+                    mine.off += cc_wrapdiff(fs[u].anchor - mine.last_cw, N);
+                mine.last_cw = fs[u].anchor;
             }
-            else
-                mine.off += cc_wrapdiff(fs.anchor - mine.last_cw, N);
-            mine.last_cw = fs.anchor;
         }
-        p.lite_U[k] = mine.off;
+        U[u] = mine.off;
     }
     CcAnchorSeg ident;
     ident.has = 0;
@@ -364,18 +422,17 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     CcMaxPair run;
     run.p = NOT_SET;
     run.f = NOT_SET;
-    for (int k = a; k < b; k++)
+#pragma unroll
+    for (int u = 0; u < CC_LITE_PER; u++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
-        p.lite_P[k] = run.p;
-        p.lite_F[k] = run.f;
-        if (fs.nvalid > 0)
+        lP[u] = run.p;
+        lF[u] = run.f;
+        if (a + u < b && fs[u].nvalid > 0)
         {
-            const int U = mybase + p.lite_U[k];
-            p.lite_U[k] = U;
-            const int rear = U + fs.rear_rel, fore = U + fs.fore_rel;
+            U[u] = mybase + U[u];
+            const int rear = U[u] + fs[u].rear_rel, fore = U[u] + fs[u].fore_rel;
             if (fore - rear > N / 2) // cpp:252-261
-                kbad = k < kbad ? k : kbad;
+                kbad = a + u < kbad ? a + u : kbad;
             run.p = rear > run.p ? rear : run.p;
             run.f = fore > run.f ? fore : run.f;
         }
@@ -386,22 +443,25 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     CcMaxPair pre = cc_block_exclusive_scan(sm_max, run, seed, CcOpMaxPair());
     pre = CcOpMaxPair()(pre, seed);
     // pass 3: rearmost / foremost so far before every firing; unwrap margins
-    for (int k = a; k < b; k++)
+#pragma unroll
+    for (int u = 0; u < CC_LITE_PER; u++)
     {
-        const CcFiringSummary fs = p.lite_sum[k];
-        const int lp = p.lite_P[k], lf = p.lite_F[k];
-        const int Pk = lp > pre.p ? lp : pre.p, Fk = lf > pre.f ? lf : pre.f;
-        p.lite_P[k] = Pk;
-        p.lite_F[k] = Fk;
-        if (fs.nvalid > 0)
+        if (a + u < b)
         {
-            const int U = p.lite_U[k];
-            const int rear = U + fs.rear_rel, fore = U + fs.fore_rel;
-            if (!(rear - Pk > -half && fore - Pk < half))
-                kbad = k < kbad ? k : kbad; // the unwrap of some point could differ from the reference's
-            const int Pnext = rear > Pk ? rear : Pk;
-            if (Pnext - colbase_rel > p.maxcols)
-                kbad = k < kbad ? k : kbad; // the per-firing path raises the error
+            const int k = a + u;
+            const int Pk = lP[u] > pre.p ? lP[u] : pre.p, Fk = lF[u] > pre.f ? lF[u] : pre.f;
+            p.lite_P[k] = Pk;
+            p.lite_F[k] = Fk;
+            p.lite_U[k] = U[u];
+            if (fs[u].nvalid > 0)
+            {
+                const int rear = U[u] + fs[u].rear_rel, fore = U[u] + fs[u].fore_rel;
+                if (!(rear - Pk > -half && fore - Pk < half))
+                    kbad = k < kbad ? k : kbad; // the unwrap of some point could differ from the reference's
+                const int Pnext = rear > Pk ? rear : Pk;
+                if (Pnext - colbase_rel > p.maxcols)
+                    kbad = k < kbad ? k : kbad; // the per-firing path raises the error
+            }
         }
     }
     if (a < n && b == n)
@@ -426,6 +486,7 @@ struct CcOpLastSetI32
 
 __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
@@ -444,22 +505,41 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
     __shared__ int sh_front;
     if (t == 0)
         sh_front = NOT_SET;
-    for (int k = a; k < b; k++)
+    for (int kb = a; kb < b; kb += 8) // loads of 8 firings issued together
     {
-        const int cw = p.s_cwr[k * R + row];
-        if (cw == CC_INVALID_CWR)
-            continue;
-        const int g = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, N);
-        if (first == NOT_SET)
+        int cw[8], U[8], an[8], P[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
         {
-            first = g;
-            firstk = k;
+            const int k = kb + u;
+            cw[u] = CC_INVALID_CWR;
+            U[u] = an[u] = P[u] = 0;
+            if (k < b)
+            {
+                cw[u] = p.s_cwr[k * R + row];
+                U[u] = p.lite_U[k];
+                an[u] = p.lite_sum[k].anchor;
+                P[u] = p.lite_P[k];
+            }
         }
-        else if (g <= last)
-            kbad = k < kbad ? k : kbad;
-        last = g;
-        if (g >= p.lite_P[k]) // stored (not too far behind, cpp:210-221): candidate for the row's new front
-            gmax = g > gmax ? g : gmax;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+        {
+            const int k = kb + u;
+            if (cw[u] == CC_INVALID_CWR)
+                continue;
+            const int g = U[u] + cc_wrapdiff(cw[u] - an[u], N);
+            if (first == NOT_SET)
+            {
+                first = g;
+                firstk = k;
+            }
+            else if (g <= last)
+                kbad = k < kbad ? k : kbad;
+            last = g;
+            if (g >= P[u]) // stored (not too far behind, cpp:210-221): candidate for the row's new front
+                gmax = g > gmax ? g : gmax;
+        }
     }
     int prev = cc_block_exclusive_scan(sm, last, NOT_SET, CcOpLastSetI32());
     if (prev == NOT_SET)
@@ -506,6 +586,7 @@ struct CcScanState // uniform across the CTA, kept in registers by every thread
 
 __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
 {
+    CC_PDL_ENTER();
     if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
@@ -1183,6 +1264,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
 // =====================================================================================================
 __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
@@ -1273,6 +1355,7 @@ CC_DEV float cc_ldcg_f32(const float* q)
 
 __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int R = cfg.R;
@@ -1446,6 +1529,7 @@ CC_DEV bool cc_slope_below(float y, float x, float m)
 
 __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
@@ -1835,24 +1919,45 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
     __threadfence();
     if (threadIdx.x == 0)
         p.st->ticket_ground = 0;
+    // tiles of 2048 columns staged in shared memory with independent coalesced loads; every thread scans a contiguous
+    // segment of the tile, the segments are chained by a block scan
+    __shared__ double sh_az[2048];
     double* part = reinterpret_cast<double*>(smem);
     const int T = blockDim.x, t = threadIdx.x;
-    const int chunk = (ncols + T - 1) / T;
-    const int lo = t * chunk, hi = (lo + chunk < ncols) ? lo + chunk : ncols;
-    double m = -1.0;
-    for (int ci = lo; ci < hi; ci++)
+    double carry = p.st->runmax_carry;
+    for (int c0 = 0; c0 < ncols; c0 += 2048)
     {
-        const double v = cc_ldcg_f64(p.col_minaz + ci);
-        m = v > m ? v : m;
-    }
-    double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
-    const double carry = p.st->runmax_carry;
-    pre = carry > pre ? carry : pre;
-    for (int ci = lo; ci < hi; ci++)
-    {
-        const double v = cc_ldcg_f64(p.col_minaz + ci);
-        pre = v > pre ? v : pre;
-        p.col_runmax[ci] = pre;
+        const int n = (ncols - c0) < 2048 ? (ncols - c0) : 2048;
+        for (int i0 = 0; i0 < n; i0 += 8 * T)
+        {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                v[u] = i0 + u * T + t < n ? cc_ldcg_f64(p.col_minaz + c0 + i0 + u * T + t) : -1.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u * T + t < n)
+                    sh_az[i0 + u * T + t] = v[u];
+        }
+        __syncthreads();
+        const int seg = ((n + T - 1) / T) | 1; // odd: the threads' segments start in different banks
+        const int lo = t * seg < n ? t * seg : n, hi = (lo + seg < n) ? lo + seg : n;
+        double m = -1.0;
+        for (int i = lo; i < hi; i++)
+            m = sh_az[i] > m ? sh_az[i] : m;
+        double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
+        pre = carry > pre ? carry : pre;
+        for (int i = lo; i < hi; i++)
+        {
+            const double v = sh_az[i];
+            pre = v > pre ? v : pre;
+            sh_az[i] = pre;
+        }
+        __syncthreads();
+        carry = sh_az[n - 1];
+        for (int i = t; i < n; i += T)
+            p.col_runmax[c0 + i] = sh_az[i];
+        __syncthreads();
     }
 }
 
@@ -1869,6 +1974,7 @@ __device__ void d_snapshot(CcDevPtrs p, int spec);
 __global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem,
                         int do_snapshot)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts); the probe itself
@@ -2171,6 +2277,7 @@ __device__ void d_snapshot(CcDevPtrs p, int spec)
 
 __global__ void k_snapshot(CcDevPtrs p, int guard)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     d_snapshot(p, guard);
@@ -2178,6 +2285,7 @@ __global__ void k_snapshot(CcDevPtrs p, int guard)
 
 __global__ void k_restore(CcDevPtrs p)
 {
+    CC_PDL_ENTER();
     const int n = p.st->n_ulist_saved;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
@@ -2191,6 +2299,7 @@ __global__ void k_restore(CcDevPtrs p)
 
 __global__ void k_restore_finish(CcDevPtrs p)
 {
+    CC_PDL_ENTER();
     p.st->n_ulist = p.st->n_ulist_saved;
     p.st->abort = 0;
     p.st->n_clusters = p.st->sv_n_clusters;
@@ -2199,6 +2308,7 @@ __global__ void k_restore_finish(CcDevPtrs p)
 
 __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2268,6 +2378,7 @@ CC_DEV unsigned long long cc_group_max_u64(bool mine, unsigned long long v)
 
 __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2326,6 +2437,7 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
 __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
                                int ci0, int ci1, int spec)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2376,6 +2488,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
 // =====================================================================================================
 __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
 {
+    CC_PDL_ENTER();
     if (blockIdx.x != 0 || threadIdx.x != 0)
         return;
     const int R = cfg.R;
@@ -2786,6 +2899,7 @@ CC_DEV void d_state_snapshot(CcDevPtrs p, CcDevState* dst)
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
                                                   int exact, int last, int smem_bytes, CcDevState* snap)
 {
+    CC_PDL_ENTER();
     if (blockIdx.x != 0)
         return;
     if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -2836,6 +2950,7 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 // host needs for the finished-cluster callback (cpp:1007-1028).
 __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
+    CC_PDL_ENTER();
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2918,6 +3033,7 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 // before clearColumns runs, cpp:1087-1091).
 __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
 {
+    CC_PDL_ENTER();
     CcDevState* st = p.st;
     if (mode)
     {
@@ -2962,6 +3078,7 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
 __device__ void d_push_done(CcDevPtrs p, int guard);
 __global__ void k_push_done(CcDevPtrs p, int guard)
 {
+    CC_PDL_ENTER();
     d_push_done(p, guard);
 }
 __device__ void d_push_done(CcDevPtrs p, int guard)
@@ -2982,6 +3099,7 @@ __device__ void d_push_done(CcDevPtrs p, int guard)
 // columns (finish passes only every n-th column: always column-sequential); -1: clear the flag
 __global__ void k_halt(CcDevPtrs p, int mode)
 {
+    CC_PDL_ENTER();
     CcDevState* st = p.st;
     if (mode < 0)
         st->halted = 0;
@@ -2993,6 +3111,7 @@ __global__ void k_halt(CcDevPtrs p, int mode)
 // device->host copy next to the other results of the push (cc_set_label_prefetch)
 __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
 {
+    CC_PDL_ENTER();
     const CcDevState* st = p.st;
     if (st->halted)
         return;
@@ -3012,12 +3131,14 @@ __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_co
 // copy of the stream state at the end of a push (what the host reads while the next push already runs)
 __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
 {
+    CC_PDL_ENTER();
     d_state_snapshot(p, dst);
 }
 
 // ---- device math self-test (bit equality with the host libm) ----
 __global__ void k_selftest_math(int op, int n, const float* a, const float* b, float* out)
 {
+    CC_PDL_ENTER();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         if (op == 0)

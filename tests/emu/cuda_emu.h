@@ -14,6 +14,7 @@
 #include <cstring>
 
 #define CC_WARP 1
+#define CC_PDL_ENTER() do { } while (0)
 #define CC_FULL_MASK 0x1u
 #define __global__
 #define __device__
