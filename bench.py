@@ -259,6 +259,9 @@ def main():
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    def l2_flush(tag):
+        flush_buf.fill_(tag & 0xFF)
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -298,7 +301,7 @@ def main():
     def flush_and_submit(s):
         with torch.cuda.stream(stream):
             ev_fa[s].record(stream)
-            flush_buf.fill_(s & 0xFF)
+            l2_flush(s)
             ev_fb[s].record(stream)
         submit_dev(W + s)
 
@@ -349,7 +352,7 @@ def main():
         d_extra_poses = torch.from_numpy(extra_poses).cuda()
         for r in range(reps):
             with torch.cuda.stream(stream):
-                flush_buf.fill_(r)
+                l2_flush(r)
             res = cc.addFiringsDevice(d_extra.data_ptr() + r * B * rec_bytes, d_extra_poses.data_ptr() + r * B * pose_bytes, B, R)
             ncols = int(res.info.ground_to_gcol - res.info.ground_from_gcol)
             for name, ms in cc.kernel_timings():

@@ -354,6 +354,20 @@ class ContinuousClustering:
         parts = names.value.decode().split(";")[: n.value]
         return [(parts[i], float(ms[i])) for i in range(n.value)]
 
+    def debug_trace(self, enable: bool):
+        """Device-side timeline of the kernels as they overlap in a normal push (cc_debug_trace)."""
+        self._check(self._L.cc_debug_trace(self._h, int(enable)))
+
+    def get_trace(self):
+        """[(kernel, first block entry ns, last block exit ns, longest block ns, blocks)] since the last call."""
+        names = C.create_string_buffer(4096)
+        out = (C.c_uint64 * (4 * 64))()
+        n = C.c_int(0)
+        self._check(self._L.cc_debug_get_trace(self._h, names, 4096, out, 64, C.byref(n)))
+        parts = names.value.decode().split(";")
+        return [(parts[i], int(out[4 * i]), int(out[4 * i + 1]), int(out[4 * i + 2]), int(out[4 * i + 3]))
+                for i in range(n.value) if out[4 * i + 3]]
+
     @property
     def total_launches(self) -> int:
         return int(self._L.cc_total_launches(self._h))

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,9 @@ struct cc_handle
     int maxcols{0};
     int gap_rows{-1};
     int debug_flag_period{0};
+    unsigned long long* d_trace{nullptr}; // device-side timeline buffer (cc_debug_trace)
+    bool trace_on{false};
+    int tune{0}; // profiling aid: CC_B200_TUNE environment variable (bit 0: cooperative probe walk without masks)
     bool label_prefetch{false};
     const uchar4* cur_labels{nullptr}; // labels of the last finished push (pinned slot buffer)
     int cur_label_cols{0};
@@ -98,6 +102,7 @@ struct cc_handle
     uint64_t launches{0};
     uint64_t launches_at_push_start{0};
     int sm_count{148};
+    int occ_probe{8}, occ_probe_heavy{8}; // resident CTAs per SM of the two association kernels
     // results of the last push
     cc_batch_info_t info{};
     std::vector<cc_column_event_t> events;
@@ -291,6 +296,8 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     if (max_firings_per_push > 0)
         h->max_firings = std::min(max_firings_per_push, 8192); // per-firing scan arrays must fit one CTA's shared memory
     cc_config_default(&h->config);
+    if (const char* t = std::getenv("CC_B200_TUNE"))
+        h->tune = std::atoi(t);
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -314,6 +321,13 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
         h->sm_count = prop.multiProcessorCount;
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe, 256, 0) == cudaSuccess && nb > 0)
+            h->occ_probe = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4)) == cudaSuccess && nb > 0)
+            h->occ_probe_heavy = nb;
+    }
 #endif
     *out = h;
     return CC_OK;
@@ -346,6 +360,8 @@ void cc_destroy(cc_handle_t* h)
         cudaStreamDestroy(h->aux_stream);
     if (h->h_state)
         cudaFreeHost(h->h_state);
+    if (h->d_trace)
+        cudaFree(h->d_trace);
     if (h->ev0)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
@@ -520,6 +536,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.s_incl, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incaz, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_MAX_CHUNK) * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_cwrT, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_rot, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.firing_rec, static_cast<size_t>(h->max_firings)));
@@ -536,6 +553,8 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.col_minaz, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_runmax, mc));
         CC_CHECK(h, dev_alloc(h, L, &d.col_flag, mc));
+        CC_CHECK(h, dev_alloc(h, L, &d.probe_list, mc * h->R));
+        CC_CHECK(h, dev_alloc(h, L, &d.heavy_list, mc * h->R));
         CC_CHECK(h, dev_alloc(h, L, &h->d_s_parent, mc * h->R));
         CC_CHECK(h, dev_alloc(h, L, &h->d_s_links, mc * h->R * CC_LINK_SLOTS));
         d.cap_ulist = 1 << 18;
@@ -820,6 +839,7 @@ static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl, bool state
 
 static void bind_slot(cc_handle* h, const cc_handle::Slot& sl)
 {
+    h->d.trace = h->trace_on ? h->d_trace : nullptr;
     h->d.raw = sl.in_points;
     h->d.poses = sl.in_poses;
     h->d.col_first_unpub = sl.d_first_unpub;
@@ -871,30 +891,18 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
         const int gw = 4; // warps (columns) per block
         const size_t ground_smem = std::max(gw * cc_ground_warp_bytes(R), gw * CC_WARP * sizeof(double));
 #ifndef CC_EMU
-        if (ground_smem > 48 * 1024 && ground_smem != h->ground_smem_set)
+        // the kernel also has 16 KiB of static shared memory (running-maximum tail): opt in as soon as the sum passes 48 KiB
+        if (ground_smem > 28 * 1024 && ground_smem != h->ground_smem_set)
         {
             CC_CHECK(h, cudaFuncSetAttribute(k_ground, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ground_smem)));
             h->ground_smem_set = ground_smem;
         }
 #endif
-        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, ground_smem, cfg, h->d); // its last block also does the running maxima
-        {
-            // one CTA per tile of 2 new columns; the tile's sliding window of prior columns is staged in shared
-            // memory; warps take the tile's non-ignored points from a shared list
-            const int tile_cols = 2;
-            const size_t list_bytes = ((static_cast<size_t>(tile_cols) * R + 4) * sizeof(int) + 15) / 16 * 16;
-            const size_t win_only = static_cast<size_t>(tile_cols + cfg.max_steps_row) * R * sizeof(float4);
-            const int use_smem = (cfg.max_steps_row >= 0 && win_only <= 160 * 1024) ? 1 : 0;
-            const size_t win_bytes = list_bytes + (use_smem ? win_only : 0);
-#ifndef CC_EMU
-            if (win_bytes > 48 * 1024 && win_bytes != h->probe_smem_set)
-            {
-                CC_CHECK(h, cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(win_bytes)));
-                h->probe_smem_set = win_bytes;
-            }
-#endif
-            CC_RUN(h, k_probe, h->sm_count * 8, 256, win_bytes, cfg, h->d, h->d_s_parent, h->d_s_links, tile_cols, use_smem, sl.spec ? 1 : 0);
-        }
+        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent); // its last block also does the running maxima
+        // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
+        CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, 0, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
+        CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,
+               h->d_s_parent, h->d_s_links, h->tune);
         if (sl.spec)
         {
             launch_commit(h, cfg, 0, -1, 1, false);
@@ -1441,6 +1449,62 @@ int cc_debug_event_query(cc_handle_t* h, int slot, int which)
     cc_handle::Slot& sl = h->slots[slot];
     cudaEvent_t e = which == 0 ? sl.ev0 : which == 1 ? sl.ev1 : which == 2 ? sl.ready : sl.done;
     return cudaEventQuery(e) == cudaSuccess ? 1 : 0;
+}
+
+cc_status_t cc_debug_trace(cc_handle_t* h, int enable)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const size_t bytes = static_cast<size_t>(CC_TRACE_KERNELS) * CC_TRACE_BLOCKS * 2 * sizeof(unsigned long long);
+    if (enable && !h->d_trace)
+        CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_trace), bytes));
+    if (h->d_trace)
+    {
+        CC_CHECK(h, cudaStreamSynchronize(h->stream));
+        CC_CHECK(h, cudaMemset(h->d_trace, 0, bytes));
+    }
+    h->trace_on = enable != 0;
+    return CC_OK;
+}
+
+cc_status_t cc_debug_get_trace(cc_handle_t* h, char* names, int names_cap, uint64_t* out, int cap_kernels, int* n_out)
+{
+    if (!h || !out || !n_out || !h->d_trace)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const size_t count = static_cast<size_t>(CC_TRACE_KERNELS) * CC_TRACE_BLOCKS * 2;
+    std::vector<unsigned long long> t(count);
+    CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    CC_CHECK(h, cudaMemcpy(t.data(), h->d_trace, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CC_CHECK(h, cudaMemset(h->d_trace, 0, count * sizeof(unsigned long long)));
+    const int n = std::min<int>(cap_kernels, CC_KID_COUNT);
+    for (int k = 0; k < n; k++)
+    {
+        // per kernel: first block entry, last block exit, longest single block, blocks seen
+        uint64_t t0 = ~0ull, t1 = 0, longest = 0, blocks = 0;
+        for (int b = 0; b < CC_TRACE_BLOCKS; b++)
+        {
+            const unsigned long long a = t[(static_cast<size_t>(k) * CC_TRACE_BLOCKS + b) * 2], z = t[(static_cast<size_t>(k) * CC_TRACE_BLOCKS + b) * 2 + 1];
+            if (!a || !z)
+                continue;
+            blocks++;
+            t0 = std::min<uint64_t>(t0, a);
+            t1 = std::max<uint64_t>(t1, z);
+            longest = std::max<uint64_t>(longest, z - a);
+        }
+        out[4 * k + 0] = blocks ? t0 : 0;
+        out[4 * k + 1] = t1;
+        out[4 * k + 2] = longest;
+        out[4 * k + 3] = blocks;
+    }
+    if (names && names_cap > 0)
+    {
+        std::strncpy(names, CC_KERNEL_NAMES, static_cast<size_t>(names_cap) - 1);
+        names[names_cap - 1] = 0;
+    }
+    *n_out = n;
+    return CC_OK;
 }
 
 cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period)

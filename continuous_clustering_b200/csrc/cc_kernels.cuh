@@ -38,6 +38,101 @@ struct CcRawPoint // layout of continuous_clustering::RawPoint (point_types.hpp:
     unsigned long long guid;
 };
 
+// ---- optional device-side timeline (cc_debug_trace): thread 0 of every block stamps its entry (after the grid
+//      dependency wait) and exit with the global nanosecond timer; the host reduces them to per-kernel start / end ----
+#define CC_TRACE_BLOCKS 2048
+#define CC_TRACE_KERNELS 56
+enum CcKernelId
+{
+    CC_KID_prep,
+    CC_KID_scan_lite,
+    CC_KID_scan_check,
+    CC_KID_insert_scan,
+    CC_KID_scatter,
+    CC_KID_gap_scan,
+    CC_KID_ground,
+    CC_KID_probe,
+    CC_KID_probe_heavy,
+    CC_KID_snapshot,
+    CC_KID_restore,
+    CC_KID_restore_finish,
+    CC_KID_commit_copy,
+    CC_KID_commit_roots,
+    CC_KID_commit_links,
+    CC_KID_careful,
+    CC_KID_fin_all,
+    CC_KID_fin_label,
+    CC_KID_clear,
+    CC_KID_push_done,
+    CC_KID_halt,
+    CC_KID_pack_labels,
+    CC_KID_state_snapshot,
+    CC_KID_ground_main,
+    CC_KID_ground_tail,
+    CC_KID_gap_main,
+    CC_KID_gap_tail,
+    CC_KID_fin_init,
+    CC_KID_fin_agg,
+    CC_KID_fin_decide,
+    CC_KID_fin_mark,
+    CC_KID_fin_copyback,
+    CC_KID_fin_columns,
+    CC_KID_lite_p1,
+    CC_KID_lite_scan1,
+    CC_KID_lite_p2,
+    CC_KID_lite_scan2,
+    CC_KID_lite_p3,
+    CC_KID_check_loop,
+    CC_KID_check_scan,
+    CC_KID_g_pose,
+    CC_KID_g_A,
+    CC_KID_g_B,
+    CC_KID_g_C,
+    CC_KID_g_D,
+    CC_KID_COUNT
+};
+#define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D"
+struct CcTraceScope
+{
+    unsigned long long* slot;
+    __device__ __forceinline__ CcTraceScope(unsigned long long* trace, int kid) : slot(nullptr)
+    {
+#ifndef CC_EMU
+        if (trace && threadIdx.x == 0)
+        {
+            const unsigned int b = blockIdx.x < CC_TRACE_BLOCKS ? blockIdx.x : CC_TRACE_BLOCKS - 1;
+            slot = trace + (static_cast<size_t>(kid) * CC_TRACE_BLOCKS + b) * 2;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            slot[0] = t;
+        }
+#endif
+    }
+    __device__ __forceinline__ void stop()
+    {
+#ifndef CC_EMU
+        if (slot)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            slot[1] = t;
+            slot = nullptr;
+        }
+#endif
+    }
+    __device__ __forceinline__ ~CcTraceScope()
+    {
+#ifndef CC_EMU
+        if (slot)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            slot[1] = t;
+        }
+#endif
+    }
+};
+
 CC_DEV float cc_nanf()
 {
     return ccm::u2f(0x7fc00000u);
@@ -189,6 +284,7 @@ CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/
 __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_prep);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
@@ -212,6 +308,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
             if (cc_isnan(fx))
             {
                 p.s_cwr[idx] = CC_INVALID_CWR;
+                p.s_cwrT[static_cast<size_t>(row) * p.max_firings + k] = CC_INVALID_CWR;
                 continue;
             }
             double po[3];
@@ -227,6 +324,7 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
             p.s_incaz[idx] = incaz;
             p.s_incl[idx] = ccm::asinf_glibc(ccm::div_rn(static_cast<float>(rz), dist));
             p.s_cwr[idx] = cwr;
+            p.s_cwrT[static_cast<size_t>(row) * p.max_firings + k] = cwr; // row-major copy for the per-row check
             if (cwr != CC_INVALID_CWR)
             {
                 nvalid++;
@@ -323,6 +421,7 @@ struct CcOpMaxPair
 __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_lite);
     if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
@@ -366,6 +465,7 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
         if (a + u < b)
             fs[u] = p.lite_sum[a + u];
     }
+    CcTraceScope cc_tr_l1(p.trace, CC_KID_lite_p1);
     // pass 1: anchor columns relative to the thread's first valid firing
     CcAnchorSeg mine;
     mine.has = 0;
@@ -398,7 +498,11 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     ident.first_cw = ident.last_cw = ident.off = 0;
     CcOpAnchorSeg op;
     op.N = N;
+    cc_tr_l1.stop();
+    CcTraceScope cc_tr_s1(p.trace, CC_KID_lite_scan1);
     const CcAnchorSeg before = cc_block_exclusive_scan(sm_seg, mine, ident, op);
+    cc_tr_s1.stop();
+    CcTraceScope cc_tr_l2(p.trace, CC_KID_lite_p2);
     if (t == T - 1)
     {
         const CcAnchorSeg all = op(before, mine);
@@ -440,7 +544,11 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     CcMaxPair seed;
     seed.p = 0;   // rearmost column at the start of the push (relative: 0)
     seed.f = Fm0; // foremost column at the start of the push
+    cc_tr_l2.stop();
+    CcTraceScope cc_tr_s2(p.trace, CC_KID_lite_scan2);
     CcMaxPair pre = cc_block_exclusive_scan(sm_max, run, seed, CcOpMaxPair());
+    cc_tr_s2.stop();
+    CcTraceScope cc_tr_l3(p.trace, CC_KID_lite_p3);
     pre = CcOpMaxPair()(pre, seed);
     // pass 3: rearmost / foremost so far before every firing; unwrap margins
 #pragma unroll
@@ -487,6 +595,7 @@ struct CcOpLastSetI32
 __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_check);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
@@ -505,6 +614,7 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
     __shared__ int sh_front;
     if (t == 0)
         sh_front = NOT_SET;
+    CcTraceScope cc_tr_cl(p.trace, CC_KID_check_loop);
     for (int kb = a; kb < b; kb += 8) // loads of 8 firings issued together
     {
         int cw[8], U[8], an[8], P[8];
@@ -516,7 +626,7 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
             U[u] = an[u] = P[u] = 0;
             if (k < b)
             {
-                cw[u] = p.s_cwr[k * R + row];
+                cw[u] = p.s_cwrT[static_cast<size_t>(row) * p.max_firings + k];
                 U[u] = p.lite_U[k];
                 an[u] = p.lite_sum[k].anchor;
                 P[u] = p.lite_P[k];
@@ -541,7 +651,10 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
                 gmax = g > gmax ? g : gmax;
         }
     }
+    cc_tr_cl.stop();
+    CcTraceScope cc_tr_cs(p.trace, CC_KID_check_scan);
     int prev = cc_block_exclusive_scan(sm, last, NOT_SET, CcOpLastSetI32());
+    cc_tr_cs.stop();
     if (prev == NOT_SET)
     {
         long long rel = p.rowmax[row] - st->scan_lite_base; // the row's front
@@ -587,6 +700,7 @@ struct CcScanState // uniform across the CTA, kept in registers by every thread
 __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_insert_scan);
     if (blockIdx.x != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
@@ -1251,6 +1365,8 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         st->push_first_unpub_old = s.first_unpub;
         st->n_edges = 0;
         st->n_flagged = 0;
+        st->n_probe = 0;
+        st->n_heavy = 0;
         st->danger_col = CC_COL_INF;
         st->abort = 0;
         st->n_clusters = 0;
@@ -1265,6 +1381,7 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
 __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scatter);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
@@ -1356,6 +1473,7 @@ CC_DEV float cc_ldcg_f32(const float* q)
 __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_gap_scan);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int R = cfg.R;
@@ -1366,6 +1484,7 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
     const float nanv = cc_nanf();
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int items = nchunks * R; // (chunk, row), rows fastest: a warp reads consecutive rows of one column
+    CcTraceScope cc_tr_gmain(p.trace, CC_KID_gap_main);
     for (int it = blockIdx.x * T + t; it < items; it += gridDim.x * T)
     {
         const int chunk = it / R, row = it - chunk * R;
@@ -1399,6 +1518,7 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
         p.gap_chunk_last[it] = last;
     }
 
+    cc_tr_gmain.stop();
     __shared__ int sh_last;
     __syncthreads();
     if (t == 0)
@@ -1413,6 +1533,7 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
     __threadfence();
     if (t == 0)
         p.st->ticket_gap = 0;
+    CcTraceScope cc_tr_gtail(p.trace, CC_KID_gap_tail);
     // chain the chunks: tiles of chunks are staged in shared memory with independent coalesced loads (one memory
     // round trip per tile); every row is then walked by `parts` threads, each over a contiguous range of chunks
     __shared__ float sh_tile[8192];
@@ -1500,7 +1621,8 @@ struct CcGroundRow
 #define CC_GF_LG 4u    /* slope / distance part of the last-certain-ground update rule (cpp:542-551) */
 static inline __host__ __device__ size_t cc_ground_warp_bytes(int R)
 {
-    return (static_cast<size_t>(R) * (2 * sizeof(CcGroundRow) + sizeof(float) + sizeof(unsigned short) + 1) + 28 * sizeof(unsigned int) + 15) / 16 * 16;
+    return (static_cast<size_t>(R) * (2 * sizeof(CcGroundRow) + sizeof(float4) + sizeof(double) + sizeof(float) + sizeof(unsigned short) + 2) +
+            28 * sizeof(unsigned int) + 15) / 16 * 16;
 }
 
 CC_DEV double cc_ldcg_f64(const double* q)
@@ -1527,9 +1649,10 @@ CC_DEV bool cc_slope_below(float y, float x, float m)
     return fabsf(ccm::div_rn(y, x)) < m;
 }
 
-__global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
+__global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_ground);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
@@ -1539,25 +1662,48 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
     unsigned char* wbase = smem + static_cast<size_t>(wib) * cc_ground_warp_bytes(R);
     CcGroundRow* s = reinterpret_cast<CcGroundRow*>(wbase);  // by row
     CcGroundRow* cseq = s + R;                               // regular points, bottom row first; flags carry the row
-    float* s_incl = reinterpret_cast<float*>(cseq + R);
+    float4* s_q = reinterpret_cast<float4*>(cseq + R);       // the cells as inserted: x, y, z, distance
+    double* s_caz = reinterpret_cast<double*>(s_q + R);      // continuous azimuth
+    float* s_incl = reinterpret_cast<float*>(s_caz + R);
     unsigned int* vm = reinterpret_cast<unsigned int*>(s_incl + R); // bitmap of regular rows (8 words)
     unsigned int* fm = vm + 8;  // by position in cseq: flat w.r.t. the previous point
     unsigned int* lm = fm + 8;  // by position in cseq: passes the slope / distance part of the last-ground update rule
     unsigned int* cst = lm + 8; // state handed from C1 to C3
     unsigned short* s_lab = reinterpret_cast<unsigned short*>(cst + 4); // label | debug label << 8
     unsigned char* s_cls = reinterpret_cast<unsigned char*>(s_lab + R);
+    unsigned char* s_int = s_cls + R; // intensity
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
     const float nanv = cc_nanf();
     const int nwords = (R + 31) / 32;
     const float hsg = cfg.height_sensor_to_ground;
 
+    CcTraceScope cc_tr_main_obj(p.trace, CC_KID_ground_main);
     for (int ci = blockIdx.x * warps_per_block + wib; ci < ncols; ci += gridDim.x * warps_per_block)
     {
         const long long gcol = colbase + ci;
         const int local = cc_local_col(gcol, cfg.ringcols);
         const size_t base = static_cast<size_t>(local) * R;
+        CcTraceScope cc_tr_pose(p.trace, CC_KID_g_pose);
+        // ---- A0: everything the column needs from global memory, issued before anything waits: the firing that
+        //      completed the column (its pose is one more dependent round trip) and the cells ----
         const int trig = p.col_trigger[ci];
+        const long long slot_before = lane == 0 ? p.slot_gcol[local] : -1;
+        for (int row = lane; row < R; row += CC_WARP)
+        {
+            const float4 q = p.pos[base + row];
+            const float incl = p.incl[base + row];
+            const unsigned char intensity = p.lab[base + row].w;
+            const double caz = p.cont_az[base + row];
+            float gap = p.col_gap[static_cast<size_t>(ci) * R + row];
+            if (cc_isnan(gap)) // nothing valid in the column's chunk so far: what the chunks before it left
+                gap = p.gap_chunk_carry[static_cast<size_t>(ci / CC_GAP_CHUNK) * R + row];
+            s_q[row] = q;
+            s_caz[row] = caz;
+            s_incl[row] = incl;
+            s_int[row] = intensity;
+            s[row].gap = gap;
+        }
         const double* pose = p.poses + 12 * trig;
         double inv[12], ego[12];
         cc_iso_inverse(pose, inv);
@@ -1566,17 +1712,19 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
                     spz = static_cast<float>(pose[11]);
         if (lane == 0)
         {
-            if (p.slot_gcol[local] != -1)
+            if (slot_before != -1)
             {
                 p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
-                p.st->err_a = p.slot_gcol[local];
+                p.st->err_a = slot_before;
                 p.st->err_b = gcol;
             }
             for (int w = 0; w < 24; w++)
                 vm[w] = 0u; // vm, fm, lm
         }
 
-        // ---- A: stage every cell (class, azimuth-plane projection), bitmap of the regular rows ----
+        cc_tr_pose.stop();
+        CcTraceScope cc_tr_A(p.trace, CC_KID_g_A);
+        // ---- A: classify every cell, project it into the azimuth plane, bitmap of the regular rows ----
         for (int row0 = 0; row0 < R; row0 += CC_WARP)
         {
             const int row = row0 + lane;
@@ -1584,9 +1732,9 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
             unsigned char cls = 0;
             if (in)
             {
-                const float4 q = p.pos[base + row];
-                const float incl = p.incl[base + row];
-                const unsigned char intensity = p.lab[base + row].w;
+                const float4 q = s_q[row]; // staged by this very lane
+                const float incl = s_incl[row];
+                const unsigned char intensity = s_int[row];
                 cls = 3;
                 unsigned short lab = CC_GP_UNKNOWN | (CC_WHITE << 8);
                 if (cc_isnan(q.w))
@@ -1609,15 +1757,9 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
                     }
                 }
                 const float x = q.x - spx, y = q.y - spy, z = q.z - spz;
-                CcGroundRow r;
-                r.c2x = ccm::sqrt_rn(x * x + y * y);
-                r.c2y = z;
-                r.flags = 0u;
-                r.gap = p.col_gap[static_cast<size_t>(ci) * R + row];
-                if (cc_isnan(r.gap)) // nothing valid in the column's chunk so far: what the chunks before it left
-                    r.gap = p.gap_chunk_carry[static_cast<size_t>(ci / CC_GAP_CHUNK) * R + row];
-                s[row] = r;
-                s_incl[row] = incl;
+                s[row].c2x = ccm::sqrt_rn(x * x + y * y);
+                s[row].c2y = z;
+                s[row].flags = 0u;
                 s_lab[row] = lab;
                 s_cls[row] = cls;
             }
@@ -1627,6 +1769,8 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
         }
         __syncwarp();
 
+        cc_tr_A.stop();
+        CcTraceScope cc_tr_B(p.trace, CC_KID_g_B);
         // ---- B: everything of the label rules that does not depend on carried state, for all rows at once: the
         //      previous regular point (fog / ego / empty cells never become "previous", cpp:360-404), the slope to it,
         //      the compacted bottom-to-top sequence; and the inclination supplement of runs of empty cells ----
@@ -1690,6 +1834,8 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
         }
         __syncwarp();
 
+        cc_tr_B.stop();
+        CcTraceScope cc_tr_C(p.trace, CC_KID_g_C);
         // ---- C: the sequential label state machine (cpp:305-565) over the regular points only ----
         // C1 (lane 0): up to the first obstacle a flat point is GREEN whatever came before, so the walk jumps from one
         //     non-flat point to the next with bit operations on the flat / last-ground-candidate masks
@@ -1797,6 +1943,11 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
             CcGroundRow nx = cseq[i];
             int prev_row = -1;
             unsigned int prev_lab = 0u;
+            const bool terrain = cfg.use_terrain != 0;
+            const float ms = cfg.max_slope;
+            // Written for a short dependency chain through (lg_x, lg_y, fod, prev_yellow): every rule is evaluated as a
+            // predicate and the label is a select; only the relabel walk of an obstacle and the (rare) exact division
+            // branch.
             for (; i < nregular; i++)
             {
                 const CcGroundRow cur = nx;
@@ -1805,20 +1956,25 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
                 const int row = static_cast<int>(cur.flags >> 16);
                 const float c2x = cur.c2x, c2y = cur.c2y;
                 const bool flat_prev = (cur.flags & CC_GF_FLAT) != 0;
-                unsigned int lab = 0u;
-                if (!fod && flat_prev)
-                    lab = CC_GP_GROUND | (CC_GREEN << 8);
-                else if (!cfg.use_terrain)
+                const float gtc_x = c2x - lg_x, gtc_y = c2y - lg_y;
+                const float agx = fabsf(gtc_x), agy = fabsf(gtc_y);
+                // |RN(gtc_y / gtc_x)| < max_slope, decided without the division unless the quotient is within 1e-6
+                // (relative) of the threshold
+                const float t = ms * agx;
+                const bool t_ok = t > 1e-30f && t < 1e30f;
+                bool slope_ok = t_ok && agy < t * 0.999999f;
+                const bool cand = fod && flat_prev && gtc_x > 0 && !terrain;
+                if (cand && !(t_ok && (slope_ok || agy > t * 1.000001f)))
+                    slope_ok = fabsf(ccm::div_rn(gtc_y, gtc_x)) < ms;
+                const bool green = !fod && flat_prev;
+                const bool yellowgreen = cand && slope_ok;
+                const bool yellow = !terrain && agx < cfg.close_d && agy < cfg.close_z;
+                unsigned int lab = green         ? (CC_GP_GROUND | (CC_GREEN << 8))
+                                   : yellowgreen ? (CC_GP_GROUND | (CC_YELLOWGREEN << 8))
+                                   : yellow      ? (CC_GP_GROUND | (CC_YELLOW << 8))
+                                                 : (CC_GP_OBSTACLE | (CC_RED << 8));
+                if (!(green || yellowgreen || yellow)) // cpp:508-536
                 {
-                    const float gtc_x = c2x - lg_x, gtc_y = c2y - lg_y;
-                    if (fod && flat_prev && gtc_x > 0 && cc_slope_below(gtc_y, gtc_x, cfg.max_slope))
-                        lab = CC_GP_GROUND | (CC_YELLOWGREEN << 8);
-                    else if (fabsf(gtc_x) < cfg.close_d && fabsf(gtc_y) < cfg.close_z)
-                        lab = CC_GP_GROUND | (CC_YELLOW << 8);
-                }
-                if (lab == 0u) // cpp:508-536
-                {
-                    lab = CC_GP_OBSTACLE | (CC_RED << 8);
                     int below = row + 1;
                     while (below < R)
                     {
@@ -1836,25 +1992,24 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
                     fod = true;
                 }
                 s_lab[row] = static_cast<unsigned short>(lab);
-                const unsigned int dbg = lab >> 8;
-                if ((dbg == CC_GREEN || dbg == CC_YELLOWGREEN) && (cur.flags & CC_GF_LG) && !prev_yellow) // cpp:541-561
-                {
-                    lg_x = c2x;
-                    lg_y = c2y;
-                }
-                prev_yellow = dbg == CC_YELLOW;
+                const bool upd = (green || yellowgreen) && (cur.flags & CC_GF_LG) && !prev_yellow; // cpp:541-561
+                lg_x = upd ? c2x : lg_x;
+                lg_y = upd ? c2y : lg_y;
+                prev_yellow = !green && !yellowgreen && yellow;
                 prev_row = row;
                 prev_lab = lab;
             }
         }
         __syncwarp();
 
+        cc_tr_C.stop();
+        CcTraceScope cc_tr_D(p.trace, CC_KID_g_D);
         // ---- D: is_ignored (cpp:567-616) + association view ----
         double min_az = 1.7976931348623157e308;
         for (int row = lane; row < R; row += CC_WARP)
         {
             const size_t cell = base + row;
-            const float4 q = p.pos[cell];
+            const float4 q = s_q[row];
             const unsigned short lab = s_lab[row];
             const unsigned char label = static_cast<unsigned char>(lab & 0xff);
             const float gap = s[row].gap;
@@ -1882,16 +2037,35 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
                 p.incl[cell] = incl;
             }
             else
-                caz = p.cont_az[cell];
+                caz = s_caz[row];
             if (caz < min_az)
                 min_az = caz;
-            uchar4 l = p.lab[cell];
-            l.x = label;
-            l.y = static_cast<unsigned char>(lab >> 8);
-            l.z = ignored ? 1 : 0;
-            p.lab[cell] = l;
+            p.lab[cell] = make_uchar4(label, static_cast<unsigned char>(lab >> 8), ignored ? 1 : 0, s_int[row]);
             p.assoc[cell] = make_float4(ignored ? nanv : q.x, q.y, q.z, incl);
             p.mad[cell] = ignored ? 0.f : ccm::asinf_glibc(ccm::div_rn(cfg.max_distance, q.w));
+            if (!ignored)
+                s_cls[row] |= 0x80; // read back by this very lane below
+            else // never takes part in the association: no parent, nothing visited
+            {
+                s_parent[static_cast<size_t>(ci) * R + row] = CC_NONE;
+                p.visited[cell] = 0;
+            }
+        }
+        // the column's non-ignored points join the list the association probe works through (one atomic per 32 rows)
+        for (int row0 = 0; row0 < R; row0 += CC_WARP)
+        {
+            const int row = row0 + lane;
+            const bool take = row < R && (s_cls[row < R ? row : 0] & 0x80) != 0;
+            const unsigned int m = __ballot_sync(CC_FULL_MASK, take);
+            if (m)
+            {
+                int pos0 = 0;
+                if (lane == __ffs(m) - 1)
+                    pos0 = atomicAdd(&p.st->n_probe, __popc(m));
+                pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(m) - 1);
+                if (take)
+                    p.probe_list[pos0 + __popc(m & ((1u << lane) - 1u))] = ci * R + row;
+            }
         }
         min_az = cc_warp_min_f64(min_az);
         if (lane == 0)
@@ -1905,6 +2079,7 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
 
     // ---- running maximum of the columns' minimum azimuth (the value every finish pass compares against,
     //      cpp:884-885), continued across pushes: done by whichever block finishes last ----
+    cc_tr_main_obj.stop();
     __shared__ int sh_last;
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1919,6 +2094,7 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p)
     __threadfence();
     if (threadIdx.x == 0)
         p.st->ticket_ground = 0;
+    CcTraceScope cc_tr_tail(p.trace, CC_KID_ground_tail);
     // tiles of 2048 columns staged in shared memory with independent coalesced loads; every thread scans a contiguous
     // segment of the tile, the segments are chained by a block scan
     __shared__ double sh_az[2048];
@@ -1971,231 +2147,569 @@ __device__ void d_snapshot(CcDevPtrs p, int spec);
 //      seen before this column, or its tree is already finished -- flags the column for the column-sequential
 //      exact path. No persistent state is modified here.
 // =====================================================================================================
-__global__ void k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tile_cols, int use_smem,
-                        int do_snapshot)
+#define CC_PROBE_PIPE 6   /* vertical runs fetched ahead per warp by the cooperative walk */
+#define CC_PROBE_BUDGET 12 /* cells a point may visit on the thread-per-point path before the warp takes it over */
+#ifdef CC_EMU
+#define CC_PROBE_PPW 1
+#else
+#define CC_PROBE_PPW 4 /* points per warp on the thread-per-point path (spreads the heavy points over more warps) */
+#endif
+
+// Warp-cooperative walk of ONE point with all lanes: every vertical run of the walk (cpp:716-750) is evaluated 32 cells
+// at once (inclination break, 3-D distance predicate) and the sequential early-exit rules are applied to the ballot
+// masks. The walk order, the visit count and which hit is first are those of the reference. The cells of the next
+// CC_PROBE_PIPE runs are fetched ahead with cp.async into a per-warp ring in shared memory (lane j holds cell j of a
+// run): an isolated point walks its whole window, 2 * max_steps_in_row + 1 runs.
+CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* s_parent, unsigned int* s_links, float4* ring,
+                         int base_local, long long colbase, int lane, int pidx)
+{
+    const int R = cfg.R, msr = cfg.max_steps_row;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int pci = pidx / R, prow = pidx - pci * R;
+    int plocal = base_local + pci;
+    if (plocal >= cfg.ringcols)
+        plocal -= cfg.ringcols;
+    const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
+    const float4 pa = p.assoc[pq];
+    const float ax = pa.x, ay = pa.y, az = pa.z, aw = pa.w;
+    const float mad = p.mad[pq];
+    const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
+    int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+    steps_back = steps_back < msr ? steps_back : msr;
+    steps_back = steps_back < 0 ? 0 : steps_back;
+    // run r of the walk order (cpp:707-719): r = 0 is the own column upwards; then for every column further back the
+    // upward run (from the own row) and the downward run
+    const int nruns = 1 + 2 * steps_back;
+    auto issue = [&](int r)
+    {
+        if (r < nruns)
+        {
+            const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+            const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+            const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+            int n = cfg.max_steps_col - start_step + 1;
+            const int room = dir < 0 ? start_row + 1 : R - start_row;
+            n = n < room ? n : room;
+            int olocal = plocal - back;
+            if (olocal < 0)
+                olocal += cfg.ringcols;
+            if (lane < n)
+                __pipeline_memcpy_async(ring + (r % CC_PROBE_PIPE) * CC_WARP + lane,
+                                        p.assoc + static_cast<size_t>(olocal) * R + (start_row + dir * lane), 16);
+        }
+        __pipeline_commit();
+    };
+    for (int r = 0; r < CC_PROBE_PIPE; r++)
+        issue(r);
+    unsigned int first = CC_NONE;
+    int visited = 0, nlinks = 0;
+    bool flagged = false;
+    for (int r = 0; r < nruns; r++)
+    {
+        const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+        int olocal = plocal - back;
+        if (olocal < 0)
+            olocal += cfg.ringcols; // cpp:768-769
+        {
+            const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+            const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+            int n = cfg.max_steps_col - start_step + 1; // cells of this vertical run
+            const int room = dir < 0 ? start_row + 1 : R - start_row;
+            n = n < room ? n : room;
+            __pipeline_wait_prior(CC_PROBE_PIPE - 1); // run r has landed (every lane reads only what it fetched itself)
+            bool run_done = false;
+            for (int jb = 0; jb < n && !run_done; jb += CC_WARP)
+            {
+                const int cnt = (n - jb) < CC_WARP ? (n - jb) : CC_WARP;
+                const int j = jb + lane;
+                const bool in = lane < cnt;
+                const int orow = start_row + dir * j;
+                const unsigned int o = static_cast<unsigned int>(olocal) * R + (in ? orow : 0);
+                float4 b = make_float4(cc_nanf(), 0.f, 0.f, cc_nanf());
+                if (in)
+                    b = jb == 0 ? ring[(r % CC_PROBE_PIPE) * CC_WARP + lane] : p.assoc[o];
+                const bool brk = in && fabsf(b.w - aw) > mad; // cpp:728-729 (NaN never breaks)
+                bool hit = false;
+                if (in && !brk && !cc_isnan(b.x))
+                {
+                    const float dx = ax - b.x, dy = ay - b.y, dz = az - b.z;
+                    hit = dx * dx + dy * dy + dz * dz < cfg.max_distance_sq; // cpp:638-641
+                }
+                const unsigned int brk_mask = __ballot_sync(CC_FULL_MASK, brk);
+                const unsigned int hit_mask = __ballot_sync(CC_FULL_MASK, hit);
+                const int limit = brk_mask ? __ffs(brk_mask) - 1 : cnt; // cells before the break are processed
+                const unsigned int below_limit = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
+                // early stop once associated (cpp:747-749): after the first cell with steps >= min steps
+                int jstop = 0x7fffffff;
+                if (cfg.stop_enabled)
+                {
+                    const int need = cfg.stop_min_steps - start_step - jb; // lane index where steps >= min
+                    if (first != CC_NONE)
+                        jstop = need > 0 ? need : 0;
+                    else if (hit_mask & below_limit)
+                    {
+                        const int jh = __ffs(hit_mask & below_limit) - 1;
+                        jstop = jh > need ? jh : need;
+                    }
+                }
+                int processed = limit; // number of cells whose association step runs
+                bool stopped = false;
+                if (jstop < limit)
+                {
+                    processed = jstop + 1;
+                    stopped = true;
+                }
+                visited += stopped ? processed : (limit < cnt ? limit + 1 : cnt);
+                const unsigned int proc_mask = processed >= 32 ? 0xffffffffu : ((1u << processed) - 1u);
+                unsigned int hp = hit_mask & proc_mask;
+                if (hp)
+                {
+                    if ((hp >> lane) & 1u) // every hit lane checks its own target
+                    {
+                        // could the reference have refused this hit?
+                        const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                        if (finish_o <= prev_runmax)
+                            flagged = true;
+                        if (back > pci)
+                        {
+                            const unsigned int ro = p.tparent[o];
+                            if (ro == CC_NONE || p.tstate[ro] != 0)
+                                flagged = true;
+                        }
+                    }
+                    if (first == CC_NONE)
+                    {
+                        const int jf = __ffs(hp) - 1;
+                        first = __shfl_sync(CC_FULL_MASK, o, jf);
+                        hp &= hp - 1;
+                    }
+                    // the remaining hits are tree<->tree link candidates (cpp:740-741)
+                    if ((hp >> lane) & 1u)
+                    {
+                        const int slot = nlinks + __popc(hp & lt_mask);
+                        if (slot < CC_LINK_SLOTS)
+                            s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + slot] = o;
+                        else
+                        {
+                            const int e = atomicAdd(&p.st->n_edges, 1);
+                            if (e < p.cap_edges)
+                            {
+                                p.edge_a[e] = pq;
+                                p.edge_b[e] = o;
+                            }
+                            else
+                                p.st->error = CC_DEV_LIST_OVERFLOW;
+                        }
+                    }
+                    nlinks += __popc(hp);
+                }
+                run_done = stopped || limit < cnt;
+            }
+        }
+        issue(r + CC_PROBE_PIPE); // into the slot just consumed
+        if ((r == 0 || !(r & 1)) && first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+            break; // cpp:757-759, after both runs of a column
+    }
+    __pipeline_wait_prior(0); // nothing in flight when the next point starts filling the ring
+    const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
+                          (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
+    for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
+        s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
+    if (lane == 0)
+    {
+        s_parent[pidx] = first == CC_NONE ? pq : first;
+        p.visited[pq] = static_cast<unsigned short>(visited);
+        if (any_flag)
+        {
+            p.col_flag[pci] = 1;
+            atomicAdd(&p.st->n_flagged, 1);
+        }
+    }
+}
+
+// K3a: every non-ignored point of the new columns (the list k_ground compacted). Most points visit a handful of cells
+// (the first neighbour above or in the previous column associates them and the walk stops, cpp:747-759): those are
+// walked by ONE thread each, literally as the reference does, with a budget of CC_PROBE_BUDGET cells. A point that
+// exceeds the budget (sparse surroundings: the walk covers up to (2 * max_steps_in_row + 1) * max_steps_in_column
+// cells) or finds more link candidates than it has slots is redone from scratch by a whole warp (k_probe_heavy).
+__global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int do_snapshot)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts); the probe itself
         d_snapshot(p, 0); // modifies no persistent state
-    CC_SMEM(smem);
     const int R = cfg.R;
-    int* plist_n = reinterpret_cast<int*>(smem);          // [0] points in the list, [1] next point to take
-    int* plist = plist_n + 4;                             // [tile_cols * R] non-ignored cells of the tile
-    // association view of the tile's columns + the window before them
-    float4* win = reinterpret_cast<float4*>(smem + ((static_cast<size_t>(tile_cols) * R + 4) * sizeof(int) + 15) / 16 * 16);
     const int ncols = p.st->ncols;
     const long long colbase = p.st->colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
-    const int msr = cfg.max_steps_row;
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int ntiles = (ncols + tile_cols - 1) / tile_cols;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    const int lane = threadIdx.x % CC_WARP;
+    const int npoints = p.st->n_probe < p.maxcols * R ? p.st->n_probe : p.maxcols * R;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) / CC_WARP;
+    const int nwarps = (gridDim.x * blockDim.x + CC_WARP - 1) / CC_WARP;
+    const int ngroups = (npoints + CC_PROBE_PPW - 1) / CC_PROBE_PPW;
+    for (int grp = gwarp; grp < ngroups; grp += nwarps)
     {
-        const int ci0 = tile * tile_cols;
-        const int nc = (ncols - ci0) < tile_cols ? (ncols - ci0) : tile_cols;
-        // ring column of window column 0 (msr columns before the tile)
-        int wl0 = (base_local + ci0 - msr) % cfg.ringcols;
-        if (wl0 < 0)
-            wl0 += cfg.ringcols;
-        if (use_smem)
+        // the points of a warp are far apart in the list: points that need the cooperative walk come in runs (the
+        // neighbouring cells of a sparse region), which one warp would have to work through one after the other
+        const int pi = lane * ngroups + grp;
+        const bool has = lane < CC_PROBE_PPW && pi < npoints;
+        bool heavy = false;
+        int pidx = 0;
+        if (has)
         {
-            // stage the sliding window: each window column is one contiguous R*16-byte span of the ring
-            const int wcells = (msr + nc) * R;
-            for (int i = tid; i < wcells; i += T)
+            pidx = p.probe_list[pi];
+            const int pci = pidx / R, prow = pidx - pci * R;
+            int plocal = base_local + pci;
+            if (plocal >= cfg.ringcols)
+                plocal -= cfg.ringcols;
+            const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
+            const float4 a = p.assoc[pq];
+            const float mad = p.mad[pq];
+            const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
+            int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+            steps_back = steps_back < cfg.max_steps_row ? steps_back : cfg.max_steps_row;
+            unsigned int first = CC_NONE, l0 = CC_NONE, l1 = CC_NONE, l2 = CC_NONE, l3 = CC_NONE;
+            static_assert(CC_LINK_SLOTS == 4, "four link registers below");
+            int nl = 0, visited = 0;
+            bool flagged = false;
+            int ocol = plocal;
+            for (int back = 0; back <= steps_back; back++)
             {
-                const int w = i / R, row = i - w * R;
-                int local = wl0 + w;
-                if (local >= cfg.ringcols)
-                    local -= cfg.ringcols;
-                win[i] = p.assoc[static_cast<size_t>(local) * R + row];
-            }
-            __syncthreads();
-        }
-        // Warp-cooperative walk: a warp takes 32 consecutive cells of the tile, ballots the non-ignored ones and walks
-        // the field of view of one point at a time with ALL lanes: every vertical run of the walk (cpp:716-750) is
-        // evaluated 32 cells at once (inclination break, 3-D distance predicate) and the sequential early-exit rules
-        // are applied to the ballot masks. The walk order, the visit count and which hit is first are those of the
-        // reference; the cost of an isolated point drops from ~860 dependent visits to ~41 warp steps.
-        const int lane = tid % CC_WARP;
-        const unsigned int lt_mask = (1u << lane) - 1u;
-        // compact the tile's non-ignored cells into a shared list; warps then take points from it one at a time, so
-        // a dense object does not serialise on the warp that happens to own its rows
-        if (tid == 0)
-        {
-            plist_n[0] = 0;
-            plist_n[1] = 0;
-        }
-        __syncthreads();
-        for (int cell = tid; cell < nc * R; cell += T)
-        {
-            const int cl = cell / R, row = cell - cl * R;
-            const int wq = msr + cl;
-            int local = wl0 + wq;
-            if (local >= cfg.ringcols)
-                local -= cfg.ringcols;
-            const unsigned int q = static_cast<unsigned int>(local) * R + row;
-            const float ax = use_smem ? win[wq * R + row].x : p.assoc[q].x;
-            if (cc_isnan(ax))
-            {
-                s_parent[(ci0 + cl) * R + row] = CC_NONE;
-                p.visited[q] = 0;
-            }
-            else
-                plist[atomicAdd(&plist_n[0], 1)] = cell;
-        }
-        __syncthreads();
-        const int npoints = plist_n[0];
-        while (true)
-        {
-            int pi = 0;
-            if (lane == 0)
-                pi = atomicAdd(&plist_n[1], 1);
-            pi = __shfl_sync(CC_FULL_MASK, pi, 0);
-            if (pi >= npoints)
-                break;
-            {
-                const int cell = plist[pi];
-                const int pcl = cell / R, prow = cell - pcl * R;
-                const int pci = ci0 + pcl, pwq = msr + pcl, pidx = pci * R + prow;
-                int plocal = wl0 + pwq;
-                if (plocal >= cfg.ringcols)
-                    plocal -= cfg.ringcols;
-                const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
-                const float4 pa = use_smem ? win[pwq * R + prow] : p.assoc[pq];
-                const float ax = pa.x, ay = pa.y, az = pa.z, aw = pa.w;
-                const float mad = p.mad[pq];
-                const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
-                int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
-                steps_back = steps_back < msr ? steps_back : msr;
-                unsigned int first = CC_NONE;
-                int visited = 0, nlinks = 0;
-                bool flagged = false;
-                for (int back = 0; back <= steps_back; back++)
+                for (int dir = -1; dir <= 1 && !heavy; dir += 2)
                 {
-                    const int wo = pwq - back;
-                    int olocal = wl0 + wo;
-                    if (olocal >= cfg.ringcols)
-                        olocal -= cfg.ringcols;
-                    for (int dir = -1; dir <= 1; dir += 2)
+                    if (dir == 1 && back == 0)
+                        continue;
+                    int steps_v = (dir == 1 || back == 0) ? 1 : 0;
+                    int orow = (dir == 1 || back == 0) ? prow + dir : prow;
+                    while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
                     {
-                        if (dir == 1 && back == 0)
-                            continue;
-                        const int start_step = (dir == 1 || back == 0) ? 1 : 0;
-                        const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
-                        int n = cfg.max_steps_col - start_step + 1; // cells of this vertical run
-                        const int room = dir < 0 ? start_row + 1 : R - start_row;
-                        n = n < room ? n : room;
-                        bool run_done = false;
-                        for (int jb = 0; jb < n && !run_done; jb += CC_WARP)
+                        if (visited >= CC_PROBE_BUDGET)
                         {
-                            const int cnt = (n - jb) < CC_WARP ? (n - jb) : CC_WARP;
-                            const int j = jb + lane;
-                            const bool in = lane < cnt;
-                            const int orow = start_row + dir * j;
-                            const unsigned int o = static_cast<unsigned int>(olocal) * R + (in ? orow : 0);
-                            float4 b = make_float4(cc_nanf(), 0.f, 0.f, cc_nanf());
-                            if (in)
-                                b = use_smem ? win[wo * R + orow] : p.assoc[o];
-                            const bool brk = in && fabsf(b.w - aw) > mad; // cpp:728-729 (NaN never breaks)
-                            bool hit = false;
-                            if (in && !brk && !cc_isnan(b.x))
+                            heavy = true;
+                            break;
+                        }
+                        const unsigned int o = static_cast<unsigned int>(ocol) * R + orow;
+                        const float4 b = p.assoc[o];
+                        visited++;
+                        if (fabsf(b.w - a.w) > mad) // cpp:728-729 (NaN never breaks)
+                            break;
+                        if (!cc_isnan(b.x))
+                        {
+                            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                            if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
                             {
-                                const float dx = ax - b.x, dy = ay - b.y, dz = az - b.z;
-                                hit = dx * dx + dy * dy + dz * dz < cfg.max_distance_sq; // cpp:638-641
-                            }
-                            const unsigned int brk_mask = __ballot_sync(CC_FULL_MASK, brk);
-                            const unsigned int hit_mask = __ballot_sync(CC_FULL_MASK, hit);
-                            const int limit = brk_mask ? __ffs(brk_mask) - 1 : cnt; // cells before the break are processed
-                            const unsigned int below_limit = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
-                            // early stop once associated (cpp:747-749): after the first cell with steps >= min steps
-                            int jstop = 0x7fffffff;
-                            if (cfg.stop_enabled)
-                            {
-                                const int need = cfg.stop_min_steps - start_step - jb; // lane index where steps >= min
-                                if (first != CC_NONE)
-                                    jstop = need > 0 ? need : 0;
-                                else if (hit_mask & below_limit)
+                                // could the reference have refused this hit?
+                                const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                                if (finish_o <= prev_runmax)
+                                    flagged = true;
+                                if (back > pci)
                                 {
-                                    const int jh = __ffs(hit_mask & below_limit) - 1;
-                                    jstop = jh > need ? jh : need;
-                                }
-                            }
-                            int processed = limit; // number of cells whose association step runs
-                            bool stopped = false;
-                            if (jstop < limit)
-                            {
-                                processed = jstop + 1;
-                                stopped = true;
-                            }
-                            visited += stopped ? processed : (limit < cnt ? limit + 1 : cnt);
-                            const unsigned int proc_mask = processed >= 32 ? 0xffffffffu : ((1u << processed) - 1u);
-                            unsigned int hp = hit_mask & proc_mask;
-                            if (hp)
-                            {
-                                if ((hp >> lane) & 1u) // every hit lane checks its own target
-                                {
-                                    // could the reference have refused this hit?
-                                    const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
-                                    if (finish_o <= prev_runmax)
+                                    const unsigned int ro = p.tparent[o];
+                                    if (ro == CC_NONE || p.tstate[ro] != 0)
                                         flagged = true;
-                                    if (back > pci)
-                                    {
-                                        const unsigned int ro = p.tparent[o];
-                                        if (ro == CC_NONE || p.tstate[ro] != 0)
-                                            flagged = true;
-                                    }
                                 }
                                 if (first == CC_NONE)
+                                    first = o;
+                                else if (nl == 0)
+                                    l0 = o, nl = 1;
+                                else if (nl == 1)
+                                    l1 = o, nl = 2;
+                                else if (nl == 2)
+                                    l2 = o, nl = 3;
+                                else if (nl == 3)
+                                    l3 = o, nl = 4;
+                                else
                                 {
-                                    const int jf = __ffs(hp) - 1;
-                                    first = __shfl_sync(CC_FULL_MASK, o, jf);
-                                    hp &= hp - 1;
+                                    heavy = true; // the overflow list is the cooperative walk's business
+                                    break;
                                 }
-                                // the remaining hits are tree<->tree link candidates (cpp:740-741)
-                                if ((hp >> lane) & 1u)
-                                {
-                                    const int slot = nlinks + __popc(hp & lt_mask);
-                                    if (slot < CC_LINK_SLOTS)
-                                        s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + slot] = o;
-                                    else
-                                    {
-                                        const int e = atomicAdd(&p.st->n_edges, 1);
-                                        if (e < p.cap_edges)
-                                        {
-                                            p.edge_a[e] = pq;
-                                            p.edge_b[e] = o;
-                                        }
-                                        else
-                                            p.st->error = CC_DEV_LIST_OVERFLOW;
-                                    }
-                                }
-                                nlinks += __popc(hp);
                             }
-                            run_done = stopped || limit < cnt;
                         }
+                        if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps) // cpp:747-749
+                            break;
+                        orow += dir;
+                        steps_v++;
                     }
-                    if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
-                        break;
                 }
-                const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
-                                      (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
-                for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
-                    s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
-                if (lane == 0)
+                if (heavy)
+                    break;
+                if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps) // cpp:757-759
+                    break;
+                ocol--;
+                if (ocol < 0)
+                    ocol += cfg.ringcols; // cpp:768-769
+            }
+            if (!heavy)
+            {
+                unsigned int* lk = s_links + static_cast<size_t>(pidx) * CC_LINK_SLOTS;
+                lk[0] = l0;
+                lk[1] = l1;
+                lk[2] = l2;
+                lk[3] = l3;
+                s_parent[pidx] = first == CC_NONE ? pq : first;
+                p.visited[pq] = static_cast<unsigned short>(visited);
+                if (flagged || (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0))
                 {
-                    s_parent[pidx] = first == CC_NONE ? pq : first;
-                    p.visited[pq] = static_cast<unsigned short>(visited);
-                    if (any_flag)
-                    {
-                        p.col_flag[pci] = 1;
-                        atomicAdd(&p.st->n_flagged, 1);
-                    }
+                    p.col_flag[pci] = 1;
+                    atomicAdd(&p.st->n_flagged, 1);
+                }
+            }
+        }
+        // points for the cooperative walk go to the list k_probe_heavy works through, one warp per point
+        const unsigned int hm = __ballot_sync(CC_FULL_MASK, has && heavy);
+        if (hm)
+        {
+            int pos0 = 0;
+            if (lane == __ffs(hm) - 1)
+                pos0 = atomicAdd(&p.st->n_heavy, __popc(hm));
+            pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(hm) - 1);
+            if (has && heavy)
+                p.heavy_list[pos0 + __popc(hm & ((1u << lane) - 1u))] = pidx;
+        }
+    }
+}
+
+// K3a': the points the thread-per-point path gave up on, one CTA per point. When a vertical run fits one warp step
+// (max_steps_in_column < 32) and the window has at most 64 runs:
+//   phase 1  the warps of the CTA share the runs of the window: independent loads, inclination-break and distance
+//            predicates of every run at once, their ballot masks left in shared memory;
+//   phase 2  warp 0 applies the sequential rules to the masks. As long as the point is not associated a run without a
+//            hit before its break only adds to the visit count, so the lanes handle those "quiet" runs in parallel and
+//            the literal rules (cpp:725-759) start at the first run with a hit.
+// A point without neighbours -- the worst case, it walks its whole window -- costs one memory round trip and a few
+// hundred instructions instead of ~100 dependent instructions per run. Other configurations: warp 0 walks alone
+// (d_probe_coop).
+__global__ void __launch_bounds__(128, 8) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
+{
+    CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy);
+    if (p.st->halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    const int R = cfg.R, msr = cfg.max_steps_row;
+    const int ncols = p.st->ncols;
+    const long long colbase = p.st->colbase;
+    const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
+    const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
+    const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int nheavy = p.st->n_heavy < p.maxcols * R ? p.st->n_heavy : p.maxcols * R;
+    CC_SMEM(smem);
+    float4* ring = reinterpret_cast<float4*>(smem);
+    __shared__ unsigned int brk_m[64], hit_m[64];
+    const bool masks_ok = CC_WARP == 32 && cfg.max_steps_col < 32 && 2 * msr + 1 <= 64 && !(tune & 1);
+    for (int hi = blockIdx.x; hi < nheavy; hi += gridDim.x)
+    {
+        const int pidx = p.heavy_list[hi];
+        if (!masks_ok)
+        {
+            if (warp == 0)
+                d_probe_coop(cfg, p, s_parent, s_links, ring, base_local, colbase, lane, pidx);
+            continue;
+        }
+        const int pci = pidx / R, prow = pidx - pci * R;
+        int plocal = base_local + pci;
+        if (plocal >= cfg.ringcols)
+            plocal -= cfg.ringcols;
+        const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
+        const float4 pa = p.assoc[pq];
+        const float ax = pa.x, ay = pa.y, az = pa.z, aw = pa.w;
+        const float mad = p.mad[pq];
+        int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+        steps_back = steps_back < msr ? steps_back : msr;
+        steps_back = steps_back < 0 ? 0 : steps_back;
+        const int nruns = 1 + 2 * steps_back; // run r: r = 0 own column upwards; odd r: column (r + 1) / 2 back, upwards
+                                              // from the own row; even r: same column downwards (cpp:707-719)
+        // ---- phase 1 ----
+        for (int r0 = 0; r0 < nruns; r0 += 8 * nwarps)
+        {
+            float4 b[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                const int r = r0 + warp + u * nwarps;
+                b[u] = make_float4(cc_nanf(), 0.f, 0.f, cc_nanf());
+                if (r < nruns)
+                {
+                    const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+                    const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+                    const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+                    int n = cfg.max_steps_col - start_step + 1;
+                    const int room = dir < 0 ? start_row + 1 : R - start_row;
+                    n = n < room ? n : room;
+                    int olocal = plocal - back;
+                    if (olocal < 0)
+                        olocal += cfg.ringcols; // cpp:768-769
+                    if (lane < n)
+                        b[u] = p.assoc[static_cast<size_t>(olocal) * R + (start_row + dir * lane)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                const int r = r0 + warp + u * nwarps;
+                // lanes beyond the run hold NaN: neither a break nor a hit
+                const bool brk = fabsf(b[u].w - aw) > mad; // cpp:728-729 (NaN never breaks)
+                bool hit = false;
+                if (!brk && !cc_isnan(b[u].x))
+                {
+                    const float dx = ax - b[u].x, dy = ay - b[u].y, dz = az - b[u].z;
+                    hit = dx * dx + dy * dy + dz * dz < cfg.max_distance_sq; // cpp:638-641
+                }
+                const unsigned int bm = __ballot_sync(CC_FULL_MASK, brk);
+                const unsigned int hm = __ballot_sync(CC_FULL_MASK, hit);
+                if (lane == 0 && r < nruns)
+                {
+                    brk_m[r] = bm;
+                    hit_m[r] = hm;
                 }
             }
         }
         __syncthreads();
+        // ---- phase 2 ----
+        if (warp == 0)
+        {
+            const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
+            unsigned int first = CC_NONE;
+            int visited = 0, nlinks = 0;
+            bool flagged = false;
+            // quiet prefix: runs without a hit before their break, summed by the lanes
+            int q = nruns;
+            for (int half = 0; half < 2 && q == nruns; half++)
+            {
+                const int r = half * 32 + lane;
+                bool loud = false;
+                int contrib = 0;
+                if (r < nruns)
+                {
+                    const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+                    const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+                    const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+                    int n = cfg.max_steps_col - start_step + 1;
+                    const int room = dir < 0 ? start_row + 1 : R - start_row;
+                    n = n < room ? n : room;
+                    if (n > 0)
+                    {
+                        const unsigned int brk_mask = brk_m[r];
+                        const int limit = brk_mask ? __ffs(brk_mask) - 1 : n;
+                        const unsigned int below_limit = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
+                        loud = (hit_m[r] & below_limit) != 0;
+                        contrib = limit < n ? limit + 1 : n;
+                    }
+                }
+                const unsigned int loud_mask = __ballot_sync(CC_FULL_MASK, loud);
+                if (loud_mask)
+                {
+                    const int l = __ffs(loud_mask) - 1;
+                    q = half * 32 + l;
+                    visited += __reduce_add_sync(CC_FULL_MASK, lane < l ? contrib : 0);
+                }
+                else
+                    visited += __reduce_add_sync(CC_FULL_MASK, contrib);
+            }
+            for (int r = q; r < nruns; r++)
+            {
+                const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+                const int start_step = (dir == 1 || back == 0) ? 1 : 0;
+                const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
+                int n = cfg.max_steps_col - start_step + 1; // cells of this vertical run
+                const int room = dir < 0 ? start_row + 1 : R - start_row;
+                n = n < room ? n : room;
+                if (n > 0)
+                {
+                    const int cnt = n;
+                    const unsigned int brk_mask = brk_m[r], hit_mask = hit_m[r];
+                    const int limit = brk_mask ? __ffs(brk_mask) - 1 : cnt; // cells before the break are processed
+                    const unsigned int below_limit = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
+                    // early stop once associated (cpp:747-749): after the first cell with steps >= min steps
+                    int jstop = 0x7fffffff;
+                    if (cfg.stop_enabled)
+                    {
+                        const int need = cfg.stop_min_steps - start_step; // lane index where steps >= min
+                        if (first != CC_NONE)
+                            jstop = need > 0 ? need : 0;
+                        else if (hit_mask & below_limit)
+                        {
+                            const int jh = __ffs(hit_mask & below_limit) - 1;
+                            jstop = jh > need ? jh : need;
+                        }
+                    }
+                    int processed = limit; // number of cells whose association step runs
+                    bool stopped = false;
+                    if (jstop < limit)
+                    {
+                        processed = jstop + 1;
+                        stopped = true;
+                    }
+                    visited += stopped ? processed : (limit < cnt ? limit + 1 : cnt);
+                    const unsigned int proc_mask = processed >= 32 ? 0xffffffffu : ((1u << processed) - 1u);
+                    unsigned int hp = hit_mask & proc_mask;
+                    if (hp)
+                    {
+                        int olocal = plocal - back;
+                        if (olocal < 0)
+                            olocal += cfg.ringcols;
+                        const unsigned int o = static_cast<unsigned int>(olocal) * R + (lane < cnt ? start_row + dir * lane : 0);
+                        if ((hp >> lane) & 1u) // every hit lane checks its own target
+                        {
+                            // could the reference have refused this hit?
+                            const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
+                            if (finish_o <= prev_runmax)
+                                flagged = true;
+                            if (back > pci)
+                            {
+                                const unsigned int ro = p.tparent[o];
+                                if (ro == CC_NONE || p.tstate[ro] != 0)
+                                    flagged = true;
+                            }
+                        }
+                        if (first == CC_NONE)
+                        {
+                            const int jf = __ffs(hp) - 1;
+                            first = __shfl_sync(CC_FULL_MASK, o, jf);
+                            hp &= hp - 1;
+                        }
+                        // the remaining hits are tree<->tree link candidates (cpp:740-741)
+                        if ((hp >> lane) & 1u)
+                        {
+                            const int slot = nlinks + __popc(hp & lt_mask);
+                            if (slot < CC_LINK_SLOTS)
+                                s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + slot] = o;
+                            else
+                            {
+                                const int e = atomicAdd(&p.st->n_edges, 1);
+                                if (e < p.cap_edges)
+                                {
+                                    p.edge_a[e] = pq;
+                                    p.edge_b[e] = o;
+                                }
+                                else
+                                    p.st->error = CC_DEV_LIST_OVERFLOW;
+                            }
+                        }
+                        nlinks += __popc(hp);
+                    }
+                }
+                if ((r == 0 || !(r & 1)) && first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
+                    break; // cpp:757-759, after both runs of a column
+            }
+            const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
+                                  (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
+            for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
+                s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
+            if (lane == 0)
+            {
+                s_parent[pidx] = first == CC_NONE ? pq : first;
+                p.visited[pq] = static_cast<unsigned short>(visited);
+                if (any_flag)
+                {
+                    p.col_flag[pci] = 1;
+                    atomicAdd(&p.st->n_flagged, 1);
+                }
+            }
+        }
+        __syncthreads(); // the masks are rewritten for the next point
     }
 }
 
@@ -2278,6 +2792,7 @@ __device__ void d_snapshot(CcDevPtrs p, int spec)
 __global__ void k_snapshot(CcDevPtrs p, int guard)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_snapshot);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     d_snapshot(p, guard);
@@ -2286,6 +2801,7 @@ __global__ void k_snapshot(CcDevPtrs p, int guard)
 __global__ void k_restore(CcDevPtrs p)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore);
     const int n = p.st->n_ulist_saved;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
@@ -2300,6 +2816,7 @@ __global__ void k_restore(CcDevPtrs p)
 __global__ void k_restore_finish(CcDevPtrs p)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore_finish);
     p.st->n_ulist = p.st->n_ulist_saved;
     p.st->abort = 0;
     p.st->n_clusters = p.st->sv_n_clusters;
@@ -2309,6 +2826,7 @@ __global__ void k_restore_finish(CcDevPtrs p)
 __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_copy);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2379,6 +2897,7 @@ CC_DEV unsigned long long cc_group_max_u64(bool mine, unsigned long long v)
 __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_roots);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2438,6 +2957,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
                                int ci0, int ci1, int spec)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_links);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -2489,6 +3009,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
 __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_careful);
     if (blockIdx.x != 0 || threadIdx.x != 0)
         return;
     const int R = cfg.R;
@@ -2900,6 +3421,7 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
                                                   int exact, int last, int smem_bytes, CcDevState* snap)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_all);
     if (blockIdx.x != 0)
         return;
     if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -2909,7 +3431,10 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         return;
     }
     CC_SMEM(smem);
-    d_fin_init(cfg, p, ci0, ci1, guard);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_init);
+        d_fin_init(cfg, p, ci0, ci1, guard);
+    }
     __syncthreads();
     // shared memory: [block-scan scratch: T x 8 B][running maximum of the segment's columns | prefix maxima of G]
     const int T = blockDim.x;
@@ -2927,15 +3452,30 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         }
     }
     __syncthreads();
-    d_fin_agg(cfg, p, guard);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_agg);
+        d_fin_agg(cfg, p, guard);
+    }
     __syncthreads();
-    d_fin_decide(cfg, p, guard, exact, runmax_s);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_decide);
+        d_fin_decide(cfg, p, guard, exact, runmax_s);
+    }
     __syncthreads();
-    d_fin_mark(cfg, p, seq, guard);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_mark);
+        d_fin_mark(cfg, p, seq, guard);
+    }
     __syncthreads();
-    d_fin_copyback(p, guard);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_copyback);
+        d_fin_copyback(p, guard);
+    }
     __syncthreads();
-    d_fin_columns(cfg, p, guard, spare * 2);
+    {
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns);
+        d_fin_columns(cfg, p, guard, spare * 2);
+    }
     __syncthreads();
     if (last && threadIdx.x == 0)
         d_push_done(p, guard);
@@ -2951,6 +3491,7 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_spec_ok(p.st, spec))
@@ -3034,6 +3575,7 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_clear);
     CcDevState* st = p.st;
     if (mode)
     {
@@ -3079,6 +3621,7 @@ __device__ void d_push_done(CcDevPtrs p, int guard);
 __global__ void k_push_done(CcDevPtrs p, int guard)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_push_done);
     d_push_done(p, guard);
 }
 __device__ void d_push_done(CcDevPtrs p, int guard)
@@ -3100,6 +3643,7 @@ __device__ void d_push_done(CcDevPtrs p, int guard)
 __global__ void k_halt(CcDevPtrs p, int mode)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_halt);
     CcDevState* st = p.st;
     if (mode < 0)
         st->halted = 0;
@@ -3112,6 +3656,7 @@ __global__ void k_halt(CcDevPtrs p, int mode)
 __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_pack_labels);
     const CcDevState* st = p.st;
     if (st->halted)
         return;
@@ -3132,6 +3677,7 @@ __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_co
 __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
 {
     CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_state_snapshot);
     d_state_snapshot(p, dst);
 }
 

@@ -35,12 +35,19 @@ static inline cudaError_t cc_launch(void (*kernel)(KArgs...), int grid, int bloc
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #define CC_LAUNCH(kernel, grid, block, smem, stream, ...) cc_launch(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
+#ifdef CC_NO_PDL /* profiling aid: kernels without the two griddepcontrol instructions */
+#define CC_PDL_ENTER()                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+    } while (0)
+#else
 #define CC_PDL_ENTER()                                                                                                 \
     do                                                                                                                 \
     {                                                                                                                  \
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");                                                \
         asm volatile("griddepcontrol.wait;" ::: "memory");                                                             \
     } while (0)
+#endif
 #define CC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define CC_FULL_MASK 0xffffffffu
 #endif

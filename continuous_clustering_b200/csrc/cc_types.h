@@ -87,6 +87,8 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     int n_ulist;       // unfinished point trees (sc_unfinished_point_trees_, hpp:273)
     int n_ulist_saved;
     int n_edges;       // tree<->tree link candidates found by the probe
+    int n_probe;       // non-ignored points of the new columns (association probe work list)
+    int n_heavy;       // of those, the points left to the warp-cooperative walk
     int n_flagged;     // columns with an association that the reference might have refused (cpp:654-659, 688-690)
     long long danger_col; // first column at which a cluster could be force-finished (cpp:909-919), CC_COL_INF if none
     int abort;            // speculative commit must be rolled back
@@ -177,6 +179,7 @@ struct CcDevPtrs
     float* s_incl;
     float* s_incaz;
     int* s_cwr;
+    int* s_cwrT;          // the same, [row][max_firings]
     int* o_g;             // resolved global column relative to CcDevState::scan_base, INT_MIN = not stored
     int* o_rot;           // rotation index used for the continuous azimuth
     CcFiringRecord* firing_rec; // [max_firings]
@@ -193,6 +196,8 @@ struct CcDevPtrs
     double* col_minaz;    // current_minimum_continuous_azimuth_angle (cpp:777, 791-793)
     double* col_runmax;   // running max of col_minaz including earlier pushes
     long long* col_first_unpub; // sc_first_unpublished_global_column_index after the column's pass
+    int* probe_list;            // [maxcols * R] new-column cell (ci * R + row) of every non-ignored point
+    int* heavy_list;            // [maxcols * R] subset of probe_list for k_probe_heavy
     unsigned char* col_flag;    // association of this column must be redone column-sequentially
     // ---- clustering scratch ----
     unsigned int* ulist;     // unfinished roots (current)
@@ -215,6 +220,7 @@ struct CcDevPtrs
     CcCluster* clusters;
     CcClusterPoint* cluster_points;
     int* n_new_ulist;
+    unsigned long long* trace; // optional device-side timeline (cc_debug_trace), else null
     int cap_ulist, cap_edges, cap_clusters, cap_cluster_points, cap_G, maxcols, max_firings;
 };
 

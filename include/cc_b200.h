@@ -283,6 +283,14 @@ CC_API cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_
  * through the column-sequential exact kernels. Results must not change. 0 = off. */
 CC_API cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period);
 
+/* Debug hook: device-side timeline. While enabled, thread 0 of every block of every kernel stamps its entry and exit
+ * with the GPU's global nanosecond timer; cc_debug_get_trace reduces what the pushes since the last call left behind
+ * to four values per kernel (first block entry, last block exit, longest single block, blocks seen; nanoseconds) and
+ * the ';'-separated kernel names, then clears the buffer. Unlike cc_set_kernel_timing this does not serialise the
+ * launches: it shows the kernels as they overlap in a normal push. */
+CC_API cc_status_t cc_debug_trace(cc_handle_t* h, int enable);
+CC_API cc_status_t cc_debug_get_trace(cc_handle_t* h, char* names, int names_cap, uint64_t* out, int cap_kernels, int* n_out);
+
 /* Debug hook: 1 if the event `which` (0 start, 1 end of kernels, 2 state snapshot ready, 3 results on the host) of
  * in-flight slot 0/1 has completed. */
 CC_API int cc_debug_event_query(cc_handle_t* h, int slot, int which);

@@ -12,7 +12,7 @@ import tempfile
 rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(REPO, "continuous_clustering_b200", "libcc_b200.so")
+lib = os.environ.get("CC_LIB", os.path.join(REPO, "continuous_clustering_b200", "libcc_b200.so"))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = [r for r in csv.reader(raw.splitlines())]
