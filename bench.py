@@ -389,11 +389,13 @@ def main():
         cc.addFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
     barrier()
     t0 = time.perf_counter()
-    # two pushes in flight: the host->device copy of push k + 1 (copy stream) overlaps the kernels of push k
-    cc.submitFirings(h_pts[W * B:(W + 1) * B], h_poses[W * B:(W + 1) * B])
+    # two pushes in flight and a third one staged: the host->device copy of push k + 2 (input stream) overlaps the
+    # kernels of pushes k and k + 1; its kernels are launched by the wait() that returns push k
+    for s in range(W, min(W + 2, W + K)):
+        cc.submitFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
     for s in range(W, W + K):
-        if s + 1 < W + K:
-            cc.submitFirings(h_pts[(s + 1) * B:(s + 2) * B], h_poses[(s + 1) * B:(s + 2) * B])
+        if s + 2 < W + K:
+            cc.submitFirings(h_pts[(s + 2) * B:(s + 3) * B], h_poses[(s + 2) * B:(s + 3) * B])
         res = cc.wait()
         labels = cc.column_labels()  # [n_cols, rows, 4] u8: ground label, debug label, is_ignored, intensity
         assert labels.shape[0] == int(res.info.ground_to_gcol - res.info.ground_from_gcol)

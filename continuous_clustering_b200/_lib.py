@@ -117,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "cc_total_launches", "cc_selftest_math", "cc_set_kernel_timing", "cc_get_kernel_timings",
     "cc_debug_flag_columns", "cc_get_result_views", "cc_submit_firings", "cc_submit_firings_device", "cc_wait", "cc_pending",
     "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
-    "cc_debug_trace", "cc_debug_get_trace",
+    "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times",
 ]
 
 
@@ -162,6 +162,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_set_kernel_timing.argtypes = [vp, i32]
     lib.cc_debug_flag_columns.argtypes = [vp, i32]
     lib.cc_debug_trace.argtypes = [vp, i32]
+    lib.cc_debug_slot_base.argtypes = [vp]
+    lib.cc_debug_slot_times.argtypes = [vp, i32, vp]
     lib.cc_debug_get_trace.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32)]
     lib.cc_get_kernel_timings.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32)]
     return lib

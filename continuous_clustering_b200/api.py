@@ -237,7 +237,8 @@ class ContinuousClustering:
         self._dispatch(out)
         return out
 
-    # ---- asynchronous pushes: keep the GPU busy with submit(k + 1); wait(k) ----
+    # ---- asynchronous pushes: keep the GPU busy with submit(k + 2); wait(k) (two pushes in flight; a third host push
+    #      is staged: its input copy starts at once, its kernels when wait() makes room) ----
     def submitFirings(self, points: np.ndarray, poses: np.ndarray):
         points = np.ascontiguousarray(points, dtype=RAW_POINT_DTYPE)
         poses = np.ascontiguousarray(poses, dtype=np.float64)

@@ -65,17 +65,14 @@ struct cc_handle
         CcCluster* d_clusters{nullptr};
         CcClusterPoint* d_points{nullptr};
         uchar4* d_labels{nullptr};
-        unsigned char* d_raw{nullptr};
-        double* d_poses{nullptr};
         // page-locked host
         CcDevState* h_state{nullptr};
         long long* h_first_unpub{nullptr};
         CcCluster* h_clusters{nullptr};
         CcClusterPoint* h_points{nullptr};
-        uchar4* h_labels{nullptr};
-        void* h_raw{nullptr};
-        double* h_poses{nullptr};
-        cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr}, h2d{nullptr};
+        uchar4* h_labels{nullptr}; // one of the handle's three label buffers (borrowed)
+        cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr};
+        cudaEvent_t h2d{nullptr}, h2d0{nullptr}; // of the input buffer the push reads (borrowed, not owned)
         // the push occupying the slot
         int n{0};
         const void* in_points{nullptr}; // device pointers of the inputs
@@ -84,6 +81,24 @@ struct cc_handle
         uint64_t launches0{0}, launches1{0};
         int pre_cols{0}, pre_clusters{0}, pre_points{0};
     } slots[2];
+    // Input staging for host pushes, one more buffer than pushes in flight: a push submitted while two are in flight
+    // starts its host -> device copy at once and waits "staged"; its kernels are launched when the oldest push in flight
+    // has been waited for. The copy of push k + 2 thereby overlaps the kernels of pushes k and k + 1.
+    struct InBuf
+    {
+        unsigned char* d_raw{nullptr};
+        double* d_poses{nullptr};
+        void* h_raw{nullptr}; // page-locked staging for callers whose buffers are pageable
+        double* h_poses{nullptr};
+        cudaEvent_t h2d0{nullptr}, h2d{nullptr};
+        int n{0};
+    } inbuf[3];
+    int next_in{0};
+    // page-locked label buffers: two pushes in flight + the labels of the last finished push, which stay valid until
+    // the next cc_wait()
+    uchar4* h_label_ring[3]{nullptr, nullptr, nullptr};
+    int next_label{0};
+    int staged{-1}; // input buffer of the staged push, -1 none
     int next_slot{0};
     int pending[2]{-1, -1}; // slots of the pushes in flight, oldest first
     int n_pending{0};
@@ -163,7 +178,7 @@ static void free_host_slots(cc_handle* h)
     for (cc_handle::Slot& sl : h->slots)
     {
         for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters),
-                        static_cast<void*>(sl.h_points), static_cast<void*>(sl.h_labels), sl.h_raw, static_cast<void*>(sl.h_poses)})
+                        static_cast<void*>(sl.h_points)})
             if (q)
                 cudaFreeHost(q);
         sl.h_state = nullptr;
@@ -171,8 +186,21 @@ static void free_host_slots(cc_handle* h)
         sl.h_clusters = nullptr;
         sl.h_points = nullptr;
         sl.h_labels = nullptr;
-        sl.h_raw = nullptr;
-        sl.h_poses = nullptr;
+    }
+    for (uchar4*& q : h->h_label_ring)
+    {
+        if (q)
+            cudaFreeHost(q);
+        q = nullptr;
+    }
+    for (cc_handle::InBuf& ib : h->inbuf)
+    {
+        if (ib.h_raw)
+            cudaFreeHost(ib.h_raw);
+        if (ib.h_poses)
+            cudaFreeHost(ib.h_poses);
+        ib.h_raw = nullptr;
+        ib.h_poses = nullptr;
     }
 }
 
@@ -312,7 +340,13 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     for (cc_handle::Slot& sl : h->slots)
         if (cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess ||
             cudaEventCreate(&sl.ready) != cudaSuccess || cudaEventCreate(&sl.done) != cudaSuccess ||
-            cudaEventCreate(&sl.h2d) != cudaSuccess)
+            false)
+        {
+            delete h;
+            return CC_ERR_CUDA;
+        }
+    for (cc_handle::InBuf& ib : h->inbuf)
+        if (cudaEventCreate(&ib.h2d) != cudaSuccess || cudaEventCreate(&ib.h2d0) != cudaSuccess)
         {
             delete h;
             return CC_ERR_CUDA;
@@ -346,7 +380,11 @@ void cc_destroy(cc_handle_t* h)
         cudaStreamSynchronize(h->copy_stream);
     free_host_slots(h);
     for (cc_handle::Slot& sl : h->slots)
-        for (cudaEvent_t e : {sl.ev0, sl.ev1, sl.ready, sl.done, sl.h2d})
+        for (cudaEvent_t e : {sl.ev0, sl.ev1, sl.ready, sl.done})
+            if (e)
+                cudaEventDestroy(e);
+    for (cc_handle::InBuf& ib : h->inbuf)
+        for (cudaEvent_t e : {ib.h2d, ib.h2d0})
             if (e)
                 cudaEventDestroy(e);
     if (h->copy_stream)
@@ -488,6 +526,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     CC_CHECK(h, cudaStreamSynchronize(h->in_stream));
     h->n_pending = 0;
     h->next_slot = 0;
+    h->staged = -1;
     const int N = h->config.num_columns;
     const bool realloc_ring = (num_rows != h->R) || (N != h->N) || h->allocs.empty();
     if (realloc_ring)
@@ -590,18 +629,22 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, dev_alloc(h, L, &sl.d_clusters, static_cast<size_t>(d.cap_clusters)));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_points, static_cast<size_t>(d.cap_cluster_points)));
             CC_CHECK(h, dev_alloc(h, L, &sl.d_labels, mc * h->R));
-            CC_CHECK(h, dev_alloc(h, L, &sl.d_raw, stage * sizeof(cc_raw_point_t)));
-            CC_CHECK(h, dev_alloc(h, L, &sl.d_poses, static_cast<size_t>(h->max_firings) * 12));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_state), sizeof(CcDevState)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_first_unpub), mc * sizeof(long long)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
-            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_labels), mc * h->R * sizeof(uchar4)));
-            CC_CHECK(h, cudaMallocHost(&sl.h_raw, stage * sizeof(cc_raw_point_t)));
-            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
         }
-        d.raw = h->slots[0].d_raw;
-        d.poses = h->slots[0].d_poses;
+        for (uchar4*& q : h->h_label_ring)
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&q), mc * h->R * sizeof(uchar4)));
+        for (cc_handle::InBuf& ib : h->inbuf)
+        {
+            CC_CHECK(h, dev_alloc(h, L, &ib.d_raw, stage * sizeof(cc_raw_point_t)));
+            CC_CHECK(h, dev_alloc(h, L, &ib.d_poses, static_cast<size_t>(h->max_firings) * 12));
+            CC_CHECK(h, cudaMallocHost(&ib.h_raw, stage * sizeof(cc_raw_point_t)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&ib.h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
+        }
+        d.raw = h->inbuf[0].d_raw;
+        d.poses = h->inbuf[0].d_poses;
         d.col_first_unpub = h->slots[0].d_first_unpub;
         d.clusters = h->slots[0].d_clusters;
         d.cluster_points = h->slots[0].d_points;
@@ -1140,11 +1183,27 @@ static cc_status_t check_push(cc_handle* h, int n, int rows)
         h->error = n <= 0 ? "empty push" : "too many firings in one push (limit: min(max_firings_per_push, 3 * num_columns))";
         return n <= 0 ? CC_ERR_INVALID_ARGUMENT : CC_ERR_BATCH_TOO_LARGE;
     }
-    if (h->n_pending >= 2)
-    {
-        h->error = "two pushes are already in flight: call cc_wait() first";
-        return CC_ERR_INVALID_ARGUMENT;
-    }
+    return CC_OK;
+}
+
+// Launches the kernels of the push whose inputs are in input buffer `ib` (or at the caller's device pointers).
+static cc_status_t launch_from(cc_handle* h, int n, const void* d_points, const double* d_poses, const cc_handle::InBuf* ib)
+{
+    cc_handle::Slot& sl = h->slots[h->next_slot];
+    sl.n = n;
+    sl.in_points = d_points;
+    sl.in_poses = d_poses;
+    sl.h_labels = h->h_label_ring[h->next_label];
+    h->next_label = (h->next_label + 1) % 3;
+    sl.h2d = ib ? ib->h2d : nullptr;
+    sl.h2d0 = ib ? ib->h2d0 : nullptr;
+    if (ib)
+        CC_CHECK(h, cudaStreamWaitEvent(h->stream, ib->h2d, 0));
+    cc_status_t s = launch_push(h, sl);
+    if (s != CC_OK)
+        return s;
+    h->pending[h->n_pending++] = h->next_slot;
+    h->next_slot ^= 1;
     return CC_OK;
 }
 
@@ -1155,53 +1214,52 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
         return s;
     if (!points || !poses)
         return CC_ERR_INVALID_ARGUMENT;
+    if (h->staged >= 0 || (h->n_pending >= 2 && device_inputs))
+    {
+        h->error = device_inputs ? "two pushes are already in flight: call cc_wait() first"
+                                 : "two pushes are in flight and a third is staged: call cc_wait() first";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
     CC_CHECK(h, cudaSetDevice(h->device));
-    cc_handle::Slot& sl = h->slots[h->next_slot];
-    sl.n = n;
     if (device_inputs)
-    {
-        sl.in_points = points;
-        sl.in_poses = poses;
-    }
-    else
-    {
-        const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
-        // page-locked caller buffers are copied straight to the device; anything else goes through the slot's own
-        // pinned staging buffer first. The copy runs on the copy stream, so it overlaps the kernels of the push
-        // before this one.
-        const void* src_pts = points;
-        const void* src_poses = poses;
+        return launch_from(h, n, points, poses, nullptr);
+    cc_handle::InBuf& ib = h->inbuf[h->next_in];
+    const size_t pb = static_cast<size_t>(n) * rows * sizeof(cc_raw_point_t), qb = static_cast<size_t>(n) * 12 * sizeof(double);
+    // page-locked caller buffers are copied straight to the device; anything else goes through the input buffer's own
+    // pinned staging area first. The copy runs on its own stream: it overlaps the kernels of the pushes in flight.
+    const void* src_pts = points;
+    const void* src_poses = poses;
 #ifndef CC_EMU
-        cudaPointerAttributes attr;
-        const bool pts_pinned = cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        const bool poses_pinned = cudaPointerGetAttributes(&attr, poses) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
+    cudaPointerAttributes attr;
+    const bool pts_pinned = cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    const bool poses_pinned = cudaPointerGetAttributes(&attr, poses) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
 #else
-        const bool pts_pinned = false, poses_pinned = false;
+    const bool pts_pinned = false, poses_pinned = false;
 #endif
-        if (!pts_pinned)
-        {
-            std::memcpy(sl.h_raw, points, pb);
-            src_pts = sl.h_raw;
-        }
-        if (!poses_pinned)
-        {
-            std::memcpy(sl.h_poses, poses, qb);
-            src_poses = sl.h_poses;
-        }
-        CC_CHECK(h, cudaMemcpyAsync(sl.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
-        CC_CHECK(h, cudaMemcpyAsync(sl.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
-        CC_CHECK(h, cudaEventRecord(sl.h2d, h->in_stream));
-        CC_CHECK(h, cudaStreamWaitEvent(h->stream, sl.h2d, 0));
-        sl.in_points = sl.d_raw;
-        sl.in_poses = sl.d_poses;
+    if (!pts_pinned)
+    {
+        std::memcpy(ib.h_raw, points, pb);
+        src_pts = ib.h_raw;
     }
-    s = launch_push(h, sl);
-    if (s != CC_OK)
-        return s;
-    h->pending[h->n_pending++] = h->next_slot;
-    h->next_slot ^= 1;
-    return CC_OK;
+    if (!poses_pinned)
+    {
+        std::memcpy(ib.h_poses, poses, qb);
+        src_poses = ib.h_poses;
+    }
+    CC_CHECK(h, cudaEventRecord(ib.h2d0, h->in_stream));
+    CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
+    CC_CHECK(h, cudaMemcpyAsync(ib.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
+    CC_CHECK(h, cudaEventRecord(ib.h2d, h->in_stream));
+    ib.n = n;
+    const int mine = h->next_in;
+    h->next_in = (h->next_in + 1) % 3;
+    if (h->n_pending >= 2)
+    {
+        h->staged = mine; // launched by the cc_wait() that makes room
+        return CC_OK;
+    }
+    return launch_from(h, n, ib.d_raw, ib.d_poses, &ib);
 }
 
 cc_status_t cc_submit_firings(cc_handle_t* h, int n, int rows, const cc_raw_point_t* points, const double* poses)
@@ -1219,17 +1277,30 @@ cc_status_t cc_wait(cc_handle_t* h)
     if (!h)
         return CC_ERR_INVALID_ARGUMENT;
     CC_CHECK(h, cudaSetDevice(h->device));
-    return finish_push(h);
+    const cc_status_t s = finish_push(h);
+    if (s != CC_OK)
+    {
+        h->staged = -1; // dropped with the pushes in flight (the stream needs a reset)
+        return s;
+    }
+    if (h->staged >= 0 && h->n_pending < 2)
+    {
+        const cc_handle::InBuf& ib = h->inbuf[h->staged];
+        h->staged = -1;
+        // finish_push left its results in the handle: launching must not disturb them (it only enqueues work)
+        return launch_from(h, ib.n, ib.d_raw, ib.d_poses, &ib);
+    }
+    return CC_OK;
 }
 
 int cc_pending(const cc_handle_t* h)
 {
-    return h ? h->n_pending : 0;
+    return h ? h->n_pending + (h->staged >= 0 ? 1 : 0) : 0;
 }
 
 static cc_status_t push_sync(cc_handle* h, int n, int rows, const void* points, const double* poses, bool device_inputs)
 {
-    if (h && h->n_pending > 0)
+    if (h && (h->n_pending > 0 || h->staged >= 0))
     {
         h->error = "asynchronous pushes are in flight: call cc_wait() first";
         return CC_ERR_INVALID_ARGUMENT;
@@ -1439,6 +1510,36 @@ cc_status_t cc_get_column_labels(const cc_handle_t* h, const uint8_t** labels, i
         return CC_ERR_INVALID_ARGUMENT;
     *labels = reinterpret_cast<const uint8_t*>(h->cur_labels);
     *n_cols = h->cur_labels ? h->cur_label_cols : 0;
+    return CC_OK;
+}
+
+cc_status_t cc_debug_slot_times(cc_handle_t* h, int slot, float out_ms[5])
+{
+    if (!h || slot < 0 || slot > 1 || !out_ms || !h->ev0)
+        return CC_ERR_INVALID_ARGUMENT;
+    cc_handle::Slot& sl = h->slots[slot];
+    // relative to the handle's base event (recorded by cc_debug_slot_base): input copy start / end, kernels start /
+    // end, results on the host; -1 where an event has not been recorded or has not completed
+    cudaEvent_t ev[5] = {sl.h2d0, sl.h2d, sl.ev0, sl.ev1, sl.done};
+    for (int i = 0; i < 5; i++)
+    {
+        float ms = -1.f;
+        if (!ev[i] || cudaEventElapsedTime(&ms, h->ev0, ev[i]) != cudaSuccess)
+            ms = -1.f;
+        out_ms[i] = ms;
+    }
+    cudaGetLastError();
+    return CC_OK;
+}
+
+cc_status_t cc_debug_slot_base(cc_handle_t* h)
+{
+    if (!h)
+        return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    CC_CHECK(h, cudaDeviceSynchronize());
+    CC_CHECK(h, cudaEventRecord(h->ev0, h->stream));
+    CC_CHECK(h, cudaEventSynchronize(h->ev0));
     return CC_OK;
 }
 

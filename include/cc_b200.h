@@ -291,6 +291,11 @@ CC_API cc_status_t cc_debug_flag_columns(cc_handle_t* h, int period);
 CC_API cc_status_t cc_debug_trace(cc_handle_t* h, int enable);
 CC_API cc_status_t cc_debug_get_trace(cc_handle_t* h, char* names, int names_cap, uint64_t* out, int cap_kernels, int* n_out);
 
+/* Debug hook: host-visible milestones of the push that last used in-flight slot 0/1, in milliseconds since
+ * cc_debug_slot_base(): input copy start, input copy end, first kernel, last kernel, results on the host. */
+CC_API cc_status_t cc_debug_slot_base(cc_handle_t* h);
+CC_API cc_status_t cc_debug_slot_times(cc_handle_t* h, int slot, float out_ms[5]);
+
 /* Debug hook: 1 if the event `which` (0 start, 1 end of kernels, 2 state snapshot ready, 3 results on the host) of
  * in-flight slot 0/1 has completed. */
 CC_API int cc_debug_event_query(cc_handle_t* h, int slot, int which);
