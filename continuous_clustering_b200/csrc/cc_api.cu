@@ -904,9 +904,9 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
 
     CC_CHECK(h, cudaEventRecord(sl.ev0, h->stream));
     const int R = h->R;
-    CC_RUN(h, k_clear, h->sm_count * 8, 256, 0, cfg, h->d, 0LL, 0LL, 1); // columns retired by the previous push
     const long long pts = static_cast<long long>(n) * R;
-    CC_RUN(h, k_prep, grid_for(h, static_cast<long long>(n) * CC_WARP, 256), 256, 0, cfg, h->d, n);
+    // recycles the columns retired two pushes ago, then prepares the firings
+    CC_RUN(h, k_prep, std::max(grid_for(h, static_cast<long long>(n) * CC_WARP, 256), h->sm_count * 2), 256, 0, cfg, h->d, n);
     // lite insertion path (regular prefix of the push, grid-wide) ...
     {
 #ifndef CC_EMU

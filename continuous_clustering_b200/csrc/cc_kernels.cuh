@@ -281,12 +281,19 @@ CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/
     return d;
 }
 
+CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to);
+
 __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_prep);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    // K5 first: clearColumns (cpp:1094-1145) for the columns retired TWO pushes ago. Recycling is deferred so that every
+    // column a push reports through a finished-column event can still be read by the caller after the push has been
+    // waited for, even while the next push is already in flight (the reference's callbacks read range_image_ before
+    // clearColumns runs, cpp:1087-1091). Pure stores: they drain while the firings below are being prepared.
+    d_clear(cfg, p, p.st->clear2_from, p.st->clear2_to);
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
     // (anchor = column-in-rotation of its first valid row; rearmost / foremost column relative to the anchor)
     const int R = cfg.R;
@@ -1545,14 +1552,14 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
         const int nc = (nchunks - cb) < tile_chunks ? (nchunks - cb) : tile_chunks;
         const int n = nc * R;
         const float* src = p.gap_chunk_last + static_cast<size_t>(cb) * R;
-        for (int i0 = 0; i0 < n; i0 += 8 * T)
+        for (int i0 = 0; i0 < n; i0 += 16 * T)
         {
-            float v[8];
+            float v[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
                 v[u] = i0 + u * T + t < n ? cc_ldcg_f32(src + i0 + u * T + t) : nanv;
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
                 if (i0 + u * T + t < n)
                     sh_tile[i0 + u * T + t] = v[u];
         }
@@ -2104,14 +2111,14 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
     for (int c0 = 0; c0 < ncols; c0 += 2048)
     {
         const int n = (ncols - c0) < 2048 ? (ncols - c0) : 2048;
-        for (int i0 = 0; i0 < n; i0 += 8 * T)
+        for (int i0 = 0; i0 < n; i0 += 16 * T)
         {
-            double v[8];
+            double v[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
                 v[u] = i0 + u * T + t < n ? cc_ldcg_f64(p.col_minaz + c0 + i0 + u * T + t) : -1.0;
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
                 if (i0 + u * T + t < n)
                     sh_az[i0 + u * T + t] = v[u];
         }
@@ -2926,10 +2933,14 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
                 r = CC_NONE; // a root contributes nothing to itself
             if (r != CC_NONE)
             {
+                // concurrent pointer jumping: every hop is published in the cell's own entry (always an ancestor, finally
+                // the root), so the walks of the other cells of the tree shortcut through it
                 unsigned int n;
                 while ((n = cc_vload(p.tparent + r)) != r)
+                {
+                    *reinterpret_cast<volatile unsigned int*>(p.tparent + q) = n;
                     r = n;
-                p.tparent[q] = r;
+                }
                 fin = cc_d2ord(p.cont_az[q] + static_cast<double>(p.mad[q]));
             }
         }
@@ -3572,18 +3583,8 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 // every column a push reports through a finished-column event can still be read by the caller after the push has
 // been waited for, even while the next push is already in flight (the reference's callbacks read range_image_
 // before clearColumns runs, cpp:1087-1091).
-__global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
+CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_clear);
-    CcDevState* st = p.st;
-    if (mode)
-    {
-        if (st->halted)
-            return;
-        from = st->clear2_from;
-        to = st->clear2_to;
-    }
     if (from < 0)
         from = 0;
     if (to <= from)
@@ -3613,6 +3614,22 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
         if (row == 0)
             p.slot_gcol[local] = -1;
     }
+}
+
+// explicit range [from, to) (reset). The columns retired during normal operation are recycled by k_prep.
+__global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
+{
+    CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_clear);
+    CcDevState* st = p.st;
+    if (mode)
+    {
+        if (st->halted)
+            return;
+        from = st->clear2_from;
+        to = st->clear2_to;
+    }
+    d_clear(cfg, p, from, to);
 }
 
 // end of a push: remember the range of columns that left the ring (recycled at the start of the next push) and
