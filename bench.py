@@ -44,12 +44,15 @@ METRIC = "range-image columns/s, 64-ring stream"
 
 # algorithmic bytes per range-image cell, per kernel (151 B/cell for the path)
 KERNEL_BYTES_PER_CELL = {
-    "k_prep": 12 + 24,  # read x,y,z (+ pose, amortised); write staged odom xyz, distance, azimuth, inclination, column
+    # read x,y,z (+ pose, amortised); write staged odom xyz, distance, azimuth, inclination, column (twice: per firing
+    # and per row); + every field group reset for a recycled cell (one cell retired per cell inserted in steady state)
+    "k_prep": 12 + 28 + (57 + 3 + 8 + 16 + 4 + 4 + 4 + 2 + 4),
     "k_insert_scan": 8 + 12 + 4,  # read column-in-rotation + distance; write resolved column + rotation; distance write-through
     "k_scatter": 37 + 57,  # SURVEY 8d insert: read raw record fields, write the 57 B of range-image fields
     "k_gap_scan": 4 + 4,
     "k_ground": 21 + 3 + 16 + 4,  # SURVEY 8d ground: 21 read + 3 written, + the association view (16) and mad (4)
     "k_probe": 21 + 4,  # SURVEY 8d associate
+    "k_probe_heavy": 21 + 4,
     "k_commit_copy": 4 + 4,
     "k_commit_roots": 4 + 4,
     "k_fin_label": 4 + 4,  # SURVEY 8d finish/label
@@ -218,7 +221,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2048, help="firings per push (= per step)")
+    ap.add_argument("--batch", type=int, default=4096, help="firings per push (= per step); 4096 = two rotations")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -250,8 +253,8 @@ def main():
     cfg = stream_configuration(SPEC)
     R = sp.rows
 
-    def new_handle():
-        cc = ContinuousClustering(device=local_rank, max_firings_per_push=max(B, 256))
+    def new_handle(batch=None):
+        cc = ContinuousClustering(device=local_rank, max_firings_per_push=max(batch or B, 256))
         cc.setConfiguration(cfg)
         cc.reset(R)
         cc.setTransformRobotFrameFromSensorFrame(IDENTITY)
@@ -269,64 +272,71 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident leg ("value")
-    total = (W + K) * B
-    pts, poses = tile_stream(base_pts, base_poses, sp, 0, total)
-    d_pts = torch.from_numpy(pts.view(np.uint8).reshape(total, R * 48)).cuda()
-    d_poses = torch.from_numpy(poses).cuda()
-    cc = new_handle()
-    stream = torch.cuda.ExternalStream(cc.stream)
-    rec_bytes, pose_bytes = R * 48, 12 * 8
+    def device_leg(B, K, W, sample_clocks):
+        """K timed pushes of B firings with the inputs already in HBM; returns a dict."""
+        total = (W + K) * B
+        pts, poses = tile_stream(base_pts, base_poses, sp, 0, total)
+        d_pts = torch.from_numpy(pts.view(np.uint8).reshape(total, R * 48)).cuda()
+        d_poses = torch.from_numpy(poses).cuda()
+        cc = new_handle(B)
+        stream = torch.cuda.ExternalStream(cc.stream)
 
-    def push_dev(step):
-        return cc.addFiringsDevice(d_pts.data_ptr() + step * B * rec_bytes, d_poses.data_ptr() + step * B * pose_bytes, B, R)
+        def submit_dev(step):
+            cc.submitFiringsDevice(d_pts.data_ptr() + step * B * rec_bytes, d_poses.data_ptr() + step * B * pose_bytes, B, R)
 
-    def submit_dev(step):
-        cc.submitFiringsDevice(d_pts.data_ptr() + step * B * rec_bytes, d_poses.data_ptr() + step * B * pose_bytes, B, R)
+        for s in range(W):
+            cc.addFiringsDevice(d_pts.data_ptr() + s * B * rec_bytes, d_poses.data_ptr() + s * B * pose_bytes, B, R)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        launches0 = cc.total_launches
+        # Timed region: K pushes, two in flight (submit(k + 1); wait(k)) so that the host's result handling of push k
+        # overlaps the kernels of push k + 1. Before every push L2 is flushed by a 256 MiB write on the same stream; the
+        # flushes are bracketed by their own events and their device time is subtracted.
+        ev_fa = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev_fb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev_end = torch.cuda.Event(enable_timing=True)
+        dev_ms = []
+        exact_pushes = 0
 
-    for s in range(W):
-        push_dev(s)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = cc.total_launches
-    # Timed region: K pushes, two in flight (submit(k + 1); wait(k)) so that the host's result handling of push k
-    # overlaps the kernels of push k + 1. Before every push L2 is flushed by a 256 MiB write on the same stream; the
-    # flushes are bracketed by their own events and their device time is subtracted.
-    ev_fa = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_fb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_end = torch.cuda.Event(enable_timing=True)
-    dev_ms = []
-    exact_pushes = 0
+        def flush_and_submit(s):
+            with torch.cuda.stream(stream):
+                ev_fa[s].record(stream)
+                l2_flush(s)
+                ev_fb[s].record(stream)
+            submit_dev(W + s)
 
-    def flush_and_submit(s):
+        t_wall0 = time.perf_counter()
+        flush_and_submit(0)
+        for s in range(K):
+            if s + 1 < K:
+                flush_and_submit(s + 1)
+            res = cc.wait()
+            dev_ms.append(res.info.device_ms)
+            exact_pushes += int(res.info.used_exact_path)
         with torch.cuda.stream(stream):
-            ev_fa[s].record(stream)
-            l2_flush(s)
-            ev_fb[s].record(stream)
-        submit_dev(W + s)
+            ev_end.record(stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        launches = cc.total_launches - launches0
+        flush_ms = sum(a.elapsed_time(b) for a, b in zip(ev_fa, ev_fb))
+        total_ms = ev_fa[0].elapsed_time(ev_end)
+        clocks = sampler.stop() if sampler else None
+        elapsed = (total_ms - flush_ms) / 1e3
+        if dist is not None:
+            t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed = float(t.item())
+        return {"cc": cc, "stream": stream, "value": world * K * B / elapsed, "elapsed": elapsed, "dev_ms": dev_ms,
+                "launches": launches, "exact": exact_pushes, "clocks": clocks, "t_wall": t_wall, "fed": total}
 
-    t_wall0 = time.perf_counter()
-    flush_and_submit(0)
-    for s in range(K):
-        if s + 1 < K:
-            flush_and_submit(s + 1)
-        res = cc.wait()
-        dev_ms.append(res.info.device_ms)
-        exact_pushes += int(res.info.used_exact_path)
-    with torch.cuda.stream(stream):
-        ev_end.record(stream)
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    launches = cc.total_launches - launches0
-    flush_ms = sum(a.elapsed_time(b) for a, b in zip(ev_fa, ev_fb))
-    total_ms = ev_fa[0].elapsed_time(ev_end)
-    clocks = sampler.stop()
-    elapsed = (total_ms - flush_ms) / 1e3
-    if dist is not None:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    value = world * K * B / elapsed
+    rec_bytes, pose_bytes = R * 48, 12 * 8
+    leg = device_leg(B, K, W, True)
+    cc, stream = leg["cc"], leg["stream"]
+    value, elapsed, dev_ms, launches, exact_pushes, clocks, t_wall = (leg["value"], leg["elapsed"], leg["dev_ms"], leg["launches"],
+                                                                      leg["exact"], leg["clocks"], leg["t_wall"])
+    total = leg["fed"]
 
     # per-push latency with ONE push in flight (the synchronous call a latency-sensitive caller makes)
     sync_ms = []
@@ -339,6 +349,26 @@ def main():
         cc.addFiringsDevice(d_lat.data_ptr() + r * B * rec_bytes, d_lat_poses.data_ptr() + r * B * pose_bytes, B, R)
         sync_ms.append(1e3 * (time.perf_counter() - t0))
     total += 6 * B
+
+    # device timeline of the kernels as they overlap in a normal push (globaltimer stamps, cc_debug_trace): the CUDA-event
+    # table below serialises the launches and adds an event round trip to every kernel
+    trace_table = None
+    if rank == 0:
+        tr_pts, tr_poses = tile_stream(base_pts, base_poses, sp, total, 4 * B)
+        d_tr = torch.from_numpy(tr_pts.view(np.uint8).reshape(4 * B, R * 48)).cuda()
+        d_tr_poses = torch.from_numpy(tr_poses).cuda()
+        cc.debug_trace(True)
+        acc_tr = {}
+        for r in range(4):
+            with torch.cuda.stream(stream):
+                l2_flush(r)
+            cc.addFiringsDevice(d_tr.data_ptr() + r * B * rec_bytes, d_tr_poses.data_ptr() + r * B * pose_bytes, B, R)
+            for name, a, z, longest, blocks in cc.get_trace():
+                if name.startswith("k_"):
+                    acc_tr.setdefault(name, []).append((z - a) / 1e3)
+        cc.debug_trace(False)
+        trace_table = {k: round(float(np.mean(v)), 2) for k, v in sorted(acc_tr.items(), key=lambda kv: -np.mean(kv[1]))}
+        total += 4 * B
 
     # ------------------------------------------------------------------ per-kernel timing + roofline (rank 0)
     roofline = None
@@ -374,6 +404,38 @@ def main():
                     "path_bytes_per_cell": 151, "path_achieved_gbs": value / world * R * 151 / 1e9,
                     "path_frac": value / world * R * 151 / 1e9 / peak}
     cc.close()
+
+    # ------------------------------------------------------------------ other operating points (rank 0, single GPU)
+    batch_sweep, latency_mode = None, None
+    if rank == 0 and world == 1:
+        batch_sweep = {}
+        for b2 in (1024, 2048, 6144):
+            if b2 == B:
+                continue
+            lg = device_leg(b2, 8, 3, False)
+            batch_sweep[str(b2)] = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 8,
+                                    "per_push_device_ms_p50": float(np.median(lg["dev_ms"]))}
+            lg["cc"].close()
+        # latency mode: small synchronous pushes (one in flight), host buffers, results back on the host
+        LB = 64
+        ccl = new_handle(LB)
+        ccl.set_label_prefetch(True)
+        nl = 120
+        lp, lq = tile_stream(base_pts, base_poses, sp, 0, nl * LB)
+        pin_lp = torch.from_numpy(lp.view(np.uint8).reshape(nl * LB, R * 48)).pin_memory()
+        pin_lq = torch.from_numpy(lq).pin_memory()
+        hlp = pin_lp.numpy().view(lp.dtype).reshape(nl * LB, R)
+        hlq = pin_lq.numpy()
+        lat = []
+        for i in range(nl):
+            t0 = time.perf_counter()
+            ccl.addFirings(hlp[i * LB:(i + 1) * LB], hlq[i * LB:(i + 1) * LB])
+            lat.append(1e3 * (time.perf_counter() - t0))
+        ccl.close()
+        lat = np.array(lat[40:])
+        latency_mode = {"batch_firings": LB, "call": "addFirings (host buffers in, events / clusters / labels back on the host)",
+                        "per_push_ms_p50": float(np.median(lat)), "per_push_ms_p99": float(np.percentile(lat, 99)),
+                        "columns_per_s": LB / (float(np.mean(lat)) / 1e3)}
 
     # ------------------------------------------------------------------ end-to-end leg through the public API
     cc = new_handle()
@@ -425,7 +487,7 @@ def main():
             "dtype": "f32 (+f64 rigid transforms, u32 union-find)", "data": "synthetic",
             "config": {"workload": workload_name(args), "batch_firings": B, "rows": R, "columns_per_rotation": sp.num_columns,
                        "l2": "256 MiB device write before every timed step (L2 flush); its event-timed duration is subtracted",
-                       "pipelining": "two pushes in flight (cc_submit_firings_device / cc_wait)",
+                       "pipelining": "two pushes in flight (cc_submit_firings_device / cc_wait); end-to-end leg: a third host push staged",
                        "streams": f"{world} independent sensor stream(s), one per GPU, no data-path collective",
                        "exact_path_pushes": exact_pushes},
             "clocks": clocks, "gpu_launches": int(launches),
@@ -436,6 +498,7 @@ def main():
                         "note": "one push = batch_firings columns; every column of a push is charged the whole push",
                         "wall_s": t_wall},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
+            "kernels_device_timeline_us": trace_table, "batch_sweep": batch_sweep, "latency_mode": latency_mode,
         }
         print(json.dumps(line))
     if dist is not None:

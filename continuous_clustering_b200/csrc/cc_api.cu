@@ -1207,6 +1207,18 @@ static cc_status_t launch_from(cc_handle* h, int n, const void* d_points, const 
     return CC_OK;
 }
 
+// The staged push is launched by the first submit / wait call AFTER the cc_wait() that made room for it, not by that
+// cc_wait() itself: its first kernel recycles columns the finished push may just have reported, and the caller reads
+// those between the two calls (cc_read_columns).
+static cc_status_t launch_staged_if_room(cc_handle* h)
+{
+    if (h->staged < 0 || h->n_pending >= 2)
+        return CC_OK;
+    const cc_handle::InBuf& ib = h->inbuf[h->staged];
+    h->staged = -1;
+    return launch_from(h, ib.n, ib.d_raw, ib.d_poses, &ib);
+}
+
 static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, const double* poses, bool device_inputs)
 {
     cc_status_t s = check_push(h, n, rows);
@@ -1214,13 +1226,16 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
         return s;
     if (!points || !poses)
         return CC_ERR_INVALID_ARGUMENT;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    s = launch_staged_if_room(h);
+    if (s != CC_OK)
+        return s;
     if (h->staged >= 0 || (h->n_pending >= 2 && device_inputs))
     {
         h->error = device_inputs ? "two pushes are already in flight: call cc_wait() first"
                                  : "two pushes are in flight and a third is staged: call cc_wait() first";
         return CC_ERR_INVALID_ARGUMENT;
     }
-    CC_CHECK(h, cudaSetDevice(h->device));
     if (device_inputs)
         return launch_from(h, n, points, poses, nullptr);
     cc_handle::InBuf& ib = h->inbuf[h->next_in];
@@ -1277,20 +1292,12 @@ cc_status_t cc_wait(cc_handle_t* h)
     if (!h)
         return CC_ERR_INVALID_ARGUMENT;
     CC_CHECK(h, cudaSetDevice(h->device));
-    const cc_status_t s = finish_push(h);
+    cc_status_t s = launch_staged_if_room(h);
+    if (s == CC_OK)
+        s = finish_push(h);
     if (s != CC_OK)
-    {
         h->staged = -1; // dropped with the pushes in flight (the stream needs a reset)
-        return s;
-    }
-    if (h->staged >= 0 && h->n_pending < 2)
-    {
-        const cc_handle::InBuf& ib = h->inbuf[h->staged];
-        h->staged = -1;
-        // finish_push left its results in the handle: launching must not disturb them (it only enqueues work)
-        return launch_from(h, ib.n, ib.d_raw, ib.d_poses, &ib);
-    }
-    return CC_OK;
+    return s;
 }
 
 int cc_pending(const cc_handle_t* h)

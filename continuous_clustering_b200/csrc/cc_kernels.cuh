@@ -133,6 +133,35 @@ struct CcTraceScope
     }
 };
 
+// The fields almost every kernel needs before it can start, loaded together (one memory round trip instead of one per
+// dependent branch). Stable for the duration of the kernels that use it.
+struct CcHead
+{
+    int halted, ncols, n_flagged, abort, error;
+    long long colbase;
+};
+CC_DEV CcHead cc_head(const CcDevState* st)
+{
+    CcHead h;
+    h.halted = st->halted;
+    h.ncols = st->ncols;
+    h.n_flagged = st->n_flagged;
+    h.abort = st->abort;
+    h.error = st->error;
+    h.colbase = st->colbase;
+    return h;
+}
+CC_DEV bool cc_head_ok(const CcHead& h, int guard) // cc_spec_ok on the loaded fields
+{
+    if (h.ncols <= 0)
+        return false;
+    if (guard == 1)
+        return h.n_flagged == 0 && h.abort == 0 && h.error == 0;
+    if (guard == 2)
+        return h.abort == 0;
+    return true;
+}
+
 CC_DEV float cc_nanf()
 {
     return ccm::u2f(0x7fc00000u);
@@ -287,7 +316,8 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_prep);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     // K5 first: clearColumns (cpp:1094-1145) for the columns retired TWO pushes ago. Recycling is deferred so that every
     // column a push reports through a finished-column event can still be read by the caller after the push has been
@@ -603,7 +633,8 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_check);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     int* sm = reinterpret_cast<int*>(smem);
@@ -1389,7 +1420,8 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_scatter);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
@@ -1481,11 +1513,12 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_gap_scan);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int R = cfg.R;
-    const int ncols = p.st->ncols;
-    const long long colbase = p.st->colbase;
+    const int ncols = hd.ncols;
+    const long long colbase = hd.colbase;
     const int T = blockDim.x, t = threadIdx.x;
     const int nchunks = (ncols + CC_GAP_CHUNK - 1) / CC_GAP_CHUNK;
     const float nanv = cc_nanf();
@@ -1660,7 +1693,8 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_ground);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     const int R = cfg.R;
@@ -1679,8 +1713,8 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
     unsigned short* s_lab = reinterpret_cast<unsigned short*>(cst + 4); // label | debug label << 8
     unsigned char* s_cls = reinterpret_cast<unsigned char*>(s_lab + R);
     unsigned char* s_int = s_cls + R; // intensity
-    const int ncols = p.st->ncols;
-    const long long colbase = p.st->colbase;
+    const int ncols = hd.ncols;
+    const long long colbase = hd.colbase;
     const float nanv = cc_nanf();
     const int nwords = (R + 31) / 32;
     const float hsg = cfg.height_sensor_to_ground;
@@ -2343,13 +2377,14 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_probe);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts); the probe itself
         d_snapshot(p, 0); // modifies no persistent state
     const int R = cfg.R;
-    const int ncols = p.st->ncols;
-    const long long colbase = p.st->colbase;
+    const int ncols = hd.ncols;
+    const long long colbase = hd.colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int lane = threadIdx.x % CC_WARP;
     const int npoints = p.st->n_probe < p.maxcols * R ? p.st->n_probe : p.maxcols * R;
@@ -2492,11 +2527,12 @@ __global__ void __launch_bounds__(128, 8) k_probe_heavy(CcDevCfg cfg, CcDevPtrs 
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int R = cfg.R, msr = cfg.max_steps_row;
-    const int ncols = p.st->ncols;
-    const long long colbase = p.st->colbase;
+    const int ncols = hd.ncols;
+    const long long colbase = hd.colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
     const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
@@ -2834,14 +2870,15 @@ __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_p
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_copy);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    if (!cc_spec_ok(p.st, spec))
+    if (!cc_head_ok(hd, spec))
         return;
     const int R = cfg.R;
     if (ci1 < 0)
-        ci1 = p.st->ncols - 1;
-    const long long colbase = p.st->colbase;
+        ci1 = hd.ncols - 1;
+    const long long colbase = hd.colbase;
     const int total = (ci1 - ci0 + 1) * R;
     const int lane = threadIdx.x % CC_WARP;
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -2905,14 +2942,15 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_roots);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    if (!cc_spec_ok(p.st, spec))
+    if (!cc_head_ok(hd, spec))
         return;
     const int R = cfg.R;
     if (ci1 < 0)
-        ci1 = p.st->ncols - 1;
-    const long long colbase = p.st->colbase;
+        ci1 = hd.ncols - 1;
+    const long long colbase = hd.colbase;
     const int total = (ci1 - ci0 + 1) * R;
     const int lane = threadIdx.x % CC_WARP;
     // warps stay converged: the contributions of a warp's cells to one root (cells of one object in neighbouring rows
@@ -2969,15 +3007,16 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_links);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    if (!cc_spec_ok(p.st, spec))
+    if (!cc_head_ok(hd, spec))
         return;
     const int R = cfg.R;
     if (ci1 < 0)
-        ci1 = p.st->ncols - 1;
+        ci1 = hd.ncols - 1;
     {
-        const long long colbase = p.st->colbase;
+        const long long colbase = hd.colbase;
         const int total = (ci1 - ci0 + 1) * R * CC_LINK_SLOTS;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
         {
@@ -2997,7 +3036,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
     }
     int n = p.st->n_edges;
     n = n < p.cap_edges ? n : p.cap_edges;
-    const int base_local = cc_local_col(p.st->colbase, cfg.ringcols);
+    const int base_local = cc_local_col(hd.colbase, cfg.ringcols);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
     {
         const unsigned int q = p.edge_a[e], o = p.edge_b[e];
@@ -3503,9 +3542,10 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label);
-    if (p.st->halted)
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    if (!cc_spec_ok(p.st, spec))
+    if (!cc_head_ok(hd, spec))
         return;
     const CcDevState* st = p.st;
     const int R = cfg.R;

@@ -26,19 +26,21 @@ def _to_cells(cols):
 
 def record(cc, pts, poses, chunk, pipelined=False):
     """Feeds the stream in pushes of `chunk` firings; returns the dict layout of tests/parity.record().
-    pipelined=True uses the asynchronous API with two pushes in flight (submit(k + 1); wait(k))."""
+    pipelined=True uses the asynchronous API with two pushes in flight (submit(k + 1); wait(k)), pipelined=2 keeps a third
+    push staged (submit(k + 2); wait(k))."""
     rows = pts.shape[1]
     events, gcols, gcells, ccols, ccells, clusters, cpoints = [], [], [], [], [], [], []
     n_events = 0
     used_exact = 0
     slow_firings = 0
     starts = list(range(0, pts.shape[0], chunk))
-    if pipelined and starts:
-        cc.submitFirings(pts[0:chunk], poses[0:chunk])
+    depth = int(pipelined) if pipelined else 0  # True: submit(k + 1); wait(k). 2: submit(k + 2); wait(k) (third push staged)
+    for b in starts[:depth]:
+        cc.submitFirings(pts[b : b + chunk], poses[b : b + chunk])
     for i, a in enumerate(starts):
         if pipelined:
-            if i + 1 < len(starts):
-                b = starts[i + 1]
+            if i + depth < len(starts):
+                b = starts[i + depth]
                 cc.submitFirings(pts[b : b + chunk], poses[b : b + chunk])
             res = cc.wait()
         else:

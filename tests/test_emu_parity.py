@@ -105,6 +105,33 @@ def test_pipelined_pushes_match_oracle(emu_library, oracle_lib, spec, kw, cfg_ov
     assert cc.pending == 0
 
 
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", ASYNC_CASES)
+def test_staged_pushes_match_oracle(emu_library, oracle_lib, spec, kw, cfg_over, chunk, flag_period):
+    """submit(k + 2); wait(k): a third push is staged behind the two in flight and launched by the first call that finds
+    room; the columns push k reported are read right after wait(k). Includes the halt + replay paths."""
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(emu_library, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk, pipelined=2)
+    parity.compare(want, got, name_a="oracle", name_b="emulated kernels, staged")
+    assert cc.pending == 0
+
+
+def test_staged_push_limits(emu_library):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0)
+    cc = make_cc(emu_library, drvlib.stream_config("tiny16"), sp.rows)
+    for k in range(3):
+        cc.submitFirings(pts[k * 32:(k + 1) * 32], poses[k * 32:(k + 1) * 32])
+    assert cc.pending == 3
+    with pytest.raises(ClusteringError):  # two in flight + one staged: the fourth has to wait
+        cc.submitFirings(pts[96:128], poses[96:128])
+    for k in range(3):
+        cc.wait()
+    assert cc.pending == 0
+
+
 def check_label_prefetch(library):
     pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0, moving=True)
     cc = make_cc(library, drvlib.stream_config("tiny16"), sp.rows)

@@ -42,6 +42,22 @@ def test_cuda_pipelined_pushes_match_oracle(cuda_library, oracle_lib, spec, kw, 
     parity.compare(want, got, name_a="oracle", name_b="cuda, pipelined")
 
 
+@pytest.mark.parametrize("spec,kw,chunk", [
+    ("tiny16", dict(n_rotations=4.0, moving=True, dropout=0.05), 100),
+    ("tiny16", dict(n_rotations=6.0), 700),                                     # pushes of more than two rotations
+    ("velodyne64", dict(n_rotations=4.2, moving=True, dropout=0.02), 4096),   # bench.py's operating point
+])
+def test_cuda_staged_pushes_match_oracle(cuda_library, oracle_lib, spec, kw, chunk):
+    """submit(k + 2); wait(k): two pushes in flight and a third one staged (its input copy starts at once, its kernels
+    when a later call finds room). Columns reported by push k are read after wait(k), as a caller would."""
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(None, cfg, sp.rows, max_push=max(4096, chunk))
+    got = recorder.record(cc, pts, poses, chunk, pipelined=2)
+    parity.compare(want, got, name_a="oracle", name_b="cuda, staged")
+
+
 @pytest.mark.parametrize("name", sorted(make_golden.FIXTURES))
 def test_cuda_matches_golden(cuda_library, name):
     pts, poses, sp, cfg = make_golden.stream_for(name)
@@ -54,6 +70,7 @@ def test_cuda_matches_golden(cuda_library, name):
 FULL = [  # BASELINE.json configs at full size (several rotations), oracle finishes these in seconds
     ("velodyne64", dict(n_rotations=4.2), 2048),
     ("velodyne64", dict(n_rotations=3.1, moving=True, dropout=0.02), 4096),
+    ("velodyne64", dict(n_rotations=6.2, moving=True, dropout=0.01), 6144),  # the largest push the ring allows (3 rotations)
     ("kitti64", dict(n_rotations=2.2, moving=True), 2200),
     ("vls128", dict(n_rotations=3.2, moving=True, start_firing=40), 1700),
     ("os32_left", dict(n_rotations=4.0, moving=True), 1024),
