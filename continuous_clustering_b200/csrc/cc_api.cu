@@ -916,7 +916,7 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
 #endif
         CC_RUN(h, k_scan_lite, 1, lite_threads, lite_threads * sizeof(CcAnchorSeg), cfg, h->d, n);
     }
-    CC_RUN(h, k_scan_check, R, 256, 256 * sizeof(int), cfg, h->d, n);
+    CC_RUN(h, k_scan_check, R, n > 2048 ? 512 : 256, 512 * sizeof(int), cfg, h->d, n);
     // ... then the single-CTA scan commits that prefix and resolves whatever is left
     const int scan_smem = scan_smem_bytes(R);
     CC_RUN(h, k_insert_scan, 1, scan_threads(), scan_smem, cfg, h->d, n, scan_chunk(R), 1);
@@ -932,16 +932,18 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     {
         CC_RUN(h, k_gap_scan, h->sm_count, 256, 0, cfg, h->d); // its last block chains the column chunks
         const int gw = 4; // warps (columns) per block
-        const size_t ground_smem = std::max(gw * cc_ground_warp_bytes(R), gw * CC_WARP * sizeof(double));
+        // dynamic shared memory: the warps' staging areas, reused by the last block for the running-maximum tail (at least
+        // a tile of 256 columns behind the block-scan scratch)
+        const size_t ground_smem = std::max(gw * cc_ground_warp_bytes(R), (32 + 256) * sizeof(double));
 #ifndef CC_EMU
-        // the kernel also has 16 KiB of static shared memory (running-maximum tail): opt in as soon as the sum passes 48 KiB
-        if (ground_smem > 28 * 1024 && ground_smem != h->ground_smem_set)
+        if (ground_smem > 48 * 1024 && ground_smem != h->ground_smem_set)
         {
             CC_CHECK(h, cudaFuncSetAttribute(k_ground, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ground_smem)));
             h->ground_smem_set = ground_smem;
         }
 #endif
-        CC_RUN(h, k_ground, h->sm_count * 4, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent); // its last block also does the running maxima
+        // one resident wave of warp-per-column blocks covers 8 * 4 * SMs columns; its last block also does the running maxima
+        CC_RUN(h, k_ground, h->sm_count * 8, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent, static_cast<int>(ground_smem));
         // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
         CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, 0, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
         CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,

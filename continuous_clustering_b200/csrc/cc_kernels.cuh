@@ -1662,7 +1662,7 @@ struct CcGroundRow
 static inline __host__ __device__ size_t cc_ground_warp_bytes(int R)
 {
     return (static_cast<size_t>(R) * (2 * sizeof(CcGroundRow) + sizeof(float4) + sizeof(double) + sizeof(float) + sizeof(unsigned short) + 2) +
-            28 * sizeof(unsigned int) + 15) / 16 * 16;
+            12 * sizeof(double) + 28 * sizeof(unsigned int) + 15) / 16 * 16;
 }
 
 CC_DEV double cc_ldcg_f64(const double* q)
@@ -1689,7 +1689,7 @@ CC_DEV bool cc_slope_below(float y, float x, float m)
     return fabsf(ccm::div_rn(y, x)) < m;
 }
 
-__global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+__global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int smem_bytes)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_ground);
@@ -1705,7 +1705,8 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
     CcGroundRow* cseq = s + R;                               // regular points, bottom row first; flags carry the row
     float4* s_q = reinterpret_cast<float4*>(cseq + R);       // the cells as inserted: x, y, z, distance
     double* s_caz = reinterpret_cast<double*>(s_q + R);      // continuous azimuth
-    float* s_incl = reinterpret_cast<float*>(s_caz + R);
+    double* s_ego = s_caz + R;                               // robot_from_sensor * odom_from_sensor^-1 of the column (3 x 4)
+    float* s_incl = reinterpret_cast<float*>(s_ego + 12);
     unsigned int* vm = reinterpret_cast<unsigned int*>(s_incl + R); // bitmap of regular rows (8 words)
     unsigned int* fm = vm + 8;  // by position in cseq: flat w.r.t. the previous point
     unsigned int* lm = fm + 8;  // by position in cseq: passes the slope / distance part of the last-ground update rule
@@ -1746,13 +1747,16 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
             s[row].gap = gap;
         }
         const double* pose = p.poses + 12 * trig;
-        double inv[12], ego[12];
-        cc_iso_inverse(pose, inv);
-        cc_iso_mul(cfg.robot_from_sensor, inv, ego);
         const float spx = static_cast<float>(pose[3]), spy = static_cast<float>(pose[7]),
                     spz = static_cast<float>(pose[11]);
         if (lane == 0)
         {
+            // ego-box transform of the column (cpp:300-301), once per column
+            double inv[12], ego[12];
+            cc_iso_inverse(pose, inv);
+            cc_iso_mul(cfg.robot_from_sensor, inv, ego);
+            for (int i = 0; i < 12; i++)
+                s_ego[i] = ego[i];
             if (slot_before != -1)
             {
                 p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
@@ -1763,6 +1767,7 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
                 vm[w] = 0u; // vm, fm, lm
         }
 
+        __syncwarp();
         cc_tr_pose.stop();
         CcTraceScope cc_tr_A(p.trace, CC_KID_g_A);
         // ---- A: classify every cell, project it into the azimuth plane, bitmap of the regular rows ----
@@ -1789,7 +1794,7 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
                 else
                 {
                     double e[3];
-                    cc_iso_apply(ego, static_cast<double>(q.x), static_cast<double>(q.y), static_cast<double>(q.z), e);
+                    cc_iso_apply(s_ego, static_cast<double>(q.x), static_cast<double>(q.y), static_cast<double>(q.z), e);
                     if (e[0] < cfg.l_front && e[0] > cfg.l_rear && e[1] < cfg.w_left && e[1] > cfg.w_right &&
                         e[2] < cfg.h_max && e[2] > cfg.h_ground)
                     {
@@ -1976,24 +1981,28 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
             }
         }
         __syncwarp();
-        if (lane == 0 && nregular > 0 && static_cast<int>(cst[0]) < nregular)
+        // C3 (all lanes): the points from the first obstacle on, 32 at a time. Once an obstacle has been seen the only
+        //     state the rules carry from point to point is the last certain ground position (and whether the previous
+        //     point was YELLOW, which the neighbouring lane knows), and few points ever move it: every lane evaluates
+        //     its point against the current position, the points up to and including the first one that moves it are
+        //     final, and the next round starts behind it. The relabel walks of the round's obstacles (cpp:513-535)
+        //     cover disjoint cells -- a walk never passes another obstacle -- so they run side by side.
+        if (nregular > 0 && static_cast<int>(cst[0]) < nregular)
         {
             int i = static_cast<int>(cst[0]);
             bool fod = (cst[1] & 1u) != 0, prev_yellow = (cst[1] & 2u) != 0;
             float lg_x = ccm::u2f(cst[2]), lg_y = ccm::u2f(cst[3]);
-            CcGroundRow nx = cseq[i];
-            int prev_row = -1;
-            unsigned int prev_lab = 0u;
             const bool terrain = cfg.use_terrain != 0;
             const float ms = cfg.max_slope;
-            // Written for a short dependency chain through (lg_x, lg_y, fod, prev_yellow): every rule is evaluated as a
-            // predicate and the label is a select; only the relabel walk of an obstacle and the (rare) exact division
-            // branch.
-            for (; i < nregular; i++)
+            while (i < nregular)
             {
-                const CcGroundRow cur = nx;
-                if (i + 1 < nregular)
-                    nx = cseq[i + 1];
+                const int k = i + lane;
+                const bool has = k < nregular;
+                CcGroundRow cur;
+                cur.c2x = cur.c2y = cur.gap = 0.f;
+                cur.flags = 0u;
+                if (has)
+                    cur = cseq[k];
                 const int row = static_cast<int>(cur.flags >> 16);
                 const float c2x = cur.c2x, c2y = cur.c2y;
                 const bool flat_prev = (cur.flags & CC_GF_FLAT) != 0;
@@ -2004,22 +2013,38 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
                 const float t = ms * agx;
                 const bool t_ok = t > 1e-30f && t < 1e30f;
                 bool slope_ok = t_ok && agy < t * 0.999999f;
-                const bool cand = fod && flat_prev && gtc_x > 0 && !terrain;
-                if (cand && !(t_ok && (slope_ok || agy > t * 1.000001f)))
+                // the point C1 stopped at is an obstacle by construction (not flat, not close to the last ground): it is
+                // the only one that can still see fod == false, and only in lane 0 of the first round
+                const bool my_fod = fod || lane > 0;
+                const bool cand = my_fod && flat_prev && gtc_x > 0 && !terrain;
+                if (has && cand && !(t_ok && (slope_ok || agy > t * 1.000001f)))
                     slope_ok = fabsf(ccm::div_rn(gtc_y, gtc_x)) < ms;
-                const bool green = !fod && flat_prev;
+                const bool green = !my_fod && flat_prev;
                 const bool yellowgreen = cand && slope_ok;
                 const bool yellow = !terrain && agx < cfg.close_d && agy < cfg.close_z;
-                unsigned int lab = green         ? (CC_GP_GROUND | (CC_GREEN << 8))
-                                   : yellowgreen ? (CC_GP_GROUND | (CC_YELLOWGREEN << 8))
-                                   : yellow      ? (CC_GP_GROUND | (CC_YELLOW << 8))
-                                                 : (CC_GP_OBSTACLE | (CC_RED << 8));
-                if (!(green || yellowgreen || yellow)) // cpp:508-536
+                const bool is_yellow = !green && !yellowgreen && yellow;
+                const unsigned int lab = green         ? (CC_GP_GROUND | (CC_GREEN << 8))
+                                         : yellowgreen ? (CC_GP_GROUND | (CC_YELLOWGREEN << 8))
+                                         : yellow      ? (CC_GP_GROUND | (CC_YELLOW << 8))
+                                                       : (CC_GP_OBSTACLE | (CC_RED << 8));
+                // was the previous point YELLOW? (cpp:545: such a point does not move the last ground position)
+                const unsigned int ymask = __ballot_sync(CC_FULL_MASK, has && is_yellow);
+                const bool py = lane == 0 ? prev_yellow : ((ymask >> (lane - 1)) & 1u) != 0;
+                const bool upd = has && (green || yellowgreen) && (cur.flags & CC_GF_LG) && !py; // cpp:541-561
+                const unsigned int umask = __ballot_sync(CC_FULL_MASK, upd);
+                int ncommit = nregular - i < CC_WARP ? nregular - i : CC_WARP;
+                if (umask)
+                    ncommit = __ffs(umask); // up to and including the first point that moves the last ground position
+                const bool mine = lane < ncommit;
+                if (mine)
+                    s_lab[row] = static_cast<unsigned short>(lab);
+                __syncwarp();
+                if (mine && !(green || yellowgreen || yellow)) // cpp:508-536
                 {
                     int below = row + 1;
                     while (below < R)
                     {
-                        const unsigned int ql = below == prev_row ? prev_lab : static_cast<unsigned int>(s_lab[below]);
+                        const unsigned int ql = s_lab[below];
                         const bool is_ground = (ql & 0xffu) == CC_GP_GROUND;
                         if ((ql >> 8) == CC_YELLOW || (is_ground && fabsf(c2x - s[below].c2x) < cfg.next_obst_d))
                         {
@@ -2030,15 +2055,20 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
                         else
                             break;
                     }
-                    fod = true;
                 }
-                s_lab[row] = static_cast<unsigned short>(lab);
-                const bool upd = (green || yellowgreen) && (cur.flags & CC_GF_LG) && !prev_yellow; // cpp:541-561
-                lg_x = upd ? c2x : lg_x;
-                lg_y = upd ? c2y : lg_y;
-                prev_yellow = !green && !yellowgreen && yellow;
-                prev_row = row;
-                prev_lab = lab;
+                __syncwarp();
+                const int last = ncommit - 1;
+                if (umask)
+                {
+                    lg_x = __shfl_sync(CC_FULL_MASK, c2x, last);
+                    lg_y = __shfl_sync(CC_FULL_MASK, c2y, last);
+                    prev_yellow = false;
+                }
+                else
+                    prev_yellow = ((ymask >> last) & 1u) != 0;
+                // any committed obstacle sets first_obstacle_detected; the first point of C3 always is one
+                fod = true;
+                i += ncommit;
             }
         }
         __syncwarp();
@@ -2136,15 +2166,18 @@ __global__ void __launch_bounds__(128) k_ground(CcDevCfg cfg, CcDevPtrs p, unsig
     if (threadIdx.x == 0)
         p.st->ticket_ground = 0;
     CcTraceScope cc_tr_tail(p.trace, CC_KID_ground_tail);
-    // tiles of 2048 columns staged in shared memory with independent coalesced loads; every thread scans a contiguous
+    // tiles of columns staged in shared memory with independent coalesced loads; every thread scans a contiguous
     // segment of the tile, the segments are chained by a block scan
-    __shared__ double sh_az[2048];
+    // (the staging areas of the block's warps are free by now: [block-scan scratch: one double per warp][tile])
     double* part = reinterpret_cast<double*>(smem);
+    double* sh_az = part + 32;
+    int tile = (smem_bytes - 32 * static_cast<int>(sizeof(double))) / static_cast<int>(sizeof(double));
+    tile = tile > 2048 ? 2048 : tile;
     const int T = blockDim.x, t = threadIdx.x;
     double carry = p.st->runmax_carry;
-    for (int c0 = 0; c0 < ncols; c0 += 2048)
+    for (int c0 = 0; c0 < ncols; c0 += tile)
     {
-        const int n = (ncols - c0) < 2048 ? (ncols - c0) : 2048;
+        const int n = (ncols - c0) < tile ? (ncols - c0) : tile;
         for (int i0 = 0; i0 < n; i0 += 16 * T)
         {
             double v[16];
