@@ -49,7 +49,7 @@ struct cc_handle
     const uchar4* cur_labels{nullptr}; // labels of the last finished push (pinned slot buffer)
     int cur_label_cols{0};
     int used_exact_flag{0};
-    size_t probe_smem_set{0};
+    size_t probe_smem{0}; // [block-scan scratch][running maxima of up to maxcols columns]
     size_t ground_smem_set{0};
     size_t lite_smem_set{0};
     size_t fin_smem_set{0};
@@ -357,8 +357,6 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
         h->sm_count = prop.multiProcessorCount;
     {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe, 256, 0) == cudaSuccess && nb > 0)
-            h->occ_probe = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4)) == cudaSuccess && nb > 0)
             h->occ_probe_heavy = nb;
     }
@@ -704,7 +702,15 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     h->clusters.clear();
     h->cluster_points.clear();
     std::memset(&h->info, 0, sizeof(h->info));
+    h->probe_smem = (32 + static_cast<size_t>(h->maxcols)) * sizeof(double);
 #ifndef CC_EMU
+    {
+        if (h->probe_smem > 48 * 1024)
+            CC_CHECK(h, cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->probe_smem)));
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe, 256, h->probe_smem) == cudaSuccess && nb > 0)
+            h->occ_probe = nb;
+    }
     {
         const int smem = scan_smem_bytes(h->R);
         if (smem > 48 * 1024)
@@ -932,9 +938,7 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     {
         CC_RUN(h, k_gap_scan, h->sm_count, 256, 0, cfg, h->d); // its last block chains the column chunks
         const int gw = 4; // warps (columns) per block
-        // dynamic shared memory: the warps' staging areas, reused by the last block for the running-maximum tail (at least
-        // a tile of 256 columns behind the block-scan scratch)
-        const size_t ground_smem = std::max(gw * cc_ground_warp_bytes(R), (32 + 256) * sizeof(double));
+        const size_t ground_smem = gw * cc_ground_warp_bytes(R);
 #ifndef CC_EMU
         if (ground_smem > 48 * 1024 && ground_smem != h->ground_smem_set)
         {
@@ -942,10 +946,11 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
             h->ground_smem_set = ground_smem;
         }
 #endif
-        // one resident wave of warp-per-column blocks covers 8 * 4 * SMs columns; its last block also does the running maxima
-        CC_RUN(h, k_ground, h->sm_count * 8, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent, static_cast<int>(ground_smem));
+        // one resident wave of warp-per-column blocks covers 8 * 4 * SMs columns
+        CC_RUN(h, k_ground, h->sm_count * 8, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent);
         // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
-        CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, 0, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
+        // (every CTA first computes the running maximum of the column minima in shared memory)
+        CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, h->probe_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
         CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,
                h->d_s_parent, h->d_s_links, h->tune);
         if (sl.spec)

@@ -1689,7 +1689,7 @@ CC_DEV bool cc_slope_below(float y, float x, float m)
     return fabsf(ccm::div_rn(y, x)) < m;
 }
 
-__global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, int smem_bytes)
+__global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_ground);
@@ -2148,67 +2148,45 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
         __syncwarp();
     }
 
-    // ---- running maximum of the columns' minimum azimuth (the value every finish pass compares against,
-    //      cpp:884-885), continued across pushes: done by whichever block finishes last ----
-    cc_tr_main_obj.stop();
-    __shared__ int sh_last;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        __threadfence();
-        const int ticket = atomicAdd(&p.st->ticket_ground, 1);
-        sh_last = ticket == static_cast<int>(gridDim.x) - 1;
-    }
-    __syncthreads();
-    if (!sh_last)
-        return;
-    __threadfence();
-    if (threadIdx.x == 0)
-        p.st->ticket_ground = 0;
-    CcTraceScope cc_tr_tail(p.trace, CC_KID_ground_tail);
-    // tiles of columns staged in shared memory with independent coalesced loads; every thread scans a contiguous
-    // segment of the tile, the segments are chained by a block scan
-    // (the staging areas of the block's warps are free by now: [block-scan scratch: one double per warp][tile])
-    double* part = reinterpret_cast<double*>(smem);
-    double* sh_az = part + 32;
-    int tile = (smem_bytes - 32 * static_cast<int>(sizeof(double))) / static_cast<int>(sizeof(double));
-    tile = tile > 2048 ? 2048 : tile;
+}
+
+// Running maximum of the columns' minimum azimuth (the value every finish pass compares against, cpp:884-885), continued
+// across pushes: every CTA of the association probe computes it for itself in shared memory (one coalesced read of the
+// per-column minima and a block scan), instead of all of them waiting for one CTA to do it. `sh` holds ncols doubles
+// behind `part` (block-scan scratch, one double per warp). CTA 0 also leaves it in col_runmax for the kernels after.
+CC_DEV void d_runmax_block(const CcDevPtrs& p, int ncols, double* part, double* sh, bool write_out)
+{
     const int T = blockDim.x, t = threadIdx.x;
-    double carry = p.st->runmax_carry;
-    for (int c0 = 0; c0 < ncols; c0 += tile)
+    const double carry = p.st->runmax_carry;
+    for (int i0 = 0; i0 < ncols; i0 += 16 * T)
     {
-        const int n = (ncols - c0) < tile ? (ncols - c0) : tile;
-        for (int i0 = 0; i0 < n; i0 += 16 * T)
-        {
-            double v[16];
+        double v[16];
 #pragma unroll
-            for (int u = 0; u < 16; u++)
-                v[u] = i0 + u * T + t < n ? cc_ldcg_f64(p.col_minaz + c0 + i0 + u * T + t) : -1.0;
+        for (int u = 0; u < 16; u++)
+            v[u] = i0 + u * T + t < ncols ? p.col_minaz[i0 + u * T + t] : -1.0;
 #pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (i0 + u * T + t < n)
-                    sh_az[i0 + u * T + t] = v[u];
-        }
-        __syncthreads();
-        const int seg = ((n + T - 1) / T) | 1; // odd: the threads' segments start in different banks
-        const int lo = t * seg < n ? t * seg : n, hi = (lo + seg < n) ? lo + seg : n;
-        double m = -1.0;
-        for (int i = lo; i < hi; i++)
-            m = sh_az[i] > m ? sh_az[i] : m;
-        double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
-        pre = carry > pre ? carry : pre;
-        for (int i = lo; i < hi; i++)
-        {
-            const double v = sh_az[i];
-            pre = v > pre ? v : pre;
-            sh_az[i] = pre;
-        }
-        __syncthreads();
-        carry = sh_az[n - 1];
-        for (int i = t; i < n; i += T)
-            p.col_runmax[c0 + i] = sh_az[i];
-        __syncthreads();
+        for (int u = 0; u < 16; u++)
+            if (i0 + u * T + t < ncols)
+                sh[i0 + u * T + t] = v[u];
     }
+    __syncthreads();
+    const int seg = ((ncols + T - 1) / T) | 1; // odd: the threads' segments start in different banks
+    const int lo = t * seg < ncols ? t * seg : ncols, hi = (lo + seg < ncols) ? lo + seg : ncols;
+    double m = -1.0;
+    for (int i = lo; i < hi; i++)
+        m = sh[i] > m ? sh[i] : m;
+    double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
+    pre = carry > pre ? carry : pre;
+    for (int i = lo; i < hi; i++)
+    {
+        const double v = sh[i];
+        pre = v > pre ? v : pre;
+        sh[i] = pre;
+    }
+    __syncthreads();
+    if (write_out)
+        for (int i = t; i < ncols; i += T)
+            p.col_runmax[i] = sh[i];
 }
 
 __device__ void d_snapshot(CcDevPtrs p, int spec);
@@ -2424,6 +2402,12 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) / CC_WARP;
     const int nwarps = (gridDim.x * blockDim.x + CC_WARP - 1) / CC_WARP;
     const int ngroups = (npoints + CC_PROBE_PPW - 1) / CC_PROBE_PPW;
+    CC_SMEM(smem);
+    double* rm_part = reinterpret_cast<double*>(smem);
+    double* rm = rm_part + 32; // running maximum of the column minima, columns of this push
+    const int ncols_rm = ncols < p.maxcols ? ncols : p.maxcols;
+    d_runmax_block(p, ncols_rm, rm_part, rm, blockIdx.x == 0);
+    const double rm_carry = p.st->runmax_carry;
     for (int grp = gwarp; grp < ngroups; grp += nwarps)
     {
         // the points of a warp are far apart in the list: points that need the cooperative walk come in runs (the
@@ -2442,7 +2426,7 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
             const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
             const float4 a = p.assoc[pq];
             const float mad = p.mad[pq];
-            const double prev_runmax = pci > 0 ? p.col_runmax[pci - 1] : p.st->runmax_carry;
+            const double prev_runmax = pci > 0 ? rm[pci - 1] : rm_carry;
             int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
             steps_back = steps_back < cfg.max_steps_row ? steps_back : cfg.max_steps_row;
             unsigned int first = CC_NONE, l0 = CC_NONE, l1 = CC_NONE, l2 = CC_NONE, l3 = CC_NONE;

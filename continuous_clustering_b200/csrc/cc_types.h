@@ -106,7 +106,6 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long scan_lite_base; // column the lite arrays are relative to
     int scan_lite_firings;
     int ticket_gap;    // same for k_gap_scan (the last block chains the column chunks)
-    int ticket_ground; // blocks of k_ground that are done (the last one computes the running maxima); 0 between launches
     int halted; // set when a push could not be committed speculatively: later pushes in flight skip themselves
 };
 
