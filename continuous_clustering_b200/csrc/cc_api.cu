@@ -12,7 +12,9 @@
 
 #include "cc_kernels.cuh"
 
-static const int CC_PREFETCH_CLUSTERS = 512, CC_PREFETCH_POINTS = 16384;
+// optimistic prefix of a push's results brought to the host behind it: cluster records, and member lists for a quarter of
+// the cells of the largest push (a synthetic street scene finishes ~8 % of a push's cells as cluster members)
+static const int CC_PREFETCH_CLUSTERS = 1024;
 
 namespace
 {
@@ -69,7 +71,7 @@ struct cc_handle
         CcDevState* h_state{nullptr};
         long long* h_first_unpub{nullptr};
         CcCluster* h_clusters{nullptr};
-        CcClusterPoint* h_points{nullptr};
+        CcClusterPoint* h_points{nullptr}; // one of the handle's three member-list buffers (borrowed)
         uchar4* h_labels{nullptr}; // one of the handle's three label buffers (borrowed)
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr};
         cudaEvent_t h2d{nullptr}, h2d0{nullptr}; // of the input buffer the push reads (borrowed, not owned)
@@ -97,6 +99,9 @@ struct cc_handle
     // page-locked label buffers: two pushes in flight + the labels of the last finished push, which stay valid until
     // the next cc_wait()
     uchar4* h_label_ring[3]{nullptr, nullptr, nullptr};
+    CcClusterPoint* h_points_ring[3]{nullptr, nullptr, nullptr}; // same rotation: the member lists are handed out as views
+    const cc_cluster_point_t* points_view{nullptr}; // member lists of the last finished push
+    size_t n_events{0};                             // events of the last finished push (h->events keeps its capacity)
     int next_label{0};
     int staged{-1}; // input buffer of the staged push, -1 none
     int next_slot{0};
@@ -117,6 +122,7 @@ struct cc_handle
     uint64_t launches{0};
     uint64_t launches_at_push_start{0};
     int sm_count{148};
+    int prefetch_points{16384};
     int occ_probe{8}, occ_probe_heavy{8}; // resident CTAs per SM of the two association kernels
     // results of the last push
     cc_batch_info_t info{};
@@ -177,8 +183,7 @@ static void free_host_slots(cc_handle* h)
 {
     for (cc_handle::Slot& sl : h->slots)
     {
-        for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters),
-                        static_cast<void*>(sl.h_points)})
+        for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters)})
             if (q)
                 cudaFreeHost(q);
         sl.h_state = nullptr;
@@ -188,6 +193,12 @@ static void free_host_slots(cc_handle* h)
         sl.h_labels = nullptr;
     }
     for (uchar4*& q : h->h_label_ring)
+    {
+        if (q)
+            cudaFreeHost(q);
+        q = nullptr;
+    }
+    for (CcClusterPoint*& q : h->h_points_ring)
     {
         if (q)
             cudaFreeHost(q);
@@ -620,6 +631,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.G, static_cast<size_t>(d.cap_G)));
         CC_CHECK(h, dev_alloc(h, L, &d.n_new_ulist, 1));
         free_host_slots(h);
+        h->prefetch_points = static_cast<int>(std::max<size_t>(16384, stage / 4));
         for (cc_handle::Slot& sl : h->slots)
         {
             CC_CHECK(h, dev_alloc(h, L, &sl.d_state_snap, 1));
@@ -630,10 +642,11 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_state), sizeof(CcDevState)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_first_unpub), mc * sizeof(long long)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
-            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_points), CC_PREFETCH_POINTS * sizeof(CcClusterPoint)));
         }
         for (uchar4*& q : h->h_label_ring)
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&q), mc * h->R * sizeof(uchar4)));
+        for (CcClusterPoint*& q : h->h_points_ring)
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&q), static_cast<size_t>(h->prefetch_points) * sizeof(CcClusterPoint)));
         for (cc_handle::InBuf& ib : h->inbuf)
         {
             CC_CHECK(h, dev_alloc(h, L, &ib.d_raw, stage * sizeof(cc_raw_point_t)));
@@ -698,9 +711,10 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     h->has_tf = false; // cpp:38
     h->reset_required_cfg = false;
     h->is_reset = true;
-    h->events.clear();
+    h->n_events = 0;
     h->clusters.clear();
     h->cluster_points.clear();
+    h->points_view = nullptr;
     std::memset(&h->info, 0, sizeof(h->info));
     h->probe_smem = (32 + static_cast<size_t>(h->maxcols)) * sizeof(double);
 #ifndef CC_EMU
@@ -871,7 +885,8 @@ static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl, bool state
     CC_CHECK(h, cudaStreamWaitEvent(h->copy_stream, sl.ready, 0));
     sl.pre_cols = std::min(h->maxcols, sl.n + 64);
     sl.pre_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
-    sl.pre_points = std::min(h->d.cap_cluster_points, CC_PREFETCH_POINTS);
+    // member lists: what a push of this size typically finishes, not the whole capacity
+    sl.pre_points = std::min(std::min(h->d.cap_cluster_points, h->prefetch_points), std::max(16384, sl.n * h->R / 4));
     CC_CHECK(h, cudaMemcpyAsync(sl.h_state, sl.d_state_snap, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->copy_stream));
     CC_CHECK(h, cudaMemcpyAsync(sl.h_first_unpub, sl.d_first_unpub, sl.pre_cols * sizeof(long long),
                                 cudaMemcpyDeviceToHost, h->copy_stream));
@@ -976,9 +991,10 @@ static cc_status_t finish_push(cc_handle* h)
         return CC_ERR_INVALID_ARGUMENT;
     }
     cc_handle::Slot& sl = h->slots[h->pending[0]];
-    h->events.clear();
+    h->n_events = 0;
     h->clusters.clear();
     h->cluster_points.clear();
+    h->points_view = nullptr;
     std::memset(&h->info, 0, sizeof(h->info));
     auto pop = [&]()
     {
@@ -1050,7 +1066,9 @@ static cc_status_t finish_push(cc_handle* h)
     const int ncl = st.n_clusters, ncp = st.n_cluster_points;
     h->h_first_unpub.resize(ncols);
     h->h_clusters.resize(ncl);
-    h->cluster_points.resize(ncp);
+    const bool points_in_place = ncp <= sl.pre_points; // the prefetch brought all member lists: hand out the pinned buffer
+    if (!points_in_place)
+        h->cluster_points.resize(ncp);
     static_assert(sizeof(CcClusterPoint) == sizeof(cc_cluster_point_t), "cluster point layout");
     {
         // what the prefetch already brought, then (rarely) the remainder from the slot's device arrays
@@ -1059,7 +1077,7 @@ static cc_status_t finish_push(cc_handle* h)
             std::memcpy(h->h_first_unpub.data(), sl.h_first_unpub, c0 * sizeof(long long));
         if (l0)
             std::memcpy(h->h_clusters.data(), sl.h_clusters, l0 * sizeof(CcCluster));
-        if (p0)
+        if (p0 && !points_in_place)
             std::memcpy(h->cluster_points.data(), sl.h_points, p0 * sizeof(CcClusterPoint));
         bool more = false;
         if (ncols > c0)
@@ -1096,6 +1114,7 @@ static cc_status_t finish_push(cc_handle* h)
         h->cur_labels = sl.h_labels;
         h->cur_label_cols = std::min(ncols, h->maxcols);
     }
+    h->points_view = points_in_place ? reinterpret_cast<const cc_cluster_point_t*>(sl.h_points) : h->cluster_points.data();
     float ms = 0.f;
     cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
 
@@ -1120,7 +1139,10 @@ static cc_status_t finish_push(cc_handle* h)
     // finished-column callbacks in the reference's single-threaded order (cpp:618-620, 1087-1089)
     long long fu_old = st.push_first_unpub_old;
     size_t next_cluster = 0;
-    h->events.reserve(static_cast<size_t>(ncols) * 2);
+    if (h->events.size() < static_cast<size_t>(ncols) * 2)
+        h->events.resize(static_cast<size_t>(ncols) * 2);
+    cc_column_event_t* ev_out = h->events.data();
+    size_t n_ev = 0;
     for (int ci = 0; ci < ncols; ci++)
     {
         const long long c = st.colbase + ci;
@@ -1129,7 +1151,7 @@ static cc_status_t finish_push(cc_handle* h)
         e.to_gcol = c;
         e.ground_points_only = 1;
         e.n_clusters_before = static_cast<int32_t>(next_cluster);
-        h->events.push_back(e);
+        ev_out[n_ev++] = e;
         if (c % cfg.nth != 0)
             continue;
         while (next_cluster < h->clusters.size() && h->clusters[next_cluster].finished_at_gcol <= c)
@@ -1139,7 +1161,7 @@ static cc_status_t finish_push(cc_handle* h)
         e.to_gcol = fu - 1;
         e.ground_points_only = 0;
         e.n_clusters_before = static_cast<int32_t>(next_cluster);
-        h->events.push_back(e);
+        ev_out[n_ev++] = e;
         fu_old = fu;
     }
     cc_batch_info_t& info = h->info;
@@ -1150,7 +1172,8 @@ static cc_status_t finish_push(cc_handle* h)
     info.ring_end_gcol = st.ring_end;
     info.cleared_from_gcol = st.clear_from;
     info.cleared_to_gcol = st.clear_to;
-    info.n_events = static_cast<int32_t>(h->events.size());
+    h->n_events = n_ev;
+    info.n_events = static_cast<int32_t>(n_ev);
     info.n_clusters = ncl;
     info.n_cluster_points = ncp;
     info.reset_required = st.reset_required;
@@ -1201,6 +1224,7 @@ static cc_status_t launch_from(cc_handle* h, int n, const void* d_points, const 
     sl.in_points = d_points;
     sl.in_poses = d_poses;
     sl.h_labels = h->h_label_ring[h->next_label];
+    sl.h_points = h->h_points_ring[h->next_label];
     h->next_label = (h->next_label + 1) % 3;
     sl.h2d = ib ? ib->h2d : nullptr;
     sl.h2d0 = ib ? ib->h2d0 : nullptr;
@@ -1321,9 +1345,11 @@ static cc_status_t push_sync(cc_handle* h, int n, int rows, const void* points, 
     }
     if (h && h->is_reset && rows == h->R && n == 0)
     {
-        h->events.clear();
+        h->n_events = 0;
         h->clusters.clear();
         h->cluster_points.clear();
+        h->points_view = nullptr;
+    h->points_view = nullptr;
         std::memset(&h->info, 0, sizeof(h->info));
         return CC_OK;
     }
@@ -1378,13 +1404,20 @@ cc_status_t cc_get_result_views(const cc_handle_t* h, const cc_column_event_t** 
     if (clusters)
         *clusters = h->clusters.data();
     if (points)
-        *points = h->cluster_points.data();
+        *points = h->points_view;
     return CC_OK;
 }
 
 cc_status_t cc_get_column_events(const cc_handle_t* h, cc_column_event_t* out, int cap, int* n_out)
 {
-    return h ? copy_out(h->events, out, cap, n_out) : CC_ERR_INVALID_ARGUMENT;
+    if (!h || cap < 0 || (cap > 0 && !out))
+        return CC_ERR_INVALID_ARGUMENT;
+    const int n = static_cast<int>(std::min<size_t>(h->n_events, static_cast<size_t>(cap)));
+    if (n)
+        std::memcpy(out, h->events.data(), static_cast<size_t>(n) * sizeof(cc_column_event_t));
+    if (n_out)
+        *n_out = n;
+    return CC_OK;
 }
 cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int cap, int* n_out)
 {
@@ -1392,7 +1425,14 @@ cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int cap, in
 }
 cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out, int cap, int* n_out)
 {
-    return h ? copy_out(h->cluster_points, out, cap, n_out) : CC_ERR_INVALID_ARGUMENT;
+    if (!h || cap < 0 || (cap > 0 && !out))
+        return CC_ERR_INVALID_ARGUMENT;
+    const int n = std::min(h->info.n_cluster_points, cap);
+    if (n > 0 && h->points_view)
+        std::memcpy(out, h->points_view, static_cast<size_t>(n) * sizeof(cc_cluster_point_t));
+    if (n_out)
+        *n_out = n > 0 ? n : 0;
+    return CC_OK;
 }
 
 // what a caller reads from range_image_ inside a column callback (ros_utils.cpp:56-63, kitti_demo.cpp:183-216)
