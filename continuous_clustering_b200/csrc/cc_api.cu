@@ -368,7 +368,7 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
         h->sm_count = prop.multiProcessorCount;
     {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4)) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 64, CC_PROBE_PIPE * CC_WARP * sizeof(float4)) == cudaSuccess && nb > 0)
             h->occ_probe_heavy = nb;
     }
 #endif
@@ -966,7 +966,7 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
         // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
         // (every CTA first computes the running maximum of the column minima in shared memory)
         CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, h->probe_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
-        CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 128, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,
+        CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 64, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,
                h->d_s_parent, h->d_s_links, h->tune);
         if (sl.spec)
         {

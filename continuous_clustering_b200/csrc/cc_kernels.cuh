@@ -2204,7 +2204,7 @@ __device__ void d_snapshot(CcDevPtrs p, int spec);
 #ifdef CC_EMU
 #define CC_PROBE_PPW 1
 #else
-#define CC_PROBE_PPW 4 /* points per warp on the thread-per-point path (spreads the heavy points over more warps) */
+#define CC_PROBE_PPW 8 /* points per warp on the thread-per-point path: one round of the resident warps at 4096 columns */
 #endif
 
 // Warp-cooperative walk of ONE point with all lanes: every vertical run of the walk (cpp:716-750) is evaluated 32 cells
@@ -2530,7 +2530,7 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
     }
 }
 
-// K3a': the points the thread-per-point path gave up on, one CTA per point. When a vertical run fits one warp step
+// K3a': the points the thread-per-point path gave up on, one CTA (two warps) per point. When a vertical run fits one warp step
 // (max_steps_in_column < 32) and the window has at most 64 runs:
 //   phase 1  the warps of the CTA share the runs of the window: independent loads, inclination-break and distance
 //            predicates of every run at once, their ballot masks left in shared memory;
@@ -2540,7 +2540,7 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
 // A point without neighbours -- the worst case, it walks its whole window -- costs one memory round trip and a few
 // hundred instructions instead of ~100 dependent instructions per run. Other configurations: warp 0 walks alone
 // (d_probe_coop).
-__global__ void __launch_bounds__(128, 8) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
+__global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy);
@@ -3235,16 +3235,47 @@ __device__ void d_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
     if (!cc_spec_ok(p.st, spec))
         return;
     const int n = p.st->n_ulist < p.cap_ulist ? p.st->n_ulist : p.cap_ulist;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    // four list entries per thread at a time: their loads are issued together (the list is a few thousand entries long
+    // and this runs in one CTA, so every dependent round trip counts once per batch instead of once per entry)
+    for (int i0 = tid; i0 < n; i0 += 4 * nt)
     {
-        const unsigned int root = p.ulist[i];
-        const unsigned int rep = cc_uf_find(p.cparent, root);
-        const int j = static_cast<int>(p.rootslot[rep]);
-        p.u_rep[i] = j;
-        atomicMax(p.u_maxfinish + j, p.tfinish[root]);
-        atomicMin(p.u_mincol + j, p.slot_gcol[root / cfg.R]);
-        atomicMax(p.u_maxend + j, p.tmaxcol[root] + 1);
-        atomicAdd(p.u_np + j, p.tnpoints[root]);
+        unsigned int root[4], cp[4], np[4];
+        unsigned long long tf[4];
+        long long gc[4], mc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            root[k] = i0 + k * nt < n ? p.ulist[i0 + k * nt] : CC_NONE;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            cp[k] = np[k] = 0u;
+            tf[k] = 0ull;
+            gc[k] = mc[k] = 0;
+            if (root[k] != CC_NONE)
+            {
+                // the root's own aggregates do not depend on the find: issued with its first hop
+                tf[k] = p.tfinish[root[k]];
+                gc[k] = p.slot_gcol[root[k] / cfg.R];
+                mc[k] = p.tmaxcol[root[k]];
+                np[k] = p.tnpoints[root[k]];
+                cp[k] = cc_vload(p.cparent + root[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            if (root[k] == CC_NONE)
+                continue;
+            const int i = i0 + k * nt;
+            const unsigned int rep = cp[k] == root[k] ? root[k] : cc_uf_find(p.cparent, root[k]);
+            const int j = rep == root[k] ? i : static_cast<int>(p.rootslot[rep]); // a list root's slot is its list position
+            p.u_rep[i] = j;
+            atomicMax(p.u_maxfinish + j, tf[k]);
+            atomicMin(p.u_mincol + j, gc[k]);
+            atomicMax(p.u_maxend + j, mc[k] + 1);
+            atomicAdd(p.u_np + j, np[k]);
+        }
     }
 }
 
@@ -3258,12 +3289,39 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, co
     CcDevState* st = p.st;
     const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
     const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const int tid_ = blockIdx.x * blockDim.x + threadIdx.x, nt_ = gridDim.x * blockDim.x;
+    // four entries per thread at a time, their loads issued together (see d_fin_agg)
+    for (int i0 = tid_; i0 < n; i0 += 4 * nt_)
     {
-        if (p.u_rep[i] != i)
+      int rep_[4];
+      unsigned long long mf_[4];
+      long long me_[4], mn_[4];
+      unsigned int np_[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+      {
+          const int i = i0 + k * nt_;
+          rep_[k] = -1;
+          mf_[k] = 0ull;
+          me_[k] = mn_[k] = 0;
+          np_[k] = 0u;
+          if (i < n)
+          {
+              rep_[k] = p.u_rep[i];
+              mf_[k] = p.u_maxfinish[i];
+              me_[k] = p.u_maxend[i];
+              mn_[k] = p.u_mincol[i];
+              np_[k] = p.u_np[i];
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+      {
+        const int i = i0 + k * nt_;
+        if (rep_[k] != i)
             continue;
-        const double F = cc_ord2d(p.u_maxfinish[i]);
-        const long long maxend = p.u_maxend[i], mincol = p.u_mincol[i];
+        const double F = cc_ord2d(mf_[k]);
+        const long long maxend = me_[k], mincol = mn_[k];
         long long finish_col = CC_COL_INF;
         if (spec)
         {
@@ -3310,7 +3368,7 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, co
         if (finish_col != CC_COL_INF)
         {
             p.u_finishcol[i] = finish_col;
-            const unsigned int np = p.u_np[i];
+            const unsigned int np = np_[k];
             if (np > 5) // cpp:936-940
             {
                 const int slot = atomicAdd(&st->n_clusters, 1);
@@ -3335,6 +3393,7 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, co
                     st->error = CC_DEV_LIST_OVERFLOW;
             }
         }
+      }
     }
 }
 
@@ -3345,41 +3404,83 @@ __device__ void d_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec
     CcDevState* st = p.st;
     const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
     const long long gbase = st->gbase;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const unsigned long long counter = st->cluster_counter;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x % CC_WARP;
+    // four entries per thread at a time (loads issued together); the entries that stay unfinished take their places in
+    // the compacted list with one atomic per warp. The loop bound is uniform per warp.
+    for (int i0 = tid - lane; i0 < n; i0 += 4 * nt)
     {
-        const int j = p.u_rep[i];
-        const long long fc = p.u_finishcol[j];
-        const unsigned int root = p.ulist[i];
-        const long long gi = p.slot_gcol[root / cfg.R] - gbase;
-        if (fc != CC_COL_INF)
+        int j[4];
+        unsigned int root[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
         {
-            const int slot = p.u_cluster[j];
-            p.tstate[root] = 1u + seq;
-            p.tslot[root] = slot;
-            p.tid[root] = slot >= 0 ? static_cast<unsigned int>(st->cluster_counter + static_cast<unsigned long long>(slot)) : 0u;
-            if (gi >= 0 && gi < p.cap_G)
-                atomicMax(p.G + gi, fc);
+            const int i = i0 + lane + k * nt;
+            j[k] = i < n ? p.u_rep[i] : -1;
+            root[k] = i < n ? p.ulist[i] : CC_NONE;
         }
-        else
+        long long fc[4], gi[4];
+        int slot[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
         {
-            if (gi >= 0 && gi < p.cap_G)
-                atomicMax(p.G + gi, CC_COL_INF);
-            const int pos = atomicAdd(p.n_new_ulist, 1);
-            p.ulist_new[pos] = root;
+            fc[k] = CC_COL_INF;
+            gi[k] = -1;
+            slot[k] = -1;
+            if (j[k] >= 0)
+            {
+                fc[k] = p.u_finishcol[j[k]];
+                slot[k] = p.u_cluster[j[k]];
+                gi[k] = p.slot_gcol[root[k] / cfg.R] - gbase;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const bool valid = j[k] >= 0;
+            const bool finished = valid && fc[k] != CC_COL_INF;
+            if (finished)
+            {
+                p.tstate[root[k]] = 1u + seq;
+                p.tslot[root[k]] = slot[k];
+                p.tid[root[k]] = slot[k] >= 0 ? static_cast<unsigned int>(counter + static_cast<unsigned long long>(slot[k])) : 0u;
+            }
+            if (valid && gi[k] >= 0 && gi[k] < p.cap_G)
+                atomicMax(p.G + gi[k], finished ? fc[k] : CC_COL_INF);
+            const bool keep = valid && !finished;
+            const unsigned int km = __ballot_sync(CC_FULL_MASK, keep);
+            if (km)
+            {
+                int pos0 = 0;
+                if (lane == __ffs(km) - 1)
+                    pos0 = atomicAdd(p.n_new_ulist, __popc(km));
+                pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(km) - 1);
+                if (keep)
+                    p.ulist_new[pos0 + __popc(km & ((1u << lane) - 1u))] = root[k];
+            }
         }
     }
 }
-
 __device__ void d_fin_copyback(CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
     const int n = *p.n_new_ulist;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i0 = tid; i0 < n; i0 += 4 * nt)
     {
-        const unsigned int root = p.ulist_new[i];
-        p.ulist[i] = root;
-        p.rootslot[root] = static_cast<unsigned int>(i);
+        unsigned int root[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            root[k] = i0 + k * nt < n ? p.ulist_new[i0 + k * nt] : CC_NONE;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (root[k] != CC_NONE)
+            {
+                p.ulist[i0 + k * nt] = root[k];
+                p.rootslot[root[k]] = static_cast<unsigned int>(i0 + k * nt);
+            }
     }
 }
 
