@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="firings per push (= per step); 4096 = two rotations")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident leg + kernel tables only (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -409,22 +410,36 @@ def main():
         cc.set_kernel_timing(False)
         tot = sum(v[0] for v in acc.values())
         kernel_table = {k: {"ms_per_step": v[0] / reps, "share": v[0] / tot} for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
-        top = next(iter(kernel_table))
+        # the dominant kernel among those that stream the range image (k_fin_all works on the list of unfinished trees,
+        # a few thousand entries: it has no per-cell traffic to put against a bandwidth roofline)
+        top = next((k for k in kernel_table if k in KERNEL_BYTES_PER_CELL), next(iter(kernel_table)))
         peak, peak_src = load_peaks()
         bpc = KERNEL_BYTES_PER_CELL.get(top, 8)
         alg_bytes = bpc * B * R
         dur_s = kernel_table[top]["ms_per_step"] / 1e3
         achieved = alg_bytes / dur_s / 1e9
+        traffic, traffic_src = None, None
+        tp = os.path.join(HERE, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            with open(tp) as f:
+                tj = json.load(f)
+            if top in tj.get("kernels", {}):
+                traffic = tj["kernels"][top]["dram_bytes"]
+                traffic_src = tj.get("source")
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": kernel_table[top]["share"],
+                    "by_kernel": {k: {"algorithmic_bytes_per_launch": KERNEL_BYTES_PER_CELL[k] * B * R,
+                                      "achieved_gbs": KERNEL_BYTES_PER_CELL[k] * B * R / (v["ms_per_step"] / 1e3) / 1e9,
+                                      "frac": KERNEL_BYTES_PER_CELL[k] * B * R / (v["ms_per_step"] / 1e3) / 1e9 / peak}
+                                  for k, v in kernel_table.items() if k in KERNEL_BYTES_PER_CELL},
                     "path_bytes_per_cell": 151, "path_achieved_gbs": value / world * R * 151 / 1e9,
                     "path_frac": value / world * R * 151 / 1e9 / peak}
     cc.close()
 
     # ------------------------------------------------------------------ other operating points (rank 0, single GPU)
     batch_sweep, latency_mode, flushed = None, None, None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.quick:
         lg = device_leg(B, 10, 3, False, flush_each_step=True)
         flushed = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 10,
                    "per_push_device_ms_p50": float(np.median(lg["dev_ms"])),
@@ -462,6 +477,11 @@ def main():
     # ------------------------------------------------------------------ end-to-end leg through the public API
     cc = new_handle()
     cc.set_label_prefetch(True)  # the ground labels of the new columns come back with every push's results
+    if args.quick:
+        K_e2e = min(K, 2)
+    else:
+        K_e2e = K
+    total = (W + K_e2e) * B
     h_pts, h_poses = tile_stream(base_pts, base_poses, sp, 0, total)
     # page-locked host buffers (the contract's "pinned host memory"): cc_push_firings copies them straight to the device
     pin_pts = torch.from_numpy(h_pts.view(np.uint8).reshape(total, R * 48)).pin_memory()
@@ -475,10 +495,10 @@ def main():
     t0 = time.perf_counter()
     # two pushes in flight and a third one staged: the host->device copy of push k + 2 (input stream) overlaps the
     # kernels of pushes k and k + 1; its kernels are launched by the wait() that returns push k
-    for s in range(W, min(W + 2, W + K)):
+    for s in range(W, min(W + 2, W + K_e2e)):
         cc.submitFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
-    for s in range(W, W + K):
-        if s + 2 < W + K:
+    for s in range(W, W + K_e2e):
+        if s + 2 < W + K_e2e:
             cc.submitFirings(h_pts[(s + 2) * B:(s + 3) * B], h_poses[(s + 2) * B:(s + 3) * B])
         res = cc.wait()
         labels = cc.column_labels()  # [n_cols, rows, 4] u8: ground label, debug label, is_ignored, intensity
@@ -490,7 +510,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * K * B / e2e_s
+    e2e_value = world * K_e2e * B / e2e_s
     cc.close()
 
     cpu = None
@@ -514,7 +534,7 @@ def main():
                        "exact_path_pushes": exact_pushes},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": B * (rec_bytes + pose_bytes),
-                    "d2h_bytes_per_step": int(d2h // K)},
+                    "d2h_bytes_per_step": int(d2h // K_e2e)},
             "latency": {"per_push_device_ms_p50": float(np.median(dev_ms)),
                         "per_push_sync_call_ms_p50": float(np.median(sync_ms)),
                         "note": "one push = batch_firings columns; every column of a push is charged the whole push",
