@@ -2122,20 +2122,27 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
                 p.visited[cell] = 0;
             }
         }
-        // the column's non-ignored points join the list the association probe works through (one atomic per 32 rows)
+        // the column's non-ignored points join the list the association probe works through (one atomic per column)
+        int ntake = 0;
         for (int row0 = 0; row0 < R; row0 += CC_WARP)
         {
             const int row = row0 + lane;
-            const bool take = row < R && (s_cls[row < R ? row : 0] & 0x80) != 0;
-            const unsigned int m = __ballot_sync(CC_FULL_MASK, take);
-            if (m)
+            ntake += __popc(__ballot_sync(CC_FULL_MASK, row < R && (s_cls[row < R ? row : 0] & 0x80) != 0));
+        }
+        if (ntake)
+        {
+            int pos0 = 0;
+            if (lane == 0)
+                pos0 = atomicAdd(&p.st->n_probe, ntake);
+            pos0 = __shfl_sync(CC_FULL_MASK, pos0, 0);
+            for (int row0 = 0; row0 < R; row0 += CC_WARP)
             {
-                int pos0 = 0;
-                if (lane == __ffs(m) - 1)
-                    pos0 = atomicAdd(&p.st->n_probe, __popc(m));
-                pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(m) - 1);
+                const int row = row0 + lane;
+                const bool take = row < R && (s_cls[row < R ? row : 0] & 0x80) != 0;
+                const unsigned int m = __ballot_sync(CC_FULL_MASK, take);
                 if (take)
                     p.probe_list[pos0 + __popc(m & ((1u << lane) - 1u))] = ci * R + row;
+                pos0 += __popc(m);
             }
         }
         min_az = cc_warp_min_f64(min_az);
