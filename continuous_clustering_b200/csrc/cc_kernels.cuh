@@ -2,13 +2,16 @@
 // contraction; it is streaming scans + a neighbourhood walk + union-find, bound by HBM/L2 latency.
 //
 // Reference functions replaced ("cpp:" = src/clustering/continuous_clustering.cpp of the reference):
-//   k_prep + k_insert_scan + k_scatter   insertFiringIntoRangeImage              cpp:105-292
+//   k_prep (+ recycling of retired columns), k_scan_lite, k_scan_check, k_insert_scan, k_scatter
+//                                        insertFiringIntoRangeImage, clearColumns cpp:105-292, 1094-1145
 //   k_gap_scan + k_ground                performGroundPointSegmentationForColumn cpp:294-624
-//   k_probe + k_commit_* / k_careful     associatePointsInColumn, traverseFieldOfView,
+//   k_probe + k_probe_heavy + k_commit_* / k_careful
+//                                        associatePointsInColumn, traverseFieldOfView,
 //                                        associatePointToPointTree, associatePointTreeToPointTree cpp:638-835
-//   k_fin_*                              findFinishedTreesAndAssignSameId        cpp:837-974 and the id / ring
+//   k_fin_all + k_fin_label              findFinishedTreesAndAssignSameId        cpp:837-974 and the id / ring
 //                                        bookkeeping half of collectPointsForCusterAndPublish cpp:976-1092
-//   k_clear                              clearColumns                            cpp:1094-1145
+// Every kernel starts with CC_PDL_ENTER() (programmatic dependent launch, cc_platform.h) and an optional timeline
+// stamp (CcTraceScope, cc_debug_trace).
 //
 // Everything is compiled with -fmad=false: the reference is built without FMA contraction (CMakeLists.txt:5-12)
 // and ground labels / column indices must be bit-identical.
@@ -1672,21 +1675,6 @@ CC_DEV double cc_ldcg_f64(const double* q)
 #else
     return __ldcg(q);
 #endif
-}
-
-// |RN(y / x)| < m, decided without the division unless the quotient is within 1e-6 (relative) of m
-CC_DEV bool cc_slope_below(float y, float x, float m)
-{
-    const float t = m * fabsf(x);
-    if (t > 1e-30f && t < 1e30f)
-    {
-        const float ay = fabsf(y);
-        if (ay < t * 0.999999f)
-            return true;
-        if (ay > t * 1.000001f)
-            return false;
-    }
-    return fabsf(ccm::div_rn(y, x)) < m;
 }
 
 __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)

@@ -7,7 +7,8 @@
 // Behavioural notes for integrators:
 //  * firings are handed to the GPU in batches of `setBatchSize()` firings (default 64, env CC_B200_BATCH); callbacks
 //    are delivered from inside the addFiring()/flush() call that completes a batch, on the caller's thread, in the
-//    order of the reference's single-threaded mode. flush() pushes a partial batch.
+//    order of the reference's single-threaded mode. flush() pushes a partial batch. setPipelined(true) trades
+//    callback latency (up to two batches) for throughput.
 //  * range_image_ holds host copies of exactly the columns reported by finished-column callbacks (that is what the
 //    reference's consumers read, ros_utils.cpp:56-63, kitti_demo.cpp:183-216).
 #ifndef CONTINUOUS_CLUSTERING_CONTINUOUS_CLUSTERING_HPP
@@ -175,6 +176,12 @@ class ContinuousClustering
     void flush();                    // push the firings buffered so far and deliver their callbacks
     void setBatchSize(int firings);  // firings per device push (1 = a push per addFiring call)
     void setDevice(int ordinal);     // CUDA device of this stream; call before the first reset()
+    // Throughput mode (off by default, env CC_B200_PIPELINE=1): a full batch is submitted asynchronously and its
+    // callbacks are delivered by a later addFiring()/flush() call -- up to two batches late, still in order and on the
+    // caller's thread -- so that the host (buffering, callbacks) and the device overlap. drain() delivers whatever is
+    // still outstanding (call it at the end of a replay; reset() discards it like the reference's reset does).
+    void setPipelined(bool on);
+    void drain();
 
   public:
     // range image (implemented as ring buffer) -- public data members read by callers (hpp:244-251)
@@ -196,9 +203,14 @@ class ContinuousClustering
     int batch_size_{64};
     Configuration config_;
     bool config_dirty_{true};
-    std::vector<unsigned char> pending_points_; // cc_raw_point_t records
-    std::vector<double> pending_poses_;
+    // firings buffered for the next push: cc_raw_point_t records + poses. Three buffers rotate in pipelined mode (a
+    // buffer handed to cc_submit_firings must stay valid until its push has been waited for; at most two pushes are
+    // outstanding when the next buffer is taken)
+    std::vector<unsigned char> points_buf_[3];
+    std::vector<double> poses_buf_[3];
+    int cur_buf_{0};
     int pending_{0};
+    bool pipelined_{false};
     std::function<void(int64_t, int64_t, bool)> finished_column_callback_;
     std::function<void(const std::vector<Point>&, uint64_t)> finished_cluster_callback_;
     std::vector<Point> cluster_buffer_;

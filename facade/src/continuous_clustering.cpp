@@ -66,6 +66,8 @@ ContinuousClustering::ContinuousClustering()
         batch_size_ = std::max(1, std::atoi(b));
     if (const char* d = std::getenv("CC_B200_DEVICE"))
         device_ = std::atoi(d);
+    if (const char* q = std::getenv("CC_B200_PIPELINE"))
+        pipelined_ = std::atoi(q) != 0;
 }
 
 ContinuousClustering::~ContinuousClustering()
@@ -106,10 +108,29 @@ void ContinuousClustering::setBatchSize(int firings)
     batch_size_ = std::max(1, std::min(firings, 4096));
 }
 
+void ContinuousClustering::setPipelined(bool on)
+{
+    flush();
+    drain();
+    pipelined_ = on;
+}
+
+void ContinuousClustering::drain()
+{
+    while (handle_ && cc_pending(handle_) > 0)
+    {
+        int s = cc_wait(handle_);
+        if (s != CC_OK)
+            fail(s);
+        deliver();
+    }
+}
+
 void ContinuousClustering::setConfiguration(const Configuration& config)
 {
     ensureHandle();
     flush(); // firings already handed over were processed with the previous parameters
+    drain();
     config_ = config;
     cc_config_t c;
     toC(config, c);
@@ -127,9 +148,12 @@ void ContinuousClustering::reset(int num_rows)
 {
     ensureHandle();
     pending_ = 0;
-    pending_points_.clear();
-    pending_poses_.clear();
-    int s = cc_reset(handle_, num_rows);
+    for (int b = 0; b < 3; b++)
+    {
+        points_buf_[b].clear();
+        poses_buf_[b].clear();
+    }
+    int s = cc_reset(handle_, num_rows); // pushes still in flight are discarded with the rest of the state
     if (s != CC_OK)
         fail(s);
     num_rows_ = cc_num_rows(handle_);
@@ -170,11 +194,13 @@ void ContinuousClustering::addFiring(const RawPoints::ConstPtr& firing, const Ei
     if (num_rows_ != static_cast<int>(firing->points.size())) // cpp:90-91
         throw std::runtime_error("The number of points in a firing has changed. This is probably a bug!");
     const size_t bytes = firing->points.size() * sizeof(RawPoint);
-    const size_t off = pending_points_.size();
-    pending_points_.resize(off + bytes);
-    std::memcpy(pending_points_.data() + off, firing->points.data(), bytes);
-    pending_poses_.resize(pending_poses_.size() + 12);
-    pose12(odom_from_sensor, pending_poses_.data() + pending_poses_.size() - 12);
+    std::vector<unsigned char>& pts = points_buf_[cur_buf_];
+    std::vector<double>& poses = poses_buf_[cur_buf_];
+    const size_t off = pts.size();
+    pts.resize(off + bytes);
+    std::memcpy(pts.data() + off, firing->points.data(), bytes);
+    poses.resize(poses.size() + 12);
+    pose12(odom_from_sensor, poses.data() + poses.size() - 12);
     if (++pending_ >= batch_size_)
         flush();
 }
@@ -185,24 +211,51 @@ void ContinuousClustering::flush()
         return;
     const int n = pending_;
     pending_ = 0;
+    std::vector<unsigned char>& pts = points_buf_[cur_buf_];
+    std::vector<double>& poses = poses_buf_[cur_buf_];
     const int step = std::max(1, cc_max_firings_per_push(handle_));
     const size_t rec = static_cast<size_t>(num_rows_) * sizeof(cc_raw_point_t);
     for (int a = 0; a < n; a += step)
     {
         const int m = std::min(step, n - a);
-        int s = cc_push_firings(handle_, m, num_rows_,
-                                reinterpret_cast<const cc_raw_point_t*>(pending_points_.data() + static_cast<size_t>(a) * rec),
-                                pending_poses_.data() + static_cast<size_t>(a) * 12);
-        if (s != CC_OK)
+        const cc_raw_point_t* src = reinterpret_cast<const cc_raw_point_t*>(pts.data() + static_cast<size_t>(a) * rec);
+        const double* src_poses = poses.data() + static_cast<size_t>(a) * 12;
+        if (!pipelined_)
         {
-            pending_points_.clear();
-            pending_poses_.clear();
-            fail(s);
+            int s = cc_push_firings(handle_, m, num_rows_, src, src_poses);
+            if (s != CC_OK)
+            {
+                pts.clear();
+                poses.clear();
+                fail(s);
+            }
+            deliver();
+            continue;
         }
-        deliver();
+        // throughput mode: make room (at most two pushes in flight and one staged), hand the push over, and deliver what
+        // has finished in the meantime; at most two pushes stay outstanding, so the buffer taken next is free again
+        while (cc_pending(handle_) > 2)
+        {
+            int s = cc_wait(handle_);
+            if (s != CC_OK)
+                fail(s);
+            deliver();
+        }
+        int s = cc_submit_firings(handle_, m, num_rows_, src, src_poses);
+        if (s != CC_OK)
+            fail(s);
+        while (cc_pending(handle_) > 2)
+        {
+            s = cc_wait(handle_);
+            if (s != CC_OK)
+                fail(s);
+            deliver();
+        }
     }
-    pending_points_.clear();
-    pending_poses_.clear();
+    if (pipelined_)
+        cur_buf_ = (cur_buf_ + 1) % 3;
+    points_buf_[cur_buf_].clear();
+    poses_buf_[cur_buf_].clear();
 }
 
 // host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63)

@@ -223,18 +223,23 @@ CC_API cc_status_t cc_push_firings(cc_handle_t* h, int n_firings, int rows_per_f
 CC_API cc_status_t cc_push_firings_device(cc_handle_t* h, int n_firings, int rows_per_firing,
                                           const cc_raw_point_t* d_points, const double* d_poses);
 
-/* Asynchronous variant: cc_submit_* enqueues the host->device copy (on a separate copy stream) and every kernel of
+/* Asynchronous variant: cc_submit_* enqueues the host->device copy (on its own input stream) and every kernel of
  * the push and returns at once; cc_wait() blocks until the OLDEST submitted push is finished and makes its results
- * current (cc_get_batch_info & co). At most two pushes may be in flight, so a caller keeps the GPU busy with
- * `submit(k+1); wait(k)`. Inputs must stay valid until the push has been waited for. cc_push_firings* ==
+ * current (cc_get_batch_info & co). At most two pushes are in flight. A third HOST push may be submitted while two
+ * are in flight: it is STAGED -- its input copy starts at once (into the third of three device input buffers), its
+ * kernels are launched by the first cc_submit_* / cc_wait call after the cc_wait() that made room (not by that cc_wait
+ * itself, so that the caller can still read the columns the finished push reported: the staged push's first kernel
+ * recycles ring columns). A caller keeps the GPU and the PCIe link busy with `submit(k+2); wait(k)`; with device
+ * inputs `submit(k+1); wait(k)`. Inputs must stay valid until the push has been waited for. cc_push_firings* ==
  * submit + wait. If a push in flight cannot be committed speculatively the pushes behind it
- * skip themselves on the device and cc_wait() transparently re-runs them after finishing it. */
+ * skip themselves on the device and cc_wait() transparently re-runs them after finishing it. Result views
+ * (cc_get_result_views, cc_get_column_labels) stay valid until the next cc_wait() on the handle. */
 CC_API cc_status_t cc_submit_firings(cc_handle_t* h, int n_firings, int rows_per_firing,
                                      const cc_raw_point_t* points, const double* poses);
 CC_API cc_status_t cc_submit_firings_device(cc_handle_t* h, int n_firings, int rows_per_firing,
                                             const cc_raw_point_t* d_points, const double* d_poses);
 CC_API cc_status_t cc_wait(cc_handle_t* h);
-CC_API int cc_pending(const cc_handle_t* h); /* pushes in flight (0..2) */
+CC_API int cc_pending(const cc_handle_t* h); /* pushes in flight + staged (0..3) */
 /* Largest n_firings one push accepts: min(max_firings_per_push, 3 * num_columns). */
 CC_API int cc_max_firings_per_push(const cc_handle_t* h);
 
@@ -246,7 +251,7 @@ CC_API cc_status_t cc_get_clusters(const cc_handle_t* h, cc_cluster_t* out, int 
 CC_API cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out, int cap, int* n_out);
 
 /* Zero-copy variant: pointers to the handle's own result arrays (n_events / n_clusters / n_cluster_points entries,
- * see cc_get_batch_info), valid until the next push or reset on this handle. */
+ * see cc_get_batch_info), valid until the next cc_wait / synchronous push or reset on this handle. */
 CC_API cc_status_t cc_get_result_views(const cc_handle_t* h, const cc_column_event_t** events,
                                        const cc_cluster_t** clusters, const cc_cluster_point_t** points);
 

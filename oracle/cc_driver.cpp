@@ -251,6 +251,7 @@ int drv_add_firings(drv_t* d, int n, int rows, const cc_raw_point_t* pts, const 
             d->cc.addFiring(makeFiring(rows, pts + static_cast<size_t>(k) * rows), poseFrom12(poses + 12 * k));
 #ifdef CC_B200_FACADE
         d->cc.flush(); // the facade batches firings; the reference delivers everything inside addFiring
+        d->cc.drain(); // and, in its throughput mode, delivers a batch's callbacks up to two batches late
 #endif
     }
     catch (const std::exception& e)
@@ -314,6 +315,7 @@ double drv_run_prepared(drv_t* d, int from, int to, int64_t max_lag_columns)
         }
 #ifdef CC_B200_FACADE
         d->cc.flush();
+        d->cc.drain();
 #endif
         if (!d->config.general.is_single_threaded)
         {

@@ -15,8 +15,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DRIVER = os.path.join(REPO, "build", "libcc_facade_driver_emu_test.so")
 
 
-def run(lib, spec, kw, cfg_over, batch):
+def run(lib, spec, kw, cfg_over, batch, pipelined=False):
     os.environ["CC_B200_BATCH"] = str(batch)
+    os.environ["CC_B200_PIPELINE"] = "1" if pipelined else "0"
     pts, poses, sp = synth.make_stream(spec, **kw)
     cfg = drvlib.stream_config(spec, **cfg_over)
     d = drvlib.Driver(lib)
@@ -41,9 +42,18 @@ def test_facade_on_emulation_library(emu_library, oracle_lib, spec, kw, cfg_over
     run(EMU_DRIVER, spec, kw, cfg_over, batch)
 
 
+@pytest.mark.parametrize("spec,kw,cfg_over,batch", CASES)
+def test_pipelined_facade_on_emulation_library(emu_library, oracle_lib, spec, kw, cfg_over, batch):
+    """Throughput mode of the facade (CC_B200_PIPELINE=1): batches are submitted asynchronously, callbacks arrive up to two
+    batches late; what the driver records must not change."""
+    subprocess.run(["make", "-C", "facade", "emu"], cwd=REPO, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    run(EMU_DRIVER, spec, kw, cfg_over, batch, pipelined=True)
+
+
 def test_facade_throws_like_reference(emu_library, oracle_lib):
     subprocess.run(["make", "-C", "facade", "emu"], cwd=REPO, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     os.environ["CC_B200_BATCH"] = "32"
+    os.environ["CC_B200_PIPELINE"] = "0"
     pts, poses, sp = synth.make_stream("tiny16", n_firings=200)
     cfg = drvlib.stream_config("tiny16")
     d = drvlib.Driver(EMU_DRIVER)
@@ -62,3 +72,11 @@ def test_facade_on_cuda_library(cuda_library, oracle_lib, spec, kw, cfg_over, ba
     if not os.path.exists(drvlib.FACADE_LIB):
         subprocess.run(["make", "-C", "facade"], cwd=REPO, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     run(drvlib.FACADE_LIB, spec, kw, cfg_over, batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,kw,cfg_over,batch", [CASES[0], ("velodyne64", dict(n_rotations=3.2, moving=True), {}, 1024)])
+def test_pipelined_facade_on_cuda_library(cuda_library, oracle_lib, spec, kw, cfg_over, batch):
+    if not os.path.exists(drvlib.FACADE_LIB):
+        subprocess.run(["make", "-C", "facade"], cwd=REPO, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    run(drvlib.FACADE_LIB, spec, kw, cfg_over, batch, pipelined=True)
