@@ -429,9 +429,11 @@ cc_status_t cc_set_config(cc_handle_t* h, const cc_config_t* cfg)
 {
     if (!h || !cfg)
         return CC_ERR_INVALID_ARGUMENT;
-    if (cfg->num_columns <= 1 || cfg->cluster_point_trees_every_nth_column <= 0)
+    // (the association probe keeps one running maximum per new column in shared memory: 8192 firings + num_columns
+    // columns at most; sensors of the reference have 1024 .. 2200 columns per rotation)
+    if (cfg->num_columns <= 1 || cfg->num_columns > 16384 || cfg->cluster_point_trees_every_nth_column <= 0)
     {
-        h->error = "invalid configuration";
+        h->error = "invalid configuration (num_columns must be in 2 .. 16384, cluster_point_trees_every_nth_column > 0)";
         return CC_ERR_INVALID_ARGUMENT;
     }
     // cpp:66-81

@@ -237,6 +237,10 @@ struct CcOpMaxF64
 {
     CC_DEV double operator()(double a, double b) const { return a > b ? a : b; }
 };
+struct CcOpMaxI32
+{
+    CC_DEV int operator()(int a, int b) const { return a > b ? a : b; }
+};
 struct CcOpMaxI64
 {
     CC_DEV long long operator()(long long a, long long b) const { return a > b ? a : b; }
@@ -3501,22 +3505,51 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec, int smem_ints
     // as columns relative to gbase (CC_COL_INF -> INT_MAX)
     int* pg = reinterpret_cast<int*>(part + T);
     const bool in_smem = glen <= smem_ints;
-    const long long chunk = (glen + T - 1) / T;
-    const long long lo = t * chunk, hi = (lo + chunk < glen) ? lo + chunk : glen;
-    long long m = -1;
-    for (long long j = lo; j < hi; j++)
-        m = p.G[j] > m ? p.G[j] : m;
-    long long pre = cc_block_exclusive_scan(part, m, -1LL, CcOpMaxI64());
-    for (long long j = lo; j < hi; j++)
+    if (in_smem)
     {
-        pre = p.G[j] > pre ? p.G[j] : pre;
-        if (in_smem)
+        // G staged once with coalesced loads issued together, as columns relative to gbase (monotone encoding, so the
+        // prefix maximum can be taken on the encoded values); contiguous segment per thread + block scan, in place
+        const int n = static_cast<int>(glen);
+        for (int i0 = 0; i0 < n; i0 += 8 * T)
         {
-            const long long rel = pre - gbase;
-            pg[j] = pre < 0 ? -1 : (rel > 0x7ffffffe ? 0x7fffffff : static_cast<int>(rel));
+            long long v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                v[u] = i0 + u * T + t < n ? p.G[i0 + u * T + t] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u * T + t < n)
+                {
+                    const long long rel = v[u] - gbase;
+                    pg[i0 + u * T + t] = v[u] < 0 ? -1 : (rel > 0x7ffffffe ? 0x7fffffff : static_cast<int>(rel));
+                }
         }
-        else
+        __syncthreads();
+        const int seg = ((n + T - 1) / T) | 1; // odd: the threads' segments start in different banks
+        const int lo = t * seg < n ? t * seg : n, hi = (lo + seg < n) ? lo + seg : n;
+        int m = -1;
+        for (int j = lo; j < hi; j++)
+            m = pg[j] > m ? pg[j] : m;
+        int pre = cc_block_exclusive_scan(reinterpret_cast<int*>(part), m, -1, CcOpMaxI32());
+        for (int j = lo; j < hi; j++)
+        {
+            pre = pg[j] > pre ? pg[j] : pre;
+            pg[j] = pre;
+        }
+    }
+    else
+    {
+        const long long chunk = (glen + T - 1) / T;
+        const long long lo = t * chunk, hi = (lo + chunk < glen) ? lo + chunk : glen;
+        long long m = -1;
+        for (long long j = lo; j < hi; j++)
+            m = p.G[j] > m ? p.G[j] : m;
+        long long pre = cc_block_exclusive_scan(part, m, -1LL, CcOpMaxI64());
+        for (long long j = lo; j < hi; j++)
+        {
+            pre = p.G[j] > pre ? p.G[j] : pre;
             p.G[j] = pre;
+        }
     }
     __syncthreads();
     for (long long c = c0 + t; c <= c1; c += T)
@@ -3594,25 +3627,28 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         return;
     }
     CC_SMEM(smem);
-    {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_init);
-        d_fin_init(cfg, p, ci0, ci1, guard);
-    }
-    __syncthreads();
     // shared memory: [block-scan scratch: T x 8 B][running maximum of the segment's columns | prefix maxima of G]
     const int T = blockDim.x;
     const int spare = (smem_bytes - T * 8) / 8; // doubles (or pairs of ints) that fit behind the scan scratch
     double* runmax_s = nullptr;
-    if (cc_spec_ok(p.st, guard))
     {
-        const int nseg = static_cast<int>(p.st->seg_c1 - p.st->seg_c0 + 1);
-        if (nseg <= spare)
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_init);
+        // the running maxima of the segment's columns are staged beside the initialisation (no barrier in between:
+        // the segment bounds are computed here the way d_fin_init stores them)
+        if (cc_spec_ok(p.st, guard))
         {
-            runmax_s = reinterpret_cast<double*>(smem) + T;
-            const long long off = p.st->seg_c0 - p.st->colbase;
-            for (int i = threadIdx.x; i < nseg; i += T)
-                runmax_s[i] = p.col_runmax[off + i];
+            const long long colbase = p.st->colbase;
+            const int ci1_eff = ci1 < 0 ? p.st->ncols - 1 : ci1;
+            const int nseg = ci1_eff - ci0 + 1;
+            if (nseg > 0 && nseg <= spare)
+            {
+                runmax_s = reinterpret_cast<double*>(smem) + T;
+                for (int i = threadIdx.x; i < nseg; i += T)
+                    runmax_s[i] = p.col_runmax[ci0 + i];
+            }
+            (void)colbase;
         }
+        d_fin_init(cfg, p, ci0, ci1, guard);
     }
     __syncthreads();
     {

@@ -231,3 +231,12 @@ def test_reset_mid_stream_and_callbacks(emu_library, oracle_lib):
     assert cols == [(int(e["from_gcol"]), int(e["to_gcol"]), bool(e["ground_points_only"])) for e in ev]
     assert sorted((s, n) for s, n, _ in clusters) == sorted((int(c["stamp"]), int(c["num_points"])) for c in want["clusters"])
     assert all(len(ids) == 1 and 0 not in ids for _, _, ids in clusters)
+
+
+def test_debug_hooks_are_inert_in_the_emulation(emu_library):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=1.0)
+    cc = make_cc(emu_library, drvlib.stream_config("tiny16"), sp.rows)
+    cc.debug_trace(True)
+    cc.addFirings(pts[:128], poses[:128])
+    assert cc.get_trace() == []  # the stamps are compiled out of the CPU build
+    cc.debug_trace(False)

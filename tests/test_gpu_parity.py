@@ -141,3 +141,20 @@ def test_device_resident_push_equals_host_push(cuda_library):
         assert np.array_equal(ra.events, rb.events)
         assert ra.info.n_cluster_points == rb.info.n_cluster_points
         assert rb.info.gpu_launches > 0
+
+
+@pytest.mark.gpu
+def test_device_timeline_does_not_change_results(cuda_library, oracle_lib):
+    """cc_debug_trace: the %globaltimer stamps of every CTA give per-kernel spans of a push as the kernels overlap in
+    normal operation; results stay identical with the hook on."""
+    pts, poses, sp = synth.make_stream("velodyne64", n_rotations=2.2, moving=True)
+    cfg = drvlib.stream_config("velodyne64")
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(None, cfg, sp.rows)
+    cc.debug_trace(True)
+    got = recorder.record(cc, pts, poses, 1024)
+    parity.compare(want, got, name_a="oracle", name_b="cuda, traced")
+    tr = {name: (a, z, longest, blocks) for name, a, z, longest, blocks in cc.get_trace()}
+    for k in ("k_prep", "k_ground", "k_probe", "k_fin_all", "k_fin_label"):
+        assert k in tr and tr[k][3] > 0 and tr[k][1] > tr[k][0]
+    assert tr["k_ground"][0] >= tr["k_prep"][0]
