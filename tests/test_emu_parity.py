@@ -53,6 +53,18 @@ CASES = [
     ("tiny16", dict(n_rotations=2.0, az_jitter=3.0), {}, 33, 0),
     ("velodyne64", dict(n_rotations=1.3, az_jitter=0.5, az_step_scale=1.04), {}, 1024, 0),
     ("vls128", dict(n_rotations=1.1, az_jitter=1.5, start_firing=40, moving=True), {}, 512, 0),
+    # rough ground (range noise) and low boxes with ground visible behind them: the label rules that carry state through
+    # a column -- YELLOW / YELLOWGREEN, the last-certain-ground updates and the DARKRED relabel walk (cpp:433-565) --
+    # fire on a large share of the points instead of on a handful
+    ("velodyne64", dict(n_rotations=1.2, range_noise=0.08, box_height_range=(0.2, 0.8), min_box_dist=3.0), {}, 700, 0),
+    ("velodyne64", dict(n_rotations=1.1, range_noise=0.05, box_height_range=(0.2, 1.0), min_box_dist=3.0, n_boxes=300,
+                        moving=True, dropout=0.03), dict(max_slope=0.08), 512, 0),
+    ("tiny16", dict(n_rotations=3.0, range_noise=0.1, box_height_range=(0.2, 0.8), min_box_dist=3.0, n_boxes=300), {}, 100, 0),
+    ("tiny16", dict(n_rotations=3.0, range_noise=0.1, box_height_range=(0.2, 0.8), min_box_dist=3.0, n_boxes=300, moving=True),
+     dict(first_ring_as_ground_max_allowed_z_diff=0.03, first_ring_as_ground_min_allowed_z_diff=-0.03), 64, 0),  # ORANGE
+    ("tiny16", dict(n_rotations=2.0, range_noise=0.1, box_height_range=(0.2, 0.8), min_box_dist=3.0), dict(use_terrain=1), 64, 0),
+    ("vls128", dict(n_rotations=1.1, range_noise=0.1, box_height_range=(0.2, 0.8), min_box_dist=3.0, n_boxes=300, moving=True),
+     {}, 600, 0),
 ]
 
 
