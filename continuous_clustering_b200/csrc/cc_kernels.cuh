@@ -3614,7 +3614,7 @@ CC_DEV void d_state_snapshot(CcDevPtrs p, CcDevState* dst)
 // All list-sized phases of a finish pass in ONE CTA (the unfinished-tree list holds 10^2..10^4 entries: a single
 // CTA with block-wide barriers between the phases is faster than six dependent launches).
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
-                                                  int exact, int last, int smem_bytes, CcDevState* snap)
+                                                  int exact, int last, int smem_bytes, CcDevState* snap, int defer_tail)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_all);
@@ -3622,7 +3622,7 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         return;
     if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
     {
-        if (snap)
+        if (snap && !defer_tail)
             d_state_snapshot(p, snap);
         return;
     }
@@ -3671,6 +3671,8 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         d_fin_copyback(p, guard);
     }
     __syncthreads();
+    if (defer_tail)
+        return; // experimental (CC_B200_TUNE bit 1): CTA 0 of k_fin_label does the rest beside the labelling
     {
         CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns);
         d_fin_columns(cfg, p, guard, spare * 2);
@@ -3687,11 +3689,36 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 
 // Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
 // host needs for the finished-cluster callback (cpp:1007-1028).
-__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec, int defer_tail, int last, int smem_bytes,
+                            CcDevState* snap)
 {
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label);
     const CcHead hd = cc_head(p.st);
+    if (defer_tail && blockIdx.x == 0)
+    {
+        // experimental (CC_B200_TUNE bit 1): the tail of the finish pass -- per-column first_unpublished, end-of-push
+        // bookkeeping, state copy -- runs in this CTA beside the labelling of the others instead of before it. Nothing it
+        // writes is read by the labelling (which uses the fields loaded above, gbase and seg_c1).
+        if (hd.halted)
+        {
+            if (snap)
+                d_state_snapshot(p, snap);
+            return;
+        }
+        {
+            CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns);
+            d_fin_columns(cfg, p, spec, (smem_bytes - static_cast<int>(blockDim.x) * 8) / 4);
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0)
+            d_push_done(p, spec);
+        if (snap)
+        {
+            __syncthreads();
+            d_state_snapshot(p, snap);
+        }
+    }
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_head_ok(hd, spec))

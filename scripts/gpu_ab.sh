@@ -3,7 +3,7 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 for t in $1; do
-  CC_B200_TUNE=$t python bench.py --no-cpu-baseline > gpurun_out/bench_ab$t.json 2> gpurun_out/bench_ab$t.err
+  CC_B200_TUNE=$t timeout 120 python bench.py --quick --no-cpu-baseline > gpurun_out/bench_ab$t.json 2> gpurun_out/bench_ab$t.err
   python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_ab$t.json'))
