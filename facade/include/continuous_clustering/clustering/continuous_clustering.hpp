@@ -175,6 +175,10 @@ class ContinuousClustering
     // ---- extensions of the B200 facade ----
     void flush();                    // push the firings buffered so far and deliver their callbacks
     void setBatchSize(int firings);  // firings per device push (1 = a push per addFiring call)
+    // A partial batch is pushed by the addFiring call that finds its oldest firing waiting longer than this (default
+    // 2000 us, env CC_B200_MAX_WAIT_US; negative = only full batches), by setTransformRobotFrameFromSensorFrame /
+    // setConfiguration / reset (order relative to addFiring is the reference's) and by the destructor.
+    void setMaxBatchLatency(int64_t microseconds);
     void setDevice(int ordinal);     // CUDA device of this stream; call before the first reset()
     // Throughput mode (off by default, env CC_B200_PIPELINE=1): a full batch is submitted asynchronously and its
     // callbacks are delivered by a later addFiring()/flush() call -- up to two batches late, still in order and on the
@@ -210,6 +214,8 @@ class ContinuousClustering
     std::vector<double> poses_buf_[3];
     int cur_buf_{0};
     int pending_{0};
+    int64_t max_wait_us_{2000};
+    int64_t first_pending_us_{0};
     bool pipelined_{false};
     std::function<void(int64_t, int64_t, bool)> finished_column_callback_;
     std::function<void(const std::vector<Point>&, uint64_t)> finished_cluster_callback_;

@@ -2,6 +2,7 @@
 // Replaces src/clustering/continuous_clustering.cpp of the reference at link time. No pipeline stage is computed here.
 #include <continuous_clustering/clustering/continuous_clustering.hpp>
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -68,10 +69,27 @@ ContinuousClustering::ContinuousClustering()
         device_ = std::atoi(d);
     if (const char* q = std::getenv("CC_B200_PIPELINE"))
         pipelined_ = std::atoi(q) != 0;
+    if (const char* w = std::getenv("CC_B200_MAX_WAIT_US"))
+        max_wait_us_ = std::atoll(w);
+}
+
+static int64_t nowMicros()
+{
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 ContinuousClustering::~ContinuousClustering()
 {
+    // an unchanged caller (kitti_demo, the ROS node) never calls flush(): whatever is still buffered or in flight is
+    // processed and delivered here, like the reference's worker threads finish their queues before the object dies
+    try
+    {
+        flush();
+        drain();
+    }
+    catch (...)
+    {
+    }
     if (handle_)
         cc_destroy(handle_);
 }
@@ -147,6 +165,16 @@ bool ContinuousClustering::resetRequired() const
 void ContinuousClustering::reset(int num_rows)
 {
     ensureHandle();
+    // firings handed over before reset() were already processed by the reference at this point: push them first (an
+    // error they raise would have escaped an earlier addFiring call there; here it is dropped with the state)
+    try
+    {
+        flush();
+        drain();
+    }
+    catch (...)
+    {
+    }
     pending_ = 0;
     for (int b = 0; b < 3; b++)
     {
@@ -167,6 +195,10 @@ void ContinuousClustering::reset(int num_rows)
 void ContinuousClustering::setTransformRobotFrameFromSensorFrame(const Eigen::Isometry3d& tf)
 {
     ensureHandle();
+    // order relative to addFiring is kept: firings buffered so far are segmented with the transform they were handed
+    // over under (or raise "Transform ... not set yet" like the reference, cpp:298-299)
+    flush();
+    drain();
     double m[12];
     pose12(tf, m);
     cc_set_robot_from_sensor(handle_, m);
@@ -201,8 +233,17 @@ void ContinuousClustering::addFiring(const RawPoints::ConstPtr& firing, const Ei
     std::memcpy(pts.data() + off, firing->points.data(), bytes);
     poses.resize(poses.size() + 12);
     pose12(odom_from_sensor, poses.data() + poses.size() - 12);
-    if (++pending_ >= batch_size_)
+    if (pending_ == 0)
+        first_pending_us_ = nowMicros();
+    // a batch goes to the device when it is full or when its oldest firing has waited max_wait_us_ (firings arrive
+    // continuously, ~50 us apart at 64x2048 @ 10 Hz, so checking on arrival bounds the added latency)
+    if (++pending_ >= batch_size_ || (max_wait_us_ >= 0 && nowMicros() - first_pending_us_ >= max_wait_us_))
         flush();
+}
+
+void ContinuousClustering::setMaxBatchLatency(int64_t microseconds)
+{
+    max_wait_us_ = microseconds;
 }
 
 void ContinuousClustering::flush()
@@ -211,6 +252,19 @@ void ContinuousClustering::flush()
         return;
     const int n = pending_;
     pending_ = 0;
+    // whatever way this function is left (fail() throws), the buffer that was handed over is not reused with stale
+    // records behind it: in pipelined mode the next buffer is taken, and the buffer taken next starts out empty
+    struct Rotate
+    {
+        ContinuousClustering* self;
+        ~Rotate()
+        {
+            if (self->pipelined_)
+                self->cur_buf_ = (self->cur_buf_ + 1) % 3;
+            self->points_buf_[self->cur_buf_].clear();
+            self->poses_buf_[self->cur_buf_].clear();
+        }
+    } rotate{this};
     std::vector<unsigned char>& pts = points_buf_[cur_buf_];
     std::vector<double>& poses = poses_buf_[cur_buf_];
     const int step = std::max(1, cc_max_firings_per_push(handle_));
@@ -224,11 +278,7 @@ void ContinuousClustering::flush()
         {
             int s = cc_push_firings(handle_, m, num_rows_, src, src_poses);
             if (s != CC_OK)
-            {
-                pts.clear();
-                poses.clear();
                 fail(s);
-            }
             deliver();
             continue;
         }
@@ -252,10 +302,6 @@ void ContinuousClustering::flush()
             deliver();
         }
     }
-    if (pipelined_)
-        cur_buf_ = (cur_buf_ + 1) % 3;
-    points_buf_[cur_buf_].clear();
-    poses_buf_[cur_buf_].clear();
 }
 
 // host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63)

@@ -17,6 +17,55 @@
 #define DRV_IMPL_NAME "unknown"
 #endif
 
+#ifdef DRV_WITH_CALLER_EXCERPTS
+// The reference's own caller code, cut out of /root/reference at build time (oracle/extract_caller_excerpts.py ->
+// oracle/_ref/*.inc, never committed) and compiled UNMODIFIED against whichever class header this driver is built
+// with: against the facade's headers this is the compile-time half of the drop-in proof (ros_utils.cpp:245-298 reads
+// every Point field the ROS node publishes, kitti_demo.cpp:173-224 is the evaluation callback), and running it on
+// both objects is the oracle for the published PointCloud2 bytes.
+#include <map>
+#include <optional>
+
+#include <sensor_msgs/PointCloud2.h>
+#include <sensor_msgs/point_cloud2_iterator.h>
+
+namespace continuous_clustering
+{
+#include "ros_utils_types.inc"
+PointCloud2Iterators prepareMessageAndCreateIterators(sensor_msgs::PointCloud2& msg, ProcessingStage fill_fields_up_to_stage);
+void addPointToMessage(PointCloud2Iterators& container, int data_index_message, const Point& point, int num_rows,
+                       ProcessingStage fill_fields_up_to_stage);
+#include "ros_utils_clouds.inc"
+#include "ros_utils_fields.inc"
+
+struct KittiSegmentationEvaluationPoint // the three members the callback writes (kitti_evaluation.hpp:18-36)
+{
+    bool has_corresponding_point_in_detection_point_cloud{false};
+    bool is_ground_point{false};
+    uint32_t detection_label{0};
+};
+
+struct KittiDemoCallback // the members of class KittiDemo the callback body touches (kitti_demo.cpp:444-448)
+{
+    std::map<std::pair<uint16_t, uint16_t>, std::vector<KittiSegmentationEvaluationPoint>> map_frame_to_point_cloud;
+    int current_sequence_index{0};
+    int previous_frame_index{0};
+    std::map<int, std::vector<KittiSegmentationEvaluationPoint>> evaluated; // by frame
+    void evaluatePreviousFrame() // kitti_demo.cpp:160-171 without the evaluation itself: keeps the labelled frame
+    {
+        auto it = map_frame_to_point_cloud.find({static_cast<uint16_t>(current_sequence_index), static_cast<uint16_t>(previous_frame_index)});
+        if (it != map_frame_to_point_cloud.end())
+        {
+            evaluated[previous_frame_index] = std::move(it->second);
+            map_frame_to_point_cloud.erase(it);
+        }
+        previous_frame_index++;
+    }
+#include "kitti_demo_callback.inc"
+};
+} // namespace continuous_clustering
+#endif
+
 using namespace continuous_clustering;
 
 struct drv
@@ -38,7 +87,36 @@ struct drv
 
     std::vector<RawPoints::Ptr> prepared;
     std::vector<Eigen::Isometry3d> prepared_poses;
+
+    bool record_clouds{false};
+    std::vector<drv_cloud_t> clouds;
+    std::vector<uint8_t> cloud_data;
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    bool kitti{false};
+    KittiDemoCallback kitti_cb;
+#endif
 };
+
+#ifdef DRV_WITH_CALLER_EXCERPTS
+static void keepCloud(drv* d, const sensor_msgs::PointCloud2Ptr& msg, int kind, int64_t from, int64_t to)
+{
+    if (!msg)
+        return;
+    drv_cloud_t c;
+    std::memset(&c, 0, sizeof(c));
+    c.from_gcol = from;
+    c.to_gcol = to;
+    c.kind = kind;
+    c.width = msg->width;
+    c.height = msg->height;
+    c.point_step = msg->point_step;
+    c.stamp_ns = msg->header.stamp.toNSec();
+    c.data_offset = static_cast<int64_t>(d->cloud_data.size());
+    c.data_size = static_cast<int64_t>(msg->data.size());
+    d->cloud_data.insert(d->cloud_data.end(), msg->data.begin(), msg->data.end());
+    d->clouds.push_back(c);
+}
+#endif
 
 static Eigen::Isometry3d poseFrom12(const double* m)
 {
@@ -84,6 +162,17 @@ static void onColumns(drv* d, int64_t from, int64_t to, bool ground_only)
     d->num_column_callbacks++;
     if (!ground_only)
         d->last_clustered_column = to;
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    if (d->record_clouds || d->kitti)
+    {
+        std::lock_guard<std::mutex> lock(d->mutex);
+        if (d->record_clouds) // continuous_clustering_node.cpp:171-178
+            keepCloud(d, columnToPointCloud(d->cc, from, to, "odom", ground_only ? GROUND_POINT_SEGMENTATION : CONTINUOUS_CLUSTERING),
+                      ground_only ? 0 : 1, from, to);
+        if (d->kitti && !ground_only) // kitti_demo.cpp:297-306
+            d->kitti_cb.addColumnAndEvaluateFrameIfCompleted(d->cc, from, to);
+    }
+#endif
     if (d->record == DRV_RECORD_NONE)
         return;
     std::lock_guard<std::mutex> lock(d->mutex);
@@ -111,6 +200,13 @@ static void onColumns(drv* d, int64_t from, int64_t to, bool ground_only)
 
 static void onCluster(drv* d, const std::vector<Point>& points, uint64_t stamp)
 {
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    if (d->record_clouds) // continuous_clustering_node.cpp:166-169
+    {
+        std::lock_guard<std::mutex> lock(d->mutex);
+        keepCloud(d, clusterToPointCloud(points, d->cc.num_rows_, stamp, "odom"), 2, -1, -1);
+    }
+#endif
     if (d->record == DRV_RECORD_NONE)
         return;
     std::lock_guard<std::mutex> lock(d->mutex);
@@ -401,6 +497,84 @@ void drv_clear_records(drv_t* d)
     d->cluster_cells.clear();
     d->clusters.clear();
     d->cluster_points.clear();
+    d->clouds.clear();
+    d->cloud_data.clear();
+}
+
+int drv_has_caller_excerpts(void)
+{
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+void drv_set_cloud_record(drv_t* d, int on)
+{
+    d->record_clouds = on != 0;
+}
+
+int64_t drv_num_clouds(drv_t* d)
+{
+    return static_cast<int64_t>(d->clouds.size());
+}
+
+int64_t drv_cloud_bytes(drv_t* d)
+{
+    return static_cast<int64_t>(d->cloud_data.size());
+}
+
+void drv_get_clouds(drv_t* d, drv_cloud_t* clouds, uint8_t* data)
+{
+    std::memcpy(clouds, d->clouds.data(), d->clouds.size() * sizeof(drv_cloud_t));
+    std::memcpy(data, d->cloud_data.data(), d->cloud_data.size());
+}
+
+void drv_kitti_begin(drv_t* d, int sequence, int n_frames, const int32_t* points_per_frame)
+{
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    d->kitti = true;
+    d->kitti_cb = KittiDemoCallback();
+    d->kitti_cb.current_sequence_index = sequence; // kitti_demo.cpp:316-317
+    d->kitti_cb.previous_frame_index = 0;
+    for (int f = 0; f < n_frames; f++) // kitti_demo.cpp:361-365
+        d->kitti_cb.map_frame_to_point_cloud.insert(
+            {{static_cast<uint16_t>(sequence), static_cast<uint16_t>(f)},
+             std::vector<KittiSegmentationEvaluationPoint>(static_cast<size_t>(points_per_frame[f]))});
+#else
+    (void)d, (void)sequence, (void)n_frames, (void)points_per_frame;
+#endif
+}
+
+int64_t drv_kitti_get(drv_t* d, int frame, uint8_t* flags, uint32_t* detection_label)
+{
+#ifdef DRV_WITH_CALLER_EXCERPTS
+    // a frame the callback has not closed yet is still in the map (kitti_demo evaluates the last frame at the end)
+    const std::vector<KittiSegmentationEvaluationPoint>* v = nullptr;
+    auto e = d->kitti_cb.evaluated.find(frame);
+    if (e != d->kitti_cb.evaluated.end())
+        v = &e->second;
+    else
+    {
+        auto it = d->kitti_cb.map_frame_to_point_cloud.find(
+            {static_cast<uint16_t>(d->kitti_cb.current_sequence_index), static_cast<uint16_t>(frame)});
+        if (it != d->kitti_cb.map_frame_to_point_cloud.end())
+            v = &it->second;
+    }
+    if (!v)
+        return -1;
+    if (flags && detection_label)
+        for (size_t i = 0; i < v->size(); i++)
+        {
+            flags[i] = ((*v)[i].has_corresponding_point_in_detection_point_cloud ? 1 : 0) | ((*v)[i].is_ground_point ? 2 : 0);
+            detection_label[i] = (*v)[i].detection_label;
+        }
+    return static_cast<int64_t>(v->size());
+#else
+    (void)d, (void)frame, (void)flags, (void)detection_label;
+    return -1;
+#endif
 }
 
 } // extern "C"

@@ -106,6 +106,31 @@ DRV_API int64_t drv_num_cluster_points(drv_t* d);
 DRV_API void drv_get_clusters(drv_t* d, drv_cluster_t* clusters, drv_cluster_point_t* points);
 DRV_API void drv_clear_records(drv_t* d);
 
+/* ---- the reference's own CALLER code run against the object (only in libraries built with
+ * -DDRV_WITH_CALLER_EXCERPTS, i.e. where /root/reference was present at build time: oracle/_ref/*.so).
+ * The excerpts (oracle/extract_caller_excerpts.py) are ros_utils.cpp's columnToPointCloud / clusterToPointCloud /
+ * addPointToMessage and kitti_demo.cpp's column callback body, compiled unmodified. ---- */
+typedef struct drv_cloud
+{
+    int64_t from_gcol, to_gcol; /* column range of a column cloud; cluster clouds: -1, -1 */
+    int32_t kind;               /* 0 ground-stage columns, 1 clustered columns, 2 finished cluster */
+    uint32_t width, height, point_step;
+    uint64_t stamp_ns;          /* msg->header.stamp */
+    int64_t data_offset, data_size; /* into the byte blob returned by drv_get_clouds */
+} drv_cloud_t;
+
+DRV_API int drv_has_caller_excerpts(void);
+/* on != 0: every column / cluster callback also builds the PointCloud2 the ROS node would publish
+ * (continuous_clustering_node.cpp:166-178) and keeps its bytes */
+DRV_API void drv_set_cloud_record(drv_t* d, int on);
+DRV_API int64_t drv_num_clouds(drv_t* d);
+DRV_API int64_t drv_cloud_bytes(drv_t* d);
+DRV_API void drv_get_clouds(drv_t* d, drv_cloud_t* clouds, uint8_t* data);
+/* kitti_demo.cpp:173-224 run from the clustered-column callback: frames of `points_per_frame[f]` points each
+ * (guid = seq << 48 | frame << 32 | index); results per point: bit 0 has_corresponding_point, bit 1 is_ground_point */
+DRV_API void drv_kitti_begin(drv_t* d, int sequence, int n_frames, const int32_t* points_per_frame);
+DRV_API int64_t drv_kitti_get(drv_t* d, int frame, uint8_t* flags, uint32_t* detection_label);
+
 #ifdef __cplusplus
 }
 #endif

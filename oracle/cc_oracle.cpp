@@ -23,7 +23,7 @@
 //
 // PINNING: the reference ships no tests or golden vectors. This restatement is pinned
 // against the reference's OWN sources compiled into oracle/_ref/libcc_ref.so (oracle/Makefile target `ref`)
-// by tests/test_oracle_vs_reference.py, and against the fixtures in tests/golden generated from that build.
+// by tests/test_oracle.py, and against the fixtures in tests/golden generated from that build.
 //
 // Nothing under continuous_clustering_b200/ may include, link or load this file. It exports the recording
 // driver API of cc_driver.h so tests can swap it for the reference build or the facade.
@@ -1073,6 +1073,27 @@ void drv_clear_records(drv_t* d)
     d->cluster_cells.clear();
     d->clusters.clear();
     d->cluster_points.clear();
+}
+
+// the caller excerpts need real `Point` objects; the restatement works on flat arrays and has none
+int drv_has_caller_excerpts(void)
+{
+    return 0;
+}
+void drv_set_cloud_record(drv_t*, int) {}
+int64_t drv_num_clouds(drv_t*)
+{
+    return 0;
+}
+int64_t drv_cloud_bytes(drv_t*)
+{
+    return 0;
+}
+void drv_get_clouds(drv_t*, drv_cloud_t*, uint8_t*) {}
+void drv_kitti_begin(drv_t*, int, int, const int32_t*) {}
+int64_t drv_kitti_get(drv_t*, int, uint8_t*, uint32_t*)
+{
+    return -1;
 }
 
 } // extern "C"
