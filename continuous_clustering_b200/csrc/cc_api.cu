@@ -46,16 +46,13 @@ struct cc_handle
     int debug_flag_period{0};
     unsigned long long* d_trace{nullptr}; // device-side timeline buffer (cc_debug_trace)
     bool trace_on{false};
-    int tune{0}; // profiling aid: CC_B200_TUNE environment variable (bit 0: cooperative probe walk without masks;
-                 // bit 1: experimental, tail of the finish pass inside k_fin_label)
+    int tune{0}; // profiling aid: CC_B200_TUNE environment variable (bit 0: cooperative probe walk without masks)
     bool label_prefetch{false};
     const uchar4* cur_labels{nullptr}; // labels of the last finished push (pinned slot buffer)
     int cur_label_cols{0};
     int used_exact_flag{0};
     size_t probe_smem{0}; // [block-scan scratch][running maxima of up to maxcols columns]
     size_t ground_smem_set{0};
-    size_t label_smem_set{0};
-    int occ_label{8};
     size_t lite_smem_set{0};
     size_t fin_smem_set{0};
     CcDevPtrs d{};
@@ -371,7 +368,7 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
         h->sm_count = prop.multiProcessorCount;
     {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 64, CC_PROBE_PIPE * CC_WARP * sizeof(float4)) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_heavy, 64, cc_heavy_smem_bytes(64, 2)) == cudaSuccess && nb > 0)
             h->occ_probe_heavy = nb;
     }
 #endif
@@ -810,35 +807,8 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
         h->fin_smem_set = fin_smem;
     }
 #endif
-    const int defer = (h->tune & 2) ? 1 : 0; // experimental: tail of the finish pass beside the labelling
-    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap, defer);
-    if (!defer)
-    {
-        CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard, 0, 0, 0, static_cast<CcDevState*>(nullptr));
-        return;
-    }
-#ifdef CC_EMU
-    const int label_threads = 1;
-#else
-    const int label_threads = 256;
-#endif
-    size_t label_smem = label_threads * sizeof(long long) + static_cast<size_t>(h->d.cap_G) * sizeof(int);
-    if (label_smem > 200 * 1024)
-        label_smem = 200 * 1024;
-    int label_blocks = h->sm_count * 8;
-#ifndef CC_EMU
-    if (label_smem != h->label_smem_set)
-    {
-        if (label_smem > 48 * 1024)
-            cudaFuncSetAttribute(k_fin_label, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(label_smem));
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fin_label, label_threads, label_smem) == cudaSuccess && nb > 0)
-            h->occ_label = nb;
-        h->label_smem_set = label_smem;
-    }
-    label_blocks = h->sm_count * std::min(8, h->occ_label);
-#endif
-    CC_RUN(h, k_fin_label, label_blocks, label_threads, label_smem, cfg, h->d, seq, guard, 1, last, static_cast<int>(label_smem), snap);
+    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
+    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)
@@ -998,7 +968,7 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
         // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
         // (every CTA first computes the running maximum of the column minima in shared memory)
         CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, h->probe_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
-        CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 64, CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d,
+        CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 64, cc_heavy_smem_bytes(64, 2), cfg, h->d,
                h->d_s_parent, h->d_s_links, h->tune);
         if (sl.spec)
         {

@@ -95,15 +95,30 @@ enum CcKernelId
     CC_KID_COUNT
 };
 #define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D"
+// Every stage is a device function over a VIRTUAL grid: (bid, nb) is (blockIdx.x, gridDim.x) when the stage runs as its
+// own kernel, and (rank of the CTA in its cluster, CTAs per cluster) when the stages of a whole push run inside the
+// single fused kernel k_push_fused with cluster barriers between them. blockDim.x / threadIdx.x are always the CTA's own.
+struct CcGrid
+{
+    int bid, nb;
+};
+CC_DEV CcGrid cc_grid()
+{
+    CcGrid g;
+    g.bid = static_cast<int>(blockIdx.x);
+    g.nb = static_cast<int>(gridDim.x);
+    return g;
+}
+
 struct CcTraceScope
 {
     unsigned long long* slot;
-    __device__ __forceinline__ CcTraceScope(unsigned long long* trace, int kid) : slot(nullptr)
+    __device__ __forceinline__ CcTraceScope(unsigned long long* trace, int kid, int bid) : slot(nullptr)
     {
 #ifndef CC_EMU
         if (trace && threadIdx.x == 0)
         {
-            const unsigned int b = blockIdx.x < CC_TRACE_BLOCKS ? blockIdx.x : CC_TRACE_BLOCKS - 1;
+            const unsigned int b = bid < CC_TRACE_BLOCKS ? bid : CC_TRACE_BLOCKS - 1;
             slot = trace + (static_cast<size_t>(kid) * CC_TRACE_BLOCKS + b) * 2;
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -317,12 +332,11 @@ CC_DEV int cc_wrapdiff(int d, int N) // representative of d (mod N) in (-N/2, N/
     return d;
 }
 
-CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to);
+CC_DEV void d_clear(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to);
 
-__global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+CC_DEV void d_prep(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_prep);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_prep, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -330,14 +344,14 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
     // column a push reports through a finished-column event can still be read by the caller after the push has been
     // waited for, even while the next push is already in flight (the reference's callbacks read range_image_ before
     // clearColumns runs, cpp:1087-1091). Pure stores: they drain while the firings below are being prepared.
-    d_clear(cfg, p, p.st->clear2_from, p.st->clear2_to);
+    d_clear(g, cfg, p, p.st->clear2_from, p.st->clear2_to);
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
     // (anchor = column-in-rotation of its first valid row; rearmost / foremost column relative to the anchor)
     const int R = cfg.R;
     const float pi_f = static_cast<float>(M_PI);
     const int lane = threadIdx.x % CC_WARP;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) / CC_WARP;
-    const int nw = (gridDim.x * blockDim.x + CC_WARP - 1) / CC_WARP;
+    const int gwarp = (g.bid * blockDim.x + threadIdx.x) / CC_WARP;
+    const int nw = (g.nb * blockDim.x + CC_WARP - 1) / CC_WARP;
     for (int k = gwarp; k < n_firings; k += nw)
     {
         const double* pose = p.poses + 12 * k;
@@ -410,6 +424,11 @@ __global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         }
     }
 }
+__global__ void k_prep(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+{
+    CC_PDL_ENTER();
+    d_prep(cc_grid(), cfg, p, n_firings);
+}
 
 // =====================================================================================================
 // K1-lite  the insertion scan when every firing of (a prefix of) the push is REGULAR (see k_insert_scan), done
@@ -462,11 +481,10 @@ struct CcOpMaxPair
 #define CC_LITE_PER 8 /* firings per thread of k_scan_lite: 8192 firings per push with 1024 threads */
 #endif
 
-__global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
+CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_lite);
-    if (blockIdx.x != 0 || p.st->halted)
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_lite, g.bid);
+    if (g.bid != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
     // every thread owns a few consecutive firings; the cross-thread parts are block scans
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
         if (a + u < b)
             fs[u] = p.lite_sum[a + u];
     }
-    CcTraceScope cc_tr_l1(p.trace, CC_KID_lite_p1);
+    CcTraceScope cc_tr_l1(p.trace, CC_KID_lite_p1, g.bid);
     // pass 1: anchor columns relative to the thread's first valid firing
     CcAnchorSeg mine;
     mine.has = 0;
@@ -543,10 +561,10 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     CcOpAnchorSeg op;
     op.N = N;
     cc_tr_l1.stop();
-    CcTraceScope cc_tr_s1(p.trace, CC_KID_lite_scan1);
+    CcTraceScope cc_tr_s1(p.trace, CC_KID_lite_scan1, g.bid);
     const CcAnchorSeg before = cc_block_exclusive_scan(sm_seg, mine, ident, op);
     cc_tr_s1.stop();
-    CcTraceScope cc_tr_l2(p.trace, CC_KID_lite_p2);
+    CcTraceScope cc_tr_l2(p.trace, CC_KID_lite_p2, g.bid);
     if (t == T - 1)
     {
         const CcAnchorSeg all = op(before, mine);
@@ -589,10 +607,10 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
     seed.p = 0;   // rearmost column at the start of the push (relative: 0)
     seed.f = Fm0; // foremost column at the start of the push
     cc_tr_l2.stop();
-    CcTraceScope cc_tr_s2(p.trace, CC_KID_lite_scan2);
+    CcTraceScope cc_tr_s2(p.trace, CC_KID_lite_scan2, g.bid);
     CcMaxPair pre = cc_block_exclusive_scan(sm_max, run, seed, CcOpMaxPair());
     cc_tr_s2.stop();
-    CcTraceScope cc_tr_l3(p.trace, CC_KID_lite_p3);
+    CcTraceScope cc_tr_l3(p.trace, CC_KID_lite_p3, g.bid);
     pre = CcOpMaxPair()(pre, seed);
     // pass 3: rearmost / foremost so far before every firing; unwrap margins
 #pragma unroll
@@ -630,36 +648,42 @@ __global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, i
         st->scan_lite_base = base;
     }
 }
+__global__ void __launch_bounds__(1024) k_scan_lite(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    CC_PDL_ENTER();
+    d_scan_lite(cc_grid(), cfg, p, n);
+}
 
 struct CcOpLastSetI32
 {
     CC_DEV int operator()(int a, int b) const { return b == (-0x7fffffff - 1) ? a : b; }
 };
 
-__global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
+CC_DEV void d_scan_check(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_check);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_check, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     CC_SMEM(smem);
     int* sm = reinterpret_cast<int*>(smem);
     const int R = cfg.R, N = cfg.N;
-    const int row = blockIdx.x;
-    if (row >= R)
-        return;
     const CcDevState* st = p.st;
-    const int kmax = st->scan_kbad < n ? st->scan_kbad : n;
+    const int kmax0 = st->scan_kbad < n ? st->scan_kbad : n; // read before any row of this grid lowers it
     const int NOT_SET = -0x7fffffff - 1;
     const int T = blockDim.x, t = threadIdx.x;
+    __shared__ int sh_front;
+  for (int row = g.bid; row < R; row += g.nb) // one CTA per row (the fused kernel has fewer CTAs than rows)
+  {
+    const int kmax = kmax0;
     const int seg = (kmax + T - 1) / T;
     const int a = t * seg < kmax ? t * seg : kmax, b = (a + seg < kmax) ? a + seg : kmax;
     int first = NOT_SET, firstk = kmax, last = NOT_SET, kbad = n, gmax = NOT_SET;
-    __shared__ int sh_front;
+    __syncthreads(); // the previous row's sh_front has been read
     if (t == 0)
         sh_front = NOT_SET;
-    CcTraceScope cc_tr_cl(p.trace, CC_KID_check_loop);
+    __syncthreads();
+    CcTraceScope cc_tr_cl(p.trace, CC_KID_check_loop, g.bid);
     for (int kb = a; kb < b; kb += 8) // loads of 8 firings issued together
     {
         int cw[8], U[8], an[8], P[8];
@@ -697,7 +721,7 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
         }
     }
     cc_tr_cl.stop();
-    CcTraceScope cc_tr_cs(p.trace, CC_KID_check_scan);
+    CcTraceScope cc_tr_cs(p.trace, CC_KID_check_scan, g.bid);
     int prev = cc_block_exclusive_scan(sm, last, NOT_SET, CcOpLastSetI32());
     cc_tr_cs.stop();
     if (prev == NOT_SET)
@@ -716,6 +740,12 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
     __syncthreads();
     if (t == 0)
         p.lite_rowfront[row] = sh_front;
+  }
+}
+__global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
+{
+    CC_PDL_ENTER();
+    d_scan_check(cc_grid(), cfg, p, n);
 }
 
 // =====================================================================================================
@@ -742,11 +772,10 @@ struct CcScanState // uniform across the CTA, kept in registers by every thread
     int reset_required, error;
 };
 
-__global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
+CC_DEV void d_insert_scan(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_insert_scan);
-    if (blockIdx.x != 0 || p.st->halted)
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_insert_scan, g.bid);
+    if (g.bid != 0 || p.st->halted)
         return;
     CC_SMEM(smem);
     const int R = cfg.R, N = cfg.N, W = CC_K1_WINDOW, ringcols = cfg.ringcols;
@@ -1418,20 +1447,24 @@ __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p,
         st->n_cluster_points = 0;
     }
 }
+__global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
+{
+    CC_PDL_ENTER();
+    d_insert_scan(cc_grid(), cfg, p, n_firings, C, after_lite);
+}
 
 // =====================================================================================================
 // K1b scatter the staged fields of every stored point into the ring (cpp:223-237). Parallel; a point whose
 //     cell was re-written by a closer return of a later firing (cpp:207) sees a different distance and skips.
 // =====================================================================================================
-__global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+CC_DEV void d_scatter(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_scatter);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scatter, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    for (int idx = g.bid * blockDim.x + threadIdx.x; idx < total; idx += g.nb * blockDim.x)
     {
         const int k = idx / cfg.R, row = idx - k * cfg.R;
         int grel, rot;
@@ -1496,6 +1529,11 @@ __global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
         p.firing_index[cell] = raw->firing_index;
     }
 }
+__global__ void k_scatter(CcDevCfg cfg, CcDevPtrs p, int n_firings)
+{
+    CC_PDL_ENTER();
+    d_scatter(cc_grid(), cfg, p, n_firings);
+}
 
 // =====================================================================================================
 // K2a  sc_inclination_angles_between_lasers_ (cpp:353-357): per row, the last non-NaN inclination difference
@@ -1516,13 +1554,8 @@ CC_DEV float cc_ldcg_f32(const float* q)
 #endif
 }
 
-__global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
+CC_DEV void d_gap_main(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, const CcHead& hd)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_gap_scan);
-    const CcHead hd = cc_head(p.st);
-    if (hd.halted)
-        return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int R = cfg.R;
     const int ncols = hd.ncols;
     const long long colbase = hd.colbase;
@@ -1531,8 +1564,8 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
     const float nanv = cc_nanf();
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int items = nchunks * R; // (chunk, row), rows fastest: a warp reads consecutive rows of one column
-    CcTraceScope cc_tr_gmain(p.trace, CC_KID_gap_main);
-    for (int it = blockIdx.x * T + t; it < items; it += gridDim.x * T)
+    CcTraceScope cc_tr_gmain(p.trace, CC_KID_gap_main, g.bid);
+    for (int it = g.bid * T + t; it < items; it += g.nb * T)
     {
         const int chunk = it / R, row = it - chunk * R;
         const int c0 = chunk * CC_GAP_CHUNK;
@@ -1564,29 +1597,23 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
         }
         p.gap_chunk_last[it] = last;
     }
+}
 
-    cc_tr_gmain.stop();
-    __shared__ int sh_last;
-    __syncthreads();
-    if (t == 0)
-    {
-        __threadfence();
-        const int ticket = atomicAdd(&p.st->ticket_gap, 1);
-        sh_last = ticket == static_cast<int>(gridDim.x) - 1;
-    }
-    __syncthreads();
-    if (!sh_last)
-        return;
-    __threadfence();
-    if (t == 0)
-        p.st->ticket_gap = 0;
-    CcTraceScope cc_tr_gtail(p.trace, CC_KID_gap_tail);
+// single CTA: chains the chunks per row, seeded with the value carried from earlier pushes
+CC_DEV void d_gap_tail(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, const CcHead& hd)
+{
+    const int R = cfg.R;
+    const int ncols = hd.ncols;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int nchunks = (ncols + CC_GAP_CHUNK - 1) / CC_GAP_CHUNK;
+    const float nanv = cc_nanf();
+    CcTraceScope cc_tr_gtail(p.trace, CC_KID_gap_tail, g.bid);
     // chain the chunks: tiles of chunks are staged in shared memory with independent coalesced loads (one memory
     // round trip per tile); every row is then walked by `parts` threads, each over a contiguous range of chunks
     __shared__ float sh_tile[8192];
-    __shared__ float sh_part[256];
+    __shared__ float sh_part[1024];
     const int tile_chunks = 8192 / R;
-    const int parts = T / R > 0 ? T / R : 1;
+    const int parts = T / R > 0 ? (T / R < 1024 / R ? T / R : 1024 / R) : 1;
     for (int cb = 0; cb < nchunks; cb += tile_chunks)
     {
         const int nc = (nchunks - cb) < tile_chunks ? (nchunks - cb) : tile_chunks;
@@ -1649,6 +1676,33 @@ __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
     }
 }
 
+__global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
+{
+    CC_PDL_ENTER();
+    const CcGrid g = cc_grid();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_gap_scan, g.bid);
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    d_gap_main(g, cfg, p, hd);
+    // the block that finishes last chains the chunks
+    __shared__ int sh_last;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        const int ticket = atomicAdd(&p.st->ticket_gap, 1);
+        sh_last = ticket == g.nb - 1;
+    }
+    __syncthreads();
+    if (!sh_last)
+        return;
+    __threadfence();
+    if (threadIdx.x == 0)
+        p.st->ticket_gap = 0;
+    d_gap_tail(g, cfg, p, hd);
+}
+
 // =====================================================================================================
 // K2b  ground-point segmentation of one column per warp (cpp:294-624). Lanes stage the column into shared
 //      memory (classification of every cell, projection into the azimuth plane, ego-box test in double), lane 0
@@ -1681,10 +1735,9 @@ CC_DEV double cc_ldcg_f64(const double* q)
 #endif
 }
 
-__global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_ground);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_ground, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -1712,13 +1765,13 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
     const int nwords = (R + 31) / 32;
     const float hsg = cfg.height_sensor_to_ground;
 
-    CcTraceScope cc_tr_main_obj(p.trace, CC_KID_ground_main);
-    for (int ci = blockIdx.x * warps_per_block + wib; ci < ncols; ci += gridDim.x * warps_per_block)
+    CcTraceScope cc_tr_main_obj(p.trace, CC_KID_ground_main, g.bid);
+    for (int ci = g.bid * warps_per_block + wib; ci < ncols; ci += g.nb * warps_per_block)
     {
         const long long gcol = colbase + ci;
         const int local = cc_local_col(gcol, cfg.ringcols);
         const size_t base = static_cast<size_t>(local) * R;
-        CcTraceScope cc_tr_pose(p.trace, CC_KID_g_pose);
+        CcTraceScope cc_tr_pose(p.trace, CC_KID_g_pose, g.bid);
         // ---- A0: everything the column needs from global memory, issued before anything waits: the firing that
         //      completed the column (its pose is one more dependent round trip) and the cells ----
         const int trig = p.col_trigger[ci];
@@ -1761,7 +1814,7 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
 
         __syncwarp();
         cc_tr_pose.stop();
-        CcTraceScope cc_tr_A(p.trace, CC_KID_g_A);
+        CcTraceScope cc_tr_A(p.trace, CC_KID_g_A, g.bid);
         // ---- A: classify every cell, project it into the azimuth plane, bitmap of the regular rows ----
         for (int row0 = 0; row0 < R; row0 += CC_WARP)
         {
@@ -1808,7 +1861,7 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
         __syncwarp();
 
         cc_tr_A.stop();
-        CcTraceScope cc_tr_B(p.trace, CC_KID_g_B);
+        CcTraceScope cc_tr_B(p.trace, CC_KID_g_B, g.bid);
         // ---- B: everything of the label rules that does not depend on carried state, for all rows at once: the
         //      previous regular point (fog / ego / empty cells never become "previous", cpp:360-404), the slope to it,
         //      the compacted bottom-to-top sequence; and the inclination supplement of runs of empty cells ----
@@ -1873,7 +1926,7 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
         __syncwarp();
 
         cc_tr_B.stop();
-        CcTraceScope cc_tr_C(p.trace, CC_KID_g_C);
+        CcTraceScope cc_tr_C(p.trace, CC_KID_g_C, g.bid);
         // ---- C: the sequential label state machine (cpp:305-565) over the regular points only ----
         // C1 (lane 0): up to the first obstacle a flat point is GREEN whatever came before, so the walk jumps from one
         //     non-flat point to the next with bit operations on the flat / last-ground-candidate masks
@@ -2066,7 +2119,7 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
         __syncwarp();
 
         cc_tr_C.stop();
-        CcTraceScope cc_tr_D(p.trace, CC_KID_g_D);
+        CcTraceScope cc_tr_D(p.trace, CC_KID_g_D, g.bid);
         // ---- D: is_ignored (cpp:567-616) + association view ----
         double min_az = 1.7976931348623157e308;
         for (int row = lane; row < R; row += CC_WARP)
@@ -2148,6 +2201,11 @@ __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, un
     }
 
 }
+__global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+{
+    CC_PDL_ENTER();
+    d_ground(cc_grid(), cfg, p, s_parent);
+}
 
 // Running maximum of the columns' minimum azimuth (the value every finish pass compares against, cpp:884-885), continued
 // across pushes: every CTA of the association probe computes it for itself in shared memory (one coalesced read of the
@@ -2188,7 +2246,7 @@ CC_DEV void d_runmax_block(const CcDevPtrs& p, int ncols, double* part, double* 
             p.col_runmax[i] = sh[i];
 }
 
-__device__ void d_snapshot(CcDevPtrs p, int spec);
+CC_DEV void d_snapshot(const CcGrid g, CcDevPtrs p, int spec);
 
 // =====================================================================================================
 // K3a  association probe (cpp:698-835): every non-ignored cell of the new columns walks its field of view and
@@ -2383,29 +2441,28 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
 // walked by ONE thread each, literally as the reference does, with a budget of CC_PROBE_BUDGET cells. A point that
 // exceeds the budget (sparse surroundings: the walk covers up to (2 * max_steps_in_row + 1) * max_steps_in_column
 // cells) or finds more link candidates than it has slots is redone from scratch by a whole warp (k_probe_heavy).
-__global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int do_snapshot)
+CC_DEV void d_probe(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int do_snapshot)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts); the probe itself
-        d_snapshot(p, 0); // modifies no persistent state
+        d_snapshot(g, p, 0); // modifies no persistent state
     const int R = cfg.R;
     const int ncols = hd.ncols;
     const long long colbase = hd.colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int lane = threadIdx.x % CC_WARP;
     const int npoints = p.st->n_probe < p.maxcols * R ? p.st->n_probe : p.maxcols * R;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) / CC_WARP;
-    const int nwarps = (gridDim.x * blockDim.x + CC_WARP - 1) / CC_WARP;
+    const int gwarp = (g.bid * blockDim.x + threadIdx.x) / CC_WARP;
+    const int nwarps = (g.nb * blockDim.x + CC_WARP - 1) / CC_WARP;
     const int ngroups = (npoints + CC_PROBE_PPW - 1) / CC_PROBE_PPW;
     CC_SMEM(smem);
     double* rm_part = reinterpret_cast<double*>(smem);
     double* rm = rm_part + 32; // running maximum of the column minima, columns of this push
     const int ncols_rm = ncols < p.maxcols ? ncols : p.maxcols;
-    d_runmax_block(p, ncols_rm, rm_part, rm, blockIdx.x == 0);
+    d_runmax_block(p, ncols_rm, rm_part, rm, g.bid == 0);
     const double rm_carry = p.st->runmax_carry;
     for (int grp = gwarp; grp < ngroups; grp += nwarps)
     {
@@ -2528,6 +2585,11 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
         }
     }
 }
+__global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int do_snapshot)
+{
+    CC_PDL_ENTER();
+    d_probe(cc_grid(), cfg, p, s_parent, s_links, do_snapshot);
+}
 
 // K3a': the points the thread-per-point path gave up on, one CTA (two warps) per point. When a vertical run fits one warp step
 // (max_steps_in_column < 32) and the window has at most 64 runs:
@@ -2539,10 +2601,31 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
 // A point without neighbours -- the worst case, it walks its whole window -- costs one memory round trip and a few
 // hundred instructions instead of ~100 dependent instructions per run. Other configurations: warp 0 walks alone
 // (d_probe_coop).
-__global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
+// The warps of a CTA work in TEAMS of `team_warps` warps, one point per team at a time: the whole CTA (2 warps) when
+// the stage runs as its own kernel, pairs of warps of a wide CTA inside the fused kernel.
+static inline __host__ __device__ size_t cc_heavy_smem_bytes(int block_threads, int team_warps)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy);
+    const int nwarps = (block_threads + CC_WARP - 1) / CC_WARP;
+    const int teams = nwarps / (team_warps > 0 ? team_warps : 1) > 0 ? nwarps / (team_warps > 0 ? team_warps : 1) : 1;
+    return static_cast<size_t>(teams) * (CC_PROBE_PIPE * CC_WARP * sizeof(float4) + 128 * sizeof(unsigned int));
+}
+CC_DEV void cc_team_sync(int team_warps, int nwarps, int team)
+{
+#ifndef CC_EMU
+    if (team_warps >= nwarps)
+        __syncthreads();
+    else if (team_warps == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(team_warps * CC_WARP) : "memory");
+#else
+    (void)team_warps, (void)nwarps, (void)team;
+#endif
+}
+
+CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune, int team_warps)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -2550,15 +2633,21 @@ __global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs 
     const int ncols = hd.ncols;
     const long long colbase = hd.colbase;
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
-    const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
-    const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    const int lane = threadIdx.x % CC_WARP;
+    const int cta_warps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    const int nwarps = team_warps < cta_warps ? team_warps : cta_warps; // warps of my team
+    const int teams_per_cta = cta_warps / nwarps;
+    const int team = (threadIdx.x / CC_WARP) / nwarps, warp = (threadIdx.x / CC_WARP) % nwarps;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int nheavy = p.st->n_heavy < p.maxcols * R ? p.st->n_heavy : p.maxcols * R;
     CC_SMEM(smem);
-    float4* ring = reinterpret_cast<float4*>(smem);
-    __shared__ unsigned int brk_m[64], hit_m[64];
+    float4* ring = reinterpret_cast<float4*>(smem) + static_cast<size_t>(team) * CC_PROBE_PIPE * CC_WARP;
+    unsigned int* brk_m = reinterpret_cast<unsigned int*>(reinterpret_cast<float4*>(smem) + static_cast<size_t>(teams_per_cta) * CC_PROBE_PIPE * CC_WARP) + team * 128;
+    unsigned int* hit_m = brk_m + 64;
     const bool masks_ok = CC_WARP == 32 && cfg.max_steps_col < 32 && 2 * msr + 1 <= 64 && !(tune & 1);
-    for (int hi = blockIdx.x; hi < nheavy; hi += gridDim.x)
+    if (team >= teams_per_cta)
+        return; // warps beyond the last full team
+    for (int hi = g.bid * teams_per_cta + team; hi < nheavy; hi += g.nb * teams_per_cta)
     {
         const int pidx = p.heavy_list[hi];
         if (!masks_ok)
@@ -2625,7 +2714,7 @@ __global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs 
                 }
             }
         }
-        __syncthreads();
+        cc_team_sync(nwarps, cta_warps, team);
         // ---- phase 2 ----
         if (warp == 0)
         {
@@ -2768,8 +2857,13 @@ __global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs 
                 }
             }
         }
-        __syncthreads(); // the masks are rewritten for the next point
+        cc_team_sync(nwarps, cta_warps, team); // the masks are rewritten for the next point
     }
+}
+__global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
+{
+    CC_PDL_ENTER();
+    d_probe_heavy(cc_grid(), cfg, p, s_parent, s_links, tune, 2);
 }
 
 // ---- union-find over tree roots (lock-free, ECL-CC style: hook the larger index under the smaller) ----
@@ -2827,12 +2921,12 @@ CC_DEV bool cc_spec_ok(const CcDevState* st, int guard)
 //      contribution to the root (finished_at, width, tree_num_points: cpp:661-672); (3) apply tree<->tree
 //      links (cpp:675-696) to the union-find.
 // =====================================================================================================
-__device__ void d_snapshot(CcDevPtrs p, int spec)
+CC_DEV void d_snapshot(const CcGrid g, CcDevPtrs p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
     const int n = p.st->n_ulist;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int i = g.bid * blockDim.x + threadIdx.x; i < n; i += g.nb * blockDim.x)
     {
         const unsigned int r = p.ulist[i];
         p.sv_cparent[i] = p.cparent[r];
@@ -2840,7 +2934,7 @@ __device__ void d_snapshot(CcDevPtrs p, int spec)
         p.sv_tmaxcol[i] = p.tmaxcol[r];
         p.sv_tnpoints[i] = p.tnpoints[r];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (g.bid == 0 && threadIdx.x == 0)
     {
         p.st->n_ulist_saved = n;
         p.st->sv_n_clusters = p.st->n_clusters;
@@ -2851,18 +2945,18 @@ __device__ void d_snapshot(CcDevPtrs p, int spec)
 __global__ void k_snapshot(CcDevPtrs p, int guard)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_snapshot);
+    const CcGrid g = cc_grid();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_snapshot, g.bid);
     if (p.st->halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
-    d_snapshot(p, guard);
+    d_snapshot(g, p, guard);
 }
 
-__global__ void k_restore(CcDevPtrs p)
+CC_DEV void d_restore(const CcGrid g, CcDevPtrs p)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore, g.bid);
     const int n = p.st->n_ulist_saved;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int i = g.bid * blockDim.x + threadIdx.x; i < n; i += g.nb * blockDim.x)
     {
         const unsigned int r = p.ulist[i];
         p.cparent[r] = p.sv_cparent[i];
@@ -2871,21 +2965,29 @@ __global__ void k_restore(CcDevPtrs p)
         p.tnpoints[r] = p.sv_tnpoints[i];
     }
 }
-
-__global__ void k_restore_finish(CcDevPtrs p)
+__global__ void k_restore(CcDevPtrs p)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore_finish);
+    d_restore(cc_grid(), p);
+}
+
+CC_DEV void d_restore_finish(const CcGrid g, CcDevPtrs p)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_restore_finish, g.bid);
     p.st->n_ulist = p.st->n_ulist_saved;
     p.st->abort = 0;
     p.st->n_clusters = p.st->sv_n_clusters;
     p.st->n_cluster_points = p.st->sv_n_cluster_points;
 }
-
-__global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
+__global__ void k_restore_finish(CcDevPtrs p)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_copy);
+    d_restore_finish(cc_grid(), p);
+}
+
+CC_DEV void d_commit_copy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_copy, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -2899,7 +3001,7 @@ __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_p
     const int lane = threadIdx.x % CC_WARP;
     const unsigned int lt_mask = (1u << lane) - 1u;
     // warps stay converged: the new roots of a warp's cells take their places in the unfinished list with one atomic
-    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x)
+    for (int i0 = g.bid * blockDim.x + threadIdx.x - lane; i0 < total; i0 += g.nb * blockDim.x)
     {
         const int i = i0 + lane;
         bool is_root = false;
@@ -2944,6 +3046,11 @@ __global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_p
         }
     }
 }
+__global__ void k_commit_copy(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, int ci0, int ci1, int spec)
+{
+    CC_PDL_ENTER();
+    d_commit_copy(cc_grid(), cfg, p, s_parent, ci0, ci1, spec);
+}
 
 // 64-bit maximum over the lanes of `grp` (all lanes of the warp call this; lanes outside the group pass anything)
 CC_DEV unsigned long long cc_group_max_u64(bool mine, unsigned long long v)
@@ -2954,10 +3061,9 @@ CC_DEV unsigned long long cc_group_max_u64(bool mine, unsigned long long v)
     return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
-__global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+CC_DEV void d_commit_roots(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_roots);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_roots, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -2971,7 +3077,7 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
     const int lane = threadIdx.x % CC_WARP;
     // warps stay converged: the contributions of a warp's cells to one root (cells of one object in neighbouring rows
     // mostly share it) are combined before they touch the root's words in memory
-    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x)
+    for (int i0 = g.bid * blockDim.x + threadIdx.x - lane; i0 < total; i0 += g.nb * blockDim.x)
     {
         const int i = i0 + lane;
         unsigned int r = CC_NONE;
@@ -3017,12 +3123,16 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
         }
     }
 }
-
-__global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
-                               int ci0, int ci1, int spec)
+__global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_links);
+    d_commit_roots(cc_grid(), cfg, p, ci0, ci1, spec);
+}
+
+CC_DEV void d_commit_links(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
+                               int ci0, int ci1, int spec)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_links, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -3034,7 +3144,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
     {
         const long long colbase = hd.colbase;
         const int total = (ci1 - ci0 + 1) * R * CC_LINK_SLOTS;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        for (int i = g.bid * blockDim.x + threadIdx.x; i < total; i += g.nb * blockDim.x)
         {
             const int cell = i / CC_LINK_SLOTS;
             const size_t idx = static_cast<size_t>(ci0) * R + cell;
@@ -3053,7 +3163,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
     int n = p.st->n_edges;
     n = n < p.cap_edges ? n : p.cap_edges;
     const int base_local = cc_local_col(hd.colbase, cfg.ringcols);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    for (int e = g.bid * blockDim.x + threadIdx.x; e < n; e += g.nb * blockDim.x)
     {
         const unsigned int q = p.edge_a[e], o = p.edge_b[e];
         int ci = static_cast<int>(q / R) - base_local;
@@ -3066,6 +3176,12 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
             cc_uf_union(p.cparent, ra, rb);
     }
 }
+__global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
+                               int ci0, int ci1, int spec)
+{
+    CC_PDL_ENTER();
+    d_commit_links(cc_grid(), cfg, p, s_parent, s_links, ci0, ci1, spec);
+}
 
 // =====================================================================================================
 // K3c  exact column-sequential association of ONE column (cpp:773-835 verbatim semantics, including refused
@@ -3075,7 +3191,7 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
 __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_careful);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_careful, static_cast<int>(blockIdx.x));
     if (blockIdx.x != 0 || threadIdx.x != 0)
         return;
     const int R = cfg.R;
@@ -3192,7 +3308,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
 //               running maximum); anything that would need the reference's forced finish (cpp:909-919) aborts.
 //     spec = 0: c0 == c1, exact single pass including the forced finish.
 // =====================================================================================================
-__device__ void d_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec)
+CC_DEV void d_fin_init(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int ci0, int ci1, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -3205,7 +3321,7 @@ __device__ void d_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec
     long long glen = c1 - gbase + 1;
     if (glen > p.cap_G)
         glen = p.cap_G;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int tid = g.bid * blockDim.x + threadIdx.x, nt = g.nb * blockDim.x;
     for (int i = tid; i < n; i += nt)
     {
         p.u_maxfinish[i] = 0ull;
@@ -3229,12 +3345,12 @@ __device__ void d_fin_init(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int spec
     }
 }
 
-__device__ void d_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
+CC_DEV void d_fin_agg(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
     const int n = p.st->n_ulist < p.cap_ulist ? p.st->n_ulist : p.cap_ulist;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int tid = g.bid * blockDim.x + threadIdx.x, nt = g.nb * blockDim.x;
     // four list entries per thread at a time: their loads are issued together (the list is a few thousand entries long
     // and this runs in one CTA, so every dependent round trip counts once per batch instead of once per entry)
     for (int i0 = tid; i0 < n; i0 += 4 * nt)
@@ -3278,7 +3394,7 @@ __device__ void d_fin_agg(CcDevCfg cfg, CcDevPtrs p, int spec)
     }
 }
 
-__device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, const double* runmax_s)
+CC_DEV void d_fin_decide(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int guard, int exact, const double* runmax_s)
 {
     if (!cc_spec_ok(p.st, guard))
         return;
@@ -3288,7 +3404,7 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, co
     CcDevState* st = p.st;
     const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
     const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase;
-    const int tid_ = blockIdx.x * blockDim.x + threadIdx.x, nt_ = gridDim.x * blockDim.x;
+    const int tid_ = g.bid * blockDim.x + threadIdx.x, nt_ = g.nb * blockDim.x;
     // four entries per thread at a time, their loads issued together (see d_fin_agg)
     for (int i0 = tid_; i0 < n; i0 += 4 * nt_)
     {
@@ -3396,7 +3512,7 @@ __device__ void d_fin_decide(CcDevCfg cfg, CcDevPtrs p, int guard, int exact, co
     }
 }
 
-__device__ void d_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+CC_DEV void d_fin_mark(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
@@ -3404,7 +3520,7 @@ __device__ void d_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec
     const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
     const long long gbase = st->gbase;
     const unsigned long long counter = st->cluster_counter;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int tid = g.bid * blockDim.x + threadIdx.x, nt = g.nb * blockDim.x;
     const int lane = threadIdx.x % CC_WARP;
     // four entries per thread at a time (loads issued together); the entries that stay unfinished take their places in
     // the compacted list with one atomic per warp. The loop bound is uniform per warp.
@@ -3461,12 +3577,12 @@ __device__ void d_fin_mark(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec
         }
     }
 }
-__device__ void d_fin_copyback(CcDevPtrs p, int spec)
+CC_DEV void d_fin_copyback(const CcGrid g, const CcDevPtrs& p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
     const int n = *p.n_new_ulist;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int tid = g.bid * blockDim.x + threadIdx.x, nt = g.nb * blockDim.x;
     for (int i0 = tid; i0 < n; i0 += 4 * nt)
     {
         unsigned int root[4];
@@ -3487,11 +3603,11 @@ __device__ void d_fin_copyback(CcDevPtrs p, int spec)
 // that were still unfinished when the pass started (cpp:943-959), or column + 1. G[r] = last column at which
 // some tree rooted in column gbase + r is unfinished; with PG = prefix max of G, the answer for column c is the
 // first r with PG[r] >= c. Single block.
-__device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec, int smem_ints)
+CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, int smem_ints)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
-    if (blockIdx.x != 0)
+    if (g.bid != 0)
         return;
     CC_SMEM(smem);
     long long* part = reinterpret_cast<long long*>(smem);
@@ -3601,8 +3717,8 @@ __device__ void d_fin_columns(CcDevCfg cfg, CcDevPtrs p, int spec, int smem_ints
     }
 }
 
-__device__ void d_push_done(CcDevPtrs p, int guard);
-CC_DEV void d_state_snapshot(CcDevPtrs p, CcDevState* dst)
+CC_DEV void d_push_done(const CcDevPtrs& p, int guard);
+CC_DEV void d_state_snapshot(const CcDevPtrs& p, CcDevState* dst)
 {
     const int n = static_cast<int>(sizeof(CcDevState) / sizeof(int));
     const int* src = reinterpret_cast<const int*>(p.st);
@@ -3612,17 +3728,19 @@ CC_DEV void d_state_snapshot(CcDevPtrs p, CcDevState* dst)
 }
 
 // All list-sized phases of a finish pass in ONE CTA (the unfinished-tree list holds 10^2..10^4 entries: a single
-// CTA with block-wide barriers between the phases is faster than six dependent launches).
+// CTA with block-wide barriers between the phases is faster than six dependent launches). The fused kernel runs the
+// same phases over all CTAs of its cluster with cluster barriers in between.
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
-                                                  int exact, int last, int smem_bytes, CcDevState* snap, int defer_tail)
+                                                  int exact, int last, int smem_bytes, CcDevState* snap)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_all);
-    if (blockIdx.x != 0)
+    const CcGrid g = cc_grid();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_all, g.bid);
+    if (g.bid != 0)
         return;
     if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
     {
-        if (snap && !defer_tail)
+        if (snap)
             d_state_snapshot(p, snap);
         return;
     }
@@ -3632,12 +3750,11 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
     const int spare = (smem_bytes - T * 8) / 8; // doubles (or pairs of ints) that fit behind the scan scratch
     double* runmax_s = nullptr;
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_init);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_init, g.bid);
         // the running maxima of the segment's columns are staged beside the initialisation (no barrier in between:
         // the segment bounds are computed here the way d_fin_init stores them)
         if (cc_spec_ok(p.st, guard))
         {
-            const long long colbase = p.st->colbase;
             const int ci1_eff = ci1 < 0 ? p.st->ncols - 1 : ci1;
             const int nseg = ci1_eff - ci0 + 1;
             if (nseg > 0 && nseg <= spare)
@@ -3646,36 +3763,33 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
                 for (int i = threadIdx.x; i < nseg; i += T)
                     runmax_s[i] = p.col_runmax[ci0 + i];
             }
-            (void)colbase;
         }
-        d_fin_init(cfg, p, ci0, ci1, guard);
+        d_fin_init(g, cfg, p, ci0, ci1, guard);
     }
     __syncthreads();
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_agg);
-        d_fin_agg(cfg, p, guard);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_agg, g.bid);
+        d_fin_agg(g, cfg, p, guard);
     }
     __syncthreads();
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_decide);
-        d_fin_decide(cfg, p, guard, exact, runmax_s);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_decide, g.bid);
+        d_fin_decide(g, cfg, p, guard, exact, runmax_s);
     }
     __syncthreads();
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_mark);
-        d_fin_mark(cfg, p, seq, guard);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_mark, g.bid);
+        d_fin_mark(g, cfg, p, seq, guard);
     }
     __syncthreads();
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_copyback);
-        d_fin_copyback(p, guard);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_copyback, g.bid);
+        d_fin_copyback(g, p, guard);
     }
     __syncthreads();
-    if (defer_tail)
-        return; // experimental (CC_B200_TUNE bit 1): CTA 0 of k_fin_label does the rest beside the labelling
     {
-        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns);
-        d_fin_columns(cfg, p, guard, spare * 2);
+        CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns, g.bid);
+        d_fin_columns(g, cfg, p, guard, spare * 2);
     }
     __syncthreads();
     if (last && threadIdx.x == 0)
@@ -3689,36 +3803,10 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 
 // Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
 // host needs for the finished-cluster callback (cpp:1007-1028).
-__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec, int defer_tail, int last, int smem_bytes,
-                            CcDevState* snap)
+CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label, g.bid);
     const CcHead hd = cc_head(p.st);
-    if (defer_tail && blockIdx.x == 0)
-    {
-        // experimental (CC_B200_TUNE bit 1): the tail of the finish pass -- per-column first_unpublished, end-of-push
-        // bookkeeping, state copy -- runs in this CTA beside the labelling of the others instead of before it. Nothing it
-        // writes is read by the labelling (which uses the fields loaded above, gbase and seg_c1).
-        if (hd.halted)
-        {
-            if (snap)
-                d_state_snapshot(p, snap);
-            return;
-        }
-        {
-            CcTraceScope cc_tr_ph(p.trace, CC_KID_fin_columns);
-            d_fin_columns(cfg, p, spec, (smem_bytes - static_cast<int>(blockDim.x) * 8) / 4);
-        }
-        __syncthreads();
-        if (last && threadIdx.x == 0)
-            d_push_done(p, spec);
-        if (snap)
-        {
-            __syncthreads();
-            d_state_snapshot(p, snap);
-        }
-    }
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     if (!cc_head_ok(hd, spec))
@@ -3731,7 +3819,7 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
     const unsigned int lt_mask = (1u << lane) - 1u;
     // warps stay converged: the members of one cluster among a warp's cells reserve their slots in the cluster's point
     // list and update its stamp range with one atomic each
-    for (long long i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (long long i0 = g.bid * blockDim.x + threadIdx.x - lane; i0 < total; i0 += static_cast<long long>(g.nb) * blockDim.x)
     {
         const long long i = i0 + lane;
         int slot = -1;
@@ -3791,6 +3879,11 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
         }
     }
 }
+__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+{
+    CC_PDL_ENTER();
+    d_fin_label(cc_grid(), cfg, p, seq, spec);
+}
 
 // =====================================================================================================
 // K5  clearColumns (cpp:1094-1145) for the columns that left the ring in this push.
@@ -3799,7 +3892,7 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
 // every column a push reports through a finished-column event can still be read by the caller after the push has
 // been waited for, even while the next push is already in flight (the reference's callbacks read range_image_
 // before clearColumns runs, cpp:1087-1091).
-CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to)
+CC_DEV void d_clear(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, long long from, long long to)
 {
     if (from < 0)
         from = 0;
@@ -3808,7 +3901,7 @@ CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, lon
     const int R = cfg.R;
     const long long total = (to - from) * R;
     const float nanv = cc_nanf();
-    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (long long i = g.bid * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(g.nb) * blockDim.x)
     {
         const long long gcol = from + i / R;
         const int row = static_cast<int>(i % R);
@@ -3833,10 +3926,9 @@ CC_DEV void d_clear(const CcDevCfg& cfg, const CcDevPtrs& p, long long from, lon
 }
 
 // explicit range [from, to) (reset). The columns retired during normal operation are recycled by k_prep.
-__global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
+CC_DEV void d_clear_range(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_clear);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_clear, g.bid);
     CcDevState* st = p.st;
     if (mode)
     {
@@ -3845,19 +3937,24 @@ __global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to,
         from = st->clear2_from;
         to = st->clear2_to;
     }
-    d_clear(cfg, p, from, to);
+    d_clear(g, cfg, p, from, to);
+}
+__global__ void k_clear(CcDevCfg cfg, CcDevPtrs p, long long from, long long to, int mode)
+{
+    CC_PDL_ENTER();
+    d_clear_range(cc_grid(), cfg, p, from, to, mode);
 }
 
 // end of a push: remember the range of columns that left the ring (recycled at the start of the next push) and
 // advance sc_cluster_counter_ (cpp:939) by the ids handed out. guard as in cc_spec_ok.
-__device__ void d_push_done(CcDevPtrs p, int guard);
+CC_DEV void d_push_done(const CcDevPtrs& p, int guard);
 __global__ void k_push_done(CcDevPtrs p, int guard)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_push_done);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_push_done, static_cast<int>(blockIdx.x));
     d_push_done(p, guard);
 }
-__device__ void d_push_done(CcDevPtrs p, int guard)
+CC_DEV void d_push_done(const CcDevPtrs& p, int guard)
 {
     CcDevState* st = p.st;
     if (guard == 1 && (st->error != 0 || st->n_flagged != 0 || st->abort != 0))
@@ -3873,23 +3970,26 @@ __device__ void d_push_done(CcDevPtrs p, int guard)
 
 // mode 1: halt if this push completed columns (no robot transform: the reference throws); 0: halt if it has new
 // columns (finish passes only every n-th column: always column-sequential); -1: clear the flag
-__global__ void k_halt(CcDevPtrs p, int mode)
+CC_DEV void d_halt(const CcGrid g, CcDevPtrs p, int mode)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_halt);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_halt, g.bid);
     CcDevState* st = p.st;
     if (mode < 0)
         st->halted = 0;
     else if (!st->halted && (st->ncols > 0 || st->error != 0))
         st->halted = 1;
 }
+__global__ void k_halt(CcDevPtrs p, int mode)
+{
+    CC_PDL_ENTER();
+    d_halt(cc_grid(), p, mode);
+}
 
 // labels (ground label, debug label, is_ignored, intensity) of the push's new columns, packed contiguously for one
 // device->host copy next to the other results of the push (cc_set_label_prefetch)
-__global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
+CC_DEV void d_pack_labels(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_pack_labels);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_pack_labels, g.bid);
     const CcDevState* st = p.st;
     if (st->halted)
         return;
@@ -3898,19 +3998,24 @@ __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_co
     const long long colbase = st->colbase;
     const int R = cfg.R;
     const long long total = static_cast<long long>(ncols) * R;
-    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (long long i = g.bid * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(g.nb) * blockDim.x)
     {
         const long long ci = i / R;
         const int row = static_cast<int>(i - ci * R);
         out[i] = p.lab[static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row];
     }
 }
+__global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_cols)
+{
+    CC_PDL_ENTER();
+    d_pack_labels(cc_grid(), cfg, p, out, cap_cols);
+}
 
 // copy of the stream state at the end of a push (what the host reads while the next push already runs)
 __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
 {
     CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_state_snapshot);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_state_snapshot, static_cast<int>(blockIdx.x));
     d_state_snapshot(p, dst);
 }
 
