@@ -75,6 +75,11 @@ struct cc_handle
         uchar4* h_labels{nullptr}; // one of the handle's three label buffers (borrowed)
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, ready{nullptr}, done{nullptr};
         cudaEvent_t h2d{nullptr}, h2d0{nullptr}; // of the input buffer the push reads (borrowed, not owned)
+        CcHostHeader* h_hdr{nullptr};            // page-locked: completion flag + device timestamps of a fused push
+        bool fused{false}, want_fused{false};
+        unsigned int ticket{0};
+        const void* src_points{nullptr}; // fused push: where the kernel fetches the firings from (page-locked host memory)
+        const double* src_poses{nullptr};
         // the push occupying the slot
         int n{0};
         const void* in_points{nullptr}; // device pointers of the inputs
@@ -94,6 +99,9 @@ struct cc_handle
         double* h_poses{nullptr};
         cudaEvent_t h2d0{nullptr}, h2d{nullptr};
         int n{0};
+        bool fused{false}; // no copy-engine transfer was queued: the fused kernel fetches src_* itself
+        const void* src_points{nullptr};
+        const double* src_poses{nullptr};
     } inbuf[3];
     int next_in{0};
     // page-locked label buffers: two pushes in flight + the labels of the last finished push, which stay valid until
@@ -122,6 +130,13 @@ struct cc_handle
     uint64_t launches{0};
     uint64_t launches_at_push_start{0};
     int sm_count{148};
+    // fused single-launch path for short pushes (k_push_fused): one thread-block cluster, inputs read from and results
+    // written to page-locked host memory by the kernel itself
+    int fused_max{512};     // pushes of at most this many firings take it (CC_B200_FUSED_MAX; 0 = never)
+    int fused_cluster{0};   // CTAs per cluster (0: not available on this device / configuration)
+    int fused_threads{512};
+    size_t fused_smem{0};
+    unsigned int ticket{0};
     int prefetch_points{16384};
     int occ_probe{8}, occ_probe_heavy{8}; // resident CTAs per SM of the two association kernels
     // results of the last push
@@ -183,9 +198,11 @@ static void free_host_slots(cc_handle* h)
 {
     for (cc_handle::Slot& sl : h->slots)
     {
-        for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters)})
+        for (void* q : {static_cast<void*>(sl.h_state), static_cast<void*>(sl.h_first_unpub), static_cast<void*>(sl.h_clusters),
+                        static_cast<void*>(sl.h_hdr)})
             if (q)
                 cudaFreeHost(q);
+        sl.h_hdr = nullptr;
         sl.h_state = nullptr;
         sl.h_first_unpub = nullptr;
         sl.h_clusters = nullptr;
@@ -337,6 +354,8 @@ cc_status_t cc_create(int device_ordinal, int max_firings_per_push, cc_handle_t*
     cc_config_default(&h->config);
     if (const char* t = std::getenv("CC_B200_TUNE"))
         h->tune = std::atoi(t);
+    if (const char* t = std::getenv("CC_B200_FUSED_MAX"))
+        h->fused_max = std::max(0, std::atoi(t));
     if (cudaSetDevice(h->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -505,10 +524,10 @@ static int scan_threads()
 #endif
 }
 
-static int scan_smem_bytes(int R)
+static int scan_smem_bytes(int R, int C = 0, int T = 0)
 {
-    const int C = scan_chunk(R);
-    const int T = scan_threads();
+    C = C > 0 ? C : scan_chunk(R);
+    T = T > 0 ? T : scan_threads();
     const int nparts = T / R > 0 ? (T / R < C ? T / R : C) : 1;
     size_t words = static_cast<size_t>(CC_K1_WINDOW) * R + 2 * R + 4 * static_cast<size_t>(C) * R + 2 * 2 * 32 +
                    static_cast<size_t>(C) * (R + 1) + 2 * C + 2 * (C + 1) + 4 * static_cast<size_t>(R) * nparts + 8;
@@ -524,6 +543,77 @@ static int grid_for(const cc_handle* h, long long work, int block)
     if (g < 1)
         g = 1;
     return static_cast<int>(g);
+}
+
+static int fused_scan_chunk(int R)
+{
+    const int c = scan_chunk(R);
+    return c < 32 ? c : 32;
+}
+
+// The fused single-launch push (k_push_fused): dynamic shared memory = the largest need of any stage at the fused
+// block size; the largest cluster the device can co-schedule (16 CTAs needs the non-portable opt-in) is used.
+static void configure_fused(cc_handle* h)
+{
+    h->fused_cluster = 0;
+    if (h->fused_max <= 0)
+        return;
+#ifdef CC_EMU
+    h->fused_threads = 1;
+#else
+    h->fused_threads = 512;
+#endif
+    const int T = h->fused_threads, R = h->R;
+    const int warps = (T + CC_WARP - 1) / CC_WARP;
+    size_t smem = static_cast<size_t>(T) * sizeof(CcAnchorSeg);
+    smem = std::max(smem, static_cast<size_t>(scan_smem_bytes(R, fused_scan_chunk(R), T)));
+    smem = std::max(smem, warps * cc_ground_warp_bytes(R));
+    smem = std::max(smem, h->probe_smem);
+    smem = std::max(smem, cc_heavy_smem_bytes(T, 2));
+    smem = std::max(smem, static_cast<size_t>(T) * 8 + static_cast<size_t>(h->d.cap_G) * sizeof(int));
+    smem = std::max(smem, static_cast<size_t>(2 * 512 * sizeof(int)));
+    if (smem > 180 * 1024)
+        return; // (the kernel also has ~40 KB of static shared memory) such a configuration keeps the kernel chain
+    h->fused_smem = smem;
+#ifdef CC_EMU
+    h->fused_cluster = 1;
+#else
+    if (cudaFuncSetAttribute(k_push_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_push_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return;
+    }
+    int want = 16;
+    if (const char* c = std::getenv("CC_B200_FUSED_CLUSTER"))
+        want = std::max(1, std::min(16, std::atoi(c)));
+    for (int cs = want; cs >= 1; cs >>= 1)
+    {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(static_cast<unsigned>(cs), 1, 1);
+        lc.blockDim = dim3(static_cast<unsigned>(T), 1, 1);
+        lc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, k_push_fused, &lc) == cudaSuccess && nc >= 1)
+        {
+            h->fused_cluster = cs;
+            break;
+        }
+        cudaGetLastError();
+    }
+#endif
+}
+
+static bool fused_eligible(const cc_handle* h, int n)
+{
+    return h->fused_cluster > 0 && n <= h->fused_max && !h->timing;
 }
 
 // ContinuousClustering::reset cpp:11-64
@@ -644,6 +734,8 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_state), sizeof(CcDevState)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_first_unpub), mc * sizeof(long long)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_clusters), CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
+            CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&sl.h_hdr), sizeof(CcHostHeader)));
+            std::memset(sl.h_hdr, 0, sizeof(CcHostHeader));
         }
         for (uchar4*& q : h->h_label_ring)
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&q), mc * h->R * sizeof(uchar4)));
@@ -733,6 +825,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, cudaFuncSetAttribute(k_insert_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
 #endif
+    configure_fused(h);
     return CC_OK;
 }
 
@@ -749,6 +842,27 @@ static cudaError_t spin_wait(cudaEvent_t e)
     {
     }
     return r;
+#endif
+}
+
+// a fused push signals completion through a flag in page-locked host memory (written after everything else it reports)
+static cudaError_t spin_flag(cc_handle* h, const volatile unsigned int* flag, unsigned int ticket)
+{
+#ifdef CC_EMU
+    (void)h;
+    return *flag == ticket ? cudaSuccess : 1;
+#else
+    unsigned int spins = 0;
+    while (*flag != ticket)
+    {
+        if ((++spins & 0x3fffu) == 0) // a failed launch / a fault never sets the flag
+        {
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            if (q != cudaErrorNotReady && *flag != ticket)
+                return q == cudaSuccess ? cudaErrorUnknown : q;
+        }
+    }
+    return cudaSuccess;
 #endif
 }
 
@@ -924,6 +1038,64 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     h->n_timed = 0;
     sl.has_tf = h->has_tf;
     sl.spec = cfg.nth == 1;
+    sl.fused = sl.want_fused; // decided when the push was submitted (its inputs were routed accordingly)
+    if (sl.fused)
+    {
+        CcFusedArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.n = n;
+        a.has_tf = sl.has_tf ? 1 : 0;
+        a.spec = sl.spec ? 1 : 0;
+        a.scan_chunk = fused_scan_chunk(h->R);
+        a.tune = h->tune;
+        a.team_warps = 2;
+        a.pack_labels = h->label_prefetch && sl.has_tf ? 1 : 0;
+        a.seq = ++h->seq;
+        if (++h->ticket == 0)
+            ++h->ticket;
+        a.ticket = sl.ticket = h->ticket;
+        a.src_raw = sl.src_points;
+        a.src_poses = sl.src_poses;
+        const bool staged = sl.src_points != sl.in_points; // host inputs: fetched into the device input buffer
+        a.dst_raw = staged ? const_cast<void*>(sl.in_points) : nullptr;
+        a.dst_poses = staged ? const_cast<double*>(sl.in_poses) : nullptr;
+        a.s_parent = h->d_s_parent;
+        a.s_links = h->d_s_links;
+        a.snap = sl.d_state_snap;
+        a.d_labels = sl.d_labels;
+        a.h_hdr = sl.h_hdr;
+        a.h_state = sl.h_state;
+        a.h_first_unpub = sl.h_first_unpub;
+        a.h_clusters = sl.h_clusters;
+        a.h_points = sl.h_points;
+        a.h_labels = sl.h_labels;
+        sl.pre_cols = a.cap_cols = std::min(h->maxcols, sl.n + 64);
+        sl.pre_clusters = a.cap_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
+        sl.pre_points = a.cap_points = std::min(std::min(h->d.cap_cluster_points, h->prefetch_points), std::max(16384, sl.n * h->R / 4));
+        a.smem_bytes = static_cast<int>(h->fused_smem);
+#ifdef CC_EMU
+        CC_LAUNCH(k_push_fused, 1, 1, h->fused_smem, h->stream, cfg, h->d, a);
+#else
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(static_cast<unsigned>(h->fused_cluster), 1, 1);
+        lc.blockDim = dim3(static_cast<unsigned>(h->fused_threads), 1, 1);
+        lc.dynamicSmemBytes = h->fused_smem;
+        lc.stream = h->stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(h->fused_cluster);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 2;
+        CC_CHECK(h, cudaLaunchKernelEx(&lc, k_push_fused, cfg, h->d, a));
+#endif
+        h->launches++;
+        sl.launches1 = h->launches;
+        return CC_OK;
+    }
 
     CC_CHECK(h, cudaEventRecord(sl.ev0, h->stream));
     const int R = h->R;
@@ -1003,7 +1175,11 @@ static cc_status_t finish_push(cc_handle* h)
         h->pending[0] = h->pending[1];
         h->n_pending--;
     };
-    CC_CHECK(h, spin_wait(sl.done));
+    const bool timed_by_device = sl.fused;
+    if (sl.fused)
+        CC_CHECK(h, spin_flag(h, &sl.h_hdr->flag, sl.ticket));
+    else
+        CC_CHECK(h, spin_wait(sl.done));
     h->state = *sl.h_state;
     CcDevCfg cfg;
     fill_devcfg(h, cfg);
@@ -1025,7 +1201,15 @@ static cc_status_t finish_push(cc_handle* h)
         // the speculative commit was not usable: pushes queued behind this one skipped themselves (halt flag).
         // Finish this push column-sequentially, then run them again.
         for (int i = 1; i < h->n_pending; i++)
-            CC_CHECK(h, cudaEventSynchronize(h->slots[h->pending[i]].done));
+        {
+            cc_handle::Slot& o = h->slots[h->pending[i]];
+            if (o.fused)
+                CC_CHECK(h, spin_flag(h, &o.h_hdr->flag, o.ticket));
+            else
+                CC_CHECK(h, cudaEventSynchronize(o.done));
+        }
+        CC_CHECK(h, cudaStreamSynchronize(h->stream));
+        sl.fused = false; // its results are collected through the copy stream below
         bind_slot(h, sl);
         CC_RUN(h, k_halt, 1, 1, 0, h->d, -1); // clear
         if (h->state.abort)
@@ -1118,7 +1302,10 @@ static cc_status_t finish_push(cc_handle* h)
     }
     h->points_view = points_in_place ? reinterpret_cast<const cc_cluster_point_t*>(sl.h_points) : h->cluster_points.data();
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
+    if (timed_by_device)
+        ms = static_cast<float>(static_cast<double>(sl.h_hdr->t_end_ns - sl.h_hdr->t_start_ns) * 1e-6);
+    else
+        cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
 
     // clusters in the order the reference would deliver them: by the column whose pass finished them
     std::stable_sort(h->h_clusters.begin(), h->h_clusters.end(),
@@ -1230,7 +1417,12 @@ static cc_status_t launch_from(cc_handle* h, int n, const void* d_points, const 
     h->next_label = (h->next_label + 1) % 3;
     sl.h2d = ib ? ib->h2d : nullptr;
     sl.h2d0 = ib ? ib->h2d0 : nullptr;
-    if (ib)
+    // where a fused push fetches its firings from: the caller's device arrays, or page-locked host memory (no copy was
+    // queued for such an input buffer); null: the copy engine brings them, kernel chain
+    sl.src_points = ib ? (ib->fused ? ib->src_points : nullptr) : d_points;
+    sl.src_poses = ib ? (ib->fused ? ib->src_poses : nullptr) : d_poses;
+    sl.want_fused = ib ? ib->fused : fused_eligible(h, n);
+    if (ib && !ib->fused)
         CC_CHECK(h, cudaStreamWaitEvent(h->stream, ib->h2d, 0));
     cc_status_t s = launch_push(h, sl);
     if (s != CC_OK)
@@ -1295,10 +1487,16 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
         std::memcpy(ib.h_poses, poses, qb);
         src_poses = ib.h_poses;
     }
-    CC_CHECK(h, cudaEventRecord(ib.h2d0, h->in_stream));
-    CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
-    CC_CHECK(h, cudaMemcpyAsync(ib.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
-    CC_CHECK(h, cudaEventRecord(ib.h2d, h->in_stream));
+    ib.fused = fused_eligible(h, n);
+    ib.src_points = src_pts;
+    ib.src_poses = static_cast<const double*>(src_poses);
+    if (!ib.fused)
+    {
+        CC_CHECK(h, cudaEventRecord(ib.h2d0, h->in_stream));
+        CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
+        CC_CHECK(h, cudaMemcpyAsync(ib.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
+        CC_CHECK(h, cudaEventRecord(ib.h2d, h->in_stream));
+    }
     ib.n = n;
     const int mine = h->next_in;
     h->next_in = (h->next_in + 1) % 3;

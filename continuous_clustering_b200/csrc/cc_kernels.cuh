@@ -92,9 +92,12 @@ enum CcKernelId
     CC_KID_g_B,
     CC_KID_g_C,
     CC_KID_g_D,
+    CC_KID_push_fused,
+    CC_KID_fetch,
+    CC_KID_export,
     CC_KID_COUNT
 };
-#define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D"
+#define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D;k_push_fused;.fetch;.export"
 // Every stage is a device function over a VIRTUAL grid: (bid, nb) is (blockIdx.x, gridDim.x) when the stage runs as its
 // own kernel, and (rank of the CTA in its cluster, CTAs per cluster) when the stages of a whole push run inside the
 // single fused kernel k_push_fused with cluster barriers between them. blockDim.x / threadIdx.x are always the CTA's own.
@@ -259,6 +262,10 @@ struct CcOpMaxI32
 struct CcOpMaxI64
 {
     CC_DEV long long operator()(long long a, long long b) const { return a > b ? a : b; }
+};
+struct CcOpAddI64
+{
+    CC_DEV long long operator()(long long a, long long b) const { return a + b; }
 };
 template<typename T>
 CC_DEV T cc_shfl_up_any(T v, int off) // shuffle of a plain struct, word by word
@@ -3803,7 +3810,12 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 
 // Point::id of every member of a cluster finished in this commit (cpp:1005) + the member list and stamp range the
 // host needs for the finished-cluster callback (cpp:1007-1028).
-CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec)
+// `spans` (shared memory, 2 * span_cap ints, or null): SPAN MODE for short pushes -- instead of testing every unpublished
+// cell (up to a rotation of columns, whatever the size of the push) only the column spans [min_col, max_col] of the
+// clusters this push finished are visited; a cell inside the spans of several clusters is taken by the one it belongs
+// to. Falls back to the scan when the spans together are no smaller than the unpublished range.
+CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec, int* spans = nullptr,
+                        int span_cap = 0)
 {
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label, g.bid);
     const CcHead hd = cc_head(p.st);
@@ -3814,9 +3826,44 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
     const CcDevState* st = p.st;
     const int R = cfg.R;
     const long long gbase = st->gbase, c1 = st->seg_c1;
-    const long long total = (c1 - gbase + 1) * R;
+    long long total = (c1 - gbase + 1) * R;
     const int lane = threadIdx.x % CC_WARP;
     const unsigned int lt_mask = (1u << lane) - 1u;
+    int nspan = 0; // > 0: span mode
+    if (spans)
+    {
+        // every CTA builds the same table: exclusive prefix sum of the clusters' span sizes in cells + their first columns
+        const int T = blockDim.x, t = threadIdx.x;
+        const int ncl = st->n_clusters < p.cap_clusters ? st->n_clusters : p.cap_clusters;
+        __shared__ int sh_span_total;
+        __shared__ long long sh_scan[32];
+        if (ncl == 0)
+            return;
+        if (ncl <= span_cap && ncl <= T)
+        {
+            int cells = 0, mincol_rel = 0;
+            if (t < ncl)
+            {
+                const long long mn = p.clusters[t].min_col, mx = p.clusters[t].max_col;
+                cells = static_cast<int>((mx - mn + 1) * R);
+                mincol_rel = static_cast<int>(mn - gbase);
+            }
+            const long long off = cc_block_exclusive_scan(sh_scan, static_cast<long long>(cells), 0LL, CcOpAddI64());
+            if (t < ncl)
+            {
+                spans[t] = static_cast<int>(off < 0x7fffffff ? off : 0x7fffffff);
+                spans[span_cap + t] = mincol_rel;
+            }
+            if (t == ncl - 1)
+                sh_span_total = off + cells < 0x7fffffff ? static_cast<int>(off + cells) : 0x7fffffff;
+            __syncthreads();
+            if (static_cast<long long>(sh_span_total) < total)
+            {
+                nspan = ncl;
+                total = sh_span_total;
+            }
+        }
+    }
     // warps stay converged: the members of one cluster among a warp's cells reserve their slots in the cluster's point
     // list and update its stamp range with one atomic each
     for (long long i0 = g.bid * blockDim.x + threadIdx.x - lane; i0 < total; i0 += static_cast<long long>(g.nb) * blockDim.x)
@@ -3828,8 +3875,28 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
         unsigned long long stamp = 0ull;
         if (i < total)
         {
-            gcol = gbase + i / R;
-            row = static_cast<int>(i % R);
+            int want = -1; // span mode: the cluster whose span this work item belongs to
+            if (nspan)
+            {
+                int a = 0, b = nspan - 1; // last k with spans[k] <= i
+                while (a < b)
+                {
+                    const int mid = (a + b + 1) >> 1;
+                    if (spans[mid] <= static_cast<int>(i))
+                        a = mid;
+                    else
+                        b = mid - 1;
+                }
+                want = a;
+                const int local_i = static_cast<int>(i) - spans[a];
+                gcol = gbase + spans[span_cap + a] + local_i / R;
+                row = local_i % R;
+            }
+            else
+            {
+                gcol = gbase + i / R;
+                row = static_cast<int>(i % R);
+            }
             const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
             if (p.slot_gcol[cell / R] == gcol)
             {
@@ -3837,6 +3904,8 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
                 if (root != CC_NONE && p.tstate[root] == 1u + seq)
                 {
                     slot = p.tslot[root];
+                    if (want >= 0 && slot != want)
+                        slot = -1; // labelled by the work item of its own cluster's span
                     if (slot >= 0)
                     {
                         p.cid[cell] = p.tid[root];
@@ -4017,6 +4086,292 @@ __global__ void k_state_snapshot(CcDevPtrs p, CcDevState* dst)
     CC_PDL_ENTER();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_state_snapshot, static_cast<int>(blockIdx.x));
     d_state_snapshot(p, dst);
+}
+
+// =====================================================================================================
+// K*  the whole push in ONE launch (short pushes: latency mode). One thread-block cluster; the stages above run one
+//     after the other over the CTAs of the cluster with a hardware cluster barrier (release / acquire, ~0.2 us) where the
+//     multi-kernel path has a kernel boundary (~1 us + ramp-up each, and ~4 us of host launch time each). The firings are
+//     read straight from page-locked HOST memory (no copy-engine hop) and the results of the push -- state, per-column
+//     first-unpublished, cluster records, member lists, packed labels -- are written straight back to page-locked host
+//     memory, followed by a flag the host polls. Same device functions, same results as the kernel chain.
+// =====================================================================================================
+struct CcHostHeader // page-locked, written by the device at the very end of a fused push
+{
+    unsigned int flag; // ticket of the push once everything else is visible
+    unsigned int pad_;
+    unsigned long long t_start_ns, t_end_ns; // %globaltimer at kernel entry (after the grid dependency) / exit
+};
+
+struct CcFusedArgs
+{
+    int n, has_tf, spec, scan_chunk, tune, team_warps, pack_labels;
+    unsigned int seq, ticket;
+    const void* src_raw;     // cc_raw_point_t[n * R]: page-locked host memory (or device memory)
+    const double* src_poses; // [n][12]
+    void* dst_raw;           // device staging the stages read (null: read src directly, device-resident inputs)
+    double* dst_poses;
+    unsigned int* s_parent;
+    unsigned int* s_links;
+    CcDevState* snap; // device copy of the state at the end of the push
+    uchar4* d_labels;
+    // results, page-locked host memory
+    CcHostHeader* h_hdr;
+    CcDevState* h_state;
+    long long* h_first_unpub;
+    CcCluster* h_clusters;
+    CcClusterPoint* h_points;
+    uchar4* h_labels;
+    int cap_cols, cap_clusters, cap_points, smem_bytes;
+};
+
+CC_DEV CcGrid cc_grid_cluster()
+{
+    CcGrid g;
+#ifdef CC_EMU
+    g.bid = 0;
+    g.nb = 1;
+#else
+    unsigned int r, n;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+    g.bid = static_cast<int>(r);
+    g.nb = static_cast<int>(n);
+#endif
+    return g;
+}
+// barrier over all threads of the cluster; global-memory writes before it are visible to every CTA after it
+CC_DEV void cc_cluster_sync()
+{
+#ifndef CC_EMU
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+CC_DEV void cc_fence_system()
+{
+#ifndef CC_EMU
+    __threadfence_system();
+#endif
+}
+CC_DEV unsigned long long cc_globaltimer()
+{
+#ifdef CC_EMU
+    return 0ull;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+
+#ifdef CC_EMU
+struct uint4
+{
+    unsigned int x, y, z, w;
+};
+#endif
+
+// 16-byte copy over the virtual grid (bytes is a multiple of 16, both pointers 16-byte aligned)
+CC_DEV void d_copy16(const CcGrid g, void* dst, const void* src, size_t bytes)
+{
+    const size_t n = bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const size_t stride = static_cast<size_t>(g.nb) * blockDim.x;
+    for (size_t i0 = static_cast<size_t>(g.bid) * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride)
+    {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * stride < n)
+                v[u] = s4[i0 + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * stride < n)
+                d4[i0 + u * stride] = v[u];
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p, CcFusedArgs a)
+{
+    CC_PDL_ENTER();
+    const CcGrid g = cc_grid_cluster();
+    const unsigned long long t_start = cc_globaltimer();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_push_fused, g.bid);
+    const int n = a.n;
+    // ---- inputs: page-locked host memory -> device staging ----
+    if (a.dst_raw)
+    {
+        CcTraceScope tr(p.trace, CC_KID_fetch, g.bid);
+        d_copy16(g, a.dst_raw, a.src_raw, static_cast<size_t>(n) * cfg.R * sizeof(CcRawPoint));
+        d_copy16(g, a.dst_poses, a.src_poses, static_cast<size_t>(n) * 12 * sizeof(double));
+        tr.stop();
+        cc_cluster_sync();
+    }
+    // ---- insertion (cpp:105-292) ----
+    d_prep(g, cfg, p, n);
+    cc_cluster_sync();
+    d_scan_lite(g, cfg, p, n);
+    cc_cluster_sync();
+    d_scan_check(g, cfg, p, n);
+    cc_cluster_sync();
+    d_insert_scan(g, cfg, p, n, a.scan_chunk, 1);
+    cc_cluster_sync();
+    d_scatter(g, cfg, p, n);
+    cc_cluster_sync();
+    if (!a.has_tf)
+    {
+        // the reference throws from the segmentation stage of the first completed column (cpp:298-299)
+        if (g.bid == 0 && threadIdx.x == 0)
+            d_halt(g, p, 1);
+    }
+    else
+    {
+        // ---- ground segmentation (cpp:294-624) ----
+        {
+            const CcHead hd = cc_head(p.st);
+            if (!hd.halted)
+            {
+                d_gap_main(g, cfg, p, hd);
+                cc_cluster_sync();
+                if (g.bid == 0)
+                    d_gap_tail(g, cfg, p, hd);
+            }
+            else
+                cc_cluster_sync();
+        }
+        cc_cluster_sync();
+        d_ground(g, cfg, p, a.s_parent);
+        cc_cluster_sync();
+        // ---- association (cpp:638-835) ----
+        d_probe(g, cfg, p, a.s_parent, a.s_links, a.spec);
+        cc_cluster_sync();
+        d_probe_heavy(g, cfg, p, a.s_parent, a.s_links, a.tune, a.team_warps);
+        cc_cluster_sync();
+        if (a.spec)
+        {
+            d_commit_copy(g, cfg, p, a.s_parent, 0, -1, 1);
+            cc_cluster_sync();
+            d_commit_roots(g, cfg, p, 0, -1, 1);
+            cc_cluster_sync();
+            d_commit_links(g, cfg, p, a.s_parent, a.s_links, 0, -1, 1);
+            cc_cluster_sync();
+            // ---- finish detection (cpp:837-974), list phases over all CTAs ----
+            if (!p.st->halted)
+            {
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_init, g.bid);
+                    d_fin_init(g, cfg, p, 0, -1, 1);
+                }
+                cc_cluster_sync();
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_agg, g.bid);
+                    d_fin_agg(g, cfg, p, 1);
+                }
+                cc_cluster_sync();
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_decide, g.bid);
+                    d_fin_decide(g, cfg, p, 1, 0, nullptr);
+                }
+                cc_cluster_sync();
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_mark, g.bid);
+                    d_fin_mark(g, cfg, p, a.seq, 1);
+                }
+                cc_cluster_sync();
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_copyback, g.bid);
+                    d_fin_copyback(g, p, 1);
+                }
+                cc_cluster_sync();
+                // per-column first-unpublished + end-of-push bookkeeping in CTA 0, beside the labelling in the others
+                // (the labelling reads gbase / seg_c1 / n_clusters, which the tail does not modify)
+                if (g.bid == 0)
+                {
+                    CcTraceScope tr(p.trace, CC_KID_fin_columns, g.bid);
+                    d_fin_columns(g, cfg, p, 1, (a.smem_bytes - static_cast<int>(blockDim.x) * 8) / 4);
+                    __syncthreads();
+                    if (threadIdx.x == 0)
+                        d_push_done(p, 1);
+                }
+                if (g.nb == 1 || g.bid != 0)
+                {
+                    CcGrid gl = g;
+                    if (g.nb > 1)
+                    {
+                        gl.bid = g.bid - 1;
+                        gl.nb = g.nb - 1;
+                    }
+                    CC_SMEM(smem_l);
+                    if (g.nb == 1)
+                        __syncthreads(); // CTA 0 did both: the tail's shared memory is free again
+                    d_fin_label(gl, cfg, p, a.seq, 1, reinterpret_cast<int*>(smem_l), 512);
+                }
+            }
+            else if (g.bid == 0 && threadIdx.x == 0)
+                d_push_done(p, 1);
+        }
+        else if (g.bid == 0 && threadIdx.x == 0)
+            d_halt(g, p, 0); // finish passes every n-th column: column-sequential path, on the host's cue
+    }
+    cc_cluster_sync();
+    // ---- results straight to the host ----
+    {
+        CcTraceScope tr(p.trace, CC_KID_export, g.bid);
+        const CcDevState* st = p.st;
+        const bool ok = !st->halted && a.has_tf;
+        if (ok)
+        {
+            int ncols = st->ncols < a.cap_cols ? st->ncols : a.cap_cols;
+            ncols = ncols > 0 ? ncols : 0;
+            const int ncl = st->n_clusters < a.cap_clusters ? st->n_clusters : a.cap_clusters;
+            const int ncp = st->n_cluster_points < a.cap_points ? st->n_cluster_points : a.cap_points;
+            const int gt = g.bid * blockDim.x + threadIdx.x, gn = g.nb * blockDim.x;
+            for (int i = gt; i < ncols; i += gn)
+                a.h_first_unpub[i] = p.col_first_unpub[i];
+            {
+                const int words = ncl * static_cast<int>(sizeof(CcCluster) / 8);
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.clusters);
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.h_clusters);
+                for (int i = gt; i < words; i += gn)
+                    dst[i] = src[i];
+            }
+            {
+                static_assert(sizeof(CcClusterPoint) == 16, "copied as 16-byte words");
+                const uint4* src = reinterpret_cast<const uint4*>(p.cluster_points);
+                uint4* dst = reinterpret_cast<uint4*>(a.h_points);
+                for (int i = gt; i < ncp; i += gn)
+                    dst[i] = src[i];
+            }
+            if (a.pack_labels)
+            {
+                const long long colbase = st->colbase;
+                const int R = cfg.R;
+                const int total = ncols * R;
+                for (int i = gt; i < total; i += gn)
+                {
+                    const int ci = i / R, row = i - ci * R;
+                    const uchar4 l = p.lab[static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row];
+                    a.d_labels[i] = l;
+                    a.h_labels[i] = l;
+                }
+            }
+        }
+        if (g.bid == 0)
+        {
+            d_state_snapshot(p, a.snap);
+            d_state_snapshot(p, a.h_state);
+        }
+        cc_fence_system();
+    }
+    cc_cluster_sync();
+    if (g.bid == 0 && threadIdx.x == 0)
+    {
+        a.h_hdr->t_start_ns = t_start;
+        a.h_hdr->t_end_ns = cc_globaltimer();
+        cc_fence_system();
+        *reinterpret_cast<volatile unsigned int*>(&a.h_hdr->flag) = a.ticket;
+    }
 }
 
 // ---- device math self-test (bit equality with the host libm) ----

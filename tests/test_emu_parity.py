@@ -252,3 +252,30 @@ def test_debug_hooks_are_inert_in_the_emulation(emu_library):
     cc.addFirings(pts[:128], poses[:128])
     assert cc.get_trace() == []  # the stamps are compiled out of the CPU build
     cc.debug_trace(False)
+
+
+CHAIN_CASES = [CASES[0], CASES[3], CASES[5], CASES[14], CASES[12]]
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", CHAIN_CASES)
+def test_short_pushes_through_the_kernel_chain(emu_library, oracle_lib, monkeypatch, spec, kw, cfg_over, chunk, flag_period):
+    """Short pushes normally take the fused single-launch kernel (k_push_fused); CC_B200_FUSED_MAX=0 sends them through
+    the kernel chain the long pushes use. Same results either way."""
+    monkeypatch.setenv("CC_B200_FUSED_MAX", "0")
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    probe = make_cc(emu_library, cfg, sp.rows)
+    assert probe.addFirings(pts[:chunk], poses[:chunk]).info.gpu_launches > 1
+    probe.close()
+    cc = make_cc(emu_library, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="emulated kernels (chain)")
+
+
+def test_short_pushes_are_one_launch(emu_library):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=2.0)
+    cc = make_cc(emu_library, drvlib.stream_config("tiny16"), sp.rows)
+    launches = [int(cc.addFirings(pts[a:a + 64], poses[a:a + 64]).info.gpu_launches) for a in range(0, 384, 64)]
+    assert launches == [1] * len(launches), launches
