@@ -565,15 +565,17 @@ static void configure_fused(cc_handle* h)
 #endif
     const int T = h->fused_threads, R = h->R;
     const int warps = (T + CC_WARP - 1) / CC_WARP;
-    size_t smem = static_cast<size_t>(T) * sizeof(CcAnchorSeg);
+    if (h->fused_max > CC_WARP * CC_SMALL_PER)
+        h->fused_max = CC_WARP * CC_SMALL_PER; // the warp-wide scans of the fused kernel
+    size_t smem = cc_lite_small_smem_bytes(h->fused_max);
     smem = std::max(smem, static_cast<size_t>(scan_smem_bytes(R, fused_scan_chunk(R), T)));
     smem = std::max(smem, warps * cc_ground_warp_bytes(R));
     smem = std::max(smem, h->probe_smem);
     smem = std::max(smem, cc_heavy_smem_bytes(T, 2));
     smem = std::max(smem, static_cast<size_t>(T) * 8 + static_cast<size_t>(h->d.cap_G) * sizeof(int));
     smem = std::max(smem, static_cast<size_t>(2 * 512 * sizeof(int)));
-    if (smem > 180 * 1024)
-        return; // (the kernel also has ~40 KB of static shared memory) such a configuration keeps the kernel chain
+    if (smem > 200 * 1024)
+        return; // such a configuration keeps the kernel chain
     h->fused_smem = smem;
 #ifdef CC_EMU
     h->fused_cluster = 1;
@@ -675,6 +677,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.s_az, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incl, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.s_incaz, stage));
+        CC_CHECK(h, dev_alloc(h, L, &d.s_ego, static_cast<size_t>(h->max_firings) * 12));
         CC_CHECK(h, dev_alloc(h, L, &d.s_cwr, stage + static_cast<size_t>(CC_K1_MAX_CHUNK) * h->R));
         CC_CHECK(h, dev_alloc(h, L, &d.s_cwrT, stage));
         CC_CHECK(h, dev_alloc(h, L, &d.o_g, stage));

@@ -279,6 +279,18 @@ CC_DEV T cc_shfl_up_any(T v, int off) // shuffle of a plain struct, word by word
     memcpy(&v, w, sizeof(T));
     return v;
 }
+template<typename T>
+CC_DEV T cc_shfl_any(T v, int src) // same for a broadcast from one lane
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized types only");
+    unsigned int w[sizeof(T) / 4];
+    memcpy(w, &v, sizeof(T));
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(T) / 4); i++)
+        w[i] = __shfl_sync(CC_FULL_MASK, w[i], src);
+    memcpy(&v, w, sizeof(T));
+    return v;
+}
 // Two-level: shuffle scan inside every warp, the warp totals scanned by warp 0 (two block barriers in all; the block
 // has at most 32 warps). `sm` needs room for one T per warp. op(identity, x) == x and op(x, identity) == x.
 template<typename T, typename Op>
@@ -352,6 +364,8 @@ CC_DEV void d_prep(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
     // waited for, even while the next push is already in flight (the reference's callbacks read range_image_ before
     // clearColumns runs, cpp:1087-1091). Pure stores: they drain while the firings below are being prepared.
     d_clear(g, cfg, p, p.st->clear2_from, p.st->clear2_to);
+    if (g.bid == 0 && threadIdx.x == 0)
+        p.st->scan_kbad = 0x7fffffff; // lowered by the scan stages to the first firing that is not regular
     // one warp per firing, lanes over rows: per-point staging + the firing's summary for the lite insertion path
     // (anchor = column-in-rotation of its first valid row; rearmost / foremost column relative to the anchor)
     const int R = cfg.R;
@@ -419,6 +433,24 @@ CC_DEV void d_prep(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
             }
             rear = cc_warp_min(lmin);
             fore = cc_warp_max(lmax);
+        }
+        // robot_from_sensor * odom_from_sensor^-1 of the firing (the ego-box transform of the columns it completes,
+        // cpp:300-301), one element per lane in the evaluation order of cc_iso_inverse + cc_iso_mul
+        for (int e = lane; e < 12; e += CC_WARP)
+        {
+            const int i = e / 4, j = e % 4;
+            const double* ra = cfg.robot_from_sensor + i * 4;
+            double v;
+            if (j < 3)
+                v = ra[0] * pose[j * 4 + 0] + (ra[1] * pose[j * 4 + 1] + ra[2] * pose[j * 4 + 2]);
+            else
+            {
+                double tr[3];
+                for (int q = 0; q < 3; q++)
+                    tr[q] = -(pose[q] * pose[3] + (pose[4 + q] * pose[7] + pose[8 + q] * pose[11]));
+                v = (ra[0] * tr[0] + (ra[1] * tr[1] + ra[2] * tr[2])) + ra[3];
+            }
+            p.s_ego[static_cast<size_t>(k) * 12 + e] = v;
         }
         if (lane == 0)
         {
@@ -753,6 +785,223 @@ __global__ void k_scan_check(CcDevCfg cfg, CcDevPtrs p, int n)
 {
     CC_PDL_ENTER();
     d_scan_check(cc_grid(), cfg, p, n);
+}
+
+// ---- the two stages above for SHORT pushes, in one phase of the fused kernel: every CTA repeats the (tiny) per-firing
+//      scan in its warp 0 with the per-firing values in shared memory -- nobody waits for one CTA to publish them -- and
+//      then checks its rows, one warp per row. Pushes of up to CC_WARP * CC_SMALL_PER firings. ----
+#ifdef CC_EMU
+#define CC_SMALL_PER 8192 /* the emulation runs a warp as one lane */
+#else
+#define CC_SMALL_PER 16
+#endif
+template<typename T, typename Op>
+CC_DEV T cc_warp_exclusive_scan(T v, T identity, Op op, int lane)
+{
+    T x = v;
+    for (int off = 1; off < CC_WARP; off <<= 1)
+    {
+        const T y = cc_shfl_up_any(x, off);
+        if (lane >= off)
+            x = op(y, x);
+    }
+    T e = cc_shfl_up_any(x, 1);
+    if (lane == 0)
+        e = identity;
+    return e;
+}
+static inline __host__ __device__ size_t cc_lite_small_smem_bytes(int n)
+{
+    return static_cast<size_t>(n) * (sizeof(CcFiringSummary) + 3 * sizeof(int)) + 16;
+}
+
+CC_DEV void d_lite_check_small(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int n)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_scan_lite, g.bid);
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    CC_SMEM(smem);
+    CcFiringSummary* fs = reinterpret_cast<CcFiringSummary*>(smem);
+    int* smU = reinterpret_cast<int*>(fs + n);
+    int* smP = smU + n;     // [n + 1]
+    int* smF = smP + n + 1; // [n + 1]
+    __shared__ int sh_kbad;
+    CcDevState* st = p.st;
+    const int T = blockDim.x, t = threadIdx.x, lane = t % CC_WARP, warp = t / CC_WARP;
+    const int nwarps = (T + CC_WARP - 1) / CC_WARP;
+    const int R = cfg.R, N = cfg.N, half = cfg.half;
+    const int NOT_SET = -0x7fffffff - 1;
+    const long long base = st->P;
+    const bool ok_state = st->F >= 0 && st->foremost >= 0 && base > 0 && st->ring_start != -1;
+    const int pc0 = static_cast<int>(base % N);
+    const int Fm0 = static_cast<int>(st->foremost - base);
+    const int colbase_rel = static_cast<int>(st->F - base);
+    const bool ok = ok_state && n <= CC_WARP * CC_SMALL_PER;
+    for (int k = t; k < n; k += T)
+        fs[k] = p.lite_sum[k];
+    __syncthreads();
+    if (warp == 0)
+    {
+        int kbad = ok ? n : 0;
+        if (ok)
+        {
+            // same three passes as d_scan_lite, one lane per run of consecutive firings
+            const int per = (n + CC_WARP - 1) / CC_WARP;
+            const int a = lane * per < n ? lane * per : n, b = (a + per < n) ? a + per : n;
+            CcAnchorSeg mine;
+            mine.has = 0;
+            mine.first_cw = mine.last_cw = mine.off = 0;
+            for (int k = a; k < b; k++)
+            {
+                if (fs[k].nvalid < 0)
+                    kbad = k < kbad ? k : kbad;
+                if (fs[k].nvalid > 0)
+                {
+                    if (!mine.has)
+                    {
+                        mine.has = 1;
+                        mine.first_cw = fs[k].anchor;
+                    }
+                    else
+                        mine.off += cc_wrapdiff(fs[k].anchor - mine.last_cw, N);
+                    mine.last_cw = fs[k].anchor;
+                }
+                smU[k] = mine.off;
+            }
+            CcAnchorSeg ident;
+            ident.has = 0;
+            ident.first_cw = ident.last_cw = ident.off = 0;
+            CcOpAnchorSeg op;
+            op.N = N;
+            const CcAnchorSeg before = cc_warp_exclusive_scan(mine, ident, op, lane);
+            CcAnchorSeg all = op(before, mine);
+            all = cc_shfl_any(all, CC_WARP - 1);
+            int U0 = 0; // the reference's unwrap of the push's first valid firing against the rearmost column (cpp:152-175)
+            if (all.has)
+            {
+                const int cw = all.first_cw, diff = cw - pc0;
+                U0 = -pc0 + cw;
+                if (diff < -half)
+                    U0 += N;
+                else if (diff > half)
+                    U0 -= N;
+            }
+            const int mybase = U0 + (before.has && mine.has ? before.off + cc_wrapdiff(mine.first_cw - before.last_cw, N) : 0);
+            CcMaxPair run;
+            run.p = NOT_SET;
+            run.f = NOT_SET;
+            for (int k = a; k < b; k++)
+            {
+                smP[k] = run.p; // exclusive running maxima inside the lane's run
+                smF[k] = run.f;
+                if (fs[k].nvalid > 0)
+                {
+                    const int U = mybase + smU[k];
+                    smU[k] = U;
+                    const int rear = U + fs[k].rear_rel, fore = U + fs[k].fore_rel;
+                    if (fore - rear > N / 2) // cpp:252-261
+                        kbad = k < kbad ? k : kbad;
+                    run.p = rear > run.p ? rear : run.p;
+                    run.f = fore > run.f ? fore : run.f;
+                }
+            }
+            CcMaxPair seed;
+            seed.p = 0;   // rearmost column at the start of the push (relative: 0)
+            seed.f = Fm0; // foremost column at the start of the push
+            CcMaxPair pre = cc_warp_exclusive_scan(run, seed, CcOpMaxPair(), lane);
+            pre = CcOpMaxPair()(pre, seed);
+            for (int k = a; k < b; k++)
+            {
+                const int Pk = smP[k] > pre.p ? smP[k] : pre.p, Fk = smF[k] > pre.f ? smF[k] : pre.f;
+                smP[k] = Pk;
+                smF[k] = Fk;
+                if (fs[k].nvalid > 0)
+                {
+                    const int rear = smU[k] + fs[k].rear_rel, fore = smU[k] + fs[k].fore_rel;
+                    if (!(rear - Pk > -half && fore - Pk < half))
+                        kbad = k < kbad ? k : kbad; // the unwrap of some point could differ from the reference's
+                    const int Pnext = rear > Pk ? rear : Pk;
+                    if (Pnext - colbase_rel > p.maxcols)
+                        kbad = k < kbad ? k : kbad; // the per-firing path raises the error
+                }
+                if (g.bid == 0) // one copy for the stages that follow (scatter, insertion commit)
+                {
+                    p.lite_P[k] = Pk;
+                    p.lite_F[k] = Fk;
+                    p.lite_U[k] = smU[k];
+                }
+            }
+            if (a < n && b == n)
+            {
+                smP[n] = run.p > pre.p ? run.p : pre.p;
+                smF[n] = run.f > pre.f ? run.f : pre.f;
+                if (g.bid == 0)
+                {
+                    p.lite_P[n] = smP[n];
+                    p.lite_F[n] = smF[n];
+                }
+            }
+            kbad = cc_warp_min(kbad);
+        }
+        if (lane == 0)
+        {
+            sh_kbad = kbad;
+            if (g.bid == 0)
+                st->scan_lite_base = base;
+        }
+    }
+    __syncthreads();
+    const int kmax = sh_kbad;
+    int kbad_all = warp == 0 ? kmax : n;
+    // ---- per row: columns strictly increasing and beyond the row's front (d_scan_check), one warp per row ----
+    for (int row = g.bid * nwarps + warp; row < R; row += g.nb * nwarps)
+    {
+        const int seg = (kmax + CC_WARP - 1) / CC_WARP;
+        const int a = lane * seg < kmax ? lane * seg : kmax, b = (a + seg < kmax) ? a + seg : kmax;
+        int first = NOT_SET, firstk = kmax, last = NOT_SET, kbad = n, gmax = NOT_SET;
+        const int* cwT = p.s_cwrT + static_cast<size_t>(row) * p.max_firings;
+        for (int kb = a; kb < b; kb += 8) // loads of 8 firings issued together
+        {
+            int cw[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                cw[u] = kb + u < b ? cwT[kb + u] : CC_INVALID_CWR;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                const int k = kb + u;
+                if (cw[u] == CC_INVALID_CWR)
+                    continue;
+                const int gc = smU[k] + cc_wrapdiff(cw[u] - fs[k].anchor, N);
+                if (first == NOT_SET)
+                {
+                    first = gc;
+                    firstk = k;
+                }
+                else if (gc <= last)
+                    kbad = k < kbad ? k : kbad;
+                last = gc;
+                if (gc >= smP[k]) // stored (not too far behind, cpp:210-221): candidate for the row's new front
+                    gmax = gc > gmax ? gc : gmax;
+            }
+        }
+        int prev = cc_warp_exclusive_scan(last, NOT_SET, CcOpLastSetI32(), lane);
+        if (prev == NOT_SET)
+        {
+            long long rel = p.rowmax[row] - base; // the row's front
+            prev = rel < -0x3fffffff ? -0x3fffffff : static_cast<int>(rel);
+        }
+        if (first != NOT_SET && first <= prev)
+            kbad = firstk < kbad ? firstk : kbad;
+        kbad = cc_warp_min(kbad);
+        gmax = cc_warp_max(gmax);
+        if (lane == 0)
+            p.lite_rowfront[row] = gmax;
+        kbad_all = kbad < kbad_all ? kbad : kbad_all;
+    }
+    if (lane == 0 && kbad_all < 0x7fffffff)
+        atomicMin(&st->scan_kbad, kbad_all); // starts out at INT_MAX (d_prep)
 }
 
 // =====================================================================================================
@@ -1471,14 +1720,18 @@ CC_DEV void d_scatter(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
     const int total = n_firings * cfg.R;
+    const int scan_kbad = p.st->scan_kbad;
+    // A push that is regular as a whole needs nothing from the insertion scan's commit (which may be running beside this
+    // stage in the fused kernel and rewrites scan_base): the column base is the one the lite stages left.
+    const long long scan_base = scan_kbad >= n_firings ? p.st->scan_lite_base : p.st->scan_base;
     for (int idx = g.bid * blockDim.x + threadIdx.x; idx < total; idx += g.nb * blockDim.x)
     {
         const int k = idx / cfg.R, row = idx - k * cfg.R;
         int grel, rot;
         bool winner_test = true;
-        if (k < p.st->scan_kbad)
+        if (k < scan_kbad)
         {
-            winner_test = p.st->scan_kbad < n_firings; // a push that is regular as a whole has one writer per cell
+            winner_test = scan_kbad < n_firings; // a push that is regular as a whole has one writer per cell
             // firing resolved by the lite path: same integers as k_scan_check / k_scan_apply
             const int cw = p.s_cwr[idx];
             if (cw == CC_INVALID_CWR)
@@ -1486,7 +1739,7 @@ CC_DEV void d_scatter(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
             grel = p.lite_U[k] + cc_wrapdiff(cw - p.lite_sum[k].anchor, cfg.N);
             if (grel < p.lite_P[k])
                 continue; // too far behind (cpp:210-221)
-            rot = static_cast<int>((p.st->scan_base + grel - cw) / cfg.N); // exact: column == rot * N + cw
+            rot = static_cast<int>((scan_base + grel - cw) / cfg.N); // exact: column == rot * N + cw
         }
         else if (p.firing_rec[k].mode)
         {
@@ -1518,8 +1771,8 @@ CC_DEV void d_scatter(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firings)
                 continue;
             rot = p.o_rot[idx];
         }
-        const long long g = p.st->scan_base + grel;
-        const size_t cell = static_cast<size_t>(cc_local_col(g, cfg.ringcols)) * cfg.R + row;
+        const long long gc = scan_base + grel;
+        const size_t cell = static_cast<size_t>(cc_local_col(gc, cfg.ringcols)) * cfg.R + row;
         const float4 sp = p.s_pos[idx];
         if (winner_test && ccm::f2u(p.pos[cell].w) != ccm::f2u(sp.w))
             continue;
@@ -1683,6 +1936,109 @@ CC_DEV void d_gap_tail(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, 
     }
 }
 
+// The same in ONE phase for short pushes (fused kernel): a warp per row, every lane a run of consecutive columns (two
+// independent loads per column issued together), the lanes chained by a warp scan seeded with the value carried from
+// earlier pushes. Leaves fully resolved values in col_gap (and NaN in the chunk carries d_ground falls back to).
+CC_DEV void d_gap_rows(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, const CcHead& hd)
+{
+    CcTraceScope cc_tr_gmain(p.trace, CC_KID_gap_main, g.bid);
+    const int R = cfg.R;
+    const int ncols = hd.ncols;
+    if (ncols <= 0)
+        return;
+    const int T = blockDim.x, lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
+    const int nwarps = (T + CC_WARP - 1) / CC_WARP;
+    const float nanv = cc_nanf();
+    const int base_local = cc_local_col(hd.colbase, cfg.ringcols);
+    const int nchunks = (ncols + CC_GAP_CHUNK - 1) / CC_GAP_CHUNK;
+    const int per = (ncols + CC_WARP - 1) / CC_WARP;
+    const bool one_pass = per <= 8; // the lane's values stay in registers between the two halves
+    for (int row = g.bid * nwarps + warp; row < R; row += g.nb * nwarps)
+    {
+        const int a = lane * per < ncols ? lane * per : ncols, b = (a + per < ncols) ? a + per : ncols;
+        const float state = p.gap_state[row]; // issued together with the cells below
+        // difference to the laser below for up to 8 columns from c0 (NaN outside the lane's run), loads issued together
+        auto diffs = [&](int c0, float* d)
+        {
+            float x[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                x[u] = y[u] = nanv;
+                if (c0 + u < b)
+                {
+                    int local = base_local + c0 + u;
+                    if (local >= cfg.ringcols)
+                        local -= cfg.ringcols;
+                    const size_t cell = static_cast<size_t>(local) * R + row;
+                    x[u] = p.incl[cell];
+                    y[u] = row == R - 1 ? 0.f : p.incl[cell + 1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                d[u] = x[u] - y[u];
+        };
+        float keep[8];
+        float last = nanv; // last valid value of the lane's run
+        if (one_pass)
+        {
+            diffs(a, keep);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                if (!cc_isnan(keep[u]))
+                    last = keep[u];
+                keep[u] = last; // value after this column, still without what came before the run
+            }
+        }
+        else
+            for (int c0 = a; c0 < b; c0 += 8)
+            {
+                float d[8];
+                diffs(c0, d);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (!cc_isnan(d[u]))
+                        last = d[u];
+            }
+        float carry = cc_warp_exclusive_scan(last, nanv, CcOpLastValid(), lane);
+        if (cc_isnan(carry))
+            carry = state;
+        if (one_pass)
+        {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (a + u < b)
+                    p.col_gap[static_cast<size_t>(a + u) * R + row] = cc_isnan(keep[u]) ? carry : keep[u];
+        }
+        else
+        {
+            float run = carry;
+            for (int c0 = a; c0 < b; c0 += 8)
+            {
+                float d[8];
+                diffs(c0, d);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                {
+                    if (!cc_isnan(d[u]))
+                        run = d[u];
+                    if (c0 + u < b)
+                        p.col_gap[static_cast<size_t>(c0 + u) * R + row] = run;
+                }
+            }
+        }
+        // the row's value after the push
+        const float mine_or_carry = cc_isnan(last) ? carry : last;
+        const float fin = cc_shfl_any(mine_or_carry, CC_WARP - 1);
+        if (lane == 0)
+            p.gap_state[row] = fin;
+        for (int ch = lane; ch < nchunks; ch += CC_WARP)
+            p.gap_chunk_carry[static_cast<size_t>(ch) * R + row] = nanv;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_gap_scan(CcDevCfg cfg, CcDevPtrs p)
 {
     CC_PDL_ENTER();
@@ -1742,7 +2098,10 @@ CC_DEV double cc_ldcg_f64(const double* q)
 #endif
 }
 
-CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
+// `d_labels` / `h_labels` (or null): the packed labels of the column (cc_set_label_prefetch) are also written to the
+// push's label buffers, device and page-locked host, for columns below `label_cap` (fused kernel).
+CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, uchar4* d_labels = nullptr,
+                     uchar4* h_labels = nullptr, int label_cap = 0)
 {
     CcTraceScope cc_trace_scope(p.trace, CC_KID_ground, g.bid);
     const CcHead hd = cc_head(p.st);
@@ -1801,14 +2160,11 @@ CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_
         const double* pose = p.poses + 12 * trig;
         const float spx = static_cast<float>(pose[3]), spy = static_cast<float>(pose[7]),
                     spz = static_cast<float>(pose[11]);
+        // ego-box transform of the column (cpp:300-301): prepared per firing by d_prep
+        for (int e = lane; e < 12; e += CC_WARP)
+            s_ego[e] = p.s_ego[static_cast<size_t>(trig) * 12 + e];
         if (lane == 0)
         {
-            // ego-box transform of the column (cpp:300-301), once per column
-            double inv[12], ego[12];
-            cc_iso_inverse(pose, inv);
-            cc_iso_mul(cfg.robot_from_sensor, inv, ego);
-            for (int i = 0; i < 12; i++)
-                s_ego[i] = ego[i];
             if (slot_before != -1)
             {
                 p.st->error = CC_DEV_COLUMN_NOT_CLEARED;
@@ -2163,7 +2519,13 @@ CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_
                 caz = s_caz[row];
             if (caz < min_az)
                 min_az = caz;
-            p.lab[cell] = make_uchar4(label, static_cast<unsigned char>(lab >> 8), ignored ? 1 : 0, s_int[row]);
+            const uchar4 packed = make_uchar4(label, static_cast<unsigned char>(lab >> 8), ignored ? 1 : 0, s_int[row]);
+            p.lab[cell] = packed;
+            if (d_labels && ci < label_cap)
+            {
+                d_labels[static_cast<size_t>(ci) * R + row] = packed;
+                h_labels[static_cast<size_t>(ci) * R + row] = packed;
+            }
             p.assoc[cell] = make_float4(ignored ? nanv : q.x, q.y, q.z, incl);
             p.mad[cell] = ignored ? 0.f : ccm::asinf_glibc(ccm::div_rn(cfg.max_distance, q.w));
             if (!ignored)
@@ -2970,6 +3332,7 @@ CC_DEV void d_restore(const CcGrid g, CcDevPtrs p)
         p.tfinish[r] = p.sv_tfinish[i];
         p.tmaxcol[r] = p.sv_tmaxcol[i];
         p.tnpoints[r] = p.sv_tnpoints[i];
+        p.tstate[r] = 0u; // list entries are unfinished trees (the fused kernel marks while it still decides)
     }
 }
 __global__ void k_restore(CcDevPtrs p)
@@ -3136,8 +3499,18 @@ __global__ void k_commit_roots(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, int 
     d_commit_roots(cc_grid(), cfg, p, ci0, ci1, spec);
 }
 
+CC_DEV unsigned int cc_tree_root(const unsigned int* tparent, unsigned int x)
+{
+    unsigned int r = cc_vload(tparent + x), n;
+    while ((n = cc_vload(tparent + r)) != r)
+        r = n;
+    return r;
+}
+
+// `chase`: the tree roots of both ends are found here (pointer chase to the fixed point) instead of being read from
+// tparent: the stage can then share a phase with d_commit_roots (whose pointer jumping only ever stores ancestors).
 CC_DEV void d_commit_links(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_parent, const unsigned int* s_links,
-                               int ci0, int ci1, int spec)
+                               int ci0, int ci1, int spec, bool chase = false)
 {
     CcTraceScope cc_trace_scope(p.trace, CC_KID_commit_links, g.bid);
     const CcHead hd = cc_head(p.st);
@@ -3162,7 +3535,8 @@ CC_DEV void d_commit_links(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsi
                 continue;
             const int ci = ci0 + cell / R, row = cell % R;
             const unsigned int q = static_cast<unsigned int>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row;
-            const unsigned int ra = cc_vload(p.tparent + q), rb = cc_vload(p.tparent + o);
+            const unsigned int ra = chase ? cc_tree_root(p.tparent, q) : cc_vload(p.tparent + q);
+            const unsigned int rb = chase ? cc_tree_root(p.tparent, o) : cc_vload(p.tparent + o);
             if (ra != rb)
                 cc_uf_union(p.cparent, ra, rb);
         }
@@ -3178,7 +3552,8 @@ CC_DEV void d_commit_links(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsi
             ci += cfg.ringcols;
         if (ci < ci0 || ci > ci1)
             continue;
-        const unsigned int ra = cc_vload(p.tparent + q), rb = cc_vload(p.tparent + o);
+        const unsigned int ra = chase ? cc_tree_root(p.tparent, q) : cc_vload(p.tparent + q);
+        const unsigned int rb = chase ? cc_tree_root(p.tparent, o) : cc_vload(p.tparent + o);
         if (ra != rb)
             cc_uf_union(p.cparent, ra, rb);
     }
@@ -3584,6 +3959,121 @@ CC_DEV void d_fin_mark(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, 
         }
     }
 }
+// Decision and marking in ONE phase (fused kernel, whole-push speculative commit only): every list entry derives its
+// component's decision from the representative's aggregates itself -- the same value for every member -- instead of
+// waiting a phase for the representative to publish it; only the representative allocates the cluster record. The roots
+// do not learn their cluster slot this way: d_fin_label(via_rep) looks it up through the representative.
+CC_DEV void d_fin_decide_mark(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq)
+{
+    if (!cc_spec_ok(p.st, 1))
+        return;
+    CcDevState* st = p.st;
+    const int n = st->n_ulist < p.cap_ulist ? st->n_ulist : p.cap_ulist;
+    const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = st->colbase, gbase = st->gbase;
+    const double* rmx = p.col_runmax;
+    const int tid = g.bid * blockDim.x + threadIdx.x, nt = g.nb * blockDim.x;
+    const int lane = threadIdx.x % CC_WARP;
+    const double rm_last = rmx[c1 - colbase];
+    for (int i0 = tid - lane; i0 < n; i0 += nt) // uniform per warp (compaction below)
+    {
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        long long finish_col = CC_COL_INF;
+        unsigned int root = CC_NONE;
+        long long gi = -1;
+        if (valid)
+        {
+            const int j = p.u_rep[i];
+            root = p.ulist[i];
+            const unsigned long long mf = p.u_maxfinish[j];
+            const long long maxend = p.u_maxend[j], mincol = p.u_mincol[j];
+            const unsigned int np = p.u_np[j];
+            gi = p.slot_gcol[root / cfg.R] - gbase;
+            const double F = cc_ord2d(mf);
+            bool bad = false;
+            if (maxend - mincol >= cfg.N)
+            {
+                // a partial component could be force-finished from column mincol + N - 1 on (cpp:909-919)
+                if (i == j)
+                {
+                    atomicMin(&st->danger_col, mincol + cfg.N - 1);
+                    st->abort = 1;
+                }
+                bad = true;
+            }
+            else if (rm_last >= F)
+            {
+                const long long lastcol = maxend - 1;
+                long long lo = lastcol > c0 ? lastcol : c0, hi = c1;
+                while (lo < hi) // first pass column c >= lo with runmax(c) >= F
+                {
+                    const long long mid = (lo + hi) >> 1;
+                    if (rmx[mid - colbase] >= F)
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+                if (!(p.col_minaz[lo - colbase] >= F))
+                {
+                    // the running maximum was reached before the component was complete while this column's own minimum
+                    // is still behind it: needs the exact pass-by-pass rule
+                    if (i == j)
+                    {
+                        st->abort = 1;
+                        atomicMin(&st->danger_col, lo);
+                    }
+                    bad = true;
+                }
+                else
+                    finish_col = lo;
+            }
+            if (!bad && finish_col != CC_COL_INF && i == j)
+            {
+                p.u_finishcol[i] = finish_col;
+                if (np > 5) // cpp:936-940
+                {
+                    const int slot = atomicAdd(&st->n_clusters, 1);
+                    const int off = atomicAdd(&st->n_cluster_points, static_cast<int>(np));
+                    if (slot < p.cap_clusters && off + static_cast<int>(np) <= p.cap_cluster_points)
+                    {
+                        CcCluster c;
+                        c.id = st->cluster_counter + static_cast<unsigned long long>(slot);
+                        c.min_stamp = ~0ull;
+                        c.max_stamp = 0ull;
+                        c.finish_col = finish_col;
+                        c.min_col = mincol;
+                        c.max_col = maxend - 1;
+                        c.num_points = np;
+                        c.point_offset = static_cast<unsigned int>(off);
+                        c.cursor = 0;
+                        c.pad_ = 0;
+                        p.clusters[slot] = c;
+                        p.u_cluster[i] = slot;
+                    }
+                    else
+                        st->error = CC_DEV_LIST_OVERFLOW;
+                }
+            }
+        }
+        const bool finished = valid && finish_col != CC_COL_INF;
+        if (finished)
+            p.tstate[root] = 1u + seq;
+        if (valid && gi >= 0 && gi < p.cap_G)
+            atomicMax(p.G + gi, finished ? finish_col : CC_COL_INF);
+        const bool keep = valid && !finished;
+        const unsigned int km = __ballot_sync(CC_FULL_MASK, keep);
+        if (km)
+        {
+            int pos0 = 0;
+            if (lane == __ffs(km) - 1)
+                pos0 = atomicAdd(p.n_new_ulist, __popc(km));
+            pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(km) - 1);
+            if (keep)
+                p.ulist_new[pos0 + __popc(km & ((1u << lane) - 1u))] = root;
+        }
+    }
+}
+
 CC_DEV void d_fin_copyback(const CcGrid g, const CcDevPtrs& p, int spec)
 {
     if (!cc_spec_ok(p.st, spec))
@@ -3814,8 +4304,11 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 // cell (up to a rotation of columns, whatever the size of the push) only the column spans [min_col, max_col] of the
 // clusters this push finished are visited; a cell inside the spans of several clusters is taken by the one it belongs
 // to. Falls back to the scan when the spans together are no smaller than the unpublished range.
+// `via_rep` (fused kernel: decision and marking share one phase, so the roots do not carry their cluster slot): the slot
+// is read from the component representative's list entry, the id from the cluster record. `h_points` (or null): member
+// list entries are also written straight to page-locked host memory (first `h_cap` entries).
 CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec, int* spans = nullptr,
-                        int span_cap = 0)
+                        int span_cap = 0, bool via_rep = false, CcClusterPoint* h_points = nullptr, int h_cap = 0)
 {
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label, g.bid);
     const CcHead hd = cc_head(p.st);
@@ -3903,12 +4396,12 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
                 const unsigned int root = p.tparent[cell];
                 if (root != CC_NONE && p.tstate[root] == 1u + seq)
                 {
-                    slot = p.tslot[root];
+                    slot = via_rep ? p.u_cluster[p.u_rep[p.rootslot[root]]] : p.tslot[root];
                     if (want >= 0 && slot != want)
                         slot = -1; // labelled by the work item of its own cluster's span
                     if (slot >= 0)
                     {
-                        p.cid[cell] = p.tid[root];
+                        p.cid[cell] = via_rep ? static_cast<unsigned int>(p.clusters[slot].id) : p.tid[root];
                         stamp = p.stamp[cell];
                     }
                 }
@@ -3942,6 +4435,8 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
                     cp.row = row;
                     cp.pad_ = 0;
                     p.cluster_points[c->point_offset + pos] = cp;
+                    if (h_points && c->point_offset + pos < static_cast<unsigned int>(h_cap))
+                        h_points[c->point_offset + pos] = cp;
                 }
             }
             remaining &= ~grp;
@@ -4211,13 +4706,28 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
     // ---- insertion (cpp:105-292) ----
     d_prep(g, cfg, p, n);
     cc_cluster_sync();
-    d_scan_lite(g, cfg, p, n);
+    d_lite_check_small(g, cfg, p, n);
     cc_cluster_sync();
-    d_scan_check(g, cfg, p, n);
-    cc_cluster_sync();
-    d_insert_scan(g, cfg, p, n, a.scan_chunk, 1);
-    cc_cluster_sync();
-    d_scatter(g, cfg, p, n);
+    if (p.st->scan_kbad >= n && g.nb > 1)
+    {
+        // the push is regular as a whole: the insertion scan only commits it (one CTA) and the scatter needs nothing
+        // from that commit -- side by side
+        if (g.bid == 0)
+            d_insert_scan(g, cfg, p, n, a.scan_chunk, 1);
+        else
+        {
+            CcGrid gs;
+            gs.bid = g.bid - 1;
+            gs.nb = g.nb - 1;
+            d_scatter(gs, cfg, p, n);
+        }
+    }
+    else
+    {
+        d_insert_scan(g, cfg, p, n, a.scan_chunk, 1);
+        cc_cluster_sync();
+        d_scatter(g, cfg, p, n);
+    }
     cc_cluster_sync();
     if (!a.has_tf)
     {
@@ -4231,39 +4741,37 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
         {
             const CcHead hd = cc_head(p.st);
             if (!hd.halted)
-            {
-                d_gap_main(g, cfg, p, hd);
-                cc_cluster_sync();
-                if (g.bid == 0)
-                    d_gap_tail(g, cfg, p, hd);
-            }
-            else
-                cc_cluster_sync();
+                d_gap_rows(g, cfg, p, hd);
         }
         cc_cluster_sync();
-        d_ground(g, cfg, p, a.s_parent);
+        d_ground(g, cfg, p, a.s_parent, a.pack_labels ? a.d_labels : nullptr, a.h_labels, a.cap_cols);
         cc_cluster_sync();
         // ---- association (cpp:638-835) ----
         d_probe(g, cfg, p, a.s_parent, a.s_links, a.spec);
         cc_cluster_sync();
-        d_probe_heavy(g, cfg, p, a.s_parent, a.s_links, a.tune, a.team_warps);
-        cc_cluster_sync();
+        if (p.st->n_heavy > 0) // (the same value in every CTA: read after the barrier)
+        {
+            d_probe_heavy(g, cfg, p, a.s_parent, a.s_links, a.tune, a.team_warps);
+            cc_cluster_sync();
+        }
         if (a.spec)
         {
             d_commit_copy(g, cfg, p, a.s_parent, 0, -1, 1);
             cc_cluster_sync();
+            // ---- tree roots + tree<->tree links in one phase (the links chase the roots themselves), together with the
+            //      initialisation of the finish pass ----
+            const bool fin = !p.st->halted;
+            if (fin)
+            {
+                CcTraceScope tr(p.trace, CC_KID_fin_init, g.bid);
+                d_fin_init(g, cfg, p, 0, -1, 1);
+            }
             d_commit_roots(g, cfg, p, 0, -1, 1);
-            cc_cluster_sync();
-            d_commit_links(g, cfg, p, a.s_parent, a.s_links, 0, -1, 1);
+            d_commit_links(g, cfg, p, a.s_parent, a.s_links, 0, -1, 1, true);
             cc_cluster_sync();
             // ---- finish detection (cpp:837-974), list phases over all CTAs ----
-            if (!p.st->halted)
+            if (fin)
             {
-                {
-                    CcTraceScope tr(p.trace, CC_KID_fin_init, g.bid);
-                    d_fin_init(g, cfg, p, 0, -1, 1);
-                }
-                cc_cluster_sync();
                 {
                     CcTraceScope tr(p.trace, CC_KID_fin_agg, g.bid);
                     d_fin_agg(g, cfg, p, 1);
@@ -4271,21 +4779,14 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
                 cc_cluster_sync();
                 {
                     CcTraceScope tr(p.trace, CC_KID_fin_decide, g.bid);
-                    d_fin_decide(g, cfg, p, 1, 0, nullptr);
+                    d_fin_decide_mark(g, cfg, p, a.seq);
                 }
                 cc_cluster_sync();
-                {
-                    CcTraceScope tr(p.trace, CC_KID_fin_mark, g.bid);
-                    d_fin_mark(g, cfg, p, a.seq, 1);
-                }
-                cc_cluster_sync();
-                {
-                    CcTraceScope tr(p.trace, CC_KID_fin_copyback, g.bid);
-                    d_fin_copyback(g, p, 1);
-                }
-                cc_cluster_sync();
-                // per-column first-unpublished + end-of-push bookkeeping in CTA 0, beside the labelling in the others
-                // (the labelling reads gbase / seg_c1 / n_clusters, which the tail does not modify)
+                // CTA 0: per-column first-unpublished + end-of-push bookkeeping; CTA 1: the compacted list goes back;
+                // the others label the members of the finished clusters (the labelling reads gbase / seg_c1 / n_clusters
+                // and the cluster records, which neither of the two modifies)
+                const int nlab = g.nb >= 4 ? g.nb - 2 : (g.nb >= 2 ? g.nb - 1 : 1);
+                const int first_lab = g.nb - nlab;
                 if (g.bid == 0)
                 {
                     CcTraceScope tr(p.trace, CC_KID_fin_columns, g.bid);
@@ -4293,19 +4794,24 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
                     __syncthreads();
                     if (threadIdx.x == 0)
                         d_push_done(p, 1);
+                    __syncthreads();
                 }
-                if (g.nb == 1 || g.bid != 0)
+                if (g.bid == (g.nb >= 4 ? 1 : 0))
                 {
-                    CcGrid gl = g;
-                    if (g.nb > 1)
-                    {
-                        gl.bid = g.bid - 1;
-                        gl.nb = g.nb - 1;
-                    }
+                    CcTraceScope tr(p.trace, CC_KID_fin_copyback, g.bid);
+                    CcGrid g1;
+                    g1.bid = 0;
+                    g1.nb = 1;
+                    d_fin_copyback(g1, p, 1);
+                }
+                if (g.bid >= first_lab)
+                {
+                    CcGrid gl;
+                    gl.bid = g.bid - first_lab;
+                    gl.nb = nlab;
                     CC_SMEM(smem_l);
-                    if (g.nb == 1)
-                        __syncthreads(); // CTA 0 did both: the tail's shared memory is free again
-                    d_fin_label(gl, cfg, p, a.seq, 1, reinterpret_cast<int*>(smem_l), 512);
+                    __syncthreads(); // (a CTA that also ran the tail: its shared memory is free again)
+                    d_fin_label(gl, cfg, p, a.seq, 1, reinterpret_cast<int*>(smem_l), 512, true, a.h_points, a.cap_points);
                 }
             }
             else if (g.bid == 0 && threadIdx.x == 0)
@@ -4314,8 +4820,13 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
         else if (g.bid == 0 && threadIdx.x == 0)
             d_halt(g, p, 0); // finish passes every n-th column: column-sequential path, on the host's cue
     }
+    // ---- results straight to the host: what is left after the stages wrote theirs (labels: d_ground, member lists:
+    //      d_fin_label) -- the per-column first-unpublished columns, and behind one more barrier (stamp ranges are final
+    //      once every labelling CTA is done) the cluster records and the state ----
+    // One system-scope fence for the whole push, by the thread that raises the flag: what the other CTAs wrote to host
+    // memory is ordered before it by the cluster barrier (release / acquire) and the fence's cumulativity.
     cc_cluster_sync();
-    // ---- results straight to the host ----
+    if (g.bid == 0)
     {
         CcTraceScope tr(p.trace, CC_KID_export, g.bid);
         const CcDevState* st = p.st;
@@ -4325,46 +4836,19 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
             int ncols = st->ncols < a.cap_cols ? st->ncols : a.cap_cols;
             ncols = ncols > 0 ? ncols : 0;
             const int ncl = st->n_clusters < a.cap_clusters ? st->n_clusters : a.cap_clusters;
-            const int ncp = st->n_cluster_points < a.cap_points ? st->n_cluster_points : a.cap_points;
-            const int gt = g.bid * blockDim.x + threadIdx.x, gn = g.nb * blockDim.x;
-            for (int i = gt; i < ncols; i += gn)
+            const int T = blockDim.x, t = threadIdx.x;
+            for (int i = t; i < ncols; i += T)
                 a.h_first_unpub[i] = p.col_first_unpub[i];
-            {
-                const int words = ncl * static_cast<int>(sizeof(CcCluster) / 8);
-                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.clusters);
-                unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.h_clusters);
-                for (int i = gt; i < words; i += gn)
-                    dst[i] = src[i];
-            }
-            {
-                static_assert(sizeof(CcClusterPoint) == 16, "copied as 16-byte words");
-                const uint4* src = reinterpret_cast<const uint4*>(p.cluster_points);
-                uint4* dst = reinterpret_cast<uint4*>(a.h_points);
-                for (int i = gt; i < ncp; i += gn)
-                    dst[i] = src[i];
-            }
-            if (a.pack_labels)
-            {
-                const long long colbase = st->colbase;
-                const int R = cfg.R;
-                const int total = ncols * R;
-                for (int i = gt; i < total; i += gn)
-                {
-                    const int ci = i / R, row = i - ci * R;
-                    const uchar4 l = p.lab[static_cast<size_t>(cc_local_col(colbase + ci, cfg.ringcols)) * R + row];
-                    a.d_labels[i] = l;
-                    a.h_labels[i] = l;
-                }
-            }
+            const int words = ncl * static_cast<int>(sizeof(CcCluster) / 8);
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.clusters);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.h_clusters);
+            for (int i = t; i < words; i += T)
+                dst[i] = src[i];
         }
-        if (g.bid == 0)
-        {
-            d_state_snapshot(p, a.snap);
-            d_state_snapshot(p, a.h_state);
-        }
-        cc_fence_system();
+        d_state_snapshot(p, a.snap);
+        d_state_snapshot(p, a.h_state);
+        __syncthreads();
     }
-    cc_cluster_sync();
     if (g.bid == 0 && threadIdx.x == 0)
     {
         a.h_hdr->t_start_ns = t_start;

@@ -177,6 +177,7 @@ struct CcDevPtrs
     float* s_az;
     float* s_incl;
     float* s_incaz;
+    double* s_ego;        // [max_firings][12] robot_from_sensor * odom_from_sensor^-1 of every firing (ego-box test)
     int* s_cwr;
     int* s_cwrT;          // the same, [row][max_firings]
     int* o_g;             // resolved global column relative to CcDevState::scan_base, INT_MIN = not stored
