@@ -81,6 +81,8 @@ class CcColumnFields(C.Structure):
             "xyz", "distance", "azimuth_angle", "inclination_angle", "continuous_azimuth_angle",
             "global_column_index", "stamp", "globally_unique_point_index", "firing_index", "intensity",
             "ground_point_label", "debug_ground_point_label", "is_ignored", "id", "tree_root_gcol", "tree_root_row",
+            "finished_at_continuous_azimuth_angle", "tree_num_points", "cluster_width", "number_of_visited_neighbors",
+            "first_parent_gcol", "first_parent_row", "belongs_to_finished_cluster",
         )
     ]
 
@@ -91,7 +93,21 @@ COLUMN_FIELD_DTYPES = {
     "globally_unique_point_index": ("<u8", 1), "firing_index": ("<u8", 1), "intensity": ("u1", 1),
     "ground_point_label": ("u1", 1), "debug_ground_point_label": ("u1", 1), "is_ignored": ("u1", 1),
     "id": ("<u8", 1), "tree_root_gcol": ("<i8", 1), "tree_root_row": ("<i4", 1),
+    "finished_at_continuous_azimuth_angle": ("<f8", 1), "tree_num_points": ("<u4", 1), "cluster_width": ("<u4", 1),
+    "number_of_visited_neighbors": ("<i4", 1), "first_parent_gcol": ("<i8", 1), "first_parent_row": ("<i4", 1),
+    "belongs_to_finished_cluster": ("u1", 1),
 }
+
+CELL_DTYPE = np.dtype([  # cc_cell_t (include/cc_b200.h): one packed record per cell, cc_export_columns
+    ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("distance", "<f4"), ("azimuth_angle", "<f4"), ("inclination_angle", "<f4"),
+    ("continuous_azimuth_angle", "<f8"), ("global_column_index", "<i8"), ("stamp", "<u8"),
+    ("globally_unique_point_index", "<u8"), ("firing_index", "<u8"), ("id", "<u8"),
+    ("finished_at_continuous_azimuth_angle", "<f8"), ("tree_root_gcol", "<i8"), ("first_parent_gcol", "<i8"),
+    ("tree_num_points", "<u4"), ("cluster_width", "<u4"), ("tree_root_row", "<i4"), ("first_parent_row", "<i4"),
+    ("number_of_visited_neighbors", "<u2"), ("pad0_", "<u2"), ("intensity", "u1"), ("ground_point_label", "u1"),
+    ("debug_ground_point_label", "u1"), ("is_ignored", "u1"), ("belongs_to_finished_cluster", "u1"), ("pad1_", "u1", (7,)),
+])
+assert CELL_DTYPE.itemsize == 128
 
 EVENT_DTYPE = np.dtype(
     [("from_gcol", "<i8"), ("to_gcol", "<i8"), ("ground_points_only", "<i4"), ("n_clusters_before", "<i4")]
@@ -117,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "cc_total_launches", "cc_selftest_math", "cc_set_kernel_timing", "cc_get_kernel_timings",
     "cc_debug_flag_columns", "cc_get_result_views", "cc_submit_firings", "cc_submit_firings_device", "cc_wait", "cc_pending",
     "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
-    "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times",
+    "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
 ]
 
 
@@ -152,6 +168,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         getattr(lib, name).argtypes = [vp, vp, i32, C.POINTER(i32)]
     lib.cc_get_result_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.cc_read_columns.argtypes = [vp, i64, i64, C.POINTER(CcColumnFields)]
+    lib.cc_export_columns.argtypes = [vp, i64, i64, C.POINTER(vp)]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]
     lib.cc_stream.argtypes = [vp]

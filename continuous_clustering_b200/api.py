@@ -324,6 +324,19 @@ class ContinuousClustering:
             out[n] = bufs[n]
         return out
 
+    def export_columns(self, from_gcol: int, to_gcol: int) -> np.ndarray:
+        """Cells of columns [from, to] (inclusive) as packed cc_cell_t records [n_cols, num_rows], gathered by one kernel
+        straight into a page-locked buffer of the handle (cc_export_columns); a VIEW, valid until the next
+        export_columns / read_columns call."""
+        ncols = max(0, to_gcol - from_gcol + 1)
+        rows = self.num_rows_
+        if ncols == 0:
+            return np.zeros((0, rows), dtype=_lib.CELL_DTYPE)
+        ptr = C.c_void_p()
+        self._check(self._L.cc_export_columns(self._h, from_gcol, to_gcol, C.byref(ptr)))
+        buf = (C.c_char * (ncols * rows * _lib.CELL_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=_lib.CELL_DTYPE, count=ncols * rows).reshape(ncols, rows)
+
     def set_label_prefetch(self, enable: bool):
         """Bring the labels of every push's new columns back with its results (cc_set_label_prefetch)."""
         self._check(self._L.cc_set_label_prefetch(self._h, int(enable)))

@@ -124,6 +124,8 @@ struct cc_handle
     cudaStream_t aux_stream{nullptr};
     std::vector<void*> allocs;       // freed on destroy / re-reset
     std::vector<void*> allocs_fixed; // independent of the ring size
+    CcCell* h_export{nullptr}; // page-locked: cells of the last cc_export_columns / cc_read_columns call
+    size_t export_cap{0};      // in cells
     CcDevState* h_state{nullptr}; // pinned mirror (reset, column-sequential path)
     CcDevState state{};
     unsigned int seq{0};
@@ -132,7 +134,8 @@ struct cc_handle
     int sm_count{148};
     // fused single-launch path for short pushes (k_push_fused): one thread-block cluster, inputs read from and results
     // written to page-locked host memory by the kernel itself
-    int fused_max{512};     // pushes of at most this many firings take it (CC_B200_FUSED_MAX; 0 = never)
+    int fused_max{384};     // pushes of at most this many firings take it (CC_B200_FUSED_MAX; 0 = never): measured
+                            // crossover with the kernel chain on a B200 at ~420 firings of 64 rows
     int fused_cluster{0};   // CTAs per cluster (0: not available on this device / configuration)
     int fused_threads{512};
     size_t fused_smem{0};
@@ -426,6 +429,8 @@ void cc_destroy(cc_handle_t* h)
         cudaStreamDestroy(h->aux_stream);
     if (h->h_state)
         cudaFreeHost(h->h_state);
+    if (h->h_export)
+        cudaFreeHost(h->h_export);
     if (h->d_trace)
         cudaFree(h->d_trace);
     if (h->ev0)
@@ -660,6 +665,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.assoc, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.mad, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.tparent, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.tfirst, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.cparent, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.tfinish, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.tmaxcol, cells));
@@ -1638,117 +1644,115 @@ cc_status_t cc_get_cluster_points(const cc_handle_t* h, cc_cluster_point_t* out,
     return CC_OK;
 }
 
-// what a caller reads from range_image_ inside a column callback (ros_utils.cpp:56-63, kitti_demo.cpp:183-216)
+// what a caller reads from range_image_ inside a column callback (ros_utils.cpp:56-63, kitti_demo.cpp:183-216): one
+// gather kernel writes packed records of the cells straight into a page-locked buffer of the handle
+cc_status_t cc_export_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_cell_t** cells)
+{
+    static_assert(sizeof(CcCell) == sizeof(cc_cell_t), "cell record layout");
+    if (!h || !cells || !h->is_reset)
+        return CC_ERR_INVALID_ARGUMENT;
+    *cells = nullptr;
+    if (to < from)
+        return CC_OK;
+    if (from < 0 || to - from + 1 > h->ringcols)
+    {
+        h->error = "cc_export_columns: range outside the ring";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const int ncols = static_cast<int>(to - from + 1);
+    const size_t n = static_cast<size_t>(ncols) * h->R;
+    if (n > h->export_cap)
+    {
+        if (h->h_export)
+            cudaFreeHost(h->h_export);
+        h->h_export = nullptr;
+        h->export_cap = 0;
+        const size_t cap = std::max<size_t>(n + n / 2, static_cast<size_t>(256) * h->R);
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_export), cap * sizeof(CcCell)));
+        h->export_cap = cap;
+    }
+    // reads run on their own stream: the host has already seen every finished push complete, and they must not queue
+    // behind the kernels of a push that is still in flight (which never touches columns already reported)
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    const int grid = std::max(1, std::min(h->sm_count * 8, static_cast<int>((n + 127) / 128)));
+    CC_LAUNCH(k_export_cells, grid, 128, 0, h->aux_stream, cfg, h->d, static_cast<long long>(from), ncols, h->h_export);
+    h->launches++;
+    CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
+    CC_CHECK(h, cudaGetLastError());
+    *cells = reinterpret_cast<const cc_cell_t*>(h->h_export);
+    return CC_OK;
+}
+
 cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_column_fields_t* f)
 {
     if (!h || !f || !h->is_reset)
         return CC_ERR_INVALID_ARGUMENT;
     if (to < from)
         return CC_OK;
-    if (from < 0 || to - from + 1 > h->ringcols)
+    const cc_cell_t* cells = nullptr;
+    cc_status_t s = cc_export_columns(h, from, to, &cells);
+    if (s != CC_OK)
     {
-        h->error = "cc_read_columns: range outside the ring";
-        return CC_ERR_INVALID_ARGUMENT;
+        if (h->error.rfind("cc_export_columns", 0) == 0)
+            h->error = "cc_read_columns: range outside the ring";
+        return s;
     }
-    CC_CHECK(h, cudaSetDevice(h->device));
-    // reads run on their own stream: the host has already seen every finished push complete, and they must not queue behind
-    // the kernels of a push that is still in flight (which never touches columns already reported)
-    const int R = h->R;
-    const int64_t ncols = to - from + 1;
-    const size_t cells = static_cast<size_t>(ncols) * R;
-    // the range may wrap around the end of the ring: at most two contiguous spans
-    const int64_t l0 = from % h->ringcols;
-    const int64_t n0 = std::min<int64_t>(ncols, h->ringcols - l0);
-    const int64_t n1 = ncols - n0;
-    auto rd = [&](void* dst, const void* src, size_t elem) -> cudaError_t
+    const size_t n = static_cast<size_t>(to - from + 1) * h->R;
+    for (size_t i = 0; i < n; i++)
     {
-        cudaError_t e = cudaMemcpyAsync(dst, static_cast<const char*>(src) + static_cast<size_t>(l0) * R * elem,
-                                        static_cast<size_t>(n0) * R * elem, cudaMemcpyDeviceToHost, h->aux_stream);
-        if (e == cudaSuccess && n1 > 0)
-            e = cudaMemcpyAsync(static_cast<char*>(dst) + static_cast<size_t>(n0) * R * elem, src,
-                                static_cast<size_t>(n1) * R * elem, cudaMemcpyDeviceToHost, h->aux_stream);
-        return e;
-    };
-    std::vector<float4> pos;
-    std::vector<uchar4> lab;
-    std::vector<unsigned int> u32;
-    std::vector<long long> slot(static_cast<size_t>(ncols));
-    if (f->xyz || f->distance || f->global_column_index)
-    {
-        pos.resize(cells);
-        CC_CHECK(h, rd(pos.data(), h->d.pos, sizeof(float4)));
-    }
-    if (f->intensity || f->ground_point_label || f->debug_ground_point_label || f->is_ignored)
-    {
-        lab.resize(cells);
-        CC_CHECK(h, rd(lab.data(), h->d.lab, sizeof(uchar4)));
-    }
-    {
-        // per-column tags
-        cudaError_t e = cudaMemcpyAsync(slot.data(), h->d.slot_gcol + l0, static_cast<size_t>(n0) * sizeof(long long),
-                                        cudaMemcpyDeviceToHost, h->aux_stream);
-        if (e == cudaSuccess && n1 > 0)
-            e = cudaMemcpyAsync(slot.data() + n0, h->d.slot_gcol, static_cast<size_t>(n1) * sizeof(long long),
-                                cudaMemcpyDeviceToHost, h->aux_stream);
-        CC_CHECK(h, e);
-    }
-    if (f->azimuth_angle)
-        CC_CHECK(h, rd(f->azimuth_angle, h->d.azimuth, sizeof(float)));
-    if (f->inclination_angle)
-        CC_CHECK(h, rd(f->inclination_angle, h->d.incl, sizeof(float)));
-    if (f->continuous_azimuth_angle)
-        CC_CHECK(h, rd(f->continuous_azimuth_angle, h->d.cont_az, sizeof(double)));
-    if (f->stamp)
-        CC_CHECK(h, rd(f->stamp, h->d.stamp, sizeof(uint64_t)));
-    if (f->globally_unique_point_index)
-        CC_CHECK(h, rd(f->globally_unique_point_index, h->d.guid, sizeof(uint64_t)));
-    if (f->firing_index)
-        CC_CHECK(h, rd(f->firing_index, h->d.firing_index, sizeof(uint64_t)));
-    std::vector<unsigned int> tpar;
-    if (f->id || f->tree_root_gcol || f->tree_root_row)
-    {
-        u32.resize(cells);
-        CC_CHECK(h, rd(u32.data(), h->d.cid, sizeof(unsigned int)));
-        tpar.resize(cells);
-        CC_CHECK(h, rd(tpar.data(), h->d.tparent, sizeof(unsigned int)));
-    }
-    CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
-    std::vector<long long> root_slot_gcol;
-    if (f->tree_root_gcol)
-    {
-        // global column of every tree root: one more small gather of the per-column tags
-        root_slot_gcol.resize(static_cast<size_t>(h->ringcols));
-        CC_CHECK(h, cudaMemcpyAsync(root_slot_gcol.data(), h->d.slot_gcol, root_slot_gcol.size() * sizeof(long long),
-                                    cudaMemcpyDeviceToHost, h->aux_stream));
-        CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
-    }
-    for (size_t i = 0; i < cells; i++)
-    {
-        const size_t col = i / R;
+        const cc_cell_t& c = cells[i];
         if (f->xyz)
         {
-            f->xyz[3 * i + 0] = pos[i].x;
-            f->xyz[3 * i + 1] = pos[i].y;
-            f->xyz[3 * i + 2] = pos[i].z;
+            f->xyz[3 * i + 0] = c.x;
+            f->xyz[3 * i + 1] = c.y;
+            f->xyz[3 * i + 2] = c.z;
         }
         if (f->distance)
-            f->distance[i] = pos[i].w;
-        if (f->global_column_index) // refilled by segmentation (cpp:347-350); -1 in cleared columns
-            f->global_column_index[i] = slot[col] == static_cast<long long>(from + static_cast<int64_t>(col)) ? slot[col] : -1;
+            f->distance[i] = c.distance;
+        if (f->azimuth_angle)
+            f->azimuth_angle[i] = c.azimuth_angle;
+        if (f->inclination_angle)
+            f->inclination_angle[i] = c.inclination_angle;
+        if (f->continuous_azimuth_angle)
+            f->continuous_azimuth_angle[i] = c.continuous_azimuth_angle;
+        if (f->global_column_index)
+            f->global_column_index[i] = c.global_column_index;
+        if (f->stamp)
+            f->stamp[i] = c.stamp;
+        if (f->globally_unique_point_index)
+            f->globally_unique_point_index[i] = c.globally_unique_point_index;
+        if (f->firing_index)
+            f->firing_index[i] = c.firing_index;
         if (f->intensity)
-            f->intensity[i] = lab[i].w;
+            f->intensity[i] = c.intensity;
         if (f->ground_point_label)
-            f->ground_point_label[i] = lab[i].x;
+            f->ground_point_label[i] = c.ground_point_label;
         if (f->debug_ground_point_label)
-            f->debug_ground_point_label[i] = lab[i].y;
+            f->debug_ground_point_label[i] = c.debug_ground_point_label;
         if (f->is_ignored)
-            f->is_ignored[i] = lab[i].z;
+            f->is_ignored[i] = c.is_ignored;
         if (f->id)
-            f->id[i] = u32[i];
+            f->id[i] = c.id;
         if (f->tree_root_gcol)
-            f->tree_root_gcol[i] = tpar[i] == CC_NONE ? -1 : root_slot_gcol[tpar[i] / R];
+            f->tree_root_gcol[i] = c.tree_root_gcol;
         if (f->tree_root_row)
-            f->tree_root_row[i] = tpar[i] == CC_NONE ? 0 : static_cast<int32_t>(tpar[i] % R);
+            f->tree_root_row[i] = c.tree_root_row;
+        if (f->finished_at_continuous_azimuth_angle)
+            f->finished_at_continuous_azimuth_angle[i] = c.finished_at_continuous_azimuth_angle;
+        if (f->tree_num_points)
+            f->tree_num_points[i] = c.tree_num_points;
+        if (f->cluster_width)
+            f->cluster_width[i] = c.cluster_width;
+        if (f->number_of_visited_neighbors)
+            f->number_of_visited_neighbors[i] = c.number_of_visited_neighbors;
+        if (f->first_parent_gcol)
+            f->first_parent_gcol[i] = c.first_parent_gcol;
+        if (f->first_parent_row)
+            f->first_parent_row[i] = c.first_parent_row;
+        if (f->belongs_to_finished_cluster)
+            f->belongs_to_finished_cluster[i] = c.belongs_to_finished_cluster;
     }
     return CC_OK;
 }

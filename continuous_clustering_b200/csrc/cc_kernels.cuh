@@ -3383,6 +3383,7 @@ CC_DEV void d_commit_copy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, const unsig
             q = static_cast<unsigned int>(cc_local_col(gcol, cfg.ringcols)) * R + row;
             const unsigned int par = s_parent[static_cast<size_t>(ci) * R + row];
             p.tparent[q] = par;
+            p.tfirst[q] = par; // the point whose child list the reference appends this one to (cpp:663)
             if (par == q) // new point tree (cpp:808-826)
             {
                 is_root = true;
@@ -3585,6 +3586,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
     {
         const unsigned int q = static_cast<unsigned int>(local) * R + row;
         p.tparent[q] = CC_NONE;
+        p.tfirst[q] = CC_NONE;
         p.visited[q] = 0;
     }
     for (int row = 0; row < R; row++)
@@ -3632,6 +3634,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
                                     {
                                         root = ro;
                                         p.tparent[q] = ro;
+                                        p.tfirst[q] = o; // cpp:663
                                         p.tmaxcol[ro] = gcol;
                                         const unsigned long long f = cc_d2ord(my_finish);
                                         if (f > p.tfinish[ro])
@@ -3662,6 +3665,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
         if (root == CC_NONE)
         {
             p.tparent[q] = q;
+            p.tfirst[q] = q;
             p.cparent[q] = q;
             p.tfinish[q] = cc_d2ord(my_finish);
             p.tmaxcol[q] = gcol;
@@ -4481,6 +4485,7 @@ CC_DEV void d_clear(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, lon
         p.assoc[cell] = make_float4(nanv, nanv, nanv, nanv);
         p.mad[cell] = 0.f;
         p.tparent[cell] = CC_NONE;
+        p.tfirst[cell] = CC_NONE;
         p.cid[cell] = 0u;
         p.visited[cell] = 0;
         p.tstate[cell] = 0u;
@@ -4855,6 +4860,92 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
         a.h_hdr->t_end_ns = cc_globaltimer();
         cc_fence_system();
         *reinterpret_cast<volatile unsigned int*>(&a.h_hdr->flag) = a.ticket;
+    }
+}
+
+// =====================================================================================================
+// K6  publish side: what callers read from `range_image_` inside the callbacks, gathered ON THE DEVICE.
+//     k_export_cells   every field of `Point` (hpp:126-161) of the cells of a column range as one packed 128-byte record
+//                      per cell, written straight to page-locked host memory: replaces 16 field-wise copies + a host
+//                      scatter per cc_read_columns call.
+// =====================================================================================================
+struct alignas(16) CcCell // == cc_cell_t (include/cc_b200.h)
+{
+    float x, y, z, distance;
+    float azimuth_angle, inclination_angle;
+    double continuous_azimuth_angle;
+    long long global_column_index; // -1 in columns that have not been segmented (cleared value, cpp:1117)
+    unsigned long long stamp, globally_unique_point_index, firing_index;
+    unsigned long long id;
+    double finished_at_continuous_azimuth_angle; // tree roots only, else 0 (cleared value)
+    long long tree_root_gcol;                    // -1 = not associated
+    long long first_parent_gcol;                 // the point whose child_points list holds this point (cpp:663), -1 = none
+    unsigned int tree_num_points, cluster_width; // tree roots only
+    int tree_root_row, first_parent_row;
+    unsigned short number_of_visited_neighbors, pad0_;
+    unsigned char intensity, ground_point_label, debug_ground_point_label, is_ignored;
+    unsigned char belongs_to_finished_cluster, pad1_[7];
+};
+static_assert(sizeof(CcCell) == 128, "cc_cell_t layout");
+
+CC_DEV CcCell cc_gather_cell(const CcDevCfg& cfg, const CcDevPtrs& p, long long gcol, int row)
+{
+    const int R = cfg.R;
+    const int local = cc_local_col(gcol, cfg.ringcols);
+    const size_t cell = static_cast<size_t>(local) * R + row;
+    CcCell c;
+    const float4 q = p.pos[cell];
+    const uchar4 l = p.lab[cell];
+    c.x = q.x;
+    c.y = q.y;
+    c.z = q.z;
+    c.distance = q.w;
+    c.azimuth_angle = p.azimuth[cell];
+    c.inclination_angle = p.incl[cell];
+    c.continuous_azimuth_angle = p.cont_az[cell];
+    c.global_column_index = p.slot_gcol[local] == gcol ? gcol : -1; // refilled by segmentation (cpp:347-350)
+    c.stamp = p.stamp[cell];
+    c.globally_unique_point_index = p.guid[cell];
+    c.firing_index = p.firing_index[cell];
+    c.id = p.cid[cell];
+    const unsigned int root = p.tparent[cell];
+    const bool is_root = root == static_cast<unsigned int>(cell);
+    c.finished_at_continuous_azimuth_angle = is_root ? cc_ord2d(p.tfinish[cell]) : 0.0;
+    c.tree_root_gcol = root == CC_NONE ? -1 : p.slot_gcol[root / R];
+    c.tree_root_row = root == CC_NONE ? 0 : static_cast<int>(root % R);
+    const unsigned int fp = p.tfirst[cell];
+    const bool has_parent = fp != CC_NONE && fp != static_cast<unsigned int>(cell) && root != CC_NONE;
+    c.first_parent_gcol = has_parent ? p.slot_gcol[fp / R] : -1;
+    c.first_parent_row = has_parent ? static_cast<int>(fp % R) : 0;
+    c.tree_num_points = is_root ? p.tnpoints[cell] : 0u;
+    c.cluster_width = is_root ? static_cast<unsigned int>(p.tmaxcol[cell] - gcol + 1) : 0u;
+    c.number_of_visited_neighbors = p.visited[cell];
+    c.pad0_ = 0;
+    c.intensity = l.w;
+    c.ground_point_label = l.x;
+    c.debug_ground_point_label = l.y;
+    c.is_ignored = l.z;
+    c.belongs_to_finished_cluster = is_root && p.tstate[cell] != 0u ? 1 : 0;
+    for (int i = 0; i < 7; i++)
+        c.pad1_[i] = 0;
+    return c;
+}
+
+__global__ void k_export_cells(CcDevCfg cfg, CcDevPtrs p, long long from, int ncols, CcCell* out)
+{
+    const long long total = static_cast<long long>(ncols) * cfg.R;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long ci = i / cfg.R;
+        const int row = static_cast<int>(i - ci * cfg.R);
+        const CcCell c = cc_gather_cell(cfg, p, from + ci, row);
+        // one full 128-byte line per thread
+        const uint4* src = reinterpret_cast<const uint4*>(&c);
+        uint4* dst = reinterpret_cast<uint4*>(out + i);
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+            dst[w] = src[w];
     }
 }
 

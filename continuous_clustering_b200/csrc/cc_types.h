@@ -155,6 +155,7 @@ struct CcDevPtrs
     float4* assoc; // association view written by segmentation: x (NaN when is_ignored), y, z, inclination
     float* mad;    // asinf(max_distance / distance) of non-ignored cells (cpp:805), else 0
     unsigned int* tparent; // point tree: first-hit parent while probing, tree root once committed (tree_root_)
+    unsigned int* tfirst;  // the first hit of the walk: the point whose child_points list holds this point (cpp:663)
     unsigned int* cparent; // union-find over tree roots (replaces associated_trees, hpp:149)
     unsigned long long* tfinish; // root: finished_at_continuous_azimuth_angle as ordered bits (hpp:146)
     long long* tmaxcol;          // root: last global column of the tree (root col + cluster_width - 1)

@@ -304,66 +304,57 @@ void ContinuousClustering::flush()
     }
 }
 
-// host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63)
+// host copies of columns [from, to] into range_image_ (what the reference's consumers index, ros_utils.cpp:56-63): one
+// device-side gather of packed cell records (cc_export_columns), then a single pass that fills every `Point` member
+// the callers read (ros_utils.cpp:245-298, kitti_demo.cpp:196-216)
 void ContinuousClustering::materialise(int64_t from, int64_t to)
 {
     if (to < from)
         return;
-    const size_t ncols = static_cast<size_t>(to - from + 1), R = static_cast<size_t>(num_rows_), n = ncols * R;
-    std::vector<float> xyz(3 * n), dist(n), az(n), incl(n);
-    std::vector<double> caz(n);
-    std::vector<int64_t> gcol(n), root_gcol(n);
-    std::vector<uint64_t> stamp(n), guid(n), fidx(n), id(n);
-    std::vector<uint8_t> intensity(n), label(n), dbg(n), ign(n);
-    std::vector<int32_t> root_row(n);
-    cc_column_fields_t f{};
-    f.xyz = xyz.data();
-    f.distance = dist.data();
-    f.azimuth_angle = az.data();
-    f.inclination_angle = incl.data();
-    f.continuous_azimuth_angle = caz.data();
-    f.global_column_index = gcol.data();
-    f.stamp = stamp.data();
-    f.globally_unique_point_index = guid.data();
-    f.firing_index = fidx.data();
-    f.intensity = intensity.data();
-    f.ground_point_label = label.data();
-    f.debug_ground_point_label = dbg.data();
-    f.is_ignored = ign.data();
-    f.id = id.data();
-    f.tree_root_gcol = root_gcol.data();
-    f.tree_root_row = root_row.data();
-    int s = cc_read_columns(handle_, from, to, &f);
+    const size_t R = static_cast<size_t>(num_rows_);
+    // children sit at most max_steps_in_row columns ahead of their parent (cpp:704-705): the child lists of [from, to]
+    // need the parent pointers of that many more columns (as far as they have been associated yet)
+    const int64_t ahead = std::max(0, config_.clustering.max_steps_in_row);
+    const int64_t last = std::max(to, std::min(to + ahead, ring_buffer_end_global_column_index));
+    const cc_cell_t* cells = nullptr;
+    int s = cc_export_columns(handle_, from, last, &cells);
     if (s != CC_OK)
         fail(s);
+    const size_t ncols = static_cast<size_t>(to - from + 1), ncols_ext = static_cast<size_t>(last - from + 1);
     for (size_t c = 0; c < ncols; c++)
     {
         const int local = static_cast<int>((from + static_cast<int64_t>(c)) % ring_buffer_max_columns);
         for (size_t r = 0; r < R; r++)
         {
-            const size_t i = c * R + r;
+            const cc_cell_t& q = cells[c * R + r];
             Point& p = range_image_[static_cast<size_t>(local) * R + r];
-            p.xyz = Point3D(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-            p.firing_index = fidx[i];
-            p.intensity = intensity[i];
-            p.distance = dist[i];
-            p.azimuth_angle = az[i];
-            p.inclination_angle = incl[i];
-            p.continuous_azimuth_angle = caz[i];
-            p.global_column_index = gcol[i];
-            p.local_column_index = gcol[i] >= 0 ? local : -1;
-            p.row_index = std::isnan(dist[i]) ? -1 : static_cast<int>(r); // set by insertion only (cpp:235)
-            p.stamp = stamp[i];
-            p.globally_unique_point_index = guid[i];
-            p.ground_point_label = label[i];
-            p.debug_ground_point_label = dbg[i];
-            p.is_ignored = ign[i] != 0;
-            p.id = id[i];
-            if (root_gcol[i] >= 0)
+            p.xyz = Point3D(q.x, q.y, q.z);
+            p.firing_index = q.firing_index;
+            p.intensity = q.intensity;
+            p.distance = q.distance;
+            p.azimuth_angle = q.azimuth_angle;
+            p.inclination_angle = q.inclination_angle;
+            p.continuous_azimuth_angle = q.continuous_azimuth_angle;
+            p.global_column_index = q.global_column_index;
+            p.local_column_index = q.global_column_index >= 0 ? local : -1;
+            p.row_index = std::isnan(q.distance) ? -1 : static_cast<int>(r); // set by insertion only (cpp:235)
+            p.stamp = q.stamp;
+            p.globally_unique_point_index = q.globally_unique_point_index;
+            p.ground_point_label = q.ground_point_label;
+            p.debug_ground_point_label = q.debug_ground_point_label;
+            p.is_ignored = q.is_ignored != 0;
+            p.id = q.id;
+            p.finished_at_continuous_azimuth_angle = q.finished_at_continuous_azimuth_angle;
+            p.tree_num_points = q.tree_num_points;
+            p.cluster_width = q.cluster_width;
+            p.number_of_visited_neighbors = q.number_of_visited_neighbors;
+            p.belongs_to_finished_cluster = q.belongs_to_finished_cluster != 0;
+            p.child_points.clear();
+            if (q.tree_root_gcol >= 0)
             {
-                p.tree_root_ = RangeImageIndex(static_cast<uint16_t>(root_row[i]),
-                                               static_cast<int64_t>(root_gcol[i] % ring_buffer_max_columns));
-                p.tree_id = static_cast<uint64_t>(root_gcol[i]) * R + static_cast<uint64_t>(root_row[i]);
+                p.tree_root_ = RangeImageIndex(static_cast<uint16_t>(q.tree_root_row),
+                                               static_cast<int64_t>(q.tree_root_gcol % ring_buffer_max_columns));
+                p.tree_id = static_cast<uint64_t>(q.tree_root_gcol) * R + static_cast<uint64_t>(q.tree_root_row);
             }
             else
             {
@@ -372,6 +363,19 @@ void ContinuousClustering::materialise(int64_t from, int64_t to)
             }
         }
     }
+    // child_points (cpp:663): every associated point names the point whose list holds it; appended in association order
+    // (column by column, rows top to bottom), which is the order the reference's lists have
+    for (size_t c = 0; c < ncols_ext; c++)
+        for (size_t r = 0; r < R; r++)
+        {
+            const cc_cell_t& q = cells[c * R + r];
+            if (q.first_parent_gcol < from || q.first_parent_gcol > to)
+                continue;
+            const int parent_local = static_cast<int>(q.first_parent_gcol % ring_buffer_max_columns);
+            const int child_local = static_cast<int>((from + static_cast<int64_t>(c)) % ring_buffer_max_columns);
+            range_image_[static_cast<size_t>(parent_local) * R + static_cast<size_t>(q.first_parent_row)].child_points.emplace_back(
+                static_cast<uint16_t>(r), static_cast<int64_t>(child_local));
+        }
 }
 
 // callbacks of the last push, in the order of the reference's single-threaded mode

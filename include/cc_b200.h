@@ -182,7 +182,37 @@ typedef struct cc_column_fields
     uint64_t* id;                      /* Point::id (0 = not part of a published cluster)      */
     int64_t* tree_root_gcol;           /* global column of Point::tree_root_ (-1 = none)       */
     int32_t* tree_root_row;            /* Point::tree_root_.row_index                          */
+    /* clustering bookkeeping the ROS node publishes (ros_utils.cpp:287-298) */
+    double* finished_at_continuous_azimuth_angle; /* tree roots: Point::finished_at_continuous_azimuth_angle, else 0 */
+    uint32_t* tree_num_points;         /* tree roots: Point::tree_num_points, else 0           */
+    uint32_t* cluster_width;           /* tree roots: Point::cluster_width, else 0             */
+    int32_t* number_of_visited_neighbors; /* Point::number_of_visited_neighbors                */
+    int64_t* first_parent_gcol;        /* the point whose child_points holds this one (cpp:663): global column, -1 none */
+    int32_t* first_parent_row;
+    uint8_t* belongs_to_finished_cluster; /* tree roots: Point::belongs_to_finished_cluster    */
 } cc_column_fields_t;
+
+/* Every field of one range-image cell (`Point`, hpp:126-161) as the device packs it: 128 bytes, one record per cell in
+ * the reference's cell order (column by column, row 0 = top laser). Cleared / never-written cells hold the reference's
+ * cleared values (cpp:1110-1142). child_points are represented by their inverse: first_parent_* names the point whose
+ * list holds this point (children are at most max_steps_in_row columns ahead of their parent). */
+typedef struct cc_cell
+{
+    float x, y, z, distance;
+    float azimuth_angle, inclination_angle;
+    double continuous_azimuth_angle;
+    int64_t global_column_index;
+    uint64_t stamp, globally_unique_point_index, firing_index;
+    uint64_t id;
+    double finished_at_continuous_azimuth_angle;
+    int64_t tree_root_gcol;
+    int64_t first_parent_gcol;
+    uint32_t tree_num_points, cluster_width;
+    int32_t tree_root_row, first_parent_row;
+    uint16_t number_of_visited_neighbors, pad0_;
+    uint8_t intensity, ground_point_label, debug_ground_point_label, is_ignored;
+    uint8_t belongs_to_finished_cluster, pad1_[7];
+} cc_cell_t;
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 
@@ -267,6 +297,11 @@ CC_API cc_status_t cc_get_column_labels(const cc_handle_t* h, const uint8_t** la
  * kitti_demo.cpp:183-216). Only valid for columns still inside the ring. */
 CC_API cc_status_t cc_read_columns(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol,
                                    const cc_column_fields_t* fields);
+
+/* The same cells as packed records, gathered by ONE kernel that writes straight into a page-locked buffer of the
+ * handle (the publish side on the device): *cells points at (to - from + 1) * num_rows records, valid until
+ * the next cc_export_columns / cc_read_columns call on the handle. This is what the facade fills `range_image_` from. */
+CC_API cc_status_t cc_export_columns(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol, const cc_cell_t** cells);
 
 /* Public data members of the reference object (hpp:244-251). */
 CC_API int cc_num_rows(const cc_handle_t* h);

@@ -147,6 +147,12 @@ static void snapshotCell(const ContinuousClustering& cc, const Point& p, drv_cel
     c.ground_point_label = p.ground_point_label;
     c.debug_ground_point_label = p.debug_ground_point_label;
     c.is_ignored = p.is_ignored ? 1 : 0;
+    c.num_child_points = static_cast<int32_t>(p.child_points.size());
+    c.finished_at_continuous_azimuth_angle = p.finished_at_continuous_azimuth_angle;
+    c.tree_num_points = p.tree_num_points;
+    c.cluster_width = p.cluster_width;
+    c.local_column_index = p.local_column_index;
+    c.row_index = p.row_index;
     c.tree_root_row = p.tree_root_.row_index;
     c.tree_root_gcol = -1;
     if (p.tree_root_.column_index >= 0)

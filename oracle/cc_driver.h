@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct drv drv_t;
 
-/* Snapshot of one range-image cell taken inside a finished-column callback. 96 bytes. */
+/* Snapshot of one range-image cell taken inside a finished-column callback. 120 bytes. */
 typedef struct drv_cell
 {
     double continuous_azimuth_angle;
@@ -45,7 +45,12 @@ typedef struct drv_cell
     uint8_t ground_point_label;
     uint8_t debug_ground_point_label;
     uint8_t is_ignored;
-    uint32_t pad_;
+    int32_t num_child_points; /* child_points.size() */
+    double finished_at_continuous_azimuth_angle;
+    uint32_t tree_num_points;
+    uint32_t cluster_width;
+    int32_t local_column_index;
+    int32_t row_index;
 } drv_cell_t;
 
 typedef struct drv_cluster

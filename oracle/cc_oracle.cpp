@@ -119,6 +119,7 @@ struct Cell // mirror of `Point` hpp:126-161, flat
     uint64_t tree_id, id;
     uint8_t finished; // belongs_to_finished_cluster
     int visited;      // number_of_visited_neighbors
+    int num_children; // child_points.size() (cpp:663)
     uint32_t link_parent; // union-find over tree roots (replaces associated_trees)
     uint32_t next_in_tree, tree_tail; // intrusive member list of a tree (replaces child_points)
     uint64_t pass_id;   // per-pass scratch (replaces visited_at_continuous_azimuth_angle)
@@ -193,6 +194,7 @@ struct drv
                 c.id = 0;
                 c.finished = 0;
                 c.visited = 0;
+                c.num_children = 0;
                 c.link_parent = NONE;
                 c.next_in_tree = NONE;
                 c.tree_tail = NONE;
@@ -264,6 +266,12 @@ struct drv
         c.ground_point_label = p.label;
         c.debug_ground_point_label = p.dbg;
         c.is_ignored = p.ignored;
+        c.num_child_points = p.num_children;
+        c.finished_at_continuous_azimuth_angle = p.finished_at;
+        c.tree_num_points = p.tree_num_points;
+        c.cluster_width = p.cluster_width;
+        c.local_column_index = p.local_col;
+        c.row_index = p.row;
         c.tree_root_row = p.root_row;
         c.tree_root_gcol = -1;
         if (p.root_col >= 0)
@@ -664,6 +672,7 @@ struct drv
                                     p.tree_id = root.gcol * R + root.row;
                                     ring[root.tree_tail].next_in_tree = p_index;
                                     root.tree_tail = p_index;
+                                    o.num_children++; // point_other.child_points.emplace_back(...) cpp:663
                                     root.cluster_width = new_width;
                                     root.finished_at = std::max(root.finished_at, p.cont_az + mad);
                                     root.tree_num_points++;

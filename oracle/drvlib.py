@@ -150,10 +150,15 @@ CELL_DTYPE = np.dtype(
         ("ground_point_label", "u1"),
         ("debug_ground_point_label", "u1"),
         ("is_ignored", "u1"),
-        ("pad_", "<u4"),
+        ("num_child_points", "<i4"),
+        ("finished_at_continuous_azimuth_angle", "<f8"),
+        ("tree_num_points", "<u4"),
+        ("cluster_width", "<u4"),
+        ("local_column_index", "<i4"),
+        ("row_index", "<i4"),
     ]
 )
-assert CELL_DTYPE.itemsize == 96
+assert CELL_DTYPE.itemsize == 120
 
 CLUSTER_DTYPE = np.dtype(
     [("stamp", "<u8"), ("id", "<u8"), ("point_offset", "<i8"), ("num_points", "<i8"), ("event_index", "<i8")]

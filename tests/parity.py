@@ -14,6 +14,9 @@ EXACT_CELL_FIELDS = [
     "ground_point_label", "debug_ground_point_label", "is_ignored",
 ]
 TREE_FIELDS = ["tree_root_gcol", "tree_root_row", "number_of_visited_neighbors"]
+# per-tree bookkeeping the ROS node publishes (ros_utils.cpp:287-298), final once a column is published as clustered
+PUBLISHED_TREE_FIELDS = ["tree_root_gcol", "tree_root_row", "finished_at_continuous_azimuth_angle", "tree_num_points",
+                         "cluster_width", "num_child_points", "local_column_index", "row_index"]
 
 
 def record(driver, pts, poses, chunk=None):
@@ -68,7 +71,7 @@ def cluster_multiset(rec):
     return sorted(out)
 
 
-def compare(a, b, check_tree_fields=False, name_a="a", name_b="b"):
+def compare(a, b, check_tree_fields=False, name_a="a", name_b="b", check_published_tree_fields=False):
     """Raises AssertionError with a readable message on the first difference."""
     assert a["reset_required"] == b["reset_required"], "reset_required differs"
     ea, eb = a["events"], b["events"]
@@ -82,6 +85,8 @@ def compare(a, b, check_tree_fields=False, name_a="a", name_b="b"):
         assert np.array_equal(ca, cb), f"{kind} column list differs"
         xa, xb = a[kind + "_cells"], b[kind + "_cells"]
         fields = list(EXACT_CELL_FIELDS) + (TREE_FIELDS if check_tree_fields and kind == "cluster" else [])
+        if check_published_tree_fields and kind == "cluster":
+            fields += [f for f in PUBLISHED_TREE_FIELDS if f not in fields]
         for f in fields:
             ba, bb = _bits(xa[f]), _bits(xb[f])
             if f in ("continuous_azimuth_angle", "x", "y", "z", "distance", "azimuth_angle", "inclination_angle"):

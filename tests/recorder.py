@@ -12,16 +12,34 @@ _MAP = {  # drv_cell_t field -> cc_read_columns field
     "id": "id", "tree_root_gcol": "tree_root_gcol", "distance": "distance", "azimuth_angle": "azimuth_angle",
     "inclination_angle": "inclination_angle", "tree_root_row": "tree_root_row", "intensity": "intensity",
     "ground_point_label": "ground_point_label", "debug_ground_point_label": "debug_ground_point_label",
-    "is_ignored": "is_ignored",
+    "is_ignored": "is_ignored", "number_of_visited_neighbors": "number_of_visited_neighbors",
+    "finished_at_continuous_azimuth_angle": "finished_at_continuous_azimuth_angle", "tree_num_points": "tree_num_points",
+    "cluster_width": "cluster_width", "x": "x", "y": "y", "z": "z",
 }
 
 
-def _to_cells(cols):
-    out = np.zeros(cols.shape, dtype=drvlib.CELL_DTYPE)
+def _to_cells(cells, ring_buffer_max_columns):
+    """cc_cell_t records (cc_export_columns) -> the recording driver's drv_cell_t."""
+    out = np.zeros(cells.shape, dtype=drvlib.CELL_DTYPE)
     for k, v in _MAP.items():
-        out[k] = cols[v]
-    out["x"], out["y"], out["z"] = cols["xyz"][..., 0], cols["xyz"][..., 1], cols["xyz"][..., 2]
+        out[k] = cells[v]
+    # what the facade derives for `Point` (facade/src/continuous_clustering.cpp materialise())
+    g = cells["global_column_index"]
+    out["local_column_index"] = np.where(g >= 0, g % ring_buffer_max_columns, -1)
+    out["row_index"] = np.where(np.isnan(cells["distance"]), -1, np.arange(cells.shape[1])[None, :])
     return out
+
+
+def child_counts(cc, lo, hi, max_steps_in_row=20):
+    """child_points.size() of the cells of columns [lo, hi]: children name their parent (first_parent_*), and sit at most
+    max_steps_in_row columns ahead of it."""
+    ext = cc.export_columns(lo, hi + max_steps_in_row).copy()
+    rows = ext.shape[1]
+    cnt = np.zeros((hi - lo + 1, rows), dtype=np.int32)
+    pg, pr = ext["first_parent_gcol"], ext["first_parent_row"]
+    sel = (pg >= lo) & (pg <= hi)
+    np.add.at(cnt, (pg[sel] - lo, pr[sel]), 1)
+    return cnt
 
 
 def record(cc, pts, poses, chunk, pipelined=False):
@@ -53,13 +71,14 @@ def record(cc, pts, poses, chunk, pipelined=False):
         g = ev[ev["ground_points_only"] == 1]
         if len(g):
             lo, hi = int(g["from_gcol"].min()), int(g["to_gcol"].max())
-            cells = _to_cells(cc.read_columns(lo, hi))
+            cells = _to_cells(cc.export_columns(lo, hi), cc.ring_buffer_max_columns)
             gcols.append(np.arange(lo, hi + 1))
             gcells.append(cells)
         c = ev[(ev["ground_points_only"] == 0) & (ev["to_gcol"] >= ev["from_gcol"])]
         if len(c):
             lo, hi = int(c["from_gcol"].min()), int(c["to_gcol"].max())
-            cells = _to_cells(cc.read_columns(lo, hi))
+            cells = _to_cells(cc.export_columns(lo, hi), cc.ring_buffer_max_columns)
+            cells["num_child_points"] = child_counts(cc, lo, hi)
             ccols.append(np.arange(lo, hi + 1))
             ccells.append(cells)
         # finished clusters the reference would hand to the callback (> 20 points, cpp:1023), with the number of

@@ -60,7 +60,7 @@ def test_oracle_matches_reference_build(oracle_lib, ref_lib, spec, kw, cfg_over)
     cfg = drvlib.stream_config(spec, **cfg_over)
     want = run_driver(ref_lib, pts, poses, sp, cfg)
     got = run_driver(oracle_lib, pts, poses, sp, cfg)
-    parity.compare(want, got, check_tree_fields=True, name_a="reference", name_b="oracle")
+    parity.compare(want, got, check_tree_fields=True, name_a="reference", name_b="oracle", check_published_tree_fields=True)
     assert np.array_equal(want["cluster_cells"]["id"], got["cluster_cells"]["id"])
 
 
