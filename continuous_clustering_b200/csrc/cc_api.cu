@@ -577,6 +577,7 @@ static void configure_fused(cc_handle* h)
     smem = std::max(smem, warps * cc_ground_warp_bytes(R));
     smem = std::max(smem, h->probe_smem);
     smem = std::max(smem, cc_heavy_smem_bytes(T, 2));
+    smem = std::max(smem, static_cast<size_t>(warps) * CC_PROBE_PIPE * CC_WARP * sizeof(float4)); // d_visited_fix
     smem = std::max(smem, static_cast<size_t>(T) * 8 + static_cast<size_t>(h->d.cap_G) * sizeof(int));
     smem = std::max(smem, static_cast<size_t>(2 * 512 * sizeof(int)));
     if (smem > 200 * 1024)
@@ -676,6 +677,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
         CC_CHECK(h, dev_alloc(h, L, &d.rootslot, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.cid, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.visited, cells));
+        CC_CHECK(h, dev_alloc(h, L, &d.vback, cells));
         CC_CHECK(h, dev_alloc(h, L, &d.slot_gcol, static_cast<size_t>(h->ringcols)));
         CC_CHECK(h, dev_alloc(h, L, &d.rowmax, static_cast<size_t>(h->R)));
         CC_CHECK(h, dev_alloc(h, L, &d.s_pos, stage));
@@ -931,7 +933,7 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
     }
 #endif
     CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
-    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
+    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, seq, guard);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)

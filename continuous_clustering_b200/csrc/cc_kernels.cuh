@@ -2534,6 +2534,7 @@ CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_
             {
                 s_parent[static_cast<size_t>(ci) * R + row] = CC_NONE;
                 p.visited[cell] = 0;
+                p.vback[cell] = 0;
             }
         }
         // the column's non-ignored points join the list the association probe works through (one atomic per column)
@@ -2638,9 +2639,12 @@ CC_DEV void d_snapshot(const CcGrid g, CcDevPtrs p, int spec);
 // masks. The walk order, the visit count and which hit is first are those of the reference. The cells of the next
 // CC_PROBE_PIPE runs are fetched ahead with cp.async into a per-warp ring in shared memory (lane j holds cell j of a
 // run): an isolated point walks its whole window, 2 * max_steps_in_row + 1 runs.
+// `max_back` >= 0 (count-only mode, d_visited_fix): the walk stops after that many columns back -- the reference's stop
+// at the first unpublished column (cpp:762-763) -- and only number_of_visited_neighbors is written.
 CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* s_parent, unsigned int* s_links, float4* ring,
-                         int base_local, long long colbase, int lane, int pidx)
+                         int base_local, long long colbase, int lane, int pidx, int max_back = -1)
 {
+    const bool count_only = max_back >= 0;
     const int R = cfg.R, msr = cfg.max_steps_row;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int pci = pidx / R, prow = pidx - pci * R;
@@ -2655,9 +2659,12 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
     int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
     steps_back = steps_back < msr ? steps_back : msr;
     steps_back = steps_back < 0 ? 0 : steps_back;
+    if (count_only && steps_back > max_back)
+        steps_back = max_back;
     // run r of the walk order (cpp:707-719): r = 0 is the own column upwards; then for every column further back the
     // upward run (from the own row) and the downward run
     const int nruns = 1 + 2 * steps_back;
+    int reached = 0; // columns back whose runs were walked
     auto issue = [&](int r)
     {
         if (r < nruns)
@@ -2685,6 +2692,7 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
     for (int r = 0; r < nruns; r++)
     {
         const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+        reached = back;
         int olocal = plocal - back;
         if (olocal < 0)
             olocal += cfg.ringcols; // cpp:768-769
@@ -2742,7 +2750,7 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
                 unsigned int hp = hit_mask & proc_mask;
                 if (hp)
                 {
-                    if ((hp >> lane) & 1u) // every hit lane checks its own target
+                    if (!count_only && ((hp >> lane) & 1u)) // every hit lane checks its own target
                     {
                         // could the reference have refused this hit?
                         const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
@@ -2762,7 +2770,7 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
                         hp &= hp - 1;
                     }
                     // the remaining hits are tree<->tree link candidates (cpp:740-741)
-                    if ((hp >> lane) & 1u)
+                    if (!count_only && ((hp >> lane) & 1u))
                     {
                         const int slot = nlinks + __popc(hp & lt_mask);
                         if (slot < CC_LINK_SLOTS)
@@ -2789,6 +2797,15 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
             break; // cpp:757-759, after both runs of a column
     }
     __pipeline_wait_prior(0); // nothing in flight when the next point starts filling the ring
+    if (count_only)
+    {
+        if (lane == 0)
+        {
+            p.visited[pq] = static_cast<unsigned short>(visited);
+            p.vback[pq] = 0;
+        }
+        return;
+    }
     const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
                           (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
     for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
@@ -2797,6 +2814,7 @@ CC_DEV void d_probe_coop(const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int* 
     {
         s_parent[pidx] = first == CC_NONE ? pq : first;
         p.visited[pq] = static_cast<unsigned short>(visited);
+        p.vback[pq] = static_cast<unsigned char>(reached);
         if (any_flag)
         {
             p.col_flag[pci] = 1;
@@ -2858,9 +2876,10 @@ CC_DEV void d_probe(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_p
             static_assert(CC_LINK_SLOTS == 4, "four link registers below");
             int nl = 0, visited = 0;
             bool flagged = false;
-            int ocol = plocal;
+            int ocol = plocal, reached = 0;
             for (int back = 0; back <= steps_back; back++)
             {
+                reached = back;
                 for (int dir = -1; dir <= 1 && !heavy; dir += 2)
                 {
                     if (dir == 1 && back == 0)
@@ -2934,6 +2953,7 @@ CC_DEV void d_probe(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_p
                 lk[3] = l3;
                 s_parent[pidx] = first == CC_NONE ? pq : first;
                 p.visited[pq] = static_cast<unsigned short>(visited);
+                p.vback[pq] = static_cast<unsigned char>(reached);
                 if (flagged || (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0))
                 {
                     p.col_flag[pci] = 1;
@@ -3125,9 +3145,11 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                 else
                     visited += __reduce_add_sync(CC_FULL_MASK, contrib);
             }
+            int reached = q >> 1; // columns back whose runs were walked (the quiet prefix is runs [0, q))
             for (int r = q; r < nruns; r++)
             {
                 const int back = (r + 1) >> 1, dir = (r == 0 || (r & 1)) ? -1 : 1;
+                reached = back;
                 const int start_step = (dir == 1 || back == 0) ? 1 : 0;
                 const int start_row = (dir == 1 || back == 0) ? prow + dir : prow;
                 int n = cfg.max_steps_col - start_step + 1; // cells of this vertical run
@@ -3219,6 +3241,7 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
             {
                 s_parent[pidx] = first == CC_NONE ? pq : first;
                 p.visited[pq] = static_cast<unsigned short>(visited);
+                p.vback[pq] = static_cast<unsigned char>(reached);
                 if (any_flag)
                 {
                     p.col_flag[pci] = 1;
@@ -3588,6 +3611,7 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
         p.tparent[q] = CC_NONE;
         p.tfirst[q] = CC_NONE;
         p.visited[q] = 0;
+        p.vback[q] = 0; // the walk below honours the stop at the first unpublished column itself
     }
     for (int row = 0; row < R; row++)
     {
@@ -4447,10 +4471,61 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
         }
     }
 }
+// number_of_visited_neighbors, exactly: the reference's walk stops at the first unpublished column (cpp:762-763), which
+// for column c is where the finish pass of column c - 1 left it -- known only now, after the finish passes of the commit.
+// The (geometric) probes walked without that stop and left how many columns back they got; the few points that went
+// beyond the stop are counted again, a warp per point, with the walk cut there. `ring`: CC_PROBE_PIPE * CC_WARP float4 of
+// shared memory per warp.
+CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, float4* ring_all)
+{
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted || !cc_head_ok(hd, spec))
+        return;
+    const CcDevState* st = p.st;
+    const int R = cfg.R;
+    const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = hd.colbase;
+    const long long fu0 = st->seg_first_unpub_old;
+    const int base_local = cc_local_col(colbase, cfg.ringcols);
+    const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
+    const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    float4* ring = ring_all + static_cast<size_t>(warp) * CC_PROBE_PIPE * CC_WARP;
+    const long long total = (c1 - c0 + 1) * R;
+    for (long long i0 = (static_cast<long long>(g.bid) * nwarps + warp) * CC_WARP; i0 < total;
+         i0 += static_cast<long long>(g.nb) * nwarps * CC_WARP)
+    {
+        const long long i = i0 + lane;
+        int max_back = -1, pidx = 0;
+        if (i < total)
+        {
+            const long long gcol = c0 + i / R;
+            const int row = static_cast<int>(i % R);
+            const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+            const long long fu = gcol == c0 ? fu0 : p.col_first_unpub[gcol - 1 - colbase];
+            const int reached = p.vback[cell];
+            if (reached > 0 && fu >= 0 && gcol - reached < fu)
+            {
+                max_back = gcol > fu ? static_cast<int>(gcol - fu) : 0;
+                pidx = static_cast<int>(gcol - colbase) * R + row;
+            }
+        }
+        unsigned int todo = __ballot_sync(CC_FULL_MASK, max_back >= 0);
+        while (todo)
+        {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int mb = __shfl_sync(CC_FULL_MASK, max_back, src), px = __shfl_sync(CC_FULL_MASK, pidx, src);
+            d_probe_coop(cfg, p, nullptr, nullptr, ring, base_local, colbase, lane, px, mb);
+        }
+    }
+}
+
 __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
     CC_PDL_ENTER();
-    d_fin_label(cc_grid(), cfg, p, seq, spec);
+    const CcGrid g = cc_grid();
+    d_fin_label(g, cfg, p, seq, spec);
+    CC_SMEM(smem);
+    d_visited_fix(g, cfg, p, spec, reinterpret_cast<float4*>(smem));
 }
 
 // =====================================================================================================
@@ -4488,6 +4563,7 @@ CC_DEV void d_clear(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, lon
         p.tfirst[cell] = CC_NONE;
         p.cid[cell] = 0u;
         p.visited[cell] = 0;
+        p.vback[cell] = 0;
         p.tstate[cell] = 0u;
         if (row == 0)
             p.slot_gcol[local] = -1;
@@ -4645,6 +4721,8 @@ CC_DEV void cc_cluster_sync()
 {
 #ifndef CC_EMU
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    asm volatile("" ::: "memory"); // the stages stay in program order for the host compiler as well
 #endif
 }
 CC_DEV void cc_fence_system()
@@ -4831,6 +4909,18 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
     // One system-scope fence for the whole push, by the thread that raises the flag: what the other CTAs wrote to host
     // memory is ordered before it by the cluster barrier (release / acquire) and the fence's cumulativity.
     cc_cluster_sync();
+    if (a.has_tf && a.spec && (g.nb == 1 || g.bid != 0))
+    {
+        CcGrid gv = g;
+        if (g.nb > 1)
+        {
+            gv.bid = g.bid - 1;
+            gv.nb = g.nb - 1;
+        }
+        CC_SMEM(smem_v);
+        d_visited_fix(gv, cfg, p, 1, reinterpret_cast<float4*>(smem_v));
+        __syncthreads();
+    }
     if (g.bid == 0)
     {
         CcTraceScope tr(p.trace, CC_KID_export, g.bid);
@@ -4939,13 +5029,16 @@ __global__ void k_export_cells(CcDevCfg cfg, CcDevPtrs p, long long from, int nc
     {
         const long long ci = i / cfg.R;
         const int row = static_cast<int>(i - ci * cfg.R);
-        const CcCell c = cc_gather_cell(cfg, p, from + ci, row);
-        // one full 128-byte line per thread
-        const uint4* src = reinterpret_cast<const uint4*>(&c);
+        union // one full 128-byte line per thread, as eight 16-byte stores
+        {
+            CcCell c;
+            uint4 v[8];
+        } u;
+        u.c = cc_gather_cell(cfg, p, from + ci, row);
         uint4* dst = reinterpret_cast<uint4*>(out + i);
 #pragma unroll
         for (int w = 0; w < 8; w++)
-            dst[w] = src[w];
+            dst[w] = u.v[w];
     }
 }
 

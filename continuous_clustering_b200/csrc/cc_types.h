@@ -166,6 +166,7 @@ struct CcDevPtrs
     unsigned int* rootslot;      // root: index in the unfinished list
     unsigned int* cid;           // Point::id
     unsigned short* visited;     // Point::number_of_visited_neighbors
+    unsigned char* vback;        // columns back the association walk of the point got (d_visited_fix)
     long long* slot_gcol;        // per ring column: global column segmented into it, -1 = cleared
     // ---- per-row carried state ----
     float* gap_state;     // sc_inclination_angles_between_lasers_ (hpp:275)

@@ -14,6 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 
 REF_LIB = os.path.join(HERE, "_ref", "libcc_ref.so")  # the reference's own sources (built where /root/reference exists)
+# the same driver + the reference's own CALLER code (ros_utils.cpp / kitti_demo.cpp excerpts) against the facade
+FACADE_CALLERS_LIB = os.path.join(HERE, "_ref", "libcc_facade_callers.so")  # facade + CUDA library
+FACADE_CALLERS_EMU_LIB = os.path.join(HERE, "_ref", "libcc_facade_callers_emu_test.so")  # facade + CPU emulation (tests)
 ORACLE_LIB = os.path.join(HERE, "libcc_oracle.so")  # the CPU restatement
 FACADE_LIB = os.path.join(REPO, "build", "libcc_facade_driver.so")  # facade + CUDA library
 
@@ -164,6 +167,28 @@ CLUSTER_DTYPE = np.dtype(
     [("stamp", "<u8"), ("id", "<u8"), ("point_offset", "<i8"), ("num_points", "<i8"), ("event_index", "<i8")]
 )
 CLUSTER_POINT_DTYPE = np.dtype([("gcol", "<i8"), ("globally_unique_point_index", "<u8"), ("row", "<i4"), ("pad_", "<i4")])
+CLOUD_DTYPE = np.dtype([("from_gcol", "<i8"), ("to_gcol", "<i8"), ("kind", "<i4"), ("width", "<u4"), ("height", "<u4"),
+                        ("point_step", "<u4"), ("stamp_ns", "<u8"), ("data_offset", "<i8"), ("data_size", "<i8")])
+assert CLOUD_DTYPE.itemsize == 56
+
+# sensor_msgs/PointCloud2 point layout of the ROS node's messages (ros_utils.cpp:108-243): fields are packed without
+# padding; the first 19 make up the ground-stage cloud (point_step 76), all 26 the clustered one (116)
+POINTCLOUD2_FIELDS = [
+    ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("firing_index", "<f8"), ("intensity", "u1"),
+    ("globally_unique_point_index", "<f8"), ("time_sec", "<u4"), ("time_nsec", "<u4"), ("distance", "<f4"),
+    ("azimuth_angle", "<f4"), ("inclination_angle", "<f4"), ("continuous_azimuth_angle", "<f8"),
+    ("global_column_index", "<f8"), ("local_column_index", "<u2"), ("row_index", "<u2"), ("ground_point_label", "u1"),
+    ("debug_ground_point_label", "u1"), ("height_over_ground", "<f4"), ("ignore_for_clustering", "u1"),
+    ("finished_at_continuous_azimuth_angle", "<f8"), ("num_child_points", "<u2"), ("tree_root_row_index", "<u2"),
+    ("tree_root_column_index", "<f8"), ("number_of_visited_neighbors", "<u4"), ("tree_id", "<f8"), ("id", "<f8"),
+]
+
+
+def pointcloud2_dtype(n_fields: int) -> np.dtype:
+    return np.dtype(POINTCLOUD2_FIELDS[:n_fields])
+
+
+assert pointcloud2_dtype(19).itemsize == 76 and pointcloud2_dtype(26).itemsize == 116
 
 
 class Driver:
@@ -202,6 +227,14 @@ class Driver:
         L.drv_get_cluster_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.drv_get_clusters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.drv_clear_records.argtypes = [C.c_void_p]
+        L.drv_set_cloud_record.argtypes = [C.c_void_p, C.c_int]
+        for name in ("drv_num_clouds", "drv_cloud_bytes"):
+            getattr(L, name).argtypes = [C.c_void_p]
+            getattr(L, name).restype = C.c_int64
+        L.drv_get_clouds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.drv_kitti_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.drv_kitti_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.drv_kitti_get.restype = C.c_int64
         self.h = L.drv_create()
         self.rows = 0
         self.name = L.drv_impl_name().decode()
@@ -292,6 +325,40 @@ class Driver:
 
     def clear_records(self):
         self.lib.drv_clear_records(self.h)
+
+    # ---- the reference's own caller code (ros_utils.cpp / kitti_demo.cpp excerpts), where the library has it ----
+    def has_caller_excerpts(self) -> bool:
+        return bool(self.lib.drv_has_caller_excerpts())
+
+    def set_cloud_record(self, on: bool):
+        self.lib.drv_set_cloud_record(self.h, int(on))
+
+    def clouds(self):
+        """[(descriptor, structured array of the message's points [height, width])] in callback order."""
+        n = self.lib.drv_num_clouds(self.h)
+        desc = np.zeros(n, dtype=CLOUD_DTYPE)
+        data = np.zeros(self.lib.drv_cloud_bytes(self.h), dtype=np.uint8)
+        if n:
+            self.lib.drv_get_clouds(self.h, desc.ctypes.data, data.ctypes.data)
+        out = []
+        for d in desc:
+            dt = pointcloud2_dtype({76: 19, 116: 26, 69: 15, 37: 8}[int(d["point_step"])])
+            raw = data[int(d["data_offset"]) : int(d["data_offset"]) + int(d["data_size"])]
+            out.append((d, raw.view(dt).reshape(int(d["height"]), int(d["width"]))))
+        return out
+
+    def kitti_begin(self, sequence: int, points_per_frame):
+        ppf = np.ascontiguousarray(points_per_frame, dtype=np.int32)
+        self.lib.drv_kitti_begin(self.h, sequence, len(ppf), ppf.ctypes.data)
+
+    def kitti_get(self, frame: int):
+        n = self.lib.drv_kitti_get(self.h, frame, None, None)
+        if n < 0:
+            return None
+        flags = np.zeros(n, dtype=np.uint8)
+        labels = np.zeros(n, dtype=np.uint32)
+        self.lib.drv_kitti_get(self.h, frame, flags.ctypes.data, labels.ctypes.data)
+        return flags, labels
 
 
 def have_ref() -> bool:

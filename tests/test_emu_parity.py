@@ -76,7 +76,8 @@ def test_emulated_kernels_match_oracle(emu_library, oracle_lib, spec, kw, cfg_ov
     cc = make_cc(emu_library, cfg, sp.rows)
     cc.debug_flag_columns(flag_period)
     got = recorder.record(cc, pts, poses, chunk)
-    parity.compare(want, got, name_a="oracle", name_b="emulated kernels")
+    parity.compare(want, got, name_a="oracle", name_b="emulated kernels", check_tree_fields=True,
+                   check_published_tree_fields=True)
     assert np.array_equal(want["cluster_cells"]["tree_root_gcol"], got["cluster_cells"]["tree_root_gcol"])
     if flag_period:
         assert got["used_exact_path"] > 0

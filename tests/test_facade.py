@@ -27,7 +27,7 @@ def run(lib, spec, kw, cfg_over, batch, pipelined=False):
     o = drvlib.Driver(drvlib.ORACLE_LIB)
     o.configure(cfg, sp.rows)
     want = parity.record(o, pts, poses)
-    parity.compare(want, rec, name_a="oracle", name_b=d.name)
+    parity.compare(want, rec, name_a="oracle", name_b=d.name, check_tree_fields=True, check_published_tree_fields=True)
     assert np.array_equal(want["cluster_cells"]["tree_root_gcol"], rec["cluster_cells"]["tree_root_gcol"])
 
 

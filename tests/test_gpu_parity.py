@@ -24,7 +24,7 @@ def test_cuda_matches_oracle_small(cuda_library, oracle_lib, spec, kw, cfg_over,
     cc = make_cc(None, cfg, sp.rows)
     cc.debug_flag_columns(flag_period)
     got = recorder.record(cc, pts, poses, chunk)
-    parity.compare(want, got, name_a="oracle", name_b="cuda")
+    parity.compare(want, got, name_a="oracle", name_b="cuda", check_tree_fields=True, check_published_tree_fields=True)
     assert np.array_equal(want["cluster_cells"]["tree_root_gcol"], got["cluster_cells"]["tree_root_gcol"])
 
 
@@ -86,7 +86,7 @@ def test_cuda_matches_oracle_full_size(cuda_library, oracle_lib, spec, kw, chunk
     want = oracle_record(oracle_lib, pts, poses, sp, cfg)
     cc = make_cc(None, cfg, sp.rows, max_push=max(4096, chunk))
     got = recorder.record(cc, pts, poses, chunk)
-    parity.compare(want, got, name_a="oracle", name_b="cuda")
+    parity.compare(want, got, name_a="oracle", name_b="cuda", check_tree_fields=True, check_published_tree_fields=True)
 
 
 def test_cuda_matches_reference_build_when_present(cuda_library):
