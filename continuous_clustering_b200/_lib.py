@@ -134,7 +134,15 @@ EXPORTED_SYMBOLS = [
     "cc_debug_flag_columns", "cc_get_result_views", "cc_submit_firings", "cc_submit_firings_device", "cc_wait", "cc_pending",
     "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
     "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
+    "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2",
 ]
+
+
+class CcCloudView(C.Structure):
+    """cc_cloud_view_t: a packed sensor_msgs/PointCloud2 payload in a page-locked buffer of the handle."""
+
+    _fields_ = [("data", C.c_void_p), ("data_size", C.c_uint64), ("stamp_ns", C.c_uint64), ("point_step", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("n_fields", C.c_uint32)]
 
 
 def bind(lib: C.CDLL) -> C.CDLL:
@@ -169,6 +177,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_get_result_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.cc_read_columns.argtypes = [vp, i64, i64, C.POINTER(CcColumnFields)]
     lib.cc_export_columns.argtypes = [vp, i64, i64, C.POINTER(vp)]
+    lib.cc_pack_columns_pointcloud2.argtypes = [vp, i64, i64, i32, C.POINTER(CcCloudView)]
+    lib.cc_pack_cluster_pointcloud2.argtypes = [vp, i32, C.POINTER(CcCloudView)]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]
     lib.cc_stream.argtypes = [vp]

@@ -337,6 +337,25 @@ class ContinuousClustering:
         buf = (C.c_char * (ncols * rows * _lib.CELL_DTYPE.itemsize)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=_lib.CELL_DTYPE, count=ncols * rows).reshape(ncols, rows)
 
+    def _cloud(self, view):
+        n = int(view.data_size)
+        data = np.frombuffer((C.c_char * n).from_address(view.data), dtype=np.uint8, count=n) if n else np.zeros(0, np.uint8)
+        return dict(data=data, point_step=int(view.point_step), width=int(view.width), height=int(view.height),
+                    stamp_ns=int(view.stamp_ns), n_fields=int(view.n_fields))
+
+    def pack_columns_pointcloud2(self, from_gcol: int, to_gcol: int, ground_points_only: bool):
+        """The sensor_msgs/PointCloud2 payload the ROS node publishes for a finished-column callback
+        (ros_utils.cpp:34-77), packed on the device. `data` is a VIEW valid until the next pack_* call."""
+        v = _lib.CcCloudView()
+        self._check(self._L.cc_pack_columns_pointcloud2(self._h, from_gcol, to_gcol, int(ground_points_only), C.byref(v)))
+        return self._cloud(v)
+
+    def pack_cluster_pointcloud2(self, cluster_index: int):
+        """Same for cluster `cluster_index` of the last finished push (ros_utils.cpp:11-32)."""
+        v = _lib.CcCloudView()
+        self._check(self._L.cc_pack_cluster_pointcloud2(self._h, int(cluster_index), C.byref(v)))
+        return self._cloud(v)
+
     def set_label_prefetch(self, enable: bool):
         """Bring the labels of every push's new columns back with its results (cc_set_label_prefetch)."""
         self._check(self._L.cc_set_label_prefetch(self._h, int(enable)))

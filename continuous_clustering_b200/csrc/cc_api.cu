@@ -126,6 +126,13 @@ struct cc_handle
     std::vector<void*> allocs_fixed; // independent of the ring size
     CcCell* h_export{nullptr}; // page-locked: cells of the last cc_export_columns / cc_read_columns call
     size_t export_cap{0};      // in cells
+    unsigned char* h_cloud{nullptr}; // page-locked: payload of the last cc_pack_*_pointcloud2 call
+    size_t cloud_cap{0};
+    unsigned int* d_counts{nullptr}; // child counts of the columns being packed
+    size_t counts_cap{0};
+    unsigned long long* d_min_stamp{nullptr};
+    unsigned long long* h_min_stamp{nullptr};
+    const CcClusterPoint* last_points_dev{nullptr}; // member lists of the last finished push, on the device
     CcDevState* h_state{nullptr}; // pinned mirror (reset, column-sequential path)
     CcDevState state{};
     unsigned int seq{0};
@@ -431,6 +438,14 @@ void cc_destroy(cc_handle_t* h)
         cudaFreeHost(h->h_state);
     if (h->h_export)
         cudaFreeHost(h->h_export);
+    if (h->h_cloud)
+        cudaFreeHost(h->h_cloud);
+    if (h->h_min_stamp)
+        cudaFreeHost(h->h_min_stamp);
+    if (h->d_counts)
+        cudaFree(h->d_counts);
+    if (h->d_min_stamp)
+        cudaFree(h->d_min_stamp);
     if (h->d_trace)
         cudaFree(h->d_trace);
     if (h->ev0)
@@ -1312,6 +1327,7 @@ static cc_status_t finish_push(cc_handle* h)
         h->cur_label_cols = std::min(ncols, h->maxcols);
     }
     h->points_view = points_in_place ? reinterpret_cast<const cc_cluster_point_t*>(sl.h_points) : h->cluster_points.data();
+    h->last_points_dev = sl.d_points;
     float ms = 0.f;
     if (timed_by_device)
         ms = static_cast<float>(static_cast<double>(sl.h_hdr->t_end_ns - sl.h_hdr->t_start_ns) * 1e-6);
@@ -1685,6 +1701,110 @@ cc_status_t cc_export_columns(cc_handle_t* h, int64_t from, int64_t to, const cc
     CC_CHECK(h, cudaGetLastError());
     *cells = reinterpret_cast<const cc_cell_t*>(h->h_export);
     return CC_OK;
+}
+
+// ---- PointCloud2 payloads packed on the device (ros_utils.cpp:11-77, 108-298) ----
+static cc_status_t pack_cloud(cc_handle* h, int mode, int64_t from, int ncols, const CcClusterPoint* list, int npoints,
+                              int64_t cfrom, int ccols, bool ground_only, uint64_t stamp, cc_cloud_view_t* out)
+{
+    CC_CHECK(h, cudaSetDevice(h->device));
+    const int nwords = (ground_only ? CC_CLOUD_STEP_GROUND : CC_CLOUD_STEP_CLUSTER) / 4;
+    const size_t total = mode == 0 ? static_cast<size_t>(ncols) * h->R : static_cast<size_t>(npoints);
+    const size_t bytes = total * nwords * 4;
+    if (bytes + 64 > h->cloud_cap)
+    {
+        if (h->h_cloud)
+            cudaFreeHost(h->h_cloud);
+        h->h_cloud = nullptr;
+        h->cloud_cap = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2 + 64, 1 << 20);
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_cloud), cap));
+        h->cloud_cap = cap;
+    }
+    if (!h->d_min_stamp)
+    {
+        CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_min_stamp), sizeof(unsigned long long)));
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_min_stamp), sizeof(unsigned long long)));
+    }
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    const unsigned int* counts = nullptr;
+    if (!ground_only && ccols > 0)
+    {
+        // child_points.size() of the cells (ros_utils.cpp:289): children name their parent
+        const size_t n = static_cast<size_t>(ccols) * h->R;
+        if (n > h->counts_cap)
+        {
+            if (h->d_counts)
+                cudaFree(h->d_counts);
+            h->d_counts = nullptr;
+            h->counts_cap = 0;
+            CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_counts), (n + n / 2) * sizeof(unsigned int)));
+            h->counts_cap = n + n / 2;
+        }
+        CC_CHECK(h, cudaMemsetAsync(h->d_counts, 0, n * sizeof(unsigned int), h->aux_stream));
+        const int ahead = std::max(0, static_cast<int>(std::min<int64_t>(cfg.max_steps_row, h->state.ring_end - (cfrom + ccols - 1))));
+        const int grid = std::max(1, std::min(h->sm_count * 8, static_cast<int>((n + 255) / 256)));
+        CC_LAUNCH(k_child_counts, grid, 256, 0, h->aux_stream, cfg, h->d, static_cast<long long>(cfrom), ccols, ahead, h->d_counts);
+        h->launches++;
+        counts = h->d_counts;
+    }
+    *h->h_min_stamp = ~0ull;
+    CC_CHECK(h, cudaMemcpyAsync(h->d_min_stamp, h->h_min_stamp, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->aux_stream));
+#ifdef CC_EMU
+    const int threads = 1;
+#else
+    const int threads = 128;
+#endif
+    const int warps = (threads + CC_WARP - 1) / CC_WARP;
+    const int grid = std::max(1, std::min(h->sm_count * 8, static_cast<int>((total + threads - 1) / threads)));
+    CC_LAUNCH(k_pack_cloud, grid, threads, static_cast<size_t>(warps) * CC_WARP * 29 * sizeof(unsigned int), h->aux_stream, cfg, h->d,
+              mode, static_cast<long long>(from), ncols, list, npoints, nwords, static_cast<long long>(cfrom), counts, h->h_cloud,
+              h->d_min_stamp);
+    h->launches++;
+    CC_CHECK(h, cudaMemcpyAsync(h->h_min_stamp, h->d_min_stamp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->aux_stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
+    CC_CHECK(h, cudaGetLastError());
+    out->data = h->h_cloud;
+    out->data_size = bytes;
+    out->point_step = static_cast<uint32_t>(nwords * 4);
+    out->n_fields = ground_only ? 19 : 26;
+    out->width = mode == 0 ? static_cast<uint32_t>(ncols) : static_cast<uint32_t>(npoints);
+    out->height = mode == 0 ? static_cast<uint32_t>(h->R) : 1u;
+    out->stamp_ns = mode == 0 ? (*h->h_min_stamp == ~0ull ? 0ull : *h->h_min_stamp) : stamp;
+    return CC_OK;
+}
+
+cc_status_t cc_pack_columns_pointcloud2(cc_handle_t* h, int64_t from, int64_t to, int ground_points_only, cc_cloud_view_t* out)
+{
+    if (!h || !out || !h->is_reset)
+        return CC_ERR_INVALID_ARGUMENT;
+    std::memset(out, 0, sizeof(*out));
+    if (to < from)
+        return CC_OK; // columnToPointCloud returns no message for an empty range (ros_utils.cpp:40-42)
+    if (from < 0 || to - from + 1 > h->ringcols)
+    {
+        h->error = "cc_pack_columns_pointcloud2: range outside the ring";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    const int ncols = static_cast<int>(to - from + 1);
+    return pack_cloud(h, 0, from, ncols, nullptr, 0, from, ncols, ground_points_only != 0, 0, out);
+}
+
+cc_status_t cc_pack_cluster_pointcloud2(cc_handle_t* h, int cluster_index, cc_cloud_view_t* out)
+{
+    if (!h || !out || !h->is_reset)
+        return CC_ERR_INVALID_ARGUMENT;
+    std::memset(out, 0, sizeof(*out));
+    if (cluster_index < 0 || cluster_index >= static_cast<int>(h->clusters.size()) || !h->last_points_dev)
+    {
+        h->error = "cc_pack_cluster_pointcloud2: no such cluster in the last finished push";
+        return CC_ERR_INVALID_ARGUMENT;
+    }
+    const cc_cluster_t& c = h->clusters[cluster_index];
+    const int ccols = static_cast<int>(c.max_gcol - c.min_gcol + 1);
+    return pack_cloud(h, 1, 0, 0, h->last_points_dev + c.point_offset, static_cast<int>(c.num_points), c.min_gcol, ccols, false,
+                      c.stamp, out);
 }
 
 cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_column_fields_t* f)

@@ -5042,6 +5042,164 @@ __global__ void k_export_cells(CcDevCfg cfg, CcDevPtrs p, long long from, int nc
     }
 }
 
+// =====================================================================================================
+// K6 (continued)
+//     k_pack_cloud     the sensor_msgs/PointCloud2 payload the ROS node publishes for a range of columns or for a finished
+//                      cluster (ros_utils.cpp:11-77: columnToPointCloud / clusterToPointCloud; point layout of
+//                      ros_utils.cpp:108-243, field values of addPointToMessage ros_utils.cpp:245-298), byte for byte:
+//                      fields packed without padding, 76 bytes per point up to the ground-segmentation stage, 116 with
+//                      the clustering fields; column clouds are row-major images (height = rows, width = columns).
+//                      A warp assembles 32 consecutive points in shared memory and writes them out as 16-byte vectors
+//                      straight into page-locked host memory.
+//     k_child_counts   child_points.size() of the cells of a column range (children name their parent, tfirst).
+// =====================================================================================================
+#define CC_CLOUD_STEP_GROUND 76
+#define CC_CLOUD_STEP_CLUSTER 116
+
+__global__ void k_child_counts(CcDevCfg cfg, CcDevPtrs p, long long from, int ncols, int ahead, unsigned int* counts)
+{
+    // children sit at most max_steps_in_row columns ahead of their parent (cpp:704-705)
+    const long long total = static_cast<long long>(ncols + ahead) * cfg.R;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long gcol = from + i / cfg.R;
+        const int row = static_cast<int>(i % cfg.R);
+        const int local = cc_local_col(gcol, cfg.ringcols);
+        if (p.slot_gcol[local] != gcol)
+            continue;
+        const size_t cell = static_cast<size_t>(local) * cfg.R + row;
+        const unsigned int fp = p.tfirst[cell];
+        if (fp == CC_NONE || fp == static_cast<unsigned int>(cell) || p.tparent[cell] == CC_NONE)
+            continue;
+        const long long pg = p.slot_gcol[fp / cfg.R];
+        if (pg >= from && pg < from + ncols)
+            atomicAdd(counts + (pg - from) * cfg.R + fp % cfg.R, 1u);
+    }
+}
+
+// the words of one point record (stage 2: 19 words, stage 3: 29 words)
+CC_DEV void cc_cloud_record(const CcDevCfg& cfg, const CcDevPtrs& p, long long gcol, int row, unsigned int nchild, int nwords,
+                            unsigned int* w, unsigned long long* stamp_out)
+{
+    const CcCell c = cc_gather_cell(cfg, p, gcol, row);
+    *stamp_out = c.stamp;
+    auto lo = [](double d) { return static_cast<unsigned int>(static_cast<unsigned long long>(__double_as_longlong(d))); };
+    auto hi = [](double d) { return static_cast<unsigned int>(static_cast<unsigned long long>(__double_as_longlong(d)) >> 32); };
+    const int local = cc_local_col(gcol, cfg.ringcols);
+    const int local_column_index = c.global_column_index >= 0 ? local : -1;        // cpp:348-350 / cleared value
+    const int row_index = cc_isnan(c.distance) ? -1 : row;                           // set by insertion only (cpp:235)
+    w[0] = ccm::f2u(c.x);
+    w[1] = ccm::f2u(c.y);
+    w[2] = ccm::f2u(c.z);
+    const double fi = static_cast<double>(c.firing_index); // (*) UINT64 fields travel as FLOAT64 (ros_utils.cpp:124-126)
+    w[3] = lo(fi);
+    w[4] = hi(fi);
+    // bytes 21 .. 75 are one byte off the word grid (the UINT8 intensity at byte 20): assembled as a stream of words ...
+    unsigned int sw[14];
+    const double gp = static_cast<double>(c.globally_unique_point_index);
+    sw[0] = lo(gp);
+    sw[1] = hi(gp);
+    sw[2] = static_cast<unsigned int>(c.stamp / 1000000000ull); // ros::Time::fromNSec
+    sw[3] = static_cast<unsigned int>(c.stamp % 1000000000ull);
+    sw[4] = ccm::f2u(c.distance);
+    sw[5] = ccm::f2u(c.azimuth_angle);
+    sw[6] = ccm::f2u(c.inclination_angle);
+    sw[7] = lo(c.continuous_azimuth_angle);
+    sw[8] = hi(c.continuous_azimuth_angle);
+    const double gc = static_cast<double>(c.global_column_index);
+    sw[9] = lo(gc);
+    sw[10] = hi(gc);
+    sw[11] = (static_cast<unsigned int>(local_column_index) & 0xffffu) | (static_cast<unsigned int>(row_index) << 16);
+    const unsigned int hog = 0x7fc00000u; // height_over_ground is never computed by the reference (only cleared, cpp:1126)
+    sw[12] = c.ground_point_label | (static_cast<unsigned int>(c.debug_ground_point_label) << 8) | (hog << 16);
+    sw[13] = (hog >> 16) | ((c.is_ignored ? 9u /* BLUE */ : 105u /* ORANGE */) << 16); // ros_utils.cpp:285
+    // ... and shifted into place
+    unsigned int carry = c.intensity;
+#pragma unroll
+    for (int k = 0; k < 14; k++)
+    {
+        w[5 + k] = (sw[k] << 8) | carry;
+        carry = sw[k] >> 24;
+    }
+    if (nwords > 19)
+    {
+        w[19] = lo(c.finished_at_continuous_azimuth_angle);
+        w[20] = hi(c.finished_at_continuous_azimuth_angle);
+        w[21] = (nchild & 0xffffu) | (static_cast<unsigned int>(c.tree_root_row) << 16);
+        // Point::tree_root_ holds the LOCAL ring column (cpp:661, 814), -1 = not associated
+        const double rc = c.tree_root_gcol >= 0 ? static_cast<double>(c.tree_root_gcol % cfg.ringcols) : -1.0;
+        w[22] = lo(rc);
+        w[23] = hi(rc);
+        w[24] = c.number_of_visited_neighbors;
+        const double tid = c.tree_root_gcol >= 0 ? static_cast<double>(static_cast<unsigned long long>(c.tree_root_gcol) * cfg.R +
+                                                                       static_cast<unsigned long long>(c.tree_root_row))
+                                                 : 0.0; // cpp:662, 815
+        w[25] = lo(tid);
+        w[26] = hi(tid);
+        const double id = static_cast<double>(c.id);
+        w[27] = lo(id);
+        w[28] = hi(id);
+    }
+}
+
+// mode 0: columns [from, from + ncols): message point o = row * ncols + column (ros_utils.cpp:62); mode 1: the points of
+// `list` in order (clusterToPointCloud). `counts`: child counts of the cells of columns [cfrom, ...) (k_child_counts) or
+// null. `min_stamp`: smallest non-zero point stamp (the column message's header stamp, ros_utils.cpp:66-74).
+__global__ void __launch_bounds__(128) k_pack_cloud(CcDevCfg cfg, CcDevPtrs p, int mode, long long from, int ncols,
+                                                    const CcClusterPoint* list, int npoints, int nwords, long long cfrom,
+                                                    const unsigned int* counts, unsigned char* out, unsigned long long* min_stamp)
+{
+    CC_SMEM(smem);
+    const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
+    const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    unsigned int* tile = reinterpret_cast<unsigned int*>(smem) + static_cast<size_t>(warp) * CC_WARP * 29;
+    const long long total = mode == 0 ? static_cast<long long>(ncols) * cfg.R : npoints;
+    unsigned long long smin = ~0ull;
+    for (long long o0 = (static_cast<long long>(blockIdx.x) * nwarps + warp) * CC_WARP; o0 < total;
+         o0 += static_cast<long long>(gridDim.x) * nwarps * CC_WARP)
+    {
+        const long long o = o0 + lane;
+        if (o < total)
+        {
+            long long gcol;
+            int row;
+            if (mode == 0)
+            {
+                row = static_cast<int>(o / ncols);
+                gcol = from + o % ncols;
+            }
+            else
+            {
+                gcol = list[o].gcol;
+                row = list[o].row;
+            }
+            const unsigned int nchild = counts ? counts[(gcol - cfrom) * cfg.R + row] : 0u;
+            unsigned int w[29];
+            unsigned long long stamp;
+            cc_cloud_record(cfg, p, gcol, row, nchild, nwords, w, &stamp);
+            if (stamp != 0ull && stamp < smin)
+                smin = stamp;
+            for (int k = 0; k < nwords; k++)
+                tile[lane * nwords + k] = w[k]; // stride 19 / 29 words: conflict free
+        }
+        __syncwarp();
+        // 32 records are 32 * 76 = 2432 or 32 * 116 = 3712 contiguous bytes, both multiples of 16
+        const long long cnt = total - o0 < CC_WARP ? total - o0 : CC_WARP;
+        const int nbytes = static_cast<int>(cnt) * nwords * 4;
+        unsigned char* dst = out + o0 * nwords * 4;
+        const int nvec = nbytes / 16;
+        const uint4* src4 = reinterpret_cast<const uint4*>(tile);
+        for (int v = lane; v < nvec; v += CC_WARP)
+            reinterpret_cast<uint4*>(dst)[v] = src4[v];
+        for (int b = nvec * 16 + lane * 4; b < nbytes; b += CC_WARP * 4) // ragged tail of the last warp
+            *reinterpret_cast<unsigned int*>(dst + b) = tile[b / 4];
+        __syncwarp();
+    }
+    if (min_stamp && smin != ~0ull)
+        atomicMin(min_stamp, smin);
+}
+
 // ---- device math self-test (bit equality with the host libm) ----
 __global__ void k_selftest_math(int op, int n, const float* a, const float* b, float* out)
 {

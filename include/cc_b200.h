@@ -303,6 +303,26 @@ CC_API cc_status_t cc_read_columns(cc_handle_t* h, int64_t from_gcol, int64_t to
  * the next cc_export_columns / cc_read_columns call on the handle. This is what the facade fills `range_image_` from. */
 CC_API cc_status_t cc_export_columns(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol, const cc_cell_t** cells);
 
+/* The sensor_msgs/PointCloud2 payloads the ROS node publishes, packed ON THE DEVICE byte for byte as the reference's
+ * message conversion builds them (src/ros/ros_utils.cpp:11-77 columnToPointCloud / clusterToPointCloud, point layout
+ * ros_utils.cpp:108-243, field values ros_utils.cpp:245-298): fields without padding, point_step 76 for the
+ * ground-segmentation stage (ground_points_only callbacks) and 116 with the clustering fields. Column messages are
+ * row-major images (height = num_rows, width = columns; point of (row, column) at index row * width + column) whose
+ * header stamp is the smallest non-zero point stamp (0 if none); a cluster message is height 1 with the cluster's
+ * stamp (cpp:1025-1028). `data` points into a page-locked buffer of the handle, valid until the next cc_pack_* call.
+ * cc_pack_cluster_pointcloud2 takes the index of a cluster of the LAST finished push (cc_get_clusters order) and is
+ * valid until the next push is submitted. */
+typedef struct cc_cloud_view
+{
+    const uint8_t* data;
+    uint64_t data_size;
+    uint64_t stamp_ns;
+    uint32_t point_step, width, height, n_fields;
+} cc_cloud_view_t;
+CC_API cc_status_t cc_pack_columns_pointcloud2(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol, int ground_points_only,
+                                               cc_cloud_view_t* out);
+CC_API cc_status_t cc_pack_cluster_pointcloud2(cc_handle_t* h, int cluster_index, cc_cloud_view_t* out);
+
 /* Public data members of the reference object (hpp:244-251). */
 CC_API int cc_num_rows(const cc_handle_t* h);
 CC_API int cc_num_columns(const cc_handle_t* h);

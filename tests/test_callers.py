@@ -163,3 +163,54 @@ def test_published_messages_identical_cuda(cuda_library, spec, kw, cfg_over, bat
 def test_kitti_demo_callback_identical_cuda(cuda_library):
     _need(drvlib.REF_LIB, drvlib.FACADE_CALLERS_LIB)
     check_kitti(drvlib.FACADE_CALLERS_LIB, False)
+
+
+# ---- the same messages packed ON THE DEVICE (cc_pack_*_pointcloud2) ----
+def device_clouds(cc, pts, poses, chunk):
+    """Runs the stream through the C ABI and builds, for every callback the reference's node would get, the message
+    payload with the device-side packer; same descriptor layout as Driver.clouds()."""
+    out = []
+    for a in range(0, pts.shape[0], chunk):
+        res = cc.addFirings(pts[a:a + chunk], poses[a:a + chunk])
+        nxt = 0
+        for e in res.events.copy():
+            while nxt < int(e["n_clusters_before"]):
+                cl = res.clusters[nxt]
+                if cl["num_points"] > 20:  # cpp:1023
+                    c = cc.pack_cluster_pointcloud2(nxt)
+                    out.append((2, -1, -1, dict(c, data=c["data"].copy())))  # the payload is a view: keep a copy
+                nxt += 1
+            if e["to_gcol"] >= e["from_gcol"]:  # columnToPointCloud: no message for an empty range
+                c = cc.pack_columns_pointcloud2(int(e["from_gcol"]), int(e["to_gcol"]), bool(e["ground_points_only"]))
+                out.append((0 if e["ground_points_only"] else 1, int(e["from_gcol"]), int(e["to_gcol"]), dict(c, data=c["data"].copy())))
+    clouds = []
+    for kind, f, t, c in out:
+        d = np.zeros((), dtype=drvlib.CLOUD_DTYPE)
+        d["from_gcol"], d["to_gcol"], d["kind"] = f, t, kind
+        d["width"], d["height"], d["point_step"], d["stamp_ns"] = c["width"], c["height"], c["point_step"], c["stamp_ns"]
+        dt = drvlib.pointcloud2_dtype(c["n_fields"])
+        clouds.append((d, c["data"].view(dt).reshape(c["height"], c["width"])))
+    return clouds
+
+
+def check_device_packer(library, spec, kw, cfg_over, chunk):
+    from test_emu_parity import make_cc
+
+    _need(drvlib.REF_LIB)
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want, _ = record_clouds(drvlib.REF_LIB, pts, poses, sp, cfg)
+    cc = make_cc(library, cfg, sp.rows)
+    got = device_clouds(cc, pts, poses, chunk)
+    compare_clouds(want, got)
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,batch", CASES)
+def test_device_packed_messages_identical_emulation(emu_library, spec, kw, cfg_over, batch):
+    check_device_packer(emu_library, spec, kw, cfg_over, batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,kw,cfg_over,batch", CASES + [("velodyne64", dict(n_rotations=2.2, moving=True), {}, 1024)])
+def test_device_packed_messages_identical_cuda(cuda_library, spec, kw, cfg_over, batch):
+    check_device_packer(None, spec, kw, cfg_over, batch)
