@@ -1,30 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- range-image columns/s of the per-column hot path on a synthetic 64-ring / 10 Hz stream.
+"""bench.py -- range-image columns/s of the per-column hot path on a synthetic LiDAR firing stream.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--spec velodyne64|vls128|os32_pair|kitti64]
+                  [--moving] [--batch B] [--quick]
 
-One STEP = one push of `--batch` consecutive firings (default 4096 = two sensor rotations of the 64 x 2048
-synthetic Velodyne-like stream, BASELINE.json configs[1]) through insertion, ground segmentation, association,
-finish detection and ring recycling. The stream keeps going across steps (the range image is continuous).
+One STEP = one push of `--batch` consecutive firings (default 4096 = two sensor rotations of the 64 x 2048 synthetic
+Velodyne-like stream, BASELINE.json configs[1]) through insertion, ground segmentation, association, finish detection
+and ring recycling. The stream keeps going across steps (the range image is continuous).
 
   value     columns/s with the firings already resident in HBM when the timed region starts (cc_submit_firings_device /
             cc_wait, two pushes in flight), timed with CUDA events on the handle's stream over K back-to-back pushes.
-            Inputs larger than L2: every push reads firings nothing has touched since L2 was flushed right before the
-            timed region. `l2_flush_each_step` reports the same with a 256 MiB write before every push.
-  e2e       the same metric through the public API with HOST buffers (ContinuousClustering.submitFirings / wait:
-            page-locked host -> device copy of the raw firings, kernels, device -> host copy of events, finished
-            clusters, member lists and the ground labels of the new columns), wall clock.
-  batch_sweep / latency_mode   other operating points: 1024 / 2048 / 6144 firings per push (device resident), and
-            64-firing synchronous pushes with host buffers (per-push latency).
+            Inputs larger than L2: every push reads firings nothing has touched since L2 was flushed (256 MiB write)
+            right before the timed region. `l2_flush_each_step` reports the same with a flush before every push.
+  e2e       the same metric through the C ABI with page-locked HOST buffers in the reference's 48-byte RawPoint layout
+            (cc_submit_firings / cc_wait: host -> device copy of the raw firings, kernels, device -> host copy of events,
+            finished clusters, member lists and the ground labels of the new columns), wall clock.
+  latency_mode   64-firing synchronous pushes with host buffers through the C ABI (one fused launch per push) and the
+            per-call wall time of ContinuousClustering::addFiring on the drop-in C++ class (facade_latency), next to
+            cpu_baseline.latency_us_*: the reference's single-threaded per-addFiring times on this box.
+  facade    columns/s through the drop-in C++ class, one addFiring call per firing, callbacks registered.
   roofline  the dominant kernel of the step (largest share of device time, measured live with CUDA events around
-            every launch): algorithmic bytes it must move / its duration, against MEASURED_PEAKS.json hbm_gbs.
+            every launch, no exclusions): SURVEY 8d algorithmic bytes / its duration, against MEASURED_PEAKS.json.
   cpu_baseline  the reference's own CPU implementation (oracle/_ref/libcc_ref.so, built from the reference's
             sources) -- or the restatement in oracle/ when that build is absent -- timed on this box's host cores
             on a bounded sample of the same stream.
 
 N > 1 (torchrun, one rank per GPU): every rank runs its own independent sensor stream (streams shard one per GPU;
-there is no data-path collective), barrier + max-over-ranks timing, value = total columns / max time ("weak").
-`--impl reference` times only the CPU reference arm (rank 0 only).
+there is no data-path collective), barrier + max-over-ranks timing, value = total columns / max time ("weak"); every
+rank contributes its per-GPU push-latency histogram. `--impl reference` times only the CPU reference arm (rank 0
+only; at N > 1 it runs N concurrent reference streams so that the ratio stays like for like).
 """
 from __future__ import annotations
 
@@ -42,25 +46,38 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
-SPEC = "velodyne64"
+SPEC = "velodyne64"  # default workload (scripts/ import this)
 IDENTITY = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
 METRIC = "range-image columns/s, 64-ring stream"
 
-# algorithmic bytes per range-image cell, per kernel (151 B/cell for the path)
+SPEC_TEXT = {
+    "velodyne64": "synthetic 64-ring 10 Hz Velodyne-like stream (64x2048 columns/rotation, ground plane + 150 boxes",
+    "kitti64": "synthetic 64x2200 KITTI-replay-like stream (kitti_demo configuration, ground plane + 150 boxes",
+    "vls128": "synthetic 128-ring 20 Hz VLS-128-like stream (128x1700 columns/rotation, 8 laser groups with azimuth offsets, "
+              "ground plane + 150 boxes",
+    "os32_left": "synthetic Ouster OS-32 stream, left sensor (32x1024, beam tables of the reference's calibration, rolled +30 deg",
+    "os32_right": "synthetic Ouster OS-32 stream, right sensor (32x1024, beam tables of the reference's calibration, rolled -30 deg",
+    "os32_pair": "synthetic Ouster OS-32 tilted-mount pair (32x1024 each, left sensor on even ranks / right on odd ranks",
+}
+
+# ALGORITHMIC bytes per range-image cell, attributed to the kernel that moves them (151 B/cell for the
+# path: insert 37 r + 57 w, ground 21 r + 3 w, associate 21 r + 4 w, finish/label 4 r + 4 w). Staging arrays, the
+# association view, list scratch and ring recycling are implementation traffic, reported separately.
 KERNEL_BYTES_PER_CELL = {
-    # read x,y,z (+ pose, amortised); write staged odom xyz, distance, azimuth, inclination, column (twice: per firing
-    # and per row); + every field group reset for a recycled cell (one cell retired per cell inserted in steady state)
-    "k_prep": 12 + 28 + (57 + 3 + 8 + 16 + 4 + 4 + 4 + 2 + 4),
-    "k_insert_scan": 8 + 12 + 4,  # read column-in-rotation + distance; write resolved column + rotation; distance write-through
-    "k_scatter": 37 + 57,  # SURVEY 8d insert: read raw record fields, write the 57 B of range-image fields
-    "k_gap_scan": 4 + 4,
-    "k_ground": 21 + 3 + 16 + 4,  # SURVEY 8d ground: 21 read + 3 written, + the association view (16) and mad (4)
-    "k_probe": 21 + 4,  # SURVEY 8d associate
-    "k_probe_heavy": 21 + 4,
-    "k_commit_copy": 4 + 4,
-    "k_commit_roots": 4 + 4,
-    "k_fin_label": 4 + 4,  # SURVEY 8d finish/label
-    "k_clear": 57 + 3 + 8 + 16 + 4 + 4 + 4 + 2 + 4,  # every field group reset for a recycled cell
+    "k_prep": 12,            # x, y, z of the raw record
+    "k_scatter": 25 + 57,    # the rest of the raw record + the 57 B of range-image fields
+    "k_ground": 21 + 3,
+    "k_probe": 21 + 4,       # every non-ignored point is probed once, by k_probe or by k_probe_heavy
+    "k_probe_heavy": 0,
+    "k_fin_label": 4 + 4,
+    "k_push_fused": 151,     # the whole path in one launch (short pushes)
+}
+# implementation traffic per cell on top of that (what ncu's dram / L2 byte counters additionally see)
+KERNEL_EXTRA_BYTES_PER_CELL = {
+    "k_prep": 28 + 102,      # staged odom xyz, distance, azimuth, inclination, column (twice) + recycling of a retired cell
+    "k_scan_check": 4, "k_insert_scan": 8, "k_gap_scan": 8,
+    "k_ground": 16 + 4 + 8,  # association view (float4), mad, inclination-gap carry
+    "k_commit_copy": 8, "k_commit_roots": 8, "k_commit_links": 16,
 }
 
 
@@ -72,12 +89,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_rotations(n_rot_unique=2, seed=1234):
+def rank_spec(spec_name: str, rank: int) -> str:
+    if spec_name == "os32_pair":
+        return "os32_left" if rank % 2 == 0 else "os32_right"
+    return spec_name
+
+
+def make_rotations(n_rot_unique=2, seed=1234, spec_name=None):
     """A few unique rotations of the static-sensor stream; longer streams tile them (a static scene repeats every
     rotation anyway) with fresh stamps / firing indices / unique point indices."""
     from continuous_clustering_b200 import synth
 
-    pts, poses, sp = synth.make_stream(SPEC, n_rotations=n_rot_unique, seed=seed)
+    pts, poses, sp = synth.make_stream(spec_name or SPEC, n_rotations=n_rot_unique, seed=seed)
     return pts, poses, sp
 
 
@@ -92,6 +115,27 @@ def tile_stream(base_pts, base_poses, sp, start, n):
     pts["firing_index"] = k[:, None]
     pts["globally_unique_point_index"] = k[:, None] * np.uint64(sp.rows) + np.arange(sp.rows, dtype=np.uint64)[None, :]
     return pts, base_poses[idx].copy()
+
+
+class Stream:
+    """The endless firing stream of one rank: tiled static rotations, or (moving sensor, BASELINE.md section 2: 10 m/s,
+    0.2 rad/s yaw) generated once for as many firings as the run needs -- poses never repeat."""
+
+    def __init__(self, spec_name, seed, moving=False, total_firings=0):
+        from continuous_clustering_b200 import synth
+
+        self.moving = moving
+        if moving:
+            self.pts, self.poses, self.sp = synth.make_stream(spec_name, n_firings=total_firings, seed=seed, moving=True)
+        else:
+            self.pts, self.poses, self.sp = make_rotations(seed=seed, spec_name=spec_name)
+
+    def take(self, start, n):
+        if self.moving:
+            if start + n > self.pts.shape[0]:
+                raise RuntimeError("moving stream exhausted: raise total_firings")
+            return self.pts[start:start + n].copy(), self.poses[start:start + n].copy()
+        return tile_stream(self.pts, self.poses, self.sp, start, n)
 
 
 class ClockSampler:
@@ -146,78 +190,167 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(base_pts, base_poses, sp, columns_target, multi_threaded=True, time_budget_s=25.0):
-    """Times the reference's CPU implementation on this box's host cores. Returns dict for `cpu_baseline`."""
+def workload_name(args):
+    motion = "moving sensor: 10 m/s, 0.2 rad/s yaw" if args.moving else "static sensor"
+    return f"{SPEC_TEXT[args.spec]}, {motion}), {args.batch} firings per push"
+
+
+def config_dict(args):
+    """The same dict in both arms (the driver compares them)."""
+    from continuous_clustering_b200 import synth
+
+    sp = synth.spec(rank_spec(args.spec, 0))
+    return {"workload": workload_name(args), "spec": args.spec, "moving": bool(args.moving), "batch_firings": args.batch,
+            "rows": sp.rows, "columns_per_rotation": sp.num_columns, "rotation_hz": sp.rotation_hz}
+
+
+def metric_name(args):
+    return METRIC if args.spec in ("velodyne64", "kitti64") else f"range-image columns/s, {args.spec} stream"
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_run(stream, spec_name, columns_target, multi_threaded=True, time_budget_s=25.0, n_streams=1):
+    """Times the reference's CPU implementation on this box's host cores (n_streams concurrent, independent sensor
+    streams: one object each, like the reference's one-process-per-sensor deployment). Returns dict for `cpu_baseline`."""
     from oracle import drvlib
 
     kind = "reference" if drvlib.have_ref() else "port"
     lib = drvlib.REF_LIB if kind == "reference" else drvlib.ORACLE_LIB
     if kind == "port":
         multi_threaded = False  # the restatement is the deterministic single-threaded mode only
-    cfg = drvlib.stream_config(SPEC, is_single_threaded=0 if multi_threaded else 1)
-    d = drvlib.Driver(lib)
-    d.configure(cfg, sp.rows)
-    d.set_record(0)
+    sp = stream.sp
+    cfg = drvlib.stream_config(spec_name, is_single_threaded=0 if multi_threaded else 1)
     rot = sp.num_columns
+    drivers = []
+    for _ in range(n_streams):
+        d = drvlib.Driver(lib)
+        d.configure(cfg, sp.rows)
+        d.set_record(0)
+        drivers.append(d)
     fed = 0
-    t_total = 0.0
-    # warm-up: two rotations
-    for w in range(2):
-        pts, poses = tile_stream(base_pts, base_poses, sp, fed, rot)
-        d.prepare(pts, poses)
-        d.run_prepared(0, rot, 3 * rot if multi_threaded else 0)
+    for w in range(2):  # warm-up: two rotations
+        pts, poses = stream.take(fed, rot)
+        for d in drivers:
+            d.prepare(pts, poses)
+            d.run_prepared(0, rot, 3 * rot if multi_threaded else 0)
         fed += rot
     timed = 0
+    t_total = 0.0
     t_wall0 = time.time()
     chunk = 16 * rot  # long runs, so that draining the reference's thread pipeline between runs does not matter
     while timed < columns_target and (time.time() - t_wall0) < time_budget_s:
-        pts, poses = tile_stream(base_pts, base_poses, sp, fed, chunk)
-        d.prepare(pts, poses)  # shared_ptr construction outside the timed region
-        t_total += d.run_prepared(0, chunk, 3 * rot if multi_threaded else 0)
+        pts, poses = stream.take(fed, chunk)
+        for d in drivers:
+            d.prepare(pts, poses)  # shared_ptr construction outside the timed region
+        secs = [0.0] * n_streams
+
+        def work(i):
+            secs[i] = drivers[i].run_prepared(0, chunk, 3 * rot if multi_threaded else 0)
+
+        if n_streams == 1:
+            work(0)
+            t_total += secs[0]
+        else:
+            th = [threading.Thread(target=work, args=(i,)) for i in range(n_streams)]
+            t0 = time.perf_counter()
+            [t.start() for t in th]
+            [t.join() for t in th]
+            t_total += time.perf_counter() - t0
         fed += chunk
         timed += chunk
-    d.close()
-    cores = 8 if multi_threaded else 1  # 4 stage threads + 3 publishers + producer (cpp:49-63)
+    for d in drivers:
+        d.close()
+    cores = (8 if multi_threaded else 1) * n_streams  # per stream: 4 stage threads + 3 publishers + producer (cpp:49-63)
     return {
-        "value": timed / t_total if t_total > 0 else 0.0,
+        "value": n_streams * timed / t_total if t_total > 0 else 0.0,
         "unit": "columns/s",
         "cores": cores,
         "kind": kind,
-        "sample": f"{timed} columns ({timed // rot} rotations of the {sp.rows}x{rot} synthetic stream) after 2 warm-up "
-                  f"rotations, {'multi-threaded 5-stage pipeline' if multi_threaded else 'single-threaded mode'}, "
+        "sample": f"{n_streams} stream(s) x {timed} columns ({timed // rot} rotations of the {sp.rows}x{rot} synthetic stream) "
+                  f"after 2 warm-up rotations, {'multi-threaded 5-stage pipeline' if multi_threaded else 'single-threaded mode'}, "
                   f"no-op callbacks, host has {os.cpu_count()} logical cores",
         "seconds": t_total,
     }
 
 
+def cpu_reference_latency(stream, spec_name, n_firings=None):
+    """per-addFiring wall time of the reference in its single-threaded mode (every stage a
+    firing triggers, callbacks included, runs inside the call)."""
+    from oracle import drvlib
+
+    if not drvlib.have_ref():
+        return None
+    sp = stream.sp
+    n = n_firings or 3 * sp.num_columns
+    cfg = drvlib.stream_config(spec_name, is_single_threaded=1)
+    d = drvlib.Driver(drvlib.REF_LIB)
+    d.configure(cfg, sp.rows)
+    d.set_record(0)
+    pts, poses = stream.take(0, n)
+    d.prepare(pts, poses)
+    lat = d.run_prepared_latency(0, n)[sp.num_columns:]  # the first rotation fills the ring
+    d.close()
+    return {"latency_us_p50": float(np.median(lat)), "latency_us_p99": float(np.percentile(lat, 99)),
+            "latency_us_mean": float(lat.mean()),
+            "latency_sample": f"{len(lat)} addFiring calls, single-threaded mode (1 core), no-op callbacks"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    base_pts, base_poses, sp = make_rotations()
+    spec_name = rank_spec(args.spec, 0)
+    stream = Stream(spec_name, 1234)
     steps, warm = args.steps, args.warmup
+    n_streams = max(1, world)
+    target = max(1, steps) * args.batch * 8
     try:
-        res = cpu_reference_run(base_pts, base_poses, sp, columns_target=max(1, steps) * args.batch * 8,
-                                multi_threaded=True, time_budget_s=60.0)
+        res = cpu_reference_run(stream, spec_name, columns_target=target, multi_threaded=True, time_budget_s=60.0, n_streams=n_streams)
     except Exception as e:  # the reference's multi-threaded mode can throw its ring-overrun error (cpp:337-344)
-        res = cpu_reference_run(base_pts, base_poses, sp, columns_target=max(1, steps) * args.batch * 8,
-                                multi_threaded=False, time_budget_s=60.0)
+        res = cpu_reference_run(stream, spec_name, columns_target=target, multi_threaded=False, time_budget_s=60.0, n_streams=n_streams)
         res["sample"] += f" (multi-threaded run failed: {str(e)[:80]})"
+    cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    try:
+        lat = cpu_reference_latency(stream, spec_name)
+        if lat:
+            cpu.update(lat)
+    except Exception as e:
+        cpu["latency_error"] = str(e)[:120]
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "columns/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * args.batch / res["value"] if res["value"] else None,
+        "impl": "reference", "metric": metric_name(args), "value": res["value"], "unit": "columns/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * args.batch * n_streams / res["value"] if res["value"] else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64 (reference CPU arithmetic)",
-        "data": "synthetic", "config": {"workload": workload_name(args), "batch_firings": args.batch},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "data": "synthetic", "config": config_dict(args), "cpu_baseline": cpu,
         "e2e": {"value": res["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_name(args):
-    return (f"synthetic 64-ring 10 Hz Velodyne-like stream (64x2048 columns/rotation, ground plane + 150 boxes, "
-            f"static sensor), {args.batch} firings per push")
+# ---------------------------------------------------------------------------------------------------- facade harness
+def facade_run(cfg_c, sp, pts, poses, batch, pipelined, callback_mode, warm, device, want_calls=False):
+    """build/libcc_facade_bench.so (facade/tools/facade_bench.cpp): the stream through the drop-in C++ class, one
+    addFiring call per firing."""
+    path = os.path.join(HERE, "build", "libcc_facade_bench.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.fb_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.c_int, C.c_void_p, C.c_void_p, C.c_char_p]
+    n = pts.shape[0]
+    calls = np.zeros(n, dtype=np.float64) if want_calls else None
+    result = np.zeros(8, dtype=np.float64)
+    err = C.create_string_buffer(256)
+    tf = np.asarray(IDENTITY, dtype=np.float64)
+    pts = np.ascontiguousarray(pts)
+    poses = np.ascontiguousarray(poses, dtype=np.float64)
+    rc = lib.fb_run(C.addressof(cfg_c), sp.rows, tf.ctypes.data, n, pts.ctypes.data, poses.ctypes.data, batch, int(pipelined),
+                    callback_mode, warm, device, calls.ctypes.data if want_calls else None, result.ctypes.data, err)
+    if rc != 0:
+        raise RuntimeError("facade_bench: " + err.value.decode(errors="replace"))
+    return {"seconds": float(result[0]), "column_callbacks": int(result[1]), "cluster_callbacks": int(result[2]),
+            "cluster_points": int(result[3]), "packed_bytes": int(result[5]), "calls_us": calls}
 
 
 def main():
@@ -225,8 +358,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="firings per push (= per step); 4096 = two rotations")
+    ap.add_argument("--batch", type=int, default=4096, help="firings per push (= per step); 4096 = two rotations of 64x2048")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spec", default=SPEC, choices=sorted(SPEC_TEXT))
+    ap.add_argument("--moving", action="store_true", help="moving sensor (10 m/s, 0.2 rad/s yaw) instead of the static pose")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident leg + kernel tables only (profiling runs)")
     args = ap.parse_args()
@@ -254,9 +389,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     K, W, B = args.steps, args.warmup, args.batch
-    base_pts, base_poses, sp = make_rotations(seed=1234 + rank)  # every rank = a different sensor stream
-    cfg = stream_configuration(SPEC)
+    spec_name = rank_spec(args.spec, rank)
+    # every rank = a different sensor stream; the moving variant needs every firing it will ever feed up front
+    stream = Stream(spec_name, 1234 + rank, args.moving, total_firings=(W + K) * B + 64 * B if args.moving else 0)
+    sp = stream.sp
+    cfg = stream_configuration(spec_name)
     R = sp.rows
+    B = min(B, 3 * sp.num_columns)  # the ring keeps 10 rotations: a push may span at most 3
+    rec_bytes, pose_bytes = R * 48, 12 * 8
+    full = rank == 0 and world == 1 and not args.quick and not args.moving
 
     def new_handle(batch=None):
         cc = ContinuousClustering(device=local_rank, max_firings_per_push=max(batch or B, 256))
@@ -276,19 +417,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def to_device(pts, poses):
+        n = pts.shape[0]
+        return (torch.from_numpy(pts.view(np.uint8).reshape(n, R * 48)).cuda(), torch.from_numpy(poses).cuda())
+
+    def pinned(pts, poses):
+        n = pts.shape[0]
+        pp = torch.from_numpy(pts.view(np.uint8).reshape(n, R * 48)).pin_memory()
+        pq = torch.from_numpy(poses).pin_memory()
+        return pp, pq, pp.numpy().view(pts.dtype).reshape(n, R), pq.numpy()
+
     # ------------------------------------------------------------------ device-resident leg ("value")
-    def device_leg(B, K, W, sample_clocks, flush_each_step=False):
+    def device_leg(B, K, W, sample_clocks, flush_each_step=False, src=None, reduce=True):
         """K timed pushes of B firings with the inputs already in HBM; returns a dict.
         flush_each_step=False: the pushes run back to back; every push reads input bytes nothing has touched since L2 was
         flushed right before the timed region (inputs larger than L2, streamed once), the stream's own state stays as
         warm as it is in steady state. flush_each_step=True: additionally a 256 MiB write before every push, its
         event-timed duration subtracted."""
+        src = src or stream
         total = (W + K) * B
-        pts, poses = tile_stream(base_pts, base_poses, sp, 0, total)
-        d_pts = torch.from_numpy(pts.view(np.uint8).reshape(total, R * 48)).cuda()
-        d_poses = torch.from_numpy(poses).cuda()
+        pts, poses = src.take(0, total)
+        d_pts, d_poses = to_device(pts, poses)
         cc = new_handle(B)
-        stream = torch.cuda.ExternalStream(cc.stream)
+        cuda_stream = torch.cuda.ExternalStream(cc.stream)
 
         def submit_dev(step):
             cc.submitFiringsDevice(d_pts.data_ptr() + step * B * rec_bytes, d_poses.data_ptr() + step * B * pose_bytes, B, R)
@@ -296,36 +447,36 @@ def main():
         for s in range(W):
             cc.addFiringsDevice(d_pts.data_ptr() + s * B * rec_bytes, d_poses.data_ptr() + s * B * pose_bytes, B, R)
         sampler = ClockSampler(local_rank) if sample_clocks else None
-        barrier()
+        if reduce:
+            barrier()
+        else:
+            torch.cuda.synchronize()
         if sampler:
             sampler.start()
         launches0 = cc.total_launches
         # Timed region: K pushes, two in flight (submit(k + 1); wait(k)) so that the host's result handling of push k
-        # overlaps the kernels of push k + 1. Before every push L2 is flushed by a 256 MiB write on the same stream; the
-        # flushes are bracketed by their own events and their device time is subtracted.
+        # overlaps the kernels of push k + 1.
         ev_fa = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
         ev_fb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
         ev_end = torch.cuda.Event(enable_timing=True)
+        ev_begin = torch.cuda.Event(enable_timing=True)
         dev_ms = []
         exact_pushes = 0
 
-        ev_begin = torch.cuda.Event(enable_timing=True)
-
         def flush_and_submit(s):
             if flush_each_step:
-                with torch.cuda.stream(stream):
-                    ev_fa[s].record(stream)
+                with torch.cuda.stream(cuda_stream):
+                    ev_fa[s].record(cuda_stream)
                     l2_flush(s)
-                    ev_fb[s].record(stream)
+                    ev_fb[s].record(cuda_stream)
             submit_dev(W + s)
 
-        with torch.cuda.stream(stream):
+        with torch.cuda.stream(cuda_stream):
             l2_flush(255)  # nothing of the inputs is cache resident when the timed region starts
-            ev_begin.record(stream)
         torch.cuda.synchronize()
         t_wall0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            ev_begin.record(stream)
+        with torch.cuda.stream(cuda_stream):
+            ev_begin.record(cuda_stream)
         flush_and_submit(0)
         for s in range(K):
             if s + 1 < K:
@@ -333,8 +484,8 @@ def main():
             res = cc.wait()
             dev_ms.append(res.info.device_ms)
             exact_pushes += int(res.info.used_exact_path)
-        with torch.cuda.stream(stream):
-            ev_end.record(stream)
+        with torch.cuda.stream(cuda_stream):
+            ev_end.record(cuda_stream)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
         launches = cc.total_launches - launches0
@@ -342,25 +493,25 @@ def main():
         total_ms = ev_begin.elapsed_time(ev_end)
         clocks = sampler.stop() if sampler else None
         elapsed = (total_ms - flush_ms) / 1e3
-        if dist is not None:
+        nranks = 1
+        if dist is not None and reduce:
             t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             elapsed = float(t.item())
-        return {"cc": cc, "stream": stream, "value": world * K * B / elapsed, "elapsed": elapsed, "dev_ms": dev_ms,
+            nranks = world
+        return {"cc": cc, "stream": cuda_stream, "value": nranks * K * B / elapsed, "elapsed": elapsed, "dev_ms": dev_ms,
                 "launches": launches, "exact": exact_pushes, "clocks": clocks, "t_wall": t_wall, "fed": total}
 
-    rec_bytes, pose_bytes = R * 48, 12 * 8
     leg = device_leg(B, K, W, True)
-    cc, stream = leg["cc"], leg["stream"]
+    cc, cuda_stream = leg["cc"], leg["stream"]
     value, elapsed, dev_ms, launches, exact_pushes, clocks, t_wall = (leg["value"], leg["elapsed"], leg["dev_ms"], leg["launches"],
                                                                       leg["exact"], leg["clocks"], leg["t_wall"])
     total = leg["fed"]
 
-    # per-push latency with ONE push in flight (the synchronous call a latency-sensitive caller makes)
+    # per-push latency with ONE push of B firings in flight (the synchronous call), device-resident inputs
     sync_ms = []
-    lat_pts, lat_poses = tile_stream(base_pts, base_poses, sp, total, 6 * B)
-    d_lat = torch.from_numpy(lat_pts.view(np.uint8).reshape(6 * B, R * 48)).cuda()
-    d_lat_poses = torch.from_numpy(lat_poses).cuda()
+    lat_pts, lat_poses = stream.take(total, 6 * B)
+    d_lat, d_lat_poses = to_device(lat_pts, lat_poses)
     for r in range(6):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -372,13 +523,12 @@ def main():
     # table below serialises the launches and adds an event round trip to every kernel
     trace_table = None
     if rank == 0:
-        tr_pts, tr_poses = tile_stream(base_pts, base_poses, sp, total, 4 * B)
-        d_tr = torch.from_numpy(tr_pts.view(np.uint8).reshape(4 * B, R * 48)).cuda()
-        d_tr_poses = torch.from_numpy(tr_poses).cuda()
+        tr_pts, tr_poses = stream.take(total, 4 * B)
+        d_tr, d_tr_poses = to_device(tr_pts, tr_poses)
         cc.debug_trace(True)
         acc_tr = {}
         for r in range(4):
-            with torch.cuda.stream(stream):
+            with torch.cuda.stream(cuda_stream):
                 l2_flush(r)
             cc.addFiringsDevice(d_tr.data_ptr() + r * B * rec_bytes, d_tr_poses.data_ptr() + r * B * pose_bytes, B, R)
             for name, a, z, longest, blocks in cc.get_trace():
@@ -395,14 +545,14 @@ def main():
         cc.set_kernel_timing(True)
         acc = {}
         reps = 5
-        extra, extra_poses = tile_stream(base_pts, base_poses, sp, total, reps * B)
-        d_extra = torch.from_numpy(extra.view(np.uint8).reshape(reps * B, R * 48)).cuda()
-        d_extra_poses = torch.from_numpy(extra_poses).cuda()
+        extra, extra_poses = stream.take(total, reps * B)
+        d_extra, d_extra_poses = to_device(extra, extra_poses)
+        n_trees = []
         for r in range(reps):
-            with torch.cuda.stream(stream):
+            with torch.cuda.stream(cuda_stream):
                 l2_flush(r)
             res = cc.addFiringsDevice(d_extra.data_ptr() + r * B * rec_bytes, d_extra_poses.data_ptr() + r * B * pose_bytes, B, R)
-            ncols = int(res.info.ground_to_gcol - res.info.ground_from_gcol)
+            n_trees.append(int(getattr(res.info, "n_unfinished_trees", 0)))
             for name, ms in cc.kernel_timings():
                 a = acc.setdefault(name, [0.0, 0])
                 a[0] += ms
@@ -410,14 +560,18 @@ def main():
         cc.set_kernel_timing(False)
         tot = sum(v[0] for v in acc.values())
         kernel_table = {k: {"ms_per_step": v[0] / reps, "share": v[0] / tot} for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
-        # the dominant kernel among those that stream the range image (k_fin_all works on the list of unfinished trees,
-        # a few thousand entries: it has no per-cell traffic to put against a bandwidth roofline)
-        top = next((k for k in kernel_table if k in KERNEL_BYTES_PER_CELL), next(iter(kernel_table)))
         peak, peak_src = load_peaks()
-        bpc = KERNEL_BYTES_PER_CELL.get(top, 8)
-        alg_bytes = bpc * B * R
+        top = next(iter(kernel_table))  # the kernel with the largest share of the step, whatever it is
+
+        def alg_bytes(k):
+            if k == "k_fin_all":
+                # list work, not per-cell: per unfinished tree 36 B read (list entry, union-find parent, finish azimuth,
+                # root column, last column, point count) + 4 B written (compacted list); per new column 8 + 8 B
+                return int(np.mean(n_trees) if n_trees else 0) * 40 + B * 16
+            return KERNEL_BYTES_PER_CELL.get(k, 0) * B * R
+
         dur_s = kernel_table[top]["ms_per_step"] / 1e3
-        achieved = alg_bytes / dur_s / 1e9
+        achieved = alg_bytes(top) / dur_s / 1e9
         traffic, traffic_src = None, None
         tp = os.path.join(HERE, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
@@ -426,68 +580,136 @@ def main():
             if top in tj.get("kernels", {}):
                 traffic = tj["kernels"][top]["dram_bytes"]
                 traffic_src = tj.get("source")
+        by_kernel = {}
+        for k, v in kernel_table.items():
+            ab = alg_bytes(k)
+            by_kernel[k] = {"algorithmic_bytes_per_launch": ab, "achieved_gbs": ab / (v["ms_per_step"] / 1e3) / 1e9,
+                            "frac": ab / (v["ms_per_step"] / 1e3) / 1e9 / peak,
+                            "extra_implementation_bytes_per_launch": KERNEL_EXTRA_BYTES_PER_CELL.get(k, 0) * B * R}
+        single_cta = {"k_fin_all", "k_scan_lite", "k_insert_scan"}
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": kernel_table[top]["share"],
-                    "by_kernel": {k: {"algorithmic_bytes_per_launch": KERNEL_BYTES_PER_CELL[k] * B * R,
-                                      "achieved_gbs": KERNEL_BYTES_PER_CELL[k] * B * R / (v["ms_per_step"] / 1e3) / 1e9,
-                                      "frac": KERNEL_BYTES_PER_CELL[k] * B * R / (v["ms_per_step"] / 1e3) / 1e9 / peak}
-                                  for k, v in kernel_table.items() if k in KERNEL_BYTES_PER_CELL},
+                    "algorithmic_bytes_per_launch": alg_bytes(top), "kernel_share_of_step": kernel_table[top]["share"],
+                    "limiter": ("latency: single-CTA list phases separated by block barriers, not bandwidth" if top in single_cta
+                                else "latency of dependent L2 round trips; the working set of a push is L2 resident"),
+                    "by_kernel": by_kernel,
                     "path_bytes_per_cell": 151, "path_achieved_gbs": value / world * R * 151 / 1e9,
                     "path_frac": value / world * R * 151 / 1e9 / peak}
     cc.close()
 
+    # ------------------------------------------------------------------ per-GPU push latency (every rank; BASELINE config 5)
+    LB = 64
+
+    def latency_leg(nl=200, warm=60):
+        ccl = new_handle(LB)
+        ccl.set_label_prefetch(True)
+        lp, lq = stream.take(0, nl * LB)
+        _keep, _keepq, hlp, hlq = pinned(lp, lq)
+        lat, dev = [], []
+        launches = 0
+        for i in range(nl):
+            t0 = time.perf_counter()
+            r = ccl.addFirings(hlp[i * LB:(i + 1) * LB], hlq[i * LB:(i + 1) * LB])
+            lat.append(1e6 * (time.perf_counter() - t0))
+            dev.append(1e3 * r.info.device_ms)
+            launches = int(r.info.gpu_launches)
+        ccl.close()
+        lat, dev = np.array(lat[warm:]), np.array(dev[warm:])
+        hist, edges = np.histogram(lat, bins=[0, 60, 70, 80, 90, 100, 110, 120, 140, 160, 200, 300, 1e9])
+        return {"batch_firings": LB, "call": "cc_push_firings via ContinuousClustering.addFirings (page-locked host buffers in; "
+                "events / clusters / member lists / labels back on the host)", "launches_per_push": launches,
+                "per_push_us_p50": float(np.median(lat)), "per_push_us_p99": float(np.percentile(lat, 99)),
+                "per_push_us_mean": float(lat.mean()), "per_push_device_us_p50": float(np.median(dev)),
+                "per_push_ms_p50": float(np.median(lat)) / 1e3, "per_push_ms_p99": float(np.percentile(lat, 99)) / 1e3,
+                "columns_per_s": LB / (float(np.mean(lat)) / 1e6),
+                "histogram_us": {"edges": [float(e) for e in edges[:-1]] + ["inf"], "counts": [int(c) for c in hist]}}
+
+    latency_mode = None
+    per_gpu_latency = None
+    if not args.quick:
+        barrier()
+        mine = latency_leg()
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {"rank": rank, "gpu": local_rank, "spec": spec_name,
+                                              **{k: mine[k] for k in ("per_push_us_p50", "per_push_us_p99", "per_push_device_us_p50", "histogram_us")}})
+            per_gpu_latency = gathered
+        else:
+            per_gpu_latency = [{"rank": 0, "gpu": local_rank, "spec": spec_name,
+                                **{k: mine[k] for k in ("per_push_us_p50", "per_push_us_p99", "per_push_device_us_p50", "histogram_us")}}]
+        latency_mode = mine
+
     # ------------------------------------------------------------------ other operating points (rank 0, single GPU)
-    batch_sweep, latency_mode, flushed = None, None, None
-    if rank == 0 and world == 1 and not args.quick:
+    batch_sweep, flushed, facade, exact_path = None, None, None, None
+    if full:
         lg = device_leg(B, 10, 3, False, flush_each_step=True)
         flushed = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 10,
                    "per_push_device_ms_p50": float(np.median(lg["dev_ms"])),
                    "how": "256 MiB device write before every timed push, its event-timed duration subtracted"}
         lg["cc"].close()
         batch_sweep = {}
-        for b2 in (1024, 2048, 6144):
-            if b2 == B:
+        for b2 in (256, 1024, 2048, 6144):
+            if b2 == B or b2 > 3 * sp.num_columns:
                 continue
             lg = device_leg(b2, 8, 3, False)
             batch_sweep[str(b2)] = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 8,
-                                    "per_push_device_ms_p50": float(np.median(lg["dev_ms"]))}
+                                    "per_push_device_ms_p50": float(np.median(lg["dev_ms"])),
+                                    "launches_per_push": lg["launches"] / 8}
             lg["cc"].close()
-        # latency mode: small synchronous pushes (one in flight), host buffers, results back on the host
-        LB = 64
-        ccl = new_handle(LB)
-        ccl.set_label_prefetch(True)
-        nl = 120
-        lp, lq = tile_stream(base_pts, base_poses, sp, 0, nl * LB)
-        pin_lp = torch.from_numpy(lp.view(np.uint8).reshape(nl * LB, R * 48)).pin_memory()
-        pin_lq = torch.from_numpy(lq).pin_memory()
-        hlp = pin_lp.numpy().view(lp.dtype).reshape(nl * LB, R)
-        hlq = pin_lq.numpy()
-        lat = []
-        for i in range(nl):
-            t0 = time.perf_counter()
-            ccl.addFirings(hlp[i * LB:(i + 1) * LB], hlq[i * LB:(i + 1) * LB])
-            lat.append(1e3 * (time.perf_counter() - t0))
-        ccl.close()
-        lat = np.array(lat[40:])
-        latency_mode = {"batch_firings": LB, "call": "addFirings (host buffers in, events / clusters / labels back on the host)",
-                        "per_push_ms_p50": float(np.median(lat)), "per_push_ms_p99": float(np.percentile(lat, 99)),
-                        "columns_per_s": LB / (float(np.mean(lat)) / 1e3)}
+        # the exact column-sequential path: a closed wall around the sensor makes one cluster span a full rotation
+        # (forced finish, cpp:909-919): speculative commits abort and the flagged columns go through k_careful
+        try:
+            from continuous_clustering_b200 import synth
+
+            class WallStream:
+                pass
+
+            ws = WallStream()
+            wp, wq, ws.sp = synth.make_stream(spec_name, n_rotations=3.0, seed=3, n_boxes=0, wall_radius=12.0)
+            ws.take = lambda a, n: (wp[a:a + n].copy(), wq[a:a + n].copy())
+            bw = 1024
+            kw = wp.shape[0] // bw - 2
+            lg = device_leg(bw, kw, 2, False, src=ws)
+            exact_path = {"workload": "closed wall around the sensor (one cluster spans a rotation: forced finish)",
+                          "batch_firings": bw, "steps": kw, "columns_per_s": lg["value"], "exact_path_pushes": lg["exact"],
+                          "per_push_device_ms_p50": float(np.median(lg["dev_ms"])), "launches_per_push": lg["launches"] / kw}
+            lg["cc"].close()
+        except Exception as e:
+            exact_path = {"error": str(e)[:200]}
+        # the drop-in C++ class: one addFiring call per firing
+        try:
+            cfg_c = cfg.to_c()
+            nf = 16 * 2048
+            fp, fq = stream.take(0, nf + 2048)
+            facade = {}
+            for name, batch, pipelined, mode in (("sync_batch64_kitti_callbacks", 64, 0, 1), ("sync_batch64_no_callbacks", 64, 0, 0),
+                                                  ("sync_batch64_packed_pointcloud2", 64, 0, 2),
+                                                  ("pipelined_batch2048_kitti_callbacks", 2048, 1, 1),
+                                                  ("pipelined_batch2048_packed_pointcloud2", 2048, 1, 2),
+                                                  ("pipelined_batch2048_no_callbacks", 2048, 1, 0)):
+                r = facade_run(cfg_c, sp, fp, fq, batch, pipelined, mode, 2048, local_rank, want_calls=(batch == 64))
+                if r is None:
+                    facade = {"unavailable": "build/libcc_facade_bench.so not built"}
+                    break
+                entry = {"columns_per_s": nf / r["seconds"], "column_callbacks": r["column_callbacks"],
+                         "cluster_callbacks": r["cluster_callbacks"], "packed_bytes": r["packed_bytes"]}
+                if r["calls_us"] is not None:
+                    calls = r["calls_us"][2048:]
+                    pushes = calls[batch - 1::batch]  # every batch-th call carries the device push and its callbacks
+                    entry.update({"addFiring_us_p50": float(np.median(calls)), "addFiring_us_p99": float(np.percentile(calls, 99)),
+                                  "push_call_us_p50": float(np.median(pushes)), "push_call_us_p99": float(np.percentile(pushes, 99))})
+                facade[name] = entry
+        except Exception as e:
+            facade = {"error": str(e)[:200]}
 
     # ------------------------------------------------------------------ end-to-end leg through the public API
     cc = new_handle()
     cc.set_label_prefetch(True)  # the ground labels of the new columns come back with every push's results
-    if args.quick:
-        K_e2e = min(K, 2)
-    else:
-        K_e2e = K
+    K_e2e = min(K, 2) if args.quick else K
     total = (W + K_e2e) * B
-    h_pts, h_poses = tile_stream(base_pts, base_poses, sp, 0, total)
-    # page-locked host buffers (the contract's "pinned host memory"): cc_push_firings copies them straight to the device
-    pin_pts = torch.from_numpy(h_pts.view(np.uint8).reshape(total, R * 48)).pin_memory()
-    pin_poses = torch.from_numpy(h_poses).pin_memory()
-    h_pts = pin_pts.numpy().view(h_pts.dtype).reshape(total, R)
-    h_poses = pin_poses.numpy()
+    h_pts, h_poses = stream.take(0, total)
+    # page-locked host buffers (the contract's "pinned host memory"): cc_submit_firings copies them straight to the device
+    pin_pts, pin_poses, h_pts, h_poses = pinned(h_pts, h_poses)
     d2h = 0
     for s in range(W):
         cc.addFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
@@ -506,41 +728,58 @@ def main():
         d2h += res.clusters.nbytes + res.cluster_points.nbytes + labels.nbytes + labels.shape[0] * 8 + 512
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_rank = K_e2e * B / e2e_s
+    per_rank_e2e = None
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, e2e_rank)
+        per_rank_e2e = gathered
     e2e_value = world * K_e2e * B / e2e_s
     cc.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_stream = stream if not args.moving else Stream(spec_name, 1234)
         try:
-            cpu = cpu_reference_run(base_pts, base_poses, sp, columns_target=10_000_000, multi_threaded=True, time_budget_s=20.0)
+            cpu = cpu_reference_run(cpu_stream, spec_name, columns_target=10_000_000, multi_threaded=True, time_budget_s=20.0)
         except Exception as e:
-            cpu = cpu_reference_run(base_pts, base_poses, sp, columns_target=10_000_000, multi_threaded=False, time_budget_s=20.0)
+            cpu = cpu_reference_run(cpu_stream, spec_name, columns_target=10_000_000, multi_threaded=False, time_budget_s=20.0)
             cpu["sample"] += f" (multi-threaded run failed: {str(e)[:80]})"
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            lat = cpu_reference_latency(cpu_stream, spec_name)
+            if lat:
+                cpu.update(lat)
+        except Exception as e:
+            cpu["latency_error"] = str(e)[:120]
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(args), "value": value, "unit": "columns/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (+f64 rigid transforms, u32 union-find)", "data": "synthetic",
-            "config": {"workload": workload_name(args), "batch_firings": B, "rows": R, "columns_per_rotation": sp.num_columns,
-                       "l2": f"inputs larger than L2: {(W + K) * B * (rec_bytes + pose_bytes) >> 20} MiB of firings streamed once, {B * (rec_bytes + pose_bytes) >> 20} MiB of never-touched input per step; L2 flushed (256 MiB write) once before the timed region; timed pushes run back to back. l2_flush_each_step reports the same with a flush before every push",
-                       "pipelining": "two pushes in flight (cc_submit_firings_device / cc_wait); end-to-end leg: a third host push staged",
-                       "streams": f"{world} independent sensor stream(s), one per GPU, no data-path collective",
-                       "exact_path_pushes": exact_pushes},
+            "config": config_dict(args),
+            "run": {"l2": f"inputs larger than L2: {(W + K) * B * (rec_bytes + pose_bytes) >> 20} MiB of firings streamed once, "
+                          f"{B * (rec_bytes + pose_bytes) >> 20} MiB of never-touched input per step; L2 flushed (256 MiB write) once "
+                          "before the timed region, timed pushes run back to back; l2_flush_each_step reports the same with a "
+                          "flush before every push",
+                    "pipelining": "two pushes in flight (cc_submit_firings_device / cc_wait); end-to-end leg: a third host push staged",
+                    "streams": f"{world} independent sensor stream(s), one per GPU, no data-path collective",
+                    "exact_path_pushes": exact_pushes},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": B * (rec_bytes + pose_bytes),
-                    "d2h_bytes_per_step": int(d2h // K_e2e)},
+                    "d2h_bytes_per_step": int(d2h // K_e2e), "h2d_gbs_per_rank": e2e_value / world * (rec_bytes + pose_bytes) / 1e9,
+                    "per_rank_columns_per_s": per_rank_e2e},
             "latency": {"per_push_device_ms_p50": float(np.median(dev_ms)),
                         "per_push_sync_call_ms_p50": float(np.median(sync_ms)),
                         "note": "one push = batch_firings columns; every column of a push is charged the whole push",
                         "wall_s": t_wall},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
             "kernels_device_timeline_us": trace_table, "batch_sweep": batch_sweep, "latency_mode": latency_mode,
+            "per_gpu_latency": per_gpu_latency, "facade": facade, "exact_path": exact_path,
             "l2_flush_each_step": flushed,
         }
         print(json.dumps(line))

@@ -71,6 +71,8 @@ class CcBatchInfo(C.Structure):
         ("gpu_launches", C.c_int32),
         ("device_ms", C.c_float),
         ("slow_insert_firings", C.c_int32),
+        ("n_unfinished_trees", C.c_int32),
+        ("fused_launch", C.c_int32),
     ]
 
 

@@ -1398,6 +1398,8 @@ static cc_status_t finish_push(cc_handle* h)
     info.gpu_launches = static_cast<int32_t>(sl.launches1 - sl.launches0);
     info.device_ms = ms;
     info.slow_insert_firings = st.scan_slow_firings + st.scan_fast_firings; // everything the lite path did not take
+    info.n_unfinished_trees = st.n_ulist;
+    info.fused_launch = timed_by_device ? 1 : 0;
     pop();
     return CC_OK;
 }

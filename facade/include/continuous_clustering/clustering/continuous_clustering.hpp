@@ -186,6 +186,23 @@ class ContinuousClustering
     // still outstanding (call it at the end of a replay; reset() discards it like the reference's reset does).
     void setPipelined(bool on);
     void drain();
+    // Publish side on the device: the sensor_msgs/PointCloud2 payloads the ROS node builds with
+    // columnToPointCloud / clusterToPointCloud (ros_utils.cpp:11-77), packed by a kernel byte for byte (point layout
+    // ros_utils.cpp:108-243; 76-byte points for ground_points_only, else 116) into page-locked memory. A node replaces
+    // `msg = columnToPointCloud(clustering_, from, to, frame, stage)` by copying `data` into msg->data.
+    // packColumnsPointCloud2 may be called from inside the finished-column callback; the view is valid until the next call.
+    struct PackedPointCloud2
+    {
+        const uint8_t* data{nullptr};
+        size_t size{0};
+        uint32_t point_step{0}, width{0}, height{0}, n_fields{0};
+        uint64_t stamp_ns{0}; // header stamp: smallest non-zero point stamp / the cluster stamp
+    };
+    PackedPointCloud2 packColumnsPointCloud2(int64_t from, int64_t to, bool ground_points_only);
+    // finished clusters (> 20 points, cpp:1023) as packed messages instead of std::vector<Point>
+    void setFinishedClusterPackedCallback(std::function<void(const PackedPointCloud2&)> cb);
+    // false: range_image_ is not filled before the callbacks (for callers that only use the packed messages)
+    void setMaterialiseRangeImage(bool on);
 
   public:
     // range image (implemented as ring buffer) -- public data members read by callers (hpp:244-251)
@@ -219,6 +236,8 @@ class ContinuousClustering
     bool pipelined_{false};
     std::function<void(int64_t, int64_t, bool)> finished_column_callback_;
     std::function<void(const std::vector<Point>&, uint64_t)> finished_cluster_callback_;
+    std::function<void(const PackedPointCloud2&)> finished_cluster_packed_callback_;
+    bool materialise_{true};
     std::vector<Point> cluster_buffer_;
 };
 

@@ -221,6 +221,38 @@ void ContinuousClustering::setFinishedClusterCallback(std::function<void(const s
 
 void ContinuousClustering::recordJobQueueWorkload(size_t) {}
 
+void ContinuousClustering::setFinishedClusterPackedCallback(std::function<void(const PackedPointCloud2&)> cb)
+{
+    finished_cluster_packed_callback_ = std::move(cb);
+}
+
+void ContinuousClustering::setMaterialiseRangeImage(bool on)
+{
+    materialise_ = on;
+}
+
+static ContinuousClustering::PackedPointCloud2 toPacked(const cc_cloud_view_t& v)
+{
+    ContinuousClustering::PackedPointCloud2 m;
+    m.data = v.data;
+    m.size = static_cast<size_t>(v.data_size);
+    m.point_step = v.point_step;
+    m.width = v.width;
+    m.height = v.height;
+    m.n_fields = v.n_fields;
+    m.stamp_ns = v.stamp_ns;
+    return m;
+}
+
+ContinuousClustering::PackedPointCloud2 ContinuousClustering::packColumnsPointCloud2(int64_t from, int64_t to, bool ground_points_only)
+{
+    cc_cloud_view_t v;
+    int s = cc_pack_columns_pointcloud2(handle_, from, to, ground_points_only ? 1 : 0, &v);
+    if (s != CC_OK)
+        fail(s);
+    return toPacked(v);
+}
+
 void ContinuousClustering::addFiring(const RawPoints::ConstPtr& firing, const Eigen::Isometry3d& odom_from_sensor)
 {
     if (num_rows_ != static_cast<int>(firing->points.size())) // cpp:90-91
@@ -385,7 +417,7 @@ void ContinuousClustering::deliver()
     cc_get_batch_info(handle_, &info);
     ring_buffer_start_global_column_index = info.ring_start_gcol;
     ring_buffer_end_global_column_index = info.ring_end_gcol;
-    if (!finished_column_callback_ && !finished_cluster_callback_)
+    if (!finished_column_callback_ && !finished_cluster_callback_ && !finished_cluster_packed_callback_)
         return;
     std::vector<cc_column_event_t> events(info.n_events);
     std::vector<cc_cluster_t> clusters(info.n_clusters);
@@ -409,7 +441,7 @@ void ContinuousClustering::deliver()
                 lo = std::min(lo, c.min_gcol);
                 hi = std::max(hi, c.max_gcol);
             }
-    if (hi >= lo && hi >= 0)
+    if (hi >= lo && hi >= 0 && (materialise_ || finished_cluster_callback_))
         materialise(lo, hi);
     size_t next = 0;
     for (const auto& e : events)
@@ -417,6 +449,14 @@ void ContinuousClustering::deliver()
         while (next < static_cast<size_t>(e.n_clusters_before) && next < clusters.size())
         {
             const cc_cluster_t& c = clusters[next++];
+            if (c.num_points > 20 && finished_cluster_packed_callback_) // cpp:1023
+            {
+                cc_cloud_view_t v;
+                int s = cc_pack_cluster_pointcloud2(handle_, static_cast<int>(next - 1), &v);
+                if (s != CC_OK)
+                    fail(s);
+                finished_cluster_packed_callback_(toPacked(v));
+            }
             if (c.num_points > 20 && finished_cluster_callback_) // cpp:1023
             {
                 cluster_buffer_.clear();

@@ -159,6 +159,8 @@ typedef struct cc_batch_info
     int32_t gpu_launches;            /* kernels launched for this batch */
     float device_ms;                 /* CUDA-event time of the batch's kernels on the handle's stream */
     int32_t slow_insert_firings;     /* firings that went through the per-firing insertion path (collisions) */
+    int32_t n_unfinished_trees;      /* sc_unfinished_point_trees_.size() after the batch (hpp:273)            */
+    int32_t fused_launch;            /* 1 if the batch ran as ONE fused kernel launch (short pushes) */
 } cc_batch_info_t;
 
 /* Field selector + destination pointers for cc_read_columns. Each non-NULL pointer receives

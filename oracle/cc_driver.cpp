@@ -445,6 +445,48 @@ double drv_run_prepared(drv_t* d, int from, int to, int64_t max_lag_columns)
     return s;
 }
 
+int drv_run_prepared_latency(drv_t* d, int from, int to, double* out_us)
+{
+    if (from < 0 || to > static_cast<int>(d->prepared.size()) || from > to)
+    {
+        d->error = "drv_run_prepared_latency: bad range";
+        return 1;
+    }
+    try
+    {
+        for (int k = from; k < to; k++)
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            d->cc.addFiring(d->prepared[k], d->prepared_poses[k]);
+            out_us[k - from] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        }
+#ifdef CC_B200_FACADE
+        d->cc.flush();
+        d->cc.drain();
+#endif
+    }
+    catch (const std::exception& e)
+    {
+        d->error = e.what();
+        return 1;
+    }
+    return 0;
+}
+
+void drv_set_callbacks(drv_t* d, int callbacks)
+{
+    if (callbacks)
+    {
+        d->cc.setFinishedColumnCallback([d](int64_t from, int64_t to, bool ground_only) { onColumns(d, from, to, ground_only); });
+        d->cc.setFinishedClusterCallback([d](const std::vector<Point>& points, uint64_t stamp) { onCluster(d, points, stamp); });
+    }
+    else
+    {
+        d->cc.setFinishedColumnCallback(nullptr);
+        d->cc.setFinishedClusterCallback(nullptr);
+    }
+}
+
 int64_t drv_num_events(drv_t* d)
 {
     return static_cast<int64_t>(d->events.size());

@@ -98,6 +98,16 @@ DRV_API int drv_ring_buffer_max_columns(drv_t* d);
 DRV_API int drv_prepare(drv_t* d, int n, int rows, const cc_raw_point_t* pts, const double* poses);
 DRV_API double drv_run_prepared(drv_t* d, int from, int to, int64_t max_lag_columns);
 
+/* Per-call latency (per-addFiring p50 / p99): feeds prepared firings [from, to) one addFiring
+ * call at a time and stores the wall-clock duration of every call in out_us[to - from] (microseconds). In the
+ * reference's single-threaded mode the call returns when everything the firing triggered -- segmentation, association,
+ * finish detection, callbacks -- is done; on the facade most calls only buffer and every batch-th call carries the whole
+ * device push and its callbacks. Returns 0, or 1 if the object threw. */
+DRV_API int drv_run_prepared_latency(drv_t* d, int from, int to, double* out_us);
+/* callbacks != 0 (default): the recording callbacks are registered; 0: none are (the object skips whatever it only does
+ * for callbacks, e.g. the facade does not fill range_image_) */
+DRV_API void drv_set_callbacks(drv_t* d, int callbacks);
+
 /* recorded outputs */
 DRV_API int64_t drv_num_events(drv_t* d);
 DRV_API void drv_get_events(drv_t* d, cc_column_event_t* out);

@@ -1025,6 +1025,24 @@ double drv_run_prepared(drv_t* d, int from, int to, int64_t /*max_lag_columns*/)
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+int drv_run_prepared_latency(drv_t* d, int from, int to, double* out_us)
+{
+    const int rows = d->prepared_rows;
+    if (from < 0 || from > to || static_cast<size_t>(to) * rows > d->prepared.size())
+    {
+        d->error = "drv_run_prepared_latency: bad range";
+        return 1;
+    }
+    for (int k = from; k < to; k++)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (drv_add_firings(d, 1, rows, d->prepared.data() + static_cast<size_t>(k) * rows, d->prepared_poses.data() + static_cast<size_t>(k) * 12))
+            return 1;
+        out_us[k - from] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return 0;
+}
+
 int64_t drv_num_events(drv_t* d)
 {
     return static_cast<int64_t>(d->events.size());
@@ -1083,6 +1101,8 @@ void drv_clear_records(drv_t* d)
     d->clusters.clear();
     d->cluster_points.clear();
 }
+
+void drv_set_callbacks(drv_t*, int) {}
 
 // the caller excerpts need real `Point` objects; the restatement works on flat arrays and has none
 int drv_has_caller_excerpts(void)

@@ -213,6 +213,8 @@ class Driver:
         L.drv_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.drv_run_prepared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64]
         L.drv_run_prepared.restype = C.c_double
+        L.drv_run_prepared_latency.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.drv_set_callbacks.argtypes = [C.c_void_p, C.c_int]
         for name in (
             "drv_num_events",
             "drv_num_ground_columns",
@@ -291,6 +293,16 @@ class Driver:
         if s < 0:
             raise RuntimeError(self.error())
         return s
+
+    def run_prepared_latency(self, a: int, b: int) -> np.ndarray:
+        """Wall-clock microseconds of every addFiring call for prepared firings [a, b)."""
+        out = np.zeros(b - a, dtype=np.float64)
+        if self.lib.drv_run_prepared_latency(self.h, a, b, out.ctypes.data):
+            raise RuntimeError(self.error())
+        return out
+
+    def set_callbacks(self, on: bool):
+        self.lib.drv_set_callbacks(self.h, int(on))
 
     # ---- recorded outputs -------------------------------------------------------------------------
     def events(self) -> np.ndarray:
