@@ -73,6 +73,8 @@ class CcBatchInfo(C.Structure):
         ("slow_insert_firings", C.c_int32),
         ("n_unfinished_trees", C.c_int32),
         ("fused_launch", C.c_int32),
+        ("visited_recounts", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -136,8 +138,12 @@ EXPORTED_SYMBOLS = [
     "cc_debug_flag_columns", "cc_get_result_views", "cc_submit_firings", "cc_submit_firings_device", "cc_wait", "cc_pending",
     "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
     "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
-    "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2",
+    "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2", "cc_pack_requests_pointcloud2",
 ]
+
+
+class CcPackRequest(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("cluster_index", C.c_int32), ("from_gcol", C.c_int64), ("to_gcol", C.c_int64)]
 
 
 class CcCloudView(C.Structure):
@@ -181,6 +187,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_export_columns.argtypes = [vp, i64, i64, C.POINTER(vp)]
     lib.cc_pack_columns_pointcloud2.argtypes = [vp, i64, i64, i32, C.POINTER(CcCloudView)]
     lib.cc_pack_cluster_pointcloud2.argtypes = [vp, i32, C.POINTER(CcCloudView)]
+    lib.cc_pack_requests_pointcloud2.argtypes = [vp, i32, vp, vp]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]
     lib.cc_stream.argtypes = [vp]

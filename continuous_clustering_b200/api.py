@@ -356,6 +356,20 @@ class ContinuousClustering:
         self._check(self._L.cc_pack_cluster_pointcloud2(self._h, int(cluster_index), C.byref(v)))
         return self._cloud(v)
 
+    def pack_requests_pointcloud2(self, requests):
+        """Every message of a push with one launch (cc_pack_requests_pointcloud2). requests: [(kind, from_gcol, to_gcol)]
+        with kind 0 ground-stage columns, 1 clustered columns, or (2, cluster_index, cluster_index). Returns the list of
+        clouds (payloads are views valid until the next pack_* call)."""
+        n = len(requests)
+        if n == 0:
+            return []
+        req = (_lib.CcPackRequest * n)()
+        for i, (kind, a, b) in enumerate(requests):
+            req[i].kind, req[i].cluster_index, req[i].from_gcol, req[i].to_gcol = kind, (a if kind == 2 else 0), a, b
+        views = (_lib.CcCloudView * n)()
+        self._check(self._L.cc_pack_requests_pointcloud2(self._h, n, C.addressof(req), C.addressof(views)))
+        return [self._cloud(views[i]) for i in range(n)]
+
     def set_label_prefetch(self, enable: bool):
         """Bring the labels of every push's new columns back with its results (cc_set_label_prefetch)."""
         self._check(self._L.cc_set_label_prefetch(self._h, int(enable)))

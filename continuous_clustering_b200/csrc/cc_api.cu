@@ -77,6 +77,10 @@ struct cc_handle
         cudaEvent_t h2d{nullptr}, h2d0{nullptr}; // of the input buffer the push reads (borrowed, not owned)
         CcHostHeader* h_hdr{nullptr};            // page-locked: completion flag + device timestamps of a fused push
         bool fused{false}, want_fused{false};
+        // the parameters the push was SUBMITTED under (cc_set_config / cc_set_robot_from_sensor may be called while it is
+        // in flight or staged): used for its kernels, for a re-run after the exact path, and for its events and stamps
+        CcDevCfg cfg;
+        bool cfg_has_tf{false};
         unsigned int ticket{0};
         const void* src_points{nullptr}; // fused push: where the kernel fetches the firings from (page-locked host memory)
         const double* src_poses{nullptr};
@@ -99,6 +103,8 @@ struct cc_handle
         double* h_poses{nullptr};
         cudaEvent_t h2d0{nullptr}, h2d{nullptr};
         int n{0};
+        CcDevCfg cfg; // snapshot taken when the push was submitted (see Slot::cfg)
+        bool cfg_has_tf{false};
         bool fused{false}; // no copy-engine transfer was queued: the fused kernel fetches src_* itself
         const void* src_points{nullptr};
         const double* src_poses{nullptr};
@@ -132,6 +138,11 @@ struct cc_handle
     size_t counts_cap{0};
     unsigned long long* d_min_stamp{nullptr};
     unsigned long long* h_min_stamp{nullptr};
+    CcPackRequest* h_requests{nullptr}; // page-locked request table of cc_pack_requests_pointcloud2 + min stamps behind it
+    CcPackRequest* d_requests{nullptr};
+    unsigned long long* d_req_stamps{nullptr};
+    unsigned long long* h_req_stamps{nullptr};
+    int requests_cap{0};
     const CcClusterPoint* last_points_dev{nullptr}; // member lists of the last finished push, on the device
     CcDevState* h_state{nullptr}; // pinned mirror (reset, column-sequential path)
     CcDevState state{};
@@ -446,6 +457,14 @@ void cc_destroy(cc_handle_t* h)
         cudaFree(h->d_counts);
     if (h->d_min_stamp)
         cudaFree(h->d_min_stamp);
+    if (h->h_requests)
+        cudaFreeHost(h->h_requests);
+    if (h->h_req_stamps)
+        cudaFreeHost(h->h_req_stamps);
+    if (h->d_requests)
+        cudaFree(h->d_requests);
+    if (h->d_req_stamps)
+        cudaFree(h->d_req_stamps);
     if (h->d_trace)
         cudaFree(h->d_trace);
     if (h->ev0)
@@ -857,12 +876,15 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
 
 // cudaEventSynchronize wakes up late (hundreds of microseconds) while other work keeps the device busy; a push is
 // only a few hundred microseconds long, so poll instead
+static bool g_block_on_events = std::getenv("CC_B200_BLOCKING_WAIT") != nullptr; // several ranks per socket: do not spin
 static cudaError_t spin_wait(cudaEvent_t e)
 {
 #ifdef CC_EMU
     (void)e;
     return cudaSuccess;
 #else
+    if (g_block_on_events)
+        return cudaEventSynchronize(e);
     cudaError_t r;
     while ((r = cudaEventQuery(e)) == cudaErrorNotReady)
     {
@@ -948,7 +970,9 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
     }
 #endif
     CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
-    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, seq, guard);
+    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
+    // number_of_visited_neighbors of the few points whose walk went beyond the first unpublished column (exact counts)
+    CC_RUN(h, k_visited_fix, h->sm_count * 4, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)
@@ -1018,11 +1042,7 @@ static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl, bool state
         h->launches++;
     }
     if (h->label_prefetch && sl.has_tf)
-    {
-        CcDevCfg cfg;
-        fill_devcfg(h, cfg);
-        CC_RUN(h, k_pack_labels, h->sm_count * 4, 256, 0, cfg, h->d, sl.d_labels, h->maxcols);
-    }
+        CC_RUN(h, k_pack_labels, h->sm_count * 4, 256, 0, sl.cfg, h->d, sl.d_labels, h->maxcols);
     CC_CHECK(h, cudaEventRecord(sl.ready, h->stream));
     CC_CHECK(h, cudaStreamWaitEvent(h->copy_stream, sl.ready, 0));
     sl.pre_cols = std::min(h->maxcols, sl.n + 64);
@@ -1056,13 +1076,12 @@ static void bind_slot(cc_handle* h, const cc_handle::Slot& sl)
 // Enqueues every kernel of one push on the handle's stream (nothing here waits for the device).
 static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
 {
-    CcDevCfg cfg;
-    fill_devcfg(h, cfg);
+    const CcDevCfg& cfg = sl.cfg;
     bind_slot(h, sl);
     const int n = sl.n;
     sl.launches0 = h->launches;
     h->n_timed = 0;
-    sl.has_tf = h->has_tf;
+    sl.has_tf = sl.cfg_has_tf;
     sl.spec = cfg.nth == 1;
     sl.fused = sl.want_fused; // decided when the push was submitted (its inputs were routed accordingly)
     if (sl.fused)
@@ -1207,8 +1226,7 @@ static cc_status_t finish_push(cc_handle* h)
     else
         CC_CHECK(h, spin_wait(sl.done));
     h->state = *sl.h_state;
-    CcDevCfg cfg;
-    fill_devcfg(h, cfg);
+    const CcDevCfg cfg = sl.cfg;
     cc_status_t es = device_error_to_status(h);
     if (es == CC_OK && !sl.has_tf && h->state.ncols > 0)
     {
@@ -1400,6 +1418,7 @@ static cc_status_t finish_push(cc_handle* h)
     info.slow_insert_firings = st.scan_slow_firings + st.scan_fast_firings; // everything the lite path did not take
     info.n_unfinished_trees = st.n_ulist;
     info.fused_launch = timed_by_device ? 1 : 0;
+    info.visited_recounts = st.n_vfix;
     pop();
     return CC_OK;
 }
@@ -1439,6 +1458,16 @@ static cc_status_t launch_from(cc_handle* h, int n, const void* d_points, const 
 {
     cc_handle::Slot& sl = h->slots[h->next_slot];
     sl.n = n;
+    if (ib)
+    {
+        sl.cfg = ib->cfg;
+        sl.cfg_has_tf = ib->cfg_has_tf;
+    }
+    else
+    {
+        fill_devcfg(h, sl.cfg);
+        sl.cfg_has_tf = h->has_tf;
+    }
     sl.in_points = d_points;
     sl.in_poses = d_poses;
     sl.h_labels = h->h_label_ring[h->next_label];
@@ -1527,6 +1556,8 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
         CC_CHECK(h, cudaEventRecord(ib.h2d, h->in_stream));
     }
     ib.n = n;
+    fill_devcfg(h, ib.cfg);
+    ib.cfg_has_tf = h->has_tf;
     const int mine = h->next_in;
     h->next_in = (h->next_in + 1) % 3;
     if (h->n_pending >= 2)
@@ -1807,6 +1838,157 @@ cc_status_t cc_pack_cluster_pointcloud2(cc_handle_t* h, int cluster_index, cc_cl
     const int ccols = static_cast<int>(c.max_gcol - c.min_gcol + 1);
     return pack_cloud(h, 1, 0, 0, h->last_points_dev + c.point_offset, static_cast<int>(c.num_points), c.min_gcol, ccols, false,
                       c.stamp, out);
+}
+
+cc_status_t cc_pack_requests_pointcloud2(cc_handle_t* h, int n, const cc_pack_request_t* requests, cc_cloud_view_t* out)
+{
+    if (!h || n < 0 || (n > 0 && (!requests || !out)) || !h->is_reset)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (n == 0)
+        return CC_OK;
+    CC_CHECK(h, cudaSetDevice(h->device));
+    if (n > h->requests_cap)
+    {
+        if (h->h_requests)
+            cudaFreeHost(h->h_requests);
+        if (h->h_req_stamps)
+            cudaFreeHost(h->h_req_stamps);
+        if (h->d_requests)
+            cudaFree(h->d_requests);
+        if (h->d_req_stamps)
+            cudaFree(h->d_req_stamps);
+        h->h_requests = nullptr;
+        h->h_req_stamps = nullptr;
+        h->d_requests = nullptr;
+        h->d_req_stamps = nullptr;
+        h->requests_cap = 0;
+        const int cap = std::max(256, 2 * n);
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_requests), cap * sizeof(CcPackRequest)));
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_req_stamps), cap * sizeof(unsigned long long)));
+        CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_requests), cap * sizeof(CcPackRequest)));
+        CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_req_stamps), cap * sizeof(unsigned long long)));
+        h->requests_cap = cap;
+    }
+    // layout: payloads one after the other (16-byte aligned), 32-point tasks numbered request by request
+    size_t bytes = 0;
+    int ntasks = 0;
+    int64_t cmin = INT64_MAX, cmax = -1;
+    for (int i = 0; i < n; i++)
+    {
+        const cc_pack_request_t& r = requests[i];
+        CcPackRequest q;
+        std::memset(&q, 0, sizeof(q));
+        q.kind = r.kind;
+        if (r.kind == 2)
+        {
+            if (r.cluster_index < 0 || r.cluster_index >= static_cast<int>(h->clusters.size()) || !h->last_points_dev)
+            {
+                h->error = "cc_pack_requests_pointcloud2: no such cluster in the last finished push";
+                return CC_ERR_INVALID_ARGUMENT;
+            }
+            const cc_cluster_t& c = h->clusters[r.cluster_index];
+            q.npoints = static_cast<int>(c.num_points);
+            q.list_offset = static_cast<int>(c.point_offset);
+            cmin = std::min(cmin, c.min_gcol);
+            cmax = std::max(cmax, c.max_gcol);
+        }
+        else if (r.kind == 0 || r.kind == 1)
+        {
+            if (r.to_gcol >= r.from_gcol)
+            {
+                if (r.from_gcol < 0 || r.to_gcol - r.from_gcol + 1 > h->ringcols)
+                {
+                    h->error = "cc_pack_requests_pointcloud2: range outside the ring";
+                    return CC_ERR_INVALID_ARGUMENT;
+                }
+                q.from = r.from_gcol;
+                q.ncols = static_cast<int>(r.to_gcol - r.from_gcol + 1);
+                q.npoints = q.ncols * h->R;
+                if (r.kind == 1)
+                {
+                    cmin = std::min(cmin, r.from_gcol);
+                    cmax = std::max(cmax, r.to_gcol);
+                }
+            }
+        }
+        else
+            return CC_ERR_INVALID_ARGUMENT;
+        q.out_offset = static_cast<long long>(bytes);
+        q.first_task = ntasks;
+        const size_t step = q.kind == 0 ? CC_CLOUD_STEP_GROUND : CC_CLOUD_STEP_CLUSTER;
+        bytes += (static_cast<size_t>(q.npoints) * step + 15) / 16 * 16;
+        ntasks += (q.npoints + CC_WARP - 1) / CC_WARP;
+        h->h_requests[i] = q;
+        h->h_req_stamps[i] = ~0ull;
+    }
+    if (bytes + 64 > h->cloud_cap)
+    {
+        if (h->h_cloud)
+            cudaFreeHost(h->h_cloud);
+        h->h_cloud = nullptr;
+        h->cloud_cap = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2 + 64, 1 << 20);
+        CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_cloud), cap));
+        h->cloud_cap = cap;
+    }
+    CcDevCfg cfg;
+    fill_devcfg(h, cfg);
+    const unsigned int* counts = nullptr;
+    if (cmax >= cmin && cmax >= 0)
+    {
+        const int ccols = static_cast<int>(cmax - cmin + 1);
+        const size_t cn = static_cast<size_t>(ccols) * h->R;
+        if (cn > h->counts_cap)
+        {
+            if (h->d_counts)
+                cudaFree(h->d_counts);
+            h->d_counts = nullptr;
+            h->counts_cap = 0;
+            CC_CHECK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_counts), (cn + cn / 2) * sizeof(unsigned int)));
+            h->counts_cap = cn + cn / 2;
+        }
+        CC_CHECK(h, cudaMemsetAsync(h->d_counts, 0, cn * sizeof(unsigned int), h->aux_stream));
+        const int ahead = std::max(0, static_cast<int>(std::min<int64_t>(cfg.max_steps_row, h->state.ring_end - cmax)));
+        const int grid = std::max(1, std::min(h->sm_count * 8, static_cast<int>((cn + 255) / 256)));
+        CC_LAUNCH(k_child_counts, grid, 256, 0, h->aux_stream, cfg, h->d, static_cast<long long>(cmin), ccols, ahead, h->d_counts);
+        h->launches++;
+        counts = h->d_counts;
+    }
+    CC_CHECK(h, cudaMemcpyAsync(h->d_requests, h->h_requests, n * sizeof(CcPackRequest), cudaMemcpyHostToDevice, h->aux_stream));
+    CC_CHECK(h, cudaMemcpyAsync(h->d_req_stamps, h->h_req_stamps, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->aux_stream));
+    if (ntasks > 0)
+    {
+#ifdef CC_EMU
+        const int threads = 1;
+#else
+        const int threads = 128;
+#endif
+        const int warps = (threads + CC_WARP - 1) / CC_WARP;
+        const int grid = std::max(1, std::min(h->sm_count * 8, (ntasks + warps - 1) / warps));
+        CC_LAUNCH(k_pack_requests, grid, threads, static_cast<size_t>(warps) * CC_WARP * 29 * sizeof(unsigned int), h->aux_stream, cfg,
+                  h->d, h->d_requests, n, ntasks, h->last_points_dev, static_cast<long long>(cmin == INT64_MAX ? 0 : cmin), counts,
+                  h->h_cloud, h->d_req_stamps);
+        h->launches++;
+    }
+    CC_CHECK(h, cudaMemcpyAsync(h->h_req_stamps, h->d_req_stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->aux_stream));
+    CC_CHECK(h, cudaStreamSynchronize(h->aux_stream));
+    CC_CHECK(h, cudaGetLastError());
+    for (int i = 0; i < n; i++)
+    {
+        const CcPackRequest& q = h->h_requests[i];
+        cc_cloud_view_t& v = out[i];
+        std::memset(&v, 0, sizeof(v));
+        if (q.npoints == 0 && q.kind != 2)
+            continue;
+        v.point_step = q.kind == 0 ? CC_CLOUD_STEP_GROUND : CC_CLOUD_STEP_CLUSTER;
+        v.n_fields = q.kind == 0 ? 19 : 26;
+        v.data = h->h_cloud + q.out_offset;
+        v.data_size = static_cast<uint64_t>(q.npoints) * v.point_step;
+        v.width = q.kind == 2 ? static_cast<uint32_t>(q.npoints) : static_cast<uint32_t>(q.ncols);
+        v.height = q.kind == 2 ? 1u : static_cast<uint32_t>(h->R);
+        v.stamp_ns = q.kind == 2 ? h->clusters[requests[i].cluster_index].stamp : (h->h_req_stamps[i] == ~0ull ? 0ull : h->h_req_stamps[i]);
+    }
+    return CC_OK;
 }
 
 cc_status_t cc_read_columns(cc_handle_t* h, int64_t from, int64_t to, const cc_column_fields_t* f)

@@ -95,9 +95,10 @@ enum CcKernelId
     CC_KID_push_fused,
     CC_KID_fetch,
     CC_KID_export,
+    CC_KID_visited_fix,
     CC_KID_COUNT
 };
-#define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D;k_push_fused;.fetch;.export"
+#define CC_KERNEL_NAMES "k_prep;k_scan_lite;k_scan_check;k_insert_scan;k_scatter;k_gap_scan;k_ground;k_probe;k_probe_heavy;k_snapshot;k_restore;k_restore_finish;k_commit_copy;k_commit_roots;k_commit_links;k_careful;k_fin_all;k_fin_label;k_clear;k_push_done;k_halt;k_pack_labels;k_state_snapshot;.ground_main;.ground_tail;.gap_main;.gap_tail;.fin_init;.fin_agg;.fin_decide;.fin_mark;.fin_copyback;.fin_columns;.lite_p1;.lite_scan1;.lite_p2;.lite_scan2;.lite_p3;.check_loop;.check_scan;.g_pose;.g_A;.g_B;.g_C;.g_D;k_push_fused;.fetch;.export;k_visited_fix"
 // Every stage is a device function over a VIRTUAL grid: (bid, nb) is (blockIdx.x, gridDim.x) when the stage runs as its
 // own kernel, and (rank of the CTA in its cluster, CTAs per cluster) when the stages of a whole push run inside the
 // single fused kernel k_push_fused with cluster barriers between them. blockDim.x / threadIdx.x are always the CTA's own.
@@ -1701,6 +1702,7 @@ CC_DEV void d_insert_scan(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firin
         st->abort = 0;
         st->n_clusters = 0;
         st->n_cluster_points = 0;
+        st->n_vfix = 0;
     }
 }
 __global__ void __launch_bounds__(1024) k_insert_scan(CcDevCfg cfg, CcDevPtrs p, int n_firings, int C, int after_lite)
@@ -2100,6 +2102,7 @@ CC_DEV double cc_ldcg_f64(const double* q)
 
 // `d_labels` / `h_labels` (or null): the packed labels of the column (cc_set_label_prefetch) are also written to the
 // push's label buffers, device and page-locked host, for columns below `label_cap` (fused kernel).
+template<bool EXPORT_LABELS>
 CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, uchar4* d_labels = nullptr,
                      uchar4* h_labels = nullptr, int label_cap = 0)
 {
@@ -2521,7 +2524,7 @@ CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_
                 min_az = caz;
             const uchar4 packed = make_uchar4(label, static_cast<unsigned char>(lab >> 8), ignored ? 1 : 0, s_int[row]);
             p.lab[cell] = packed;
-            if (d_labels && ci < label_cap)
+            if (EXPORT_LABELS && d_labels && ci < label_cap)
             {
                 d_labels[static_cast<size_t>(ci) * R + row] = packed;
                 h_labels[static_cast<size_t>(ci) * R + row] = packed;
@@ -2574,7 +2577,7 @@ CC_DEV void d_ground(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_
 __global__ void __launch_bounds__(128, 8) k_ground(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent)
 {
     CC_PDL_ENTER();
-    d_ground(cc_grid(), cfg, p, s_parent);
+    d_ground<false>(cc_grid(), cfg, p, s_parent);
 }
 
 // Running maximum of the columns' minimum azimuth (the value every finish pass compares against, cpp:884-885), continued
@@ -2998,10 +3001,11 @@ static inline __host__ __device__ size_t cc_heavy_smem_bytes(int block_threads, 
     const int teams = nwarps / (team_warps > 0 ? team_warps : 1) > 0 ? nwarps / (team_warps > 0 ? team_warps : 1) : 1;
     return static_cast<size_t>(teams) * (CC_PROBE_PIPE * CC_WARP * sizeof(float4) + 128 * sizeof(unsigned int));
 }
+template<bool TEAMS>
 CC_DEV void cc_team_sync(int team_warps, int nwarps, int team)
 {
 #ifndef CC_EMU
-    if (team_warps >= nwarps)
+    if (!TEAMS || team_warps >= nwarps)
         __syncthreads();
     else if (team_warps == 1)
         __syncwarp();
@@ -3012,6 +3016,8 @@ CC_DEV void cc_team_sync(int team_warps, int nwarps, int team)
 #endif
 }
 
+// TEAMS = false: the team is the whole CTA (the stage as its own kernel: plain block barriers, no named barriers reserved)
+template<bool TEAMS>
 CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune, int team_warps)
 {
     CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy, g.bid);
@@ -3024,14 +3030,17 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
     const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
     const int lane = threadIdx.x % CC_WARP;
     const int cta_warps = (blockDim.x + CC_WARP - 1) / CC_WARP;
-    const int nwarps = team_warps < cta_warps ? team_warps : cta_warps; // warps of my team
+    const int nwarps = TEAMS && team_warps < cta_warps ? team_warps : cta_warps; // warps of my team
     const int teams_per_cta = cta_warps / nwarps;
     const int team = (threadIdx.x / CC_WARP) / nwarps, warp = (threadIdx.x / CC_WARP) % nwarps;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int nheavy = p.st->n_heavy < p.maxcols * R ? p.st->n_heavy : p.maxcols * R;
     CC_SMEM(smem);
-    float4* ring = reinterpret_cast<float4*>(smem) + static_cast<size_t>(team) * CC_PROBE_PIPE * CC_WARP;
-    unsigned int* brk_m = reinterpret_cast<unsigned int*>(reinterpret_cast<float4*>(smem) + static_cast<size_t>(teams_per_cta) * CC_PROBE_PIPE * CC_WARP) + team * 128;
+    float4* ring = reinterpret_cast<float4*>(smem) + (TEAMS ? static_cast<size_t>(team) * CC_PROBE_PIPE * CC_WARP : 0);
+    __shared__ unsigned int sh_masks[128]; // the whole CTA is one team: fixed addresses
+    unsigned int* brk_m = TEAMS ? reinterpret_cast<unsigned int*>(reinterpret_cast<float4*>(smem) +
+                                                                  static_cast<size_t>(teams_per_cta) * CC_PROBE_PIPE * CC_WARP) + team * 128
+                                : sh_masks;
     unsigned int* hit_m = brk_m + 64;
     const bool masks_ok = CC_WARP == 32 && cfg.max_steps_col < 32 && 2 * msr + 1 <= 64 && !(tune & 1);
     if (team >= teams_per_cta)
@@ -3103,7 +3112,7 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                 }
             }
         }
-        cc_team_sync(nwarps, cta_warps, team);
+        cc_team_sync<TEAMS>(nwarps, cta_warps, team);
         // ---- phase 2 ----
         if (warp == 0)
         {
@@ -3249,13 +3258,13 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                 }
             }
         }
-        cc_team_sync(nwarps, cta_warps, team); // the masks are rewritten for the next point
+        cc_team_sync<TEAMS>(nwarps, cta_warps, team); // the masks are rewritten for the next point
     }
 }
 __global__ void __launch_bounds__(64, 16) k_probe_heavy(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune)
 {
     CC_PDL_ENTER();
-    d_probe_heavy(cc_grid(), cfg, p, s_parent, s_links, tune, 2);
+    d_probe_heavy<false>(cc_grid(), cfg, p, s_parent, s_links, tune, 2);
 }
 
 // ---- union-find over tree roots (lock-free, ECL-CC style: hook the larger index under the smaller) ----
@@ -4335,9 +4344,27 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
 // `via_rep` (fused kernel: decision and marking share one phase, so the roots do not carry their cluster slot): the slot
 // is read from the component representative's list entry, the id from the cluster record. `h_points` (or null): member
 // list entries are also written straight to page-locked host memory (first `h_cap` entries).
-CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec, int* spans = nullptr,
-                        int span_cap = 0, bool via_rep = false, CcClusterPoint* h_points = nullptr, int h_cap = 0)
+// Both are compiled in only with FUSED. The other instantiation (the stage as its own kernel, which visits every cell of
+// the commit's columns anyway) also lists the points whose visit count has to be redone (d_visited_fix).
+CC_DEV int cc_visited_max_back(const CcDevCfg& cfg, const CcDevPtrs& p, long long gcol, size_t cell, long long c0, long long fu0,
+                               long long colbase)
 {
+    // >= 0: the walk of this point went beyond the first unpublished column (cpp:762-763) and has to be cut there
+    const int reached = p.vback[cell];
+    if (reached <= 0)
+        return -1;
+    const long long fu = gcol == c0 ? fu0 : p.col_first_unpub[gcol - 1 - colbase];
+    if (fu >= 0 && gcol - reached < fu)
+        return gcol > fu ? static_cast<int>(gcol - fu) : 0;
+    return -1;
+}
+template<bool FUSED>
+CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, unsigned int seq, int spec, int* spans_ = nullptr,
+                        int span_cap = 0, bool via_rep_ = false, CcClusterPoint* h_points_ = nullptr, int h_cap = 0)
+{
+    int* spans = FUSED ? spans_ : nullptr;
+    const bool via_rep = FUSED && via_rep_;
+    CcClusterPoint* h_points = FUSED ? h_points_ : nullptr;
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
@@ -4419,6 +4446,17 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
                 row = static_cast<int>(i % R);
             }
             const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
+            if (!FUSED && gcol >= st->seg_c0)
+            {
+                const int mb = cc_visited_max_back(cfg, p, gcol, cell, st->seg_c0, st->seg_first_unpub_old, hd.colbase);
+                if (mb >= 0)
+                {
+                    // (the probe's work lists are free again: the probes of this push are done)
+                    const int pos = atomicAdd(&p.st->n_vfix, 1);
+                    p.heavy_list[pos] = static_cast<int>(gcol - hd.colbase) * R + row;
+                    p.probe_list[pos] = mb;
+                }
+            }
             if (p.slot_gcol[cell / R] == gcol)
             {
                 const unsigned int root = p.tparent[cell];
@@ -4474,15 +4512,30 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
 // number_of_visited_neighbors, exactly: the reference's walk stops at the first unpublished column (cpp:762-763), which
 // for column c is where the finish pass of column c - 1 left it -- known only now, after the finish passes of the commit.
 // The (geometric) probes walked without that stop and left how many columns back they got; the few points that went
-// beyond the stop are counted again, a warp per point, with the walk cut there. `ring`: CC_PROBE_PIPE * CC_WARP float4 of
-// shared memory per warp.
-CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, float4* ring_all)
+// beyond the stop (mostly the first points of a new object while nothing else is unfinished) are counted again, a warp
+// per point, with the walk cut there. Such points come in runs of neighbouring cells: the cells a warp inspects are
+// spread over the range (stride = number of warps) so that a run is shared by many warps.
+// `ring`: CC_PROBE_PIPE * CC_WARP float4 of shared memory per warp.
+// from_list: the points were listed by d_fin_label (heavy_list / probe_list, n_vfix entries); else the cells of the
+// commit's columns are scanned here (fused kernel: short pushes).
+CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, float4* ring_all, bool from_list)
 {
     const CcHead hd = cc_head(p.st);
     if (hd.halted || !cc_head_ok(hd, spec))
         return;
     const CcDevState* st = p.st;
     const int R = cfg.R;
+    if (from_list)
+    {
+        const int n = st->n_vfix;
+        const int bl = cc_local_col(hd.colbase, cfg.ringcols);
+        const int ln = threadIdx.x % CC_WARP, wp = threadIdx.x / CC_WARP;
+        const int nw = (blockDim.x + CC_WARP - 1) / CC_WARP;
+        float4* rg = ring_all + static_cast<size_t>(wp) * CC_PROBE_PIPE * CC_WARP;
+        for (int e = g.bid * nw + wp; e < n; e += g.nb * nw)
+            d_probe_coop(cfg, p, nullptr, nullptr, rg, bl, hd.colbase, ln, p.heavy_list[e], p.probe_list[e]);
+        return;
+    }
     const long long c0 = st->seg_c0, c1 = st->seg_c1, colbase = hd.colbase;
     const long long fu0 = st->seg_first_unpub_old;
     const int base_local = cc_local_col(colbase, cfg.ringcols);
@@ -4490,25 +4543,22 @@ CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
     const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
     float4* ring = ring_all + static_cast<size_t>(warp) * CC_PROBE_PIPE * CC_WARP;
     const long long total = (c1 - c0 + 1) * R;
-    for (long long i0 = (static_cast<long long>(g.bid) * nwarps + warp) * CC_WARP; i0 < total;
-         i0 += static_cast<long long>(g.nb) * nwarps * CC_WARP)
+    const long long W = static_cast<long long>(g.nb) * nwarps, w = static_cast<long long>(g.bid) * nwarps + warp;
+    for (long long j0 = 0; j0 * W < total; j0 += CC_WARP) // cell (j0 + lane) * W + w
     {
-        const long long i = i0 + lane;
+        const long long i = (j0 + lane) * W + w;
         int max_back = -1, pidx = 0;
         if (i < total)
         {
             const long long gcol = c0 + i / R;
             const int row = static_cast<int>(i % R);
             const size_t cell = static_cast<size_t>(cc_local_col(gcol, cfg.ringcols)) * R + row;
-            const long long fu = gcol == c0 ? fu0 : p.col_first_unpub[gcol - 1 - colbase];
-            const int reached = p.vback[cell];
-            if (reached > 0 && fu >= 0 && gcol - reached < fu)
-            {
-                max_back = gcol > fu ? static_cast<int>(gcol - fu) : 0;
-                pidx = static_cast<int>(gcol - colbase) * R + row;
-            }
+            max_back = cc_visited_max_back(cfg, p, gcol, cell, c0, fu0, colbase);
+            pidx = static_cast<int>(gcol - colbase) * R + row;
         }
         unsigned int todo = __ballot_sync(CC_FULL_MASK, max_back >= 0);
+        if (todo && lane == 0)
+            atomicAdd(&p.st->n_vfix, __popc(todo));
         while (todo)
         {
             const int src = __ffs(todo) - 1;
@@ -4522,10 +4572,16 @@ CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
 __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
 {
     CC_PDL_ENTER();
+    d_fin_label<false>(cc_grid(), cfg, p, seq, spec);
+}
+
+__global__ void __launch_bounds__(256) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec)
+{
+    CC_PDL_ENTER();
     const CcGrid g = cc_grid();
-    d_fin_label(g, cfg, p, seq, spec);
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_visited_fix, g.bid);
     CC_SMEM(smem);
-    d_visited_fix(g, cfg, p, spec, reinterpret_cast<float4*>(smem));
+    d_visited_fix(g, cfg, p, spec, reinterpret_cast<float4*>(smem), true);
 }
 
 // =====================================================================================================
@@ -4827,14 +4883,14 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
                 d_gap_rows(g, cfg, p, hd);
         }
         cc_cluster_sync();
-        d_ground(g, cfg, p, a.s_parent, a.pack_labels ? a.d_labels : nullptr, a.h_labels, a.cap_cols);
+        d_ground<true>(g, cfg, p, a.s_parent, a.pack_labels ? a.d_labels : nullptr, a.h_labels, a.cap_cols);
         cc_cluster_sync();
         // ---- association (cpp:638-835) ----
         d_probe(g, cfg, p, a.s_parent, a.s_links, a.spec);
         cc_cluster_sync();
         if (p.st->n_heavy > 0) // (the same value in every CTA: read after the barrier)
         {
-            d_probe_heavy(g, cfg, p, a.s_parent, a.s_links, a.tune, a.team_warps);
+            d_probe_heavy<true>(g, cfg, p, a.s_parent, a.s_links, a.tune, a.team_warps);
             cc_cluster_sync();
         }
         if (a.spec)
@@ -4894,7 +4950,7 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
                     gl.nb = nlab;
                     CC_SMEM(smem_l);
                     __syncthreads(); // (a CTA that also ran the tail: its shared memory is free again)
-                    d_fin_label(gl, cfg, p, a.seq, 1, reinterpret_cast<int*>(smem_l), 512, true, a.h_points, a.cap_points);
+                    d_fin_label<true>(gl, cfg, p, a.seq, 1, reinterpret_cast<int*>(smem_l), 512, true, a.h_points, a.cap_points);
                 }
             }
             else if (g.bid == 0 && threadIdx.x == 0)
@@ -4918,7 +4974,7 @@ __global__ void __launch_bounds__(512, 1) k_push_fused(CcDevCfg cfg, CcDevPtrs p
             gv.nb = g.nb - 1;
         }
         CC_SMEM(smem_v);
-        d_visited_fix(gv, cfg, p, 1, reinterpret_cast<float4*>(smem_v));
+        d_visited_fix(gv, cfg, p, 1, reinterpret_cast<float4*>(smem_v), false);
         __syncthreads();
     }
     if (g.bid == 0)
@@ -4986,13 +5042,18 @@ CC_DEV CcCell cc_gather_cell(const CcDevCfg& cfg, const CcDevPtrs& p, long long 
     CcCell c;
     const float4 q = p.pos[cell];
     const uchar4 l = p.lab[cell];
-    c.x = q.x;
-    c.y = q.y;
-    c.z = q.z;
-    c.distance = q.w;
-    c.azimuth_angle = p.azimuth[cell];
-    c.inclination_angle = p.incl[cell];
-    c.continuous_azimuth_angle = p.cont_az[cell];
+    // NaN bit patterns: the reference's NaNs all descend from std::nanf("") / std::nan("") (0x7fc00000 / 0x7ff8...0), which
+    // x86 arithmetic propagates unchanged; the GPU's arithmetic produces 0x7fffffff instead. Published bytes (PointCloud2
+    // payloads) carry the reference's pattern.
+    auto canon = [](float v) { return v != v ? ccm::u2f(0x7fc00000u) : v; };
+    auto canon64 = [](double v) { return v != v ? __longlong_as_double(0x7ff8000000000000LL) : v; };
+    c.x = canon(q.x);
+    c.y = canon(q.y);
+    c.z = canon(q.z);
+    c.distance = canon(q.w);
+    c.azimuth_angle = canon(p.azimuth[cell]);
+    c.inclination_angle = canon(p.incl[cell]);
+    c.continuous_azimuth_angle = canon64(p.cont_az[cell]);
     c.global_column_index = p.slot_gcol[local] == gcol ? gcol : -1; // refilled by segmentation (cpp:347-350)
     c.stamp = p.stamp[cell];
     c.globally_unique_point_index = p.guid[cell];
@@ -5198,6 +5259,88 @@ __global__ void __launch_bounds__(128) k_pack_cloud(CcDevCfg cfg, CcDevPtrs p, i
     }
     if (min_stamp && smin != ~0ull)
         atomicMin(min_stamp, smin);
+}
+
+// Every message of a push in ONE launch (the node publishes a message per finished-column callback and per finished
+// cluster: dozens to hundreds per push): a request table names, per message, what to pack and where its payload starts.
+struct CcPackRequest // == cc_pack_request_t + the layout the host computed
+{
+    int kind;             // 0 ground-stage columns (76-byte points), 1 clustered columns (116), 2 cluster (116)
+    int npoints;          // points of the message
+    long long from;       // first column (kinds 0 / 1)
+    int ncols;            // columns (kinds 0 / 1)
+    int list_offset;      // first member-list entry (kind 2)
+    long long out_offset; // byte offset of the payload in the output buffer (16-byte aligned)
+    int first_task, pad_; // first 32-point task of the request
+};
+
+__global__ void __launch_bounds__(128) k_pack_requests(CcDevCfg cfg, CcDevPtrs p, const CcPackRequest* req, int nreq, int ntasks,
+                                                       const CcClusterPoint* list, long long cfrom, const unsigned int* counts,
+                                                       unsigned char* out, unsigned long long* min_stamps)
+{
+    CC_SMEM(smem);
+    const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
+    const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
+    unsigned int* tile = reinterpret_cast<unsigned int*>(smem) + static_cast<size_t>(warp) * CC_WARP * 29;
+    for (int task = blockIdx.x * nwarps + warp; task < ntasks; task += gridDim.x * nwarps)
+    {
+        int a = 0, b = nreq - 1; // last request with first_task <= task
+        while (a < b)
+        {
+            const int mid = (a + b + 1) >> 1;
+            if (req[mid].first_task <= task)
+                a = mid;
+            else
+                b = mid - 1;
+        }
+        const CcPackRequest rq = req[a];
+        const int nwords = rq.kind == 0 ? CC_CLOUD_STEP_GROUND / 4 : CC_CLOUD_STEP_CLUSTER / 4;
+        const long long o0 = static_cast<long long>(task - rq.first_task) * CC_WARP;
+        const long long o = o0 + lane;
+        unsigned long long smin = ~0ull;
+        if (o < rq.npoints)
+        {
+            long long gcol;
+            int row;
+            if (rq.kind != 2)
+            {
+                row = static_cast<int>(o / rq.ncols);
+                gcol = rq.from + o % rq.ncols;
+            }
+            else
+            {
+                gcol = list[rq.list_offset + o].gcol;
+                row = list[rq.list_offset + o].row;
+            }
+            const unsigned int nchild = rq.kind != 0 && counts ? counts[(gcol - cfrom) * cfg.R + row] : 0u;
+            unsigned int w[29];
+            unsigned long long stamp;
+            cc_cloud_record(cfg, p, gcol, row, nchild, nwords, w, &stamp);
+            if (stamp != 0ull)
+                smin = stamp;
+            for (int k = 0; k < nwords; k++)
+                tile[lane * nwords + k] = w[k];
+        }
+        __syncwarp();
+        const long long cnt = rq.npoints - o0 < CC_WARP ? rq.npoints - o0 : CC_WARP;
+        const int nbytes = static_cast<int>(cnt) * nwords * 4;
+        unsigned char* dst = out + rq.out_offset + o0 * nwords * 4;
+        const int nvec = nbytes / 16;
+        const uint4* src4 = reinterpret_cast<const uint4*>(tile);
+        for (int v = lane; v < nvec; v += CC_WARP)
+            reinterpret_cast<uint4*>(dst)[v] = src4[v];
+        for (int bb = nvec * 16 + lane * 4; bb < nbytes; bb += CC_WARP * 4)
+            *reinterpret_cast<unsigned int*>(dst + bb) = tile[bb / 4];
+        __syncwarp();
+        // smallest non-zero point stamp of the message
+        for (int off = CC_WARP / 2; off > 0; off >>= 1)
+        {
+            const unsigned long long other = __shfl_xor_sync(CC_FULL_MASK, smin, off);
+            smin = other < smin ? other : smin;
+        }
+        if (lane == 0 && smin != ~0ull)
+            atomicMin(min_stamps + a, smin);
+    }
 }
 
 // ---- device math self-test (bit equality with the host libm) ----

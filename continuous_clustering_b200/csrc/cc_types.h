@@ -106,6 +106,7 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     long long scan_lite_base; // column the lite arrays are relative to
     int scan_lite_firings;
     int ticket_gap;    // same for k_gap_scan (the last block chains the column chunks)
+    int n_vfix; // points whose visit count was redone with the walk cut at the first unpublished column (d_visited_fix)
     int halted; // set when a push could not be committed speculatively: later pushes in flight skip themselves
 };
 

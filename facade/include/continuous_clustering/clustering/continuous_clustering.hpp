@@ -238,6 +238,15 @@ class ContinuousClustering
     std::function<void(const std::vector<Point>&, uint64_t)> finished_cluster_callback_;
     std::function<void(const PackedPointCloud2&)> finished_cluster_packed_callback_;
     bool materialise_{true};
+    // packed messages of the push being delivered, built by ONE device launch before its callbacks run
+    struct Prepacked
+    {
+        int64_t from, to;
+        int kind;
+        PackedPointCloud2 msg;
+    };
+    std::vector<Prepacked> prepacked_;
+    void prepack(const void* events, int n_events, const void* clusters, int n_clusters);
     std::vector<Point> cluster_buffer_;
 };
 

@@ -244,8 +244,56 @@ static ContinuousClustering::PackedPointCloud2 toPacked(const cc_cloud_view_t& v
     return m;
 }
 
+// Every message the callbacks of this push can ask for, with one device launch: one per finished-column event and one
+// per finished cluster handed to the packed cluster callback
+void ContinuousClustering::prepack(const void* events_, int n_events, const void* clusters_, int n_clusters)
+{
+    const cc_column_event_t* events = static_cast<const cc_column_event_t*>(events_);
+    const cc_cluster_t* clusters = static_cast<const cc_cluster_t*>(clusters_);
+    std::vector<cc_pack_request_t> req;
+    req.reserve(static_cast<size_t>(n_events) + n_clusters);
+    if (finished_column_callback_)
+        for (int i = 0; i < n_events; i++)
+        {
+            cc_pack_request_t r{};
+            r.kind = events[i].ground_points_only ? 0 : 1;
+            r.from_gcol = events[i].from_gcol;
+            r.to_gcol = events[i].to_gcol;
+            req.push_back(r);
+        }
+    if (finished_cluster_packed_callback_)
+        for (int i = 0; i < n_clusters; i++)
+            if (clusters[i].num_points > 20) // cpp:1023
+            {
+                cc_pack_request_t r{};
+                r.kind = 2;
+                r.cluster_index = i;
+                r.from_gcol = i; // key of the lookup below
+                r.to_gcol = i;
+                req.push_back(r);
+            }
+    prepacked_.clear();
+    if (req.empty())
+        return;
+    std::vector<cc_cloud_view_t> views(req.size());
+    int s = cc_pack_requests_pointcloud2(handle_, static_cast<int>(req.size()), req.data(), views.data());
+    if (s != CC_OK)
+        fail(s);
+    prepacked_.resize(req.size());
+    for (size_t i = 0; i < req.size(); i++)
+    {
+        prepacked_[i].from = req[i].from_gcol;
+        prepacked_[i].to = req[i].to_gcol;
+        prepacked_[i].kind = req[i].kind;
+        prepacked_[i].msg = toPacked(views[i]);
+    }
+}
+
 ContinuousClustering::PackedPointCloud2 ContinuousClustering::packColumnsPointCloud2(int64_t from, int64_t to, bool ground_points_only)
 {
+    for (const Prepacked& q : prepacked_) // inside a callback: the message was packed with the rest of the push
+        if (q.kind == (ground_points_only ? 0 : 1) && q.from == from && q.to == to)
+            return q.msg;
     cc_cloud_view_t v;
     int s = cc_pack_columns_pointcloud2(handle_, from, to, ground_points_only ? 1 : 0, &v);
     if (s != CC_OK)
@@ -443,6 +491,9 @@ void ContinuousClustering::deliver()
             }
     if (hi >= lo && hi >= 0 && (materialise_ || finished_cluster_callback_))
         materialise(lo, hi);
+    prepacked_.clear();
+    if (!materialise_ || finished_cluster_packed_callback_)
+        prepack(events.data(), static_cast<int>(events.size()), clusters.data(), static_cast<int>(clusters.size()));
     size_t next = 0;
     for (const auto& e : events)
     {
@@ -450,13 +501,12 @@ void ContinuousClustering::deliver()
         {
             const cc_cluster_t& c = clusters[next++];
             if (c.num_points > 20 && finished_cluster_packed_callback_) // cpp:1023
-            {
-                cc_cloud_view_t v;
-                int s = cc_pack_cluster_pointcloud2(handle_, static_cast<int>(next - 1), &v);
-                if (s != CC_OK)
-                    fail(s);
-                finished_cluster_packed_callback_(toPacked(v));
-            }
+                for (const Prepacked& q : prepacked_)
+                    if (q.kind == 2 && q.from == static_cast<int64_t>(next - 1))
+                    {
+                        finished_cluster_packed_callback_(q.msg);
+                        break;
+                    }
             if (c.num_points > 20 && finished_cluster_callback_) // cpp:1023
             {
                 cluster_buffer_.clear();

@@ -161,6 +161,9 @@ typedef struct cc_batch_info
     int32_t slow_insert_firings;     /* firings that went through the per-firing insertion path (collisions) */
     int32_t n_unfinished_trees;      /* sc_unfinished_point_trees_.size() after the batch (hpp:273)            */
     int32_t fused_launch;            /* 1 if the batch ran as ONE fused kernel launch (short pushes) */
+    int32_t visited_recounts;        /* points whose number_of_visited_neighbors was recounted (walk cut at the first
+                                        unpublished column, cpp:762-763) */
+    int32_t pad_;
 } cc_batch_info_t;
 
 /* Field selector + destination pointers for cc_read_columns. Each non-NULL pointer receives
@@ -324,6 +327,17 @@ typedef struct cc_cloud_view
 CC_API cc_status_t cc_pack_columns_pointcloud2(cc_handle_t* h, int64_t from_gcol, int64_t to_gcol, int ground_points_only,
                                                cc_cloud_view_t* out);
 CC_API cc_status_t cc_pack_cluster_pointcloud2(cc_handle_t* h, int cluster_index, cc_cloud_view_t* out);
+/* Every message of a push with ONE launch: request i is a range of columns (kind 0: ground_points_only callback, kind 1:
+ * clustered columns) or cluster `cluster_index` of the last finished push (kind 2); out[i] receives its view (an empty
+ * column range gives an empty view, like columnToPointCloud's nullptr). All payloads live in one page-locked buffer,
+ * valid until the next cc_pack_* call. */
+typedef struct cc_pack_request
+{
+    int32_t kind;
+    int32_t cluster_index;
+    int64_t from_gcol, to_gcol;
+} cc_pack_request_t;
+CC_API cc_status_t cc_pack_requests_pointcloud2(cc_handle_t* h, int n, const cc_pack_request_t* requests, cc_cloud_view_t* out);
 
 /* Public data members of the reference object (hpp:244-251). */
 CC_API int cc_num_rows(const cc_handle_t* h);

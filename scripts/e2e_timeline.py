@@ -6,11 +6,11 @@ import bench
 from continuous_clustering_b200 import ContinuousClustering
 from continuous_clustering_b200.presets import stream_configuration
 
-B = 2048
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 base_pts, base_poses, sp = bench.make_rotations()
 cfg = stream_configuration(bench.SPEC)
 R = sp.rows
-cc = ContinuousClustering(device=0, max_firings_per_push=B)
+cc = ContinuousClustering(device=0, max_firings_per_push=max(B, 256))
 cc.setConfiguration(cfg); cc.reset(R); cc.setTransformRobotFrameFromSensorFrame(bench.IDENTITY)
 cc.set_label_prefetch(True)
 n = 16

@@ -193,6 +193,27 @@ def device_clouds(cc, pts, poses, chunk):
     return clouds
 
 
+def device_clouds_batched(cc, pts, poses, chunk):
+    """Same as device_clouds, but every message of a push comes from ONE launch (cc_pack_requests_pointcloud2)."""
+    clouds = []
+    for a in range(0, pts.shape[0], chunk):
+        res = cc.addFirings(pts[a:a + chunk], poses[a:a + chunk])
+        req, nxt = [], 0
+        for e in res.events.copy():
+            while nxt < int(e["n_clusters_before"]):
+                if res.clusters[nxt]["num_points"] > 20:
+                    req.append((2, nxt, nxt))
+                nxt += 1
+            if e["to_gcol"] >= e["from_gcol"]:
+                req.append((0 if e["ground_points_only"] else 1, int(e["from_gcol"]), int(e["to_gcol"])))
+        for (kind, f, t), c in zip(req, cc.pack_requests_pointcloud2(req)):
+            d = np.zeros((), dtype=drvlib.CLOUD_DTYPE)
+            d["from_gcol"], d["to_gcol"], d["kind"] = (-1, -1, 2) if kind == 2 else (f, t, kind)
+            d["width"], d["height"], d["point_step"], d["stamp_ns"] = c["width"], c["height"], c["point_step"], c["stamp_ns"]
+            clouds.append((d, c["data"].copy().view(drvlib.pointcloud2_dtype(c["n_fields"])).reshape(c["height"], c["width"])))
+    return clouds
+
+
 def check_device_packer(library, spec, kw, cfg_over, chunk):
     from test_emu_parity import make_cc
 
@@ -202,6 +223,9 @@ def check_device_packer(library, spec, kw, cfg_over, chunk):
     want, _ = record_clouds(drvlib.REF_LIB, pts, poses, sp, cfg)
     cc = make_cc(library, cfg, sp.rows)
     got = device_clouds(cc, pts, poses, chunk)
+    compare_clouds(want, got)
+    cc = make_cc(library, cfg, sp.rows)
+    got = device_clouds_batched(cc, pts, poses, chunk)
     compare_clouds(want, got)
 
 
