@@ -37,10 +37,28 @@ def test_library_is_sm100a_cuda_code():
     assert "sm_100a" in out, out
 
 
-def test_struct_sizes_match_header(product_lib):
-    assert C.sizeof(_lib.CcConfig) == 33 * 4
-    assert C.sizeof(_lib.CcBatchInfo) == 7 * 8 + 8 * 4
-    assert _lib.EVENT_DTYPE.itemsize == 24 and _lib.CLUSTER_DTYPE.itemsize == 64 and _lib.CLUSTER_POINT_DTYPE.itemsize == 16
+def test_struct_sizes_match_header(product_lib, tmp_path):
+    """sizeof of every struct of include/cc_b200.h as the C compiler lays it out == the ctypes / numpy mirrors."""
+    import subprocess
+
+    names = ["cc_config_t", "cc_batch_info_t", "cc_column_event_t", "cc_cluster_t", "cc_cluster_point_t", "cc_raw_point_t",
+             "cc_cell_t", "cc_cloud_view_t", "cc_pack_request_t", "cc_column_fields_t"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "cc_b200.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = dict(zip(names, map(int, subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout.split())))
+    assert C.sizeof(_lib.CcConfig) == sizes["cc_config_t"] == 33 * 4
+    assert C.sizeof(_lib.CcBatchInfo) == sizes["cc_batch_info_t"]
+    assert _lib.EVENT_DTYPE.itemsize == sizes["cc_column_event_t"] == 24
+    assert _lib.CLUSTER_DTYPE.itemsize == sizes["cc_cluster_t"] == 64
+    assert _lib.CLUSTER_POINT_DTYPE.itemsize == sizes["cc_cluster_point_t"] == 16
+    assert _lib.CELL_DTYPE.itemsize == sizes["cc_cell_t"] == 128
+    assert C.sizeof(_lib.CcCloudView) == sizes["cc_cloud_view_t"]
+    assert C.sizeof(_lib.CcPackRequest) == sizes["cc_pack_request_t"]
+    assert C.sizeof(_lib.CcColumnFields) == sizes["cc_column_fields_t"]
+    assert sizes["cc_raw_point_t"] == 48
     cfg = _lib.CcConfig()
     product_lib.cc_config_default(C.byref(cfg))
     assert cfg.num_columns == 1700 and abs(cfg.max_distance - 0.7) < 1e-7 and cfg.max_steps_in_row == 20
