@@ -10,4 +10,5 @@ from .api import (  # noqa: F401
     ContinuousGroundSegmentationConfiguration,
     ContinuousRangeImageConfiguration,
     GeneralConfiguration,
+    KittiEvaluation,
 )

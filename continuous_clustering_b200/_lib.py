@@ -139,7 +139,15 @@ EXPORTED_SYMBOLS = [
     "cc_max_firings_per_push", "cc_debug_event_query", "cc_set_label_prefetch", "cc_get_column_labels",
     "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
     "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2", "cc_pack_requests_pointcloud2",
+    "cc_eval_create", "cc_eval_destroy", "cc_eval_frame",
 ]
+
+
+class CcEvalResult(C.Structure):
+    """cc_eval_result_t == EvaluationResultForFrame (kitti_evaluation.hpp:38-50)."""
+
+    _fields_ = [("tp", C.c_double), ("fn", C.c_double), ("fp", C.c_double), ("tn", C.c_double),
+                ("over_segmentation_entropy", C.c_double), ("under_segmentation_entropy", C.c_double)]
 
 
 class CcPackRequest(C.Structure):
@@ -188,6 +196,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_pack_columns_pointcloud2.argtypes = [vp, i64, i64, i32, C.POINTER(CcCloudView)]
     lib.cc_pack_cluster_pointcloud2.argtypes = [vp, i32, C.POINTER(CcCloudView)]
     lib.cc_pack_requests_pointcloud2.argtypes = [vp, i32, vp, vp]
+    lib.cc_eval_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.cc_eval_destroy.argtypes = [vp]
+    lib.cc_eval_destroy.restype = None
+    lib.cc_eval_frame.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(CcEvalResult)]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]
     lib.cc_stream.argtypes = [vp]

@@ -422,3 +422,39 @@ class ContinuousClustering:
     @property
     def stream(self) -> int:
         return int(self._L.cc_stream(self._h) or 0)
+
+
+class KittiEvaluation:
+    """The per-frame evaluation metrics of the reference's KittiEvaluation (kitti_evaluation.cpp:44-146) on the device:
+    ground-segmentation confusion counts and over- / under-segmentation entropies."""
+
+    def __init__(self, device: int = 0, max_points_per_frame: int = 1 << 18, _library=None):
+        self._L = _library or _lib.load_library()
+        h = C.c_void_p()
+        rc = self._L.cc_eval_create(device, max_points_per_frame, C.byref(h))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_eval_create failed (no CUDA device: there is no CPU path)")
+        self._h = h
+
+    def evaluate(self, semantic_label, is_ground_point, euclidean_clustering_label, detection_label) -> dict:
+        sem = np.ascontiguousarray(semantic_label, dtype=np.uint16)
+        gr = np.ascontiguousarray(is_ground_point, dtype=np.uint8)
+        gt = np.ascontiguousarray(euclidean_clustering_label, dtype=np.uint32)
+        det = np.ascontiguousarray(detection_label, dtype=np.uint32)
+        assert sem.shape == gr.shape == gt.shape == det.shape
+        res = _lib.CcEvalResult()
+        rc = self._L.cc_eval_frame(self._h, sem.size, sem.ctypes.data, gr.ctypes.data, gt.ctypes.data, det.ctypes.data, C.byref(res))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_eval_frame failed")
+        return {k: getattr(res, k) for k, _ in _lib.CcEvalResult._fields_}
+
+    def close(self):
+        if self._h:
+            self._L.cc_eval_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

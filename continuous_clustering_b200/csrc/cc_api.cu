@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "cc_kernels.cuh"
+#include "cc_eval.cuh"
 
 // optimistic prefix of a push's results brought to the host behind it: cluster records, and member lists for a quarter of
 // the cells of the largest push (a synthetic street scene finishes ~8 % of a push's cells as cluster members)
@@ -1551,7 +1552,20 @@ static cc_status_t submit(cc_handle* h, int n, int rows, const void* points, con
     if (!ib.fused)
     {
         CC_CHECK(h, cudaEventRecord(ib.h2d0, h->in_stream));
-        CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
+        static const int split = std::getenv("CC_B200_H2D_SPLIT") ? std::max(1, std::atoi(std::getenv("CC_B200_H2D_SPLIT"))) : 1;
+        if (split > 1 && pb >= (1u << 20))
+        {
+            // experiment: the upper part of the copy on a second stream (a second copy engine)
+            const size_t half = (pb / 2) & ~static_cast<size_t>(255);
+            CC_CHECK(h, cudaStreamWaitEvent(h->aux_stream, ib.h2d0, 0));
+            CC_CHECK(h, cudaMemcpyAsync(ib.d_raw + half, static_cast<const unsigned char*>(src_pts) + half, pb - half,
+                                        cudaMemcpyHostToDevice, h->aux_stream));
+            CC_CHECK(h, cudaEventRecord(h->ev1, h->aux_stream));
+            CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, half, cudaMemcpyHostToDevice, h->in_stream));
+            CC_CHECK(h, cudaStreamWaitEvent(h->in_stream, h->ev1, 0));
+        }
+        else
+            CC_CHECK(h, cudaMemcpyAsync(ib.d_raw, src_pts, pb, cudaMemcpyHostToDevice, h->in_stream));
         CC_CHECK(h, cudaMemcpyAsync(ib.d_poses, src_poses, qb, cudaMemcpyHostToDevice, h->in_stream));
         CC_CHECK(h, cudaEventRecord(ib.h2d, h->in_stream));
     }
@@ -2222,6 +2236,121 @@ cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_cap, fl
         names[names_cap - 1] = 0;
     }
     *n_out = n;
+    return CC_OK;
+}
+
+// ---- evaluation metrics on the device (kitti_evaluation.cpp:44-146) ----
+struct cc_eval
+{
+    int device{0};
+    int max_points{0};
+    cudaStream_t stream{nullptr};
+    CcEvalPtrs d{};
+    unsigned short* d_sem{nullptr};
+    unsigned char* d_ground{nullptr};
+    unsigned int* d_gt{nullptr};
+    unsigned int* d_det{nullptr};
+    unsigned long long* h_counts{nullptr}; // page-locked: 4 counts + 2 doubles
+    std::vector<void*> allocs;
+};
+
+cc_status_t cc_eval_create(int device_ordinal, int max_points, cc_eval_t** out)
+{
+    if (!out || max_points <= 0)
+        return CC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ordinal < 0 || device_ordinal >= ndev)
+        return CC_ERR_CUDA;
+    cc_eval* e = new cc_eval();
+    e->device = device_ordinal;
+    e->max_points = max_points;
+    int cap = 1024;
+    while (cap < 2 * max_points)
+        cap <<= 1;
+    e->d.pair_cap = cap;
+    e->d.marg_cap = cap;
+    auto alloc = [&](void** p, size_t bytes) -> bool
+    {
+        if (cudaMalloc(p, bytes) != cudaSuccess)
+            return false;
+        e->allocs.push_back(*p);
+        return true;
+    };
+    bool ok = cudaSetDevice(device_ordinal) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              alloc(reinterpret_cast<void**>(&e->d_sem), max_points * sizeof(unsigned short)) &&
+              alloc(reinterpret_cast<void**>(&e->d_ground), max_points) &&
+              alloc(reinterpret_cast<void**>(&e->d_gt), max_points * sizeof(unsigned int)) &&
+              alloc(reinterpret_cast<void**>(&e->d_det), max_points * sizeof(unsigned int)) &&
+              alloc(reinterpret_cast<void**>(&e->d.pair_keys), cap * sizeof(unsigned long long)) &&
+              alloc(reinterpret_cast<void**>(&e->d.pair_cnt), cap * sizeof(unsigned int)) &&
+              alloc(reinterpret_cast<void**>(&e->d.marg_keys), cap * sizeof(unsigned long long)) &&
+              alloc(reinterpret_cast<void**>(&e->d.marg_cnt), cap * sizeof(unsigned int)) &&
+              alloc(reinterpret_cast<void**>(&e->d.counts), 4 * sizeof(unsigned long long) + 2 * sizeof(double)) &&
+              cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 4 * sizeof(unsigned long long) + 2 * sizeof(double)) == cudaSuccess;
+    if (!ok)
+    {
+        cc_eval_destroy(e);
+        return CC_ERR_CUDA;
+    }
+    e->d.entropy = reinterpret_cast<double*>(e->d.counts + 4);
+    *out = e;
+    return CC_OK;
+}
+
+void cc_eval_destroy(cc_eval_t* e)
+{
+    if (!e)
+        return;
+    cudaSetDevice(e->device);
+    if (e->stream)
+    {
+        cudaStreamSynchronize(e->stream);
+        cudaStreamDestroy(e->stream);
+    }
+    for (void* p : e->allocs)
+        cudaFree(p);
+    if (e->h_counts)
+        cudaFreeHost(e->h_counts);
+    delete e;
+}
+
+cc_status_t cc_eval_frame(cc_eval_t* e, int n, const uint16_t* sem, const uint8_t* ground, const uint32_t* gt, const uint32_t* det,
+                          cc_eval_result_t* out)
+{
+    if (!e || !out || n < 0 || n > e->max_points || (n > 0 && (!sem || !ground || !gt || !det)))
+        return CC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(e->device) != cudaSuccess)
+        return CC_ERR_CUDA;
+    cudaStream_t st = e->stream;
+    bool ok = cudaMemcpyAsync(e->d_sem, sem, static_cast<size_t>(n) * sizeof(uint16_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaMemcpyAsync(e->d_ground, ground, static_cast<size_t>(n), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaMemcpyAsync(e->d_gt, gt, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaMemcpyAsync(e->d_det, det, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok)
+        return CC_ERR_CUDA;
+    CcEvalPtrs d = e->d;
+    d.semantic_label = e->d_sem;
+    d.is_ground = e->d_ground;
+    d.gt_label = e->d_gt;
+    d.det_label = e->d_det;
+    d.n = n;
+    const int g_tab = std::max(1, std::min(148 * 4, (d.pair_cap + 255) / 256));
+    const int g_pts = std::max(1, std::min(148 * 8, (n + 255) / 256));
+    CC_LAUNCH(k_eval_clear, g_tab, 256, 0, st, d);
+    CC_LAUNCH(k_eval_count, g_pts, 256, 0, st, d);
+    CC_LAUNCH(k_eval_entropy, g_tab, 256, 0, st, d);
+    if (cudaMemcpyAsync(e->h_counts, d.counts, 4 * sizeof(unsigned long long) + 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return CC_ERR_CUDA;
+    out->tp = static_cast<double>(e->h_counts[0]);
+    out->fn = static_cast<double>(e->h_counts[1]);
+    out->fp = static_cast<double>(e->h_counts[2]);
+    out->tn = static_cast<double>(e->h_counts[3]);
+    const double* ent = reinterpret_cast<const double*>(e->h_counts + 4);
+    out->over_segmentation_entropy = ent[0];
+    out->under_segmentation_entropy = ent[1];
     return CC_OK;
 }
 

@@ -376,6 +376,25 @@ CC_API cc_status_t cc_debug_slot_times(cc_handle_t* h, int slot, float out_ms[5]
  * in-flight slot 0/1 has completed. */
 CC_API int cc_debug_event_query(cc_handle_t* h, int slot, int which);
 
+/* ---- evaluation metrics ---------------------------------------------------------------
+ * The per-frame metrics of the reference's KittiEvaluation (src/evaluation/kitti_evaluation.cpp:44-146) on the device:
+ * ground-segmentation confusion counts against the SemanticKITTI ground classes (evaluateGroundPoints, cpp:44-84) and
+ * the over- / under-segmentation entropies between ground-truth clusters and detections (evaluateClusters, cpp:86-146).
+ * Per point: semantic_label (KittiPoint::semantic_label), is_ground_point, euclidean_clustering_label (0 = none) and
+ * detection_label (Point::id, 0 = none) -- the members kitti_demo.cpp:211-213 fills. Host arrays in, six doubles out. */
+typedef struct cc_eval cc_eval_t;
+typedef struct cc_eval_result
+{
+    double tp, fn, fp, tn;                 /* EvaluationResultForFrame, kitti_evaluation.hpp:38-50 */
+    double over_segmentation_entropy;
+    double under_segmentation_entropy;
+} cc_eval_result_t;
+CC_API cc_status_t cc_eval_create(int device_ordinal, int max_points_per_frame, cc_eval_t** out);
+CC_API void cc_eval_destroy(cc_eval_t* e);
+CC_API cc_status_t cc_eval_frame(cc_eval_t* e, int n_points, const uint16_t* semantic_label, const uint8_t* is_ground_point,
+                                 const uint32_t* euclidean_clustering_label, const uint32_t* detection_label,
+                                 cc_eval_result_t* out);
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */

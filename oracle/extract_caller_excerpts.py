@@ -6,6 +6,13 @@ the reference's class and the facade's:
   ros_utils.cpp   clusterToPointCloud, columnToPointCloud                            ros_utils.cpp:11-77
                   prepareMessageAndCreateIterators, addPointToMessage                ros_utils.cpp:108-298
   kitti_demo.cpp  KittiDemo::addColumnAndEvaluateFrameIfCompleted (callback body)    kitti_demo.cpp:173-224
+                  KittiDemo::makePseudoFiringFromRangeImageColumn                    kitti_demo.cpp:123-159
+and the functions of the rows SURVEY 8f-2 / 8f-4 name (oracle/cc_eval_driver.cpp compiles them against the reference's
+own headers):
+  kitti_evaluation.cpp  KittiEvaluation ctor, evaluate, evaluateGroundPoints, evaluateClusters, addPointForKey  :10-157
+  kitti_loader.cpp      recoverLaserIndices, generateRangeImage, undoEgoMotionCorrection     kitti_loader.cpp:47-210
+                        interpolate                                                          kitti_loader.cpp:297-328
+                        getSemanticKittiLabel*Mapping                                        kitti_loader.cpp:566-613
 
 Ranges are found by their first lines, not by line numbers.   usage: extract_caller_excerpts.py REFERENCE OUTDIR
 """
@@ -32,6 +39,17 @@ def main(ref, out):
         "ros_utils_fields.inc": cut(cpp, "PointCloud2Iterators prepareMessageAndCreateIterators(",
                                     "void addRawPointToMessage("),
         "kitti_demo_callback.inc": cut(demo, "    void addColumnAndEvaluateFrameIfCompleted(", "  public:"),
+        "kitti_demo_pseudo_firing.inc": cut(demo, "    static inline RawPoints::Ptr makePseudoFiringFromRangeImageColumn(",
+                                            "    void evaluatePreviousFrame()"),
+        "kitti_eval_metrics.inc": cut(os.path.join(ref, "src/evaluation/kitti_evaluation.cpp"), "KittiEvaluation::KittiEvaluation()",
+                                      "std::string KittiEvaluation::generateEvaluationResults()"),
+        "kitti_loader_range_image.inc": cut(os.path.join(ref, "src/evaluation/kitti_loader.cpp"),
+                                            "void KittiLoader::recoverLaserIndices(", "Oxts KittiLoader::loadSingleOxfordMeasurement("),
+        "kitti_loader_interpolate.inc": cut(os.path.join(ref, "src/evaluation/kitti_loader.cpp"),
+                                            "StampedPose KittiLoader::interpolate(", "std::vector<StampedPose> KittiLoader::getAllDynamicTransforms("),
+        "kitti_loader_labels.inc": cut(os.path.join(ref, "src/evaluation/kitti_loader.cpp"),
+                                       "std::map<uint16_t, std::string> KittiLoader::getSemanticKittiLabelNumericToLabelNameMapping()",
+                                       "std::vector<std::string> KittiLoader::split("),
     }
     for name, text in parts.items():
         with open(os.path.join(out, name), "w") as f:

@@ -70,8 +70,24 @@ def id_bijection(a, b):
     assert len(np.unique(pairs[:, 0])) == len(pairs) and len(np.unique(pairs[:, 1])) == len(pairs), "id mapping is not 1:1"
 
 
+def canonical_order(clouds):
+    """Clusters finished by the same pass are delivered back to back in an unspecified order (the reference's BFS order
+    over its list of unfinished trees): runs of consecutive cluster messages are sorted by (stamp, size, smallest point)."""
+    out, run = [], []
+    for d, c in clouds:
+        if d["kind"] == 2:
+            run.append((d, c))
+            continue
+        out += sorted(run, key=lambda x: (int(x[0]["stamp_ns"]), int(x[0]["width"]), float(x[1]["globally_unique_point_index"].min())))
+        run = []
+        out.append((d, c))
+    out += sorted(run, key=lambda x: (int(x[0]["stamp_ns"]), int(x[0]["width"]), float(x[1]["globally_unique_point_index"].min())))
+    return out
+
+
 def compare_clouds(want, got, check_visited=True):
     assert len(want) == len(got), f"{len(want)} vs {len(got)} messages"
+    want, got = canonical_order(want), canonical_order(got)
     ids_w, ids_g = [], []
     for i, ((dw, cw), (dg, cg)) in enumerate(zip(want, got)):
         for f in ("from_gcol", "to_gcol", "kind", "width", "height", "point_step", "stamp_ns"):
