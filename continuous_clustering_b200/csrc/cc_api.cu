@@ -158,6 +158,8 @@ struct cc_handle
     int fused_cluster{0};   // CTAs per cluster (0: not available on this device / configuration)
     int fused_threads{512};
     size_t fused_smem{0};
+    int fin_cluster{0};       // CTAs of k_fin_cluster (0: one-CTA k_fin_all)
+    size_t fin_cluster_smem{0};
     unsigned int ticket{0};
     int prefetch_points{16384};
     int occ_probe{8}, occ_probe_heavy{8}; // resident CTAs per SM of the two association kernels
@@ -654,6 +656,49 @@ static void configure_fused(cc_handle* h)
 #endif
 }
 
+// k_fin_cluster: the finish pass of whole-push commits over one thread-block cluster
+static void configure_fin_cluster(cc_handle* h)
+{
+    h->fin_cluster = 0;
+    if (std::getenv("CC_B200_FIN_CLUSTER") && std::atoi(std::getenv("CC_B200_FIN_CLUSTER")) == 0)
+        return;
+    size_t smem = static_cast<size_t>(512) * 8 + static_cast<size_t>(h->d.cap_G) * sizeof(int);
+    if (smem > 200 * 1024)
+        smem = 200 * 1024;
+    h->fin_cluster_smem = smem;
+#ifdef CC_EMU
+    h->fin_cluster = 1;
+#else
+    if (cudaFuncSetAttribute(k_fin_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fin_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return;
+    }
+    for (int cs = 16; cs >= 2; cs >>= 1)
+    {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(static_cast<unsigned>(cs), 1, 1);
+        lc.blockDim = dim3(512, 1, 1);
+        lc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, k_fin_cluster, &lc) == cudaSuccess && nc >= 1)
+        {
+            h->fin_cluster = cs;
+            break;
+        }
+        cudaGetLastError();
+    }
+#endif
+}
+
 static bool fused_eligible(const cc_handle* h, int n)
 {
     return h->fused_cluster > 0 && n <= h->fused_max && !h->timing;
@@ -872,6 +917,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     }
 #endif
     configure_fused(h);
+    configure_fin_cluster(h);
     return CC_OK;
 }
 
@@ -970,10 +1016,43 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
         h->fin_smem_set = fin_smem;
     }
 #endif
-    CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
-    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard);
+    // whole-push speculative pass: the list phases over a thread-block cluster (k_fin_cluster); everything else (commits of
+    // sub-ranges and exact single-column passes of the split path): one CTA
+    const bool clustered = guard == 1 && !exact && ci0 == 0 && ci1 < 0 && h->fin_cluster > 0;
+    if (clustered)
+    {
+#ifdef CC_EMU
+        const int t0 = timing_begin(h, "k_fin_all");
+        CC_LAUNCH(k_fin_cluster, 1, 1, h->fin_cluster_smem, h->stream, cfg, h->d, seq, last, static_cast<int>(h->fin_cluster_smem), snap);
+        timing_end(h, t0);
+#else
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(static_cast<unsigned>(h->fin_cluster), 1, 1);
+        lc.blockDim = dim3(512, 1, 1);
+        lc.dynamicSmemBytes = h->fin_cluster_smem;
+        lc.stream = h->stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(h->fin_cluster);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 2;
+        const int t0 = timing_begin(h, "k_fin_all");
+        cudaLaunchKernelEx(&lc, k_fin_cluster, cfg, h->d, seq, last, static_cast<int>(h->fin_cluster_smem), snap);
+        timing_end(h, t0);
+#endif
+        h->launches++;
+    }
+    else
+        CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
+    CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard, clustered ? 1 : 0);
     // number_of_visited_neighbors of the few points whose walk went beyond the first unpublished column (exact counts)
-    CC_RUN(h, k_visited_fix, h->sm_count * 4, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard);
+    // (a small grid: the list is empty or short; a warp redoes one point in a few microseconds)
+    static const int vfix_grid = std::getenv("CC_B200_VFIX_GRID") ? std::max(1, std::atoi(std::getenv("CC_B200_VFIX_GRID"))) : 32;
+    CC_RUN(h, k_visited_fix, vfix_grid, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)
@@ -1155,7 +1234,15 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
 #else
         const int lite_threads = 1;
 #endif
-        CC_RUN(h, k_scan_lite, 1, lite_threads, lite_threads * sizeof(CcAnchorSeg), cfg, h->d, n);
+        const size_t lite_smem = cc_lite_smem_bytes(n);
+#ifndef CC_EMU
+        if (lite_smem > 48 * 1024 && lite_smem > h->lite_smem_set)
+        {
+            CC_CHECK(h, cudaFuncSetAttribute(k_scan_lite, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lite_smem)));
+            h->lite_smem_set = lite_smem;
+        }
+#endif
+        CC_RUN(h, k_scan_lite, 1, lite_threads, lite_smem, cfg, h->d, n);
     }
     CC_RUN(h, k_scan_check, R, n > 2048 ? 512 : 256, 512 * sizeof(int), cfg, h->d, n);
     // ... then the single-CTA scan commits that prefix and resolves whatever is left

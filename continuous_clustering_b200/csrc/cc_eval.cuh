@@ -83,6 +83,7 @@ CC_DEV unsigned int cc_table_get(const unsigned long long* keys, const unsigned 
 
 __global__ void k_eval_clear(CcEvalPtrs e)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int i = t; i < e.pair_cap; i += nt)
     {
@@ -102,6 +103,7 @@ __global__ void k_eval_clear(CcEvalPtrs e)
 
 __global__ void k_eval_count(CcEvalPtrs e)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     const int lane = threadIdx.x % CC_WARP;
     for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < e.n; i0 += gridDim.x * blockDim.x)
     {
@@ -134,6 +136,7 @@ __global__ void k_eval_count(CcEvalPtrs e)
 
 __global__ void k_eval_entropy(CcEvalPtrs e)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     double ose = 0.0, use = 0.0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < e.pair_cap; s += gridDim.x * blockDim.x)
     {

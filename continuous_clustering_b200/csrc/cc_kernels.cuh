@@ -515,6 +515,14 @@ struct CcOpMaxPair
     }
 };
 
+CC_DEV int cc_lite_slot(int k) // one slot of padding per 8 firings
+{
+    return k + (k >> 3);
+}
+static inline __host__ __device__ size_t cc_lite_smem_bytes(int n)
+{
+    return 1024 + (static_cast<size_t>(n) + (n >> 3) + 8) * sizeof(CcFiringSummary);
+}
 #ifdef CC_EMU
 #define CC_LITE_PER 8192 /* the emulation runs the block as one thread */
 #else
@@ -556,8 +564,14 @@ CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
     const int per = (n + T - 1) / T;
     const int a = t * per < n ? t * per : n, b = (a + per < n) ? a + per : n;
     int kbad = n;
-    // every thread keeps its (at most CC_LITE_PER) firings in registers across the three passes: one batch of loads, one
-    // batch of stores
+    // The per-firing summaries come in and the results go out through shared memory: a thread owns CONSECUTIVE firings
+    // (128 bytes apart per thread: one memory sector per thread and access), so the global accesses are done by all
+    // threads side by side instead (slot padding keeps the per-thread accesses off the same banks).
+    CcFiringSummary* stage = reinterpret_cast<CcFiringSummary*>(smem + 1024);
+    for (int k = t; k < n; k += T)
+        stage[cc_lite_slot(k)] = p.lite_sum[k];
+    __syncthreads();
+    // every thread keeps its (at most CC_LITE_PER) firings in registers across the three passes
     CcFiringSummary fs[CC_LITE_PER];
     int U[CC_LITE_PER], lP[CC_LITE_PER], lF[CC_LITE_PER];
 #pragma unroll
@@ -565,7 +579,7 @@ CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
     {
         fs[u].anchor = fs[u].rear_rel = fs[u].fore_rel = fs[u].nvalid = 0;
         if (a + u < b)
-            fs[u] = p.lite_sum[a + u];
+            fs[u] = stage[cc_lite_slot(a + u)]; // staged with coalesced loads above
     }
     CcTraceScope cc_tr_l1(p.trace, CC_KID_lite_p1, g.bid);
     // pass 1: anchor columns relative to the thread's first valid firing
@@ -660,9 +674,12 @@ CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
         {
             const int k = a + u;
             const int Pk = lP[u] > pre.p ? lP[u] : pre.p, Fk = lF[u] > pre.f ? lF[u] : pre.f;
-            p.lite_P[k] = Pk;
-            p.lite_F[k] = Fk;
-            p.lite_U[k] = U[u];
+            CcFiringSummary o; // (rearmost so far, foremost so far, unwrapped anchor) of firing k, copied out below
+            o.anchor = Pk;
+            o.rear_rel = Fk;
+            o.fore_rel = U[u];
+            o.nvalid = 0;
+            stage[cc_lite_slot(k)] = o;
             if (fs[u].nvalid > 0)
             {
                 const int rear = U[u] + fs[u].rear_rel, fore = U[u] + fs[u].fore_rel;
@@ -682,6 +699,13 @@ CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
     if (kbad < n)
         atomicMin(&sh_kbad, kbad);
     __syncthreads();
+    for (int k = t; k < n; k += T)
+    {
+        const CcFiringSummary o = stage[cc_lite_slot(k)];
+        p.lite_P[k] = o.anchor;
+        p.lite_F[k] = o.rear_rel;
+        p.lite_U[k] = o.fore_rel;
+    }
     if (t == 0)
     {
         st->scan_kbad = sh_kbad;
@@ -4363,7 +4387,7 @@ CC_DEV void d_fin_label(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p,
                         int span_cap = 0, bool via_rep_ = false, CcClusterPoint* h_points_ = nullptr, int h_cap = 0)
 {
     int* spans = FUSED ? spans_ : nullptr;
-    const bool via_rep = FUSED && via_rep_;
+    const bool via_rep = via_rep_;
     CcClusterPoint* h_points = FUSED ? h_points_ : nullptr;
     CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_label, g.bid);
     const CcHead hd = cc_head(p.st);
@@ -4569,10 +4593,11 @@ CC_DEV void d_visited_fix(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
     }
 }
 
-__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec)
+// via_rep: the finish pass before it was k_fin_cluster (the roots do not carry their cluster slot, see d_fin_decide_mark)
+__global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spec, int via_rep)
 {
     CC_PDL_ENTER();
-    d_fin_label<false>(cc_grid(), cfg, p, seq, spec);
+    d_fin_label<false>(cc_grid(), cfg, p, seq, spec, nullptr, 0, via_rep != 0);
 }
 
 __global__ void __launch_bounds__(256) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec)
@@ -5084,6 +5109,7 @@ CC_DEV CcCell cc_gather_cell(const CcDevCfg& cfg, const CcDevPtrs& p, long long 
 
 __global__ void k_export_cells(CcDevCfg cfg, CcDevPtrs p, long long from, int ncols, CcCell* out)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     const long long total = static_cast<long long>(ncols) * cfg.R;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -5119,6 +5145,7 @@ __global__ void k_export_cells(CcDevCfg cfg, CcDevPtrs p, long long from, int nc
 
 __global__ void k_child_counts(CcDevCfg cfg, CcDevPtrs p, long long from, int ncols, int ahead, unsigned int* counts)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     // children sit at most max_steps_in_row columns ahead of their parent (cpp:704-705)
     const long long total = static_cast<long long>(ncols + ahead) * cfg.R;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -5211,6 +5238,7 @@ __global__ void __launch_bounds__(128) k_pack_cloud(CcDevCfg cfg, CcDevPtrs p, i
                                                     const CcClusterPoint* list, int npoints, int nwords, long long cfrom,
                                                     const unsigned int* counts, unsigned char* out, unsigned long long* min_stamp)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     CC_SMEM(smem);
     const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
     const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
@@ -5278,6 +5306,7 @@ __global__ void __launch_bounds__(128) k_pack_requests(CcDevCfg cfg, CcDevPtrs p
                                                        const CcClusterPoint* list, long long cfrom, const unsigned int* counts,
                                                        unsigned char* out, unsigned long long* min_stamps)
 {
+    CC_PDL_ENTER(); // launched with programmatic stream serialization (cc_platform.h): wait for the kernel before
     CC_SMEM(smem);
     const int lane = threadIdx.x % CC_WARP, warp = threadIdx.x / CC_WARP;
     const int nwarps = (blockDim.x + CC_WARP - 1) / CC_WARP;
@@ -5340,6 +5369,62 @@ __global__ void __launch_bounds__(128) k_pack_requests(CcDevCfg cfg, CcDevPtrs p
         }
         if (lane == 0 && smin != ~0ull)
             atomicMin(min_stamps + a, smin);
+    }
+}
+
+// =====================================================================================================
+// K4' the list phases of a whole-push finish pass over ONE thread-block cluster (16 CTAs, cluster barriers) instead of
+//     one CTA with block barriers: aggregate | decide + mark | compacted list back (CTA 1) beside the per-column
+//     first-unpublished columns and the end-of-push bookkeeping (CTA 0). Same device functions as the fused kernel's tail.
+// =====================================================================================================
+__global__ void __launch_bounds__(512, 1) k_fin_cluster(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int last, int smem_bytes,
+                                                        CcDevState* snap)
+{
+    CC_PDL_ENTER();
+    const CcGrid g = cc_grid_cluster();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_fin_all, g.bid);
+    if (p.st->halted) // an earlier push in flight could not be committed speculatively (see k_halt)
+    {
+        if (snap && g.bid == 0)
+            d_state_snapshot(p, snap);
+        return;
+    }
+    {
+        CcTraceScope tr(p.trace, CC_KID_fin_init, g.bid);
+        d_fin_init(g, cfg, p, 0, -1, 1);
+    }
+    cc_cluster_sync();
+    {
+        CcTraceScope tr(p.trace, CC_KID_fin_agg, g.bid);
+        d_fin_agg(g, cfg, p, 1);
+    }
+    cc_cluster_sync();
+    {
+        CcTraceScope tr(p.trace, CC_KID_fin_decide, g.bid);
+        d_fin_decide_mark(g, cfg, p, seq);
+    }
+    cc_cluster_sync();
+    if (g.bid == (g.nb >= 2 ? 1 : 0))
+    {
+        CcTraceScope tr(p.trace, CC_KID_fin_copyback, g.bid);
+        CcGrid g1;
+        g1.bid = 0;
+        g1.nb = 1;
+        d_fin_copyback(g1, p, 1);
+    }
+    if (g.bid == 0)
+    {
+        CcTraceScope tr(p.trace, CC_KID_fin_columns, g.bid);
+        __syncthreads();
+        d_fin_columns(g, cfg, p, 1, (smem_bytes - static_cast<int>(blockDim.x) * 8) / 4);
+        __syncthreads();
+        if (last && threadIdx.x == 0)
+            d_push_done(p, 1);
+        if (snap)
+        {
+            __syncthreads();
+            d_state_snapshot(p, snap);
+        }
     }
 }
 

@@ -30,7 +30,7 @@ for s in range(n):
     if s >= n - 3:
         tr = sorted(cc.get_trace(), key=lambda t: t[1])
         t0 = tr[0][1]
-        print(f"push {s}: device_ms {res.info.device_ms*1e3:.1f} us, n_clusters {res.info.n_clusters}")
+        print(f"push {s}: device_ms {res.info.device_ms*1e3:.1f} us, n_clusters {res.info.n_clusters}, visited recounts {res.info.visited_recounts}")
         prev_end = t0
         for name, a, z, longest, blocks in tr:
             print(f"  {name:18s} start {(a-t0)/1e3:7.1f}  end {(z-t0)/1e3:7.1f}  span {(z-a)/1e3:6.1f}  gap_after_prev {(a-prev_end)/1e3:6.1f}  longest_block {longest/1e3:6.1f}  blocks {blocks}")
