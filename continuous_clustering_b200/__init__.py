@@ -11,4 +11,5 @@ from .api import (  # noqa: F401
     ContinuousRangeImageConfiguration,
     GeneralConfiguration,
     KittiEvaluation,
+    KittiReplay,
 )

@@ -140,6 +140,7 @@ EXPORTED_SYMBOLS = [
     "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
     "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2", "cc_pack_requests_pointcloud2",
     "cc_eval_create", "cc_eval_destroy", "cc_eval_frame",
+    "cc_kitti_create", "cc_kitti_destroy", "cc_kitti_set_poses", "cc_kitti_frame", "cc_kitti_read_debug",
 ]
 
 
@@ -148,6 +149,13 @@ class CcEvalResult(C.Structure):
 
     _fields_ = [("tp", C.c_double), ("fn", C.c_double), ("fp", C.c_double), ("tn", C.c_double),
                 ("over_segmentation_entropy", C.c_double), ("under_segmentation_entropy", C.c_double)]
+
+
+class CcKittiFrame(C.Structure):
+    """cc_kitti_frame_t: the pseudo firings of one KITTI frame, resident on the device."""
+
+    _fields_ = [("n_firings", C.c_int32), ("rows_per_firing", C.c_int32), ("d_firings", C.c_void_p), ("d_poses", C.c_void_p),
+                ("poses", C.c_void_p), ("rows_found", C.c_int32), ("max_points_in_row", C.c_int32)]
 
 
 class CcPackRequest(C.Structure):
@@ -200,6 +208,12 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_eval_destroy.argtypes = [vp]
     lib.cc_eval_destroy.restype = None
     lib.cc_eval_frame.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(CcEvalResult)]
+    lib.cc_kitti_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.cc_kitti_destroy.argtypes = [vp]
+    lib.cc_kitti_destroy.restype = None
+    lib.cc_kitti_set_poses.argtypes = [vp, i32, vp, vp]
+    lib.cc_kitti_frame.argtypes = [vp, i32, vp, C.c_uint64, C.c_uint64, vp, i32, i32, C.POINTER(CcKittiFrame)]
+    lib.cc_kitti_read_debug.argtypes = [vp, vp, vp, vp, vp]
     for name in ("cc_num_rows", "cc_num_columns", "cc_ring_buffer_max_columns"):
         getattr(lib, name).argtypes = [vp]
     lib.cc_stream.argtypes = [vp]

@@ -458,3 +458,70 @@ class KittiEvaluation:
             self.close()
         except Exception:
             pass
+
+
+class KittiReplay:
+    """The per-frame body of the reference's kitti_demo (kitti_demo.cpp:369-403) on the device: a
+    SemanticKITTI frame becomes 2200 pseudo firings of 64 rows with their interpolated poses, resident in device memory
+    (KittiLoader::recoverLaserIndices / undoEgoMotionCorrection / generateRangeImage / interpolate, kitti_loader.cpp:47-210,
+    297-328; makePseudoFiringFromRangeImageColumn, kitti_demo.cpp:123-159)."""
+
+    WIDTH, HEIGHT = 2200, 64
+
+    def __init__(self, device: int = 0, max_points_per_frame: int = 1 << 18, _library=None):
+        self._L = _library or _lib.load_library()
+        h = C.c_void_p()
+        rc = self._L.cc_kitti_create(device, max_points_per_frame, C.byref(h))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_kitti_create failed (no CUDA device: there is no CPU path)")
+        self._h = h
+        self._n = 0
+
+    def set_poses(self, stamps, poses12) -> None:
+        """odom_from_velodyne of the sequence: stamps [n] uint64 ascending, poses [n][12] (3x4 row major)."""
+        st = np.ascontiguousarray(stamps, dtype=np.uint64)
+        ps = np.ascontiguousarray(poses12, dtype=np.float64).reshape(-1, 12)
+        assert st.size == ps.shape[0]
+        rc = self._L.cc_kitti_set_poses(self._h, st.size, st.ctypes.data, ps.ctypes.data)
+        if rc != 0:
+            raise ClusteringError(rc, "cc_kitti_set_poses failed")
+
+    def frame(self, xyzi, stamp_start: int, stamp_end: int, frame_pose12, sequence_index: int, frame_index: int) -> dict:
+        """Returns the device pointers of the frame's firings / poses (feed them to
+        ContinuousClustering.push_device in chunks), the host copy of the poses and the reference's sanity values."""
+        pts = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+        pose = np.ascontiguousarray(frame_pose12, dtype=np.float64).reshape(12)
+        out = _lib.CcKittiFrame()
+        rc = self._L.cc_kitti_frame(self._h, pts.shape[0], pts.ctypes.data, int(stamp_start), int(stamp_end), pose.ctypes.data,
+                                    int(sequence_index), int(frame_index), C.byref(out))
+        if rc != 0:
+            raise ClusteringError(rc, f"cc_kitti_frame failed (longest row: {out.max_points_in_row} points)")
+        self._n = pts.shape[0]
+        poses = np.ctypeslib.as_array(C.cast(out.poses, C.POINTER(C.c_double)), shape=(out.n_firings, 12)).copy()
+        return {"n_firings": out.n_firings, "rows_per_firing": out.rows_per_firing, "d_firings": out.d_firings,
+                "d_poses": out.d_poses, "poses": poses, "rows_found": out.rows_found, "max_points_in_row": out.max_points_in_row}
+
+    def read_debug(self) -> dict:
+        """Intermediate results of the last frame (tests): laser indices, range-image cells, un-corrected points, firings."""
+        laser = np.zeros(self._n, np.uint8)
+        cells = np.zeros(self.WIDTH * self.HEIGHT, np.int32)
+        unc = np.zeros((self._n, 3), np.float32)
+        from .synth import RAW_POINT_DTYPE
+
+        firings = np.zeros(self.WIDTH * self.HEIGHT, dtype=RAW_POINT_DTYPE)
+        rc = self._L.cc_kitti_read_debug(self._h, laser.ctypes.data, cells.ctypes.data, unc.ctypes.data, firings.ctypes.data)
+        if rc != 0:
+            raise ClusteringError(rc, "cc_kitti_read_debug failed")
+        return {"laser_index": laser, "cell_point": cells.reshape(self.HEIGHT, self.WIDTH), "uncorrected": unc,
+                "firings": firings.reshape(self.WIDTH, self.HEIGHT)}
+
+    def close(self):
+        if self._h:
+            self._L.cc_kitti_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

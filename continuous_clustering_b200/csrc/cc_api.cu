@@ -12,6 +12,7 @@
 
 #include "cc_kernels.cuh"
 #include "cc_eval.cuh"
+#include "cc_kitti.cuh"
 
 // optimistic prefix of a push's results brought to the host behind it: cluster records, and member lists for a quarter of
 // the cells of the largest push (a synthetic street scene finishes ~8 % of a push's cells as cluster members)
@@ -2325,6 +2326,315 @@ cc_status_t cc_get_kernel_timings(cc_handle_t* h, char* names, int names_cap, fl
     *n_out = n;
     return CC_OK;
 }
+
+} // extern "C"
+
+// ---- KITTI replay front-end on the device (kitti_loader.cpp:47-210, 297-328; kitti_demo.cpp:123-159, 369-403) ----
+namespace
+{
+// KittiLoader::interpolate, kitti_loader.cpp:297-328: the pose of the sequence at `stamp` -- rotation by quaternion
+// slerp (Eigen 3.3's published formulas: matrix -> quaternion by the trace branches, the (1 - epsilon) shortcut,
+// quaternion -> matrix from the doubled products), translation linearly. f64 on the host, 3x4 row major.
+struct KQuat
+{
+    double x, y, z, w;
+};
+static KQuat kq_from_matrix(const double* m)
+{
+    double c[4];
+    double t = m[0] + m[5] + m[10];
+    if (t > 0.)
+    {
+        t = std::sqrt(t + 1.0);
+        c[3] = 0.5 * t;
+        t = 0.5 / t;
+        c[0] = (m[2 * 4 + 1] - m[1 * 4 + 2]) * t;
+        c[1] = (m[0 * 4 + 2] - m[2 * 4 + 0]) * t;
+        c[2] = (m[1 * 4 + 0] - m[0 * 4 + 1]) * t;
+    }
+    else
+    {
+        int i = 0;
+        if (m[5] > m[0])
+            i = 1;
+        if (m[10] > m[i * 4 + i])
+            i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i * 4 + i] - m[j * 4 + j] - m[k * 4 + k] + 1.0);
+        c[i] = 0.5 * t;
+        t = 0.5 / t;
+        c[3] = (m[k * 4 + j] - m[j * 4 + k]) * t;
+        c[j] = (m[j * 4 + i] + m[i * 4 + j]) * t;
+        c[k] = (m[k * 4 + i] + m[i * 4 + k]) * t;
+    }
+    return KQuat{c[0], c[1], c[2], c[3]};
+}
+static KQuat kq_slerp(const KQuat& a, double t, const KQuat& b)
+{
+    const double one = 1.0 - 2.220446049250313e-16;
+    const double d = (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+    const double ad = std::fabs(d);
+    double s0, s1;
+    if (ad >= one)
+    {
+        s0 = 1.0 - t;
+        s1 = t;
+    }
+    else
+    {
+        const double theta = std::acos(ad), st = std::sin(theta);
+        s0 = std::sin((1.0 - t) * theta) / st;
+        s1 = std::sin(t * theta) / st;
+    }
+    if (d < 0.)
+        s1 = -s1;
+    return KQuat{s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
+}
+static void kq_to_matrix(const KQuat& q, double* m)
+{
+    const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    m[0] = 1.0 - (tyy + tzz);
+    m[1] = txy - twz;
+    m[2] = txz + twy;
+    m[4] = txy + twz;
+    m[5] = 1.0 - (txx + tzz);
+    m[6] = tyz - twx;
+    m[8] = txz - twy;
+    m[9] = tyz + twx;
+    m[10] = 1.0 - (txx + tyy);
+}
+static void kitti_interpolate(const std::vector<uint64_t>& stamps, const std::vector<double>& poses, uint64_t stamp, double* out)
+{
+    const size_t after = static_cast<size_t>(std::lower_bound(stamps.begin(), stamps.end(), stamp) - stamps.begin());
+    if (after == stamps.size())
+        std::memcpy(out, poses.data() + 12 * (after - 1), 12 * sizeof(double));
+    else if (after == 0)
+        std::memcpy(out, poses.data(), 12 * sizeof(double));
+    else
+    {
+        const double* pb = poses.data() + 12 * (after - 1);
+        const double* pa = poses.data() + 12 * after;
+        const double f = static_cast<double>(stamp - stamps[after - 1]) / static_cast<double>(stamps[after] - stamps[after - 1]);
+        kq_to_matrix(kq_slerp(kq_from_matrix(pb), f, kq_from_matrix(pa)), out);
+        for (int i = 0; i < 3; i++)
+            out[4 * i + 3] = (1 - f) * pb[4 * i + 3] + f * pa[4 * i + 3];
+    }
+}
+static void host_iso_inverse(const double* m, double* r)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            r[i * 4 + j] = m[j * 4 + i];
+    for (int i = 0; i < 3; i++)
+        r[i * 4 + 3] = -(r[i * 4 + 0] * m[3] + (r[i * 4 + 1] * m[7] + r[i * 4 + 2] * m[11]));
+}
+static void host_iso_mul(const double* a, const double* b, double* r)
+{
+    for (int i = 0; i < 3; i++)
+    {
+        for (int j = 0; j < 3; j++)
+            r[i * 4 + j] = a[i * 4 + 0] * b[j] + (a[i * 4 + 1] * b[4 + j] + a[i * 4 + 2] * b[8 + j]);
+        r[i * 4 + 3] = (a[i * 4 + 0] * b[3] + (a[i * 4 + 1] * b[7] + a[i * 4 + 2] * b[11])) + a[i * 4 + 3];
+    }
+}
+} // namespace
+
+struct cc_kitti
+{
+    int device{0};
+    int max_points{0};
+    int max_bins{0};
+    cudaStream_t stream{nullptr};
+    CcKittiPtrs d{};
+    float4* d_xyzi{nullptr};
+    double* d_bin_tf{nullptr};
+    CcRawPoint* d_firings{nullptr};
+    double* d_poses{nullptr};
+    double* h_poses{nullptr};  // page-locked [W][12]
+    double* h_bin_tf{nullptr}; // page-locked [max_bins][12]
+    int* h_row_start{nullptr}; // page-locked [H + 2]
+    int last_n{0};
+    std::vector<uint64_t> stamps;
+    std::vector<double> poses;
+    std::vector<void*> allocs;
+};
+
+extern "C" {
+
+cc_status_t cc_kitti_create(int device_ordinal, int max_points_per_frame, cc_kitti_t** out)
+{
+    if (!out || max_points_per_frame <= 0)
+        return CC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ordinal < 0 || device_ordinal >= ndev)
+        return CC_ERR_CUDA;
+    cc_kitti* k = new cc_kitti();
+    k->device = device_ordinal;
+    k->max_points = max_points_per_frame;
+    k->max_bins = 1024; // a rotation of up to one second
+    const size_t np = static_cast<size_t>(max_points_per_frame);
+    const size_t cells = static_cast<size_t>(CC_KITTI_W) * CC_KITTI_H;
+    auto alloc = [&](void** p, size_t bytes) -> bool
+    {
+        if (cudaMalloc(p, bytes) != cudaSuccess)
+            return false;
+        k->allocs.push_back(*p);
+        return true;
+    };
+    bool ok = cudaSetDevice(device_ordinal) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              alloc(reinterpret_cast<void**>(&k->d_xyzi), np * sizeof(float4)) &&
+              alloc(reinterpret_cast<void**>(&k->d.wrap_flag), np) &&
+              alloc(reinterpret_cast<void**>(&k->d.seg_sums), ((np + CC_KITTI_SEG - 1) / CC_KITTI_SEG + 1) * sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&k->d.laser_index), np) &&
+              alloc(reinterpret_cast<void**>(&k->d.uncorrected), np * 3 * sizeof(float)) &&
+              alloc(reinterpret_cast<void**>(&k->d.column), np * sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&k->d.row_start), (CC_KITTI_H + 2) * sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&k->d.cell_point), cells * sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&k->d_bin_tf), static_cast<size_t>(k->max_bins) * 12 * sizeof(double)) &&
+              alloc(reinterpret_cast<void**>(&k->d_firings), cells * sizeof(CcRawPoint)) &&
+              alloc(reinterpret_cast<void**>(&k->d_poses), static_cast<size_t>(CC_KITTI_W) * 12 * sizeof(double)) &&
+              cudaMallocHost(reinterpret_cast<void**>(&k->h_poses), static_cast<size_t>(CC_KITTI_W) * 12 * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void**>(&k->h_bin_tf), static_cast<size_t>(k->max_bins) * 12 * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void**>(&k->h_row_start), (CC_KITTI_H + 2) * sizeof(int)) == cudaSuccess;
+    if (!ok)
+    {
+        cc_kitti_destroy(k);
+        return CC_ERR_CUDA;
+    }
+    *out = k;
+    return CC_OK;
+}
+
+void cc_kitti_destroy(cc_kitti_t* k)
+{
+    if (!k)
+        return;
+    cudaSetDevice(k->device);
+    if (k->stream)
+    {
+        cudaStreamSynchronize(k->stream);
+        cudaStreamDestroy(k->stream);
+    }
+    for (void* p : k->allocs)
+        cudaFree(p);
+    if (k->h_poses)
+        cudaFreeHost(k->h_poses);
+    if (k->h_bin_tf)
+        cudaFreeHost(k->h_bin_tf);
+    if (k->h_row_start)
+        cudaFreeHost(k->h_row_start);
+    delete k;
+}
+
+cc_status_t cc_kitti_set_poses(cc_kitti_t* k, int n_poses, const uint64_t* stamps, const double* poses12)
+{
+    if (!k || n_poses <= 0 || !stamps || !poses12)
+        return CC_ERR_INVALID_ARGUMENT;
+    k->stamps.assign(stamps, stamps + n_poses);
+    k->poses.assign(poses12, poses12 + static_cast<size_t>(n_poses) * 12);
+    return CC_OK;
+}
+
+cc_status_t cc_kitti_frame(cc_kitti_t* k, int n_points, const float* xyzi, uint64_t stamp_start, uint64_t stamp_end,
+                           const double* frame_pose12, int sequence_index, int frame_index, cc_kitti_frame_t* out)
+{
+    if (!k || !out || n_points < 0 || n_points > k->max_points || (n_points > 0 && !xyzi) || !frame_pose12 || k->stamps.empty() ||
+        stamp_end < stamp_start)
+        return CC_ERR_INVALID_ARGUMENT;
+    // undoEgoMotionCorrection's lookup table (kitti_loader.cpp:183-197): one transform per millisecond of the rotation
+    const uint64_t bin_resolution = 1000000;
+    const uint64_t duration = stamp_end - stamp_start;
+    const int n_bins = static_cast<int>(std::ceil(static_cast<double>(duration) / static_cast<double>(bin_resolution)));
+    if (n_bins > k->max_bins)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(k->device) != cudaSuccess)
+        return CC_ERR_CUDA;
+    cudaStream_t st = k->stream;
+    if (n_points > 0 &&
+        cudaMemcpyAsync(k->d_xyzi, xyzi, static_cast<size_t>(n_points) * sizeof(float4), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return CC_ERR_CUDA;
+    for (int b = 0; b < n_bins; b++)
+    {
+        const uint64_t stamp_at_bin = stamp_start + static_cast<uint64_t>(b) * bin_resolution + (bin_resolution / 2);
+        double pose[12], inv[12];
+        kitti_interpolate(k->stamps, k->poses, stamp_at_bin, pose);
+        host_iso_inverse(pose, inv);
+        host_iso_mul(inv, frame_pose12, k->h_bin_tf + 12 * b);
+    }
+    if (n_bins > 0 && cudaMemcpyAsync(k->d_bin_tf, k->h_bin_tf, static_cast<size_t>(n_bins) * 12 * sizeof(double),
+                                      cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return CC_ERR_CUDA;
+    CcKittiPtrs d = k->d;
+    d.xyzi = k->d_xyzi;
+    d.n = n_points;
+    d.bin_tf = k->d_bin_tf;
+    d.n_bins = n_bins > 0 ? n_bins : 1;
+    d.stamp_start = stamp_start;
+    d.stamp_end = stamp_end;
+    const int nseg = (n_points + CC_KITTI_SEG - 1) / CC_KITTI_SEG;
+    const int g_seg = std::max(1, std::min(148 * 4, nseg));
+    const int g_pts = std::max(1, std::min(148 * 8, (n_points + 255) / 256));
+    CC_LAUNCH(k_kitti_flags, g_seg, 256, 0, st, d);
+    CC_LAUNCH(k_kitti_rows, g_seg, 256, 0, st, d);
+    CC_LAUNCH(k_kitti_undo_ego, g_pts, 256, 0, st, d);
+    CC_LAUNCH(k_kitti_range_image, CC_KITTI_H, 256, 0, st, d);
+    CC_LAUNCH(k_kitti_firings, 148 * 4, 256, 0, st, d, k->d_firings, sequence_index, frame_index);
+    // the pose of every pseudo firing (kitti_demo.cpp:386-396) while the device works
+    for (int col = 0; col < CC_KITTI_W; col++)
+    {
+        const double elapsed_ratio = static_cast<double>(col) / (CC_KITTI_W - 1);
+        const double elapsed_time = static_cast<double>(duration) * elapsed_ratio;
+        kitti_interpolate(k->stamps, k->poses, stamp_start + static_cast<uint64_t>(elapsed_time), k->h_poses + 12 * col);
+    }
+    if (cudaMemcpyAsync(k->d_poses, k->h_poses, static_cast<size_t>(CC_KITTI_W) * 12 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(k->h_row_start, d.row_start, (CC_KITTI_H + 2) * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return CC_ERR_CUDA;
+    k->last_n = n_points;
+    // the reference's sanity checks (kitti_loader.cpp:91-98): rows found, longest COMPLETED row
+    int rows = 0, longest = 0;
+    for (int r = 0; r <= CC_KITTI_H; r++)
+        if (n_points > 0 && (r == 0 || k->h_row_start[r] < n_points))
+            rows = r + 1;
+    for (int r = 0; r + 1 < std::min(rows, CC_KITTI_H); r++)
+        longest = std::max(longest, k->h_row_start[r + 1] - k->h_row_start[r]);
+    out->n_firings = CC_KITTI_W;
+    out->rows_per_firing = CC_KITTI_H;
+    out->d_firings = reinterpret_cast<const cc_raw_point_t*>(k->d_firings);
+    out->d_poses = k->d_poses;
+    out->poses = k->h_poses;
+    out->rows_found = rows;
+    out->max_points_in_row = longest;
+    return longest > CC_KITTI_W ? CC_ERR_INVALID_ARGUMENT : CC_OK; // "More points in a single row than expected", cpp:96-97
+}
+
+cc_status_t cc_kitti_read_debug(cc_kitti_t* k, uint8_t* laser_index, int32_t* cell_point, float* uncorrected_xyz, cc_raw_point_t* firings)
+{
+    if (!k)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(k->device) != cudaSuccess)
+        return CC_ERR_CUDA;
+    const size_t n = static_cast<size_t>(k->last_n), cells = static_cast<size_t>(CC_KITTI_W) * CC_KITTI_H;
+    bool ok = true;
+    if (laser_index && n)
+        ok = ok && cudaMemcpy(laser_index, k->d.laser_index, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (cell_point)
+        ok = ok && cudaMemcpy(cell_point, k->d.cell_point, cells * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (uncorrected_xyz && n)
+        ok = ok && cudaMemcpy(uncorrected_xyz, k->d.uncorrected, n * 3 * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (firings)
+        ok = ok && cudaMemcpy(firings, k->d_firings, cells * sizeof(CcRawPoint), cudaMemcpyDeviceToHost) == cudaSuccess;
+    return ok ? CC_OK : CC_ERR_CUDA;
+}
+
+} // extern "C"
+
+extern "C" {
 
 // ---- evaluation metrics on the device (kitti_evaluation.cpp:44-146) ----
 struct cc_eval

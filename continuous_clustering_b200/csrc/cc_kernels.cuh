@@ -264,6 +264,10 @@ struct CcOpMaxI64
 {
     CC_DEV long long operator()(long long a, long long b) const { return a > b ? a : b; }
 };
+struct CcOpAddI32
+{
+    CC_DEV int operator()(int a, int b) const { return a + b; }
+};
 struct CcOpAddI64
 {
     CC_DEV long long operator()(long long a, long long b) const { return a + b; }

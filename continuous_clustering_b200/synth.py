@@ -244,3 +244,57 @@ def make_stream(
             rows, dtype=np.uint64
         )[None, :]
     return pts, poses, sp
+
+
+def make_kitti_frame(seed: int = 7, frame_index: int = 3, n_poses: int = 8, dropout: float = 0.05, n_boxes: int = 150,
+                     top_rows_empty: int = 0):
+    """A synthetic frame in the layout of a SemanticKITTI velodyne .bin file, for the replay front-end (SURVEY 8f-2;
+    there is no dataset in the image): the returns of one rotation of the 64-ring stream above, row after row (top laser
+    first), NaN returns omitted, every row ordered by atan2 azimuth 0 -> pi -> -pi -> 0 (kitti_loader.cpp:49-54),
+    ego-motion corrected to the pose at the middle of the rotation, intensity in [0, 1).
+    Returns (xyzi [n, 4] float32, stamp_start, stamp_end, pose_stamps [n_poses] uint64, poses [n_poses, 12],
+    frame_pose [12]) with poses = odom_from_velodyne of a sensor driving an arc, one per rotation."""
+    sp = spec("velodyne64")
+    n = sp.num_columns
+    pts, fposes, _ = make_stream("velodyne64", n_firings=n, seed=seed, moving=True, start_firing=frame_index * n, dropout=dropout,
+                                 n_boxes=n_boxes)
+    rng = np.random.RandomState(seed + 77)
+    t_rot = 1e9 / sp.rotation_hz
+    t0 = 1_000_000_000
+    stamp_start = int(t0 + frame_index * t_rot)
+    stamp_end = int(stamp_start + t_rot)
+
+    def pose_at(t_ns):
+        t_s = t_ns * 1e-9
+        yaw = 0.2 * t_s
+        m = np.zeros(12)
+        r = _rot_z(yaw)
+        m[0:3], m[4:7], m[8:11] = r[0], r[1], r[2]
+        m[3] = 10.0 / 0.2 * np.sin(yaw)
+        m[7] = 10.0 / 0.2 * (1.0 - np.cos(yaw))
+        return m
+
+    first = frame_index - n_poses // 2
+    pose_stamps = np.array([int(t0 + (first + i + 0.5) * t_rot) - t0 for i in range(n_poses)], dtype=np.int64)
+    poses = np.stack([pose_at(s) for s in pose_stamps])
+    pose_stamps = (pose_stamps + t0).astype(np.uint64)
+    mid = pose_at(stamp_start - t0 + 0.5 * t_rot)
+    # ego-motion correction: sensor frame at the firing -> odom -> sensor frame at the middle of the rotation
+    rm = mid.reshape(3, 4)
+    xyz = np.stack([pts["x"], pts["y"], pts["z"]], -1).astype(np.float64)  # (firing, row, 3)
+    fp = fposes.reshape(-1, 3, 4)
+    odom = np.einsum("fij,frj->fri", fp[:, :, :3], xyz) + fp[:, None, :, 3]
+    corr = np.einsum("ji,frj->fri", rm[:, :3], odom - rm[:, 3])
+    out = []
+    for row in range(sp.rows):
+        p = corr[:, row, :]
+        p = p[~np.isnan(p[:, 0])]
+        if row < top_rows_empty:
+            continue
+        az = np.arctan2(p[:, 1], p[:, 0])
+        order = np.argsort(np.where(az < 0, az + 2 * np.pi, az), kind="stable")
+        out.append(p[order])
+    xyz = np.concatenate(out).astype(np.float32)
+    inten = (rng.randint(0, 100, size=xyz.shape[0]) / 100.0).astype(np.float32)
+    xyzi = np.concatenate([xyz, inten[:, None]], axis=1).astype(np.float32)
+    return np.ascontiguousarray(xyzi), stamp_start, stamp_end, pose_stamps, poses, mid

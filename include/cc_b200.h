@@ -395,6 +395,37 @@ CC_API cc_status_t cc_eval_frame(cc_eval_t* e, int n_points, const uint16_t* sem
                                  const uint32_t* euclidean_clustering_label, const uint32_t* detection_label,
                                  cc_eval_result_t* out);
 
+/* ---- KITTI replay front-end -------------------------------------------------------------
+ * The per-frame body of the reference's kitti_demo (src/tools/kitti_demo.cpp:369-403) on the device: one SemanticKITTI
+ * frame (n points x {x, y, z, intensity} floats in file order) -> KittiLoader::recoverLaserIndices
+ * (src/evaluation/kitti_loader.cpp:47-99) -> undoEgoMotionCorrection (kitti_loader.cpp:176-210) -> generateRangeImage
+ * (kitti_loader.cpp:101-174) -> one pseudo firing per range-image column (makePseudoFiringFromRangeImageColumn,
+ * kitti_demo.cpp:123-159) with its interpolated pose (KittiLoader::interpolate, kitti_loader.cpp:297-328). The 2200 x 64
+ * RawPoint records stay in device memory, ready for cc_submit_firings_device / cc_push_firings_device (in chunks of at most
+ * cc_max_firings_per_push firings: d_firings + k * 64, d_poses + k * 12). */
+typedef struct cc_kitti cc_kitti_t;
+typedef struct cc_kitti_frame
+{
+    int32_t n_firings;               /* KittiLoader::RANGE_IMAGE_WIDTH = 2200 */
+    int32_t rows_per_firing;         /* KittiLoader::RANGE_IMAGE_HEIGHT = 64 */
+    const cc_raw_point_t* d_firings; /* device: [n_firings][rows_per_firing] */
+    const double* d_poses;           /* device: [n_firings][12] odom_from_velodyne at the firing's stamp */
+    const double* poses;             /* the same on the host (page-locked), valid until the next cc_kitti_frame */
+    int32_t rows_found;              /* laser_index + 1 of recoverLaserIndices: != 64 is the reference's "Wrong number of rows found" */
+    int32_t max_points_in_row;       /* > 2200 is the reference's "More points in a single row than expected" (status != CC_OK) */
+} cc_kitti_frame_t;
+CC_API cc_status_t cc_kitti_create(int device_ordinal, int max_points_per_frame, cc_kitti_t** out);
+CC_API void cc_kitti_destroy(cc_kitti_t* k);
+/* The sequence's odom_from_velodyne transforms (3x4 row major) and their stamps, ascending (kitti_demo.cpp:331-341). */
+CC_API cc_status_t cc_kitti_set_poses(cc_kitti_t* k, int n_poses, const uint64_t* stamps, const double* poses12);
+/* frame_pose12: odom_from_velodyne at the middle of this frame's rotation (transforms_odom_from_velodyne[frame_index]). */
+CC_API cc_status_t cc_kitti_frame(cc_kitti_t* k, int n_points, const float* xyzi, uint64_t stamp_start, uint64_t stamp_end,
+                                  const double* frame_pose12, int sequence_index, int frame_index, cc_kitti_frame_t* out);
+/* Intermediate results of the last frame for tests (any pointer may be NULL): laser_index[n], the point held by every
+ * range-image cell [64 * 2200] (row major, -1 = empty), the un-corrected coordinates [n][3], the firings [2200][64]. */
+CC_API cc_status_t cc_kitti_read_debug(cc_kitti_t* k, uint8_t* laser_index, int32_t* cell_point, float* uncorrected_xyz,
+                                       cc_raw_point_t* firings);
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */
