@@ -9,7 +9,7 @@ CXX := $(if $(wildcard /usr/bin/g++),/usr/bin/g++,g++)
 CSRC := continuous_clustering_b200/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
            -Xcompiler -fPIC,-fvisibility=hidden -shared
-HDRS := $(CSRC)/cc_kernels.cuh $(CSRC)/cc_eval.cuh $(CSRC)/cc_kitti.cuh $(CSRC)/cc_types.h $(CSRC)/cc_math.cuh $(CSRC)/cc_platform.h include/cc_b200.h
+HDRS := $(CSRC)/cc_kernels.cuh $(CSRC)/cc_eval.cuh $(CSRC)/cc_kitti.cuh $(CSRC)/cc_packets.cuh $(CSRC)/cc_types.h $(CSRC)/cc_math.cuh $(CSRC)/cc_platform.h include/cc_b200.h
 
 .PHONY: all lib oracle emu facade clean
 all: lib oracle emu

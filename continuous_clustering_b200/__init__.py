@@ -12,4 +12,5 @@ from .api import (  # noqa: F401
     GeneralConfiguration,
     KittiEvaluation,
     KittiReplay,
+    OusterInput,
 )

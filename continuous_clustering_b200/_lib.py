@@ -140,6 +140,8 @@ EXPORTED_SYMBOLS = [
     "cc_debug_trace", "cc_debug_get_trace", "cc_debug_slot_base", "cc_debug_slot_times", "cc_export_columns",
     "cc_pack_columns_pointcloud2", "cc_pack_cluster_pointcloud2", "cc_pack_requests_pointcloud2",
     "cc_eval_create", "cc_eval_destroy", "cc_eval_frame",
+    "cc_ouster_format_legacy", "cc_ouster_create", "cc_ouster_destroy", "cc_ouster_packet_size", "cc_ouster_set_lut",
+    "cc_ouster_reset", "cc_ouster_decode", "cc_ouster_read_firings",
     "cc_kitti_create", "cc_kitti_destroy", "cc_kitti_set_poses", "cc_kitti_frame", "cc_kitti_read_debug",
 ]
 
@@ -156,6 +158,21 @@ class CcKittiFrame(C.Structure):
 
     _fields_ = [("n_firings", C.c_int32), ("rows_per_firing", C.c_int32), ("d_firings", C.c_void_p), ("d_poses", C.c_void_p),
                 ("poses", C.c_void_p), ("rows_found", C.c_int32), ("max_points_in_row", C.c_int32)]
+
+
+class CcOusterFormat(C.Structure):
+    """cc_ouster_format_t: the layout of a lidar packet (ouster::sensor::packet_format as data)."""
+
+    _fields_ = [(n, C.c_int32) for n in ("columns_per_packet", "pixels_per_column", "columns_per_frame", "packet_header_size",
+                                         "col_header_size", "col_footer_size", "pixel_bytes", "col_measurement_id_offset",
+                                         "col_status_offset", "col_status_bytes", "range_offset", "range_bytes")] + [
+        ("range_mask", C.c_uint32), ("range_shift", C.c_int32), ("signal_offset", C.c_int32), ("signal_bytes", C.c_int32),
+        ("signal_mask", C.c_uint32), ("signal_shift", C.c_int32), ("offset_from_direction_table", C.c_int32)]
+
+
+class CcDecodedFirings(C.Structure):
+    _fields_ = [("n_firings", C.c_int32), ("rows_per_firing", C.c_int32), ("d_firings", C.c_void_p), ("firing_stamps", C.c_void_p),
+                ("first_firing_index", C.c_uint64)]
 
 
 class CcPackRequest(C.Structure):
@@ -208,6 +225,16 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cc_eval_destroy.argtypes = [vp]
     lib.cc_eval_destroy.restype = None
     lib.cc_eval_frame.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(CcEvalResult)]
+    lib.cc_ouster_format_legacy.argtypes = [i32, i32, C.POINTER(CcOusterFormat)]
+    lib.cc_ouster_format_legacy.restype = None
+    lib.cc_ouster_create.argtypes = [i32, C.POINTER(CcOusterFormat), i32, C.POINTER(vp)]
+    lib.cc_ouster_destroy.argtypes = [vp]
+    lib.cc_ouster_destroy.restype = None
+    lib.cc_ouster_packet_size.argtypes = [vp]
+    lib.cc_ouster_set_lut.argtypes = [vp, vp, vp]
+    lib.cc_ouster_reset.argtypes = [vp]
+    lib.cc_ouster_decode.argtypes = [vp, i32, vp, vp, C.POINTER(CcDecodedFirings)]
+    lib.cc_ouster_read_firings.argtypes = [vp, i32, vp]
     lib.cc_kitti_create.argtypes = [i32, i32, C.POINTER(vp)]
     lib.cc_kitti_destroy.argtypes = [vp]
     lib.cc_kitti_destroy.restype = None

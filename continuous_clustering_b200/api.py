@@ -525,3 +525,62 @@ class KittiReplay:
             self.close()
         except Exception:
             pass
+
+
+class OusterInput:
+    """OusterInput::onRawDataArrived (ouster_input.hpp:105-181) for batches of lidar packets on the device (SURVEY 8f-3):
+    every valid measurement block becomes one firing of RawPoints in device memory."""
+
+    def __init__(self, rows: int, columns_per_frame: int, direction, offset, device: int = 0, max_packets_per_call: int = 256,
+                 fmt: "_lib.CcOusterFormat | None" = None, _library=None):
+        self._L = _library or _lib.load_library()
+        if fmt is None:
+            fmt = _lib.CcOusterFormat()
+            self._L.cc_ouster_format_legacy(rows, columns_per_frame, C.byref(fmt))
+        self.format = fmt
+        h = C.c_void_p()
+        rc = self._L.cc_ouster_create(device, C.byref(fmt), max_packets_per_call, C.byref(h))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_ouster_create failed (no CUDA device: there is no CPU path)")
+        self._h = h
+        d = np.ascontiguousarray(direction, dtype=np.float32)
+        o = np.ascontiguousarray(offset, dtype=np.float32)
+        assert d.shape == o.shape == (columns_per_frame * rows, 3)
+        if self._L.cc_ouster_set_lut(h, d.ctypes.data, o.ctypes.data) != 0:
+            raise ClusteringError(2, "cc_ouster_set_lut failed")
+        self.packet_size = int(self._L.cc_ouster_packet_size(h))
+
+    def reset(self):
+        self._L.cc_ouster_reset(self._h)
+
+    def decode(self, packets, receive_stamps) -> dict:
+        pk = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, self.packet_size)
+        st = np.ascontiguousarray(receive_stamps, dtype=np.uint64)
+        assert st.size == pk.shape[0]
+        out = _lib.CcDecodedFirings()
+        rc = self._L.cc_ouster_decode(self._h, pk.shape[0], pk.ctypes.data, st.ctypes.data, C.byref(out))
+        if rc != 0:
+            raise ClusteringError(rc, "cc_ouster_decode failed")
+        stamps = (np.ctypeslib.as_array(C.cast(out.firing_stamps, C.POINTER(C.c_uint64)), shape=(out.n_firings,)).copy()
+                  if out.n_firings else np.zeros(0, np.uint64))
+        return {"n_firings": out.n_firings, "rows_per_firing": out.rows_per_firing, "d_firings": out.d_firings,
+                "firing_stamps": stamps, "first_firing_index": out.first_firing_index}
+
+    def read_firings(self, n_firings: int) -> np.ndarray:
+        from .synth import RAW_POINT_DTYPE
+
+        out = np.zeros((n_firings, self.format.pixels_per_column), dtype=RAW_POINT_DTYPE)
+        if self._L.cc_ouster_read_firings(self._h, n_firings, out.ctypes.data) != 0:
+            raise ClusteringError(2, "cc_ouster_read_firings failed")
+        return out
+
+    def close(self):
+        if self._h:
+            self._L.cc_ouster_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -13,6 +13,7 @@
 #include "cc_kernels.cuh"
 #include "cc_eval.cuh"
 #include "cc_kitti.cuh"
+#include "cc_packets.cuh"
 
 // optimistic prefix of a push's results brought to the host behind it: cluster records, and member lists for a quarter of
 // the cells of the largest push (a synthetic street scene finishes ~8 % of a push's cells as cluster members)
@@ -2630,6 +2631,218 @@ cc_status_t cc_kitti_read_debug(cc_kitti_t* k, uint8_t* laser_index, int32_t* ce
     if (firings)
         ok = ok && cudaMemcpy(firings, k->d_firings, cells * sizeof(CcRawPoint), cudaMemcpyDeviceToHost) == cudaSuccess;
     return ok ? CC_OK : CC_ERR_CUDA;
+}
+
+} // extern "C"
+
+// ---- sensor packets -> firings on the device (ouster_input.hpp:105-181) ----
+static_assert(sizeof(cc_ouster_format_t) == sizeof(CcOusterFormat), "cc_ouster_format_t and CcOusterFormat must match");
+struct cc_ouster
+{
+    int device{0};
+    int max_packets{0};
+    cudaStream_t stream{nullptr};
+    CcOusterFormat fmt{};
+    int packet_size{0};
+    bool has_lut{false};
+    bool interrupt{true}; // OusterInput::interrupt_message after reset() (:97-101): the packet in flight is discarded
+    unsigned long long firing_index{0};
+    unsigned char* d_packets{nullptr};
+    unsigned long long* d_recv{nullptr};
+    float* d_direction{nullptr};
+    float* d_offset{nullptr};
+    int* d_firing_of_column{nullptr};
+    int* d_n_firings{nullptr};
+    CcRawPoint* d_firings{nullptr};
+    unsigned long long* d_firing_stamp{nullptr};
+    unsigned long long* h_firing_stamp{nullptr}; // page-locked
+    int* h_n_firings{nullptr};                   // page-locked
+    std::vector<void*> allocs;
+};
+
+extern "C" {
+
+void cc_ouster_format_legacy(int pixels_per_column, int columns_per_frame, cc_ouster_format_t* f)
+{
+    // the LEGACY lidar data profile: 16 measurement blocks per packet; block = 16-byte header (timestamp u64,
+    // measurement id u16, frame id u16, encoder u32), 12 bytes per pixel (range u32 of which 20 bits, flags in the top 4,
+    // reflectivity u16, signal u16, near-infrared u16, 2 unused), 4-byte status (0xffffffff = valid)
+    std::memset(f, 0, sizeof(*f));
+    f->columns_per_packet = 16;
+    f->pixels_per_column = pixels_per_column;
+    f->columns_per_frame = columns_per_frame;
+    f->packet_header_size = 0;
+    f->col_header_size = 16;
+    f->col_footer_size = 4;
+    f->pixel_bytes = 12;
+    f->col_measurement_id_offset = 8;
+    f->col_status_offset = 16 + 12 * pixels_per_column;
+    f->col_status_bytes = 4;
+    f->range_offset = 0;
+    f->range_bytes = 4;
+    f->range_mask = 0x000fffffu;
+    f->range_shift = 0;
+    f->signal_offset = 6;
+    f->signal_bytes = 2;
+    f->signal_mask = 0;
+    f->signal_shift = 0;
+    f->offset_from_direction_table = 1;
+}
+
+cc_status_t cc_ouster_create(int device_ordinal, const cc_ouster_format_t* format, int max_packets_per_call, cc_ouster_t** out)
+{
+    if (!out || !format || max_packets_per_call <= 0 || format->columns_per_packet <= 0 || format->pixels_per_column <= 0 ||
+        format->columns_per_frame <= 0 || format->pixel_bytes <= 0 || format->range_bytes < 1 || format->range_bytes > 4 ||
+        format->signal_bytes < 1 || format->signal_bytes > 4 || (format->col_status_bytes != 2 && format->col_status_bytes != 4))
+        return CC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ordinal < 0 || device_ordinal >= ndev)
+        return CC_ERR_CUDA;
+    cc_ouster* o = new cc_ouster();
+    o->device = device_ordinal;
+    o->max_packets = max_packets_per_call;
+    std::memcpy(&o->fmt, format, sizeof(CcOusterFormat));
+    const int H = format->pixels_per_column;
+    o->packet_size = format->packet_header_size +
+                     format->columns_per_packet * (format->col_header_size + H * format->pixel_bytes + format->col_footer_size);
+    const size_t ncol = static_cast<size_t>(max_packets_per_call) * format->columns_per_packet;
+    const size_t lut = static_cast<size_t>(format->columns_per_frame) * H * 3 * sizeof(float);
+    auto alloc = [&](void** p, size_t bytes) -> bool
+    {
+        if (cudaMalloc(p, bytes) != cudaSuccess)
+            return false;
+        o->allocs.push_back(*p);
+        return true;
+    };
+    bool ok = cudaSetDevice(device_ordinal) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              alloc(reinterpret_cast<void**>(&o->d_packets), static_cast<size_t>(max_packets_per_call) * o->packet_size) &&
+              alloc(reinterpret_cast<void**>(&o->d_recv), static_cast<size_t>(max_packets_per_call) * sizeof(unsigned long long)) &&
+              alloc(reinterpret_cast<void**>(&o->d_direction), lut) && alloc(reinterpret_cast<void**>(&o->d_offset), lut) &&
+              alloc(reinterpret_cast<void**>(&o->d_firing_of_column), ncol * sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&o->d_n_firings), sizeof(int)) &&
+              alloc(reinterpret_cast<void**>(&o->d_firings), ncol * H * sizeof(CcRawPoint)) &&
+              alloc(reinterpret_cast<void**>(&o->d_firing_stamp), ncol * sizeof(unsigned long long)) &&
+              cudaMallocHost(reinterpret_cast<void**>(&o->h_firing_stamp), ncol * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void**>(&o->h_n_firings), sizeof(int)) == cudaSuccess;
+    if (!ok)
+    {
+        cc_ouster_destroy(o);
+        return CC_ERR_CUDA;
+    }
+    *out = o;
+    return CC_OK;
+}
+
+void cc_ouster_destroy(cc_ouster_t* o)
+{
+    if (!o)
+        return;
+    cudaSetDevice(o->device);
+    if (o->stream)
+    {
+        cudaStreamSynchronize(o->stream);
+        cudaStreamDestroy(o->stream);
+    }
+    for (void* p : o->allocs)
+        cudaFree(p);
+    if (o->h_firing_stamp)
+        cudaFreeHost(o->h_firing_stamp);
+    if (o->h_n_firings)
+        cudaFreeHost(o->h_n_firings);
+    delete o;
+}
+
+int cc_ouster_packet_size(const cc_ouster_t* o)
+{
+    return o ? o->packet_size : 0;
+}
+
+cc_status_t cc_ouster_set_lut(cc_ouster_t* o, const float* direction, const float* offset)
+{
+    if (!o || !direction || !offset)
+        return CC_ERR_INVALID_ARGUMENT;
+    const size_t lut = static_cast<size_t>(o->fmt.columns_per_frame) * o->fmt.pixels_per_column * 3 * sizeof(float);
+    if (cudaSetDevice(o->device) != cudaSuccess || cudaMemcpy(o->d_direction, direction, lut, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(o->d_offset, offset, lut, cudaMemcpyHostToDevice) != cudaSuccess)
+        return CC_ERR_CUDA;
+    o->has_lut = true;
+    return CC_OK;
+}
+
+cc_status_t cc_ouster_reset(cc_ouster_t* o)
+{
+    if (!o)
+        return CC_ERR_INVALID_ARGUMENT;
+    o->firing_index = 0; // SensorInput::reset, sensor_input.hpp:15-19
+    o->interrupt = true; // OusterInput::reset, ouster_input.hpp:97-101
+    return CC_OK;
+}
+
+cc_status_t cc_ouster_decode(cc_ouster_t* o, int n_packets, const uint8_t* packets, const uint64_t* receive_stamps, cc_decoded_firings_t* out)
+{
+    if (!o || !out || n_packets < 0 || n_packets > o->max_packets || (n_packets > 0 && (!packets || !receive_stamps)) || !o->has_lut)
+        return CC_ERR_INVALID_ARGUMENT;
+    std::memset(out, 0, sizeof(*out));
+    out->rows_per_firing = o->fmt.pixels_per_column;
+    out->d_firings = reinterpret_cast<const cc_raw_point_t*>(o->d_firings);
+    out->firing_stamps = reinterpret_cast<const uint64_t*>(o->h_firing_stamp);
+    out->first_firing_index = o->firing_index;
+    // after a reset the packet in flight is cut short: its first valid measurement block is parsed into a firing that
+    // is thrown away and the rest of the packet is skipped (ouster_input.hpp:171-180) -- nothing of it is published
+    if (o->interrupt && n_packets > 0)
+    {
+        o->interrupt = false;
+        packets += o->packet_size;
+        receive_stamps++;
+        n_packets--;
+    }
+    if (n_packets == 0)
+        return CC_OK;
+    if (cudaSetDevice(o->device) != cudaSuccess)
+        return CC_ERR_CUDA;
+    cudaStream_t st = o->stream;
+    if (cudaMemcpyAsync(o->d_packets, packets, static_cast<size_t>(n_packets) * o->packet_size, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(o->d_recv, receive_stamps, static_cast<size_t>(n_packets) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return CC_ERR_CUDA;
+    CcOusterPtrs p{};
+    p.packets = o->d_packets;
+    p.n_packets = n_packets;
+    p.packet_size = o->packet_size;
+    p.receive_stamp = o->d_recv;
+    p.direction = o->d_direction;
+    p.offset = o->d_offset;
+    p.firing_of_column = o->d_firing_of_column;
+    p.n_firings = o->d_n_firings;
+    p.first_firing_index = o->firing_index;
+    p.firings = o->d_firings;
+    p.firing_stamp = o->d_firing_stamp;
+    const int total = n_packets * o->fmt.columns_per_packet * o->fmt.pixels_per_column;
+    CC_LAUNCH(k_ouster_index, 1, 256, 0, st, o->fmt, p);
+    CC_LAUNCH(k_ouster_decode, std::max(1, std::min(148 * 8, (total + 255) / 256)), 256, 0, st, o->fmt, p);
+    const size_t ncol = static_cast<size_t>(n_packets) * o->fmt.columns_per_packet;
+    if (cudaMemcpyAsync(o->h_n_firings, o->d_n_firings, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(o->h_firing_stamp, o->d_firing_stamp, ncol * sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return CC_ERR_CUDA;
+    out->n_firings = *o->h_n_firings;
+    o->firing_index += static_cast<unsigned long long>(out->n_firings);
+    return CC_OK;
+}
+
+cc_status_t cc_ouster_read_firings(cc_ouster_t* o, int n_firings, cc_raw_point_t* firings)
+{
+    if (!o || n_firings < 0 || (n_firings > 0 && !firings) ||
+        static_cast<size_t>(n_firings) > static_cast<size_t>(o->max_packets) * o->fmt.columns_per_packet)
+        return CC_ERR_INVALID_ARGUMENT;
+    if (n_firings == 0)
+        return CC_OK;
+    if (cudaSetDevice(o->device) != cudaSuccess ||
+        cudaMemcpy(firings, o->d_firings, static_cast<size_t>(n_firings) * o->fmt.pixels_per_column * sizeof(CcRawPoint),
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+        return CC_ERR_CUDA;
+    return CC_OK;
 }
 
 } // extern "C"

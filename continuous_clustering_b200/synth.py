@@ -298,3 +298,54 @@ def make_kitti_frame(seed: int = 7, frame_index: int = 3, n_poses: int = 8, drop
     inten = (rng.randint(0, 100, size=xyz.shape[0]) / 100.0).astype(np.float32)
     xyzi = np.concatenate([xyz, inten[:, None]], axis=1).astype(np.float32)
     return np.ascontiguousarray(xyzi), stamp_start, stamp_end, pose_stamps, poses, mid
+
+
+def ouster_xyz_lut(side: str = "left", columns_per_frame: int = 1024, origin_to_beam_mm: float = 27.67,
+                   lidar_to_sensor=(-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 36.18, 0, 0, 0, 1), range_unit: float = 0.001):
+    """The sensor's lookup table the way OusterInput builds it (ouster_input.hpp:66-95): ouster::make_xyz_lut for the
+    beam tables of calibrations/touareg_os32_<side>.json (published geometry: encoder angle 2 pi (1 - col / W), beam azimuth
+    / altitude, beam origin offset, lidar-to-sensor transform, millimetres -> metres), cast to float and reordered so
+    that the pixels of one measurement block are consecutive: ([W * H, 3] direction, [W * H, 3] offset).
+    Test / bench scaffolding: a deployment takes the tables from the SDK."""
+    alt = np.deg2rad(np.asarray(_OS32_ALTITUDE_DEG[side], dtype=np.float64))
+    azi = -np.deg2rad(np.asarray(_OS32_AZIMUTH_DEG[side], dtype=np.float64))
+    w, h = columns_per_frame, alt.shape[0]
+    enc = 2.0 * np.pi * (1.0 - np.arange(w, dtype=np.float64) / w)  # (w,)
+    e, a, t = enc[:, None], azi[None, :], alt[None, :]
+    direction = np.stack([np.cos(e + a) * np.cos(t), np.sin(e + a) * np.cos(t), np.broadcast_to(np.sin(t), (w, h))], -1)
+    offset = np.stack([(np.cos(e) - direction[..., 0]) * origin_to_beam_mm, (np.sin(e) - direction[..., 1]) * origin_to_beam_mm,
+                       -direction[..., 2] * origin_to_beam_mm], -1)
+    m = np.asarray(lidar_to_sensor, dtype=np.float64).reshape(4, 4)
+    direction = direction @ m[:3, :3].T
+    offset = offset @ m[:3, :3].T + m[:3, 3]
+    direction = (direction * range_unit).astype(np.float32).reshape(w * h, 3)
+    offset = (offset * range_unit).astype(np.float32).reshape(w * h, 3)
+    return np.ascontiguousarray(direction), np.ascontiguousarray(offset)
+
+
+def make_ouster_packets(n_packets: int, rows: int = 32, columns_per_frame: int = 1024, seed: int = 5, first_measurement_id: int = 0,
+                        p_invalid: float = 0.03, p_no_return: float = 0.2):
+    """LEGACY-profile lidar packets (16 measurement blocks of 16 + 12 * rows + 4 bytes) with random ranges (20 bits, a
+    share of zeros = no return), signal photons 0..3000 and a few invalid blocks; measurement ids run through the frame.
+    Returns (packets [n_packets, packet_size] uint8, receive_stamps [n_packets] uint64)."""
+    rng = np.random.RandomState(seed)
+    col_size = 16 + 12 * rows + 4
+    packets = np.zeros((n_packets, 16, col_size), dtype=np.uint8)
+    m_id = (first_measurement_id + np.arange(n_packets * 16)) % columns_per_frame
+    hdr = packets[:, :, :16].reshape(-1, 16)
+    hdr[:, 0:8] = (np.arange(n_packets * 16, dtype=np.uint64) * 97656 + 1_000_000).view(np.uint8).reshape(-1, 8)
+    hdr[:, 8:10] = m_id.astype("<u2").view(np.uint8).reshape(-1, 2)
+    hdr[:, 10:12] = ((first_measurement_id + np.arange(n_packets * 16)) // columns_per_frame).astype("<u2").view(np.uint8).reshape(-1, 2)
+    hdr[:, 12:16] = (m_id * (90112 // columns_per_frame)).astype("<u4").view(np.uint8).reshape(-1, 4)
+    px = packets[:, :, 16:16 + 12 * rows].reshape(-1, rows, 12)
+    rng_mm = rng.randint(300, 120000, size=(n_packets * 16, rows)).astype("<u4")
+    rng_mm[rng.uniform(size=rng_mm.shape) < p_no_return] = 0
+    flags = rng.randint(0, 16, size=rng_mm.shape).astype("<u4") << 28  # the top bits of the range word are not range
+    px[:, :, 0:4] = (rng_mm | flags).view(np.uint8).reshape(-1, rows, 4)
+    px[:, :, 4:6] = rng.randint(0, 65536, size=rng_mm.shape).astype("<u2").view(np.uint8).reshape(-1, rows, 2)
+    px[:, :, 6:8] = rng.randint(0, 3000, size=rng_mm.shape).astype("<u2").view(np.uint8).reshape(-1, rows, 2)
+    px[:, :, 8:10] = rng.randint(0, 65536, size=rng_mm.shape).astype("<u2").view(np.uint8).reshape(-1, rows, 2)
+    status = np.where(rng.uniform(size=n_packets * 16) < p_invalid, 0, 0xFFFFFFFF).astype("<u4")
+    packets[:, :, 16 + 12 * rows:].reshape(-1, 4)[:] = status.view(np.uint8).reshape(-1, 4)
+    stamps = (2_000_000_000 + np.arange(n_packets, dtype=np.uint64) * np.uint64(1_562_500)).astype(np.uint64)
+    return np.ascontiguousarray(packets.reshape(n_packets, 16 * col_size)), stamps

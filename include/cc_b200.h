@@ -426,6 +426,55 @@ CC_API cc_status_t cc_kitti_frame(cc_kitti_t* k, int n_points, const float* xyzi
 CC_API cc_status_t cc_kitti_read_debug(cc_kitti_t* k, uint8_t* laser_index, int32_t* cell_point, float* uncorrected_xyz,
                                        cc_raw_point_t* firings);
 
+/* ---- sensor packets -> firings -----------------------------------------------------------
+ * OusterInput::onRawDataArrived (include/continuous_clustering/ros/ouster_input.hpp:105-181) for a batch of lidar UDP
+ * packets on the device: every VALID measurement block of every packet becomes one firing of pixels_per_column RawPoints
+ * (x, y, z from the sensor's lookup table, NaN for range 0; intensity = min(1, signal / 1000) * 255; firing_index counts
+ * the published firings; stamp = the packet's receive time), resident in device memory for cc_submit_firings_device.
+ * The packet layout is data: fill cc_ouster_format_t from ouster::sensor::packet_format (col_field offsets / masks of
+ * ChanField::RANGE and ChanField::SIGNAL) or use cc_ouster_format_legacy. The lookup tables are the caller's
+ * ouster::make_xyz_lut(info) cast to float and reordered column-major exactly like ouster_input.hpp:72-95:
+ * [columns_per_frame * pixels_per_column][3]. The ouster SDK is not part of the reference tree (dependencies.repos:10-13):
+ * parity for this row is pinned only to the restatement in oracle/cc_packets_oracle.cpp.
+ * VelodyneInput (velodyne_input.hpp:46-91) delegates the whole decode to velodyne_rawdata::RawData::unpack of a
+ * DataContainerBase variant that is neither in the reference tree nor published upstream (addPoint with a time argument +
+ * newLine): not restated, see DESIGN.md. */
+typedef struct cc_ouster_format
+{
+    int32_t columns_per_packet, pixels_per_column, columns_per_frame;
+    int32_t packet_header_size, col_header_size, col_footer_size, pixel_bytes;
+    int32_t col_measurement_id_offset; /* u16, from the start of the measurement block */
+    int32_t col_status_offset;         /* from the start of the measurement block; bit 0 = valid (:120-124) */
+    int32_t col_status_bytes;          /* 2 or 4 */
+    int32_t range_offset, range_bytes; /* within the pixel; value = (little-endian word & mask) >> shift */
+    uint32_t range_mask;               /* 0 = no mask */
+    int32_t range_shift;
+    int32_t signal_offset, signal_bytes;
+    uint32_t signal_mask;
+    int32_t signal_shift;
+    int32_t offset_from_direction_table; /* 1 = like ouster_input.hpp:134, which cuts the offset block out of lut_direction [sic] */
+} cc_ouster_format_t;
+typedef struct cc_decoded_firings
+{
+    int32_t n_firings;
+    int32_t rows_per_firing;
+    const cc_raw_point_t* d_firings; /* device: [n_firings][rows_per_firing] */
+    const uint64_t* firing_stamps;   /* host (page-locked): RawPoints::stamp of every firing (sensor_input.hpp:31) */
+    uint64_t first_firing_index;
+} cc_decoded_firings_t;
+typedef struct cc_ouster cc_ouster_t;
+CC_API void cc_ouster_format_legacy(int pixels_per_column, int columns_per_frame, cc_ouster_format_t* out);
+CC_API cc_status_t cc_ouster_create(int device_ordinal, const cc_ouster_format_t* format, int max_packets_per_call, cc_ouster_t** out);
+CC_API void cc_ouster_destroy(cc_ouster_t* o);
+CC_API int cc_ouster_packet_size(const cc_ouster_t* o);
+CC_API cc_status_t cc_ouster_set_lut(cc_ouster_t* o, const float* direction, const float* offset);
+/* SensorInput::reset + OusterInput::reset (sensor_input.hpp:15-19, ouster_input.hpp:97-101): firing index 0, the next
+ * packet is discarded. A new decoder starts in this state. */
+CC_API cc_status_t cc_ouster_reset(cc_ouster_t* o);
+CC_API cc_status_t cc_ouster_decode(cc_ouster_t* o, int n_packets, const uint8_t* packets, const uint64_t* receive_stamps,
+                                    cc_decoded_firings_t* out);
+CC_API cc_status_t cc_ouster_read_firings(cc_ouster_t* o, int n_firings, cc_raw_point_t* firings); /* tests */
+
 /* ---- device math self-test (used by tests: bit-equality with host libm) ---------------- */
 /* Evaluates the device re-implementations on n host inputs: out[i] = atan2f(a[i], b[i]) (op 0),
  * asinf(a[i]) (op 1). */
