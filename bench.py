@@ -717,9 +717,12 @@ def main():
     # FIRST device access to freshly page-locked pages runs at ~35 GB/s, every later one at ~50 GB/s (scripts/h2d_probe2.py).
     # One untimed copy of the whole buffer to a scratch tensor touches every page; the data of the timed pushes has still
     # never been in HBM or in the GPU's L2 when its push starts.
-    scratch = pin_pts.cuda()
-    torch.cuda.synchronize()
-    del scratch
+    # (scripts/h2d_vs_kernels.py: after ONE warming pass the next pass still runs at ~42 GB/s, from the third on at the
+    # link's 53-54 GB/s -- with or without pushes running beside it: three passes.)
+    for _ in range(3):
+        scratch = pin_pts.cuda()
+        torch.cuda.synchronize()
+        del scratch
     barrier()
     t0 = time.perf_counter()
     # two pushes in flight and a third one staged: the host->device copy of push k + 2 (input stream) overlaps the
@@ -779,7 +782,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": B * (rec_bytes + pose_bytes),
                     "d2h_bytes_per_step": int(d2h // K_e2e),
-                    "host_buffers": "page-locked, DMA-warm (one untimed device read of the staging memory before the timed region)",
+                    "host_buffers": "page-locked, DMA-warm (three untimed device reads of the staging memory before the timed region, as the reused staging buffers of a long-running producer are; every timed push still reads bytes that have never been in HBM or L2)",
                     "h2d_gbs_per_rank": e2e_value / world * (rec_bytes + pose_bytes) / 1e9,
                     "per_rank_columns_per_s": per_rank_e2e},
             "latency": {"per_push_device_ms_p50": float(np.median(dev_ms)),

@@ -340,6 +340,21 @@ int drv_configure(drv_t* d, const cc_config_t* cfg, int num_rows, const double* 
     return 0;
 }
 
+// setConfiguration without reset (cpp:66-81), as a caller may do mid-stream (node.cpp:234)
+int drv_set_config(drv_t* d, const cc_config_t* cfg)
+{
+    toConfiguration(*cfg, d->config);
+    d->cc.setConfiguration(d->config);
+    return 0;
+}
+
+// the reference does not count the associations it refuses: only the restatement (cc_oracle.cpp) reports them
+void drv_refusals(drv_t*, int64_t* joins, int64_t* links)
+{
+    *joins = -1;
+    *links = -1;
+}
+
 void drv_set_record(drv_t* d, int level)
 {
     d->record = level;

@@ -84,6 +84,8 @@ DRV_API void drv_destroy(drv_t* d);
 DRV_API const char* drv_last_error(drv_t* d);
 /* setConfiguration + reset(num_rows) + setTransformRobotFrameFromSensorFrame (skipped if NULL) */
 DRV_API int drv_configure(drv_t* d, const cc_config_t* cfg, int num_rows, const double* robot_from_sensor);
+DRV_API int drv_set_config(drv_t* d, const cc_config_t* cfg);
+DRV_API void drv_refusals(drv_t* d, int64_t* joins, int64_t* links);
 DRV_API void drv_set_record(drv_t* d, int level);
 /* addFiring for each of n firings; returns 0, or 1 if the object threw (message in drv_last_error) */
 DRV_API int drv_add_firings(drv_t* d, int n, int rows, const cc_raw_point_t* pts, const double* poses);

@@ -232,6 +232,8 @@ struct drv
         incl_gap.resize(R, NANF);
     }
 
+    int64_t refused_joins{0}, refused_links{0}; // test statistics: associations the reference refuses (cpp:654-659, 688-690)
+
     // setConfiguration cpp:66-81
     void set_config(const cc_config_t& c)
     {
@@ -677,6 +679,8 @@ struct drv
                                     root.finished_at = std::max(root.finished_at, p.cont_az + mad);
                                     root.tree_num_points++;
                                 }
+                                else
+                                    refused_joins++; // cpp:654-659
                             }
                             else
                             {
@@ -689,6 +693,8 @@ struct drv
                                     if (a != b)
                                         ring[b].link_parent = a;
                                 }
+                                else
+                                    refused_links++; // cpp:688-690
                             }
                         }
                     }
@@ -960,6 +966,20 @@ int drv_configure(drv_t* d, const cc_config_t* cfg, int num_rows, const double* 
         return 1;
     }
     return 0;
+}
+
+// setConfiguration without reset (cpp:66-81), as a caller may do mid-stream (node.cpp:234)
+int drv_set_config(drv_t* d, const cc_config_t* cfg)
+{
+    d->set_config(*cfg);
+    return 0;
+}
+
+// test statistics of the restatement only: refused joins / links so far (-1 in the builds of the reference itself)
+void drv_refusals(drv_t* d, int64_t* joins, int64_t* links)
+{
+    *joins = d->refused_joins;
+    *links = d->refused_links;
 }
 
 void drv_set_record(drv_t* d, int level)

@@ -266,6 +266,18 @@ class Driver:
             raise RuntimeError(self.error())
         self.rows = rows
 
+    def set_config(self, cfg: CcConfig):
+        """setConfiguration without reset (cpp:66-81)."""
+        self.lib.drv_set_config.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.drv_set_config(self.h, C.byref(cfg))
+
+    def refusals(self):
+        """(refused joins, refused links) counted by the restatement; (-1, -1) from the reference builds."""
+        self.lib.drv_refusals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.drv_refusals(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def set_record(self, level: int):
         self.lib.drv_set_record(self.h, level)
 

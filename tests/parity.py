@@ -19,11 +19,13 @@ PUBLISHED_TREE_FIELDS = ["tree_root_gcol", "tree_root_row", "finished_at_continu
                          "cluster_width", "num_child_points", "local_column_index", "row_index"]
 
 
-def record(driver, pts, poses, chunk=None):
-    """Feeds the stream and returns everything the driver recorded."""
+def record(driver, pts, poses, chunk=None, hooks=None):
+    """Feeds the stream and returns everything the driver recorded. hooks: {first firing of a chunk: callable(driver)}."""
     n = pts.shape[0]
     chunk = chunk or n
     for a in range(0, n, chunk):
+        if hooks and a in hooks:
+            hooks[a](driver)
         driver.add_firings(pts[a : a + chunk], poses[a : a + chunk])
     gcols, gcells = driver.ground_columns()
     ccols, ccells = driver.cluster_columns()

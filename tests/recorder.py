@@ -42,7 +42,7 @@ def child_counts(cc, lo, hi, max_steps_in_row=20):
     return cnt
 
 
-def record(cc, pts, poses, chunk, pipelined=False):
+def record(cc, pts, poses, chunk, pipelined=False, hooks=None):
     """Feeds the stream in pushes of `chunk` firings; returns the dict layout of tests/parity.record().
     pipelined=True uses the asynchronous API with two pushes in flight (submit(k + 1); wait(k)), pipelined=2 keeps a third
     push staged (submit(k + 2); wait(k))."""
@@ -62,6 +62,8 @@ def record(cc, pts, poses, chunk, pipelined=False):
                 cc.submitFirings(pts[b : b + chunk], poses[b : b + chunk])
             res = cc.wait()
         else:
+            if hooks and a in hooks:  # e.g. setConfiguration between two pushes (synchronous pushes only)
+                hooks[a](cc)
             res = cc.addFirings(pts[a : a + chunk], poses[a : a + chunk])
         used_exact += int(res.info.used_exact_path)
         slow_firings += int(res.info.slow_insert_firings)

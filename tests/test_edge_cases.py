@@ -1,0 +1,121 @@
+"""Edge cases of the hot path the reference handles with exceptions or refusals:
+  * the ring-overrun throw of performGroundPointSegmentationForColumn (cpp:318-344): a column that was never cleared is
+    reached again after ten rotations,
+  * associations the reference REFUSES on an organic (no closed wall) scene -- joining a finished tree (cpp:654-659),
+    linking finished trees (cpp:688-690): tall boxes right beside an OS-32 whose steep beams see them under a wide azimuth,
+  * setConfiguration between two firings of a running stream (cpp:66-81, node.cpp:234) without a reset.
+Each on the CPU emulation of the kernels and, marked gpu, on the device."""
+import numpy as np
+import pytest
+
+import parity
+import recorder
+from continuous_clustering_b200 import ClusteringError, synth
+from oracle import drvlib
+from test_emu_parity import make_cc
+
+ORGANIC = ("os32_left", dict(n_rotations=1.5, seed=2, min_box_dist=1.7, n_boxes=60, extent=8.0, box_height_range=(3.5, 6.0)))
+
+
+def overrun(library, oracle_lib):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=11.5)
+    cfg = drvlib.stream_config("tiny16", cluster_point_trees_every_nth_column=1 << 30)  # nothing is ever published or cleared
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg, sp.rows)
+    chunk, failed_at = 128, None
+    for a in range(0, pts.shape[0], chunk):
+        try:
+            d.add_firings(pts[a:a + chunk], poses[a:a + chunk])
+        except RuntimeError as e:
+            assert "This column is not cleared" in str(e)
+            failed_at = a
+            break
+    assert failed_at is not None and failed_at >= 9 * sp.num_columns
+    cc = make_cc(library, cfg, sp.rows)
+    for a in range(0, failed_at, chunk):
+        cc.addFirings(pts[a:a + chunk], poses[a:a + chunk])
+    with pytest.raises(ClusteringError, match="This column is not cleared"):
+        cc.addFirings(pts[failed_at:failed_at + chunk], poses[failed_at:failed_at + chunk])
+    cc.reset(sp.rows)  # the handle is usable again after a reset
+    cc.setTransformRobotFrameFromSensorFrame([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0])
+    assert cc.addFirings(pts[:chunk], poses[:chunk]).info.n_events >= 0
+
+
+def organic_refusals(library, oracle_lib, chunk):
+    spec, kw = ORGANIC
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec)
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg, sp.rows)
+    want = parity.record(d, pts, poses)
+    joins, links = d.refusals()
+    assert joins > 0 and links > 0, "the scene must make the restatement refuse joins and links"
+    cc = make_cc(library, cfg, sp.rows)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="product", check_tree_fields=True, check_published_tree_fields=True)
+    return got
+
+
+def config_mid_stream(library, oracle_lib, chunk=100):
+    pts, poses, sp = synth.make_stream("tiny16", n_rotations=3.0, moving=True, dropout=0.05)
+    cfg_a = drvlib.stream_config("tiny16")
+    cfg_b = drvlib.stream_config("tiny16", max_distance=0.4, max_slope=0.1, cluster_point_trees_every_nth_column=2,
+                                 ignore_points_in_chessboard_pattern=0)
+    cfg_c = drvlib.stream_config("tiny16", max_steps_in_row=5, use_last_point_for_cluster_stamp=1)
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg_a, sp.rows)
+    want = parity.record(d, pts, poses, chunk, hooks={300: lambda x: x.set_config(cfg_b), 600: lambda x: x.set_config(cfg_c)})
+    assert not d.reset_required()
+    cc = make_cc(library, cfg_a, sp.rows)
+    got = recorder.record(cc, pts, poses, chunk, hooks={300: lambda x: x.setConfiguration(cfg_b), 600: lambda x: x.setConfiguration(cfg_c)})
+    parity.compare(want, got, name_a="oracle", name_b="product")
+    plain = parity.record(_fresh(oracle_lib, cfg_a, sp.rows), pts, poses, chunk)
+    assert not np.array_equal(plain["cluster_cells"]["id"], want["cluster_cells"]["id"]), "the configuration change must matter"
+
+
+def _fresh(oracle_lib, cfg, rows):
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg, rows)
+    return d
+
+
+def test_ring_overrun_throws_emulation(emu_library, oracle_lib):
+    overrun(emu_library, oracle_lib)
+
+
+def test_organic_refusals_emulation(emu_library, oracle_lib):
+    organic_refusals(emu_library, oracle_lib, 256)
+
+
+def test_set_configuration_mid_stream_emulation(emu_library, oracle_lib):
+    config_mid_stream(emu_library, oracle_lib)
+
+
+def test_reference_build_agrees_on_the_organic_scene(oracle_lib):
+    """The restatement's refusals are the reference's: same recording from the reference build on the same scene."""
+    import os
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcc_ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/libcc_ref.so not built (needs /root/reference at build time)")
+    spec, kw = ORGANIC
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec)
+    parity.compare(parity.record(_fresh(ref, cfg, sp.rows), pts, poses), parity.record(_fresh(oracle_lib, cfg, sp.rows), pts, poses),
+                   name_a="reference", name_b="oracle")
+
+
+@pytest.mark.gpu
+def test_ring_overrun_throws_cuda(cuda_library, oracle_lib):
+    overrun(None, oracle_lib)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", [64, 1024])
+def test_organic_refusals_cuda(cuda_library, oracle_lib, chunk):
+    organic_refusals(None, oracle_lib, chunk)
+
+
+@pytest.mark.gpu
+def test_set_configuration_mid_stream_cuda(cuda_library, oracle_lib):
+    config_mid_stream(None, oracle_lib)
