@@ -100,6 +100,18 @@ class ClusteringError(RuntimeError):
         self.status = status
 
 
+class _EmptyViews(dict):
+    def __missing__(self, key):
+        for dt in (_lib.EVENT_DTYPE, _lib.CLUSTER_DTYPE, _lib.CLUSTER_POINT_DTYPE):
+            if (dt.itemsize, dt.names) == key:
+                self[key] = np.zeros(0, dtype=dt)
+                return self[key]
+        raise KeyError(key)
+
+
+_EMPTY = _EmptyViews()
+
+
 @dataclasses.dataclass
 class BatchResult:
     """Results of one push. The arrays are zero-copy views of the handle's buffers: valid until the next push on the
@@ -218,11 +230,18 @@ class ContinuousClustering:
 
     def addFirings(self, points: np.ndarray, poses: np.ndarray) -> BatchResult:
         """A batch of consecutive firings: points[n, num_rows] (RAW_POINT_DTYPE), poses[n, 12]."""
-        points = np.ascontiguousarray(points, dtype=RAW_POINT_DTYPE)
-        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        if not (points.flags.c_contiguous and points.dtype == RAW_POINT_DTYPE):
+            points = np.ascontiguousarray(points, dtype=RAW_POINT_DTYPE)
+        if not (poses.flags.c_contiguous and poses.dtype == np.float64):
+            poses = np.ascontiguousarray(poses, dtype=np.float64)
         n, rows = points.shape
         out = None
         step = max(1, int(self._L.cc_max_firings_per_push(self._h)))
+        if n <= step:  # the common case: one push
+            self._check(self._L.cc_push_firings(self._h, n, rows, points.ctypes.data, poses.ctypes.data))
+            out = self._collect()
+            self._dispatch(out)
+            return out
         for a in range(0, max(n, 1), step):  # larger batches are pushed piecewise; the LAST piece's result is returned
             b = min(n, a + step)
             self._check(self._L.cc_push_firings(self._h, b - a, rows, points[a:b].ctypes.data, poses[a:b].ctypes.data))
@@ -272,11 +291,20 @@ class ContinuousClustering:
         pe, pc, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._L.cc_get_result_views(self._h, C.byref(pe), C.byref(pc), C.byref(pp))
 
+        cache = self.__dict__.setdefault("_views", {})
+
         def view(ptr, n, dtype):
+            # the handle hands out a few long-lived buffers (three slots): one numpy view per buffer, sliced per push
             if n == 0 or not ptr.value:
-                return np.zeros(0, dtype=dtype)
-            buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
-            return np.frombuffer(buf, dtype=dtype, count=n)
+                return _EMPTY[dtype.itemsize, dtype.names]
+            ent = cache.get((ptr.value, dtype.itemsize))
+            if ent is None or ent.shape[0] < n:
+                cap = max(n, 1024)
+                buf = (C.c_char * (cap * dtype.itemsize)).from_address(ptr.value)
+                ent = cache[(ptr.value, dtype.itemsize)] = np.frombuffer(buf, dtype=dtype, count=cap)
+                if len(cache) > 64:
+                    cache.clear()
+            return ent[:n]
 
         self.last = BatchResult(info, view(pe, info.n_events, _lib.EVENT_DTYPE), view(pc, info.n_clusters, _lib.CLUSTER_DTYPE),
                                 view(pp, info.n_cluster_points, _lib.CLUSTER_POINT_DTYPE))

@@ -998,7 +998,7 @@ static cc_status_t device_error_to_status(cc_handle* h)
 
 // finish passes for columns [ci0, ci1] (ci1 < 0: all new columns); `last` also closes the push (k_push_done)
 static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, int exact, int last,
-                          CcDevState* snap = nullptr)
+                          CcDevState* snap = nullptr, int careful_ci = -1)
 {
     const unsigned int seq = ++h->seq;
 #ifdef CC_EMU
@@ -1049,12 +1049,16 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
         h->launches++;
     }
     else
-        CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap);
+        CC_RUN(h, k_fin_all, 1, fin_threads, fin_smem, cfg, h->d, ci0, ci1, seq, guard, exact, last, static_cast<int>(fin_smem), snap,
+               careful_ci);
     CC_RUN(h, k_fin_label, h->sm_count * 8, 256, 0, cfg, h->d, seq, guard, clustered ? 1 : 0);
     // number_of_visited_neighbors of the few points whose walk went beyond the first unpublished column (exact counts)
     // (a small grid: the list is empty or short; a warp redoes one point in a few microseconds)
+    // (not after the exact pass of a single column: k_careful's walk honours the stop itself, nothing is listed)
+    if (exact)
+        return;
     static const int vfix_grid = std::getenv("CC_B200_VFIX_GRID") ? std::max(1, std::atoi(std::getenv("CC_B200_VFIX_GRID"))) : 32;
-    CC_RUN(h, k_visited_fix, vfix_grid, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard);
+    CC_RUN(h, k_visited_fix, vfix_grid, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard, snap);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)
@@ -1086,9 +1090,10 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
     {
         if (careful[ci])
         {
-            CC_RUN(h, k_careful, 1, 1, 0, cfg, h->d, ci);
             if ((colbase + ci) % cfg.nth == 0)
-                launch_finish(h, cfg, ci, ci, 0, 1, 0);
+                launch_finish(h, cfg, ci, ci, 0, 1, 0, nullptr, ci); // k_careful's work at the head of the finish pass
+            else
+                CC_RUN(h, k_careful, 1, 1, 0, cfg, h->d, ci);
             ci++;
             continue;
         }

@@ -3631,12 +3631,8 @@ __global__ void k_commit_links(CcDevCfg cfg, CcDevPtrs p, const unsigned int* s_
 //      associations and the stop at the first unpublished column). One thread; used only for columns the probe
 //      flagged and while a cluster is about to span a full rotation.
 // =====================================================================================================
-__global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
+CC_DEV void d_careful(const CcDevCfg& cfg, const CcDevPtrs& p, int ci) // one thread
 {
-    CC_PDL_ENTER();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_careful, static_cast<int>(blockIdx.x));
-    if (blockIdx.x != 0 || threadIdx.x != 0)
-        return;
     const int R = cfg.R;
     CcDevState* st = p.st;
     const long long gcol = st->colbase + ci;
@@ -3745,6 +3741,14 @@ __global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
                 st->error = CC_DEV_LIST_OVERFLOW;
         }
     }
+}
+__global__ void k_careful(CcDevCfg cfg, CcDevPtrs p, int ci)
+{
+    CC_PDL_ENTER();
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_careful, static_cast<int>(blockIdx.x));
+    if (blockIdx.x != 0 || threadIdx.x != 0)
+        return;
+    d_careful(cfg, p, ci);
 }
 
 // =====================================================================================================
@@ -4293,7 +4297,7 @@ CC_DEV void d_state_snapshot(const CcDevPtrs& p, CcDevState* dst)
 // CTA with block-wide barriers between the phases is faster than six dependent launches). The fused kernel runs the
 // same phases over all CTAs of its cluster with cluster barriers in between.
 __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int ci0, int ci1, unsigned int seq, int guard,
-                                                  int exact, int last, int smem_bytes, CcDevState* snap)
+                                                  int exact, int last, int smem_bytes, CcDevState* snap, int careful_ci)
 {
     CC_PDL_ENTER();
     const CcGrid g = cc_grid();
@@ -4305,6 +4309,15 @@ __global__ void __launch_bounds__(1024) k_fin_all(CcDevCfg cfg, CcDevPtrs p, int
         if (snap)
             d_state_snapshot(p, snap);
         return;
+    }
+    if (careful_ci >= 0) // split path: the exact association of the column (K3c) shares the launch with its finish pass
+    {
+        if (threadIdx.x == 0)
+        {
+            CcTraceScope cc_tr_c(p.trace, CC_KID_careful, g.bid);
+            d_careful(cfg, p, careful_ci);
+        }
+        __syncthreads();
     }
     CC_SMEM(smem);
     // shared memory: [block-scan scratch: T x 8 B][running maximum of the segment's columns | prefix maxima of G]
@@ -4604,11 +4617,13 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
     d_fin_label<false>(cc_grid(), cfg, p, seq, spec, nullptr, 0, via_rep != 0);
 }
 
-__global__ void __launch_bounds__(256) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec)
+__global__ void __launch_bounds__(256) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec, CcDevState* snap)
 {
     CC_PDL_ENTER();
     const CcGrid g = cc_grid();
     CcTraceScope cc_trace_scope(p.trace, CC_KID_visited_fix, g.bid);
+    if (snap && g.bid == 0 && threadIdx.x == 0)
+        snap->n_vfix = p.st->n_vfix; // the list was filled after the finish pass copied the state
     CC_SMEM(smem);
     d_visited_fix(g, cfg, p, spec, reinterpret_cast<float4*>(smem), true);
 }
