@@ -329,6 +329,27 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------- facade harness
+def cabi_e2e(cfg_c, rows, pts, poses, batch, warm, steps, device, label_prefetch=True):
+    """build/libcc_cabi_bench.so (facade/tools/cabi_bench.cpp): the C ABI driven by a C++ caller -- W synchronous warm-up
+    pushes, then `steps` timed pushes with submit(k + 2); wait(k) over the given page-locked host buffers, results read on
+    the host after every wait. Returns None when the harness has not been built."""
+    path = os.path.join(HERE, "build", "libcc_cabi_bench.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.cb_e2e.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                           C.c_void_p, C.c_void_p, C.c_char_p]
+    out = np.zeros(4, dtype=np.float64)
+    marks = np.zeros(max(steps, 1), dtype=np.float64)
+    err = C.create_string_buffer(256)
+    tf = np.asarray(IDENTITY, dtype=np.float64)
+    rc = lib.cb_e2e(C.addressof(cfg_c), rows, tf.ctypes.data, device, batch, warm, steps, pts.ctypes.data, poses.ctypes.data,
+                    int(label_prefetch), out.ctypes.data, marks.ctypes.data, err)
+    if rc != 0:
+        raise RuntimeError("cabi_bench: " + err.value.decode(errors="replace"))
+    return {"seconds": float(out[0]), "d2h_bytes_per_step": float(out[1]), "exact_pushes": int(out[3]), "marks_ms": marks[:steps].tolist()}
+
+
 def facade_run(cfg_c, sp, pts, poses, batch, pipelined, callback_mode, warm, device, want_calls=False):
     """build/libcc_facade_bench.so (facade/tools/facade_bench.cpp): the stream through the drop-in C++ class, one
     addFiring call per firing."""
@@ -507,6 +528,81 @@ def main():
     value, elapsed, dev_ms, launches, exact_pushes, clocks, t_wall = (leg["value"], leg["elapsed"], leg["dev_ms"], leg["launches"],
                                                                       leg["exact"], leg["clocks"], leg["t_wall"])
     total = leg["fed"]
+
+    # ------------------------------------------------------------------ end-to-end leg through the public API
+    # (runs right after the device-resident leg, before the other operating points: it is the headline and should not
+    # depend on what the optional legs leave behind in the process)
+    cce = new_handle()
+    cce.set_label_prefetch(True)  # the ground labels of the new columns come back with every push's results
+    K_e2e = min(K, 2) if args.quick else K
+    h_pts, h_poses = stream.take(0, (W + K_e2e) * B)
+    # page-locked host buffers (the contract's "pinned host memory"): cc_submit_firings copies them straight to the device
+    pin_pts, pin_poses, h_pts, h_poses = pinned(h_pts, h_poses)
+    d2h = 0
+    for s in range(W):
+        cce.addFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
+    # (scripts/h2d_probe4.py: only the very first device access to freshly page-locked pages is slow, ~20 GB/s; CPU rewrites
+    # of the buffer do not make it slow again.)
+    # The page-locked staging memory is "DMA warm", as that of any long-running producer is: on this pool's hosts the
+    # FIRST device access to freshly page-locked pages runs at ~35 GB/s, every later one at ~50 GB/s (scripts/h2d_probe2.py).
+    # One untimed copy of the whole buffer to a scratch tensor touches every page; the data of the timed pushes has still
+    # never been in HBM or in the GPU's L2 when its push starts.
+    # (scripts/h2d_vs_kernels.py: after ONE warming pass the next pass still runs at ~42 GB/s, from the third on at the
+    # link's 53-54 GB/s -- with or without pushes running beside it: three passes.)
+    for _ in range(3):
+        scratch = pin_pts.cuda()
+        torch.cuda.synchronize()
+        del scratch
+    barrier()
+    e2e_marks = []
+    t0 = time.perf_counter()
+    # two pushes in flight and a third one staged: the host->device copy of push k + 2 (input stream) overlaps the
+    # kernels of pushes k and k + 1; its kernels are launched by the wait() that returns push k
+    for s in range(W, min(W + 2, W + K_e2e)):
+        cce.submitFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
+    for s in range(W, W + K_e2e):
+        if s + 2 < W + K_e2e:
+            cce.submitFirings(h_pts[(s + 2) * B:(s + 3) * B], h_poses[(s + 2) * B:(s + 3) * B])
+        res = cce.wait()
+        e2e_marks.append(time.perf_counter() - t0)
+        labels = cce.column_labels()  # [n_cols, rows, 4] u8: ground label, debug label, is_ignored, intensity
+        assert labels.shape[0] == int(res.info.ground_to_gcol - res.info.ground_from_gcol)
+        d2h += res.clusters.nbytes + res.cluster_points.nbytes + labels.nbytes + labels.shape[0] * 8 + 512
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_rank = K_e2e * B / e2e_s
+    per_rank_e2e = None
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, e2e_rank)
+        per_rank_e2e = gathered
+    e2e_python = world * K_e2e * B / e2e_s
+    cce.close()
+    # The same loop written by a C++ caller of the C ABI (facade/tools/cabi_bench.cpp), same page-locked buffers: no
+    # interpreter between the calls. This is the reported end-to-end number; the Python loop above is kept beside it
+    # (its wait() returns are 10-20 % further apart on this host: interpreter jitter between submit and wait).
+    e2e_c = None
+    try:
+        barrier()
+        e2e_c = cabi_e2e(cfg.to_c(), R, h_pts, h_poses, B, W, K_e2e, local_rank)
+    except Exception as e:
+        print(f"cabi e2e leg failed: {e}", file=sys.stderr)
+    e2e_value, e2e_how, e2e_marks_c = e2e_python, "python loop (ContinuousClustering.submitFirings / wait)", None
+    if e2e_c is not None:
+        c_s = e2e_c["seconds"]
+        if dist is not None:
+            t = torch.tensor([c_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, K_e2e * B / c_s)
+            per_rank_e2e = gathered
+            c_s = float(t.item())
+        e2e_value = world * K_e2e * B / c_s
+        e2e_how = "C++ caller of the C ABI (cc_submit_firings / cc_wait, build/libcc_cabi_bench.so)"
+        e2e_marks_c = [round(m, 3) for m in e2e_c["marks_ms"]]
 
     # per-push latency with ONE push of B firings in flight (the synchronous call), device-resident inputs
     sync_ms = []
@@ -702,54 +798,6 @@ def main():
         except Exception as e:
             facade = {"error": str(e)[:200]}
 
-    # ------------------------------------------------------------------ end-to-end leg through the public API
-    cc = new_handle()
-    cc.set_label_prefetch(True)  # the ground labels of the new columns come back with every push's results
-    K_e2e = min(K, 2) if args.quick else K
-    total = (W + K_e2e) * B
-    h_pts, h_poses = stream.take(0, total)
-    # page-locked host buffers (the contract's "pinned host memory"): cc_submit_firings copies them straight to the device
-    pin_pts, pin_poses, h_pts, h_poses = pinned(h_pts, h_poses)
-    d2h = 0
-    for s in range(W):
-        cc.addFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
-    # The page-locked staging memory is "DMA warm", as that of any long-running producer is: on this pool's hosts the
-    # FIRST device access to freshly page-locked pages runs at ~35 GB/s, every later one at ~50 GB/s (scripts/h2d_probe2.py).
-    # One untimed copy of the whole buffer to a scratch tensor touches every page; the data of the timed pushes has still
-    # never been in HBM or in the GPU's L2 when its push starts.
-    # (scripts/h2d_vs_kernels.py: after ONE warming pass the next pass still runs at ~42 GB/s, from the third on at the
-    # link's 53-54 GB/s -- with or without pushes running beside it: three passes.)
-    for _ in range(3):
-        scratch = pin_pts.cuda()
-        torch.cuda.synchronize()
-        del scratch
-    barrier()
-    t0 = time.perf_counter()
-    # two pushes in flight and a third one staged: the host->device copy of push k + 2 (input stream) overlaps the
-    # kernels of pushes k and k + 1; its kernels are launched by the wait() that returns push k
-    for s in range(W, min(W + 2, W + K_e2e)):
-        cc.submitFirings(h_pts[s * B:(s + 1) * B], h_poses[s * B:(s + 1) * B])
-    for s in range(W, W + K_e2e):
-        if s + 2 < W + K_e2e:
-            cc.submitFirings(h_pts[(s + 2) * B:(s + 3) * B], h_poses[(s + 2) * B:(s + 3) * B])
-        res = cc.wait()
-        labels = cc.column_labels()  # [n_cols, rows, 4] u8: ground label, debug label, is_ignored, intensity
-        assert labels.shape[0] == int(res.info.ground_to_gcol - res.info.ground_from_gcol)
-        d2h += res.clusters.nbytes + res.cluster_points.nbytes + labels.nbytes + labels.shape[0] * 8 + 512
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_rank = K_e2e * B / e2e_s
-    per_rank_e2e = None
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        gathered = [None] * world
-        dist.all_gather_object(gathered, e2e_rank)
-        per_rank_e2e = gathered
-    e2e_value = world * K_e2e * B / e2e_s
-    cc.close()
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_stream = stream if not args.moving else Stream(spec_name, 1234)
@@ -783,7 +831,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": B * (rec_bytes + pose_bytes),
                     "d2h_bytes_per_step": int(d2h // K_e2e),
                     "host_buffers": "page-locked, DMA-warm (three untimed device reads of the staging memory before the timed region, as the reused staging buffers of a long-running producer are; every timed push still reads bytes that have never been in HBM or L2)",
-                    "h2d_gbs_per_rank": e2e_value / world * (rec_bytes + pose_bytes) / 1e9,
+                    "caller": e2e_how, "wait_return_ms": e2e_marks_c, "python_loop": {"value": e2e_python, "wait_return_ms": [round(1e3 * m, 3) for m in e2e_marks]}, "h2d_gbs_per_rank": e2e_value / world * (rec_bytes + pose_bytes) / 1e9,
                     "per_rank_columns_per_s": per_rank_e2e},
             "latency": {"per_push_device_ms_p50": float(np.median(dev_ms)),
                         "per_push_sync_call_ms_p50": float(np.median(sync_ms)),

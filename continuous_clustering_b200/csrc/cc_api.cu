@@ -841,6 +841,35 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
             CC_CHECK(h, cudaMallocHost(&ib.h_raw, stage * sizeof(cc_raw_point_t)));
             CC_CHECK(h, cudaMallocHost(reinterpret_cast<void**>(&ib.h_poses), static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
         }
+        // The first DMA access to freshly page-locked pages runs at a third of the link rate on some hosts (measured:
+        // ~20 GB/s against ~54 GB/s from the second access on, scripts/h2d_probe4.py): touch every page-locked buffer of
+        // the handle once in both directions now, so that the first pushes do not pay for it on their critical path.
+        {
+            void* scratch = h->inbuf[0].d_raw;
+            const size_t scratch_bytes = stage * sizeof(cc_raw_point_t);
+            auto warm = [&](void* hp, size_t bytes) -> cudaError_t
+            {
+                bytes = std::min(bytes, scratch_bytes);
+                cudaError_t e = cudaMemcpyAsync(hp, scratch, bytes, cudaMemcpyDeviceToHost, h->stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(scratch, hp, bytes, cudaMemcpyHostToDevice, h->stream);
+                return e;
+            };
+            for (cc_handle::Slot& sl : h->slots)
+            {
+                CC_CHECK(h, warm(sl.h_first_unpub, mc * sizeof(long long)));
+                CC_CHECK(h, warm(sl.h_clusters, CC_PREFETCH_CLUSTERS * sizeof(CcCluster)));
+            }
+            for (uchar4* q : h->h_label_ring)
+                CC_CHECK(h, warm(q, mc * h->R * sizeof(uchar4)));
+            for (CcClusterPoint* q : h->h_points_ring)
+                CC_CHECK(h, warm(q, static_cast<size_t>(h->prefetch_points) * sizeof(CcClusterPoint)));
+            for (cc_handle::InBuf& ib : h->inbuf)
+            {
+                CC_CHECK(h, warm(ib.h_raw, stage * sizeof(cc_raw_point_t)));
+                CC_CHECK(h, warm(ib.h_poses, static_cast<size_t>(h->max_firings) * 12 * sizeof(double)));
+            }
+        }
         d.raw = h->inbuf[0].d_raw;
         d.poses = h->inbuf[0].d_poses;
         d.col_first_unpub = h->slots[0].d_first_unpub;

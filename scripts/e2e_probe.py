@@ -15,6 +15,9 @@ n = 24
 pts, poses = bench.tile_stream(base_pts, base_poses, sp, 0, n * B)
 pp = torch.from_numpy(pts.view(np.uint8).reshape(n * B, R * 48)).pin_memory(); pq = torch.from_numpy(poses).pin_memory()
 hp = pp.numpy().view(pts.dtype).reshape(n * B, R); hq = pq.numpy()
+if os.environ.get('E2E_WARM'):
+    for _ in range(3):
+        _w = pp.cuda(); torch.cuda.synchronize(); del _w
 for rep in range(3):
     cc.reset(R); cc.setTransformRobotFrameFromSensorFrame(bench.IDENTITY)
     for s in range(3):

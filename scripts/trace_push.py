@@ -8,7 +8,11 @@ from continuous_clustering_b200.presets import stream_configuration
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 FLUSH = (sys.argv[2] != '0') if len(sys.argv) > 2 else True
+WALL = len(sys.argv) > 3 and sys.argv[3] == "wall"  # closed wall around the sensor: the split / exact path
 base_pts, base_poses, sp = bench.make_rotations()
+if WALL:
+    from continuous_clustering_b200 import synth
+    base_pts, base_poses, sp = synth.make_stream(bench.SPEC, n_rotations=2.0, seed=3, n_boxes=0, wall_radius=12.0)
 cfg = stream_configuration(bench.SPEC)
 R = sp.rows
 cc = ContinuousClustering(device=0, max_firings_per_push=max(B, 256))
