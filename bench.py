@@ -338,15 +338,20 @@ def cabi_e2e(cfg_c, rows, pts, poses, batch, warm, steps, device, label_prefetch
         return None
     lib = C.CDLL(path)
     lib.cb_e2e.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                           C.c_void_p, C.c_void_p, C.c_char_p]
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
     out = np.zeros(4, dtype=np.float64)
     marks = np.zeros(max(steps, 1), dtype=np.float64)
+    slots = np.full((max(steps, 1), 5), -1.0, dtype=np.float32) if os.environ.get("CC_BENCH_SLOT_TIMES") else None
     err = C.create_string_buffer(256)
     tf = np.asarray(IDENTITY, dtype=np.float64)
     rc = lib.cb_e2e(C.addressof(cfg_c), rows, tf.ctypes.data, device, batch, warm, steps, pts.ctypes.data, poses.ctypes.data,
-                    int(label_prefetch), out.ctypes.data, marks.ctypes.data, err)
+                    int(label_prefetch), out.ctypes.data, marks.ctypes.data, slots.ctypes.data if slots is not None else None, err)
     if rc != 0:
         raise RuntimeError("cabi_bench: " + err.value.decode(errors="replace"))
+    if slots is not None:
+        for i in range(min(steps, 6)):
+            print(f"e2e push {i}: wait returned {marks[i]:.3f} | h2d {slots[i][0]:.3f}->{slots[i][1]:.3f} kernels {slots[i][2]:.3f}->{slots[i][3]:.3f} "
+                  f"results {slots[i][4]:.3f}", file=sys.stderr)
     return {"seconds": float(out[0]), "d2h_bytes_per_step": float(out[1]), "exact_pushes": int(out[3]), "marks_ms": marks[:steps].tolist()}
 
 
@@ -385,6 +390,7 @@ def main():
     ap.add_argument("--moving", action="store_true", help="moving sensor (10 m/s, 0.2 rad/s yaw) instead of the static pose")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident leg + kernel tables only (profiling runs)")
+    ap.add_argument("--quick-e2e", action="store_true", help="device-resident and end-to-end legs only (A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -418,7 +424,7 @@ def main():
     R = sp.rows
     B = min(B, 3 * sp.num_columns)  # the ring keeps 10 rotations: a push may span at most 3
     rec_bytes, pose_bytes = R * 48, 12 * 8
-    full = rank == 0 and world == 1 and not args.quick and not args.moving
+    full = rank == 0 and world == 1 and not args.quick and not args.moving and not args.quick_e2e
 
     def new_handle(batch=None):
         cc = ContinuousClustering(device=local_rank, max_firings_per_push=max(batch or B, 256))
@@ -722,7 +728,7 @@ def main():
 
     latency_mode = None
     per_gpu_latency = None
-    if not args.quick:
+    if not args.quick and not args.quick_e2e:
         barrier()
         mine = latency_leg()
         if dist is not None:

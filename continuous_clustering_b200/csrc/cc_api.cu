@@ -49,12 +49,13 @@ struct cc_handle
     int debug_flag_period{0};
     unsigned long long* d_trace{nullptr}; // device-side timeline buffer (cc_debug_trace)
     bool trace_on{false};
-    int tune{0}; // profiling aid: CC_B200_TUNE environment variable (bit 0: cooperative probe walk without masks)
+    int tune{0}; // profiling aid: CC_B200_TUNE environment variable (bit 0: cooperative probe walk without masks; bit 2: tiled probe)
     bool label_prefetch{false};
     const uchar4* cur_labels{nullptr}; // labels of the last finished push (pinned slot buffer)
     int cur_label_cols{0};
     int used_exact_flag{0};
     size_t probe_smem{0}; // [block-scan scratch][running maxima of up to maxcols columns]
+    size_t tile_smem_set{0};
     size_t ground_smem_set{0};
     size_t lite_smem_set{0};
     size_t fin_smem_set{0};
@@ -1165,6 +1166,26 @@ static cc_status_t enqueue_results(cc_handle* h, cc_handle::Slot& sl, bool state
     sl.pre_clusters = std::min(h->d.cap_clusters, CC_PREFETCH_CLUSTERS);
     // member lists: what a push of this size typically finishes, not the whole capacity
     sl.pre_points = std::min(std::min(h->d.cap_cluster_points, h->prefetch_points), std::max(16384, sl.n * h->R / 4));
+    static const bool results_by_copy_engine = std::getenv("CC_B200_RESULT_COPIES") != nullptr; // A/B aid: the five transfers
+    if (!results_by_copy_engine)
+    {
+        CcResultDst dst;
+        dst.h_state = sl.h_state;
+        dst.h_first_unpub = sl.h_first_unpub;
+        dst.h_clusters = reinterpret_cast<CcCluster*>(sl.h_clusters);
+        dst.h_points = reinterpret_cast<CcClusterPoint*>(sl.h_points);
+        dst.h_labels = h->label_prefetch && sl.has_tf ? sl.h_labels : nullptr;
+        dst.cap_cols = sl.pre_cols;
+        dst.cap_clusters = sl.pre_clusters;
+        dst.cap_points = sl.pre_points;
+        dst.rows = h->R;
+        static const int export_grid = std::getenv("CC_B200_EXPORT_GRID") ? std::max(1, std::atoi(std::getenv("CC_B200_EXPORT_GRID"))) : 16;
+        CC_LAUNCH(k_results_to_host, export_grid, 512, 0, h->copy_stream, sl.d_state_snap, sl.d_first_unpub, sl.d_clusters, sl.d_points,
+                  sl.d_labels, dst);
+        h->launches++;
+        CC_CHECK(h, cudaEventRecord(sl.done, h->copy_stream));
+        return CC_OK;
+    }
     CC_CHECK(h, cudaMemcpyAsync(sl.h_state, sl.d_state_snap, sizeof(CcDevState), cudaMemcpyDeviceToHost, h->copy_stream));
     CC_CHECK(h, cudaMemcpyAsync(sl.h_first_unpub, sl.d_first_unpub, sl.pre_cols * sizeof(long long),
                                 cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1308,7 +1329,28 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
         CC_RUN(h, k_ground, h->sm_count * 8, gw * CC_WARP, ground_smem, cfg, h->d, h->d_s_parent);
         // one resident wave each (the blocks loop over the work lists): a second wave would only repeat the prologue
         // (every CTA first computes the running maximum of the column minima in shared memory)
-        CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, h->probe_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
+        // The list-driven thread-per-point probe (global loads, 8 lanes per warp) is the default: measured against the tiled
+        // probe with its field of view staged in shared memory by bulk asynchronous copies (CC_B200_TUNE bit 2), it is the
+        // faster one at 4096 firings per push (13.9 + 13.5 us with k_probe_heavy against 18.4 + 12.5 us, profiles/r02_probe_ab.md):
+        // a tile's time is its latency chain -- column-minimum reduction, copy landing, walk -- over two resident waves.
+        if (!(h->tune & 4))
+            CC_RUN(h, k_probe, h->sm_count * h->occ_probe, 256, h->probe_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
+        else
+        {
+            // tiles of 256 / R columns, their field of view staged in shared memory by a bulk asynchronous copy; + 1 CTA
+            // that publishes the running maxima
+            const size_t tile_smem = cc_tile_smem_bytes(R, cfg.max_steps_row);
+#ifndef CC_EMU
+            if (tile_smem > 48 * 1024 && tile_smem > h->tile_smem_set)
+            {
+                CC_CHECK(h, cudaFuncSetAttribute(k_probe_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
+                h->tile_smem_set = tile_smem;
+            }
+#endif
+            const int tiles = (std::min(h->maxcols, n + 64) + cc_tile_cols(R) - 1) / cc_tile_cols(R);
+            const int workers = std::max(1, std::min(tiles, h->sm_count * 8));
+            CC_RUN(h, k_probe_tile, workers + 1, CC_TILE_CELLS, tile_smem, cfg, h->d, h->d_s_parent, h->d_s_links, sl.spec ? 1 : 0);
+        }
         CC_RUN(h, k_probe_heavy, h->sm_count * h->occ_probe_heavy, 64, cc_heavy_smem_bytes(64, 2), cfg, h->d,
                h->d_s_parent, h->d_s_links, h->tune);
         if (sl.spec)

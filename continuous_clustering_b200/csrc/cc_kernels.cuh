@@ -3011,6 +3011,313 @@ __global__ void __launch_bounds__(256) k_probe(CcDevCfg cfg, CcDevPtrs p, unsign
     d_probe(cc_grid(), cfg, p, s_parent, s_links, do_snapshot);
 }
 
+// K3a (tiled): the same walk, one thread per CELL of a tile of consecutive new columns, with the tile's whole field of
+// view -- the tile's columns and the max_steps_in_row columns before them, one contiguous span of `assoc` in the ring
+// (two where the ring wraps) -- staged in shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier): the
+// dependent loads of a walk then cost a shared-memory access instead of an L2 round trip, all 32 lanes of a warp walk
+// (they are neighbouring rows of one column: similar walks), and the budget before a point is handed to the
+// cooperative walk is CC_TILE_BUDGET cells instead of CC_PROBE_BUDGET. While the copy is in flight the CTA reduces the
+// column minima before its tile (the validator's running maximum). One extra CTA leaves the running maxima of all
+// columns in col_runmax for the kernels after this one. Results are those of d_probe, cell for cell.
+#define CC_TILE_CELLS 256 /* cells (threads) per tile: 256 / R columns */
+#define CC_TILE_BUDGET 16
+static inline __host__ __device__ int cc_tile_cols(int R)
+{
+    return CC_TILE_CELLS / R > 0 ? CC_TILE_CELLS / R : 1;
+}
+static inline __host__ __device__ size_t cc_tile_smem_bytes(int R, int max_steps_row)
+{
+    return static_cast<size_t>(cc_tile_cols(R) + max_steps_row) * R * (sizeof(float4) + sizeof(double) + sizeof(float)) +
+           (32 + 64) * sizeof(double) + 16;
+}
+#ifndef CC_EMU
+CC_DEV unsigned int cc_smem_addr(const void* q)
+{
+    return static_cast<unsigned int>(__cvta_generic_to_shared(q));
+}
+CC_DEV void cc_mbar_init(unsigned long long* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cc_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+CC_DEV void cc_mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cc_smem_addr(bar)), "r"(bytes) : "memory");
+}
+CC_DEV void cc_bulk_g2s(void* dst_smem, const void* src_global, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cc_smem_addr(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(cc_smem_addr(bar))
+                 : "memory");
+}
+CC_DEV void cc_mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    unsigned int done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(cc_smem_addr(bar)), "r"(parity)
+                     : "memory");
+}
+#endif
+
+CC_DEV void d_probe_tile(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int do_snapshot)
+{
+    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe, g.bid);
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted)
+        return; // an earlier push in flight could not be committed speculatively (see k_halt)
+    if (do_snapshot) // list-root state before the speculative commit (rolled back if it aborts)
+        d_snapshot(g, p, 0);
+    const int R = cfg.R, msr = cfg.max_steps_row;
+    const int ncols = hd.ncols < p.maxcols ? hd.ncols : p.maxcols;
+    const long long colbase = hd.colbase;
+    const int base_local = ncols > 0 ? cc_local_col(colbase, cfg.ringcols) : 0;
+    const int T = blockDim.x, t = threadIdx.x;
+    const double rm_carry = p.st->runmax_carry;
+    CC_SMEM(smem);
+    const int tile_cols = cc_tile_cols(R), wcols = tile_cols + msr;
+    float4* win = reinterpret_cast<float4*>(smem);                                  // [wcols][R] x, y, z, inclination
+    double* win_caz = reinterpret_cast<double*>(win + static_cast<size_t>(wcols) * R); // [wcols][R] continuous azimuth
+    double* part = win_caz + static_cast<size_t>(wcols) * R; // block-scan scratch (32) + per-tile maxima (64)
+    double* rm_tile = part + 32; // running maximum BEFORE every column of the tile
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(rm_tile + 64);
+    float* win_mad = reinterpret_cast<float*>(bar + 2);                             // [wcols][R] maximum azimuth difference
+    const int n_workers = g.nb > 1 ? g.nb - 1 : 1;
+    if (g.nb > 1 && g.bid == g.nb - 1)
+    {
+        // the extra CTA: running maximum of the column minima of every column of the push, for k_probe_heavy and the finish pass
+        const int per = (ncols + T - 1) / T;
+        const int lo = t * per < ncols ? t * per : ncols, hi = lo + per < ncols ? lo + per : ncols;
+        double m = -1.0;
+        for (int i = lo; i < hi; i++)
+        {
+            const double v = p.col_minaz[i];
+            m = v > m ? v : m;
+        }
+        double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
+        pre = rm_carry > pre ? rm_carry : pre;
+        for (int i = lo; i < hi; i++)
+        {
+            const double v = p.col_minaz[i];
+            pre = v > pre ? v : pre;
+            p.col_runmax[i] = pre;
+        }
+        return;
+    }
+    const int ntiles = (ncols + tile_cols - 1) / tile_cols;
+#ifndef CC_EMU
+    if (t == 0)
+        cc_mbar_init(bar, 1);
+    __syncthreads();
+#endif
+    unsigned int phase = 0;
+    for (int tile = g.bid; tile < ntiles; tile += n_workers)
+    {
+        const int ci0 = tile * tile_cols;
+        // ---- the tile's field of view: ring columns [w0, w0 + wcols), wrapped ----
+        int w0 = base_local + ci0 - msr;
+        w0 %= cfg.ringcols;
+        if (w0 < 0)
+            w0 += cfg.ringcols;
+        const int n1 = wcols < cfg.ringcols - w0 ? wcols : cfg.ringcols - w0; // columns up to the end of the ring
+#ifdef CC_EMU
+        for (int i = t; i < wcols * R; i += T)
+        {
+            const int wc = i / R;
+            const int lc = wc < n1 ? w0 + wc : wc - n1;
+            win[i] = p.assoc[static_cast<size_t>(lc) * R + (i - wc * R)];
+            win_caz[i] = p.cont_az[static_cast<size_t>(lc) * R + (i - wc * R)];
+            win_mad[i] = p.mad[static_cast<size_t>(lc) * R + (i - wc * R)];
+        }
+#else
+        if (t == 0)
+        {
+            const unsigned int cells1 = static_cast<unsigned int>(n1 * R), cells2 = static_cast<unsigned int>((wcols - n1) * R);
+            cc_mbar_expect_tx(bar, static_cast<unsigned int>(wcols * R * (sizeof(float4) + sizeof(double) + sizeof(float))));
+            cc_bulk_g2s(win, p.assoc + static_cast<size_t>(w0) * R, cells1 * sizeof(float4), bar);
+            cc_bulk_g2s(win_caz, p.cont_az + static_cast<size_t>(w0) * R, cells1 * sizeof(double), bar);
+            cc_bulk_g2s(win_mad, p.mad + static_cast<size_t>(w0) * R, cells1 * sizeof(float), bar);
+            if (cells2)
+            {
+                cc_bulk_g2s(win + cells1, p.assoc, cells2 * sizeof(float4), bar);
+                cc_bulk_g2s(win_caz + cells1, p.cont_az, cells2 * sizeof(double), bar);
+                cc_bulk_g2s(win_mad + cells1, p.mad, cells2 * sizeof(float), bar);
+            }
+        }
+#endif
+        // ---- while it lands: the largest column minimum before the tile ----
+        {
+            double m = -1.0;
+            for (int i = t; i < ci0; i += T)
+            {
+                const double v = p.col_minaz[i];
+                m = v > m ? v : m;
+            }
+            const double pre = cc_block_exclusive_scan(part, m, -1.0, CcOpMaxF64());
+            if (t == T - 1)
+            {
+                double run = pre > m ? pre : m;
+                run = rm_carry > run ? rm_carry : run;
+                for (int k = 0; k < tile_cols && k < 64; k++)
+                {
+                    rm_tile[k] = run;
+                    if (ci0 + k < ncols)
+                    {
+                        const double v = p.col_minaz[ci0 + k];
+                        run = v > run ? v : run;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#ifndef CC_EMU
+        cc_mbar_wait(bar, phase);
+        phase ^= 1u;
+#endif
+        for (int cell0 = 0; cell0 < tile_cols * R; cell0 += T) // (whole warps stay in the loop: ballot below)
+        {
+            const int cell = cell0 + t;
+            const int tcol = cell / R, prow = cell - tcol * R;
+            const int pci = ci0 + tcol;
+            bool heavy = false;
+            const int pidx = pci * R + prow;
+            bool has = cell < tile_cols * R && pci < ncols;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has)
+            {
+                a = win[static_cast<size_t>(msr + tcol) * R + prow];
+                has = !cc_isnan(a.x);
+            }
+            if (has)
+            {
+                int plocal = base_local + pci;
+                if (plocal >= cfg.ringcols)
+                    plocal -= cfg.ringcols;
+                const unsigned int pq = static_cast<unsigned int>(plocal) * R + prow;
+                const float mad = win_mad[static_cast<size_t>(msr + tcol) * R + prow];
+                const double prev_runmax = rm_tile[tcol < 64 ? tcol : 63];
+                int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
+                steps_back = steps_back < msr ? steps_back : msr;
+                unsigned int first = CC_NONE, l0 = CC_NONE, l1 = CC_NONE, l2 = CC_NONE, l3 = CC_NONE;
+                int nl = 0, visited = 0;
+                bool flagged = false;
+                int ocol = plocal, reached = 0;
+                for (int back = 0; back <= steps_back; back++)
+                {
+                    reached = back;
+                    const size_t wofs = static_cast<size_t>(msr + tcol - back) * R;
+                    const float4* wcol = win + wofs;
+                    for (int dir = -1; dir <= 1 && !heavy; dir += 2)
+                    {
+                        if (dir == 1 && back == 0)
+                            continue;
+                        int steps_v = (dir == 1 || back == 0) ? 1 : 0;
+                        int orow = (dir == 1 || back == 0) ? prow + dir : prow;
+                        while (orow >= 0 && orow < R && steps_v <= cfg.max_steps_col)
+                        {
+                            if (visited >= CC_TILE_BUDGET)
+                            {
+                                heavy = true;
+                                break;
+                            }
+                            const float4 b = wcol[orow];
+                            visited++;
+                            if (fabsf(b.w - a.w) > mad) // cpp:728-729 (NaN never breaks)
+                                break;
+                            if (!cc_isnan(b.x))
+                            {
+                                const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                                if (dx * dx + dy * dy + dz * dz < cfg.max_distance_sq) // cpp:638-641
+                                {
+                                    const unsigned int o = static_cast<unsigned int>(ocol) * R + orow;
+                                    // could the reference have refused this hit?
+                                    const double finish_o = win_caz[wofs + orow] + static_cast<double>(win_mad[wofs + orow]);
+                                    if (finish_o <= prev_runmax)
+                                        flagged = true;
+                                    if (back > pci)
+                                    {
+                                        const unsigned int ro = p.tparent[o];
+                                        if (ro == CC_NONE || p.tstate[ro] != 0)
+                                            flagged = true;
+                                    }
+                                    if (first == CC_NONE)
+                                        first = o;
+                                    else if (nl == 0)
+                                        l0 = o, nl = 1;
+                                    else if (nl == 1)
+                                        l1 = o, nl = 2;
+                                    else if (nl == 2)
+                                        l2 = o, nl = 3;
+                                    else if (nl == 3)
+                                        l3 = o, nl = 4;
+                                    else
+                                    {
+                                        heavy = true; // the overflow list is the cooperative walk's business
+                                        break;
+                                    }
+                                }
+                            }
+                            if (first != CC_NONE && cfg.stop_enabled && steps_v >= cfg.stop_min_steps) // cpp:747-749
+                                break;
+                            orow += dir;
+                            steps_v++;
+                        }
+                    }
+                    if (heavy)
+                        break;
+                    if (first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps) // cpp:757-759
+                        break;
+                    ocol--;
+                    if (ocol < 0)
+                        ocol += cfg.ringcols; // cpp:768-769
+                }
+                if (!heavy)
+                {
+                    unsigned int* lk = s_links + static_cast<size_t>(pidx) * CC_LINK_SLOTS;
+                    lk[0] = l0;
+                    lk[1] = l1;
+                    lk[2] = l2;
+                    lk[3] = l3;
+                    s_parent[pidx] = first == CC_NONE ? pq : first;
+                    p.visited[pq] = static_cast<unsigned short>(visited);
+                    p.vback[pq] = static_cast<unsigned char>(reached);
+                    if (flagged || (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0))
+                    {
+                        p.col_flag[pci] = 1;
+                        atomicAdd(&p.st->n_flagged, 1);
+                    }
+                }
+            }
+            // points for the cooperative walk go to the list k_probe_heavy works through
+#ifdef CC_EMU
+            if (has && heavy)
+                p.heavy_list[atomicAdd(&p.st->n_heavy, 1)] = pidx;
+#else
+            const unsigned int hm = __ballot_sync(CC_FULL_MASK, has && heavy);
+            if (hm)
+            {
+                const int lane = t % CC_WARP;
+                int pos0 = 0;
+                if (lane == __ffs(hm) - 1)
+                    pos0 = atomicAdd(&p.st->n_heavy, __popc(hm));
+                pos0 = __shfl_sync(CC_FULL_MASK, pos0, __ffs(hm) - 1);
+                if (has && heavy)
+                    p.heavy_list[pos0 + __popc(hm & ((1u << lane) - 1u))] = pidx;
+            }
+#endif
+        }
+        __syncthreads(); // the window is overwritten by the next tile's copy
+    }
+}
+__global__ void __launch_bounds__(CC_TILE_CELLS) k_probe_tile(CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links,
+                                                            int do_snapshot)
+{
+    CC_PDL_ENTER();
+    d_probe_tile(cc_grid(), cfg, p, s_parent, s_links, do_snapshot);
+}
+
 // K3a': the points the thread-per-point path gave up on, one CTA (two warps) per point. When a vertical run fits one warp step
 // (max_steps_in_column < 32) and the window has at most 64 runs:
 //   phase 1  the warps of the CTA share the runs of the window: independent loads, inclination-break and distance
@@ -4754,6 +5061,51 @@ __global__ void k_pack_labels(CcDevCfg cfg, CcDevPtrs p, uchar4* out, int cap_co
 {
     CC_PDL_ENTER();
     d_pack_labels(cc_grid(), cfg, p, out, cap_cols);
+}
+
+// The results of a push -- stream state, first unpublished column per column, cluster records, member lists, packed
+// labels -- written straight into the push's page-locked HOST buffers by one kernel on the copy stream: exactly as many
+// bytes as the push produced (the copy engine moved capacity-sized prefixes in five transfers, ~150 us behind the last
+// kernel; this is one launch and ~1.4 MB of stores over the link at 4096 firings per push).
+struct CcResultDst
+{
+    CcDevState* h_state;
+    long long* h_first_unpub;
+    CcCluster* h_clusters;
+    CcClusterPoint* h_points;
+    uchar4* h_labels; // or null
+    int cap_cols, cap_clusters, cap_points, rows;
+};
+CC_DEV void cc_copy_out(void* dst, const void* src, size_t bytes, size_t tid, size_t nt)
+{
+    // 16-byte pieces (every source array is 16-byte aligned and the records are 8 or 16 bytes), then the 4-byte tail
+    const size_t n16 = bytes / 16;
+    const float4* s16 = reinterpret_cast<const float4*>(src);
+    float4* d16 = reinterpret_cast<float4*>(dst);
+    for (size_t i = tid; i < n16; i += nt)
+        d16[i] = s16[i];
+    const unsigned int* s4 = reinterpret_cast<const unsigned int*>(src);
+    unsigned int* d4 = reinterpret_cast<unsigned int*>(dst);
+    for (size_t i = n16 * 4 + tid; i < bytes / 4; i += nt)
+        d4[i] = s4[i];
+}
+__global__ void k_results_to_host(const CcDevState* snap, const long long* d_first_unpub, const CcCluster* d_clusters,
+                                  const CcClusterPoint* d_points, const uchar4* d_labels, CcResultDst dst)
+{
+    CC_PDL_ENTER();
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nt = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const int ncols = snap->ncols < dst.cap_cols ? snap->ncols : dst.cap_cols;
+    const int ncl = snap->n_clusters < dst.cap_clusters ? snap->n_clusters : dst.cap_clusters;
+    const int ncp = snap->n_cluster_points < dst.cap_points ? snap->n_cluster_points : dst.cap_points;
+    cc_copy_out(dst.h_state, snap, sizeof(CcDevState), tid, nt);
+    if (ncols > 0)
+        cc_copy_out(dst.h_first_unpub, d_first_unpub, static_cast<size_t>(ncols) * sizeof(long long), tid, nt);
+    if (ncl > 0)
+        cc_copy_out(dst.h_clusters, d_clusters, static_cast<size_t>(ncl) * sizeof(CcCluster), tid, nt);
+    if (ncp > 0)
+        cc_copy_out(dst.h_points, d_points, static_cast<size_t>(ncp) * sizeof(CcClusterPoint), tid, nt);
+    if (dst.h_labels && ncols > 0)
+        cc_copy_out(dst.h_labels, d_labels, static_cast<size_t>(ncols) * dst.rows * sizeof(uchar4), tid, nt);
 }
 
 // copy of the stream state at the end of a push (what the host reads while the next push already runs)

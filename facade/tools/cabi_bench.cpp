@@ -16,7 +16,8 @@
 // out[0] seconds of the K timed pushes, out[1] device->host bytes read per push (mean), out[2] checksum of what was read,
 // out[3] pushes that took the exact path; marks_ms[steps]: time of every cc_wait return since the clock started.
 CB_API int cb_e2e(const cc_config_t* cfg, int rows, const double* robot_from_sensor, int device, int batch, int warm, int steps,
-                  const cc_raw_point_t* pts, const double* poses, int label_prefetch, double* out, double* marks_ms, char* err)
+                  const cc_raw_point_t* pts, const double* poses, int label_prefetch, double* out, double* marks_ms, float* slot_ms,
+                  char* err)
 {
     cc_handle_t* h = nullptr;
     auto fail = [&](const char* what) -> int
@@ -65,6 +66,8 @@ CB_API int cb_e2e(const cc_config_t* cfg, int rows, const double* robot_from_sen
         exact += info.used_exact_path ? 1 : 0;
         return true;
     };
+    if (slot_ms)
+        cc_debug_slot_base(h);
     const auto t0 = std::chrono::steady_clock::now();
     // two pushes in flight and a third one staged: the host->device copy of push k + 2 overlaps the kernels of k and k + 1
     for (int s = warm; s < warm + steps && s < warm + 2; s++)
@@ -79,6 +82,8 @@ CB_API int cb_e2e(const cc_config_t* cfg, int rows, const double* robot_from_sen
             return fail("cc_wait");
         if (marks_ms)
             marks_ms[s - warm] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (slot_ms)
+            cc_debug_slot_times(h, s % 2, slot_ms + 5 * (s - warm)); // the slots alternate from the first push on
         if (!consume())
             return fail("results");
     }

@@ -3,9 +3,8 @@
 tag=${1:-s}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-python bench.py --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
-E2E_WARM=1 python scripts/e2e_probe.py 4096 1 > gpurun_out/e2e_probe_$tag.txt 2>&1
-tail -3 gpurun_out/bench_$tag.err
+CC_BENCH_SLOT_TIMES=1 python bench.py --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+tail -8 gpurun_out/bench_$tag.err
 python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_$tag.json'))
@@ -14,4 +13,4 @@ print('marks', d['e2e'].get('wait_return_ms'))
 print('latency_mode', {k:v for k,v in d['latency_mode'].items() if k not in ('histogram_us','call')})
 print('exact', d['exact_path'])
 PY
-cat gpurun_out/e2e_probe_$tag.txt
+( timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "staged or pipelined or full_size" 2>&1 | tail -3 ) 

@@ -280,3 +280,21 @@ def test_short_pushes_are_one_launch(emu_library):
     cc = make_cc(emu_library, drvlib.stream_config("tiny16"), sp.rows)
     launches = [int(cc.addFirings(pts[a:a + 64], poses[a:a + 64]).info.gpu_launches) for a in range(0, 384, 64)]
     assert launches == [1] * len(launches), launches
+
+
+TILE_CASES = [CASES[0], CASES[2], CASES[5], CASES[11], CASES[12], CASES[13], CASES[17]]
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", TILE_CASES)
+def test_tiled_probe_matches_oracle(emu_library, oracle_lib, monkeypatch, spec, kw, cfg_over, chunk, flag_period):
+    """The alternative association probe (k_probe_tile: one thread per cell of a tile of columns, the tile's field of view
+    staged in shared memory; CC_B200_TUNE bit 2) gives the same results as the list-driven one, through the kernel chain."""
+    monkeypatch.setenv("CC_B200_TUNE", "4")
+    monkeypatch.setenv("CC_B200_FUSED_MAX", "0")
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(emu_library, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="emulated kernels (tiled probe)", check_tree_fields=True)

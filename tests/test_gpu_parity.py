@@ -158,3 +158,24 @@ def test_device_timeline_does_not_change_results(cuda_library, oracle_lib):
     for k in ("k_prep", "k_ground", "k_probe", "k_fin_all", "k_fin_label"):
         assert k in tr and tr[k][3] > 0 and tr[k][1] > tr[k][0]
     assert tr["k_ground"][0] >= tr["k_prep"][0]
+
+
+@pytest.mark.parametrize("spec,kw,cfg_over,chunk,flag_period", [
+    ("velodyne64", dict(n_rotations=2.2, moving=True, dropout=0.03), {}, 1024, 0),
+    ("vls128", dict(n_rotations=1.3, moving=True), {}, 700, 0),
+    ("os32_left", dict(n_rotations=2.5, moving=True), {}, 512, 0),
+    ("tiny16", dict(n_rotations=3.0, n_boxes=0, wall_radius=8.0), {}, 128, 0),
+    ("velodyne64", dict(n_rotations=1.3, az_jitter=0.5, az_step_scale=1.04), {}, 1024, 0),
+])
+def test_cuda_tiled_probe_matches_oracle(cuda_library, oracle_lib, monkeypatch, spec, kw, cfg_over, chunk, flag_period):
+    """k_probe_tile (field of view of a tile of columns staged in shared memory by cp.async.bulk + mbarrier, one thread per
+    cell; CC_B200_TUNE bit 2): same results as the default list-driven probe."""
+    monkeypatch.setenv("CC_B200_TUNE", "4")
+    monkeypatch.setenv("CC_B200_FUSED_MAX", "0")
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, **cfg_over)
+    want = oracle_record(oracle_lib, pts, poses, sp, cfg)
+    cc = make_cc(None, cfg, sp.rows)
+    cc.debug_flag_columns(flag_period)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="cuda (tiled probe)", check_tree_fields=True)
