@@ -409,6 +409,20 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200): there is no CPU path in continuous_clustering_b200")
     torch.cuda.set_device(local_rank)
     dist = None
+    cpu_binding = None
+    if world > 1:
+        # one rank per GPU on one host: give every rank's host thread (it polls for completion) its own share of the
+        # cores the job may use, so that the ranks do not migrate over each other (round-1 verdict: e2e scaling)
+        try:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // max(1, local_world))
+            mine = cores[(local_rank * per) % len(cores):][:per]
+            if mine:
+                os.sched_setaffinity(0, set(mine))
+                cpu_binding = {"cores": mine, "of": len(cores)}
+        except Exception as e:
+            cpu_binding = {"error": str(e)[:80]}
     if world > 1:
         import torch.distributed as dist_mod
 
@@ -831,7 +845,7 @@ def main():
                           "before the timed region, timed pushes run back to back; l2_flush_each_step reports the same with a "
                           "flush before every push",
                     "pipelining": "two pushes in flight (cc_submit_firings_device / cc_wait); end-to-end leg: a third host push staged",
-                    "streams": f"{world} independent sensor stream(s), one per GPU, no data-path collective",
+                    "cpu_binding": cpu_binding, "streams": f"{world} independent sensor stream(s), one per GPU, no data-path collective",
                     "exact_path_pushes": exact_pushes},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": B * (rec_bytes + pose_bytes),

@@ -12,10 +12,13 @@ if [ -z "$2" ]; then
 fi
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python bench.py --impl reference --steps 5 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err
-for g in 32 296; do
-  CC_B200_VFIX_GRID=$g python scripts/trace_push.py 4096 > gpurun_out/tl4096_${tag}_v$g.txt 2>&1
-done
+python scripts/trace_push.py 4096 > gpurun_out/tl4096_$tag.txt 2>&1
 python scripts/trace_push.py 64 0 > gpurun_out/tl64_$tag.txt 2>&1
+python scripts/trace_push.py 1024 0 wall > gpurun_out/tlwall_$tag.txt 2>&1
+# the other BASELINE configurations (config 3: 128 rings; config 1 stand-in: 64 x 2200; moving sensor)
+python bench.py --spec vls128 --no-cpu-baseline > gpurun_out/bench_vls128_$tag.json 2>> gpurun_out/bench_$tag.err
+python bench.py --spec kitti64 --no-cpu-baseline --quick-e2e > gpurun_out/bench_kitti64_$tag.json 2>> gpurun_out/bench_$tag.err
+python bench.py --moving --no-cpu-baseline > gpurun_out/bench_moving_$tag.json 2>> gpurun_out/bench_$tag.err
 python scripts/e2e_timeline.py 4096 > gpurun_out/e2e_tl_$tag.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 4 --warmup 3 --quick --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
@@ -31,5 +34,12 @@ print('exact', d['exact_path'])
 print('cpu', d['cpu_baseline']['value'])
 for k,v in d['kernels'].items(): print(f"{k:18s} {v['ms_per_step']*1000:7.1f} us {v['share']*100:5.1f}%")
 PY
-grep -h "device_ms\|k_visited_fix\|k_fin_all " gpurun_out/tl4096_${tag}_v*.txt | tail -12
+for c in vls128 kitti64 moving; do python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/bench_${c}_$tag.json'))
+    print('$c value',round(d['value']/1e6,2),'e2e',round(d['e2e']['value']/1e6,2),'lat', d.get('latency_mode') and round(d['latency_mode']['per_push_us_p50'],1))
+except Exception as e: print('$c', e)
+PY
+done
 tail -8 gpurun_out/e2e_tl_$tag.txt

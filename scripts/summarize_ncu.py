@@ -70,6 +70,22 @@ if os.path.exists(rep):
     lines.append("")
     json.dump(table, open(os.path.join(out_dir, f"{tag}_full.json"), "w"), indent=1)
 
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: what bench.py reports as roofline.traffic
+    def mbytes(v):
+        val, unit = v
+        val = float(val)
+        return int(val * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1))
+
+    traffic = {"source": f"profiles/{tag}_full.json (ncu --set full --clock-control none, one launch per kernel, bench.py --quick at 4096 "
+                         "firings per push; cold-cache replay)", "kernels": {}}
+    for n, t in table.items():
+        if "dram__bytes_read.sum" in t and "dram__bytes_write.sum" in t:
+            rd, wr = mbytes(t["dram__bytes_read.sum"]), mbytes(t["dram__bytes_write.sum"])
+            traffic["kernels"][n] = {"dram_bytes": rd + wr, "read": rd, "write": wr}
+    if "k_fin_cluster" in traffic["kernels"]:  # the whole-push finish pass is timed under the name of its single-CTA variant
+        traffic["kernels"]["k_fin_all"] = traffic["kernels"]["k_fin_cluster"]
+    json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
+
 bench = os.path.join(g, f"bench_{tag}.json")
 if os.path.exists(bench):
     txt = open(bench).read().strip().splitlines()
