@@ -100,7 +100,12 @@ def make_rotations(n_rot_unique=2, seed=1234, spec_name=None):
     rotation anyway) with fresh stamps / firing indices / unique point indices."""
     from continuous_clustering_b200 import synth
 
-    pts, poses, sp = synth.make_stream(spec_name or SPEC, n_rotations=n_rot_unique, seed=seed)
+    # Sensors whose lasers fire at different azimuths (VLS-128: 8 groups over +-6.4 degrees, OS-32: 8 - 11 degrees) must not
+    # START on the negative x axis: the reference drops a first firing that straddles it and asks for a reset (cpp:252-261,
+    # SURVEY 8d "start just after the -x axis so the first firing does not straddle it"); 64 firings later no row does.
+    name = spec_name or SPEC
+    start = 64 if float(np.abs(synth.spec(name).azimuth_offsets_rad).max()) > 0 else 0
+    pts, poses, sp = synth.make_stream(name, n_rotations=n_rot_unique, seed=seed, start_firing=start)
     return pts, poses, sp
 
 
@@ -126,7 +131,8 @@ class Stream:
 
         self.moving = moving
         if moving:
-            self.pts, self.poses, self.sp = synth.make_stream(spec_name, n_firings=total_firings, seed=seed, moving=True)
+            start = 64 if float(np.abs(synth.spec(spec_name).azimuth_offsets_rad).max()) > 0 else 0
+            self.pts, self.poses, self.sp = synth.make_stream(spec_name, n_firings=total_firings, seed=seed, moving=True, start_firing=start)
         else:
             self.pts, self.poses, self.sp = make_rotations(seed=seed, spec_name=spec_name)
 
@@ -716,6 +722,26 @@ def main():
     # ------------------------------------------------------------------ per-GPU push latency (every rank; BASELINE config 5)
     LB = 64
 
+    def latency_leg_c(nl=200, warm=60):
+        """The same through a C++ caller of the C ABI (facade/tools/cabi_bench.cpp cb_latency): no interpreter in the loop."""
+        path = os.path.join(HERE, "build", "libcc_cabi_bench.so")
+        if not os.path.exists(path):
+            return None
+        lib = C.CDLL(path)
+        lib.cb_latency.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+        lp, lq = stream.take(0, nl * LB)
+        _keep, _keepq, hlp, hlq = pinned(lp, lq)
+        call_us, dev_us, out = np.zeros(nl), np.zeros(nl), np.zeros(2)
+        err = C.create_string_buffer(256)
+        tf = np.asarray(IDENTITY, dtype=np.float64)
+        cfg_c = cfg.to_c()
+        rc = lib.cb_latency(C.addressof(cfg_c), R, tf.ctypes.data, local_rank, LB, nl, hlp.ctypes.data, hlq.ctypes.data, 1,
+                            call_us.ctypes.data, dev_us.ctypes.data, out.ctypes.data, err)
+        if rc != 0:
+            raise RuntimeError("cabi_bench: " + err.value.decode(errors="replace"))
+        return call_us[warm:], dev_us[warm:], int(out[1])
+
     def latency_leg(nl=200, warm=60):
         ccl = new_handle(LB)
         ccl.set_label_prefetch(True)
@@ -731,9 +757,20 @@ def main():
             launches = int(r.info.gpu_launches)
         ccl.close()
         lat, dev = np.array(lat[warm:]), np.array(dev[warm:])
+        python_loop = {"per_push_us_p50": float(np.median(lat)), "per_push_us_p99": float(np.percentile(lat, 99)),
+                       "call": "ContinuousClustering.addFirings (Python mirror: ctypes + numpy views around the same C call)"}
+        call = "cc_push_firings via ContinuousClustering.addFirings (page-locked host buffers in; events / clusters / member lists / labels back on the host)"
+        try:
+            c = latency_leg_c(nl, warm)
+        except Exception as e:
+            print(f"cabi latency leg failed: {e}", file=sys.stderr)
+            c = None
+        if c is not None:
+            lat, dev, launches = c
+            call = ("cc_push_firings from a C++ caller of the C ABI (build/libcc_cabi_bench.so; page-locked host buffers in; events / "
+                    "clusters / member lists / labels read on the host before the clock stops)")
         hist, edges = np.histogram(lat, bins=[0, 60, 70, 80, 90, 100, 110, 120, 140, 160, 200, 300, 1e9])
-        return {"batch_firings": LB, "call": "cc_push_firings via ContinuousClustering.addFirings (page-locked host buffers in; "
-                "events / clusters / member lists / labels back on the host)", "launches_per_push": launches,
+        return {"batch_firings": LB, "call": call, "python_loop": python_loop, "launches_per_push": launches,
                 "per_push_us_p50": float(np.median(lat)), "per_push_us_p99": float(np.percentile(lat, 99)),
                 "per_push_us_mean": float(lat.mean()), "per_push_device_us_p50": float(np.median(dev)),
                 "per_push_ms_p50": float(np.median(lat)) / 1e3, "per_push_ms_p99": float(np.percentile(lat, 99)) / 1e3,
