@@ -4476,11 +4476,15 @@ CC_DEV void d_fin_copyback(const CcGrid g, const CcDevPtrs& p, int spec)
 // that were still unfinished when the pass started (cpp:943-959), or column + 1. G[r] = last column at which
 // some tree rooted in column gbase + r is unfinished; with PG = prefix max of G, the answer for column c is the
 // first r with PG[r] >= c. Single block.
-CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, int smem_ints)
+// `nslices` > 1 (k_fin_cluster): every CTA of the cluster builds the prefix maxima in its own shared memory and answers
+// every nslices-th group of columns; CTA `slice` 0 also does the end-of-pass bookkeeping. Falls back to one CTA when the
+// prefix maxima do not fit shared memory (they are then built in place in global memory).
+CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p, int spec, int smem_ints, int slice = 0,
+                          int nslices = 1)
 {
     if (!cc_spec_ok(p.st, spec))
         return;
-    if (g.bid != 0)
+    if (nslices <= 1 && g.bid != 0)
         return;
     CC_SMEM(smem);
     long long* part = reinterpret_cast<long long*>(smem);
@@ -4494,6 +4498,9 @@ CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
     // as columns relative to gbase (CC_COL_INF -> INT_MAX)
     int* pg = reinterpret_cast<int*>(part + T);
     const bool in_smem = glen <= smem_ints;
+    if (!in_smem && slice != 0)
+        return;
+    const bool sliced = nslices > 1 && in_smem;
     if (in_smem)
     {
         // G staged once with coalesced loads issued together, as columns relative to gbase (monotone encoding, so the
@@ -4541,9 +4548,9 @@ CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
         }
     }
     __syncthreads();
-    for (long long c = c0 + t; c <= c1; c += T)
+    // first r in [0, c - gbase] with PG[r] >= c, else c + 1 - gbase
+    auto first_unpublished_after = [&](long long c) -> long long
     {
-        // first r in [0, c - gbase] with PG[r] >= c, else c + 1 - gbase
         long long a = 0, b = c - gbase + 1;
         if (b > glen)
             b = glen;
@@ -4568,15 +4575,21 @@ CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
                 else
                     a = mid + 1;
             }
-        long long fu = gbase + a;
-        if (fu > c + 1)
-            fu = c + 1;
-        p.col_first_unpub[c - colbase] = fu;
-    }
+        const long long fu = gbase + a;
+        return fu > c + 1 ? c + 1 : fu;
+    };
+    const long long c_first = c0 + t + (sliced ? static_cast<long long>(slice) * T : 0);
+    const long long c_step = static_cast<long long>(sliced ? nslices : 1) * T;
+    for (long long c = c_first; c <= c1; c += c_step)
+        p.col_first_unpub[c - colbase] = first_unpublished_after(c);
+    // the bookkeeping below needs the answer for the last column: thread 0 of slice 0 computes it itself (another CTA may own it)
+    long long fu_last = 0;
+    if (t == 0 && slice == 0)
+        fu_last = c1 >= c0 ? first_unpublished_after(c1) : p.col_first_unpub[c1 - colbase];
     __syncthreads();
-    if (t == 0)
+    if (t == 0 && slice == 0)
     {
-        const long long fu = p.col_first_unpub[c1 - colbase];
+        const long long fu = fu_last;
         if (fu < st->first_unpub)
         {
             st->error = CC_DEV_RING_START_DECREASED; // cpp:1072-1075
@@ -5783,11 +5796,14 @@ __global__ void __launch_bounds__(512, 1) k_fin_cluster(CcDevCfg cfg, CcDevPtrs 
         g1.nb = 1;
         d_fin_copyback(g1, p, 1);
     }
-    if (g.bid == 0)
     {
+        // every CTA answers its share of the columns (each with its own copy of the prefix maxima in shared memory)
         CcTraceScope tr(p.trace, CC_KID_fin_columns, g.bid);
         __syncthreads();
-        d_fin_columns(g, cfg, p, 1, (smem_bytes - static_cast<int>(blockDim.x) * 8) / 4);
+        d_fin_columns(g, cfg, p, 1, (smem_bytes - static_cast<int>(blockDim.x) * 8) / 4, g.bid, g.nb);
+    }
+    if (g.bid == 0)
+    {
         __syncthreads();
         if (last && threadIdx.x == 0)
             d_push_done(p, 1);
