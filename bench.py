@@ -416,7 +416,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     cpu_binding = None
-    if world > 1:
+    if world > 1 and not os.environ.get("CC_BENCH_NO_BIND"):
         # one rank per GPU on one host: give every rank's host thread (it polls for completion) its own share of the
         # cores the job may use, so that the ranks do not migrate over each other (round-1 verdict: e2e scaling)
         try:
