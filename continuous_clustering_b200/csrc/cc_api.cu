@@ -1087,8 +1087,8 @@ static void launch_finish(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, i
     // (not after the exact pass of a single column: k_careful's walk honours the stop itself, nothing is listed)
     if (exact)
         return;
-    static const int vfix_grid = std::getenv("CC_B200_VFIX_GRID") ? std::max(1, std::atoi(std::getenv("CC_B200_VFIX_GRID"))) : 32;
-    CC_RUN(h, k_visited_fix, vfix_grid, 256, (256 / CC_WARP) * CC_PROBE_PIPE * CC_WARP * sizeof(float4), cfg, h->d, guard, snap);
+    static const int vfix_grid = std::getenv("CC_B200_VFIX_GRID") ? std::max(1, std::atoi(std::getenv("CC_B200_VFIX_GRID"))) : 128;
+    CC_RUN(h, k_visited_fix, vfix_grid, 64, cc_heavy_smem_bytes(64, 2), cfg, h->d, guard, snap, h->tune);
 }
 
 static void launch_commit(cc_handle* h, const CcDevCfg& cfg, int ci0, int ci1, int guard, bool snapshot)

@@ -3352,10 +3352,12 @@ CC_DEV void cc_team_sync(int team_warps, int nwarps, int team)
 }
 
 // TEAMS = false: the team is the whole CTA (the stage as its own kernel: plain block barriers, no named barriers reserved)
-template<bool TEAMS>
+// COUNT: count-only mode of k_visited_fix -- the list is (heavy_list[e], probe_list[e]) = (point, columns back at which the
+// reference's walk stops, cpp:762-763), n_vfix entries; only number_of_visited_neighbors is written.
+template<bool TEAMS, bool COUNT = false>
 CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned int* s_parent, unsigned int* s_links, int tune, int team_warps)
 {
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_probe_heavy, g.bid);
+    CcTraceScope cc_trace_scope(p.trace, COUNT ? CC_KID_visited_fix : CC_KID_probe_heavy, g.bid);
     const CcHead hd = cc_head(p.st);
     if (hd.halted)
         return; // an earlier push in flight could not be committed speculatively (see k_halt)
@@ -3369,7 +3371,8 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
     const int teams_per_cta = cta_warps / nwarps;
     const int team = (threadIdx.x / CC_WARP) / nwarps, warp = (threadIdx.x / CC_WARP) % nwarps;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    const int nheavy = p.st->n_heavy < p.maxcols * R ? p.st->n_heavy : p.maxcols * R;
+    const int n_listed = COUNT ? p.st->n_vfix : p.st->n_heavy;
+    const int nheavy = n_listed < p.maxcols * R ? n_listed : p.maxcols * R;
     CC_SMEM(smem);
     float4* ring = reinterpret_cast<float4*>(smem) + (TEAMS ? static_cast<size_t>(team) * CC_PROBE_PIPE * CC_WARP : 0);
     __shared__ unsigned int sh_masks[128]; // the whole CTA is one team: fixed addresses
@@ -3383,10 +3386,11 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
     for (int hi = g.bid * teams_per_cta + team; hi < nheavy; hi += g.nb * teams_per_cta)
     {
         const int pidx = p.heavy_list[hi];
+        const int max_back = COUNT ? p.probe_list[hi] : -1;
         if (!masks_ok)
         {
             if (warp == 0)
-                d_probe_coop(cfg, p, s_parent, s_links, ring, base_local, colbase, lane, pidx);
+                d_probe_coop(cfg, p, s_parent, s_links, ring, base_local, colbase, lane, pidx, max_back);
             continue;
         }
         const int pci = pidx / R, prow = pidx - pci * R;
@@ -3400,6 +3404,8 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
         int steps_back = static_cast<int>(ceilf(ccm::div_rn(mad, cfg.width)));
         steps_back = steps_back < msr ? steps_back : msr;
         steps_back = steps_back < 0 ? 0 : steps_back;
+        if (COUNT && steps_back > max_back)
+            steps_back = max_back;
         const int nruns = 1 + 2 * steps_back; // run r: r = 0 own column upwards; odd r: column (r + 1) / 2 back, upwards
                                               // from the own row; even r: same column downwards (cpp:707-719)
         // ---- phase 1 ----
@@ -3534,7 +3540,7 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                         if (olocal < 0)
                             olocal += cfg.ringcols;
                         const unsigned int o = static_cast<unsigned int>(olocal) * R + (lane < cnt ? start_row + dir * lane : 0);
-                        if ((hp >> lane) & 1u) // every hit lane checks its own target
+                        if (!COUNT && ((hp >> lane) & 1u)) // every hit lane checks its own target
                         {
                             // could the reference have refused this hit?
                             const double finish_o = p.cont_az[o] + static_cast<double>(p.mad[o]);
@@ -3554,7 +3560,7 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                             hp &= hp - 1;
                         }
                         // the remaining hits are tree<->tree link candidates (cpp:740-741)
-                        if ((hp >> lane) & 1u)
+                        if (!COUNT && ((hp >> lane) & 1u))
                         {
                             const int slot = nlinks + __popc(hp & lt_mask);
                             if (slot < CC_LINK_SLOTS)
@@ -3577,19 +3583,27 @@ CC_DEV void d_probe_heavy(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, unsigned in
                 if ((r == 0 || !(r & 1)) && first != CC_NONE && cfg.stop_enabled && back >= cfg.stop_min_steps)
                     break; // cpp:757-759, after both runs of a column
             }
-            const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
-                                  (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
-            for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
-                s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
-            if (lane == 0)
+            if (COUNT)
             {
-                s_parent[pidx] = first == CC_NONE ? pq : first;
-                p.visited[pq] = static_cast<unsigned short>(visited);
-                p.vback[pq] = static_cast<unsigned char>(reached);
-                if (any_flag)
+                if (lane == 0)
+                    p.visited[pq] = static_cast<unsigned short>(visited);
+            }
+            else
+            {
+                const bool any_flag = __ballot_sync(CC_FULL_MASK, flagged) != 0 ||
+                                      (cfg.debug_flag_period > 0 && ((colbase + pci) % cfg.debug_flag_period) == 0);
+                for (int jl = nlinks + lane; jl < CC_LINK_SLOTS; jl += CC_WARP)
+                    s_links[static_cast<size_t>(pidx) * CC_LINK_SLOTS + jl] = CC_NONE;
+                if (lane == 0)
                 {
-                    p.col_flag[pci] = 1;
-                    atomicAdd(&p.st->n_flagged, 1);
+                    s_parent[pidx] = first == CC_NONE ? pq : first;
+                    p.visited[pq] = static_cast<unsigned short>(visited);
+                    p.vback[pq] = static_cast<unsigned char>(reached);
+                    if (any_flag)
+                    {
+                        p.col_flag[pci] = 1;
+                        atomicAdd(&p.st->n_flagged, 1);
+                    }
                 }
             }
         }
@@ -4937,15 +4951,19 @@ __global__ void k_fin_label(CcDevCfg cfg, CcDevPtrs p, unsigned int seq, int spe
     d_fin_label<false>(cc_grid(), cfg, p, seq, spec, nullptr, 0, via_rep != 0);
 }
 
-__global__ void __launch_bounds__(256) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec, CcDevState* snap)
+// The listed points are recounted by the mask algorithm of k_probe_heavy (a two-warp CTA per point: every vertical run of the cut
+// window evaluated at once, the sequential rules applied to the ballot masks) -- a point that walked its whole window costs one
+// memory round trip instead of one per run.
+__global__ void __launch_bounds__(64) k_visited_fix(CcDevCfg cfg, CcDevPtrs p, int spec, CcDevState* snap, int tune)
 {
     CC_PDL_ENTER();
     const CcGrid g = cc_grid();
-    CcTraceScope cc_trace_scope(p.trace, CC_KID_visited_fix, g.bid);
     if (snap && g.bid == 0 && threadIdx.x == 0)
         snap->n_vfix = p.st->n_vfix; // the list was filled after the finish pass copied the state
-    CC_SMEM(smem);
-    d_visited_fix(g, cfg, p, spec, reinterpret_cast<float4*>(smem), true);
+    const CcHead hd = cc_head(p.st);
+    if (hd.halted || !cc_head_ok(hd, spec))
+        return;
+    d_probe_heavy<false, true>(g, cfg, p, nullptr, nullptr, tune, 2);
 }
 
 // =====================================================================================================
