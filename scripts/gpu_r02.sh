@@ -10,7 +10,7 @@ if [ -z "$2" ]; then
   ( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 ) > gpurun_out/pytest_gpu_$tag.log
   tail -3 gpurun_out/pytest_gpu_$tag.log
 fi
-python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+CC_BENCH_SLOT_TIMES=1 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python bench.py --impl reference --steps 5 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err
 python scripts/trace_push.py 4096 > gpurun_out/tl4096_$tag.txt 2>&1
 python scripts/trace_push.py 64 0 > gpurun_out/tl64_$tag.txt 2>&1
