@@ -361,6 +361,86 @@ def cabi_e2e(cfg_c, rows, pts, poses, batch, warm, steps, device, label_prefetch
     return {"seconds": float(out[0]), "d2h_bytes_per_step": float(out[1]), "exact_pushes": int(out[3]), "marks_ms": marks[:steps].tolist()}
 
 
+def rows_around_the_path(device):
+    """SURVEY 8f rows 2-4 (the steps before and after the hot path), each timed through its C-ABI call with host buffers in and
+    its results on the host, beside the reference's own code (oracle/_ref/libcc_eval_ref.so, excerpts compiled unmodified) or the
+    restatement (packet decode) on one host core. Synthetic inputs of the tests (tests/test_kitti.py, test_packets.py, test_evaluation.py)."""
+    from continuous_clustering_b200 import KittiEvaluation, KittiReplay, OusterInput, synth
+
+    out = {}
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    eval_ref = os.path.join(HERE, "oracle", "_ref", "libcc_eval_ref.so")
+    ref = C.CDLL(eval_ref) if os.path.exists(eval_ref) else None
+    # ---- f2: one KITTI frame -> 2200 pseudo firings resident on the device (+ their poses)
+    xyzi, s0, s1, pstamps, poses, mid = synth.make_kitti_frame(seed=7, frame_index=3)
+    kr = KittiReplay(device=device)
+    kr.set_poses(pstamps, poses)
+    t = timed(lambda: kr.frame(xyzi, s0, s1, mid, 0, 3), 20)
+    kr.close()
+    entry = {"unit": "frames/s", "points_per_frame": int(xyzi.shape[0]), "value": 1.0 / t, "ms_per_frame": 1e3 * t,
+             "call": "cc_kitti_frame (host points in, 2200 x 64 RawPoint firings + poses left in device memory)"}
+    if ref is not None:
+        vp = C.c_void_p
+        ref.ev_frame_to_firings.argtypes = [C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        n = xyzi.shape[0]
+        firings = np.zeros(2200 * 64 * 48, np.uint8)
+        fposes, laser, cell, unc = np.zeros((2200, 12)), np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros((n, 3), np.float32)
+        pc = np.ascontiguousarray(poses, dtype=np.float64)
+        tc = timed(lambda: ref.ev_frame_to_firings(n, xyzi.ctypes.data, s0, s1, mid.ctypes.data, len(pstamps), pstamps.ctypes.data, pc.ctypes.data, 0, 3,
+                                                   firings.ctypes.data, fposes.ctypes.data, laser.ctypes.data, cell.ctypes.data, unc.ctypes.data), 5, 1)
+        entry["cpu_reference"] = {"value": 1.0 / tc, "ms_per_frame": 1e3 * tc, "cores": 1, "kind": "reference (kitti_loader.cpp / kitti_demo.cpp excerpts)"}
+    out["kitti_frame_to_firings"] = entry
+    # ---- f3: 256 Ouster lidar packets (16 blocks x 32 pixels) -> firings resident on the device
+    direction, offset = synth.ouster_xyz_lut("left")
+    packets, stamps = synth.make_ouster_packets(257, rows=32, columns_per_frame=1024, seed=1)
+    dec = OusterInput(32, 1024, direction, offset, device=device, max_packets_per_call=256)
+    dec.decode(packets[:1], stamps[:1])  # the packet in flight after a reset is dropped
+    t = timed(lambda: dec.decode(packets[1:], stamps[1:]), 30)
+    entry = {"unit": "packets/s", "value": 256 / t, "us_per_256_packets": 1e6 * t, "pixels_per_packet": 512,
+             "call": "cc_ouster_decode (host packets in, RawPoint firings left in device memory, firing stamps on the host)"}
+    orc_path = os.path.join(HERE, "oracle", "libcc_oracle.so")
+    if os.path.exists(orc_path):
+        orc = C.CDLL(orc_path)
+        vp = C.c_void_p
+        orc.orc_ouster_decode.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_uint64, vp, vp]
+        f_out, s_out = np.zeros(256 * 16 * 32 * 48, np.uint8), np.zeros(256 * 16, np.uint64)
+        pk, st = np.ascontiguousarray(packets[1:]), np.ascontiguousarray(stamps[1:])
+        tc = timed(lambda: orc.orc_ouster_decode(C.addressof(dec.format), direction.ctypes.data, offset.ctypes.data, 256, pk.ctypes.data, pk.shape[1],
+                                                 st.ctypes.data, 0, 0, f_out.ctypes.data, s_out.ctypes.data), 10, 1)
+        entry["cpu_reference"] = {"value": 256 / tc, "us_per_256_packets": 1e6 * tc, "cores": 1, "kind": "port (oracle/cc_packets_oracle.cpp, parity unpinned)"}
+    dec.close()
+    out["ouster_packets_to_firings"] = entry
+    # ---- f4: evaluation metrics of one frame
+    rng = np.random.RandomState(4)
+    n = 120000
+    sem = rng.choice(np.array([60, 40, 44, 48, 49, 72, 0, 1, 10, 11, 30, 50, 51, 70, 71, 80, 81, 99], dtype=np.uint16), size=n).astype(np.uint16)
+    ground = (rng.uniform(size=n) < 0.4).astype(np.uint8)
+    gt = rng.randint(0, 300, size=n).astype(np.uint32)
+    det = ((gt * 7 + (rng.uniform(size=n) < 0.3) * rng.randint(0, 5, size=n)) % 500).astype(np.uint32)
+    ev = KittiEvaluation(device=device, max_points_per_frame=1 << 17)
+    t = timed(lambda: ev.evaluate(sem, ground, gt, det), 30)
+    ev.close()
+    entry = {"unit": "frames/s", "points_per_frame": n, "value": 1.0 / t, "us_per_frame": 1e6 * t,
+             "call": "cc_eval_frame (host label arrays in, six numbers out)"}
+    if ref is not None:
+        ref.ev_evaluate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        o6 = np.zeros(6)
+        tc = timed(lambda: ref.ev_evaluate(n, sem.ctypes.data, ground.ctypes.data, gt.ctypes.data, det.ctypes.data, o6.ctypes.data), 5, 1)
+        entry["cpu_reference"] = {"value": 1.0 / tc, "us_per_frame": 1e6 * tc, "cores": 1, "kind": "reference (kitti_evaluation.cpp excerpts)"}
+    out["evaluation_metrics"] = entry
+    return out
+
+
 def facade_run(cfg_c, sp, pts, poses, batch, pipelined, callback_mode, warm, device, want_calls=False):
     """build/libcc_facade_bench.so (facade/tools/facade_bench.cpp): the stream through the drop-in C++ class, one
     addFiring call per firing."""
@@ -793,7 +873,7 @@ def main():
         latency_mode = mine
 
     # ------------------------------------------------------------------ other operating points (rank 0, single GPU)
-    batch_sweep, flushed, facade, exact_path = None, None, None, None
+    batch_sweep, flushed, facade, exact_path, rows_around = None, None, None, None, None
     if full:
         lg = device_leg(B, 10, 3, False, flush_each_step=True)
         flushed = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 10,
@@ -829,6 +909,10 @@ def main():
             lg["cc"].close()
         except Exception as e:
             exact_path = {"error": str(e)[:200]}
+        try:
+            rows_around = rows_around_the_path(local_rank)
+        except Exception as e:
+            rows_around = {"error": str(e)[:200]}
         # the drop-in C++ class: one addFiring call per firing
         try:
             cfg_c = cfg.to_c()
@@ -896,7 +980,7 @@ def main():
                         "wall_s": t_wall},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
             "kernels_device_timeline_us": trace_table, "batch_sweep": batch_sweep, "latency_mode": latency_mode,
-            "per_gpu_latency": per_gpu_latency, "facade": facade, "exact_path": exact_path,
+            "per_gpu_latency": per_gpu_latency, "facade": facade, "exact_path": exact_path, "rows_around_the_path": rows_around,
             "l2_flush_each_step": flushed,
         }
         print(json.dumps(line))
