@@ -474,23 +474,36 @@ void ContinuousClustering::deliver()
     cc_get_column_events(handle_, events.data(), info.n_events, &n);
     cc_get_clusters(handle_, clusters.data(), info.n_clusters, &n);
     cc_get_cluster_points(handle_, points.data(), info.n_cluster_points, &n);
-    // one read of every column any callback of this push can look at
-    int64_t lo = INT64_MAX, hi = -1;
-    for (const auto& e : events)
-        if (e.to_gcol >= e.from_gcol)
+    // every column a callback of this push can look at is read once: the ranges of the events (ground columns at the front
+    // of the stream, clustered columns up to a rotation behind them) and the spans of the clusters handed out, merged where
+    // they touch -- not their hull: the columns in between were delivered by earlier pushes or are not due yet
+    if (materialise_ || finished_cluster_callback_)
+    {
+        std::vector<std::pair<int64_t, int64_t>> spans;
+        for (const auto& e : events)
+            if (e.to_gcol >= e.from_gcol && e.to_gcol >= 0)
+                spans.emplace_back(e.from_gcol, e.to_gcol);
+        if (finished_cluster_callback_)
+            for (const auto& c : clusters)
+                if (c.num_points > 20 && c.max_gcol >= c.min_gcol)
+                    spans.emplace_back(c.min_gcol, c.max_gcol);
+        std::sort(spans.begin(), spans.end());
+        // a gap shorter than this many columns is cheaper to read than another device round trip (~25 us)
+        const int64_t min_gap = 16;
+        size_t i = 0;
+        while (i < spans.size())
         {
-            lo = std::min(lo, e.from_gcol);
-            hi = std::max(hi, e.to_gcol);
-        }
-    if (finished_cluster_callback_)
-        for (const auto& c : clusters)
-            if (c.num_points > 20)
+            int64_t lo = spans[i].first, hi = spans[i].second;
+            size_t j = i + 1;
+            while (j < spans.size() && spans[j].first <= hi + min_gap)
             {
-                lo = std::min(lo, c.min_gcol);
-                hi = std::max(hi, c.max_gcol);
+                hi = std::max(hi, spans[j].second);
+                j++;
             }
-    if (hi >= lo && hi >= 0 && (materialise_ || finished_cluster_callback_))
-        materialise(lo, hi);
+            materialise(std::max<int64_t>(lo, 0), hi);
+            i = j;
+        }
+    }
     prepacked_.clear();
     if (!materialise_ || finished_cluster_packed_callback_)
         prepack(events.data(), static_cast<int>(events.size()), clusters.data(), static_cast<int>(clusters.size()));
