@@ -572,8 +572,18 @@ CC_DEV void d_scan_lite(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n)
     // (128 bytes apart per thread: one memory sector per thread and access), so the global accesses are done by all
     // threads side by side instead (slot padding keeps the per-thread accesses off the same banks).
     CcFiringSummary* stage = reinterpret_cast<CcFiringSummary*>(smem + 1024);
-    for (int k = t; k < n; k += T)
-        stage[cc_lite_slot(k)] = p.lite_sum[k];
+    for (int k0 = 0; k0 < n; k0 += 8 * T) // the loads of a thread's eight firings are issued together: one round trip
+    {
+        CcFiringSummary v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (k0 + u * T + t < n)
+                v[u] = p.lite_sum[k0 + u * T + t];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (k0 + u * T + t < n)
+                stage[cc_lite_slot(k0 + u * T + t)] = v[u];
+    }
     __syncthreads();
     // every thread keeps its (at most CC_LITE_PER) firings in registers across the three passes
     CcFiringSummary fs[CC_LITE_PER];
