@@ -656,9 +656,9 @@ def main():
     # (scripts/h2d_vs_kernels.py: after ONE warming pass the next pass still runs at ~42 GB/s, from the third on at the
     # link's 53-54 GB/s -- with or without pushes running beside it: three passes.)
     for _ in range(3):
-        scratch = pin_pts.cuda()
+        scratch, scratch_poses = pin_pts.cuda(), pin_poses.cuda()  # (the poses travel with every push too: 96 B per firing)
         torch.cuda.synchronize()
-        del scratch
+        del scratch, scratch_poses
     barrier()
     e2e_marks = []
     t0 = time.perf_counter()

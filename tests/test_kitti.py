@@ -167,3 +167,18 @@ def test_cuda_frame_feeds_the_clustering(cuda_library):
     assert results[0] == results[1]
     assert sum(r[1] for r in results[0]) >= 0
     kr.close()
+
+
+def test_empty_and_tiny_frames(emu_library):
+    """Degenerate inputs: a frame without points gives 2200 firings of empty cells (NaN coordinates, guid of an empty cell);
+    a frame with a single point puts it into exactly one cell. Same on the reference build where it is present."""
+    _, s0, s1, pstamps, poses, mid, seq, frame = make_case("street")
+    for pts in (np.zeros((0, 4), np.float32), np.array([[5.0, -2.0, -1.0, 0.5]], np.float32)):
+        got = product(emu_library, pts, s0, s1, pstamps, poses, mid, seq, frame)
+        f = got["firings"]
+        assert int((~np.isnan(f["x"])).sum()) == pts.shape[0]
+        assert int((f["globally_unique_point_index"] != np.uint64(0xFFFFFFFFFFFFFFFF)).sum()) == pts.shape[0]
+        assert got["info"]["rows_found"] == (1 if pts.shape[0] else 0)
+        assert np.array_equal(f["firing_index"][:, 0], np.arange(W, dtype=np.uint64))
+        if os.path.exists(EVAL_REF) and pts.shape[0]:
+            compare(reference(pts, s0, s1, pstamps, poses, mid, seq, frame), got, "single point vs reference")

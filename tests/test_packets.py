@@ -93,3 +93,21 @@ def test_emulated_decoder_matches_oracle(emu_library, side, n_packets, seed, chu
 @pytest.mark.parametrize("side,n_packets,seed,chunks", [("left", 40, 1, [1, 7, 32]), ("right", 640, 2, [256, 256, 128])])
 def test_cuda_decoder_matches_oracle(cuda_library, side, n_packets, seed, chunks):
     assert run(None, side, n_packets, seed, chunks) > 0
+
+
+def test_no_packets_and_invalid_blocks(emu_library):
+    """Degenerate inputs: an empty call, a call with only the packet that is dropped after a reset, packets whose
+    measurement blocks are all invalid (status 0): no firings, firing index unchanged."""
+    direction, offset = ouster_xyz_lut("left")
+    packets, stamps = make_ouster_packets(6, rows=H, columns_per_frame=W, seed=3, p_invalid=1.0)
+    dec = OusterInput(H, W, direction, offset, max_packets_per_call=8, _library=emu_library)
+    assert dec.decode(packets[:0], stamps[:0])["n_firings"] == 0
+    assert dec.decode(packets[:1], stamps[:1])["n_firings"] == 0  # dropped: first packet after the reset
+    got = dec.decode(packets[1:], stamps[1:])
+    ref_f, _ = oracle_decode(dec.format, direction, offset, packets[1:], stamps[1:], False, 0)
+    assert got["n_firings"] == ref_f.shape[0] == 0 and got["first_firing_index"] == 0
+    good, gstamps = make_ouster_packets(2, rows=H, columns_per_frame=W, seed=4, p_invalid=0.0)
+    got = dec.decode(good, gstamps)
+    assert got["n_firings"] == 32 and got["first_firing_index"] == 0
+    assert dec.decode(good, gstamps)["first_firing_index"] == 32
+    dec.close()
