@@ -1112,9 +1112,15 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
     h->h_flags.assign(ncols, 0);
     CC_CHECK(h, cudaMemcpyAsync(h->h_flags.data(), h->d.col_flag, ncols, cudaMemcpyDeviceToHost, h->stream));
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
+    // A forced finish (cpp:909-919) at column `danger` invalidates the probe's results only for the columns whose walk can
+    // reach a cell of the force-finished component, i.e. the next max_steps_in_row columns (cpp:704-705): their hits on it
+    // are refused by the reference and they found new trees. Those columns go through the exact path; the columns behind
+    // them only meet cells associated after the forced finish and are committed speculatively again (and checked again:
+    // the range's own finish pass aborts at the next dangerous column, which is handled the same way below).
+    const int reach = std::max(0, cfg.max_steps_row);
     std::vector<unsigned char> careful(ncols, 0);
     for (int ci = 0; ci < ncols; ci++)
-        careful[ci] = all_careful || h->h_flags[ci] || (colbase + ci >= danger);
+        careful[ci] = all_careful || h->h_flags[ci] || (colbase + ci >= danger && colbase + ci <= danger + reach);
     int ci = 0;
     while (ci < ncols)
     {
@@ -1137,10 +1143,19 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
             return s;
         if (h->state.abort)
         {
+            const long long d2 = h->state.danger_col;
             CC_RUN(h, k_restore, h->sm_count * 2, 256, 0, h->d);
             CC_RUN(h, k_restore_finish, 1, 1, 0, h->d);
-            for (int c = ci; c <= cj; c++)
-                careful[c] = 1;
+            if (d2 >= colbase + ci && d2 <= colbase + cj)
+            {
+                // the range runs into a (further) dangerous column: exact path from there for the columns its forced finish
+                // can affect, the part before it and the part behind are tried again as ranges
+                for (long long c = d2; c <= d2 + reach && c <= colbase + cj; c++)
+                    careful[static_cast<size_t>(c - colbase)] = 1;
+            }
+            else
+                for (int c = ci; c <= cj; c++)
+                    careful[c] = 1;
             continue;
         }
         ci = cj + 1;

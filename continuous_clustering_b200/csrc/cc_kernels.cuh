@@ -3737,6 +3737,7 @@ CC_DEV void d_restore_finish(const CcGrid g, CcDevPtrs p)
     CcTraceScope cc_trace_scope(p.trace, CC_KID_restore_finish, g.bid);
     p.st->n_ulist = p.st->n_ulist_saved;
     p.st->abort = 0;
+    p.st->danger_col = CC_COL_INF; // (the host has read it; the next attempt on a sub-range reports its own)
     p.st->n_clusters = p.st->sv_n_clusters;
     p.st->n_cluster_points = p.st->sv_n_cluster_points;
 }

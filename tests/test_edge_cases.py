@@ -119,3 +119,43 @@ def test_organic_refusals_cuda(cuda_library, oracle_lib, chunk):
 @pytest.mark.gpu
 def test_set_configuration_mid_stream_cuda(cuda_library, oracle_lib):
     config_mid_stream(None, oracle_lib)
+
+
+# Forced finish (cpp:909-919): a closed wall makes one cluster span a rotation, again and again. Only the columns whose walk can
+# reach the force-finished component go through the exact path; the ranges behind them are committed speculatively again --
+# pushes that contain several dangerous columns, walls at different ranges (different window sizes), walls + boxes.
+WALL_CASES = [
+    ("tiny16", dict(n_rotations=4.0, n_boxes=0, wall_radius=4.0), 64),
+    ("tiny16", dict(n_rotations=4.0, n_boxes=0, wall_radius=8.0), 300),
+    ("tiny16", dict(n_rotations=5.0, n_boxes=0, wall_radius=15.0, moving=False), 700),   # > 2 rotations per push: several forced finishes in one
+    ("tiny16", dict(n_rotations=4.0, n_boxes=60, wall_radius=10.0, extent=9.0, min_box_dist=2.0), 128),
+    ("tiny16", dict(n_rotations=4.0, n_boxes=0, wall_radius=6.0, dropout=0.2), 100),
+]
+
+
+def wall_case(library, oracle_lib, spec, kw, chunk):
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec)
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg, sp.rows)
+    want = parity.record(d, pts, poses)
+    cc = make_cc(library, cfg, sp.rows)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="product", check_tree_fields=True, check_published_tree_fields=True)
+    if kw.get("n_boxes", 150) == 0:  # (boxes in front of the wall can break the ring)
+        assert got["used_exact_path"] > 0, "the scene must send pushes through the split path"
+
+
+@pytest.mark.parametrize("spec,kw,chunk", WALL_CASES)
+def test_forced_finish_scenes_emulation(emu_library, oracle_lib, spec, kw, chunk):
+    wall_case(emu_library, oracle_lib, spec, kw, chunk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,kw,chunk", WALL_CASES + [
+    ("velodyne64", dict(n_rotations=2.6, n_boxes=0, wall_radius=12.0), 1024),
+    ("velodyne64", dict(n_rotations=2.6, n_boxes=100, wall_radius=20.0), 4096),
+    ("os32_left", dict(n_rotations=3.0, n_boxes=0, wall_radius=6.0), 512),
+])
+def test_forced_finish_scenes_cuda(cuda_library, oracle_lib, spec, kw, chunk):
+    wall_case(None, oracle_lib, spec, kw, chunk)
