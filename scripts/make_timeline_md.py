@@ -45,15 +45,17 @@ for title, path, which in (("One 4096-firing push (throughput mode, device-resid
     md.append("")
 lines = push_block(g + f"tlwall_{tag}.txt", "push 10")
 md += ["## The split (exact) path: a 1024-firing push on the closed-wall scene", "", "`" + lines[0].strip() + "`", "",
-       "The speculative whole-push commit aborts (one cluster is about to span a rotation: forced finish, cpp:909-919), the state is rolled back and",
-       "every column goes through `k_fin_all` with `k_careful` at its head + `k_fin_label`, one column after the other. The stamps below are those of",
-       "the LAST column (every launch overwrites its kernel's slot), so the start of kernels launched 1024 times reads as the whole push:", "",
+       "The speculative whole-push commit aborts (one cluster is about to span a rotation: forced finish, cpp:909-919), the state is rolled back; the",
+       "columns before the dangerous one are committed as a range, the dangerous column and the max_steps_in_row columns behind it go through",
+       "`k_fin_all` with `k_careful` at its head + `k_fin_label` one after the other, the rest of the push is committed as a range again (DESIGN 5.2).",
+       "Kernels launched several times overwrite their slot: the stamps below are those of their LAST launch.", "",
        "| kernel / phase | start | end | span | longest CTA | CTAs |", "|---|---|---|---|---|---|"]
 for r in table(lines):
     if r[0] in ("k_careful", ".fin_init", ".fin_agg", ".fin_decide", ".fin_mark", ".fin_copyback", ".fin_columns", "k_fin_label", "k_fin_all", "k_restore", "k_halt"):
         md.append(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[5]} | {r[6]} |")
-md += ["", "Per column: `k_careful` ≈ 31 µs with the trace on (one thread walking the 64 rows of the column one after the other, dependent loads), the five",
-       "list phases ≈ 1.2 µs each, `k_fin_label` ≈ 2 µs: ≈ 43 µs with the trace on, ≈ 22 µs without (bench.py `exact_path`).", ""]
+md += ["", "Per exact column: `k_careful` (one thread walking the 64 rows of the column one after the other, dependent loads; ≈ 12 - 15 µs, ≈ 30 with the trace",
+       "on), the list phases of the single-CTA finish pass ≈ 1.2 µs each, `k_fin_label` ≈ 2 µs: ≈ 22 µs. The push above: 1.19 ms with the trace on, 0.66 ms",
+       "without (bench.py `exact_path`: 1.39 M columns/s over pushes with and without a dangerous column).", ""]
 if os.path.exists(e2e_err):
     pushes = [line for line in open(e2e_err).read().split("\n") if line.startswith("e2e push")]
     if pushes:
