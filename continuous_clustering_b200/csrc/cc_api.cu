@@ -918,6 +918,7 @@ cc_status_t cc_reset(cc_handle_t* h, int num_rows)
     s.clear2_from = -1;
     s.clear2_to = -1;
     s.danger_col = CC_COL_INF;
+    s.forced_col = -1;
     *h->h_state = s;
     CC_CHECK(h, cudaMemcpyAsync(h->d.st, h->h_state, sizeof(s), cudaMemcpyHostToDevice, h->stream));
     std::vector<long long> rm(h->R, -1);
@@ -1131,6 +1132,18 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
             else
                 CC_RUN(h, k_careful, 1, 1, 0, cfg, h->d, ci);
             ci++;
+            if (!all_careful && ci < ncols && !careful[ci])
+            {
+                // end of a run of exact columns: a forced finish inside it (any component, not only the one that was
+                // announced) reaches max_steps_in_row columns further
+                cc_status_t s = fetch_state(h);
+                if (s != CC_OK)
+                    return s;
+                const long long f = h->state.forced_col;
+                if (f >= 0)
+                    for (long long c = std::max<long long>(f + 1, colbase + ci); c <= f + reach && c < colbase + ncols; c++)
+                        careful[static_cast<size_t>(c - colbase)] = 1;
+            }
             continue;
         }
         int cj = ci;

@@ -1737,6 +1737,7 @@ CC_DEV void d_insert_scan(const CcGrid g, CcDevCfg cfg, CcDevPtrs p, int n_firin
         st->n_probe = 0;
         st->n_heavy = 0;
         st->danger_col = CC_COL_INF;
+        st->forced_col = -1;
         st->abort = 0;
         st->n_clusters = 0;
         st->n_cluster_points = 0;
@@ -4262,6 +4263,8 @@ CC_DEV void d_fin_decide(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p
             const bool exceeds = (maxend - mincol) >= cfg.N;    // cpp:909-919
             if (!unfinished || exceeds)
                 finish_col = c1;
+            if (unfinished && exceeds) // a forced finish: associations of the next max_steps_in_row columns may be refused
+                atomicMax(&st->forced_col, c1);
         }
         if (finish_col != CC_COL_INF)
         {

@@ -91,6 +91,7 @@ struct CcDevState // persistent scalars of the stream, resident in HBM; copied t
     int n_heavy;       // of those, the points left to the warp-cooperative walk
     int n_flagged;     // columns with an association that the reference might have refused (cpp:654-659, 688-690)
     long long danger_col; // first column at which a cluster could be force-finished (cpp:909-919), CC_COL_INF if none
+    long long forced_col; // last column whose exact finish pass force-finished a component in this push, -1 if none
     int abort;            // speculative commit must be rolled back
     int n_clusters, n_cluster_points;
     long long clear_from, clear_to;   // columns retired by this push [from, to)
