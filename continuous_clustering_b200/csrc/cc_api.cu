@@ -1109,7 +1109,7 @@ static cc_status_t slow_path(cc_handle* h, const CcDevCfg& cfg)
     const int ncols = h->state.ncols;
     const long long colbase = h->state.colbase;
     const long long danger = h->state.danger_col;
-    const bool all_careful = cfg.nth != 1;
+    const bool all_careful = false; // (passes every n-th column are handled by the speculative commit too: cc_pass_at_or_after)
     h->h_flags.assign(ncols, 0);
     CC_CHECK(h, cudaMemcpyAsync(h->h_flags.data(), h->d.col_flag, ncols, cudaMemcpyDeviceToHost, h->stream));
     CC_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -1247,7 +1247,7 @@ static cc_status_t launch_push(cc_handle* h, cc_handle::Slot& sl)
     sl.launches0 = h->launches;
     h->n_timed = 0;
     sl.has_tf = sl.cfg_has_tf;
-    sl.spec = cfg.nth == 1;
+    sl.spec = true; // whole-push speculative commit (finish passes at every n-th column included)
     sl.fused = sl.want_fused; // decided when the push was submitted (its inputs were routed accordingly)
     if (sl.fused)
     {

@@ -338,6 +338,16 @@ CC_DEV T cc_block_exclusive_scan(T* sm, T v, T identity, Op op)
     return excl;
 }
 
+// finish passes run at the columns that are multiples of cluster_point_trees_every_nth_column (cpp:841)
+CC_DEV long long cc_pass_at_or_after(long long c, int nth)
+{
+    return nth <= 1 ? c : ((c + nth - 1) / nth) * nth;
+}
+CC_DEV long long cc_pass_at_or_before(long long c, int nth)
+{
+    return nth <= 1 ? c : c - (c % nth);
+}
+
 CC_DEV int cc_local_col(long long g, int ringcols)
 {
     return static_cast<int>(g % ringcols);
@@ -4232,11 +4242,12 @@ CC_DEV void d_fin_decide(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p
                 continue;
             }
             const long long lastcol = maxend - 1;
-            const long long s = lastcol > c0 ? lastcol : c0;
+            const long long s = cc_pass_at_or_after(lastcol > c0 ? lastcol : c0, cfg.nth);
+            const long long c1p = cc_pass_at_or_before(c1, cfg.nth); // last pass column of the range
             // first pass column c >= s with runmax(c) >= F
-            if (rmx[c1 - colbase] >= F)
+            if (s <= c1p && rmx[c1p - colbase] >= F)
             {
-                long long lo = s, hi = c1;
+                long long lo = s, hi = c1p;
                 while (lo < hi)
                 {
                     const long long mid = (lo + hi) >> 1;
@@ -4245,6 +4256,7 @@ CC_DEV void d_fin_decide(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& p
                     else
                         lo = mid + 1;
                 }
+                lo = cc_pass_at_or_after(lo, cfg.nth); // (<= c1p: the running maximum is monotone)
                 if (!(p.col_minaz[lo - colbase] >= F))
                 {
                     // the running maximum was reached before the component was complete while this column's own
@@ -4405,10 +4417,11 @@ CC_DEV void d_fin_decide_mark(const CcGrid g, const CcDevCfg& cfg, const CcDevPt
                 }
                 bad = true;
             }
-            else if (rm_last >= F)
+            else if (cc_pass_at_or_after((maxend - 1) > c0 ? (maxend - 1) : c0, cfg.nth) <= cc_pass_at_or_before(c1, cfg.nth) &&
+                     rmx[cc_pass_at_or_before(c1, cfg.nth) - colbase] >= F)
             {
                 const long long lastcol = maxend - 1;
-                long long lo = lastcol > c0 ? lastcol : c0, hi = c1;
+                long long lo = cc_pass_at_or_after(lastcol > c0 ? lastcol : c0, cfg.nth), hi = cc_pass_at_or_before(c1, cfg.nth);
                 while (lo < hi) // first pass column c >= lo with runmax(c) >= F
                 {
                     const long long mid = (lo + hi) >> 1;
@@ -4417,6 +4430,7 @@ CC_DEV void d_fin_decide_mark(const CcGrid g, const CcDevCfg& cfg, const CcDevPt
                     else
                         lo = mid + 1;
                 }
+                lo = cc_pass_at_or_after(lo, cfg.nth); // (still inside the range: the running maximum is monotone)
                 if (!(p.col_minaz[lo - colbase] >= F))
                 {
                     // the running maximum was reached before the component was complete while this column's own minimum
@@ -4608,12 +4622,21 @@ CC_DEV void d_fin_columns(const CcGrid g, const CcDevCfg& cfg, const CcDevPtrs& 
     };
     const long long c_first = c0 + t + (sliced ? static_cast<long long>(slice) * T : 0);
     const long long c_step = static_cast<long long>(sliced ? nslices : 1) * T;
+    // with passes only every n-th column (cpp:841) a column between two passes keeps what the pass before it left
+    const long long fu_before = st->seg_first_unpub_old; // first unpublished column when this pass started (d_fin_init)
     for (long long c = c_first; c <= c1; c += c_step)
-        p.col_first_unpub[c - colbase] = first_unpublished_after(c);
-    // the bookkeeping below needs the answer for the last column: thread 0 of slice 0 computes it itself (another CTA may own it)
+    {
+        const long long cp = cc_pass_at_or_before(c, cfg.nth);
+        p.col_first_unpub[c - colbase] = cp >= c0 ? first_unpublished_after(cp) : fu_before;
+    }
+    // the bookkeeping below needs the answer for the last pass column: thread 0 of slice 0 computes it itself (another CTA
+    // may own it)
     long long fu_last = 0;
     if (t == 0 && slice == 0)
-        fu_last = c1 >= c0 ? first_unpublished_after(c1) : p.col_first_unpub[c1 - colbase];
+    {
+        const long long cp = cc_pass_at_or_before(c1, cfg.nth);
+        fu_last = c1 >= c0 ? (cp >= c0 ? first_unpublished_after(cp) : fu_before) : p.col_first_unpub[c1 - colbase];
+    }
     __syncthreads();
     if (t == 0 && slice == 0)
     {

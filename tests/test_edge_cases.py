@@ -159,3 +159,41 @@ def test_forced_finish_scenes_emulation(emu_library, oracle_lib, spec, kw, chunk
 ])
 def test_forced_finish_scenes_cuda(cuda_library, oracle_lib, spec, kw, chunk):
     wall_case(None, oracle_lib, spec, kw, chunk)
+
+
+# cluster_point_trees_every_nth_column > 1 (cpp:841): finish passes only at every n-th column. The speculative whole-push
+# commit handles it (finish columns rounded up to pass columns, columns between two passes keep the first unpublished column
+# of the pass before them); until round 2 such configurations went through the exact path column by column.
+NTH_CASES = [
+    ("tiny16", dict(n_rotations=3.0), 2, 64),
+    ("tiny16", dict(n_rotations=3.0, moving=True, dropout=0.1), 5, 37),
+    ("tiny16", dict(n_rotations=3.0), 16, 1),                                   # one firing per push (fused kernel)
+    ("tiny16", dict(n_rotations=3.2, n_boxes=0, wall_radius=8.0), 3, 300),      # with forced finishes
+    ("tiny16", dict(n_rotations=3.0, az_jitter=0.4, az_step_scale=0.95), 100, 700),
+]
+
+
+def nth_case(library, oracle_lib, spec, kw, nth, chunk):
+    pts, poses, sp = synth.make_stream(spec, **kw)
+    cfg = drvlib.stream_config(spec, cluster_point_trees_every_nth_column=nth)
+    want = parity.record(_fresh(oracle_lib, cfg, sp.rows), pts, poses)
+    cc = make_cc(library, cfg, sp.rows)
+    got = recorder.record(cc, pts, poses, chunk)
+    parity.compare(want, got, name_a="oracle", name_b="product", check_tree_fields=True, check_published_tree_fields=True)
+    if "wall_radius" not in kw:
+        assert got["used_exact_path"] == 0, "every-nth-column passes must not need the exact path on an ordinary scene"
+
+
+@pytest.mark.parametrize("spec,kw,nth,chunk", NTH_CASES)
+def test_every_nth_column_emulation(emu_library, oracle_lib, spec, kw, nth, chunk):
+    nth_case(emu_library, oracle_lib, spec, kw, nth, chunk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,kw,nth,chunk", NTH_CASES + [
+    ("velodyne64", dict(n_rotations=2.3, moving=True, dropout=0.02), 4, 1024),
+    ("velodyne64", dict(n_rotations=2.3), 7, 4096),
+    ("os32_left", dict(n_rotations=2.5, moving=True), 3, 256),
+])
+def test_every_nth_column_cuda(cuda_library, oracle_lib, spec, kw, nth, chunk):
+    nth_case(None, oracle_lib, spec, kw, nth, chunk)
