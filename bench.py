@@ -873,7 +873,7 @@ def main():
         latency_mode = mine
 
     # ------------------------------------------------------------------ other operating points (rank 0, single GPU)
-    batch_sweep, flushed, facade, exact_path, rows_around = None, None, None, None, None
+    batch_sweep, flushed, facade, exact_path, rows_around, irregular = None, None, None, None, None, None
     if full:
         lg = device_leg(B, 10, 3, False, flush_each_step=True)
         flushed = {"columns_per_s": lg["value"], "ms_per_step": 1e3 * lg["elapsed"] / 10,
@@ -909,6 +909,28 @@ def main():
             lg["cc"].close()
         except Exception as e:
             exact_path = {"error": str(e)[:200]}
+        # a sensor that does not deliver exactly one firing per range-image column (5 % more firings per rotation than
+        # columns: two firings share a column every ~20 firings, the collision rule cpp:188-208 fires): the insertion leaves
+        # the grid-wide regular path at the first such firing of a push and the rest goes through the single-CTA scan
+        try:
+            from continuous_clustering_b200 import synth
+
+            class IrregularStream:
+                pass
+
+            irs = IrregularStream()
+            ib = 2048
+            ip, iq, irs.sp = synth.make_stream(spec_name, n_firings=6 * ib, seed=5, az_step_scale=0.95)
+            irs.take = lambda a, n: (ip[a:a + n].copy(), iq[a:a + n].copy())
+            lg = device_leg(ib, 3, 3, False, src=irs)
+            irregular = {"workload": "the same scene, sensor delivering 5 % more firings per rotation than the range image has columns "
+                                     "(az_step_scale 0.95): column collisions every ~20 firings",
+                         "batch_firings": ib, "steps": 3, "columns_per_s": lg["value"], "per_push_device_ms_p50": float(np.median(lg["dev_ms"])),
+                         "exact_path_pushes": lg["exact"],
+                         "note": "after the first irregular firing of a push the insertion runs in one CTA (k_insert_scan): the known slow case of the path"}
+            lg["cc"].close()
+        except Exception as e:
+            irregular = {"error": str(e)[:200]}
         try:
             rows_around = rows_around_the_path(local_rank)
         except Exception as e:
@@ -980,7 +1002,7 @@ def main():
                         "wall_s": t_wall},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
             "kernels_device_timeline_us": trace_table, "batch_sweep": batch_sweep, "latency_mode": latency_mode,
-            "per_gpu_latency": per_gpu_latency, "facade": facade, "exact_path": exact_path, "rows_around_the_path": rows_around,
+            "per_gpu_latency": per_gpu_latency, "facade": facade, "exact_path": exact_path, "irregular_stream": irregular, "rows_around_the_path": rows_around,
             "l2_flush_each_step": flushed,
         }
         print(json.dumps(line))
