@@ -324,7 +324,7 @@ def ouster_xyz_lut(side: str = "left", columns_per_frame: int = 1024, origin_to_
 
 
 def make_ouster_packets(n_packets: int, rows: int = 32, columns_per_frame: int = 1024, seed: int = 5, first_measurement_id: int = 0,
-                        p_invalid: float = 0.03, p_no_return: float = 0.2):
+                        p_invalid: float = 0.03, p_no_return: float = 0.2, ranges_mm=None):
     """LEGACY-profile lidar packets (16 measurement blocks of 16 + 12 * rows + 4 bytes) with random ranges (20 bits, a
     share of zeros = no return), signal photons 0..3000 and a few invalid blocks; measurement ids run through the frame.
     Returns (packets [n_packets, packet_size] uint8, receive_stamps [n_packets] uint64)."""
@@ -338,8 +338,11 @@ def make_ouster_packets(n_packets: int, rows: int = 32, columns_per_frame: int =
     hdr[:, 10:12] = ((first_measurement_id + np.arange(n_packets * 16)) // columns_per_frame).astype("<u2").view(np.uint8).reshape(-1, 2)
     hdr[:, 12:16] = (m_id * (90112 // columns_per_frame)).astype("<u4").view(np.uint8).reshape(-1, 4)
     px = packets[:, :, 16:16 + 12 * rows].reshape(-1, rows, 12)
-    rng_mm = rng.randint(300, 120000, size=(n_packets * 16, rows)).astype("<u4")
-    rng_mm[rng.uniform(size=rng_mm.shape) < p_no_return] = 0
+    if ranges_mm is not None:  # a coherent scene: [n_packets * 16, rows] millimetres, 0 = no return
+        rng_mm = np.ascontiguousarray(ranges_mm, dtype="<u4").reshape(n_packets * 16, rows).copy()
+    else:
+        rng_mm = rng.randint(300, 120000, size=(n_packets * 16, rows)).astype("<u4")
+        rng_mm[rng.uniform(size=rng_mm.shape) < p_no_return] = 0
     flags = rng.randint(0, 16, size=rng_mm.shape).astype("<u4") << 28  # the top bits of the range word are not range
     px[:, :, 0:4] = (rng_mm | flags).view(np.uint8).reshape(-1, rows, 4)
     px[:, :, 4:6] = rng.randint(0, 65536, size=rng_mm.shape).astype("<u2").view(np.uint8).reshape(-1, rows, 2)

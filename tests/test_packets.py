@@ -111,3 +111,86 @@ def test_no_packets_and_invalid_blocks(emu_library):
     assert got["n_firings"] == 32 and got["first_firing_index"] == 0
     assert dec.decode(good, gstamps)["first_firing_index"] == 32
     dec.close()
+
+
+# ---- packets -> firings -> hot path, firings never leaving the device --------------------------------------------------
+def scene_packets(n_packets, seed):
+    """LEGACY packets whose ranges come from the synthetic OS-32 scene (the ranges of stream firing k go into measurement block
+    k): decoded through the sensor's lookup table they are a coherent street scene again."""
+    from continuous_clustering_b200 import synth
+
+    pts, fposes, sp = synth.make_stream("os32_left", n_firings=n_packets * 16, seed=seed, start_firing=64)
+    scene_packets.pose = fposes[0].copy()  # static sensor: odom_from_sensor = the mount roll, the same for every firing
+    dist = np.sqrt(pts["x"].astype(np.float64) ** 2 + pts["y"].astype(np.float64) ** 2 + pts["z"].astype(np.float64) ** 2)
+    mm = np.where(np.isnan(dist), 0, np.round(dist * 1000.0)).astype(np.uint32)
+    # (encoder angle 2 pi (1 - col / W) and the lidar-to-sensor transform: the azimuth decreases with the measurement id, like
+    # the stream's: a clockwise sensor)
+    return make_ouster_packets(n_packets, rows=H, columns_per_frame=W, seed=seed, first_measurement_id=64, p_invalid=0.02, ranges_mm=mm)
+
+
+def chain(library, oracle_lib, n_packets=160, per_call=32):
+    import parity
+    import recorder
+    from continuous_clustering_b200 import ContinuousClustering
+    from oracle import drvlib
+
+    direction, offset = ouster_xyz_lut("left")
+    packets, stamps = scene_packets(n_packets, 9)
+    cfg = drvlib.stream_config("os32_left")
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float64)
+    mount = scene_packets.pose
+    dec = OusterInput(H, W, direction, offset, max_packets_per_call=per_call, _library=library)
+    # oracle chain: restated decoder -> host RawPoints -> restated clustering
+    ref_f, _ = oracle_decode(dec.format, direction, offset, packets, stamps, True, 0)
+    d = drvlib.Driver(oracle_lib)
+    d.configure(cfg, H)
+    want = parity.record(d, np.ascontiguousarray(ref_f), np.tile(mount, (ref_f.shape[0], 1)))
+    assert not want["reset_required"] and len(want["clusters"]) > 5 and int((want["ground_cells"]["ground_point_label"] == 54).sum()) > 5000
+    # product chain: device decoder -> firings resident in device memory -> hot path (cc_push_firings_device)
+    cc = ContinuousClustering(max_firings_per_push=per_call * 16, _library=library)
+    cc.setConfiguration(cfg)
+    cc.reset(H)
+    cc.setTransformRobotFrameFromSensorFrame(ident)
+    poses = np.tile(mount, (per_call * 16, 1))
+    if library is None:  # the CUDA library: the poses have to be in device memory too
+        import torch
+
+        keep = torch.from_numpy(poses).cuda()
+        d_poses = keep.data_ptr()
+    else:  # the emulation's "device" memory is host memory
+        d_poses = poses.ctypes.data
+
+    class DecodeAndPush:
+        """What tests/recorder.py drives instead of the clustering object: every addFirings call decodes the next packets
+        and pushes the firings the decoder left on the device."""
+
+        def __init__(self):
+            self.call, self.firings = 0, 0
+
+        def __getattr__(self, name):
+            return getattr(cc, name)
+
+        def addFirings(self, _points, _poses):
+            a = self.call * per_call
+            self.call += 1
+            out = dec.decode(packets[a:a + per_call], stamps[a:a + per_call])
+            self.firings += out["n_firings"]
+            return cc.addFiringsDevice(out["d_firings"], d_poses, out["n_firings"], H)
+
+    feeder = DecodeAndPush()
+    n_calls = (n_packets + per_call - 1) // per_call
+    got = recorder.record(feeder, np.zeros((n_calls, H), dtype=RAW_POINT_DTYPE), np.zeros((n_calls, 12)), 1)
+    assert feeder.firings == ref_f.shape[0]
+    parity.compare(want, got, name_a="oracle chain", name_b="product chain")
+    dec.close()
+    cc.close()
+    return feeder.firings
+
+
+def test_packets_feed_the_hot_path_emulation(emu_library, oracle_lib):
+    assert chain(emu_library, oracle_lib) > 2000
+
+
+@pytest.mark.gpu
+def test_packets_feed_the_hot_path_cuda(cuda_library, oracle_lib):
+    assert chain(None, oracle_lib) > 2000
