@@ -197,3 +197,27 @@ def test_every_nth_column_emulation(emu_library, oracle_lib, spec, kw, nth, chun
 ])
 def test_every_nth_column_cuda(cuda_library, oracle_lib, spec, kw, nth, chunk):
     nth_case(None, oracle_lib, spec, kw, nth, chunk)
+
+
+def test_two_ring_components_emulation(emu_library, oracle_lib):
+    """Two concentric walls (a low inner one, a tall outer one broken by boxes): several ring-spanning components whose forced
+    finishes fall at unrelated columns -- the retry at the next dangerous column and the extension of a run of exact columns
+    (forced_col). A sample of tests/tools/fuzz_scenes.py two_walls."""
+    exact_pushes = 0
+    for seed, r1, h1, r2, nb, chunk in ((1, 3.0, 0.5, 9.0, 3, 128), (2, 5.0, 0.9, 14.0, 8, 400), (3, 3.0, 0.9, 9.0, 8, 40)):
+        a, poses, sp = synth.make_stream("tiny16", n_rotations=4.2, seed=seed, n_boxes=0, wall_radius=r1, wall_height=h1)
+        b, _, _ = synth.make_stream("tiny16", n_rotations=4.2, seed=seed + 10, n_boxes=nb, wall_radius=r2, wall_height=3.0, extent=r2 * 0.8,
+                                    min_box_dist=r1 + 1.0, box_height_range=(2.0, 3.0))
+        da = np.sqrt(a["x"] ** 2 + a["y"] ** 2 + a["z"] ** 2)
+        db = np.sqrt(b["x"] ** 2 + b["y"] ** 2 + b["z"] ** 2)
+        use_a = (~np.isnan(da)) & (np.isnan(db) | (da < db))
+        pts = b.copy()
+        for f in ("x", "y", "z"):
+            pts[f] = np.where(use_a, a[f], b[f])
+        cfg = drvlib.stream_config("tiny16")
+        want = parity.record(_fresh(oracle_lib, cfg, sp.rows), pts, poses)
+        cc = make_cc(emu_library, cfg, sp.rows)
+        got = recorder.record(cc, pts, poses, chunk)
+        parity.compare(want, got, name_a="oracle", name_b="product", check_tree_fields=True, check_published_tree_fields=True)
+        exact_pushes += got["used_exact_path"]
+    assert exact_pushes > 0
