@@ -204,7 +204,7 @@ def test_two_ring_components_emulation(emu_library, oracle_lib):
     finishes fall at unrelated columns -- the retry at the next dangerous column and the extension of a run of exact columns
     (forced_col). A sample of tests/tools/fuzz_scenes.py two_walls."""
     exact_pushes = 0
-    for seed, r1, h1, r2, nb, chunk in ((1, 3.0, 0.5, 9.0, 3, 128), (2, 5.0, 0.9, 14.0, 8, 400), (3, 3.0, 0.9, 9.0, 8, 40)):
+    for seed, r1, h1, r2, nb, chunk in ((1, 5.0, 0.5, 9.0, 3, 40), (1, 5.0, 0.5, 9.0, 8, 128), (2, 5.0, 0.9, 14.0, 8, 400)):
         a, poses, sp = synth.make_stream("tiny16", n_rotations=4.2, seed=seed, n_boxes=0, wall_radius=r1, wall_height=h1)
         b, _, _ = synth.make_stream("tiny16", n_rotations=4.2, seed=seed + 10, n_boxes=nb, wall_radius=r2, wall_height=3.0, extent=r2 * 0.8,
                                     min_box_dist=r1 + 1.0, box_height_range=(2.0, 3.0))
